@@ -1,0 +1,332 @@
+#!/usr/bin/env python
+"""bench.py — assembly hot-path benchmark (contract: task brief ④, BASELINE.json metric).
+
+  python bench.py --gpus N --steps K --warmup W            this repo's CUDA path
+  python bench.py --impl reference --steps K --warmup W     CPU reference arm (oracle port)
+
+A "step" is one fused energy + gradient + Hessian assembly (pfa_grad_hess) of NeoHookean
+P2 tets on the synthetic Kuhn cube with a random displacement (BASELINE.json configs[2]:
+n=69 cells/side, 1 971 054 elements, 8 056 857 dofs, 685 941 705 nnz). Prints ONE JSON line.
+
+  value      elements/s, whole job, x / E / grad / values[] resident in HBM
+  e2e        the same metric through the C-ABI call with HOST (pinned) buffers: H2D of x and
+             D2H of energy, gradient and the CSC values[] inside the timed region
+  roofline   achieved = B_alg(=SURVEY.md §8d bytes/element) * elements / assembly-kernel time
+             (CUDA events on the launching stream, live in this run) vs measured HBM copy peak
+  cpu_baseline  the CPU oracle (a port of the reference algorithm, NOT PolyFEM itself) timed
+             on this box's host cores on a bounded sample of the same workload
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "elements/s (NeoHookean P2 grad+Hessian assembly)"
+UNIT = "elements/s"
+E_MOD, NU = 1e5, 0.3
+
+
+def b_alg_bytes_per_element(n_loc, ndof, nnz, n_el):
+    """compulsory traffic per element (inputs once, outputs once)."""
+    return 4 * n_loc + 80 + 16 + 8 * ndof / n_el + 8 * ndof / n_el + 8 * nnz / n_el
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi sampling during the timed region (B200_PROFILING.md clocks line)."""
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+                 "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+                 "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.gpu), "-lms", "100"],
+                                         stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        try:
+            rows = [r.split(",") for r in open(self.path).read().strip().splitlines() if r.strip()]
+            sm = [float(r[1]) for r in rows if len(r) >= 9]
+            if sm:
+                out["sm_mhz"] = float(np.median(sm))
+                out["sm_max_mhz"] = float(rows[0][2])
+                names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+                seen = set()
+                for r in rows:
+                    for k, nm in enumerate(names):
+                        if "Active" in r[5 + k] and "Not" not in r[5 + k]:
+                            seen.add(nm)
+                out["reasons"] = sorted(seen)
+                out["samples"] = len(sm)
+        except Exception:
+            pass
+        finally:
+            try:
+                os.unlink(self.path)
+            except Exception:
+                pass
+        return out
+
+
+def build_workload(n, p, rank=0, world=1):
+    """Mesh + tables; for world > 1 the elements are split into `world` contiguous blocks
+    (x-slabs of the cube) and this rank keeps its block, renumbered locally."""
+    from polyfem_b200 import mesh as M, tables
+    mesh = M.kuhn_cube(n, p)
+    x = M.random_displacement(mesh)
+    t = tables.reference_tables(p)
+    return mesh, x, t
+
+
+def cpu_baseline_run(n_sample, p, steps, warmup, threads):
+    """Times the oracle (reference-algorithm port) on a bounded sample of the workload:
+    steady-state energy + gradient + Hessian per step (pattern build = first call, untimed)."""
+    from oracle import pyoracle
+    from polyfem_b200 import mesh as M
+    mesh = M.kuhn_cube(n_sample, p)
+    x = M.random_displacement(mesh)
+    prob = pyoracle.problem_from_mesh(mesh, "NeoHookean", E=E_MOD, nu=NU, n_threads=threads, use_cache=True)
+    t0 = time.perf_counter()
+    prob.assemble_hessian(x)  # first call: triplets + pattern + slot map (one-off, like pfa_create)
+    first = time.perf_counter() - t0
+    for _ in range(warmup):
+        prob.assemble_energy(x)
+        prob.assemble_gradient(x)
+        prob.assemble_hessian(x)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        prob.assemble_energy(x)
+        prob.assemble_gradient(x)
+        prob.assemble_hessian(x)
+    dt = (time.perf_counter() - t0) / max(steps, 1)
+    return {"elements": mesh.n_elements, "seconds_per_step": dt, "first_call_seconds": first,
+            "value": mesh.n_elements / dt}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    threads = os.cpu_count() or 1
+    steps = max(args.steps, 1)
+    r = cpu_baseline_run(args.cpu_sample_n, args.p, steps, min(args.warmup, 1), threads)
+    sample = (f"NeoHookean P{args.p} Kuhn cube n={args.cpu_sample_n} ({r['elements']} elements), steady-state "
+              f"energy+gradient+Hessian per step; first call (pattern build) {r['first_call_seconds']:.2f}s excluded")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
+        "steps": steps, "warmup": min(args.warmup, 1), "ms_per_step": r["seconds_per_step"] * 1e3,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"NeoHookean P{args.p} tets, Kuhn cube n={args.n} (bounded CPU sample n={args.cpu_sample_n})",
+                   "material": "E=1e5 nu=0.3", "displacement": "0.05*h*U(-1,1) seed 42"},
+        "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+        "note": "CPU restatement of the reference algorithm (oracle/), not the PolyFEM binary: Eigen/TBB are not available offline",
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--n", type=int, default=69, help="cells per side (69 -> 1 971 054 tets, BASELINE cfg 3)")
+    ap.add_argument("--p", type=int, default=2)
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--cpu-sample-n", type=int, default=12)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    from polyfem_b200 import capi
+    from polyfem_b200 import dist as pdist
+    from polyfem_b200.mesh import lame_from_E_nu
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the assembly path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    mesh, x_host, t = build_workload(args.n, args.p)
+    lam, mu = lame_from_E_nu(E_MOD, NU)
+    part = pdist.partition_elements(mesh, rank, world)
+    h = capi.Handle("NeoHookean", part.conn, part.n_bases, t["weights"], t["grad"], vertices=part.vertices,
+                    lam=lam, mu=mu, device=local_rank, n_ghost_elements=part.n_ghost_elements)
+    h.set_stream(torch.cuda.current_stream().cuda_stream)
+    exch = pdist.InterfaceExchange(h, part, rank, world, dev) if world > 1 else None
+
+    x_loc = np.ascontiguousarray(x_host.reshape(-1, 3)[part.l2g].reshape(-1))
+    xd = torch.from_numpy(x_loc).to(dev)
+    e_d = torch.zeros(1, dtype=torch.float64, device=dev)
+    g_d = torch.zeros(h.ndof, dtype=torch.float64, device=dev)
+    v_d = torch.zeros(h.nnz, dtype=torch.float64, device=dev)
+
+    def step():
+        h.grad_hess_raw(xd, e_d, g_d, v_d)
+        if exch is not None:
+            exch.reduce(e_d, g_d, v_d)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    h.profile_enable(True)
+    launches0 = h.launch_count() + (exch.launches if exch else 0)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for _ in range(args.steps):
+        step()
+    ev1.record()
+    barrier()
+    ms_total = ev0.elapsed_time(ev1)
+    clocks = sampler.stop() if rank == 0 else None
+    recs = h.profile_read()
+    h.profile_enable(False)
+    launches = h.launch_count() + (exch.launches if exch else 0) - launches0
+    if world > 1:
+        tt = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms_total = float(tt.item())
+    ms_step = ms_total / args.steps
+    n_el_total = mesh.n_elements
+    value = n_el_total / (ms_step * 1e-3)
+
+    # dominant kernel: average launch duration from the library's own CUDA events (same stream)
+    kern = [ms for (name, ms) in recs if "assemble" in name]
+    fill = [ms for (name, ms) in recs if "zero_fill" in name]
+    kern_ms = float(np.mean(kern)) if kern else float("nan")
+    peak, peak_src = measured_peaks()
+    b_alg = b_alg_bytes_per_element(h.n_loc, h.ndof, h.nnz, h.n_elements)
+    achieved = b_alg * h.n_elements / (kern_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": None, "kernel": "assemble_generic_kernel", "kernel_ms": kern_ms,
+                "zero_fill_ms": float(np.mean(fill)) if fill else 0.0,
+                "algorithmic_bytes_per_element": b_alg, "peak_source": peak_src + " (of measured)"}
+
+    # e2e through the C ABI with pinned HOST buffers (H2D x, D2H E + grad + values every step)
+    e2e = None
+    if world == 1:
+        xh = torch.from_numpy(x_loc).pin_memory()
+        eh = torch.zeros(1, dtype=torch.float64).pin_memory()
+        gh = torch.zeros(h.ndof, dtype=torch.float64).pin_memory()
+        vh = torch.zeros(h.nnz, dtype=torch.float64).pin_memory()
+        h.grad_hess_raw(xh.numpy(), eh.numpy(), gh.numpy(), vh.numpy())
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            h.grad_hess_raw(xh.numpy(), eh.numpy(), gh.numpy(), vh.numpy())
+        torch.cuda.synchronize()
+        dt = (time.perf_counter() - t0) / args.e2e_steps
+        e2e = {"value": n_el_total / dt, "unit": UNIT, "h2d_bytes_per_step": int(8 * h.ndof),
+               "d2h_bytes_per_step": int(8 * (1 + h.ndof + h.nnz)), "ms_per_step": dt * 1e3, "steps": args.e2e_steps,
+               "buffers": "pinned host"}
+        assert abs(float(eh[0]) - float(e_d.item())) <= 1e-9 * abs(float(e_d.item()))
+    else:
+        # multi-GPU: host buffers per rank, same call + exchange
+        xh = torch.from_numpy(x_loc).pin_memory()
+        gh = torch.zeros(h.ndof, dtype=torch.float64).pin_memory()
+        vh = torch.zeros(h.nnz, dtype=torch.float64).pin_memory()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            xd.copy_(xh, non_blocking=True)
+            step()
+            gh.copy_(g_d, non_blocking=True)
+            vh.copy_(v_d, non_blocking=True)
+            _ = float(e_d.item())
+        barrier()
+        dt = (time.perf_counter() - t0) / args.e2e_steps
+        tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e2e = {"value": n_el_total / float(tt.item()), "unit": UNIT, "h2d_bytes_per_step": int(8 * h.ndof),
+               "d2h_bytes_per_step": int(8 * (1 + h.ndof + h.nnz)), "ms_per_step": float(tt.item()) * 1e3,
+               "steps": args.e2e_steps, "buffers": "pinned host, per rank"}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        r = cpu_baseline_run(args.cpu_sample_n, args.p, 2, 1, threads)
+        cpu = {"value": r["value"], "unit": UNIT, "cores": threads, "kind": "port",
+               "sample": f"NeoHookean P{args.p} Kuhn cube n={args.cpu_sample_n} ({r['elements']} elements), 2 steady-state "
+                         f"steps of energy+gradient+Hessian, basis cache on; first call {r['first_call_seconds']:.2f}s excluded"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"NeoHookean P{args.p} tets, Kuhn cube n={args.n}: {mesh.n_elements} elements, "
+                                   f"{mesh.n_bases * 3} dofs, fused energy+gradient+Hessian (pfa_grad_hess)",
+                       "material": "E=1e5 nu=0.3", "displacement": "0.05*h*U(-1,1) seed 42",
+                       "l2": "outputs (values[] %.2f GB per GPU) exceed the 126 MB L2, no flush needed" % (8 * h.nnz / 1e9),
+                       "parallelism": f"element partition x{world}" if world > 1 else "single GPU",
+                       "nnz": int(h.nnz) if world == 1 else None},
+            "nnz_per_s": (h.nnz / (ms_step * 1e-3)) if world == 1 else None,
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+            "setup_seconds": h.setup_seconds(),
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

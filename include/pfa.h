@@ -1,0 +1,162 @@
+/* pfa.h — C ABI of the B200 assembly path ("PolyFEM assembler", libpfa.so).
+ *
+ * This is the drop-in boundary for PolyFEM's per-element energy / gradient / Hessian
+ * assembly. Each entry point replaces one virtual of
+ * polyfem::assembler::Assembler (reference: src/polyfem/assembler/Assembler.hpp:68-125)
+ * as ElasticForm calls it (src/polyfem/solver/forms/ElasticForm.cpp:287-328,411-418);
+ * the C++ shim that overrides those virtuals and forwards here is host/assembler_shim.hpp,
+ * the binding a PolyFEM maintainer adds is shown in INTEGRATION.md.
+ *
+ * Conventions
+ *  - plain C, no exceptions cross the boundary: every call returns PFA_OK (0) or a negative
+ *    pfa_status; pfa_last_error() gives the message (the shim turns it into
+ *    log_and_throw_error, utils/Logger.hpp:42-49). NaN/Inf results are NOT errors
+ *    (ElasticForm.cpp:388-396 relies on NaN reaching the caller).
+ *  - dofs are node-major: x[node*size + d] (NeoHookeanElasticity.cpp:352); size = 3 for
+ *    NeoHookean / LinearElasticity, 1 for Laplacian.
+ *  - matrices are returned as the values[] array of the CSC pattern reported by
+ *    pfa_pattern(): column-major, int32 indices, inner indices ascending, all structural
+ *    entries kept (explicit zeros included) — byte-identical to what
+ *    SparseMatrixCache::get_matrix produces (utils/MatrixCache.cpp:134-228), so the shim can
+ *    wrap it in Eigen::Map<const StiffnessMatrix>.
+ *  - every `const double *x` / output pointer may be HOST or DEVICE memory (detected with
+ *    cudaPointerGetAttributes). Calls are synchronous w.r.t. host pointers they fill; with
+ *    device pointers the work is enqueued on the handle's stream and pfa_synchronize() (or
+ *    any later host-pointer call) waits for it.
+ *  - one handle = one GPU = one host thread at a time (the reference's callers are serial,
+ *    SURVEY.md §8b "Threading").
+ */
+#ifndef PFA_H
+#define PFA_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C"
+{
+#endif
+
+#define PFA_VERSION 1
+
+	typedef enum
+	{
+		PFA_OK = 0,
+		PFA_ERR_INVALID = -1,     /* bad argument / inconsistent description */
+		PFA_ERR_UNSUPPORTED = -2, /* valid PolyFEM configuration this path does not cover */
+		PFA_ERR_CUDA = -3,        /* CUDA runtime / launch failure */
+		PFA_ERR_NOMEM = -4,       /* host or device allocation failed (std::bad_alloc analogue) */
+		PFA_ERR_NO_DEVICE = -5    /* no usable sm_100 device: there is NO CPU fallback */
+	} pfa_status;
+
+	typedef enum
+	{
+		PFA_NEOHOOKEAN = 0,        /* assembler/NeoHookeanElasticity.cpp, name() == "NeoHookean" */
+		PFA_LINEAR_ELASTICITY = 1, /* assembler/LinearElasticity.cpp,    name() == "LinearElasticity" */
+		PFA_LAPLACIAN = 2          /* assembler/Laplacian.cpp,           name() == "Laplacian" */
+	} pfa_material;
+
+	/* What the shim reads out of std::vector<basis::ElementBases> bases / gbases and the
+	 * AssemblyValsCache once per mesh. All pointers are
+	 * host memory and are copied during pfa_create. */
+	typedef struct
+	{
+		int32_t struct_size; /* sizeof(pfa_mesh_desc), for ABI evolution */
+		int32_t material;    /* pfa_material */
+		int32_t n_elements;  /* bases.size() */
+		int32_t n_loc;       /* bases[e].bases.size(): 4, 10, 20, 35 (P1..P4 tets) */
+		int32_t n_bases;     /* n_basis argument of the assembler virtuals */
+		int32_t n_qp;        /* quadrature points per element */
+		/* conn[e*n_loc + j] = bases[e].bases[j].global()[0].index. Local2Global lists must have
+		 * length 1 and weight 1 (conforming mesh, basis/Basis.hpp:21-38); otherwise the shim
+		 * must not use this path. */
+		const int32_t *conn;
+		const double *quad_weights; /* [n_qp] vals.quadrature.weights (tet weights already /6) */
+		const double *ref_grads;    /* [n_qp][n_loc][3] basis_values[j].grad.row(q) (reference element) */
+		/* geometry, one of:
+		 *  (a) affine (P1 gbases): vertices[e][4][3] = gbases[e].bases[k].global()[0].node, and
+		 *      jac_it / da are NULL. J^-T and det are computed once here
+		 *      (ElementAssemblyValues.cpp:65-104).
+		 *  (b) general: jac_it[e][q][9] (row-major vals.jac_it[q]) and da[e][q] = det*weight. */
+		const double *vertices;
+		const double *jac_it;
+		const double *da;
+		/* Lame parameters, LameParameters::lambda_mu evaluated by the host (MatParams.cpp:368-401):
+		 * material_stride == 1: [n_elements]; == n_qp: [n_elements][n_qp]. Ignored for Laplacian. */
+		const double *lambda;
+		const double *mu;
+		int32_t material_stride;
+		int32_t device; /* CUDA device ordinal */
+		int32_t flags;  /* reserved, 0 */
+		/* Multi-GPU element partition: conn may carry n_ghost_elements extra rows
+		 * after the n_elements computed ones. Ghost elements (elements of other ranks touching a
+		 * node this rank owns) only widen the sparsity pattern so that owned columns have their
+		 * full global row set; they are never evaluated and need no geometry/material entries. */
+		int32_t n_ghost_elements;
+	} pfa_mesh_desc;
+
+	typedef struct pfa_handle pfa_handle;
+
+	/* Builds the device-resident SoA precompute, the CSC pattern and the slot map. One-off per
+	 * mesh (replaces AssemblyValsCache::init + the first-call pattern build of
+	 * SparseMatrixCache, MatrixCache.cpp:88-100,134-213). */
+	int pfa_create(const pfa_mesh_desc *desc, pfa_handle **out);
+	void pfa_destroy(pfa_handle *h);
+	/* message of the last failing call on this handle (or of pfa_create when h == NULL) */
+	const char *pfa_last_error(const pfa_handle *h);
+
+	/* size() of the assembler, ndof = n_bases*size, nnz of the CSC pattern */
+	int pfa_sizes(const pfa_handle *h, int32_t *size, int64_t *ndof, int64_t *nnz);
+	/* CSC pattern, host copies owned by the handle: outer[ndof+1], inner[nnz]
+	 * (== mat.outerIndexPtr() / innerIndexPtr() of the reference result). */
+	int pfa_pattern(pfa_handle *h, int64_t *nnz, const int32_t **outer, const int32_t **inner);
+	/* node-block form of the same (symmetric) pattern: column node b lists its row nodes
+	 * adj[adj_off[b] .. adj_off[b+1]) ascending; values index of (row (a,m), col (b,n)) with a at
+	 * position k is size*size*adj_off[b] + n*size*deg(b) + size*k + m. Host arrays owned by the handle. */
+	int pfa_block_pattern(pfa_handle *h, int64_t *n_pairs, const int32_t **adj_off, const int32_t **adj);
+	/* same arrays in device memory (for a GPU linear solver / the multi-GPU exchange) */
+	int pfa_pattern_device(pfa_handle *h, const int32_t **outer_dev, const int32_t **inner_dev);
+
+	/* Re-upload Lame parameters when t changes (Assembler::set_materials, Assembler.cpp:97-151). */
+	int pfa_set_materials(pfa_handle *h, const double *lambda, const double *mu, int32_t material_stride);
+
+	/* NLAssembler::assemble_energy (Assembler.cpp:495-531) */
+	int pfa_energy(pfa_handle *h, const double *x, double *energy);
+	/* NLAssembler::assemble_energy_per_element (Assembler.cpp:533-572); out[n_elements] */
+	int pfa_energy_per_element(pfa_handle *h, const double *x, double *out);
+	/* NLAssembler::assemble_gradient (Assembler.cpp:574-643); grad[ndof] fully overwritten */
+	int pfa_gradient(pfa_handle *h, const double *x, double *grad);
+	/* NLAssembler::assemble_hessian (Assembler.cpp:645-771); values[nnz] fully overwritten.
+	 * project_to_psd != 0 applies ipc::project_to_psd per element (Assembler.cpp:693-694).
+	 * For LinearElasticity this is the constant stiffness (ElasticForm.cpp:316-320). */
+	int pfa_hessian(pfa_handle *h, const double *x, int project_to_psd, double *values);
+	/* LinearAssembler::assemble (Assembler.cpp:157-384) for LinearElasticity / Laplacian */
+	int pfa_linear_stiffness(pfa_handle *h, double *values);
+	/* Fused energy + gradient + Hessian of one Newton iteration (the benchmarked entry).
+	 * Any of energy / grad / values may be NULL to skip that output. */
+	int pfa_grad_hess(pfa_handle *h, const double *x, int project_to_psd, double *energy, double *grad, double *values);
+
+	/* waits for all work enqueued on the handle's stream */
+	int pfa_synchronize(pfa_handle *h);
+	/* cudaStream_t the handle launches on (as void*), so callers can order their own work */
+	void *pfa_stream(pfa_handle *h);
+
+	/* makes the handle launch on a caller-owned cudaStream_t (e.g. the framework's current
+	 * stream, so the caller's events bracket this library's kernels). NULL = legacy stream. */
+	int pfa_set_stream(pfa_handle *h, void *stream);
+
+	/* Instrumentation for bench.py: when enabled every kernel launch / fill of the next calls
+	 * is bracketed by CUDA events on the handle's stream; records accumulate across calls.
+	 * pfa_profile_read synchronizes the stream, returns the number of accumulated records,
+	 * writes up to `cap` (name, ms) of them and clears the list. */
+	int pfa_profile_enable(pfa_handle *h, int on);
+	int pfa_profile_read(pfa_handle *h, int cap, const char **names, float *ms);
+	/* kernels of this library launched by this handle since creation (bench.py's gpu_launches;
+	 * driver memsets are not counted) */
+	int64_t pfa_launch_count(const pfa_handle *h);
+	/* seconds spent in pfa_create building pattern + slot map + precompute (one-off setup) */
+	double pfa_setup_seconds(const pfa_handle *h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PFA_H */

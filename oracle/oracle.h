@@ -1,0 +1,104 @@
+/* CPU ORACLE — TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+ *
+ * A plain C++17 (no Eigen, no TBB) restatement of PolyFEM's assembly hot path, used only by
+ * tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs as the
+ * checker and the timed CPU baseline. The product (libpfa.so) never links or calls this.
+ *
+ * Parity status ("pinned" / "unpinned"), see DESIGN.md §Oracle:
+ *   - quadrature + basis tables: PINNED against the reference's own generated sources
+ *     (oracle/_ref, tests/golden/ref_tables.npz).
+ *   - SparseMatrixCache semantics: PINNED by the reference's self-contained known-answer test
+ *     tests/test_matrix.cpp:202-249 ("cache"), restated in tests/test_oracle_cache.py.
+ *   - NeoHookean / LinearElasticity / Laplacian local math and the global loops: the reference
+ *     cannot be compiled here (Eigen, TBB, spdlog, ... are not vendored) and its tests for this
+ *     path are property tests on a mesh from polyfem-data (absent). They are restated on the
+ *     synthetic cube (closed form == autodiff 1e-12, NL Hessian == linear stiffness 1e-8,
+ *     gradient/Hessian vs finite differences); numeric end-to-end values are UNPINNED.
+ *   - project_to_psd (ipc-toolkit, source absent): UNPINNED, documented behaviour restated.
+ *
+ * Every function cites the reference file:line it follows (paths relative to
+ * /root/reference/src/polyfem/).
+ */
+#pragma once
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C"
+{
+#endif
+
+	enum
+	{
+		ORACLE_NEOHOOKEAN = 0,
+		ORACLE_LINEAR_ELASTICITY = 1,
+		ORACLE_LAPLACIAN = 2
+	};
+
+	typedef struct
+	{
+		int32_t material;   /* ORACLE_* */
+		int32_t n_elements; /* bases.size() */
+		int32_t n_loc;      /* local bases per element */
+		int32_t n_bases;    /* global bases (n_basis argument of the assembler) */
+		int32_t n_qp;
+		int32_t basis_order;         /* p of the Lagrange basis (used only when use_cache == 0) */
+		const int32_t *node_lattice; /* [n_loc][3] lattice coordinates (x,y,z)*p of the local nodes */
+		const int32_t *conn;         /* [n_elements][n_loc] global basis index of local basis j */
+		const double *vertices;      /* [n_elements][4][3] P1 geometric nodes (gbases) */
+		const double *quad_points;   /* [n_qp][3] */
+		const double *quad_weights;  /* [n_qp], already divided by 6 */
+		const double *ref_grads;     /* [n_qp][n_loc][3] reference gradients (used when use_cache == 1) */
+		const double *lambda;        /* [n_elements] */
+		const double *mu;            /* [n_elements] */
+		int32_t use_cache;           /* 1: AssemblyValsCache::init, 0: init_empty (recompute per call) */
+		int32_t n_threads;           /* stand-in for TBB's thread count */
+	} oracle_desc;
+
+	typedef struct oracle_problem oracle_problem;
+
+	oracle_problem *oracle_create(const oracle_desc *desc);
+	void oracle_destroy(oracle_problem *p);
+	int oracle_size(const oracle_problem *p); /* Assembler::size(): 3, or 1 for Laplacian */
+
+	/* NLAssembler entry points (assembler/Assembler.cpp:495-771) */
+	double oracle_assemble_energy(oracle_problem *p, const double *x);
+	void oracle_assemble_energy_per_element(oracle_problem *p, const double *x, double *out);
+	void oracle_assemble_gradient(oracle_problem *p, const double *x, double *rhs);
+	/* Runs assemble_hessian through the problem's persistent SparseMatrixCache (first call builds
+	 * the pattern + slot map, later calls use it). Returns nnz; read the result with oracle_csc_*. */
+	int64_t oracle_assemble_hessian(oracle_problem *p, const double *x, int project_to_psd);
+	/* LinearAssembler::assemble (assembler/Assembler.cpp:157-384). Returns nnz. */
+	int64_t oracle_assemble_linear(oracle_problem *p);
+	/* the last matrix produced by oracle_assemble_hessian / oracle_assemble_linear (CSC, int32) */
+	int64_t oracle_csc_nnz(const oracle_problem *p);
+	const int32_t *oracle_csc_outer(const oracle_problem *p);
+	const int32_t *oracle_csc_inner(const oracle_problem *p);
+	const double *oracle_csc_values(const oracle_problem *p);
+	/* seconds spent in the element loop / in merge+get_matrix of the last matrix assembly */
+	double oracle_last_loop_seconds(const oracle_problem *p);
+	double oracle_last_merge_seconds(const oracle_problem *p);
+
+	/* local (per element) quantities, for unit tests */
+	double oracle_local_energy(oracle_problem *p, int e, const double *x, int autodiff);
+	void oracle_local_gradient(oracle_problem *p, int e, const double *x, int autodiff, double *g /*[n_loc*size]*/);
+	void oracle_local_hessian(oracle_problem *p, int e, const double *x, int autodiff, double *h /*[N*N] row-major*/);
+	void oracle_local_stiffness(oracle_problem *p, int e, int i, int j, double *blk /*[size*size], index n*size+m*/);
+
+	/* ipc::project_to_psd restatement on a dense symmetric n x n matrix (row-major, in place) */
+	void oracle_project_to_psd(int n, double *a);
+
+	/* SparseMatrixCache restatement exposed for the reference's "cache" known-answer test */
+	typedef struct oracle_cache oracle_cache;
+	oracle_cache *oracle_cache_new(int size);
+	oracle_cache *oracle_cache_copy(const oracle_cache *other); /* SparseMatrixCache(const MatrixCache &) */
+	void oracle_cache_free(oracle_cache *c);
+	void oracle_cache_add_value(oracle_cache *c, int e, int i, int j, double v);
+	void oracle_cache_prune(oracle_cache *c);
+	int64_t oracle_cache_get_matrix(oracle_cache *c); /* returns nnz; then read with the getters */
+	const int32_t *oracle_cache_outer(const oracle_cache *c);
+	const int32_t *oracle_cache_inner(const oracle_cache *c);
+	const double *oracle_cache_values(const oracle_cache *c);
+
+#ifdef __cplusplus
+}
+#endif

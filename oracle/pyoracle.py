@@ -1,0 +1,260 @@
+"""ctypes binding of the CPU oracle (oracle/oracle.h). TEST INFRASTRUCTURE ONLY.
+
+Importers allowed by the project rules: tests/, __graft_entry__.smoke(), and bench.py's
+cpu_baseline / --impl reference legs. The product package never imports this module.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+NEOHOOKEAN, LINEAR_ELASTICITY, LAPLACIAN = 0, 1, 2
+MATERIAL_IDS = {"NeoHookean": NEOHOOKEAN, "LinearElasticity": LINEAR_ELASTICITY, "Laplacian": LAPLACIAN}
+
+_dp = ctypes.POINTER(ctypes.c_double)
+_ip = ctypes.POINTER(ctypes.c_int32)
+
+
+class _Desc(ctypes.Structure):
+    _fields_ = [
+        ("material", ctypes.c_int32), ("n_elements", ctypes.c_int32), ("n_loc", ctypes.c_int32),
+        ("n_bases", ctypes.c_int32), ("n_qp", ctypes.c_int32), ("basis_order", ctypes.c_int32),
+        ("node_lattice", _ip), ("conn", _ip), ("vertices", _dp), ("quad_points", _dp),
+        ("quad_weights", _dp), ("ref_grads", _dp), ("lambda_", _dp), ("mu", _dp),
+        ("use_cache", ctypes.c_int32), ("n_threads", ctypes.c_int32),
+    ]
+
+
+def build():
+    """Compile liboracle.so (and oracle/_ref when the reference tree is mounted)."""
+    subprocess.check_call(["make", "-s", "-C", _HERE, "oracle"])
+    subprocess.check_call(["make", "-s", "-C", _HERE, "ref"])
+
+
+def lib():
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = os.path.join(_HERE, "liboracle.so")
+    src = os.path.join(_HERE, "oracle.cpp")
+    if not os.path.exists(path) or (os.path.exists(src) and os.path.getmtime(src) > os.path.getmtime(path)):
+        subprocess.check_call(["make", "-s", "-C", _HERE, "oracle"])
+    L = ctypes.CDLL(path)
+    vp = ctypes.c_void_p
+    L.oracle_create.restype = vp
+    L.oracle_create.argtypes = [ctypes.POINTER(_Desc)]
+    L.oracle_destroy.argtypes = [vp]
+    L.oracle_size.argtypes = [vp]
+    L.oracle_assemble_energy.restype = ctypes.c_double
+    L.oracle_assemble_energy.argtypes = [vp, _dp]
+    L.oracle_assemble_energy_per_element.argtypes = [vp, _dp, _dp]
+    L.oracle_assemble_gradient.argtypes = [vp, _dp, _dp]
+    L.oracle_assemble_hessian.restype = ctypes.c_int64
+    L.oracle_assemble_hessian.argtypes = [vp, _dp, ctypes.c_int]
+    L.oracle_assemble_linear.restype = ctypes.c_int64
+    L.oracle_assemble_linear.argtypes = [vp]
+    L.oracle_csc_nnz.restype = ctypes.c_int64
+    L.oracle_csc_nnz.argtypes = [vp]
+    for name, rt in (("oracle_csc_outer", _ip), ("oracle_csc_inner", _ip), ("oracle_csc_values", _dp)):
+        getattr(L, name).restype = rt
+        getattr(L, name).argtypes = [vp]
+    for name in ("oracle_last_loop_seconds", "oracle_last_merge_seconds"):
+        getattr(L, name).restype = ctypes.c_double
+        getattr(L, name).argtypes = [vp]
+    L.oracle_local_energy.restype = ctypes.c_double
+    L.oracle_local_energy.argtypes = [vp, ctypes.c_int, _dp, ctypes.c_int]
+    L.oracle_local_gradient.argtypes = [vp, ctypes.c_int, _dp, ctypes.c_int, _dp]
+    L.oracle_local_hessian.argtypes = [vp, ctypes.c_int, _dp, ctypes.c_int, _dp]
+    L.oracle_local_stiffness.argtypes = [vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, _dp]
+    L.oracle_project_to_psd.argtypes = [ctypes.c_int, _dp]
+    L.oracle_cache_new.restype = vp
+    L.oracle_cache_new.argtypes = [ctypes.c_int]
+    L.oracle_cache_copy.restype = vp
+    L.oracle_cache_copy.argtypes = [vp]
+    L.oracle_cache_free.argtypes = [vp]
+    L.oracle_cache_add_value.argtypes = [vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_double]
+    L.oracle_cache_prune.argtypes = [vp]
+    L.oracle_cache_get_matrix.restype = ctypes.c_int64
+    L.oracle_cache_get_matrix.argtypes = [vp]
+    for name, rt in (("oracle_cache_outer", _ip), ("oracle_cache_inner", _ip), ("oracle_cache_values", _dp)):
+        getattr(L, name).restype = rt
+        getattr(L, name).argtypes = [vp]
+    _LIB = L
+    return L
+
+
+def _d(a):
+    return a.ctypes.data_as(_dp)
+
+
+def _i(a):
+    return a.ctypes.data_as(_ip)
+
+
+class CSC:
+    """Column-compressed matrix as Eigen::SparseMatrix<double, ColMajor, int> stores it."""
+
+    def __init__(self, n, outer, inner, values):
+        self.n, self.outer, self.inner, self.values = n, outer, inner, values
+
+    @property
+    def nnz(self):
+        return int(self.values.size)
+
+    def to_scipy(self):
+        import scipy.sparse as sp
+        return sp.csc_matrix((self.values, self.inner, self.outer), shape=(self.n, self.n))
+
+
+class OracleProblem:
+    """One assembler + FE space, as the reference's NLAssembler/LinearAssembler sees it."""
+
+    def __init__(self, material, conn, vertices, n_bases, quad_points, quad_weights, ref_grads,
+                 lam=None, mu=None, basis_order=1, node_lattice=None, use_cache=True, n_threads=1):
+        L = lib()
+        self.material = MATERIAL_IDS[material] if isinstance(material, str) else int(material)
+        self.conn = np.ascontiguousarray(conn, dtype=np.int32)
+        self.vertices = np.ascontiguousarray(vertices, dtype=np.float64)
+        self.qp = np.ascontiguousarray(quad_points, dtype=np.float64)
+        self.qw = np.ascontiguousarray(quad_weights, dtype=np.float64)
+        self.rg = np.ascontiguousarray(ref_grads, dtype=np.float64)
+        ne, nl = self.conn.shape
+        self.n_elements, self.n_loc, self.n_bases = ne, nl, int(n_bases)
+        self.lam = np.ascontiguousarray(np.broadcast_to(0.0 if lam is None else lam, (ne,)), dtype=np.float64)
+        self.mu = np.ascontiguousarray(np.broadcast_to(0.0 if mu is None else mu, (ne,)), dtype=np.float64)
+        self.lattice = None if node_lattice is None else np.ascontiguousarray(node_lattice, dtype=np.int32)
+        d = _Desc()
+        d.material, d.n_elements, d.n_loc, d.n_bases = self.material, ne, nl, self.n_bases
+        d.n_qp, d.basis_order = int(self.qw.size), int(basis_order)
+        d.node_lattice = _i(self.lattice) if self.lattice is not None else None
+        d.conn, d.vertices = _i(self.conn), _d(self.vertices)
+        d.quad_points, d.quad_weights, d.ref_grads = _d(self.qp), _d(self.qw), _d(self.rg)
+        d.lambda_, d.mu = _d(self.lam), _d(self.mu)
+        d.use_cache, d.n_threads = int(bool(use_cache)), int(n_threads)
+        self._h = L.oracle_create(ctypes.byref(d))
+        self.size = L.oracle_size(self._h)
+        self.ndof = self.n_bases * self.size
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().oracle_destroy(self._h)
+            self._h = None
+
+    def _x(self, x):
+        x = np.ascontiguousarray(x, dtype=np.float64).reshape(-1)
+        assert x.size == self.ndof
+        return x
+
+    def assemble_energy(self, x):
+        x = self._x(x)
+        return float(lib().oracle_assemble_energy(self._h, _d(x)))
+
+    def assemble_energy_per_element(self, x):
+        x = self._x(x)
+        out = np.zeros(self.n_elements)
+        lib().oracle_assemble_energy_per_element(self._h, _d(x), _d(out))
+        return out
+
+    def assemble_gradient(self, x):
+        x = self._x(x)
+        rhs = np.zeros(self.ndof)
+        lib().oracle_assemble_gradient(self._h, _d(x), _d(rhs))
+        return rhs
+
+    def _csc(self):
+        L = lib()
+        nnz = int(L.oracle_csc_nnz(self._h))
+        outer = np.ctypeslib.as_array(L.oracle_csc_outer(self._h), shape=(self.ndof + 1,)).copy()
+        inner = np.ctypeslib.as_array(L.oracle_csc_inner(self._h), shape=(nnz,)).copy() if nnz else np.zeros(0, np.int32)
+        vals = np.ctypeslib.as_array(L.oracle_csc_values(self._h), shape=(nnz,)).copy() if nnz else np.zeros(0)
+        return CSC(self.ndof, outer, inner, vals)
+
+    def assemble_hessian(self, x, project_to_psd=False):
+        x = self._x(x)
+        lib().oracle_assemble_hessian(self._h, _d(x), int(bool(project_to_psd)))
+        return self._csc()
+
+    def assemble(self):
+        lib().oracle_assemble_linear(self._h)
+        return self._csc()
+
+    def last_times(self):
+        L = lib()
+        return float(L.oracle_last_loop_seconds(self._h)), float(L.oracle_last_merge_seconds(self._h))
+
+    def local_energy(self, e, x, autodiff=False):
+        x = self._x(x)
+        return float(lib().oracle_local_energy(self._h, int(e), _d(x), int(autodiff)))
+
+    def local_gradient(self, e, x, autodiff=False):
+        x = self._x(x)
+        g = np.zeros(self.n_loc * self.size)
+        lib().oracle_local_gradient(self._h, int(e), _d(x), int(autodiff), _d(g))
+        return g
+
+    def local_hessian(self, e, x, autodiff=False):
+        x = self._x(x)
+        n = self.n_loc * self.size
+        h = np.zeros((n, n))
+        lib().oracle_local_hessian(self._h, int(e), _d(x), int(autodiff), _d(h))
+        return h
+
+    def local_stiffness(self, e, i, j):
+        blk = np.zeros(self.size * self.size)
+        lib().oracle_local_stiffness(self._h, int(e), int(i), int(j), _d(blk))
+        return blk
+
+
+def project_to_psd(a):
+    a = np.array(a, dtype=np.float64, order="C")
+    lib().oracle_project_to_psd(a.shape[0], _d(a))
+    return a
+
+
+class Cache:
+    """SparseMatrixCache restatement (the reference's tests/test_matrix.cpp "cache" test)."""
+
+    def __init__(self, size=None, _h=None):
+        self._h = _h if _h is not None else lib().oracle_cache_new(int(size))
+        self.size = size
+
+    def copy(self):
+        c = Cache(_h=lib().oracle_cache_copy(self._h))
+        c.size = self.size
+        return c
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().oracle_cache_free(self._h)
+            self._h = None
+
+    def add_value(self, e, i, j, v):
+        lib().oracle_cache_add_value(self._h, e, i, j, float(v))
+
+    def prune(self):
+        lib().oracle_cache_prune(self._h)
+
+    def get_matrix(self):
+        L = lib()
+        nnz = int(L.oracle_cache_get_matrix(self._h))
+        outer = np.ctypeslib.as_array(L.oracle_cache_outer(self._h), shape=(self.size + 1,)).copy()
+        inner = np.ctypeslib.as_array(L.oracle_cache_inner(self._h), shape=(nnz,)).copy()
+        vals = np.ctypeslib.as_array(L.oracle_cache_values(self._h), shape=(nnz,)).copy()
+        return CSC(self.size, outer, inner, vals)
+
+
+def problem_from_mesh(mesh, material, E=1e5, nu=0.3, order=None, **kw):
+    """Convenience: oracle problem on a polyfem_b200.mesh.TetMesh with a single material."""
+    from polyfem_b200 import tables
+    from polyfem_b200.mesh import lame_from_E_nu
+    t = tables.reference_tables(mesh.p, order)
+    lam, mu = lame_from_E_nu(E, nu)
+    return OracleProblem(material, mesh.conn, mesh.vertices, mesh.n_bases, t["points"], t["weights"], t["grad"],
+                         lam=lam, mu=mu, basis_order=mesh.p,
+                         node_lattice=np.array(tables.P_NODES_LATTICE[mesh.p], dtype=np.int32), **kw)

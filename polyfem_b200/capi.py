@@ -1,0 +1,278 @@
+"""ctypes binding of libpfa.so — the same C ABI (include/pfa.h) a PolyFEM-side shim binds.
+
+Arrays may be numpy arrays (host memory) or torch CUDA tensors (device memory, passed by
+`data_ptr()`); the library detects which with cudaPointerGetAttributes. There is no CPU
+fallback: if libpfa.so is missing or no sm_100 device is present the calls raise.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libpfa.so")
+
+PFA_OK = 0
+PFA_ERR_INVALID, PFA_ERR_UNSUPPORTED, PFA_ERR_CUDA, PFA_ERR_NOMEM, PFA_ERR_NO_DEVICE = -1, -2, -3, -4, -5
+NEOHOOKEAN, LINEAR_ELASTICITY, LAPLACIAN = 0, 1, 2
+MATERIAL_IDS = {"NeoHookean": NEOHOOKEAN, "LinearElasticity": LINEAR_ELASTICITY, "Laplacian": LAPLACIAN}
+
+_dp = ctypes.POINTER(ctypes.c_double)
+_ip = ctypes.POINTER(ctypes.c_int32)
+
+# every symbol include/pfa.h declares (tests check that the library exports all of them)
+EXPORTS = [
+    "pfa_create", "pfa_destroy", "pfa_last_error", "pfa_sizes", "pfa_pattern", "pfa_block_pattern", "pfa_pattern_device",
+    "pfa_set_materials", "pfa_energy", "pfa_energy_per_element", "pfa_gradient", "pfa_hessian",
+    "pfa_linear_stiffness", "pfa_grad_hess", "pfa_synchronize", "pfa_stream", "pfa_set_stream", "pfa_profile_enable",
+    "pfa_profile_read", "pfa_launch_count", "pfa_setup_seconds",
+]
+
+
+class MeshDesc(ctypes.Structure):
+    _fields_ = [
+        ("struct_size", ctypes.c_int32), ("material", ctypes.c_int32), ("n_elements", ctypes.c_int32),
+        ("n_loc", ctypes.c_int32), ("n_bases", ctypes.c_int32), ("n_qp", ctypes.c_int32),
+        ("conn", _ip), ("quad_weights", _dp), ("ref_grads", _dp),
+        ("vertices", _dp), ("jac_it", _dp), ("da", _dp),
+        ("lambda_", _dp), ("mu", _dp),
+        ("material_stride", ctypes.c_int32), ("device", ctypes.c_int32), ("flags", ctypes.c_int32),
+        ("n_ghost_elements", ctypes.c_int32),
+    ]
+
+
+class PfaError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"pfa error {code}: {msg}")
+        self.code = code
+
+
+_LIB = None
+
+
+def lib():
+    """Loads libpfa.so; fails loudly when it has not been built (no fallback path exists)."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(f"{LIB_PATH} is missing: run `python -m polyfem_b200.build` (nvcc, sm_100a). "
+                          "polyfem_b200 has no CPU fallback.")
+    L = ctypes.CDLL(LIB_PATH)
+    vp, c_int, i64 = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64
+    L.pfa_create.argtypes = [ctypes.POINTER(MeshDesc), ctypes.POINTER(vp)]
+    L.pfa_destroy.argtypes = [vp]
+    L.pfa_destroy.restype = None
+    L.pfa_last_error.argtypes = [vp]
+    L.pfa_last_error.restype = ctypes.c_char_p
+    L.pfa_sizes.argtypes = [vp, ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(i64), ctypes.POINTER(i64)]
+    L.pfa_pattern.argtypes = [vp, ctypes.POINTER(i64), ctypes.POINTER(_ip), ctypes.POINTER(_ip)]
+    L.pfa_block_pattern.argtypes = [vp, ctypes.POINTER(i64), ctypes.POINTER(_ip), ctypes.POINTER(_ip)]
+    L.pfa_pattern_device.argtypes = [vp, ctypes.POINTER(vp), ctypes.POINTER(vp)]
+    L.pfa_set_materials.argtypes = [vp, vp, vp, ctypes.c_int32]
+    L.pfa_energy.argtypes = [vp, vp, vp]
+    L.pfa_energy_per_element.argtypes = [vp, vp, vp]
+    L.pfa_gradient.argtypes = [vp, vp, vp]
+    L.pfa_hessian.argtypes = [vp, vp, c_int, vp]
+    L.pfa_linear_stiffness.argtypes = [vp, vp]
+    L.pfa_grad_hess.argtypes = [vp, vp, c_int, vp, vp, vp]
+    L.pfa_synchronize.argtypes = [vp]
+    L.pfa_stream.argtypes = [vp]
+    L.pfa_stream.restype = vp
+    L.pfa_set_stream.argtypes = [vp, vp]
+    L.pfa_profile_enable.argtypes = [vp, c_int]
+    L.pfa_profile_read.argtypes = [vp, c_int, ctypes.POINTER(ctypes.c_char_p), ctypes.POINTER(ctypes.c_float)]
+    L.pfa_launch_count.argtypes = [vp]
+    L.pfa_launch_count.restype = i64
+    L.pfa_setup_seconds.argtypes = [vp]
+    L.pfa_setup_seconds.restype = ctypes.c_double
+    _LIB = L
+    return L
+
+
+def _ptr(a):
+    """Raw address of a numpy array (host) / torch tensor (host or device) / int / None."""
+    if a is None:
+        return None
+    if isinstance(a, int):
+        return ctypes.c_void_p(a)
+    if isinstance(a, np.ndarray):
+        assert a.flags["C_CONTIGUOUS"]
+        return ctypes.c_void_p(a.ctypes.data)
+    if hasattr(a, "data_ptr"):
+        assert a.is_contiguous()
+        return ctypes.c_void_p(a.data_ptr())
+    raise TypeError(f"unsupported buffer type {type(a)}")
+
+
+class Handle:
+    """One pfa_handle: one mesh + material on one GPU."""
+
+    def __init__(self, material, conn, n_bases, quad_weights, ref_grads, vertices=None, jac_it=None, da=None,
+                 lam=None, mu=None, device=0, n_ghost_elements=0):
+        L = lib()
+        self.material = MATERIAL_IDS[material] if isinstance(material, str) else int(material)
+        conn = np.ascontiguousarray(conn, dtype=np.int32)
+        qw = np.ascontiguousarray(quad_weights, dtype=np.float64)
+        rg = np.ascontiguousarray(ref_grads, dtype=np.float64)
+        ne, nl = conn.shape
+        ne -= int(n_ghost_elements)  # trailing rows of conn are pattern-only ghost elements
+        nq = qw.size
+        assert rg.shape == (nq, nl, 3), f"ref_grads must be [n_qp, n_loc, 3], got {rg.shape}"
+        d = MeshDesc()
+        d.struct_size = ctypes.sizeof(MeshDesc)
+        d.material, d.n_elements, d.n_loc, d.n_bases, d.n_qp = self.material, ne, nl, int(n_bases), nq
+        keep = [conn, qw, rg]
+        d.conn = conn.ctypes.data_as(_ip)
+        d.quad_weights = qw.ctypes.data_as(_dp)
+        d.ref_grads = rg.ctypes.data_as(_dp)
+        if vertices is not None:
+            v = np.ascontiguousarray(vertices, dtype=np.float64).reshape(ne, 4, 3)
+            d.vertices = v.ctypes.data_as(_dp)
+            keep.append(v)
+        if jac_it is not None:
+            j = np.ascontiguousarray(jac_it, dtype=np.float64).reshape(ne, nq, 9)
+            a = np.ascontiguousarray(da, dtype=np.float64).reshape(ne, nq)
+            d.jac_it, d.da = j.ctypes.data_as(_dp), a.ctypes.data_as(_dp)
+            keep += [j, a]
+        stride = 1
+        if self.material != LAPLACIAN:
+            lam = np.asarray(lam, dtype=np.float64)
+            mu = np.asarray(mu, dtype=np.float64)
+            if lam.ndim == 0:
+                lam = np.full(ne, float(lam))
+                mu = np.full(ne, float(mu))
+            lam = np.ascontiguousarray(lam)
+            mu = np.ascontiguousarray(mu)
+            stride = 1 if lam.size == ne else nq
+            assert lam.size == ne * stride and mu.size == ne * stride
+            d.lambda_, d.mu = lam.ctypes.data_as(_dp), mu.ctypes.data_as(_dp)
+            keep += [lam, mu]
+        d.material_stride, d.device, d.flags = stride, int(device), 0
+        d.n_ghost_elements = int(n_ghost_elements)
+        h = ctypes.c_void_p()
+        rc = L.pfa_create(ctypes.byref(d), ctypes.byref(h))
+        if rc != PFA_OK:
+            raise PfaError(rc, L.pfa_last_error(None).decode())
+        self._h = h
+        self.device = int(device)
+        self.n_elements, self.n_loc, self.n_bases, self.n_qp = ne, nl, int(n_bases), nq
+        size, ndof, nnz = ctypes.c_int32(), ctypes.c_int64(), ctypes.c_int64()
+        L.pfa_sizes(self._h, ctypes.byref(size), ctypes.byref(ndof), ctypes.byref(nnz))
+        self.size, self.ndof, self.nnz = size.value, ndof.value, nnz.value
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().pfa_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc < 0:
+            raise PfaError(rc, lib().pfa_last_error(self._h).decode())
+        return rc
+
+    # ---- pattern ----
+    def pattern(self):
+        """(outer[ndof+1], inner[nnz]) int32 host arrays, Eigen CSC layout."""
+        L = lib()
+        nnz = ctypes.c_int64()
+        po, pi = _ip(), _ip()
+        self._check(L.pfa_pattern(self._h, ctypes.byref(nnz), ctypes.byref(po), ctypes.byref(pi)))
+        outer = np.ctypeslib.as_array(po, shape=(self.ndof + 1,)).copy()
+        inner = np.ctypeslib.as_array(pi, shape=(nnz.value,)).copy()
+        return outer, inner
+
+    def block_pattern(self):
+        """(adj_off[n_bases+1], adj[n_pairs]) int32 host arrays: node-block form of the pattern."""
+        n = ctypes.c_int64()
+        po, pa = _ip(), _ip()
+        self._check(lib().pfa_block_pattern(self._h, ctypes.byref(n), ctypes.byref(po), ctypes.byref(pa)))
+        return (np.ctypeslib.as_array(po, shape=(self.n_bases + 1,)).copy(),
+                np.ctypeslib.as_array(pa, shape=(n.value,)).copy())
+
+    def pattern_device_ptrs(self):
+        po, pi = ctypes.c_void_p(), ctypes.c_void_p()
+        self._check(lib().pfa_pattern_device(self._h, ctypes.byref(po), ctypes.byref(pi)))
+        return po.value, pi.value
+
+    def set_materials(self, lam, mu, stride=1):
+        lam = np.ascontiguousarray(lam, dtype=np.float64)
+        mu = np.ascontiguousarray(mu, dtype=np.float64)
+        self._check(lib().pfa_set_materials(self._h, _ptr(lam), _ptr(mu), int(stride)))
+
+    # ---- host-array convenience wrappers (numpy in, numpy out) ----
+    def energy(self, x):
+        x = np.ascontiguousarray(x, dtype=np.float64).reshape(-1)
+        e = np.zeros(1)
+        self._check(lib().pfa_energy(self._h, _ptr(x), _ptr(e)))
+        return float(e[0])
+
+    def energy_per_element(self, x):
+        x = np.ascontiguousarray(x, dtype=np.float64).reshape(-1)
+        out = np.zeros(self.n_elements)
+        self._check(lib().pfa_energy_per_element(self._h, _ptr(x), _ptr(out)))
+        return out
+
+    def gradient(self, x):
+        x = np.ascontiguousarray(x, dtype=np.float64).reshape(-1)
+        g = np.zeros(self.ndof)
+        self._check(lib().pfa_gradient(self._h, _ptr(x), _ptr(g)))
+        return g
+
+    def hessian(self, x, project_to_psd=False):
+        x = np.ascontiguousarray(x, dtype=np.float64).reshape(-1)
+        v = np.zeros(self.nnz)
+        self._check(lib().pfa_hessian(self._h, _ptr(x), int(bool(project_to_psd)), _ptr(v)))
+        return v
+
+    def linear_stiffness(self):
+        v = np.zeros(self.nnz)
+        self._check(lib().pfa_linear_stiffness(self._h, _ptr(v)))
+        return v
+
+    def grad_hess(self, x, project_to_psd=False):
+        x = np.ascontiguousarray(x, dtype=np.float64).reshape(-1)
+        e, g, v = np.zeros(1), np.zeros(self.ndof), np.zeros(self.nnz)
+        self._check(lib().pfa_grad_hess(self._h, _ptr(x), int(bool(project_to_psd)), _ptr(e), _ptr(g), _ptr(v)))
+        return float(e[0]), g, v
+
+    # ---- raw pointer entry (host numpy arrays or torch CUDA tensors, any may be None) ----
+    def grad_hess_raw(self, x, energy=None, grad=None, values=None, project_to_psd=False):
+        self._check(lib().pfa_grad_hess(self._h, _ptr(x), int(bool(project_to_psd)), _ptr(energy), _ptr(grad), _ptr(values)))
+
+    def linear_stiffness_raw(self, values):
+        self._check(lib().pfa_linear_stiffness(self._h, _ptr(values)))
+
+    def synchronize(self):
+        self._check(lib().pfa_synchronize(self._h))
+
+    def stream(self):
+        return lib().pfa_stream(self._h)
+
+    def set_stream(self, stream_ptr):
+        """Launch on a caller-owned CUDA stream (e.g. torch.cuda.current_stream().cuda_stream)."""
+        self._check(lib().pfa_set_stream(self._h, ctypes.c_void_p(stream_ptr)))
+
+    def profile_enable(self, on=True):
+        self._check(lib().pfa_profile_enable(self._h, int(bool(on))))
+
+    def profile_read(self):
+        cap = 8192
+        names = (ctypes.c_char_p * cap)()
+        ms = (ctypes.c_float * cap)()
+        n = self._check(lib().pfa_profile_read(self._h, cap, names, ms))
+        return [(names[i].decode(), float(ms[i])) for i in range(min(n, cap))]
+
+    def launch_count(self):
+        return int(lib().pfa_launch_count(self._h))
+
+    def setup_seconds(self):
+        return float(lib().pfa_setup_seconds(self._h))

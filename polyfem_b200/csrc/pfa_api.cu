@@ -1,0 +1,649 @@
+// C-ABI layer of libpfa.so (include/pfa.h): handle lifetime, host<->device staging,
+// error translation. No CPU fallback: every compute entry point runs the CUDA kernels or
+// fails with PFA_ERR_NO_DEVICE / PFA_ERR_CUDA.
+#include "pfa_internal.h"
+
+#include <chrono>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+using namespace pfa;
+
+namespace
+{
+	thread_local std::string g_create_error;
+
+	struct ProfRecord
+	{
+		const char *name;
+		cudaEvent_t start, stop;
+		bool stop_recorded;
+	};
+} // namespace
+
+struct pfa_handle
+{
+	int device = 0;
+	int sm_count = 148;
+	cudaStream_t stream = nullptr;
+	bool own_stream = true;
+	DeviceMesh dm;
+	int64_t ndof = 0, nnz = 0;
+
+	// owned device memory
+	std::vector<void *> owned;
+	int32_t *d_outer = nullptr, *d_inner = nullptr;
+	double *d_lambda = nullptr, *d_mu = nullptr;
+	// staging for host-pointer calls (allocated on first use)
+	double *s_x = nullptr, *s_grad = nullptr, *s_values = nullptr, *s_epe = nullptr;
+	double *d_energy = nullptr;
+
+	std::vector<int32_t> h_outer, h_inner;
+	std::vector<int32_t> h_adj_off, h_adj;
+	std::string err;
+
+	bool profiling = false;
+	std::vector<ProfRecord> prof;
+	std::vector<const char *> prof_names;
+	std::vector<float> prof_ms;
+	int64_t launches = 0;
+	double setup_seconds = 0.0;
+};
+
+namespace
+{
+	int fail(pfa_handle *h, int code, const std::string &msg)
+	{
+		if (h)
+			h->err = msg;
+		else
+			g_create_error = msg;
+		return code;
+	}
+
+#define PFA_CUDA(h, call)                                                                                      \
+	do                                                                                                         \
+	{                                                                                                          \
+		cudaError_t e_ = (call);                                                                               \
+		if (e_ != cudaSuccess)                                                                                 \
+			return fail(h, e_ == cudaErrorMemoryAllocation ? PFA_ERR_NOMEM : PFA_ERR_CUDA,                     \
+						std::string(#call) + ": " + cudaGetErrorString(e_));                                   \
+	} while (0)
+
+	template <typename T>
+	int dev_alloc(pfa_handle *h, T **p, size_t count)
+	{
+		void *q = nullptr;
+		PFA_CUDA(h, cudaMalloc(&q, std::max<size_t>(count, 1) * sizeof(T)));
+		h->owned.push_back(q);
+		*p = static_cast<T *>(q);
+		return PFA_OK;
+	}
+
+	template <typename T>
+	int dev_upload(pfa_handle *h, T **p, const T *src, size_t count)
+	{
+		int rc = dev_alloc(h, p, count);
+		if (rc != PFA_OK)
+			return rc;
+		PFA_CUDA(h, cudaMemcpyAsync(*p, src, count * sizeof(T), cudaMemcpyHostToDevice, h->stream));
+		return PFA_OK;
+	}
+
+	bool is_device_ptr(const void *p)
+	{
+		cudaPointerAttributes attr;
+		if (cudaPointerGetAttributes(&attr, p) != cudaSuccess)
+		{
+			cudaGetLastError();
+			return false;
+		}
+		return attr.type == cudaMemoryTypeDevice || attr.type == cudaMemoryTypeManaged;
+	}
+
+	constexpr size_t kMaxProfRecords = 8192;
+
+	void prof_begin(pfa_handle *h, const char *name, bool is_kernel = true)
+	{
+		if (is_kernel)
+			++h->launches;
+		if (!h->profiling || h->prof.size() >= kMaxProfRecords)
+			return;
+		ProfRecord r;
+		r.name = name;
+		r.stop_recorded = false;
+		cudaEventCreate(&r.start);
+		cudaEventCreate(&r.stop);
+		cudaEventRecord(r.start, h->stream);
+		h->prof.push_back(r);
+	}
+	void prof_end(pfa_handle *h)
+	{
+		if (!h->profiling || h->prof.empty() || h->prof.back().stop_recorded)
+			return;
+		cudaEventRecord(h->prof.back().stop, h->stream);
+		h->prof.back().stop_recorded = true;
+	}
+	void prof_reset(pfa_handle *h)
+	{
+		for (auto &r : h->prof)
+		{
+			cudaEventDestroy(r.start);
+			cudaEventDestroy(r.stop);
+		}
+		h->prof.clear();
+	}
+
+	int ensure_staging(pfa_handle *h, double **buf, size_t count)
+	{
+		if (*buf)
+			return PFA_OK;
+		return dev_alloc(h, buf, count);
+	}
+
+	// resolves an input vector to a device pointer (copying from the host when needed)
+	int stage_input(pfa_handle *h, const double *x, const double **x_dev)
+	{
+		if (x == nullptr)
+			return fail(h, PFA_ERR_INVALID, "displacement pointer is NULL");
+		if (is_device_ptr(x))
+		{
+			*x_dev = x;
+			return PFA_OK;
+		}
+		int rc = ensure_staging(h, &h->s_x, size_t(h->ndof));
+		if (rc != PFA_OK)
+			return rc;
+		PFA_CUDA(h, cudaMemcpyAsync(h->s_x, x, size_t(h->ndof) * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+		*x_dev = h->s_x;
+		return PFA_OK;
+	}
+
+	struct OutBuf
+	{
+		double *user = nullptr; // caller pointer (host or device) or NULL
+		double *dev = nullptr;  // where the kernels write
+		bool to_host = false;
+		size_t count = 0;
+	};
+
+	int stage_output(pfa_handle *h, double *user, size_t count, double **staging, OutBuf &o)
+	{
+		o.user = user;
+		o.count = count;
+		if (user == nullptr)
+			return PFA_OK;
+		if (is_device_ptr(user))
+		{
+			o.dev = user;
+			return PFA_OK;
+		}
+		int rc = ensure_staging(h, staging, count);
+		if (rc != PFA_OK)
+			return rc;
+		o.dev = *staging;
+		o.to_host = true;
+		return PFA_OK;
+	}
+
+	int finish_output(pfa_handle *h, const OutBuf &o)
+	{
+		if (o.to_host)
+			PFA_CUDA(h, cudaMemcpyAsync(o.user, o.dev, o.count * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+		return PFA_OK;
+	}
+
+	// the one place that launches the assembly kernels
+	int run_assemble(pfa_handle *h, bool linear, const double *x, int project_to_psd,
+					 double *energy, double *energy_per_el, double *grad, double *values)
+	{
+		h->err.clear();
+		PFA_CUDA(h, cudaSetDevice(h->device));
+		if (project_to_psd)
+			return fail(h, PFA_ERR_UNSUPPORTED, "project_to_psd is not implemented on the GPU path yet");
+		if (h->dm.material == PFA_LAPLACIAN && !linear)
+			return fail(h, PFA_ERR_UNSUPPORTED, "Laplacian is a LinearAssembler: only pfa_linear_stiffness applies");
+		if (h->dm.material == PFA_NEOHOOKEAN && linear)
+			return fail(h, PFA_ERR_UNSUPPORTED, "NeoHookean is an NLAssembler: pfa_linear_stiffness does not apply");
+
+		AssembleArgs a;
+		int rc;
+		if (!linear)
+		{
+			rc = stage_input(h, x, &a.x);
+			if (rc != PFA_OK)
+				return rc;
+		}
+		OutBuf oe, op, og, ov;
+		if ((rc = stage_output(h, energy, 1, &h->d_energy, oe)) != PFA_OK)
+			return rc;
+		if ((rc = stage_output(h, energy_per_el, size_t(h->dm.n_el), &h->s_epe, op)) != PFA_OK)
+			return rc;
+		if ((rc = stage_output(h, grad, size_t(h->ndof), &h->s_grad, og)) != PFA_OK)
+			return rc;
+		if ((rc = stage_output(h, values, size_t(h->nnz), &h->s_values, ov)) != PFA_OK)
+			return rc;
+		a.energy = oe.dev;
+		a.energy_per_el = op.dev;
+		a.grad = og.dev;
+		a.values = ov.dev;
+		a.project_to_psd = project_to_psd;
+
+		// outputs are accumulated with atomics: zero them first (rhs.setZero / set_zero,
+		// Assembler.cpp:586-587, 666-667)
+		if (a.energy || a.grad || a.values)
+		{
+			prof_begin(h, "zero_fill(cudaMemsetAsync)", false);
+			if (a.energy)
+				PFA_CUDA(h, cudaMemsetAsync(a.energy, 0, sizeof(double), h->stream));
+			if (a.grad)
+				PFA_CUDA(h, cudaMemsetAsync(a.grad, 0, size_t(h->ndof) * sizeof(double), h->stream));
+			if (a.values)
+				PFA_CUDA(h, cudaMemsetAsync(a.values, 0, size_t(h->nnz) * sizeof(double), h->stream));
+			prof_end(h);
+		}
+
+		const char *kname = "assemble";
+		prof_begin(h, kname);
+		cudaError_t ce = launch_assemble(h->dm, a, linear, h->sm_count, h->stream, &kname);
+		if (h->profiling && !h->prof.empty() && !h->prof.back().stop_recorded)
+			h->prof.back().name = kname;
+		prof_end(h);
+		if (ce != cudaSuccess)
+			return fail(h, PFA_ERR_CUDA, std::string("assembly kernel launch: ") + cudaGetErrorString(ce));
+
+		if ((rc = finish_output(h, oe)) != PFA_OK || (rc = finish_output(h, op)) != PFA_OK || (rc = finish_output(h, og)) != PFA_OK || (rc = finish_output(h, ov)) != PFA_OK)
+			return rc;
+		if (oe.to_host || op.to_host || og.to_host || ov.to_host)
+			PFA_CUDA(h, cudaStreamSynchronize(h->stream));
+		return PFA_OK;
+	}
+} // namespace
+
+extern "C"
+{
+	int pfa_create(const pfa_mesh_desc *d, pfa_handle **out)
+	{
+		g_create_error.clear();
+		if (!d || !out)
+			return fail(nullptr, PFA_ERR_INVALID, "pfa_create: NULL argument");
+		*out = nullptr;
+		if (d->struct_size != int32_t(sizeof(pfa_mesh_desc)))
+			return fail(nullptr, PFA_ERR_INVALID, "pfa_create: struct_size does not match this library's pfa_mesh_desc");
+		if (d->material < PFA_NEOHOOKEAN || d->material > PFA_LAPLACIAN)
+			return fail(nullptr, PFA_ERR_INVALID, "pfa_create: unknown material");
+		if (d->n_elements <= 0 || d->n_loc <= 0 || d->n_bases <= 0 || d->n_qp <= 0 || d->n_ghost_elements < 0)
+			return fail(nullptr, PFA_ERR_INVALID, "pfa_create: n_elements, n_loc, n_bases and n_qp must be positive");
+		if (!d->conn || !d->quad_weights || !d->ref_grads)
+			return fail(nullptr, PFA_ERR_INVALID, "pfa_create: conn, quad_weights and ref_grads are required");
+		const bool affine = d->vertices != nullptr;
+		if (!affine && !(d->jac_it && d->da))
+			return fail(nullptr, PFA_ERR_INVALID, "pfa_create: give either vertices (affine) or jac_it + da");
+		if (d->material != PFA_LAPLACIAN && (!d->lambda || !d->mu))
+			return fail(nullptr, PFA_ERR_INVALID, "pfa_create: lambda and mu are required for elastic materials");
+		if (d->material != PFA_LAPLACIAN && d->material_stride != 1 && d->material_stride != d->n_qp)
+			return fail(nullptr, PFA_ERR_INVALID, "pfa_create: material_stride must be 1 or n_qp");
+
+		int n_dev = 0;
+		if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev <= 0)
+		{
+			cudaGetLastError();
+			return fail(nullptr, PFA_ERR_NO_DEVICE, "pfa_create: no CUDA device available (this path has no CPU fallback)");
+		}
+		if (d->device < 0 || d->device >= n_dev)
+			return fail(nullptr, PFA_ERR_INVALID, "pfa_create: device ordinal out of range");
+
+		const auto t0 = std::chrono::steady_clock::now();
+		pfa_handle *h = new (std::nothrow) pfa_handle();
+		if (!h)
+			return fail(nullptr, PFA_ERR_NOMEM, "pfa_create: out of host memory");
+		auto bail = [&](int rc) {
+			g_create_error = h->err;
+			pfa_destroy(h);
+			return rc;
+		};
+		h->device = d->device;
+		{
+			cudaError_t e = cudaSetDevice(d->device);
+			cudaDeviceProp prop;
+			if (e == cudaSuccess)
+				e = cudaGetDeviceProperties(&prop, d->device);
+			if (e != cudaSuccess)
+			{
+				h->err = std::string("pfa_create: ") + cudaGetErrorString(e);
+				return bail(PFA_ERR_CUDA);
+			}
+			if (prop.major < 10)
+			{
+				h->err = "pfa_create: device is not sm_100 class (library is built for sm_100a only)";
+				return bail(PFA_ERR_NO_DEVICE);
+			}
+			h->sm_count = prop.multiProcessorCount;
+			e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+			if (e != cudaSuccess)
+			{
+				h->err = std::string("pfa_create: ") + cudaGetErrorString(e);
+				return bail(PFA_ERR_CUDA);
+			}
+		}
+
+		DeviceMesh &m = h->dm;
+		m.material = d->material;
+		m.size = d->material == PFA_LAPLACIAN ? 1 : 3;
+		m.n_el = d->n_elements;
+		m.n_loc = d->n_loc;
+		m.n_bases = d->n_bases;
+		m.n_qp = d->n_qp;
+		m.geom_per_qp = affine ? 0 : 1;
+		m.mat_stride = d->material == PFA_LAPLACIAN ? 1 : d->material_stride;
+		if (!assemble_supported(m))
+		{
+			h->err = "pfa_create: n_loc x n_qp too large for the shared-memory staging of this build";
+			return bail(PFA_ERR_UNSUPPORTED);
+		}
+
+		// pattern + slot map on the host (once per mesh)
+		HostPattern hp;
+		try
+		{
+			build_pattern(d->conn, d->n_elements + d->n_ghost_elements, d->n_loc, d->n_bases, hp);
+		}
+		catch (const std::bad_alloc &)
+		{
+			h->err = "pfa_create: out of host memory while building the pattern";
+			return bail(PFA_ERR_NOMEM);
+		}
+		catch (const std::exception &ex)
+		{
+			h->err = ex.what();
+			return bail(PFA_ERR_INVALID);
+		}
+		m.n_pairs = int64_t(hp.adj.size());
+		h->ndof = int64_t(m.n_bases) * m.size;
+		h->nnz = m.n_pairs * m.size * m.size;
+		if (h->nnz >= (int64_t(1) << 31))
+		{
+			h->err = "pfa_create: nnz exceeds int32 (StiffnessMatrix uses int indices unless POLYSOLVE_LARGE_INDEX)";
+			return bail(PFA_ERR_UNSUPPORTED);
+		}
+
+		int rc = PFA_OK;
+#define UP(dst, src, count, T)                                             \
+	do                                                                     \
+	{                                                                      \
+		T *tmp_ = nullptr;                                                 \
+		rc = dev_upload<T>(h, &tmp_, (const T *)(src), size_t(count));     \
+		if (rc != PFA_OK)                                                  \
+			return bail(rc);                                               \
+		dst = tmp_;                                                        \
+	} while (0)
+		const size_t ne = size_t(m.n_el), nl = size_t(m.n_loc), nq = size_t(m.n_qp);
+		UP(m.conn, d->conn, ne * nl, int32_t);
+		UP(m.ref_grads, d->ref_grads, nq * nl * 3, double);
+		UP(m.qweights, d->quad_weights, nq, double);
+		UP(m.adj_off, hp.adj_off.data(), hp.adj_off.size(), int32_t);
+		UP(m.adj, hp.adj.data(), hp.adj.size(), int32_t);
+		UP(m.slot, hp.slot.data(), size_t(ne) * nl * nl, int32_t);
+		if (m.material != PFA_LAPLACIAN)
+		{
+			const size_t cnt = ne * size_t(m.mat_stride);
+			if ((rc = dev_upload<double>(h, &h->d_lambda, d->lambda, cnt)) != PFA_OK || (rc = dev_upload<double>(h, &h->d_mu, d->mu, cnt)) != PFA_OK)
+				return bail(rc);
+			m.lambda = h->d_lambda;
+			m.mu = h->d_mu;
+		}
+		if (affine)
+		{
+			double *d_vert = nullptr, *jit = nullptr, *detj = nullptr;
+			if ((rc = dev_upload<double>(h, &d_vert, d->vertices, ne * 12)) != PFA_OK || (rc = dev_alloc<double>(h, &jit, ne * 9)) != PFA_OK || (rc = dev_alloc<double>(h, &detj, ne)) != PFA_OK)
+				return bail(rc);
+			++h->launches;
+			cudaError_t e = launch_geometry_precompute(d_vert, m.n_el, jit, detj, h->stream);
+			if (e != cudaSuccess)
+			{
+				h->err = std::string("geometry precompute: ") + cudaGetErrorString(e);
+				return bail(PFA_ERR_CUDA);
+			}
+			m.jit = jit;
+			m.detj = detj;
+		}
+		else
+		{
+			UP(m.jit, d->jac_it, ne * nq * 9, double);
+			UP(m.detj, d->da, ne * nq, double);
+		}
+#undef UP
+		if ((rc = dev_alloc<int32_t>(h, &h->d_outer, size_t(h->ndof) + 1)) != PFA_OK || (rc = dev_alloc<int32_t>(h, &h->d_inner, size_t(h->nnz))) != PFA_OK || (rc = dev_alloc<double>(h, &h->d_energy, 1)) != PFA_OK)
+			return bail(rc);
+		{
+			++h->launches;
+			cudaError_t e = launch_expand_inner(m, h->d_outer, h->d_inner, h->stream);
+			if (e == cudaSuccess)
+				e = cudaStreamSynchronize(h->stream);
+			if (e != cudaSuccess)
+			{
+				h->err = std::string("pattern expansion: ") + cudaGetErrorString(e);
+				return bail(PFA_ERR_CUDA);
+			}
+		}
+		h->h_adj_off.swap(hp.adj_off);
+		h->h_adj.swap(hp.adj);
+		h->setup_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+		*out = h;
+		return PFA_OK;
+	}
+
+	void pfa_destroy(pfa_handle *h)
+	{
+		if (!h)
+			return;
+		cudaSetDevice(h->device);
+		if (h->stream)
+			cudaStreamSynchronize(h->stream);
+		prof_reset(h);
+		for (void *p : h->owned)
+			cudaFree(p);
+		if (h->stream && h->own_stream)
+			cudaStreamDestroy(h->stream);
+		delete h;
+	}
+
+	const char *pfa_last_error(const pfa_handle *h)
+	{
+		return h ? h->err.c_str() : g_create_error.c_str();
+	}
+
+	int pfa_sizes(const pfa_handle *h, int32_t *size, int64_t *ndof, int64_t *nnz)
+	{
+		if (!h)
+			return PFA_ERR_INVALID;
+		if (size)
+			*size = h->dm.size;
+		if (ndof)
+			*ndof = h->ndof;
+		if (nnz)
+			*nnz = h->nnz;
+		return PFA_OK;
+	}
+
+	int pfa_pattern(pfa_handle *h, int64_t *nnz, const int32_t **outer, const int32_t **inner)
+	{
+		if (!h)
+			return PFA_ERR_INVALID;
+		PFA_CUDA(h, cudaSetDevice(h->device));
+		if (h->h_outer.empty())
+		{
+			try
+			{
+				h->h_outer.resize(size_t(h->ndof) + 1);
+				h->h_inner.resize(size_t(h->nnz));
+			}
+			catch (const std::bad_alloc &)
+			{
+				h->h_outer.clear();
+				return fail(h, PFA_ERR_NOMEM, "pfa_pattern: out of host memory");
+			}
+			PFA_CUDA(h, cudaMemcpyAsync(h->h_outer.data(), h->d_outer, h->h_outer.size() * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+			PFA_CUDA(h, cudaMemcpyAsync(h->h_inner.data(), h->d_inner, h->h_inner.size() * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+			PFA_CUDA(h, cudaStreamSynchronize(h->stream));
+		}
+		if (nnz)
+			*nnz = h->nnz;
+		if (outer)
+			*outer = h->h_outer.data();
+		if (inner)
+			*inner = h->h_inner.data();
+		return PFA_OK;
+	}
+
+	int pfa_block_pattern(pfa_handle *h, int64_t *n_pairs, const int32_t **adj_off, const int32_t **adj)
+	{
+		if (!h)
+			return PFA_ERR_INVALID;
+		if (n_pairs)
+			*n_pairs = int64_t(h->h_adj.size());
+		if (adj_off)
+			*adj_off = h->h_adj_off.data();
+		if (adj)
+			*adj = h->h_adj.data();
+		return PFA_OK;
+	}
+
+	int pfa_pattern_device(pfa_handle *h, const int32_t **outer_dev, const int32_t **inner_dev)
+	{
+		if (!h)
+			return PFA_ERR_INVALID;
+		if (outer_dev)
+			*outer_dev = h->d_outer;
+		if (inner_dev)
+			*inner_dev = h->d_inner;
+		return PFA_OK;
+	}
+
+	int pfa_set_materials(pfa_handle *h, const double *lambda, const double *mu, int32_t material_stride)
+	{
+		if (!h)
+			return PFA_ERR_INVALID;
+		if (h->dm.material == PFA_LAPLACIAN)
+			return PFA_OK;
+		if (!lambda || !mu || material_stride != h->dm.mat_stride)
+			return fail(h, PFA_ERR_INVALID, "pfa_set_materials: NULL array or material_stride differs from pfa_create");
+		PFA_CUDA(h, cudaSetDevice(h->device));
+		const size_t cnt = size_t(h->dm.n_el) * size_t(h->dm.mat_stride) * sizeof(double);
+		PFA_CUDA(h, cudaMemcpyAsync(h->d_lambda, lambda, cnt, cudaMemcpyDefault, h->stream));
+		PFA_CUDA(h, cudaMemcpyAsync(h->d_mu, mu, cnt, cudaMemcpyDefault, h->stream));
+		PFA_CUDA(h, cudaStreamSynchronize(h->stream));
+		return PFA_OK;
+	}
+
+	int pfa_energy(pfa_handle *h, const double *x, double *energy)
+	{
+		if (!h || !energy)
+			return fail(h, PFA_ERR_INVALID, "pfa_energy: NULL argument");
+		return run_assemble(h, false, x, 0, energy, nullptr, nullptr, nullptr);
+	}
+
+	int pfa_energy_per_element(pfa_handle *h, const double *x, double *out)
+	{
+		if (!h || !out)
+			return fail(h, PFA_ERR_INVALID, "pfa_energy_per_element: NULL argument");
+		return run_assemble(h, false, x, 0, nullptr, out, nullptr, nullptr);
+	}
+
+	int pfa_gradient(pfa_handle *h, const double *x, double *grad)
+	{
+		if (!h || !grad)
+			return fail(h, PFA_ERR_INVALID, "pfa_gradient: NULL argument");
+		return run_assemble(h, false, x, 0, nullptr, nullptr, grad, nullptr);
+	}
+
+	int pfa_hessian(pfa_handle *h, const double *x, int project_to_psd, double *values)
+	{
+		if (!h || !values)
+			return fail(h, PFA_ERR_INVALID, "pfa_hessian: NULL argument");
+		return run_assemble(h, false, x, project_to_psd, nullptr, nullptr, nullptr, values);
+	}
+
+	int pfa_linear_stiffness(pfa_handle *h, double *values)
+	{
+		if (!h || !values)
+			return fail(h, PFA_ERR_INVALID, "pfa_linear_stiffness: NULL argument");
+		return run_assemble(h, true, nullptr, 0, nullptr, nullptr, nullptr, values);
+	}
+
+	int pfa_grad_hess(pfa_handle *h, const double *x, int project_to_psd, double *energy, double *grad, double *values)
+	{
+		if (!h)
+			return PFA_ERR_INVALID;
+		if (!energy && !grad && !values)
+			return fail(h, PFA_ERR_INVALID, "pfa_grad_hess: all outputs are NULL");
+		return run_assemble(h, false, x, project_to_psd, energy, nullptr, grad, values);
+	}
+
+	int pfa_synchronize(pfa_handle *h)
+	{
+		if (!h)
+			return PFA_ERR_INVALID;
+		PFA_CUDA(h, cudaSetDevice(h->device));
+		PFA_CUDA(h, cudaStreamSynchronize(h->stream));
+		return PFA_OK;
+	}
+
+	void *pfa_stream(pfa_handle *h) { return h ? (void *)h->stream : nullptr; }
+
+	int pfa_set_stream(pfa_handle *h, void *stream)
+	{
+		if (!h)
+			return PFA_ERR_INVALID;
+		PFA_CUDA(h, cudaSetDevice(h->device));
+		PFA_CUDA(h, cudaStreamSynchronize(h->stream));
+		if (h->own_stream && h->stream)
+			cudaStreamDestroy(h->stream);
+		h->stream = (cudaStream_t)stream;
+		h->own_stream = false;
+		return PFA_OK;
+	}
+
+	int pfa_profile_enable(pfa_handle *h, int on)
+	{
+		if (!h)
+			return PFA_ERR_INVALID;
+		h->profiling = on != 0;
+		return PFA_OK;
+	}
+
+	int pfa_profile_read(pfa_handle *h, int cap, const char **names, float *ms)
+	{
+		if (!h)
+			return PFA_ERR_INVALID;
+		PFA_CUDA(h, cudaSetDevice(h->device));
+		PFA_CUDA(h, cudaStreamSynchronize(h->stream));
+		h->prof_names.clear();
+		h->prof_ms.clear();
+		for (auto &r : h->prof)
+		{
+			float t = 0.f;
+			if (r.stop_recorded)
+				cudaEventElapsedTime(&t, r.start, r.stop);
+			h->prof_names.push_back(r.name);
+			h->prof_ms.push_back(t);
+		}
+		prof_reset(h);
+		const int n = int(h->prof_ms.size());
+		for (int i = 0; i < n && i < cap; ++i)
+		{
+			if (names)
+				names[i] = h->prof_names[i];
+			if (ms)
+				ms[i] = h->prof_ms[i];
+		}
+		return n;
+	}
+
+	int64_t pfa_launch_count(const pfa_handle *h) { return h ? h->launches : 0; }
+	double pfa_setup_seconds(const pfa_handle *h) { return h ? h->setup_seconds : 0.0; }
+}

@@ -1,0 +1,66 @@
+// Internal declarations shared by the C-ABI layer (pfa_api.cu), the host-side pattern /
+// slot-map builder (pfa_pattern.cu) and the kernels (pfa_kernels.cu).
+#pragma once
+#include "../../include/pfa.h"
+
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <string>
+#include <vector>
+
+namespace pfa
+{
+	// ---- what the kernels see (device pointers, SoA as described in DESIGN.md §Data layout) ----
+	struct DeviceMesh
+	{
+		int32_t material = 0;
+		int32_t size = 3; // dofs per node: 3 (elasticity) or 1 (Laplacian)
+		int32_t n_el = 0, n_loc = 0, n_bases = 0, n_qp = 0;
+		int32_t geom_per_qp = 0; // 0: affine, one J^-T/det per element; 1: one per (element, qp)
+		int32_t mat_stride = 1;  // 1 or n_qp
+
+		const int32_t *conn = nullptr;     // [n_el][n_loc]
+		const double *jit = nullptr;       // [n_el][gq][9] row-major J^-T
+		const double *detj = nullptr;      // [n_el][gq]   affine: det(J) ; per-qp: da = det*w
+		const double *lambda = nullptr;    // [n_el][mat_stride]
+		const double *mu = nullptr;        // [n_el][mat_stride]
+		const double *ref_grads = nullptr; // [n_qp][n_loc][3]
+		const double *qweights = nullptr;  // [n_qp]
+
+		// node-block CSR/CSC pattern (symmetric): adj_off[n_bases+1], adj[n_pairs] ascending
+		const int32_t *adj_off = nullptr;
+		const int32_t *adj = nullptr;
+		int64_t n_pairs = 0;
+		// slot map: pair index (into adj) of block (i,j) of element e: slot[e][i*n_loc+j],
+		// where the pair is (row node g_i) inside the column list of node g_j
+		const int32_t *slot = nullptr;
+	};
+
+	struct AssembleArgs
+	{
+		const double *x = nullptr;       // [ndof] device
+		double *energy = nullptr;        // device scalar (accumulated, must be zeroed by caller)
+		double *energy_per_el = nullptr; // [n_el]
+		double *grad = nullptr;          // [ndof] (accumulated, zeroed by caller)
+		double *values = nullptr;        // [nnz]  (accumulated, zeroed by caller)
+		int project_to_psd = 0;
+	};
+
+	// kernel launchers (pfa_kernels.cu). Return cudaError_t of the launch.
+	cudaError_t launch_geometry_precompute(const double *vertices_dev, int n_el, double *jit, double *detj, cudaStream_t st);
+	cudaError_t launch_expand_inner(const DeviceMesh &m, int32_t *outer, int32_t *inner, cudaStream_t st);
+	// fused per-element energy / gradient / Hessian with scatter (NLAssembler entry points);
+	// `linear` selects LinearAssembler::assemble semantics (x ignored).
+	cudaError_t launch_assemble(const DeviceMesh &m, const AssembleArgs &a, bool linear, int sm_count, cudaStream_t st, const char **kernel_name);
+	bool assemble_supported(const DeviceMesh &m);
+
+	// ---- host-side pattern + slot map (pfa_pattern.cu) ----
+	struct HostPattern
+	{
+		std::vector<int32_t> adj_off; // [n_bases+1]
+		std::vector<int32_t> adj;     // [n_pairs]
+		std::vector<int32_t> slot;    // [n_el][n_loc*n_loc]
+	};
+	// throws std::runtime_error on invalid connectivity
+	void build_pattern(const int32_t *conn, int n_el, int n_loc, int n_bases, HostPattern &out);
+} // namespace pfa

@@ -1,0 +1,123 @@
+// Host-side, once-per-mesh construction of the sparsity pattern and the slot map.
+//
+// Replaces the first-call path of SparseMatrixCache (reference utils/MatrixCache.cpp:88-100
+// triplet buffering, :115-132 prune/setFromTriplets, :134-213 mapping + second_cache): the
+// pattern is derived from connectivity alone. Because every element contributes the full
+// (g_i*size+m, g_j*size+n) block for every local pair (i,j) — explicit zeros included,
+// Assembler.cpp:712-737 — the scalar pattern is the node-adjacency pattern expanded by
+// size x size, which is what `adj_off/adj` encode (one entry per node pair instead of
+// size^2 scalar entries), and the slot map stores one int per local node pair instead of
+// the reference's one int per scalar contribution (MatrixCache.hpp:118).
+#include "pfa_internal.h"
+
+#include <algorithm>
+#include <stdexcept>
+#include <thread>
+
+namespace pfa
+{
+	namespace
+	{
+		template <typename F>
+		void parallel_ranges(int64_t n, F &&body)
+		{
+			unsigned hw = std::thread::hardware_concurrency();
+			int nt = int(std::max(1u, std::min(hw ? hw : 1u, 64u)));
+			if (n < 4096)
+				nt = 1;
+			std::vector<std::thread> pool;
+			for (int t = 0; t < nt; ++t)
+			{
+				const int64_t s = n * t / nt, e = n * (t + 1) / nt;
+				pool.emplace_back([=, &body]() { body(t, s, e); });
+			}
+			for (auto &th : pool)
+				th.join();
+		}
+	} // namespace
+
+	void build_pattern(const int32_t *conn, int n_el, int n_loc, int n_bases, HostPattern &out)
+	{
+		// node -> incident elements (counting sort)
+		std::vector<int64_t> ne_off(size_t(n_bases) + 1, 0);
+		for (int64_t k = 0; k < int64_t(n_el) * n_loc; ++k)
+		{
+			const int32_t g = conn[k];
+			if (g < 0 || g >= n_bases)
+				throw std::runtime_error("pfa: connectivity index out of range [0, n_bases)");
+			++ne_off[size_t(g) + 1];
+		}
+		for (int b = 0; b < n_bases; ++b)
+			ne_off[size_t(b) + 1] += ne_off[b];
+		std::vector<int32_t> node_el;
+		node_el.resize(size_t(ne_off[size_t(n_bases)]));
+		{
+			std::vector<int64_t> pos(ne_off.begin(), ne_off.end() - 1);
+			for (int e = 0; e < n_el; ++e)
+				for (int j = 0; j < n_loc; ++j)
+					node_el[size_t(pos[conn[size_t(e) * n_loc + j]]++)] = e;
+		}
+
+		// adjacency of every node = sorted union of the nodes of its incident elements
+		const int max_threads = 64; // parallel_ranges never uses more
+		std::vector<std::vector<int32_t>> part(max_threads);
+		std::vector<int32_t> deg(size_t(n_bases), 0);
+		parallel_ranges(n_bases, [&](int t, int64_t s, int64_t e) {
+			std::vector<int32_t> buf;
+			std::vector<int32_t> &mine = part[t];
+			for (int64_t b = s; b < e; ++b)
+			{
+				buf.clear();
+				for (int64_t k = ne_off[b]; k < ne_off[b + 1]; ++k)
+				{
+					const int32_t *c = conn + size_t(node_el[size_t(k)]) * n_loc;
+					buf.insert(buf.end(), c, c + n_loc);
+				}
+				std::sort(buf.begin(), buf.end());
+				buf.erase(std::unique(buf.begin(), buf.end()), buf.end());
+				deg[size_t(b)] = int32_t(buf.size());
+				mine.insert(mine.end(), buf.begin(), buf.end());
+			}
+		});
+		int64_t total = 0;
+		for (int b = 0; b < n_bases; ++b)
+			total += deg[b];
+		if (total >= (int64_t(1) << 31))
+			throw std::runtime_error("pfa: more than 2^31 node pairs; int32 StiffnessMatrix indices cannot hold this pattern");
+		out.adj_off.resize(size_t(n_bases) + 1);
+		out.adj_off[0] = 0;
+		for (int b = 0; b < n_bases; ++b)
+			out.adj_off[size_t(b) + 1] = out.adj_off[b] + deg[b];
+		out.adj.resize(size_t(total));
+		{
+			// parts are in node order (thread t handled a contiguous node range)
+			size_t at = 0;
+			for (auto &p : part)
+			{
+				std::copy(p.begin(), p.end(), out.adj.begin() + at);
+				at += p.size();
+				std::vector<int32_t>().swap(p);
+			}
+		}
+
+		// slot map: pair index of (row node g_i) in the column list of node g_j
+		const int nl2 = n_loc * n_loc;
+		out.slot.resize(size_t(n_el) * nl2);
+		parallel_ranges(n_el, [&](int, int64_t s, int64_t e) {
+			for (int64_t el = s; el < e; ++el)
+			{
+				const int32_t *c = conn + size_t(el) * n_loc;
+				for (int j = 0; j < n_loc; ++j)
+				{
+					const int32_t *lb = out.adj.data() + out.adj_off[c[j]];
+					const int32_t *le = out.adj.data() + out.adj_off[size_t(c[j]) + 1];
+					for (int i = 0; i < n_loc; ++i)
+					{
+						const int32_t *it = std::lower_bound(lb, le, c[i]);
+						out.slot[size_t(el) * nl2 + i * n_loc + j] = int32_t(it - out.adj.data());
+					}
+				}
+			}
+		});
+	}
+} // namespace pfa

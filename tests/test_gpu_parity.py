@@ -1,0 +1,175 @@
+"""GPU parity tests proper: CUDA path (through the C ABI) vs the CPU oracle on the same
+seeded inputs. Bars: pattern bit-exact; energy / gradient / Hessian values
+within 1e-12 relative (row-scale guarded); NaN <=> NaN."""
+import numpy as np
+import pytest
+
+from helpers import REL_TOL, assert_values_close, assert_vector_close, gpu_handle, make_case
+
+pytestmark = pytest.mark.gpu
+
+CASES = [(1, 4), (2, 3), (3, 2), (4, 1)]
+
+
+@pytest.mark.parametrize("p,n", CASES)
+def test_pattern_bit_exact(oracle, p, n):
+    mesh, x, t = make_case(n, p)
+    ref = oracle.problem_from_mesh(mesh, "LinearElasticity").assemble()
+    h = gpu_handle(mesh, "LinearElasticity", t)
+    outer, inner = h.pattern()
+    assert outer.dtype == np.int32 and inner.dtype == np.int32
+    assert outer.tobytes() == ref.outer.tobytes()
+    assert inner.tobytes() == ref.inner.tobytes()
+    lap = oracle.problem_from_mesh(mesh, "Laplacian").assemble()
+    hl = gpu_handle(mesh, "Laplacian", t)
+    o2, i2 = hl.pattern()
+    assert o2.tobytes() == lap.outer.tobytes() and i2.tobytes() == lap.inner.tobytes()
+
+
+@pytest.mark.parametrize("p,n", CASES[:3])
+@pytest.mark.parametrize("jitter", [0.0, 0.2])
+def test_neohookean_energy_gradient_hessian(oracle, p, n, jitter):
+    mesh, x, t = make_case(n, p, jitter=jitter)
+    ref = oracle.problem_from_mesh(mesh, "NeoHookean", n_threads=2)
+    h = gpu_handle(mesh, "NeoHookean", t)
+    e_ref, g_ref, H_ref = ref.assemble_energy(x), ref.assemble_gradient(x), ref.assemble_hessian(x)
+    assert abs(h.energy(x) - e_ref) <= REL_TOL * abs(e_ref)
+    assert_vector_close(h.gradient(x), g_ref)
+    assert_values_close(H_ref.outer, H_ref.inner, h.hessian(x), H_ref.values)
+    epe = h.energy_per_element(x)
+    epe_ref = ref.assemble_energy_per_element(x)
+    assert np.abs(epe - epe_ref).max() <= REL_TOL * np.abs(epe_ref).max()
+    # fused entry
+    e, g, v = h.grad_hess(x)
+    assert abs(e - e_ref) <= REL_TOL * abs(e_ref)
+    assert_vector_close(g, g_ref)
+    assert_values_close(H_ref.outer, H_ref.inner, v, H_ref.values)
+    # steady-state (slot-map) call of the oracle with another displacement, same handle
+    x2 = 0.3 * x
+    H2 = ref.assemble_hessian(x2)
+    assert_values_close(H2.outer, H2.inner, h.hessian(x2), H2.values)
+
+
+def test_neohookean_nan_propagation(oracle):
+    mesh, x, t = make_case(3, 2)
+    xi = x.copy()
+    nodes = mesh.conn[11]
+    xi.reshape(-1, 3)[nodes[1]] += 3.0 * (mesh.node_xyz[nodes[0]] - mesh.node_xyz[nodes[1]])
+    ref = oracle.problem_from_mesh(mesh, "NeoHookean")
+    h = gpu_handle(mesh, "NeoHookean", t)
+    e_ref = ref.assemble_energy(xi)
+    assert np.isnan(e_ref) and np.isnan(h.energy(xi))
+    g_ref, g = ref.assemble_gradient(xi), h.gradient(xi)
+    assert np.array_equal(np.isnan(g_ref), np.isnan(g)) and np.isnan(g).any()
+    assert_vector_close(g, g_ref)
+    H_ref = ref.assemble_hessian(xi)
+    assert_values_close(H_ref.outer, H_ref.inner, h.hessian(xi), H_ref.values)
+    assert np.array_equal(np.isnan(ref.assemble_energy_per_element(xi)), np.isnan(h.energy_per_element(xi)))
+
+
+@pytest.mark.parametrize("p,n", CASES)
+def test_linear_elasticity_stiffness_and_nl_path(oracle, p, n):
+    mesh, x, t = make_case(n, p, jitter=0.2)
+    ref = oracle.problem_from_mesh(mesh, "LinearElasticity", n_threads=2)
+    h = gpu_handle(mesh, "LinearElasticity", t)
+    K = ref.assemble()
+    assert_values_close(K.outer, K.inner, h.linear_stiffness(), K.values, what="stiffness")
+    if p <= 2:  # the oracle's autodiff NL path is O(N^2) per operation
+        e_ref, g_ref = ref.assemble_energy(x), ref.assemble_gradient(x)
+        assert abs(h.energy(x) - e_ref) <= REL_TOL * abs(e_ref)
+        assert_vector_close(h.gradient(x), g_ref)
+        H = ref.assemble_hessian(x)
+        assert_values_close(H.outer, H.inner, h.hessian(x), H.values)
+
+
+@pytest.mark.parametrize("p,n", CASES)
+def test_laplacian_stiffness(oracle, p, n):
+    mesh, x, t = make_case(n, p, jitter=0.2)
+    ref = oracle.problem_from_mesh(mesh, "Laplacian")
+    h = gpu_handle(mesh, "Laplacian", t)
+    assert h.size == 1 and h.ndof == mesh.n_bases
+    K = ref.assemble()
+    assert_values_close(K.outer, K.inner, h.linear_stiffness(), K.values, what="laplacian")
+
+
+def test_general_geometry_input_equals_affine(oracle):
+    """jac_it / da given per quadrature point (non-affine input form) reproduce the affine path."""
+    from polyfem_b200 import capi, mesh as M
+    mesh, x, t = make_case(3, 2, jitter=0.2)
+    e = mesh.vertices[:, 1:, :] - mesh.vertices[:, :1, :]
+    jit = np.linalg.inv(e).transpose(0, 2, 1)  # (J^-1)^T, J rows = edges
+    det = np.linalg.det(e)
+    nq = t["weights"].size
+    jac_it = np.repeat(jit[:, None, :, :], nq, axis=1).reshape(mesh.n_elements, nq, 9)
+    da = det[:, None] * t["weights"][None, :]
+    lam, mu = M.lame_from_E_nu(1e5, 0.3)
+    h = capi.Handle("NeoHookean", mesh.conn, mesh.n_bases, t["weights"], t["grad"], jac_it=jac_it, da=da, lam=lam, mu=mu)
+    ref = oracle.problem_from_mesh(mesh, "NeoHookean")
+    H = ref.assemble_hessian(x)
+    e1, g1, v1 = h.grad_hess(x)
+    assert abs(e1 - ref.assemble_energy(x)) <= REL_TOL * abs(e1)
+    assert_vector_close(g1, ref.assemble_gradient(x))
+    assert_values_close(H.outer, H.inner, v1, H.values)
+
+
+def test_per_element_and_per_qp_materials(oracle):
+    from polyfem_b200 import capi
+    mesh, x, t = make_case(2, 2)
+    rng = np.random.default_rng(9)
+    lam = rng.uniform(4e4, 8e4, mesh.n_elements)
+    mu = rng.uniform(2e4, 5e4, mesh.n_elements)
+    ref = oracle.OracleProblem("NeoHookean", mesh.conn, mesh.vertices, mesh.n_bases, t["points"], t["weights"], t["grad"], lam=lam, mu=mu)
+    H = ref.assemble_hessian(x)
+    h = capi.Handle("NeoHookean", mesh.conn, mesh.n_bases, t["weights"], t["grad"], vertices=mesh.vertices, lam=lam, mu=mu)
+    assert_values_close(H.outer, H.inner, h.hessian(x), H.values)
+    nq = t["weights"].size
+    h2 = capi.Handle("NeoHookean", mesh.conn, mesh.n_bases, t["weights"], t["grad"], vertices=mesh.vertices,
+                     lam=np.repeat(lam, nq), mu=np.repeat(mu, nq))
+    assert_values_close(H.outer, H.inner, h2.hessian(x), H.values)
+    # set_materials (t changed): back to constants
+    h.set_materials(np.full(mesh.n_elements, lam[0]), np.full(mesh.n_elements, mu[0]))
+    ref2 = oracle.OracleProblem("NeoHookean", mesh.conn, mesh.vertices, mesh.n_bases, t["points"], t["weights"], t["grad"], lam=lam[0], mu=mu[0])
+    H2 = ref2.assemble_hessian(x)
+    assert_values_close(H2.outer, H2.inner, h.hessian(x), H2.values)
+
+
+def test_device_pointers_and_profile(oracle):
+    import torch
+    mesh, x, t = make_case(3, 2)
+    h = gpu_handle(mesh, "NeoHookean", t)
+    ref = oracle.problem_from_mesh(mesh, "NeoHookean")
+    xd = torch.from_numpy(x).cuda()
+    e = torch.zeros(1, dtype=torch.float64, device="cuda")
+    g = torch.zeros(h.ndof, dtype=torch.float64, device="cuda")
+    v = torch.zeros(h.nnz, dtype=torch.float64, device="cuda")
+    h.profile_enable(True)
+    h.grad_hess_raw(xd, e, g, v)
+    h.synchronize()
+    recs = h.profile_read()
+    assert any("assemble" in r[0] for r in recs) and all(r[1] >= 0 for r in recs)
+    H = ref.assemble_hessian(x)
+    assert_values_close(H.outer, H.inner, v.cpu().numpy(), H.values)
+    assert_vector_close(g.cpu().numpy(), ref.assemble_gradient(x))
+    assert h.launch_count() >= 3
+
+
+def test_interface_mirror_reads_like_reference_test(oracle):
+    """tests/test_assembler.cpp:24-84 ("hessian_lin") through the mirrored operator interface."""
+    from polyfem_b200 import assembler as A, mesh as M
+    mesh = M.kuhn_cube(3, 2, jitter=0.1)
+    bases = gbases = A.FESpace.from_mesh(mesh)
+    cache = A.AssemblyValsCache(mesh.p)
+    asm = A.make_assembler("LinearElasticity")
+    asm.set_size(3)
+    asm.set_materials([], {"E": 1e5, "nu": 0.3})
+    n_basis = mesh.n_bases
+    stiffness = asm.assemble(True, n_basis, bases, gbases, cache, 0)
+    mat_cache = A.MatrixCache()
+    rng = np.random.default_rng(2)
+    for _ in range(10):
+        disp = rng.uniform(-1, 1, (n_basis * 3, 1))
+        hessian = asm.assemble_hessian(True, n_basis, False, bases, gbases, cache, 0, 0, disp, np.zeros(0), mat_cache)
+        assert np.array_equal(hessian.indices, stiffness.indices)
+        assert abs(hessian - stiffness).max() < 1e-8
+    with pytest.raises(RuntimeError):
+        A.make_assembler("MooneyRivlin")

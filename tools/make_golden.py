@@ -1,0 +1,103 @@
+#!/usr/bin/env python
+"""Regenerate the committed data/golden files from the reference's own sources.
+
+Runs only in the build container (needs /root/reference): `oracle/Makefile` compiles the
+reference's `autogen/auto_p_bases.cpp` and `quadrature/TetQuadrature.cpp` unmodified into
+`oracle/_ref/libpfref.so`; this script calls it and writes
+
+  polyfem_b200/data/tet_quadrature.json   tet rules, orders 1..8, hex floats (bit exact)
+  tests/golden/ref_tables.npz             reference P1..P4 nodes, values and gradients
+                                          evaluated by the reference's generated code at
+                                          the quadrature points of orders 1,2,4,6 and at 16
+                                          fixed interior points
+
+Nothing under tests/ or the product reads /root/reference at run time; they read these files.
+"""
+import ctypes
+import json
+import os
+import subprocess
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def load_ref():
+    subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "ref"])
+    lib = ctypes.CDLL(os.path.join(ROOT, "oracle", "_ref", "libpfref.so"))
+    dp = ctypes.POINTER(ctypes.c_double)
+    lib.pfref_tet_quadrature.argtypes = [ctypes.c_int, dp, dp, ctypes.c_int]
+    lib.pfref_p_nodes_3d.argtypes = [ctypes.c_int, dp, ctypes.c_int]
+    lib.pfref_p_basis_3d.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, dp, dp, dp]
+    return lib
+
+
+def ptr(a):
+    return a.ctypes.data_as(ctypes.POINTER(ctypes.c_double))
+
+
+def ref_quadrature(lib, order):
+    pts = np.zeros((512, 3))
+    w = np.zeros(512)
+    n = lib.pfref_tet_quadrature(order, ptr(pts), ptr(w), 512)
+    assert n > 0
+    return pts[:n].copy(), w[:n].copy()
+
+
+def ref_nodes(lib, p):
+    nodes = np.zeros((64, 3))
+    n = lib.pfref_p_nodes_3d(p, ptr(nodes), 64)
+    return nodes[:n].copy()
+
+
+def ref_basis(lib, p, pts):
+    pts = np.ascontiguousarray(pts, dtype=np.float64)
+    n_loc = ref_nodes(lib, p).shape[0]
+    val = np.zeros((pts.shape[0], n_loc))
+    grad = np.zeros((pts.shape[0], n_loc, 3))
+    for li in range(n_loc):
+        v = np.zeros(pts.shape[0])
+        g = np.zeros((pts.shape[0], 3))
+        lib.pfref_p_basis_3d(p, li, pts.shape[0], ptr(pts), ptr(v), ptr(g))
+        val[:, li] = v
+        grad[:, li, :] = g
+    return val, grad
+
+
+def main():
+    lib = load_ref()
+    quad = {"source": "polyfem autogen/auto_tetrahedron.ipp via quadrature/TetQuadrature.cpp (weights /= 6)",
+            "orders": {}}
+    for order in range(1, 9):
+        pts, w = ref_quadrature(lib, order)
+        quad["orders"][str(order)] = {
+            "points": [[float(c).hex() for c in row] for row in pts],
+            "weights": [float(c).hex() for c in w],
+        }
+    os.makedirs(os.path.join(ROOT, "polyfem_b200", "data"), exist_ok=True)
+    with open(os.path.join(ROOT, "polyfem_b200", "data", "tet_quadrature.json"), "w") as f:
+        json.dump(quad, f, indent=0)
+
+    rng = np.random.default_rng(20261017)
+    bary = rng.dirichlet(np.ones(4), size=16)
+    extra = bary[:, 1:4].copy()
+    gold = {"extra_points": extra}
+    for p in (1, 2, 3, 4):
+        gold[f"nodes_p{p}"] = ref_nodes(lib, p)
+        for order in (1, 2, 4, 6, 8):
+            pts, w = ref_quadrature(lib, order)
+            v, g = ref_basis(lib, p, pts)
+            gold[f"val_p{p}_q{order}"] = v
+            gold[f"grad_p{p}_q{order}"] = g
+        v, g = ref_basis(lib, p, extra)
+        gold[f"val_p{p}_extra"] = v
+        gold[f"grad_p{p}_extra"] = g
+    os.makedirs(os.path.join(ROOT, "tests", "golden"), exist_ok=True)
+    np.savez_compressed(os.path.join(ROOT, "tests", "golden", "ref_tables.npz"), **gold)
+    print("wrote tet_quadrature.json and tests/golden/ref_tables.npz")
+
+
+if __name__ == "__main__":
+    sys.exit(main())
