@@ -29,10 +29,12 @@ def test_pattern_bit_exact(oracle, p, n):
 @pytest.mark.parametrize("p,n", CASES[:3])
 @pytest.mark.parametrize("jitter", [0.0, 0.2])
 def test_neohookean_energy_gradient_hessian(oracle, p, n, jitter):
-    mesh, x, t = make_case(n, p, jitter=jitter)
+    # P3 bases overshoot between nodes: keep the random field small enough that det F > 0
+    mesh, x, t = make_case(n, p, jitter=jitter, scale=0.05 if p < 3 else 0.01)
     ref = oracle.problem_from_mesh(mesh, "NeoHookean", n_threads=2)
     h = gpu_handle(mesh, "NeoHookean", t)
     e_ref, g_ref, H_ref = ref.assemble_energy(x), ref.assemble_gradient(x), ref.assemble_hessian(x)
+    assert np.isfinite(e_ref)
     assert abs(h.energy(x) - e_ref) <= REL_TOL * abs(e_ref)
     assert_vector_close(h.gradient(x), g_ref)
     assert_values_close(H_ref.outer, H_ref.inner, h.hessian(x), H_ref.values)
