@@ -397,6 +397,299 @@ namespace pfa
 			}
 		}
 
+		// ------------------------------------------------------------------------------------
+		// NeoHookean kernel for n_qp in {1, 4} (P1, P2 tets): "row-lane" mapping.
+		//  phase 1  lane <-> (element, quadrature point): 32/NQ elements per warp batch. Gathers
+		//           x, builds F, stress and the Hessian coefficients in registers, leaves per
+		//           (element, qp) records {D_i, C D_i, c2 da F, mu da, c1 da} in shared memory;
+		//           gradient and energy are reduced over the qp lanes with shuffles.
+		//  phase 2  lane <-> (local node i, component m) of one element: the lane keeps its row's
+		//           data in registers, walks the column nodes j (records broadcast from shared
+		//           memory) and produces H[(i,m),(j,0..2)]. The three m-lanes of a node write three
+		//           consecutive doubles and the NL nodes of the element hit one CSC column segment
+		//           per RED instruction, which minimises L2 sector operations.
+		// ------------------------------------------------------------------------------------
+		template <int NL, int NQ>
+		struct RowLane
+		{
+			static constexpr int EB = 32 / NQ;      // elements per phase-1 batch
+			static constexpr int REC = NL * 6 + 12; // doubles per (element, qp) record
+			static constexpr int ROWL = 3 * NL;     // phase-2 lanes per element
+			static constexpr int EPW = 32 / ROWL;   // elements per phase-2 round
+			static constexpr int WARP_DOUBLES = EB * NQ * REC;
+			static constexpr int WARP_INTS = EB * NL * 3;
+			static size_t smem_bytes(int warps)
+			{
+				return sizeof(double) * (size_t(NQ) * NL * 3 + ((NQ + 1) & ~1) + size_t(warps) * WARP_DOUBLES) + sizeof(int) * size_t(warps) * WARP_INTS;
+			}
+		};
+
+		template <int NL, int NQ, int WARPS>
+		__global__ void __launch_bounds__(WARPS * 32) assemble_nh_rowlane_kernel(const DeviceMesh m, const AssembleArgs a)
+		{
+			using RL = RowLane<NL, NQ>;
+			constexpr int EB = RL::EB, REC = RL::REC, ROWL = RL::ROWL, EPW = RL::EPW;
+			extern __shared__ double smem[];
+			const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+			double *s_rg = smem;               // [NQ][NL][3]
+			double *s_w = s_rg + NQ * NL * 3;  // [NQ]
+			double *s_rec = s_w + ((NQ + 1) & ~1) + warp * RL::WARP_DOUBLES;
+			int *s_int = reinterpret_cast<int *>(s_w + ((NQ + 1) & ~1) + WARPS * RL::WARP_DOUBLES) + warp * RL::WARP_INTS;
+			int *sG = s_int, *sOff = s_int + EB * NL, *sDeg = s_int + 2 * EB * NL;
+			for (int t = threadIdx.x; t < NQ * NL * 3; t += WARPS * 32)
+				s_rg[t] = m.ref_grads[t];
+			for (int t = threadIdx.x; t < NQ; t += WARPS * 32)
+				s_w[t] = m.qweights[t];
+			__syncthreads();
+
+			const bool want_h = a.values != nullptr;
+			const bool want_g = a.grad != nullptr;
+			const bool want_e = a.energy != nullptr || a.energy_per_el != nullptr;
+			double energy_acc = 0.0;
+			const int el = lane / NQ, q = lane % NQ;
+			const int stride = gridDim.x * WARPS * EB;
+
+			for (int batch = (blockIdx.x * WARPS + warp) * EB; batch < m.n_el; batch += stride)
+			{
+				// ---- connectivity and pattern offsets of the batch ----
+				for (int t = lane; t < EB * NL; t += 32)
+				{
+					const int ee = batch + t / NL;
+					if (ee < m.n_el)
+					{
+						const int g = m.conn[size_t(ee) * NL + (t % NL)];
+						const int o = m.adj_off[g];
+						sG[t] = g;
+						sOff[t] = o;
+						sDeg[t] = m.adj_off[g + 1] - o;
+					}
+				}
+				__syncwarp();
+
+				// ---- phase 1 ----
+				const int e = batch + el;
+				const bool valid = e < m.n_el;
+				double G[NL * 3];
+#pragma unroll
+				for (int t = 0; t < NL * 3; ++t)
+					G[t] = 0.0;
+				double e_q = 0.0;
+				if (valid)
+				{
+					double *rec = s_rec + (el * NQ + q) * REC;
+					const size_t gi = m.geom_per_qp ? size_t(e) * NQ + q : size_t(e);
+					double J[9];
+#pragma unroll
+					for (int k = 0; k < 9; ++k)
+						J[k] = m.jit[gi * 9 + k];
+					const double da = m.geom_per_qp ? m.detj[gi] : m.detj[e] * s_w[q];
+					const size_t mi = size_t(e) * m.mat_stride + (m.mat_stride == 1 ? 0 : q);
+					const double lam = m.lambda[mi], mu = m.mu[mi];
+					double F[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+#pragma unroll
+					for (int i = 0; i < NL; ++i)
+					{
+						const int g = sG[el * NL + i];
+						const double u0 = a.x[size_t(g) * 3 + 0], u1 = a.x[size_t(g) * 3 + 1], u2 = a.x[size_t(g) * 3 + 2];
+						const double *r = s_rg + (q * NL + i) * 3;
+						const double d0 = r[0] * J[0] + r[1] * J[3] + r[2] * J[6];
+						const double d1 = r[0] * J[1] + r[1] * J[4] + r[2] * J[7];
+						const double d2 = r[0] * J[2] + r[1] * J[5] + r[2] * J[8];
+						rec[i * 6 + 0] = d0;
+						rec[i * 6 + 1] = d1;
+						rec[i * 6 + 2] = d2;
+						F[0] += u0 * d0;
+						F[1] += u0 * d1;
+						F[2] += u0 * d2;
+						F[3] += u1 * d0;
+						F[4] += u1 * d1;
+						F[5] += u1 * d2;
+						F[6] += u2 * d0;
+						F[7] += u2 * d1;
+						F[8] += u2 * d2;
+					}
+					const double Jd = det3(F);
+					const double lJ = log(Jd); // NaN for J <= 0, propagates like the reference
+					double C[9];
+					cofactor3(F, C);
+					const double invJ = 1.0 / Jd;
+					const double pc = (lam * lJ - mu) * invJ; // P = mu F + pc C ; c2 = pc
+					double P[9], sq = 0.0;
+#pragma unroll
+					for (int k = 0; k < 9; ++k)
+					{
+						sq += F[k] * F[k];
+						P[k] = (mu * F[k] + pc * C[k]) * da;
+						rec[NL * 6 + k] = pc * da * F[k];
+					}
+					rec[NL * 6 + 9] = mu * da;
+					rec[NL * 6 + 10] = (mu + lam * (1.0 - lJ)) * invJ * invJ * da;
+					e_q = (0.5 * mu * (sq - 3.0 - 2.0 * lJ) + 0.5 * lam * lJ * lJ) * da;
+#pragma unroll
+					for (int i = 0; i < NL; ++i)
+					{
+						const double d0 = rec[i * 6 + 0], d1 = rec[i * 6 + 1], d2 = rec[i * 6 + 2];
+						rec[i * 6 + 3] = C[0] * d0 + C[1] * d1 + C[2] * d2;
+						rec[i * 6 + 4] = C[3] * d0 + C[4] * d1 + C[5] * d2;
+						rec[i * 6 + 5] = C[6] * d0 + C[7] * d1 + C[8] * d2;
+						G[i * 3 + 0] = d0 * P[0] + d1 * P[1] + d2 * P[2];
+						G[i * 3 + 1] = d0 * P[3] + d1 * P[4] + d2 * P[5];
+						G[i * 3 + 2] = d0 * P[6] + d1 * P[7] + d2 * P[8];
+					}
+				}
+				if (want_e)
+				{
+#pragma unroll
+					for (int k = 1; k < NQ; k <<= 1)
+						e_q += __shfl_xor_sync(0xffffffffu, e_q, k);
+					if (valid && q == 0)
+					{
+						energy_acc += e_q;
+						if (a.energy_per_el != nullptr)
+							a.energy_per_el[e] = e_q;
+					}
+				}
+				if (want_g)
+				{
+#pragma unroll
+					for (int t = 0; t < NL * 3; ++t)
+					{
+#pragma unroll
+						for (int k = 1; k < NQ; k <<= 1)
+							G[t] += __shfl_xor_sync(0xffffffffu, G[t], k);
+					}
+#pragma unroll
+					for (int i = 0; i < NL; ++i)
+						if (valid && (i % NQ) == q)
+						{
+							double *dst = a.grad + size_t(sG[el * NL + i]) * 3;
+							atomicAdd(dst + 0, G[i * 3 + 0]);
+							atomicAdd(dst + 1, G[i * 3 + 1]);
+							atomicAdd(dst + 2, G[i * 3 + 2]);
+						}
+				}
+				__syncwarp();
+
+				// ---- phase 2 ----
+				if (want_h)
+				{
+					const int sub = lane / ROWL, r = lane % ROWL;
+					const int i = r / 3, mm = r % 3;
+					const int ra = (mm + 1) % 3, rb = (mm + 2) % 3;
+					for (int eb = 0; eb < EB; eb += EPW)
+					{
+						const int el2 = eb + sub;
+						const int e2 = batch + el2;
+						if (lane < EPW * ROWL && el2 < EB && e2 < m.n_el)
+						{
+							// row-side registers: mu da D_i, c1 da (C D_i)_m, rows (m+1)%3,(m+2)%3 of c2 da F x D_i
+							double Dp[NQ][3], cA[NQ], Ma[NQ][3], Mb[NQ][3];
+#pragma unroll
+							for (int qq = 0; qq < NQ; ++qq)
+							{
+								const double *rec = s_rec + (el2 * NQ + qq) * REC;
+								const double d0 = rec[i * 6 + 0], d1 = rec[i * 6 + 1], d2 = rec[i * 6 + 2];
+								const double mu_da = rec[NL * 6 + 9], c1_da = rec[NL * 6 + 10];
+								const double *fa = rec + NL * 6 + ra * 3, *fb = rec + NL * 6 + rb * 3;
+								Dp[qq][0] = mu_da * d0;
+								Dp[qq][1] = mu_da * d1;
+								Dp[qq][2] = mu_da * d2;
+								cA[qq] = c1_da * rec[i * 6 + 3 + mm];
+								Ma[qq][0] = fa[1] * d2 - fa[2] * d1;
+								Ma[qq][1] = fa[2] * d0 - fa[0] * d2;
+								Ma[qq][2] = fa[0] * d1 - fa[1] * d0;
+								Mb[qq][0] = fb[1] * d2 - fb[2] * d1;
+								Mb[qq][1] = fb[2] * d0 - fb[0] * d2;
+								Mb[qq][2] = fb[0] * d1 - fb[1] * d0;
+							}
+							const int32_t *slot = m.slot + size_t(e2) * NL * NL + i * NL;
+#pragma unroll 2
+							for (int j = 0; j < NL; ++j)
+							{
+								double s = 0.0, R0 = 0.0, R1 = 0.0, R2 = 0.0, wa = 0.0, wb = 0.0;
+#pragma unroll
+								for (int qq = 0; qq < NQ; ++qq)
+								{
+									const double2 *nj = reinterpret_cast<const double2 *>(s_rec + (el2 * NQ + qq) * REC + j * 6);
+									const double2 v0 = nj[0], v1 = nj[1], v2 = nj[2]; // D0 D1 | D2 A0 | A1 A2
+									s += Dp[qq][0] * v0.x + Dp[qq][1] * v0.y + Dp[qq][2] * v1.x;
+									R0 += cA[qq] * v1.y;
+									R1 += cA[qq] * v2.x;
+									R2 += cA[qq] * v2.y;
+									wa += Ma[qq][0] * v0.x + Ma[qq][1] * v0.y + Ma[qq][2] * v1.x;
+									wb += Mb[qq][0] * v0.x + Mb[qq][1] * v0.y + Mb[qq][2] * v1.x;
+								}
+								// row m of  R + s I - hat(w):  out[m] += s, out[(m+1)%3] += w_{(m+2)%3}, out[(m+2)%3] -= w_{(m+1)%3}
+								if (mm == 0)
+								{
+									R0 += s;
+									R1 += wb;
+									R2 -= wa;
+								}
+								else if (mm == 1)
+								{
+									R1 += s;
+									R2 += wb;
+									R0 -= wa;
+								}
+								else
+								{
+									R2 += s;
+									R0 += wb;
+									R1 -= wa;
+								}
+								const int off = sOff[el2 * NL + j], deg = sDeg[el2 * NL + j];
+								double *dst = a.values + (size_t(off) * 9 + size_t(slot[j] - off) * 3 + mm);
+								atomicAdd(dst, R0);
+								atomicAdd(dst + size_t(3) * deg, R1);
+								atomicAdd(dst + size_t(6) * deg, R2);
+							}
+						}
+					}
+				}
+				__syncwarp();
+			}
+
+			if (want_e && a.energy != nullptr)
+			{
+				__shared__ double s_e[WARPS];
+#pragma unroll
+				for (int o = 16; o > 0; o >>= 1)
+					energy_acc += __shfl_xor_sync(0xffffffffu, energy_acc, o);
+				if (lane == 0)
+					s_e[warp] = energy_acc;
+				__syncthreads();
+				if (threadIdx.x == 0)
+				{
+					double t = 0.0;
+					for (int w = 0; w < WARPS; ++w)
+						t += s_e[w];
+					atomicAdd(a.energy, t);
+				}
+			}
+		}
+
+		template <int NL, int NQ, int WARPS>
+		cudaError_t launch_rowlane(const DeviceMesh &m, const AssembleArgs &a, int sm_count, cudaStream_t st)
+		{
+			using RL = RowLane<NL, NQ>;
+			const size_t smem = RL::smem_bytes(WARPS);
+			auto kern = assemble_nh_rowlane_kernel<NL, NQ, WARPS>;
+			cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+			if (err != cudaSuccess)
+				return err;
+			int per_sm = 1;
+			err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, WARPS * 32, smem);
+			if (err != cudaSuccess)
+				return err;
+			if (per_sm < 1)
+				per_sm = 1;
+			const int64_t need = (int64_t(m.n_el) + WARPS * RL::EB - 1) / (WARPS * RL::EB);
+			const int grid = int(std::max<int64_t>(1, std::min<int64_t>(need, int64_t(sm_count) * per_sm)));
+			kern<<<grid, WARPS * 32, smem, st>>>(m, a);
+			return cudaGetLastError();
+		}
+
 		constexpr size_t kMaxSmem = 227 * 1024;
 
 		size_t generic_smem_bytes(int n_loc, int n_qp, int warps)
@@ -479,6 +772,18 @@ namespace pfa
 		switch (m.material)
 		{
 		case PFA_NEOHOOKEAN:
+			if (m.n_loc == 10 && m.n_qp == 4)
+			{
+				if (kernel_name)
+					*kernel_name = "assemble_nh_rowlane_kernel<10,4>";
+				return launch_rowlane<10, 4, 5>(m, a, sm_count, st);
+			}
+			if (m.n_loc == 4 && m.n_qp == 1)
+			{
+				if (kernel_name)
+					*kernel_name = "assemble_nh_rowlane_kernel<4,1>";
+				return launch_rowlane<4, 1, 8>(m, a, sm_count, st);
+			}
 			return launch_generic<PFA_NEOHOOKEAN, false>(m, a, sm_count, st);
 		case PFA_LINEAR_ELASTICITY:
 			return linear ? launch_generic<PFA_LINEAR_ELASTICITY, true>(m, a, sm_count, st)
