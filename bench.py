@@ -256,7 +256,8 @@ def main():
     b_alg = b_alg_bytes_per_element(h.n_loc, h.ndof, h.nnz, h.n_elements)
     achieved = b_alg * h.n_elements / (kern_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "kernel": "assemble_generic_kernel", "kernel_ms": kern_ms,
+                "traffic": None, "kernel": sorted({name for (name, ms) in recs if "assemble" in name})[0] if kern else None,
+                "kernel_ms": kern_ms,
                 "zero_fill_ms": float(np.mean(fill)) if fill else 0.0,
                 "algorithmic_bytes_per_element": b_alg, "peak_source": peak_src + " (of measured)"}
 

@@ -13,6 +13,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libpfa.so")
+# experiment hook: PFA_DEFS="-DFOO=1 ..." PFA_LIB_SUFFIX=_foo builds polyfem_b200/libpfa_foo.so
 SOURCES = ["pfa_api.cu", "pfa_pattern.cu", "pfa_kernels.cu"]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "--use_fast_math=false"]
@@ -34,14 +35,17 @@ def _stale():
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and not _stale():
+    suffix = os.environ.get("PFA_LIB_SUFFIX", "")
+    defs = os.environ.get("PFA_DEFS", "").split()
+    lib = LIB if not suffix else os.path.join(HERE, f"libpfa{suffix}.so")
+    if not force and not suffix and not _stale():
         return LIB
     nvcc = _nvcc()
-    flags = [f for f in FLAGS if not f.startswith("--use_fast_math")]
+    flags = [f for f in FLAGS if not f.startswith("--use_fast_math")] + defs
     objs = []
     procs = []
     for src in SOURCES:
-        obj = os.path.join(CSRC, src.replace(".cu", ".o"))
+        obj = os.path.join(CSRC, src.replace(".cu", f"{suffix}.o"))
         cmd = [nvcc, *ARCH, *flags, "-Xptxas", "-v" if verbose else "-warn-spills", "-c", os.path.join(CSRC, src), "-o", obj]
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
         objs.append(obj)
@@ -51,8 +55,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
             sys.stderr.write(out)
         if p.returncode != 0:
             raise RuntimeError(f"nvcc failed on {src}")
-    subprocess.check_call([nvcc, *ARCH, "-shared", "-o", LIB, *objs, "-lcudart"])
-    return LIB
+    subprocess.check_call([nvcc, *ARCH, "-shared", "-o", lib, *objs, "-lcudart"])
+    return lib
 
 
 if __name__ == "__main__":

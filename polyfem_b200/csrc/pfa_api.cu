@@ -41,6 +41,7 @@ struct pfa_handle
 	// staging for host-pointer calls (allocated on first use)
 	double *s_x = nullptr, *s_grad = nullptr, *s_values = nullptr, *s_epe = nullptr;
 	double *d_energy = nullptr;
+	int *d_counter = nullptr;
 
 	std::vector<int32_t> h_outer, h_inner;
 	std::vector<int32_t> h_adj_off, h_adj;
@@ -232,6 +233,8 @@ namespace
 		a.grad = og.dev;
 		a.values = ov.dev;
 		a.project_to_psd = project_to_psd;
+		a.work_counter = h->d_counter;
+		PFA_CUDA(h, cudaMemsetAsync(h->d_counter, 0, 4 * sizeof(int), h->stream));
 
 		// outputs are accumulated with atomics: zero them first (rhs.setZero / set_zero,
 		// Assembler.cpp:586-587, 666-667)
@@ -417,7 +420,7 @@ extern "C"
 			UP(m.detj, d->da, ne * nq, double);
 		}
 #undef UP
-		if ((rc = dev_alloc<int32_t>(h, &h->d_outer, size_t(h->ndof) + 1)) != PFA_OK || (rc = dev_alloc<int32_t>(h, &h->d_inner, size_t(h->nnz))) != PFA_OK || (rc = dev_alloc<double>(h, &h->d_energy, 1)) != PFA_OK)
+		if ((rc = dev_alloc<int32_t>(h, &h->d_outer, size_t(h->ndof) + 1)) != PFA_OK || (rc = dev_alloc<int32_t>(h, &h->d_inner, size_t(h->nnz))) != PFA_OK || (rc = dev_alloc<double>(h, &h->d_energy, 1)) != PFA_OK || (rc = dev_alloc<int>(h, &h->d_counter, 4)) != PFA_OK)
 			return bail(rc);
 		{
 			++h->launches;

@@ -44,6 +44,7 @@ namespace pfa
 		double *grad = nullptr;          // [ndof] (accumulated, zeroed by caller)
 		double *values = nullptr;        // [nnz]  (accumulated, zeroed by caller)
 		int project_to_psd = 0;
+		int *work_counter = nullptr; // device int, zeroed before the launch (dynamic batch hand-out)
 	};
 
 	// kernel launchers (pfa_kernels.cu). Return cudaError_t of the launch.

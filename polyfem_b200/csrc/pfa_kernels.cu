@@ -409,15 +409,22 @@ namespace pfa
 		//           consecutive doubles and the NL nodes of the element hit one CSC column segment
 		//           per RED instruction, which minimises L2 sector operations.
 		// ------------------------------------------------------------------------------------
+#ifndef PFA_RL_PAD
+#define PFA_RL_PAD 14
+#endif
+#ifndef PFA_RL_WARPS_P2
+#define PFA_RL_WARPS_P2 4
+#endif
 		template <int NL, int NQ>
 		struct RowLane
 		{
 			static constexpr int EB = 32 / NQ;      // elements per phase-1 batch
-			static constexpr int REC = NL * 6 + 12; // doubles per (element, qp) record
+			static constexpr int REC = NL * 6 + PFA_RL_PAD; // doubles per (element, qp) record; (REC mod 16) = 6/10 keeps the
+			                                        // lane-strided phase-1 stores at 2-way bank conflicts, 16-byte aligned
 			static constexpr int ROWL = 3 * NL;     // phase-2 lanes per element
 			static constexpr int EPW = 32 / ROWL;   // elements per phase-2 round
 			static constexpr int WARP_DOUBLES = EB * NQ * REC;
-			static constexpr int WARP_INTS = EB * NL * 3;
+			static constexpr int WARP_INTS = EB * NL * 3 + EB * NL * NL; // g, off, deg per node + slot per pair
 			static size_t smem_bytes(int warps)
 			{
 				return sizeof(double) * (size_t(NQ) * NL * 3 + ((NQ + 1) & ~1) + size_t(warps) * WARP_DOUBLES) + sizeof(int) * size_t(warps) * WARP_INTS;
@@ -435,7 +442,7 @@ namespace pfa
 			double *s_w = s_rg + NQ * NL * 3;  // [NQ]
 			double *s_rec = s_w + ((NQ + 1) & ~1) + warp * RL::WARP_DOUBLES;
 			int *s_int = reinterpret_cast<int *>(s_w + ((NQ + 1) & ~1) + WARPS * RL::WARP_DOUBLES) + warp * RL::WARP_INTS;
-			int *sG = s_int, *sOff = s_int + EB * NL, *sDeg = s_int + 2 * EB * NL;
+			int *sG = s_int, *sOff = s_int + EB * NL, *sDeg = s_int + 2 * EB * NL, *sSlot = s_int + 3 * EB * NL;
 			for (int t = threadIdx.x; t < NQ * NL * 3; t += WARPS * 32)
 				s_rg[t] = m.ref_grads[t];
 			for (int t = threadIdx.x; t < NQ; t += WARPS * 32)
@@ -447,10 +454,17 @@ namespace pfa
 			const bool want_e = a.energy != nullptr || a.energy_per_el != nullptr;
 			double energy_acc = 0.0;
 			const int el = lane / NQ, q = lane % NQ;
-			const int stride = gridDim.x * WARPS * EB;
 
-			for (int batch = (blockIdx.x * WARPS + warp) * EB; batch < m.n_el; batch += stride)
+			// batches are handed out dynamically (one atomic per warp and batch) so that SMs slowed
+			// down by L2 contention do not leave a tail
+			for (;;)
 			{
+				int batch = 0;
+				if (lane == 0)
+					batch = atomicAdd(a.work_counter, EB);
+				batch = __shfl_sync(0xffffffffu, batch, 0);
+				if (batch >= m.n_el)
+					break;
 				// ---- connectivity and pattern offsets of the batch ----
 				for (int t = lane; t < EB * NL; t += 32)
 				{
@@ -463,6 +477,13 @@ namespace pfa
 						sOff[t] = o;
 						sDeg[t] = m.adj_off[g + 1] - o;
 					}
+				}
+				if (want_h)
+				{
+					const int n_batch = min(EB, m.n_el - batch);
+					const int32_t *src = m.slot + size_t(batch) * NL * NL;
+					for (int t = lane; t < n_batch * NL * NL; t += 32)
+						sSlot[t] = src[t];
 				}
 				__syncwarp();
 
@@ -602,8 +623,12 @@ namespace pfa
 								Mb[qq][1] = fb[2] * d0 - fb[0] * d2;
 								Mb[qq][2] = fb[0] * d1 - fb[1] * d0;
 							}
-							const int32_t *slot = m.slot + size_t(e2) * NL * NL + i * NL;
-#pragma unroll 2
+#ifndef PFA_RL_UNROLL_J
+#define PFA_RL_UNROLL_J 10
+#endif
+							const int *sl = sSlot + el2 * NL * NL + i * NL;
+							constexpr int kUnrollJ = PFA_RL_UNROLL_J;
+#pragma unroll kUnrollJ
 							for (int j = 0; j < NL; ++j)
 							{
 								double s = 0.0, R0 = 0.0, R1 = 0.0, R2 = 0.0, wa = 0.0, wb = 0.0;
@@ -612,12 +637,18 @@ namespace pfa
 								{
 									const double2 *nj = reinterpret_cast<const double2 *>(s_rec + (el2 * NQ + qq) * REC + j * 6);
 									const double2 v0 = nj[0], v1 = nj[1], v2 = nj[2]; // D0 D1 | D2 A0 | A1 A2
-									s += Dp[qq][0] * v0.x + Dp[qq][1] * v0.y + Dp[qq][2] * v1.x;
-									R0 += cA[qq] * v1.y;
-									R1 += cA[qq] * v2.x;
-									R2 += cA[qq] * v2.y;
-									wa += Ma[qq][0] * v0.x + Ma[qq][1] * v0.y + Ma[qq][2] * v1.x;
-									wb += Mb[qq][0] * v0.x + Mb[qq][1] * v0.y + Mb[qq][2] * v1.x;
+									s = fma(Dp[qq][0], v0.x, s);
+									s = fma(Dp[qq][1], v0.y, s);
+									s = fma(Dp[qq][2], v1.x, s);
+									R0 = fma(cA[qq], v1.y, R0);
+									R1 = fma(cA[qq], v2.x, R1);
+									R2 = fma(cA[qq], v2.y, R2);
+									wa = fma(Ma[qq][0], v0.x, wa);
+									wa = fma(Ma[qq][1], v0.y, wa);
+									wa = fma(Ma[qq][2], v1.x, wa);
+									wb = fma(Mb[qq][0], v0.x, wb);
+									wb = fma(Mb[qq][1], v0.y, wb);
+									wb = fma(Mb[qq][2], v1.x, wb);
 								}
 								// row m of  R + s I - hat(w):  out[m] += s, out[(m+1)%3] += w_{(m+2)%3}, out[(m+2)%3] -= w_{(m+1)%3}
 								if (mm == 0)
@@ -639,7 +670,7 @@ namespace pfa
 									R1 -= wa;
 								}
 								const int off = sOff[el2 * NL + j], deg = sDeg[el2 * NL + j];
-								double *dst = a.values + (size_t(off) * 9 + size_t(slot[j] - off) * 3 + mm);
+								double *dst = a.values + (size_t(off) * 9 + size_t(sl[j] - off) * 3 + mm);
 								atomicAdd(dst, R0);
 								atomicAdd(dst + size_t(3) * deg, R1);
 								atomicAdd(dst + size_t(6) * deg, R2);
@@ -776,7 +807,7 @@ namespace pfa
 			{
 				if (kernel_name)
 					*kernel_name = "assemble_nh_rowlane_kernel<10,4>";
-				return launch_rowlane<10, 4, 5>(m, a, sm_count, st);
+				return launch_rowlane<10, 4, PFA_RL_WARPS_P2>(m, a, sm_count, st);
 			}
 			if (m.n_loc == 4 && m.n_qp == 1)
 			{
