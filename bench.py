@@ -263,7 +263,9 @@ def main():
 
     # e2e through the C ABI with pinned HOST buffers (H2D x, D2H E + grad + values every step)
     e2e = None
-    if world == 1:
+    if args.e2e_steps <= 0:
+        e2e = None
+    elif world == 1:
         xh = torch.from_numpy(x_loc).pin_memory()
         eh = torch.zeros(1, dtype=torch.float64).pin_memory()
         gh = torch.zeros(h.ndof, dtype=torch.float64).pin_memory()
