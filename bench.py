@@ -174,6 +174,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--cpu-sample-n", type=int, default=12)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--flags", type=int, default=0, help="pfa_mesh_desc.flags (1 = keep the caller's element order)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -200,7 +201,7 @@ def main():
     lam, mu = lame_from_E_nu(E_MOD, NU)
     part = pdist.partition_elements(mesh, rank, world)
     h = capi.Handle("NeoHookean", part.conn, part.n_bases, t["weights"], t["grad"], vertices=part.vertices,
-                    lam=lam, mu=mu, device=local_rank, n_ghost_elements=part.n_ghost_elements)
+                    lam=lam, mu=mu, device=local_rank, n_ghost_elements=part.n_ghost_elements, flags=args.flags)
     h.set_stream(torch.cuda.current_stream().cuda_stream)
     exch = pdist.InterfaceExchange(h, part, rank, world, dev) if world > 1 else None
 

@@ -86,13 +86,17 @@ extern "C"
 		const double *mu;
 		int32_t material_stride;
 		int32_t device; /* CUDA device ordinal */
-		int32_t flags;  /* reserved, 0 */
+		int32_t flags;  /* 0, or PFA_FLAG_* */
 		/* Multi-GPU element partition: conn may carry n_ghost_elements extra rows
 		 * after the n_elements computed ones. Ghost elements (elements of other ranks touching a
 		 * node this rank owns) only widen the sparsity pattern so that owned columns have their
 		 * full global row set; they are never evaluated and need no geometry/material entries. */
 		int32_t n_ghost_elements;
 	} pfa_mesh_desc;
+
+/* pfa_mesh_desc.flags: keep the caller's element order internally (default: elements are
+ * re-sorted along a space-filling curve once per mesh; results are identical either way) */
+#define PFA_FLAG_KEEP_ELEMENT_ORDER 1
 
 	typedef struct pfa_handle pfa_handle;
 

@@ -111,7 +111,7 @@ class Handle:
     """One pfa_handle: one mesh + material on one GPU."""
 
     def __init__(self, material, conn, n_bases, quad_weights, ref_grads, vertices=None, jac_it=None, da=None,
-                 lam=None, mu=None, device=0, n_ghost_elements=0):
+                 lam=None, mu=None, device=0, n_ghost_elements=0, flags=0):
         L = lib()
         self.material = MATERIAL_IDS[material] if isinstance(material, str) else int(material)
         conn = np.ascontiguousarray(conn, dtype=np.int32)
@@ -150,7 +150,7 @@ class Handle:
             assert lam.size == ne * stride and mu.size == ne * stride
             d.lambda_, d.mu = lam.ctypes.data_as(_dp), mu.ctypes.data_as(_dp)
             keep += [lam, mu]
-        d.material_stride, d.device, d.flags = stride, int(device), 0
+        d.material_stride, d.device, d.flags = stride, int(device), int(flags)
         d.n_ghost_elements = int(n_ghost_elements)
         h = ctypes.c_void_p()
         rc = L.pfa_create(ctypes.byref(d), ctypes.byref(h))

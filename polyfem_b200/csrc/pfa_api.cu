@@ -38,6 +38,8 @@ struct pfa_handle
 	std::vector<void *> owned;
 	int32_t *d_outer = nullptr, *d_inner = nullptr;
 	double *d_lambda = nullptr, *d_mu = nullptr;
+	int32_t *d_elem_id = nullptr; // internal -> caller element index (nullptr: identity)
+	double *s_mat = nullptr;      // staging for pfa_set_materials when elements are re-ordered
 	// staging for host-pointer calls (allocated on first use)
 	double *s_x = nullptr, *s_grad = nullptr, *s_values = nullptr, *s_epe = nullptr;
 	double *d_energy = nullptr;
@@ -45,6 +47,7 @@ struct pfa_handle
 
 	std::vector<int32_t> h_outer, h_inner;
 	std::vector<int32_t> h_adj_off, h_adj;
+	std::vector<double> h_ref_grads;
 	std::string err;
 
 	bool profiling = false;
@@ -349,11 +352,57 @@ extern "C"
 			return bail(PFA_ERR_UNSUPPORTED);
 		}
 
+		// internal element order (once per mesh): Morton order of the centroids when the vertices
+		// are known; the caller's order otherwise
+		std::vector<int32_t> perm;
+		std::vector<int32_t> conn_p;
+		std::vector<double> vert_p, lam_p, mu_p;
+		const int32_t *conn_in = d->conn;
+		const double *vert_in = d->vertices, *lam_in = d->lambda, *mu_in = d->mu;
+		try
+		{
+			if (affine && !(d->flags & PFA_FLAG_KEEP_ELEMENT_ORDER) && d->n_elements > 1)
+			{
+				spatial_element_order(d->vertices, d->n_elements, perm);
+				const size_t ne_ = size_t(d->n_elements), nl_ = size_t(d->n_loc), ng_ = size_t(d->n_ghost_elements);
+				conn_p.resize((ne_ + ng_) * nl_);
+				vert_p.resize(ne_ * 12);
+				for (size_t e = 0; e < ne_; ++e)
+				{
+					const size_t o = size_t(perm[e]);
+					std::memcpy(&conn_p[e * nl_], d->conn + o * nl_, nl_ * sizeof(int32_t));
+					std::memcpy(&vert_p[e * 12], d->vertices + o * 12, 12 * sizeof(double));
+				}
+				std::memcpy(conn_p.data() + ne_ * nl_, d->conn + ne_ * nl_, ng_ * nl_ * sizeof(int32_t));
+				conn_in = conn_p.data();
+				vert_in = vert_p.data();
+				if (d->material != PFA_LAPLACIAN)
+				{
+					const size_t st_ = size_t(d->material_stride);
+					lam_p.resize(ne_ * st_);
+					mu_p.resize(ne_ * st_);
+					for (size_t e = 0; e < ne_; ++e)
+						for (size_t k = 0; k < st_; ++k)
+						{
+							lam_p[e * st_ + k] = d->lambda[size_t(perm[e]) * st_ + k];
+							mu_p[e * st_ + k] = d->mu[size_t(perm[e]) * st_ + k];
+						}
+					lam_in = lam_p.data();
+					mu_in = mu_p.data();
+				}
+			}
+		}
+		catch (const std::bad_alloc &)
+		{
+			h->err = "pfa_create: out of host memory while re-ordering the elements";
+			return bail(PFA_ERR_NOMEM);
+		}
+
 		// pattern + slot map on the host (once per mesh)
 		HostPattern hp;
 		try
 		{
-			build_pattern(d->conn, d->n_elements + d->n_ghost_elements, d->n_loc, d->n_bases, hp);
+			build_pattern(conn_in, d->n_elements + d->n_ghost_elements, d->n_loc, d->n_bases, hp);
 		}
 		catch (const std::bad_alloc &)
 		{
@@ -385,16 +434,44 @@ extern "C"
 		dst = tmp_;                                                        \
 	} while (0)
 		const size_t ne = size_t(m.n_el), nl = size_t(m.n_loc), nq = size_t(m.n_qp);
-		UP(m.conn, d->conn, ne * nl, int32_t);
+		UP(m.conn, conn_in, ne * nl, int32_t);
+		if (!perm.empty())
+		{
+			UP(h->d_elem_id, perm.data(), ne, int32_t);
+			m.elem_id = h->d_elem_id;
+		}
 		UP(m.ref_grads, d->ref_grads, nq * nl * 3, double);
+		h->h_ref_grads.assign(d->ref_grads, d->ref_grads + nq * nl * 3);
+		m.ref_grads_host = h->h_ref_grads.data();
 		UP(m.qweights, d->quad_weights, nq, double);
 		UP(m.adj_off, hp.adj_off.data(), hp.adj_off.size(), int32_t);
 		UP(m.adj, hp.adj.data(), hp.adj.size(), int32_t);
-		UP(m.slot, hp.slot.data(), size_t(ne) * nl * nl, int32_t);
+		if (rowlane_applies(m.material, m.n_loc, m.n_qp))
+		{
+			// values index of the (i, j) block's first entry and the column stride, per element
+			std::vector<int32_t> cstride(ne * nl);
+			for (size_t e = 0; e < ne; ++e)
+				for (size_t j = 0; j < nl; ++j)
+				{
+					const int32_t gj = conn_in[e * nl + j];
+					const int32_t off = hp.adj_off[size_t(gj)], deg = hp.adj_off[size_t(gj) + 1] - off;
+					cstride[e * nl + j] = 3 * deg;
+					for (size_t i = 0; i < nl; ++i)
+					{
+						int32_t &sl = hp.slot[e * nl * nl + i * nl + j];
+						sl = 9 * off + 3 * (sl - off);
+					}
+				}
+			UP(m.entry, hp.slot.data(), size_t(ne) * nl * nl, int32_t);
+			UP(m.cstride, cstride.data(), ne * nl, int32_t);
+			PFA_CUDA(h, cudaStreamSynchronize(h->stream)); // cstride is a local
+		}
+		else
+			UP(m.slot, hp.slot.data(), size_t(ne) * nl * nl, int32_t);
 		if (m.material != PFA_LAPLACIAN)
 		{
 			const size_t cnt = ne * size_t(m.mat_stride);
-			if ((rc = dev_upload<double>(h, &h->d_lambda, d->lambda, cnt)) != PFA_OK || (rc = dev_upload<double>(h, &h->d_mu, d->mu, cnt)) != PFA_OK)
+			if ((rc = dev_upload<double>(h, &h->d_lambda, lam_in, cnt)) != PFA_OK || (rc = dev_upload<double>(h, &h->d_mu, mu_in, cnt)) != PFA_OK)
 				return bail(rc);
 			m.lambda = h->d_lambda;
 			m.mu = h->d_mu;
@@ -402,7 +479,7 @@ extern "C"
 		if (affine)
 		{
 			double *d_vert = nullptr, *jit = nullptr, *detj = nullptr;
-			if ((rc = dev_upload<double>(h, &d_vert, d->vertices, ne * 12)) != PFA_OK || (rc = dev_alloc<double>(h, &jit, ne * 9)) != PFA_OK || (rc = dev_alloc<double>(h, &detj, ne)) != PFA_OK)
+			if ((rc = dev_upload<double>(h, &d_vert, vert_in, ne * 12)) != PFA_OK || (rc = dev_alloc<double>(h, &jit, ne * 9)) != PFA_OK || (rc = dev_alloc<double>(h, &detj, ne)) != PFA_OK)
 				return bail(rc);
 			++h->launches;
 			cudaError_t e = launch_geometry_precompute(d_vert, m.n_el, jit, detj, h->stream);
@@ -537,8 +614,26 @@ extern "C"
 			return fail(h, PFA_ERR_INVALID, "pfa_set_materials: NULL array or material_stride differs from pfa_create");
 		PFA_CUDA(h, cudaSetDevice(h->device));
 		const size_t cnt = size_t(h->dm.n_el) * size_t(h->dm.mat_stride) * sizeof(double);
-		PFA_CUDA(h, cudaMemcpyAsync(h->d_lambda, lambda, cnt, cudaMemcpyDefault, h->stream));
-		PFA_CUDA(h, cudaMemcpyAsync(h->d_mu, mu, cnt, cudaMemcpyDefault, h->stream));
+		if (h->d_elem_id == nullptr)
+		{
+			PFA_CUDA(h, cudaMemcpyAsync(h->d_lambda, lambda, cnt, cudaMemcpyDefault, h->stream));
+			PFA_CUDA(h, cudaMemcpyAsync(h->d_mu, mu, cnt, cudaMemcpyDefault, h->stream));
+		}
+		else
+		{
+			// elements live in the internal order: stage, then gather rows through elem_id
+			int rc = ensure_staging(h, &h->s_mat, cnt / sizeof(double));
+			if (rc != PFA_OK)
+				return rc;
+			const double *src[2] = {lambda, mu};
+			double *dst[2] = {h->d_lambda, h->d_mu};
+			for (int k = 0; k < 2; ++k)
+			{
+				PFA_CUDA(h, cudaMemcpyAsync(h->s_mat, src[k], cnt, cudaMemcpyDefault, h->stream));
+				++h->launches;
+				PFA_CUDA(h, launch_gather_rows(h->s_mat, h->d_elem_id, h->dm.n_el, h->dm.mat_stride, dst[k], h->stream));
+			}
+		}
 		PFA_CUDA(h, cudaStreamSynchronize(h->stream));
 		return PFA_OK;
 	}

@@ -26,6 +26,7 @@ namespace pfa
 		const double *mu = nullptr;        // [n_el][mat_stride]
 		const double *ref_grads = nullptr; // [n_qp][n_loc][3]
 		const double *qweights = nullptr;  // [n_qp]
+		const double *ref_grads_host = nullptr; // host copy of ref_grads (owned by the handle): source of the __constant__ table
 
 		// node-block CSR/CSC pattern (symmetric): adj_off[n_bases+1], adj[n_pairs] ascending
 		const int32_t *adj_off = nullptr;
@@ -34,6 +35,14 @@ namespace pfa
 		// slot map: pair index (into adj) of block (i,j) of element e: slot[e][i*n_loc+j],
 		// where the pair is (row node g_i) inside the column list of node g_j
 		const int32_t *slot = nullptr;
+		// row-lane kernels (size 3): entry[e][i*n_loc+j] = 9*adj_off[g_j] + 3*k, k = position of g_i in
+		// adj(g_j): values index of H[(g_i,0),(g_j,0)]; cstride[e][j] = 3*deg(g_j), the distance between
+		// the three scalar columns of node g_j. When these are set, `slot` is not uploaded.
+		const int32_t *entry = nullptr;
+		const int32_t *cstride = nullptr;
+		// elements are stored in an internal (spatially sorted, L2-friendly) order; elem_id[e] is the
+		// caller's index of internal element e (nullptr = identity)
+		const int32_t *elem_id = nullptr;
 	};
 
 	struct AssembleArgs
@@ -54,6 +63,8 @@ namespace pfa
 	// `linear` selects LinearAssembler::assemble semantics (x ignored).
 	cudaError_t launch_assemble(const DeviceMesh &m, const AssembleArgs &a, bool linear, int sm_count, cudaStream_t st, const char **kernel_name);
 	bool assemble_supported(const DeviceMesh &m);
+	// true when launch_assemble uses the row-lane kernels (which read entry/cstride instead of slot)
+	bool rowlane_applies(int material, int n_loc, int n_qp);
 
 	// ---- host-side pattern + slot map (pfa_pattern.cu) ----
 	struct HostPattern
@@ -64,4 +75,8 @@ namespace pfa
 	};
 	// throws std::runtime_error on invalid connectivity
 	void build_pattern(const int32_t *conn, int n_el, int n_loc, int n_bases, HostPattern &out);
+	// Morton order of the element centroids (vertices[e][4][3]): perm[internal] = caller's element index
+	void spatial_element_order(const double *vertices, int n_el, std::vector<int32_t> &perm);
+	// dst[i*stride+s] = src[perm[i]*stride+s] (device pointers)
+	cudaError_t launch_gather_rows(const double *src, const int32_t *perm, int n, int stride, double *dst, cudaStream_t st);
 } // namespace pfa

@@ -14,6 +14,18 @@
 #include "pfa_internal.h"
 
 #include <cstdio>
+#include <cstring>
+#include <mutex>
+
+#ifndef PFA_RL_UNROLL_Q
+#define PFA_RL_UNROLL_Q 1 // qp loop of phase 2: 1 keeps register pressure low (c_refgrad is read with LDC)
+#endif
+#ifndef PFA_RL_WARPS_P2
+#define PFA_RL_WARPS_P2 6
+#endif
+#ifndef PFA_RL_MINB_P2
+#define PFA_RL_MINB_P2 2
+#endif
 
 namespace pfa
 {
@@ -61,6 +73,13 @@ namespace pfa
 			for (int k = 0; k < 9; ++k)
 				jit[size_t(e) * 9 + k] = C[k] * inv;
 			detj[e] = det;
+		}
+
+		__global__ void gather_rows_kernel(const double *__restrict__ src, const int32_t *__restrict__ perm, int n, int stride, double *__restrict__ dst)
+		{
+			const int64_t t = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+			if (t < int64_t(n) * stride)
+				dst[t] = src[int64_t(perm[t / stride]) * stride + t % stride];
 		}
 
 		// scalar CSC arrays from the node-block pattern: column (b,n) lists rows (a,m), a in adj(b)
@@ -265,7 +284,7 @@ namespace pfa
 						e_loc += __shfl_xor_sync(0xffffffffu, e_loc, o);
 					energy_acc += e_loc; // identical on all lanes
 					if (a.energy_per_el != nullptr && lane == 0)
-						a.energy_per_el[e] = e_loc;
+						a.energy_per_el[m.elem_id ? m.elem_id[e] : e] = e_loc;
 				}
 				if (want_g)
 				{
@@ -398,51 +417,65 @@ namespace pfa
 		}
 
 		// ------------------------------------------------------------------------------------
-		// NeoHookean kernel for n_qp in {1, 4} (P1, P2 tets): "row-lane" mapping.
-		//  phase 1  lane <-> (element, quadrature point): 32/NQ elements per warp batch. Gathers
-		//           x, builds F, stress and the Hessian coefficients in registers, leaves per
-		//           (element, qp) records {D_i, C D_i, c2 da F, mu da, c1 da} in shared memory;
-		//           gradient and energy are reduced over the qp lanes with shuffles.
-		//  phase 2  lane <-> (local node i, component m) of one element: the lane keeps its row's
-		//           data in registers, walks the column nodes j (records broadcast from shared
-		//           memory) and produces H[(i,m),(j,0..2)]. The three m-lanes of a node write three
-		//           consecutive doubles and the NL nodes of the element hit one CSC column segment
-		//           per RED instruction, which minimises L2 sector operations.
+		// NeoHookean kernel for P1 (n_loc 4, 1 qp) and P2 (n_loc 10, 4 qp) tets: "row-lane" mapping
+		// in reference coordinates.
+		//
+		// With D_j = J^-T^T g_j (g_j = reference gradient of basis j at the quadrature point, the
+		// same table for every element) the closed form (top of this file) becomes
+		//     H[(i,m),(j,n)] = sum_q  Y_q[(i,m)][n] . g_j(q)
+		// where the 3-vector Y[(i,m)][n] depends on the row (i,m) only. The column operand g_j(q)
+		// is a mesh-independent constant: it lives in __constant__ memory and enters the DFMAs as
+		// a constant-bank operand, so the inner loop (9 DFMA per column node) loads nothing.
+		//
+		//  phase 1  lane <-> (element, quadrature point). Gathers x, builds F, stress and
+		//           coefficients and leaves a 34-double record per (element, qp) in shared memory:
+		//             [0..5]   mu da K,  K = J^-T J^-1 (symmetric: 00 01 02 11 12 22)
+		//             [6..14]  T = (c2 da F) cof(J^-T)^T   (row r: t_r = cof(J^-T) (c2 da F)_r)
+		//             [15..23] CJ = cof(F) J^-T^T           (A_j = cof(F) D_j = CJ g_j)
+		//             [24..32] PJ = (P da) J^-T^T           (gradient: G[(i,m)] = PJ_m . g_i)
+		//             [33]     c1 da
+		//  phase 2  lane <-> (local node i, component m) of one element; per quadrature point
+		//             Y[m]       = mu da K g_i
+		//             Y[(m+1)%3] =  t_{(m+2)%3} x g_i
+		//             Y[(m+2)%3] = -t_{(m+1)%3} x g_i
+		//             Y[n]      += c1 da (CJ_m . g_i) CJ_n        for n = 0,1,2
+		//           then acc[j][n] += Y[n] . g_j(q) for all column nodes j (registers only), and
+		//           after the qp loop 3 REDs per column node: for a fixed (j, n) the 3 NL lanes of an
+		//           element write NL runs of 3 consecutive doubles inside one CSC column segment,
+		//           the densest pattern the CSC layout allows.
 		// ------------------------------------------------------------------------------------
-#ifndef PFA_RL_PAD
-#define PFA_RL_PAD 14
-#endif
-#ifndef PFA_RL_WARPS_P2
-#define PFA_RL_WARPS_P2 4
-#endif
+		constexpr int kConstSlotDoubles = 4 * 10 * 3;
+		__constant__ double c_refgrad[2][kConstSlotDoubles]; // slot 0: P1 [1][4][3], slot 1: P2 [4][10][3]
+
 		template <int NL, int NQ>
 		struct RowLane
 		{
-			static constexpr int EB = 32 / NQ;      // elements per phase-1 batch
-			static constexpr int REC = NL * 6 + PFA_RL_PAD; // doubles per (element, qp) record; (REC mod 16) = 6/10 keeps the
-			                                        // lane-strided phase-1 stores at 2-way bank conflicts, 16-byte aligned
-			static constexpr int ROWL = 3 * NL;     // phase-2 lanes per element
-			static constexpr int EPW = 32 / ROWL;   // elements per phase-2 round
+			static constexpr int SLOT = NL == 4 ? 0 : 1;
+			static constexpr int ROWL = 3 * NL;       // phase-2 lanes per element
+			static constexpr int EPW = 32 / ROWL;     // elements per phase-2 round
+			static constexpr int EB = (32 / NQ) / EPW * EPW; // elements per warp batch (whole rounds)
+			static constexpr int REC = 35;            // doubles per record (34 used), odd: conflict-free lane-strided stores
 			static constexpr int WARP_DOUBLES = EB * NQ * REC;
-			static constexpr int WARP_INTS = EB * NL * 3 + EB * NL * NL; // g, off, deg per node + slot per pair
+			static constexpr int WARP_INTS = EB * NL * 2 + EB * NL * NL; // global node, column stride per (element, node); entry per (element, i, j)
+			static_assert((EB * NL * 2) % 4 == 0 && (NL * NL) % 4 == 0, "16-byte cp.async staging of the entry table");
 			static size_t smem_bytes(int warps)
 			{
 				return sizeof(double) * (size_t(NQ) * NL * 3 + ((NQ + 1) & ~1) + size_t(warps) * WARP_DOUBLES) + sizeof(int) * size_t(warps) * WARP_INTS;
 			}
 		};
 
-		template <int NL, int NQ, int WARPS>
-		__global__ void __launch_bounds__(WARPS * 32) assemble_nh_rowlane_kernel(const DeviceMesh m, const AssembleArgs a)
+		template <int NL, int NQ, int WARPS, int MINB>
+		__global__ void __launch_bounds__(WARPS * 32, MINB) assemble_nh_rowlane_kernel(const DeviceMesh m, const AssembleArgs a)
 		{
 			using RL = RowLane<NL, NQ>;
-			constexpr int EB = RL::EB, REC = RL::REC, ROWL = RL::ROWL, EPW = RL::EPW;
+			constexpr int EB = RL::EB, REC = RL::REC, ROWL = RL::ROWL, EPW = RL::EPW, SLOT = RL::SLOT;
 			extern __shared__ double smem[];
 			const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-			double *s_rg = smem;               // [NQ][NL][3]
-			double *s_w = s_rg + NQ * NL * 3;  // [NQ]
+			double *s_rg = smem;              // [NQ][NL][3] (lane-indexed reads; the column side uses c_refgrad)
+			double *s_w = s_rg + NQ * NL * 3; // [NQ]
 			double *s_rec = s_w + ((NQ + 1) & ~1) + warp * RL::WARP_DOUBLES;
 			int *s_int = reinterpret_cast<int *>(s_w + ((NQ + 1) & ~1) + WARPS * RL::WARP_DOUBLES) + warp * RL::WARP_INTS;
-			int *sG = s_int, *sOff = s_int + EB * NL, *sDeg = s_int + 2 * EB * NL, *sSlot = s_int + 3 * EB * NL;
+			int *sG = s_int, *sStride = s_int + EB * NL, *sEnt = s_int + 2 * EB * NL;
 			for (int t = threadIdx.x; t < NQ * NL * 3; t += WARPS * 32)
 				s_rg[t] = m.ref_grads[t];
 			for (int t = threadIdx.x; t < NQ; t += WARPS * 32)
@@ -453,47 +486,47 @@ namespace pfa
 			const bool want_g = a.grad != nullptr;
 			const bool want_e = a.energy != nullptr || a.energy_per_el != nullptr;
 			double energy_acc = 0.0;
+			// phase-1 role
 			const int el = lane / NQ, q = lane % NQ;
+			// phase-2 role
+			const int sub = lane / ROWL, r = lane % ROWL;
+			const int ri = r / 3, mm = r % 3;
+			const int ra = (mm + 1) % 3, rb = (mm + 2) % 3;
+			const bool row_lane = lane < EPW * ROWL;
 
-			// batches are handed out dynamically (one atomic per warp and batch) so that SMs slowed
-			// down by L2 contention do not leave a tail
-			for (;;)
+			// warp batches are handed out dynamically (one atomic per batch); the next index is
+			// fetched before the current batch is processed so that its latency is hidden
+			int batch = 0;
+			if (lane == 0)
+				batch = atomicAdd(a.work_counter, EB);
+			batch = __shfl_sync(0xffffffffu, batch, 0);
+			while (batch < m.n_el)
 			{
-				int batch = 0;
+				int next = 0;
 				if (lane == 0)
-					batch = atomicAdd(a.work_counter, EB);
-				batch = __shfl_sync(0xffffffffu, batch, 0);
-				if (batch >= m.n_el)
-					break;
-				// ---- connectivity and pattern offsets of the batch ----
-				for (int t = lane; t < EB * NL; t += 32)
+					next = atomicAdd(a.work_counter, EB);
+				// ---- connectivity and entry offsets of the batch ----
+				const int n_batch = min(EB, m.n_el - batch);
+				for (int t = lane; t < n_batch * NL; t += 32)
 				{
-					const int ee = batch + t / NL;
-					if (ee < m.n_el)
-					{
-						const int g = m.conn[size_t(ee) * NL + (t % NL)];
-						const int o = m.adj_off[g];
-						sG[t] = g;
-						sOff[t] = o;
-						sDeg[t] = m.adj_off[g + 1] - o;
-					}
+					sG[t] = m.conn[size_t(batch) * NL + t];
+					if (want_h)
+						sStride[t] = m.cstride[size_t(batch) * NL + t];
 				}
 				if (want_h)
 				{
-					const int n_batch = min(EB, m.n_el - batch);
-					const int32_t *src = m.slot + size_t(batch) * NL * NL;
-					for (int t = lane; t < n_batch * NL * NL; t += 32)
-						sSlot[t] = src[t];
+					// asynchronous 16-byte copies that land during phase 1
+					const int32_t *src = m.entry + size_t(batch) * NL * NL;
+					const uint32_t dst = uint32_t(__cvta_generic_to_shared(sEnt));
+					for (int t = lane; t < n_batch * NL * NL / 4; t += 32)
+						asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 16u * t), "l"(src + 4 * t) : "memory");
+					asm volatile("cp.async.commit_group;" ::: "memory");
 				}
 				__syncwarp();
 
 				// ---- phase 1 ----
 				const int e = batch + el;
-				const bool valid = e < m.n_el;
-				double G[NL * 3];
-#pragma unroll
-				for (int t = 0; t < NL * 3; ++t)
-					G[t] = 0.0;
+				const bool valid = lane < EB * NQ && e < m.n_el;
 				double e_q = 0.0;
 				if (valid)
 				{
@@ -512,13 +545,10 @@ namespace pfa
 					{
 						const int g = sG[el * NL + i];
 						const double u0 = a.x[size_t(g) * 3 + 0], u1 = a.x[size_t(g) * 3 + 1], u2 = a.x[size_t(g) * 3 + 2];
-						const double *r = s_rg + (q * NL + i) * 3;
-						const double d0 = r[0] * J[0] + r[1] * J[3] + r[2] * J[6];
-						const double d1 = r[0] * J[1] + r[1] * J[4] + r[2] * J[7];
-						const double d2 = r[0] * J[2] + r[1] * J[5] + r[2] * J[8];
-						rec[i * 6 + 0] = d0;
-						rec[i * 6 + 1] = d1;
-						rec[i * 6 + 2] = d2;
+						const double *rr = s_rg + (q * NL + i) * 3;
+						const double d0 = rr[0] * J[0] + rr[1] * J[3] + rr[2] * J[6];
+						const double d1 = rr[0] * J[1] + rr[1] * J[4] + rr[2] * J[7];
+						const double d2 = rr[0] * J[2] + rr[1] * J[5] + rr[2] * J[8];
 						F[0] += u0 * d0;
 						F[1] += u0 * d1;
 						F[2] += u0 * d2;
@@ -535,27 +565,47 @@ namespace pfa
 					cofactor3(F, C);
 					const double invJ = 1.0 / Jd;
 					const double pc = (lam * lJ - mu) * invJ; // P = mu F + pc C ; c2 = pc
-					double P[9], sq = 0.0;
+					double sq = 0.0;
 #pragma unroll
 					for (int k = 0; k < 9; ++k)
-					{
 						sq += F[k] * F[k];
-						P[k] = (mu * F[k] + pc * C[k]) * da;
-						rec[NL * 6 + k] = pc * da * F[k];
-					}
-					rec[NL * 6 + 9] = mu * da;
-					rec[NL * 6 + 10] = (mu + lam * (1.0 - lJ)) * invJ * invJ * da;
 					e_q = (0.5 * mu * (sq - 3.0 - 2.0 * lJ) + 0.5 * lam * lJ * lJ) * da;
+					// PJ[a][c] = sum_k (P da)[a][k] J[c][k]
 #pragma unroll
-					for (int i = 0; i < NL; ++i)
+					for (int aa = 0; aa < 3; ++aa)
 					{
-						const double d0 = rec[i * 6 + 0], d1 = rec[i * 6 + 1], d2 = rec[i * 6 + 2];
-						rec[i * 6 + 3] = C[0] * d0 + C[1] * d1 + C[2] * d2;
-						rec[i * 6 + 4] = C[3] * d0 + C[4] * d1 + C[5] * d2;
-						rec[i * 6 + 5] = C[6] * d0 + C[7] * d1 + C[8] * d2;
-						G[i * 3 + 0] = d0 * P[0] + d1 * P[1] + d2 * P[2];
-						G[i * 3 + 1] = d0 * P[3] + d1 * P[4] + d2 * P[5];
-						G[i * 3 + 2] = d0 * P[6] + d1 * P[7] + d2 * P[8];
+						const double p0 = (mu * F[aa * 3 + 0] + pc * C[aa * 3 + 0]) * da;
+						const double p1 = (mu * F[aa * 3 + 1] + pc * C[aa * 3 + 1]) * da;
+						const double p2 = (mu * F[aa * 3 + 2] + pc * C[aa * 3 + 2]) * da;
+#pragma unroll
+						for (int c = 0; c < 3; ++c)
+							rec[24 + aa * 3 + c] = p0 * J[c * 3 + 0] + p1 * J[c * 3 + 1] + p2 * J[c * 3 + 2];
+					}
+					if (want_h)
+					{
+						const double mu_da = mu * da;
+						rec[0] = mu_da * (J[0] * J[0] + J[1] * J[1] + J[2] * J[2]);
+						rec[1] = mu_da * (J[0] * J[3] + J[1] * J[4] + J[2] * J[5]);
+						rec[2] = mu_da * (J[0] * J[6] + J[1] * J[7] + J[2] * J[8]);
+						rec[3] = mu_da * (J[3] * J[3] + J[4] * J[4] + J[5] * J[5]);
+						rec[4] = mu_da * (J[3] * J[6] + J[4] * J[7] + J[5] * J[8]);
+						rec[5] = mu_da * (J[6] * J[6] + J[7] * J[7] + J[8] * J[8]);
+						// rows of cof(J^-T): R_k = r_{k+1} x r_{k+2}; cofactor3 returns exactly these rows
+						double R[9];
+						cofactor3(J, R);
+						const double c2da = pc * da;
+#pragma unroll
+						for (int rr = 0; rr < 3; ++rr)
+						{
+							const double f0 = c2da * F[rr * 3 + 0], f1 = c2da * F[rr * 3 + 1], f2 = c2da * F[rr * 3 + 2];
+#pragma unroll
+							for (int k = 0; k < 3; ++k)
+								rec[6 + rr * 3 + k] = f0 * R[k * 3 + 0] + f1 * R[k * 3 + 1] + f2 * R[k * 3 + 2];
+#pragma unroll
+							for (int c = 0; c < 3; ++c)
+								rec[15 + rr * 3 + c] = C[rr * 3 + 0] * J[c * 3 + 0] + C[rr * 3 + 1] * J[c * 3 + 1] + C[rr * 3 + 2] * J[c * 3 + 2];
+						}
+						rec[33] = (mu + lam * (1.0 - lJ)) * invJ * invJ * da;
 					}
 				}
 				if (want_e)
@@ -567,118 +617,89 @@ namespace pfa
 					{
 						energy_acc += e_q;
 						if (a.energy_per_el != nullptr)
-							a.energy_per_el[e] = e_q;
+							a.energy_per_el[m.elem_id ? m.elem_id[e] : e] = e_q;
 					}
 				}
-				if (want_g)
-				{
-#pragma unroll
-					for (int t = 0; t < NL * 3; ++t)
-					{
-#pragma unroll
-						for (int k = 1; k < NQ; k <<= 1)
-							G[t] += __shfl_xor_sync(0xffffffffu, G[t], k);
-					}
-#pragma unroll
-					for (int i = 0; i < NL; ++i)
-						if (valid && (i % NQ) == q)
-						{
-							double *dst = a.grad + size_t(sG[el * NL + i]) * 3;
-							atomicAdd(dst + 0, G[i * 3 + 0]);
-							atomicAdd(dst + 1, G[i * 3 + 1]);
-							atomicAdd(dst + 2, G[i * 3 + 2]);
-						}
-				}
+				if (want_h)
+					asm volatile("cp.async.wait_group 0;" ::: "memory");
 				__syncwarp();
 
 				// ---- phase 2 ----
-				if (want_h)
+				if (want_h || want_g)
 				{
-					const int sub = lane / ROWL, r = lane % ROWL;
-					const int i = r / 3, mm = r % 3;
-					const int ra = (mm + 1) % 3, rb = (mm + 2) % 3;
+#pragma unroll 1
 					for (int eb = 0; eb < EB; eb += EPW)
 					{
 						const int el2 = eb + sub;
 						const int e2 = batch + el2;
-						if (lane < EPW * ROWL && el2 < EB && e2 < m.n_el)
+						if (row_lane && e2 < m.n_el)
 						{
-							// row-side registers: mu da D_i, c1 da (C D_i)_m, rows (m+1)%3,(m+2)%3 of c2 da F x D_i
-							double Dp[NQ][3], cA[NQ], Ma[NQ][3], Mb[NQ][3];
+							double acc[NL][3];
 #pragma unroll
+							for (int j = 0; j < NL; ++j)
+								acc[j][0] = acc[j][1] = acc[j][2] = 0.0;
+							double g_row = 0.0;
+							constexpr int kUnrollQ = PFA_RL_UNROLL_Q;
+#pragma unroll kUnrollQ
 							for (int qq = 0; qq < NQ; ++qq)
 							{
 								const double *rec = s_rec + (el2 * NQ + qq) * REC;
-								const double d0 = rec[i * 6 + 0], d1 = rec[i * 6 + 1], d2 = rec[i * 6 + 2];
-								const double mu_da = rec[NL * 6 + 9], c1_da = rec[NL * 6 + 10];
-								const double *fa = rec + NL * 6 + ra * 3, *fb = rec + NL * 6 + rb * 3;
-								Dp[qq][0] = mu_da * d0;
-								Dp[qq][1] = mu_da * d1;
-								Dp[qq][2] = mu_da * d2;
-								cA[qq] = c1_da * rec[i * 6 + 3 + mm];
-								Ma[qq][0] = fa[1] * d2 - fa[2] * d1;
-								Ma[qq][1] = fa[2] * d0 - fa[0] * d2;
-								Ma[qq][2] = fa[0] * d1 - fa[1] * d0;
-								Mb[qq][0] = fb[1] * d2 - fb[2] * d1;
-								Mb[qq][1] = fb[2] * d0 - fb[0] * d2;
-								Mb[qq][2] = fb[0] * d1 - fb[1] * d0;
-							}
-#ifndef PFA_RL_UNROLL_J
-#define PFA_RL_UNROLL_J 10
-#endif
-							const int *sl = sSlot + el2 * NL * NL + i * NL;
-							constexpr int kUnrollJ = PFA_RL_UNROLL_J;
-#pragma unroll kUnrollJ
-							for (int j = 0; j < NL; ++j)
-							{
-								double s = 0.0, R0 = 0.0, R1 = 0.0, R2 = 0.0, wa = 0.0, wb = 0.0;
+								const double *gr = s_rg + (qq * NL + ri) * 3;
+								const double g0 = gr[0], g1 = gr[1], g2 = gr[2];
+								const double *pj = rec + 24 + mm * 3;
+								g_row = fma(g0, pj[0], fma(g1, pj[1], fma(g2, pj[2], g_row)));
+								if (want_h)
+								{
+									// Y rows before the rotation by m
+									const double K00 = rec[0], K01 = rec[1], K02 = rec[2], K11 = rec[3], K12 = rec[4], K22 = rec[5];
+									const double v0 = K00 * g0 + K01 * g1 + K02 * g2;
+									const double v1 = K01 * g0 + K11 * g1 + K12 * g2;
+									const double v2 = K02 * g0 + K12 * g1 + K22 * g2;
+									const double *ta = rec + 6 + ra * 3, *tb = rec + 6 + rb * 3;
+									const double b0 = tb[1] * g2 - tb[2] * g1, b1 = tb[2] * g0 - tb[0] * g2, b2 = tb[0] * g1 - tb[1] * g0; //  t_b x g
+									const double a0 = ta[2] * g1 - ta[1] * g2, a1 = ta[0] * g2 - ta[2] * g0, a2 = ta[1] * g0 - ta[0] * g1; // -t_a x g
+									const double *cj = rec + 15;
+									const double cA = rec[33] * (cj[mm * 3 + 0] * g0 + cj[mm * 3 + 1] * g1 + cj[mm * 3 + 2] * g2);
+									double Y[3][3];
+									Y[0][0] = fma(cA, cj[0], mm == 0 ? v0 : (mm == 1 ? a0 : b0));
+									Y[0][1] = fma(cA, cj[1], mm == 0 ? v1 : (mm == 1 ? a1 : b1));
+									Y[0][2] = fma(cA, cj[2], mm == 0 ? v2 : (mm == 1 ? a2 : b2));
+									Y[1][0] = fma(cA, cj[3], mm == 1 ? v0 : (mm == 2 ? a0 : b0));
+									Y[1][1] = fma(cA, cj[4], mm == 1 ? v1 : (mm == 2 ? a1 : b1));
+									Y[1][2] = fma(cA, cj[5], mm == 1 ? v2 : (mm == 2 ? a2 : b2));
+									Y[2][0] = fma(cA, cj[6], mm == 2 ? v0 : (mm == 0 ? a0 : b0));
+									Y[2][1] = fma(cA, cj[7], mm == 2 ? v1 : (mm == 0 ? a1 : b1));
+									Y[2][2] = fma(cA, cj[8], mm == 2 ? v2 : (mm == 0 ? a2 : b2));
 #pragma unroll
-								for (int qq = 0; qq < NQ; ++qq)
-								{
-									const double2 *nj = reinterpret_cast<const double2 *>(s_rec + (el2 * NQ + qq) * REC + j * 6);
-									const double2 v0 = nj[0], v1 = nj[1], v2 = nj[2]; // D0 D1 | D2 A0 | A1 A2
-									s = fma(Dp[qq][0], v0.x, s);
-									s = fma(Dp[qq][1], v0.y, s);
-									s = fma(Dp[qq][2], v1.x, s);
-									R0 = fma(cA[qq], v1.y, R0);
-									R1 = fma(cA[qq], v2.x, R1);
-									R2 = fma(cA[qq], v2.y, R2);
-									wa = fma(Ma[qq][0], v0.x, wa);
-									wa = fma(Ma[qq][1], v0.y, wa);
-									wa = fma(Ma[qq][2], v1.x, wa);
-									wb = fma(Mb[qq][0], v0.x, wb);
-									wb = fma(Mb[qq][1], v0.y, wb);
-									wb = fma(Mb[qq][2], v1.x, wb);
+									for (int j = 0; j < NL; ++j)
+									{
+										const double c0 = c_refgrad[SLOT][(qq * NL + j) * 3 + 0], c1 = c_refgrad[SLOT][(qq * NL + j) * 3 + 1], c2 = c_refgrad[SLOT][(qq * NL + j) * 3 + 2];
+										acc[j][0] = fma(Y[0][0], c0, fma(Y[0][1], c1, fma(Y[0][2], c2, acc[j][0])));
+										acc[j][1] = fma(Y[1][0], c0, fma(Y[1][1], c1, fma(Y[1][2], c2, acc[j][1])));
+										acc[j][2] = fma(Y[2][0], c0, fma(Y[2][1], c1, fma(Y[2][2], c2, acc[j][2])));
+									}
 								}
-								// row m of  R + s I - hat(w):  out[m] += s, out[(m+1)%3] += w_{(m+2)%3}, out[(m+2)%3] -= w_{(m+1)%3}
-								if (mm == 0)
+							}
+							if (want_g)
+								atomicAdd(a.grad + size_t(sG[el2 * NL + ri]) * 3 + mm, g_row);
+							if (want_h)
+							{
+								const int *ent = sEnt + el2 * NL * NL + ri * NL;
+								const int *st = sStride + el2 * NL;
+#pragma unroll
+								for (int j = 0; j < NL; ++j)
 								{
-									R0 += s;
-									R1 += wb;
-									R2 -= wa;
+									double *dst = a.values + (size_t(ent[j]) + mm);
+									const size_t cs = size_t(st[j]);
+									atomicAdd(dst, acc[j][0]);
+									atomicAdd(dst + cs, acc[j][1]);
+									atomicAdd(dst + 2 * cs, acc[j][2]);
 								}
-								else if (mm == 1)
-								{
-									R1 += s;
-									R2 += wb;
-									R0 -= wa;
-								}
-								else
-								{
-									R2 += s;
-									R0 += wb;
-									R1 -= wa;
-								}
-								const int off = sOff[el2 * NL + j], deg = sDeg[el2 * NL + j];
-								double *dst = a.values + (size_t(off) * 9 + size_t(sl[j] - off) * 3 + mm);
-								atomicAdd(dst, R0);
-								atomicAdd(dst + size_t(3) * deg, R1);
-								atomicAdd(dst + size_t(6) * deg, R2);
 							}
 						}
 					}
 				}
-				__syncwarp();
+				batch = __shfl_sync(0xffffffffu, next, 0);
 			}
 
 			if (want_e && a.energy != nullptr)
@@ -700,13 +721,40 @@ namespace pfa
 			}
 		}
 
-		template <int NL, int NQ, int WARPS>
+		// the reference-gradient table of a handle goes to its __constant__ slot when it differs
+		// from what the slot holds (one table per basis order and device at a time: two handles
+		// with DIFFERENT quadrature tables for the same order must not run concurrently)
+		std::mutex g_const_mutex;
+		double g_const_shadow[16][2][kConstSlotDoubles];
+		bool g_const_valid[16][2] = {};
+
+		cudaError_t ensure_const_table(const DeviceMesh &m, int slot, cudaStream_t st)
+		{
+			int dev = 0;
+			cudaError_t err = cudaGetDevice(&dev);
+			if (err != cudaSuccess)
+				return err;
+			if (dev < 0 || dev >= 16 || m.ref_grads_host == nullptr)
+				return cudaErrorInvalidValue;
+			const size_t bytes = sizeof(double) * size_t(m.n_qp) * m.n_loc * 3;
+			std::lock_guard<std::mutex> lock(g_const_mutex);
+			if (g_const_valid[dev][slot] && std::memcmp(g_const_shadow[dev][slot], m.ref_grads_host, bytes) == 0)
+				return cudaSuccess;
+			std::memcpy(g_const_shadow[dev][slot], m.ref_grads_host, bytes);
+			g_const_valid[dev][slot] = true;
+			return cudaMemcpyToSymbolAsync(c_refgrad, g_const_shadow[dev][slot], bytes, sizeof(double) * size_t(slot) * kConstSlotDoubles, cudaMemcpyHostToDevice, st);
+		}
+
+		template <int NL, int NQ, int WARPS, int MINB>
 		cudaError_t launch_rowlane(const DeviceMesh &m, const AssembleArgs &a, int sm_count, cudaStream_t st)
 		{
 			using RL = RowLane<NL, NQ>;
 			const size_t smem = RL::smem_bytes(WARPS);
-			auto kern = assemble_nh_rowlane_kernel<NL, NQ, WARPS>;
-			cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+			auto kern = assemble_nh_rowlane_kernel<NL, NQ, WARPS, MINB>;
+			cudaError_t err = ensure_const_table(m, RL::SLOT, st);
+			if (err != cudaSuccess)
+				return err;
+			err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
 			if (err != cudaSuccess)
 				return err;
 			int per_sm = 1;
@@ -777,6 +825,11 @@ namespace pfa
 		}
 	} // namespace
 
+	bool rowlane_applies(int material, int n_loc, int n_qp)
+	{
+		return material == PFA_NEOHOOKEAN && ((n_loc == 10 && n_qp == 4) || (n_loc == 4 && n_qp == 1));
+	}
+
 	bool assemble_supported(const DeviceMesh &m)
 	{
 		return pick_warps(m.n_loc, m.n_qp) > 0;
@@ -786,6 +839,13 @@ namespace pfa
 	{
 		const int threads = 256;
 		geometry_precompute_kernel<<<(n_el + threads - 1) / threads, threads, 0, st>>>(vertices_dev, n_el, jit, detj);
+		return cudaGetLastError();
+	}
+
+	cudaError_t launch_gather_rows(const double *src, const int32_t *perm, int n, int stride, double *dst, cudaStream_t st)
+	{
+		const int64_t total = int64_t(n) * stride;
+		gather_rows_kernel<<<unsigned((total + 255) / 256), 256, 0, st>>>(src, perm, n, stride, dst);
 		return cudaGetLastError();
 	}
 
@@ -807,13 +867,13 @@ namespace pfa
 			{
 				if (kernel_name)
 					*kernel_name = "assemble_nh_rowlane_kernel<10,4>";
-				return launch_rowlane<10, 4, PFA_RL_WARPS_P2>(m, a, sm_count, st);
+				return launch_rowlane<10, 4, PFA_RL_WARPS_P2, PFA_RL_MINB_P2>(m, a, sm_count, st);
 			}
 			if (m.n_loc == 4 && m.n_qp == 1)
 			{
 				if (kernel_name)
 					*kernel_name = "assemble_nh_rowlane_kernel<4,1>";
-				return launch_rowlane<4, 1, 8>(m, a, sm_count, st);
+				return launch_rowlane<4, 1, 8, 2>(m, a, sm_count, st);
 			}
 			return launch_generic<PFA_NEOHOOKEAN, false>(m, a, sm_count, st);
 		case PFA_LINEAR_ELASTICITY:
