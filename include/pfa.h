@@ -97,6 +97,10 @@ extern "C"
 /* pfa_mesh_desc.flags: keep the caller's element order internally (default: elements are
  * re-sorted along a space-filling curve once per mesh; results are identical either way) */
 #define PFA_FLAG_KEEP_ELEMENT_ORDER 1
+/* experimental: the row-lane kernels clear values[] themselves, block by block, a few warp
+ * batches ahead of the scatter, instead of a cudaMemsetAsync before the launch (measured slower
+ * on B200 in round 1: the cleared lines do not stay in L2 until their first RED) */
+#define PFA_FLAG_INKERNEL_ZERO 2
 
 	typedef struct pfa_handle pfa_handle;
 

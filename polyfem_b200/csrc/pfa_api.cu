@@ -44,6 +44,7 @@ struct pfa_handle
 	double *s_x = nullptr, *s_grad = nullptr, *s_values = nullptr, *s_epe = nullptr;
 	double *d_energy = nullptr;
 	int *d_counter = nullptr;
+	int32_t epoch = 0; // in-kernel zero-fill generation (row-lane kernels)
 
 	std::vector<int32_t> h_outer, h_inner;
 	std::vector<int32_t> h_adj_off, h_adj;
@@ -248,7 +249,9 @@ namespace
 				PFA_CUDA(h, cudaMemsetAsync(a.energy, 0, sizeof(double), h->stream));
 			if (a.grad)
 				PFA_CUDA(h, cudaMemsetAsync(a.grad, 0, size_t(h->ndof) * sizeof(double), h->stream));
-			if (a.values)
+			if (a.values && h->dm.zoff != nullptr && !linear)
+				a.epoch = ++h->epoch; // the row-lane kernel clears values[] itself, block by block, just ahead of the scatter
+			else if (a.values)
 				PFA_CUDA(h, cudaMemsetAsync(a.values, 0, size_t(h->nnz) * sizeof(double), h->stream));
 			prof_end(h);
 		}
@@ -464,7 +467,24 @@ extern "C"
 				}
 			UP(m.entry, hp.slot.data(), size_t(ne) * nl * nl, int32_t);
 			UP(m.cstride, cstride.data(), ne * nl, int32_t);
-			PFA_CUDA(h, cudaStreamSynchronize(h->stream)); // cstride is a local
+			// in-kernel zero fill of values[] (opt-in): who clears which column block
+			std::vector<int32_t> zoff, zruns;
+			if (d->flags & PFA_FLAG_INKERNEL_ZERO)
+			{
+			build_zero_schedule(conn_in, m.n_el, m.n_loc, m.n_bases, hp.adj_off, m.size, rowlane_batch_elements(m.n_loc, m.n_qp), zoff, zruns);
+			m.n_batches = int32_t(zoff.size()) - 1;
+			UP(m.zoff, zoff.data(), zoff.size(), int32_t);
+			{
+				int32_t *zr = nullptr;
+				if ((rc = dev_upload<int32_t>(h, &zr, zruns.data(), zruns.size())) != PFA_OK)
+					return bail(rc);
+				m.zruns = reinterpret_cast<const int2 *>(zr);
+			}
+			if ((rc = dev_alloc<int32_t>(h, &m.zflag, size_t(m.n_batches))) != PFA_OK)
+				return bail(rc);
+			PFA_CUDA(h, cudaMemsetAsync(m.zflag, 0, size_t(m.n_batches) * sizeof(int32_t), h->stream));
+			}
+			PFA_CUDA(h, cudaStreamSynchronize(h->stream)); // cstride, zoff, zruns are locals
 		}
 		else
 			UP(m.slot, hp.slot.data(), size_t(ne) * nl * nl, int32_t);

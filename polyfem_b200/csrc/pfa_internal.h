@@ -40,6 +40,13 @@ namespace pfa
 		// the three scalar columns of node g_j. When these are set, `slot` is not uploaded.
 		const int32_t *entry = nullptr;
 		const int32_t *cstride = nullptr;
+		// in-kernel zero fill of values[] (row-lane kernels): the column blocks first touched by warp
+		// batch b are the runs zruns[zoff[b] .. zoff[b+1]) = (first double, number of doubles); they are
+		// cleared by batch b - kZeroLookahead, which then publishes zflag[b] = epoch
+		const int32_t *zoff = nullptr;
+		const int2 *zruns = nullptr;
+		int32_t *zflag = nullptr;
+		int32_t n_batches = 0;
 		// elements are stored in an internal (spatially sorted, L2-friendly) order; elem_id[e] is the
 		// caller's index of internal element e (nullptr = identity)
 		const int32_t *elem_id = nullptr;
@@ -54,6 +61,7 @@ namespace pfa
 		double *values = nullptr;        // [nnz]  (accumulated, zeroed by caller)
 		int project_to_psd = 0;
 		int *work_counter = nullptr; // device int, zeroed before the launch (dynamic batch hand-out)
+		int32_t epoch = 0;           // > 0: values[] is zero-filled inside the kernel (see DeviceMesh::zoff)
 	};
 
 	// kernel launchers (pfa_kernels.cu). Return cudaError_t of the launch.
@@ -65,6 +73,15 @@ namespace pfa
 	bool assemble_supported(const DeviceMesh &m);
 	// true when launch_assemble uses the row-lane kernels (which read entry/cstride instead of slot)
 	bool rowlane_applies(int material, int n_loc, int n_qp);
+	// elements per warp batch of the row-lane kernel for this element type
+	int rowlane_batch_elements(int n_loc, int n_qp);
+#ifndef PFA_ZERO_LOOKAHEAD
+#define PFA_ZERO_LOOKAHEAD 64
+#endif
+	constexpr int kZeroLookahead = PFA_ZERO_LOOKAHEAD; // batches between clearing a column block and its first use
+	// zero-fill schedule of the row-lane kernels (host, once per mesh): zoff[n_batches+1], runs (start, length)
+	void build_zero_schedule(const int32_t *conn, int n_el, int n_loc, int n_bases, const std::vector<int32_t> &adj_off, int size, int batch_elements,
+							 std::vector<int32_t> &zoff, std::vector<int32_t> &zruns);
 
 	// ---- host-side pattern + slot map (pfa_pattern.cu) ----
 	struct HostPattern

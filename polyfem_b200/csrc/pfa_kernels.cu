@@ -37,6 +37,13 @@ namespace pfa
 			return F[0] * (F[4] * F[8] - F[5] * F[7]) - F[1] * (F[3] * F[8] - F[5] * F[6]) + F[2] * (F[3] * F[7] - F[4] * F[6]);
 		}
 
+		// fire-and-forget reduction (REDG): spelled in PTX so that fences elsewhere in a kernel do not
+		// make the compiler fall back to the returning form (ATOMG)
+		__device__ __forceinline__ void red_add(double *p, double v)
+		{
+			asm volatile("red.global.add.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
+		}
+
 		// cofactor matrix C = dJ/dF (row-major), columns are cross products of the columns of F
 		__device__ __forceinline__ void cofactor3(const double *F, double *C)
 		{
@@ -464,6 +471,34 @@ namespace pfa
 			}
 		};
 
+		// In-kernel zero fill of values[] (DeviceMesh::zoff): the warp that draws batch index bi clears
+		// the column blocks first touched by batch bi + kZeroLookahead (the first kZeroLookahead
+		// batches also clear their own) and publishes zflag = epoch for them.
+		__device__ __forceinline__ void zero_duty(const DeviceMesh &m, const AssembleArgs &a, int bi, int lane)
+		{
+			if (bi >= m.n_batches)
+				return;
+			for (int pass = (bi < kZeroLookahead ? 0 : 1); pass < 2; ++pass)
+			{
+				const int zb = pass == 0 ? bi : bi + kZeroLookahead;
+				if (zb < m.n_batches)
+				{
+					const int r0 = m.zoff[zb], r1 = m.zoff[zb + 1];
+					for (int rr = r0; rr < r1; ++rr)
+					{
+						const int2 run = m.zruns[rr];
+						double *dst = a.values + size_t(run.x);
+						for (int t = lane; t < run.y; t += 32)
+							dst[t] = 0.0;
+					}
+					__threadfence();
+					__syncwarp();
+					if (lane == 0)
+						*reinterpret_cast<volatile int32_t *>(m.zflag + zb) = a.epoch;
+				}
+			}
+		}
+
 		template <int NL, int NQ, int WARPS, int MINB>
 		__global__ void __launch_bounds__(WARPS * 32, MINB) assemble_nh_rowlane_kernel(const DeviceMesh m, const AssembleArgs a)
 		{
@@ -500,6 +535,8 @@ namespace pfa
 			if (lane == 0)
 				batch = atomicAdd(a.work_counter, EB);
 			batch = __shfl_sync(0xffffffffu, batch, 0);
+			if (a.epoch > 0)
+				zero_duty(m, a, batch / EB, lane);
 			while (batch < m.n_el)
 			{
 				int next = 0;
@@ -622,6 +659,24 @@ namespace pfa
 				}
 				if (want_h)
 					asm volatile("cp.async.wait_group 0;" ::: "memory");
+				const int next_batch = __shfl_sync(0xffffffffu, next, 0);
+				if (a.epoch > 0)
+				{
+					// zero-fill duty of the batch index just drawn: clear the column blocks first touched
+					// kZeroLookahead batches after it and publish their flag. The duty is tied to the
+					// DRAW of an index (draws are ordered in time), not to the start of its processing.
+					zero_duty(m, a, next_batch / EB, lane);
+					// the blocks this batch is the first to touch were cleared by the warp that drew batch
+					// index - kZeroLookahead; blocks first touched by earlier batches transitively earlier
+					if (lane == 0)
+					{
+						const volatile int32_t *flag = m.zflag + batch / EB;
+						while (*flag != a.epoch)
+							__nanosleep(64);
+					}
+					__syncwarp();
+					__threadfence();
+				}
 				__syncwarp();
 
 				// ---- phase 2 ----
@@ -691,15 +746,15 @@ namespace pfa
 								{
 									double *dst = a.values + (size_t(ent[j]) + mm);
 									const size_t cs = size_t(st[j]);
-									atomicAdd(dst, acc[j][0]);
-									atomicAdd(dst + cs, acc[j][1]);
-									atomicAdd(dst + 2 * cs, acc[j][2]);
+									red_add(dst, acc[j][0]);
+									red_add(dst + cs, acc[j][1]);
+									red_add(dst + 2 * cs, acc[j][2]);
 								}
 							}
 						}
 					}
 				}
-				batch = __shfl_sync(0xffffffffu, next, 0);
+				batch = next_batch;
 			}
 
 			if (want_e && a.energy != nullptr)
@@ -828,6 +883,11 @@ namespace pfa
 	bool rowlane_applies(int material, int n_loc, int n_qp)
 	{
 		return material == PFA_NEOHOOKEAN && ((n_loc == 10 && n_qp == 4) || (n_loc == 4 && n_qp == 1));
+	}
+
+	int rowlane_batch_elements(int n_loc, int n_qp)
+	{
+		return n_loc == 4 ? RowLane<4, 1>::EB : RowLane<10, 4>::EB;
 	}
 
 	bool assemble_supported(const DeviceMesh &m)

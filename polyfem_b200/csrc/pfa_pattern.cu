@@ -171,4 +171,72 @@ namespace pfa
 		for (int64_t el = 0; el < n_el; ++el)
 			perm[size_t(el)] = keyed[size_t(el)].second;
 	}
+
+	// Which warp batch touches a node's column block first decides who clears it: the block of
+	// node b (values[size^2 adj_off[b] .. size^2 adj_off[b+1])) goes to the list of batch
+	// first(b) = min element index containing b / batch_elements. Nodes no computed element touches
+	// (pattern-only ghost connectivity) are spread round-robin. Neighbouring blocks are merged.
+	void build_zero_schedule(const int32_t *conn, int n_el, int n_loc, int n_bases, const std::vector<int32_t> &adj_off, int size, int batch_elements,
+							 std::vector<int32_t> &zoff, std::vector<int32_t> &zruns)
+	{
+		const int n_batches = (n_el + batch_elements - 1) / batch_elements;
+		std::vector<int32_t> first;
+		first.assign(size_t(n_bases), -1);
+		for (int e = 0; e < n_el; ++e)
+			for (int j = 0; j < n_loc; ++j)
+			{
+				int32_t &f = first[size_t(conn[size_t(e) * n_loc + j])];
+				if (f < 0)
+					f = e / batch_elements; // elements are visited in increasing order
+			}
+		std::vector<int32_t> count;
+		count.assign(size_t(n_batches) + 1, 0);
+		int rr = 0;
+		for (int b = 0; b < n_bases; ++b)
+		{
+			if (first[b] < 0)
+				first[b] = (rr++) % n_batches;
+			++count[size_t(first[b]) + 1];
+		}
+		for (int k = 0; k < n_batches; ++k)
+			count[size_t(k) + 1] += count[k];
+		std::vector<int32_t> nodes;
+		nodes.resize(size_t(n_bases));
+		std::vector<int32_t> pos(count.begin(), count.end() - 1);
+		for (int b = 0; b < n_bases; ++b) // increasing b inside every list
+			nodes[size_t(pos[first[b]]++)] = b;
+		zoff.assign(size_t(n_batches) + 1, 0);
+		zruns.clear();
+		zruns.reserve(size_t(n_bases) * 2);
+		const int64_t s2 = int64_t(size) * size;
+		for (int k = 0; k < n_batches; ++k)
+		{
+			int64_t run_start = -1, run_end = -1;
+			for (int32_t t = count[k]; t < count[size_t(k) + 1]; ++t)
+			{
+				const int b = nodes[size_t(t)];
+				const int64_t s = s2 * adj_off[size_t(b)], e = s2 * adj_off[size_t(b) + 1];
+				if (e == s)
+					continue;
+				if (s == run_end)
+					run_end = e;
+				else
+				{
+					if (run_end > run_start)
+					{
+						zruns.push_back(int32_t(run_start));
+						zruns.push_back(int32_t(run_end - run_start));
+					}
+					run_start = s;
+					run_end = e;
+				}
+			}
+			if (run_end > run_start)
+			{
+				zruns.push_back(int32_t(run_start));
+				zruns.push_back(int32_t(run_end - run_start));
+			}
+			zoff[size_t(k) + 1] = int32_t(zruns.size() / 2);
+		}
+	}
 } // namespace pfa

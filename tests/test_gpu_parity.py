@@ -175,3 +175,36 @@ def test_interface_mirror_reads_like_reference_test(oracle):
         assert abs(hessian - stiffness).max() < 1e-8
     with pytest.raises(RuntimeError):
         A.make_assembler("MooneyRivlin")
+
+
+@pytest.mark.parametrize("p,n", [(1, 5), (2, 4)])
+@pytest.mark.parametrize("flags", [1, 2, 3])
+def test_create_flags_do_not_change_results(oracle, p, n, flags):
+    """pfa_mesh_desc.flags (caller element order kept; values[] cleared inside the kernel) change
+    the schedule only: same pattern, same values, per-element energies in the caller's order."""
+    mesh, x, t = make_case(n, p, jitter=0.15)
+    ref = oracle.problem_from_mesh(mesh, "NeoHookean", n_threads=2)
+    h = gpu_handle(mesh, "NeoHookean", t, flags=flags)
+    H = ref.assemble_hessian(x)
+    for rep in range(3):  # repeated calls: the in-kernel zero fill must not leave stale sums
+        e, g, v = h.grad_hess(x)
+        assert abs(e - ref.assemble_energy(x)) <= REL_TOL * abs(e)
+        assert_vector_close(g, ref.assemble_gradient(x))
+        assert_values_close(H.outer, H.inner, v, H.values)
+    epe = h.energy_per_element(x)
+    epe_ref = ref.assemble_energy_per_element(x)
+    assert np.abs(epe - epe_ref).max() <= REL_TOL * np.abs(epe_ref).max()
+
+
+def test_two_quadrature_tables_in_one_process(oracle):
+    """The reference gradients of the column side live in one __constant__ slot per basis order;
+    handles with different tables for the same order must still give their own results."""
+    mesh, x, t = make_case(3, 2)
+    ref = oracle.problem_from_mesh(mesh, "NeoHookean")
+    h1 = gpu_handle(mesh, "NeoHookean", t)
+    # same rule with the quadrature points listed in reverse order: a different table, same integrals
+    t2 = {k: (v[::-1].copy() if k in ("points", "weights", "val", "grad") else v) for k, v in t.items()}
+    h2 = gpu_handle(mesh, "NeoHookean", t2)
+    H = ref.assemble_hessian(x)
+    for h in (h1, h2, h1, h2):
+        assert_values_close(H.outer, H.inner, h.hessian(x), H.values)
