@@ -208,8 +208,12 @@ namespace
 	{
 		h->err.clear();
 		PFA_CUDA(h, cudaSetDevice(h->device));
-		if (project_to_psd)
-			return fail(h, PFA_ERR_UNSUPPORTED, "project_to_psd is not implemented on the GPU path yet");
+		if (project_to_psd && !(values != nullptr && rowlane_applies(h->dm.material, h->dm.n_loc, h->dm.n_qp)))
+		{
+			if (values != nullptr)
+				return fail(h, PFA_ERR_UNSUPPORTED, "project_to_psd is implemented for NeoHookean P1/P2 tets only");
+			project_to_psd = 0; // no Hessian requested: nothing to project
+		}
 		if (h->dm.material == PFA_LAPLACIAN && !linear)
 			return fail(h, PFA_ERR_UNSUPPORTED, "Laplacian is a LinearAssembler: only pfa_linear_stiffness applies");
 		if (h->dm.material == PFA_NEOHOOKEAN && linear)
@@ -249,7 +253,7 @@ namespace
 				PFA_CUDA(h, cudaMemsetAsync(a.energy, 0, sizeof(double), h->stream));
 			if (a.grad)
 				PFA_CUDA(h, cudaMemsetAsync(a.grad, 0, size_t(h->ndof) * sizeof(double), h->stream));
-			if (a.values && h->dm.zoff != nullptr && !linear)
+			if (a.values && h->dm.zoff != nullptr && !linear && !project_to_psd)
 				a.epoch = ++h->epoch; // the row-lane kernel clears values[] itself, block by block, just ahead of the scatter
 			else if (a.values)
 				PFA_CUDA(h, cudaMemsetAsync(a.values, 0, size_t(h->nnz) * sizeof(double), h->stream));

@@ -824,6 +824,409 @@ namespace pfa
 			return cudaGetLastError();
 		}
 
+		// ------------------------------------------------------------------------------------
+		// NeoHookean P1/P2 with project_to_psd (Assembler.cpp:693-694, ipc::project_to_psd): one
+		// warp per element. The local Hessian is formed with the same row-lane math as above, put
+		// in shared memory, diagonalised by a parallel cyclic Jacobi method (round-robin ordering:
+		// N/2 disjoint rotations per step, lanes <-> rows), and, if its smallest eigenvalue is
+		// negative, rebuilt as V max(D, 0) V^T before the scatter. Matrices with non-finite
+		// entries and matrices that are already PSD are scattered unchanged (as the oracle does).
+		// ------------------------------------------------------------------------------------
+		template <int NL, int NQ, int WARPS>
+		struct PsdLayout
+		{
+			static constexpr int N = 3 * NL;
+			static constexpr int LD = N | 1; // odd leading dimension: conflict-free row- and column-wise access
+			static constexpr int REC = 35;
+			static constexpr int WARP_DOUBLES = NQ * REC + 2 * N * LD + 2 * (N / 2);
+			static constexpr int WARP_INTS = 2 * (N / 2) + 2 * NL + NL * NL;
+			static size_t smem_bytes()
+			{
+				return sizeof(double) * (size_t(NQ) * NL * 3 + ((NQ + 1) & ~1) + size_t(WARPS) * WARP_DOUBLES) + sizeof(int) * size_t(WARPS) * WARP_INTS;
+			}
+		};
+
+		template <int NL, int NQ, int WARPS>
+		__global__ void __launch_bounds__(WARPS * 32) assemble_nh_psd_kernel(const DeviceMesh m, const AssembleArgs a)
+		{
+			using PL = PsdLayout<NL, NQ, WARPS>;
+			constexpr int N = PL::N, LD = PL::LD, REC = PL::REC, SLOT = RowLane<NL, NQ>::SLOT, HALF = N / 2;
+			extern __shared__ double smem[];
+			const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+			double *s_rg = smem;
+			double *s_w = s_rg + NQ * NL * 3;
+			double *ws = s_w + ((NQ + 1) & ~1) + warp * PL::WARP_DOUBLES;
+			double *s_rec = ws, *sA = ws + NQ * REC, *sV = sA + N * LD, *sC = sV + N * LD, *sS = sC + HALF;
+			int *wi = reinterpret_cast<int *>(s_w + ((NQ + 1) & ~1) + WARPS * PL::WARP_DOUBLES) + warp * PL::WARP_INTS;
+			int *sP = wi, *sQ = wi + HALF, *sG = wi + 2 * HALF, *sStride = sG + NL, *sEnt = sStride + NL;
+			for (int t = threadIdx.x; t < NQ * NL * 3; t += WARPS * 32)
+				s_rg[t] = m.ref_grads[t];
+			for (int t = threadIdx.x; t < NQ; t += WARPS * 32)
+				s_w[t] = m.qweights[t];
+			__syncthreads();
+
+			const bool want_g = a.grad != nullptr;
+			const bool want_e = a.energy != nullptr || a.energy_per_el != nullptr;
+			double energy_acc = 0.0;
+			const int ri = lane / 3, mm = lane % 3;
+			const int ra = (mm + 1) % 3, rb = (mm + 2) % 3;
+			const bool row_lane = lane < N;
+
+			for (int e = blockIdx.x * WARPS + warp; e < m.n_el; e += gridDim.x * WARPS)
+			{
+				for (int t = lane; t < NL; t += 32)
+				{
+					sG[t] = m.conn[size_t(e) * NL + t];
+					sStride[t] = m.cstride[size_t(e) * NL + t];
+				}
+				for (int t = lane; t < NL * NL; t += 32)
+					sEnt[t] = m.entry[size_t(e) * NL * NL + t];
+				__syncwarp();
+				// ---- phase 1: lane <-> quadrature point ----
+				double e_q = 0.0;
+				if (lane < NQ)
+				{
+					const int q = lane;
+					double *rec = s_rec + q * REC;
+					const size_t gi = m.geom_per_qp ? size_t(e) * NQ + q : size_t(e);
+					double J[9];
+#pragma unroll
+					for (int k = 0; k < 9; ++k)
+						J[k] = m.jit[gi * 9 + k];
+					const double da = m.geom_per_qp ? m.detj[gi] : m.detj[e] * s_w[q];
+					const size_t mi = size_t(e) * m.mat_stride + (m.mat_stride == 1 ? 0 : q);
+					const double lam = m.lambda[mi], mu = m.mu[mi];
+					double F[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+					for (int i = 0; i < NL; ++i)
+					{
+						const int g = sG[i];
+						const double u0 = a.x[size_t(g) * 3 + 0], u1 = a.x[size_t(g) * 3 + 1], u2 = a.x[size_t(g) * 3 + 2];
+						const double *rr = s_rg + (q * NL + i) * 3;
+						const double d0 = rr[0] * J[0] + rr[1] * J[3] + rr[2] * J[6];
+						const double d1 = rr[0] * J[1] + rr[1] * J[4] + rr[2] * J[7];
+						const double d2 = rr[0] * J[2] + rr[1] * J[5] + rr[2] * J[8];
+						F[0] += u0 * d0;
+						F[1] += u0 * d1;
+						F[2] += u0 * d2;
+						F[3] += u1 * d0;
+						F[4] += u1 * d1;
+						F[5] += u1 * d2;
+						F[6] += u2 * d0;
+						F[7] += u2 * d1;
+						F[8] += u2 * d2;
+					}
+					const double Jd = det3(F);
+					const double lJ = log(Jd);
+					double C[9];
+					cofactor3(F, C);
+					const double invJ = 1.0 / Jd;
+					const double pc = (lam * lJ - mu) * invJ;
+					double sq = 0.0;
+					for (int k = 0; k < 9; ++k)
+						sq += F[k] * F[k];
+					e_q = (0.5 * mu * (sq - 3.0 - 2.0 * lJ) + 0.5 * lam * lJ * lJ) * da;
+					for (int aa = 0; aa < 3; ++aa)
+					{
+						const double p0 = (mu * F[aa * 3 + 0] + pc * C[aa * 3 + 0]) * da;
+						const double p1 = (mu * F[aa * 3 + 1] + pc * C[aa * 3 + 1]) * da;
+						const double p2 = (mu * F[aa * 3 + 2] + pc * C[aa * 3 + 2]) * da;
+						for (int c = 0; c < 3; ++c)
+							rec[24 + aa * 3 + c] = p0 * J[c * 3 + 0] + p1 * J[c * 3 + 1] + p2 * J[c * 3 + 2];
+					}
+					const double mu_da = mu * da;
+					rec[0] = mu_da * (J[0] * J[0] + J[1] * J[1] + J[2] * J[2]);
+					rec[1] = mu_da * (J[0] * J[3] + J[1] * J[4] + J[2] * J[5]);
+					rec[2] = mu_da * (J[0] * J[6] + J[1] * J[7] + J[2] * J[8]);
+					rec[3] = mu_da * (J[3] * J[3] + J[4] * J[4] + J[5] * J[5]);
+					rec[4] = mu_da * (J[3] * J[6] + J[4] * J[7] + J[5] * J[8]);
+					rec[5] = mu_da * (J[6] * J[6] + J[7] * J[7] + J[8] * J[8]);
+					double R[9];
+					cofactor3(J, R);
+					const double c2da = pc * da;
+					for (int rr = 0; rr < 3; ++rr)
+					{
+						const double f0 = c2da * F[rr * 3 + 0], f1 = c2da * F[rr * 3 + 1], f2 = c2da * F[rr * 3 + 2];
+						for (int k = 0; k < 3; ++k)
+							rec[6 + rr * 3 + k] = f0 * R[k * 3 + 0] + f1 * R[k * 3 + 1] + f2 * R[k * 3 + 2];
+						for (int c = 0; c < 3; ++c)
+							rec[15 + rr * 3 + c] = C[rr * 3 + 0] * J[c * 3 + 0] + C[rr * 3 + 1] * J[c * 3 + 1] + C[rr * 3 + 2] * J[c * 3 + 2];
+					}
+					rec[33] = (mu + lam * (1.0 - lJ)) * invJ * invJ * da;
+				}
+				if (want_e)
+				{
+#pragma unroll
+					for (int k = 1; k < NQ; k <<= 1)
+						e_q += __shfl_xor_sync(0xffffffffu, e_q, k);
+					if (lane == 0)
+					{
+						energy_acc += e_q;
+						if (a.energy_per_el != nullptr)
+							a.energy_per_el[m.elem_id ? m.elem_id[e] : e] = e_q;
+					}
+				}
+				__syncwarp();
+
+				// ---- phase 2: row (i, m) of the local Hessian in registers ----
+				double acc[NL][3];
+#pragma unroll
+				for (int j = 0; j < NL; ++j)
+					acc[j][0] = acc[j][1] = acc[j][2] = 0.0;
+				double g_row = 0.0;
+				if (row_lane)
+				{
+#pragma unroll 1
+					for (int qq = 0; qq < NQ; ++qq)
+					{
+						const double *rec = s_rec + qq * REC;
+						const double *gr = s_rg + (qq * NL + ri) * 3;
+						const double g0 = gr[0], g1 = gr[1], g2 = gr[2];
+						const double *pj = rec + 24 + mm * 3;
+						g_row = fma(g0, pj[0], fma(g1, pj[1], fma(g2, pj[2], g_row)));
+						const double K00 = rec[0], K01 = rec[1], K02 = rec[2], K11 = rec[3], K12 = rec[4], K22 = rec[5];
+						const double v0 = K00 * g0 + K01 * g1 + K02 * g2;
+						const double v1 = K01 * g0 + K11 * g1 + K12 * g2;
+						const double v2 = K02 * g0 + K12 * g1 + K22 * g2;
+						const double *ta = rec + 6 + ra * 3, *tb = rec + 6 + rb * 3;
+						const double b0 = tb[1] * g2 - tb[2] * g1, b1 = tb[2] * g0 - tb[0] * g2, b2 = tb[0] * g1 - tb[1] * g0;
+						const double a0 = ta[2] * g1 - ta[1] * g2, a1 = ta[0] * g2 - ta[2] * g0, a2 = ta[1] * g0 - ta[0] * g1;
+						const double *cj = rec + 15;
+						const double cA = rec[33] * (cj[mm * 3 + 0] * g0 + cj[mm * 3 + 1] * g1 + cj[mm * 3 + 2] * g2);
+						double Y[3][3];
+						Y[0][0] = fma(cA, cj[0], mm == 0 ? v0 : (mm == 1 ? a0 : b0));
+						Y[0][1] = fma(cA, cj[1], mm == 0 ? v1 : (mm == 1 ? a1 : b1));
+						Y[0][2] = fma(cA, cj[2], mm == 0 ? v2 : (mm == 1 ? a2 : b2));
+						Y[1][0] = fma(cA, cj[3], mm == 1 ? v0 : (mm == 2 ? a0 : b0));
+						Y[1][1] = fma(cA, cj[4], mm == 1 ? v1 : (mm == 2 ? a1 : b1));
+						Y[1][2] = fma(cA, cj[5], mm == 1 ? v2 : (mm == 2 ? a2 : b2));
+						Y[2][0] = fma(cA, cj[6], mm == 2 ? v0 : (mm == 0 ? a0 : b0));
+						Y[2][1] = fma(cA, cj[7], mm == 2 ? v1 : (mm == 0 ? a1 : b1));
+						Y[2][2] = fma(cA, cj[8], mm == 2 ? v2 : (mm == 0 ? a2 : b2));
+#pragma unroll
+						for (int j = 0; j < NL; ++j)
+						{
+							const double *cg = &c_refgrad[SLOT][(qq * NL + j) * 3];
+							const double c0 = cg[0], c1 = cg[1], c2 = cg[2];
+							acc[j][0] = fma(Y[0][0], c0, fma(Y[0][1], c1, fma(Y[0][2], c2, acc[j][0])));
+							acc[j][1] = fma(Y[1][0], c0, fma(Y[1][1], c1, fma(Y[1][2], c2, acc[j][1])));
+							acc[j][2] = fma(Y[2][0], c0, fma(Y[2][1], c1, fma(Y[2][2], c2, acc[j][2])));
+						}
+					}
+					// local Hessian row -> shared memory; V = identity
+#pragma unroll
+					for (int j = 0; j < NL; ++j)
+					{
+						sA[lane * LD + j * 3 + 0] = acc[j][0];
+						sA[lane * LD + j * 3 + 1] = acc[j][1];
+						sA[lane * LD + j * 3 + 2] = acc[j][2];
+					}
+					for (int c = 0; c < N; ++c)
+						sV[lane * LD + c] = c == lane ? 1.0 : 0.0;
+				}
+				__syncwarp();
+				// the solver reads one triangle (SelfAdjointEigenSolver): mirror the lower one
+				bool finite = true;
+				if (row_lane)
+				{
+					for (int c = lane + 1; c < N; ++c)
+						sA[lane * LD + c] = sA[c * LD + lane];
+				}
+				__syncwarp();
+				if (row_lane)
+				{
+					for (int c = 0; c < N; ++c)
+						finite = finite && isfinite(sA[lane * LD + c]);
+				}
+				finite = __all_sync(0xffffffffu, finite);
+				bool nonzero = false;
+				if (row_lane)
+					for (int c = 0; c < N; ++c)
+						nonzero = nonzero || sA[lane * LD + c] != 0.0;
+				nonzero = __any_sync(0xffffffffu, nonzero);
+
+				if (finite && nonzero)
+				{
+					for (int sweep = 0; sweep < 100; ++sweep)
+					{
+						double off = 0.0, diag = 0.0;
+						if (row_lane)
+							for (int c = 0; c < N; ++c)
+							{
+								const double v = sA[lane * LD + c];
+								if (c == lane)
+									diag += v * v;
+								else
+									off += v * v;
+							}
+#pragma unroll
+						for (int o = 16; o > 0; o >>= 1)
+						{
+							off += __shfl_xor_sync(0xffffffffu, off, o);
+							diag += __shfl_xor_sync(0xffffffffu, diag, o);
+						}
+						if (off <= 1e-30 * diag || off == 0.0)
+							break;
+						for (int step = 0; step < N - 1; ++step)
+						{
+							// round-robin pairing: (N-1, step), ((step+k) mod (N-1), (step-k) mod (N-1))
+							if (lane < HALF)
+							{
+								int p, q;
+								if (lane == 0)
+								{
+									p = step;
+									q = N - 1;
+								}
+								else
+								{
+									p = (step + lane) % (N - 1);
+									q = (step - lane + (N - 1)) % (N - 1);
+								}
+								if (p > q)
+								{
+									const int t = p;
+									p = q;
+									q = t;
+								}
+								const double apq = sA[p * LD + q];
+								double c = 1.0, sn = 0.0;
+								if (apq != 0.0)
+								{
+									const double app = sA[p * LD + p], aqq = sA[q * LD + q];
+									const double theta = (aqq - app) / (2.0 * apq);
+									const double t = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+									c = 1.0 / sqrt(t * t + 1.0);
+									sn = t * c;
+								}
+								sP[lane] = p;
+								sQ[lane] = q;
+								sC[lane] = c;
+								sS[lane] = sn;
+							}
+							__syncwarp();
+							if (row_lane) // A <- A J and V <- V J: lane = row
+							{
+								for (int k = 0; k < HALF; ++k)
+								{
+									const int p = sP[k], q = sQ[k];
+									const double c = sC[k], sn = sS[k];
+									const double akp = sA[lane * LD + p], akq = sA[lane * LD + q];
+									sA[lane * LD + p] = c * akp - sn * akq;
+									sA[lane * LD + q] = sn * akp + c * akq;
+									const double vkp = sV[lane * LD + p], vkq = sV[lane * LD + q];
+									sV[lane * LD + p] = c * vkp - sn * vkq;
+									sV[lane * LD + q] = sn * vkp + c * vkq;
+								}
+							}
+							__syncwarp();
+							if (row_lane) // A <- J^T A: lane = column
+							{
+								for (int k = 0; k < HALF; ++k)
+								{
+									const int p = sP[k], q = sQ[k];
+									const double c = sC[k], sn = sS[k];
+									const double apk = sA[p * LD + lane], aqk = sA[q * LD + lane];
+									sA[p * LD + lane] = c * apk - sn * aqk;
+									sA[q * LD + lane] = sn * apk + c * aqk;
+								}
+							}
+							__syncwarp();
+						}
+					}
+					double w = row_lane ? sA[lane * LD + lane] : 0.0;
+					double wmin = row_lane ? w : 1e300;
+#pragma unroll
+					for (int o = 16; o > 0; o >>= 1)
+						wmin = fmin(wmin, __shfl_xor_sync(0xffffffffu, wmin, o));
+					if (wmin < 0.0)
+					{
+						// rebuild row `lane` of V max(D,0) V^T; the clamped eigenvalues go to sC-like scratch in sA's diagonal
+						__syncwarp();
+						if (row_lane)
+							sA[lane * LD + lane] = w < 0.0 ? 0.0 : w;
+						__syncwarp();
+						if (row_lane)
+						{
+#pragma unroll
+							for (int j = 0; j < NL; ++j)
+#pragma unroll
+								for (int n = 0; n < 3; ++n)
+								{
+									const int c = j * 3 + n;
+									double sum = 0.0;
+									for (int k = 0; k < N; ++k)
+										sum += sV[lane * LD + k] * sA[k * LD + k] * sV[c * LD + k];
+									acc[j][n] = sum;
+								}
+						}
+					}
+				}
+				__syncwarp();
+
+				// ---- scatter ----
+				if (row_lane)
+				{
+					if (want_g)
+						atomicAdd(a.grad + size_t(sG[ri]) * 3 + mm, g_row);
+					if (a.values != nullptr)
+					{
+#pragma unroll
+						for (int j = 0; j < NL; ++j)
+						{
+							double *dst = a.values + (size_t(sEnt[ri * NL + j]) + mm);
+							const size_t cs = size_t(sStride[j]);
+							red_add(dst, acc[j][0]);
+							red_add(dst + cs, acc[j][1]);
+							red_add(dst + 2 * cs, acc[j][2]);
+						}
+					}
+				}
+				__syncwarp();
+			}
+
+			if (want_e && a.energy != nullptr)
+			{
+				__shared__ double s_e[WARPS];
+#pragma unroll
+				for (int o = 16; o > 0; o >>= 1)
+					energy_acc += __shfl_xor_sync(0xffffffffu, energy_acc, o);
+				if (lane == 0)
+					s_e[warp] = energy_acc;
+				__syncthreads();
+				if (threadIdx.x == 0)
+				{
+					double t = 0.0;
+					for (int w = 0; w < WARPS; ++w)
+						t += s_e[w];
+					atomicAdd(a.energy, t);
+				}
+			}
+		}
+
+		template <int NL, int NQ, int WARPS>
+		cudaError_t launch_psd(const DeviceMesh &m, const AssembleArgs &a, int sm_count, cudaStream_t st)
+		{
+			using PL = PsdLayout<NL, NQ, WARPS>;
+			const size_t smem = PL::smem_bytes();
+			auto kern = assemble_nh_psd_kernel<NL, NQ, WARPS>;
+			cudaError_t err = ensure_const_table(m, RowLane<NL, NQ>::SLOT, st);
+			if (err != cudaSuccess)
+				return err;
+			err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+			if (err != cudaSuccess)
+				return err;
+			int per_sm = 1;
+			err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, WARPS * 32, smem);
+			if (err != cudaSuccess)
+				return err;
+			if (per_sm < 1)
+				per_sm = 1;
+			const int64_t need = (int64_t(m.n_el) + WARPS - 1) / WARPS;
+			const int grid = int(std::max<int64_t>(1, std::min<int64_t>(need, int64_t(sm_count) * per_sm)));
+			kern<<<grid, WARPS * 32, smem, st>>>(m, a);
+			return cudaGetLastError();
+		}
+
 		constexpr size_t kMaxSmem = 227 * 1024;
 
 		size_t generic_smem_bytes(int n_loc, int n_qp, int warps)
@@ -923,6 +1326,16 @@ namespace pfa
 		switch (m.material)
 		{
 		case PFA_NEOHOOKEAN:
+			if (a.project_to_psd)
+			{
+				if (kernel_name)
+					*kernel_name = "assemble_nh_psd_kernel";
+				if (m.n_loc == 10 && m.n_qp == 4)
+					return launch_psd<10, 4, 8>(m, a, sm_count, st);
+				if (m.n_loc == 4 && m.n_qp == 1)
+					return launch_psd<4, 1, 8>(m, a, sm_count, st);
+				return cudaErrorNotSupported;
+			}
 			if (m.n_loc == 10 && m.n_qp == 4)
 			{
 				if (kernel_name)
