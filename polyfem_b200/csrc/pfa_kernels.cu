@@ -26,6 +26,11 @@
 #ifndef PFA_RL_MINB_P2
 #define PFA_RL_MINB_P2 2
 #endif
+// timing experiments (tools/kbench.py, never in the product build): drop the column FMAs, drop
+// the scatter, or scatter with plain stores
+#ifndef PFA_EXP_MODE // bit 0: no phase-1 math, bit 1: no phase-2 math, bit 2: no scatter, bit 3: plain stores
+#define PFA_EXP_MODE 0
+#endif
 
 namespace pfa
 {
@@ -42,6 +47,14 @@ namespace pfa
 		__device__ __forceinline__ void red_add(double *p, double v)
 		{
 			asm volatile("red.global.add.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
+		}
+
+		// p ? a : b as SEL instructions (a ternary on doubles may be compiled into a divergent branch)
+		__device__ __forceinline__ double sel(int p, double a, double b)
+		{
+			double r;
+			asm("{ .reg .pred q; setp.ne.s32 q, %3, 0; selp.f64 %0, %1, %2, q; }" : "=d"(r) : "d"(a), "d"(b), "r"(p));
+			return r;
 		}
 
 		// cofactor matrix C = dJ/dF (row-major), columns are cross products of the columns of F
@@ -527,6 +540,7 @@ namespace pfa
 			const int sub = lane / ROWL, r = lane % ROWL;
 			const int ri = r / 3, mm = r % 3;
 			const int ra = (mm + 1) % 3, rb = (mm + 2) % 3;
+			const int is0 = mm == 0, is1 = mm == 1;
 			const bool row_lane = lane < EPW * ROWL;
 
 			// warp batches are handed out dynamically (one atomic per batch); the next index is
@@ -565,7 +579,14 @@ namespace pfa
 				const int e = batch + el;
 				const bool valid = lane < EB * NQ && e < m.n_el;
 				double e_q = 0.0;
+#if PFA_EXP_MODE & 1
 				if (valid)
+					for (int k = 0; k < 34; ++k)
+						s_rec[(el * NQ + q) * REC + k] = 1.0 + k;
+				if (false)
+#else
+				if (valid)
+#endif
 				{
 					double *rec = s_rec + (el * NQ + q) * REC;
 					const size_t gi = m.geom_per_qp ? size_t(e) * NQ + q : size_t(e);
@@ -695,8 +716,13 @@ namespace pfa
 								acc[j][0] = acc[j][1] = acc[j][2] = 0.0;
 							double g_row = 0.0;
 							constexpr int kUnrollQ = PFA_RL_UNROLL_Q;
+#if PFA_EXP_MODE & 2
+#pragma unroll
+							for (int j = 0; j < NL; ++j)
+								acc[j][0] = acc[j][1] = acc[j][2] = double(j + lane);
+#endif
 #pragma unroll kUnrollQ
-							for (int qq = 0; qq < NQ; ++qq)
+							for (int qq = 0; qq < ((PFA_EXP_MODE & 2) ? 0 : NQ); ++qq)
 							{
 								const double *rec = s_rec + (el2 * NQ + qq) * REC;
 								const double *gr = s_rg + (qq * NL + ri) * 3;
@@ -715,16 +741,18 @@ namespace pfa
 									const double a0 = ta[2] * g1 - ta[1] * g2, a1 = ta[0] * g2 - ta[2] * g0, a2 = ta[1] * g0 - ta[0] * g1; // -t_a x g
 									const double *cj = rec + 15;
 									const double cA = rec[33] * (cj[mm * 3 + 0] * g0 + cj[mm * 3 + 1] * g1 + cj[mm * 3 + 2] * g2);
+									// rotated rows: Y[s] is row n = (m + s) % 3 of the header's Y (no lane-dependent selects)
+									const double *c0r = cj + mm * 3, *c1r = cj + ra * 3, *c2r = cj + rb * 3;
 									double Y[3][3];
-									Y[0][0] = fma(cA, cj[0], mm == 0 ? v0 : (mm == 1 ? a0 : b0));
-									Y[0][1] = fma(cA, cj[1], mm == 0 ? v1 : (mm == 1 ? a1 : b1));
-									Y[0][2] = fma(cA, cj[2], mm == 0 ? v2 : (mm == 1 ? a2 : b2));
-									Y[1][0] = fma(cA, cj[3], mm == 1 ? v0 : (mm == 2 ? a0 : b0));
-									Y[1][1] = fma(cA, cj[4], mm == 1 ? v1 : (mm == 2 ? a1 : b1));
-									Y[1][2] = fma(cA, cj[5], mm == 1 ? v2 : (mm == 2 ? a2 : b2));
-									Y[2][0] = fma(cA, cj[6], mm == 2 ? v0 : (mm == 0 ? a0 : b0));
-									Y[2][1] = fma(cA, cj[7], mm == 2 ? v1 : (mm == 0 ? a1 : b1));
-									Y[2][2] = fma(cA, cj[8], mm == 2 ? v2 : (mm == 0 ? a2 : b2));
+									Y[0][0] = fma(cA, c0r[0], v0);
+									Y[0][1] = fma(cA, c0r[1], v1);
+									Y[0][2] = fma(cA, c0r[2], v2);
+									Y[1][0] = fma(cA, c1r[0], b0);
+									Y[1][1] = fma(cA, c1r[1], b1);
+									Y[1][2] = fma(cA, c1r[2], b2);
+									Y[2][0] = fma(cA, c2r[0], a0);
+									Y[2][1] = fma(cA, c2r[1], a1);
+									Y[2][2] = fma(cA, c2r[2], a2);
 #pragma unroll
 									for (int j = 0; j < NL; ++j)
 									{
@@ -741,15 +769,35 @@ namespace pfa
 							{
 								const int *ent = sEnt + el2 * NL * NL + ri * NL;
 								const int *st = sStride + el2 * NL;
+#if PFA_EXP_MODE & 4 // timing experiment: no scatter (the condition is never true)
+								double ssum = 0.0;
+#pragma unroll
+								for (int j = 0; j < NL; ++j)
+									ssum += acc[j][0] + acc[j][1] + acc[j][2];
+								if (ssum == 12345.6789)
+									red_add(a.values + ent[0] + st[0], ssum);
+#else
 #pragma unroll
 								for (int j = 0; j < NL; ++j)
 								{
 									double *dst = a.values + (size_t(ent[j]) + mm);
 									const size_t cs = size_t(st[j]);
-									red_add(dst, acc[j][0]);
-									red_add(dst + cs, acc[j][1]);
-									red_add(dst + 2 * cs, acc[j][2]);
+									// undo the rotation with selects so that one instruction still writes one column
+									// component n for all lanes (runs of 3 consecutive doubles per node)
+									const double o0 = sel(is0, acc[j][0], sel(is1, acc[j][2], acc[j][1]));
+									const double o1 = sel(is0, acc[j][1], sel(is1, acc[j][0], acc[j][2]));
+									const double o2 = sel(is0, acc[j][2], sel(is1, acc[j][1], acc[j][0]));
+#if PFA_EXP_MODE & 8 // timing experiment: plain stores instead of reductions (wrong values)
+									dst[0] = o0;
+									dst[cs] = o1;
+									dst[2 * cs] = o2;
+#else
+									red_add(dst, o0);
+									red_add(dst + cs, o1);
+									red_add(dst + 2 * cs, o2);
+#endif
 								}
+#endif
 							}
 						}
 					}
