@@ -450,6 +450,7 @@ extern "C"
 		UP(m.ref_grads, d->ref_grads, nq * nl * 3, double);
 		h->h_ref_grads.assign(d->ref_grads, d->ref_grads + nq * nl * 3);
 		m.ref_grads_host = h->h_ref_grads.data();
+		m.p2_structured = p2_table_structured(m.ref_grads_host, m.n_loc, m.n_qp) ? 1 : 0;
 		UP(m.qweights, d->quad_weights, nq, double);
 		UP(m.adj_off, hp.adj_off.data(), hp.adj_off.size(), int32_t);
 		UP(m.adj, hp.adj.data(), hp.adj.size(), int32_t);

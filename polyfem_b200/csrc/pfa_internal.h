@@ -27,6 +27,7 @@ namespace pfa
 		const double *ref_grads = nullptr; // [n_qp][n_loc][3]
 		const double *qweights = nullptr;  // [n_qp]
 		const double *ref_grads_host = nullptr; // host copy of ref_grads (owned by the handle): source of the __constant__ table
+		int32_t p2_structured = 0;              // ref_grads has the structural zeros / equal components of the P2 tet basis
 
 		// node-block CSR/CSC pattern (symmetric): adj_off[n_bases+1], adj[n_pairs] ascending
 		const int32_t *adj_off = nullptr;
@@ -73,6 +74,8 @@ namespace pfa
 	bool assemble_supported(const DeviceMesh &m);
 	// true when launch_assemble uses the row-lane kernels (which read entry/cstride instead of slot)
 	bool rowlane_applies(int material, int n_loc, int n_qp);
+	// exact structural zeros / equal components of the P2 tet basis gradients in a [n_qp][10][3] table
+	bool p2_table_structured(const double *ref_grads, int n_loc, int n_qp);
 	// elements per warp batch of the row-lane kernel for this element type
 	int rowlane_batch_elements(int n_loc, int n_qp);
 #ifndef PFA_ZERO_LOOKAHEAD

@@ -28,6 +28,12 @@
 #endif
 // timing experiments (tools/kbench.py, never in the product build): drop the column FMAs, drop
 // the scatter, or scatter with plain stores
+#ifndef PFA_RL_DENSE_COLUMNS // 1: never use the structured (P2S) column loop
+#define PFA_RL_DENSE_COLUMNS 0
+#endif
+#ifndef PFA_NO_LAPLACIAN_TILE // 1: Laplacian always through the generic kernel
+#define PFA_NO_LAPLACIAN_TILE 0
+#endif
 #ifndef PFA_EXP_MODE // bit 0: no phase-1 math, bit 1: no phase-2 math, bit 2: no scatter, bit 3: plain stores
 #define PFA_EXP_MODE 0
 #endif
@@ -512,7 +518,12 @@ namespace pfa
 			}
 		}
 
-		template <int NL, int NQ, int WARPS, int MINB>
+		// P2S: the reference-gradient table has the structural zeros / equal components of the P2 tet basis
+		// (auto_p_bases.cpp:1286-1344: grad phi_0 = c (1,1,1), grad phi_1..3 along one axis, phi_4 = (p,r,r),
+		// phi_5 = (a,b,0), phi_6 = (r,p,r), phi_7 = (r,r,p), phi_8 = (a,0,b), phi_9 = (0,a,b)) at every quadrature
+		// point, checked on the host (p2_structured); the column loop then needs 20 instead of 30 DFMA-pipe
+		// operations per (row lane, column component, quadrature point).
+		template <int NL, int NQ, int WARPS, int MINB, bool P2S>
 		__global__ void __launch_bounds__(WARPS * 32, MINB) assemble_nh_rowlane_kernel(const DeviceMesh m, const AssembleArgs a)
 		{
 			using RL = RowLane<NL, NQ>;
@@ -753,13 +764,36 @@ namespace pfa
 									Y[2][0] = fma(cA, c2r[0], a0);
 									Y[2][1] = fma(cA, c2r[1], a1);
 									Y[2][2] = fma(cA, c2r[2], a2);
-#pragma unroll
-									for (int j = 0; j < NL; ++j)
+									if constexpr (P2S && NL == 10)
 									{
-										const double c0 = c_refgrad[SLOT][(qq * NL + j) * 3 + 0], c1 = c_refgrad[SLOT][(qq * NL + j) * 3 + 1], c2 = c_refgrad[SLOT][(qq * NL + j) * 3 + 2];
-										acc[j][0] = fma(Y[0][0], c0, fma(Y[0][1], c1, fma(Y[0][2], c2, acc[j][0])));
-										acc[j][1] = fma(Y[1][0], c0, fma(Y[1][1], c1, fma(Y[1][2], c2, acc[j][1])));
-										acc[j][2] = fma(Y[2][0], c0, fma(Y[2][1], c1, fma(Y[2][2], c2, acc[j][2])));
+										const double *G = &c_refgrad[SLOT][qq * NL * 3];
+#pragma unroll
+										for (int n = 0; n < 3; ++n)
+										{
+											const double y0 = Y[n][0], y1 = Y[n][1], y2 = Y[n][2];
+											const double u12 = y1 + y2, u02 = y0 + y2, u01 = y0 + y1, sy = y0 + u12;
+											acc[0][n] = fma(sy, G[0], acc[0][n]);
+											acc[1][n] = fma(y0, G[3], acc[1][n]);
+											acc[2][n] = fma(y1, G[7], acc[2][n]);
+											acc[3][n] = fma(y2, G[11], acc[3][n]);
+											acc[4][n] = fma(y0, G[12], fma(u12, G[13], acc[4][n]));
+											acc[5][n] = fma(y0, G[15], fma(y1, G[16], acc[5][n]));
+											acc[6][n] = fma(y1, G[19], fma(u02, G[18], acc[6][n]));
+											acc[7][n] = fma(y2, G[23], fma(u01, G[21], acc[7][n]));
+											acc[8][n] = fma(y0, G[24], fma(y2, G[26], acc[8][n]));
+											acc[9][n] = fma(y1, G[28], fma(y2, G[29], acc[9][n]));
+										}
+									}
+									else
+									{
+#pragma unroll
+										for (int j = 0; j < NL; ++j)
+										{
+											const double c0 = c_refgrad[SLOT][(qq * NL + j) * 3 + 0], c1 = c_refgrad[SLOT][(qq * NL + j) * 3 + 1], c2 = c_refgrad[SLOT][(qq * NL + j) * 3 + 2];
+											acc[j][0] = fma(Y[0][0], c0, fma(Y[0][1], c1, fma(Y[0][2], c2, acc[j][0])));
+											acc[j][1] = fma(Y[1][0], c0, fma(Y[1][1], c1, fma(Y[1][2], c2, acc[j][1])));
+											acc[j][2] = fma(Y[2][0], c0, fma(Y[2][1], c1, fma(Y[2][2], c2, acc[j][2])));
+										}
 									}
 								}
 							}
@@ -848,12 +882,12 @@ namespace pfa
 			return cudaMemcpyToSymbolAsync(c_refgrad, g_const_shadow[dev][slot], bytes, sizeof(double) * size_t(slot) * kConstSlotDoubles, cudaMemcpyHostToDevice, st);
 		}
 
-		template <int NL, int NQ, int WARPS, int MINB>
+		template <int NL, int NQ, int WARPS, int MINB, bool P2S = false>
 		cudaError_t launch_rowlane(const DeviceMesh &m, const AssembleArgs &a, int sm_count, cudaStream_t st)
 		{
 			using RL = RowLane<NL, NQ>;
 			const size_t smem = RL::smem_bytes(WARPS);
-			auto kern = assemble_nh_rowlane_kernel<NL, NQ, WARPS, MINB>;
+			auto kern = assemble_nh_rowlane_kernel<NL, NQ, WARPS, MINB, P2S>;
 			cudaError_t err = ensure_const_table(m, RL::SLOT, st);
 			if (err != cudaSuccess)
 				return err;
@@ -1275,6 +1309,143 @@ namespace pfa
 			return cudaGetLastError();
 		}
 
+		// ------------------------------------------------------------------------------------
+		// Laplacian stiffness (Laplacian.cpp:13-26, LinearAssembler::assemble Assembler.cpp:157-384)
+		// for P1..P4 tets: one warp per element, K_e = sum_q da_q D_q D_q^T as a register-tiled
+		// rank-3 update. 25 lanes hold a T x T tile each (T = ceil(NL / 5): 7 for P4, 4 for P3);
+		// per quadrature point a lane reads T row and T column gradients (broadcast loads from the
+		// warp's staging area) for 3 T^2 DFMAs. FP64-bound for P4 (84.5 kFLOP per element).
+		// ------------------------------------------------------------------------------------
+		template <int NL>
+		struct LapTile
+		{
+			static constexpr int T = (NL + 4) / 5;
+			static constexpr int NLP = 5 * T; // padded basis count (rows beyond NL hold zeros)
+			__host__ __device__ static size_t warp_doubles(int n_qp) { return size_t(n_qp) * NLP * 3 + size_t(n_qp) * 9 + n_qp; }
+			static size_t smem_bytes(int n_qp, int warps)
+			{
+				return sizeof(double) * (size_t(n_qp) * NL * 3 + n_qp + size_t(warps) * warp_doubles(n_qp));
+			}
+		};
+
+		template <int NL, int WARPS>
+		__global__ void __launch_bounds__(WARPS * 32) assemble_laplacian_tile_kernel(const DeviceMesh m, const AssembleArgs a)
+		{
+			using LT = LapTile<NL>;
+			constexpr int T = LT::T, NLP = LT::NLP;
+			extern __shared__ double smem[];
+			const int n_qp = m.n_qp;
+			const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+			double *s_rg = smem;               // [n_qp][NL][3]
+			double *s_w = s_rg + n_qp * NL * 3; // [n_qp]
+			double *ws = s_w + n_qp + warp * LT::warp_doubles(n_qp);
+			double *sD = ws;                   // [n_qp][NLP][3] physical gradients
+			double *sJ = sD + n_qp * NLP * 3;  // [gq][9]
+			double *sDA = sJ + n_qp * 9;       // [n_qp]
+			for (int t = threadIdx.x; t < n_qp * NL * 3; t += WARPS * 32)
+				s_rg[t] = m.ref_grads[t];
+			for (int t = threadIdx.x; t < n_qp; t += WARPS * 32)
+				s_w[t] = m.qweights[t];
+			__syncthreads();
+			const int ti = lane / 5, tj = lane % 5;
+			const bool tile_lane = lane < 25;
+			const int gq = m.geom_per_qp ? n_qp : 1;
+
+			for (int e = blockIdx.x * WARPS + warp; e < m.n_el; e += gridDim.x * WARPS)
+			{
+				for (int t = lane; t < gq * 9; t += 32)
+					sJ[t] = m.jit[size_t(e) * gq * 9 + t];
+				for (int q = lane; q < n_qp; q += 32)
+					sDA[q] = m.geom_per_qp ? m.detj[size_t(e) * n_qp + q] : m.detj[e] * s_w[q];
+				__syncwarp();
+				for (int t = lane; t < n_qp * NLP; t += 32)
+				{
+					const int q = t / NLP, i = t - q * NLP;
+					double d0 = 0.0, d1 = 0.0, d2 = 0.0;
+					if (i < NL)
+					{
+						const double *J = sJ + (m.geom_per_qp ? q * 9 : 0);
+						const double *g = s_rg + (q * NL + i) * 3;
+						d0 = g[0] * J[0] + g[1] * J[3] + g[2] * J[6];
+						d1 = g[0] * J[1] + g[1] * J[4] + g[2] * J[7];
+						d2 = g[0] * J[2] + g[1] * J[5] + g[2] * J[8];
+					}
+					sD[t * 3 + 0] = d0;
+					sD[t * 3 + 1] = d1;
+					sD[t * 3 + 2] = d2;
+				}
+				__syncwarp();
+				if (tile_lane)
+				{
+					double acc[T][T];
+#pragma unroll
+					for (int r = 0; r < T; ++r)
+#pragma unroll
+						for (int c = 0; c < T; ++c)
+							acc[r][c] = 0.0;
+#pragma unroll 1
+					for (int q = 0; q < n_qp; ++q)
+					{
+						const double da = sDA[q];
+						const double *Dq = sD + q * NLP * 3;
+						double cj[T][3];
+#pragma unroll
+						for (int c = 0; c < T; ++c)
+						{
+							cj[c][0] = da * Dq[(tj * T + c) * 3 + 0];
+							cj[c][1] = da * Dq[(tj * T + c) * 3 + 1];
+							cj[c][2] = da * Dq[(tj * T + c) * 3 + 2];
+						}
+#pragma unroll
+						for (int r = 0; r < T; ++r)
+						{
+							const double r0 = Dq[(ti * T + r) * 3 + 0], r1 = Dq[(ti * T + r) * 3 + 1], r2 = Dq[(ti * T + r) * 3 + 2];
+#pragma unroll
+							for (int c = 0; c < T; ++c)
+								acc[r][c] = fma(r0, cj[c][0], fma(r1, cj[c][1], fma(r2, cj[c][2], acc[r][c])));
+						}
+					}
+					const int32_t *slot = m.slot + size_t(e) * NL * NL;
+#pragma unroll
+					for (int r = 0; r < T; ++r)
+					{
+						const int i = ti * T + r;
+#pragma unroll
+						for (int c = 0; c < T; ++c)
+						{
+							const int j = tj * T + c;
+							if (i < NL && j < NL)
+								red_add(a.values + slot[i * NL + j], acc[r][c]);
+						}
+					}
+				}
+				__syncwarp();
+			}
+		}
+
+		template <int NL>
+		cudaError_t launch_laplacian_tile(const DeviceMesh &m, const AssembleArgs &a, int sm_count, cudaStream_t st)
+		{
+			constexpr int WARPS = 8;
+			const size_t smem = LapTile<NL>::smem_bytes(m.n_qp, WARPS);
+			if (smem > 227 * 1024)
+				return cudaErrorInvalidConfiguration;
+			auto kern = assemble_laplacian_tile_kernel<NL, WARPS>;
+			cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+			if (err != cudaSuccess)
+				return err;
+			int per_sm = 1;
+			err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, WARPS * 32, smem);
+			if (err != cudaSuccess)
+				return err;
+			if (per_sm < 1)
+				per_sm = 1;
+			const int64_t need = (int64_t(m.n_el) + WARPS - 1) / WARPS;
+			const int grid = int(std::max<int64_t>(1, std::min<int64_t>(need, int64_t(sm_count) * per_sm)));
+			kern<<<grid, WARPS * 32, smem, st>>>(m, a);
+			return cudaGetLastError();
+		}
+
 		constexpr size_t kMaxSmem = 227 * 1024;
 
 		size_t generic_smem_bytes(int n_loc, int n_qp, int warps)
@@ -1330,6 +1501,29 @@ namespace pfa
 			}
 		}
 	} // namespace
+
+	bool p2_table_structured(const double *g, int n_loc, int n_qp)
+	{
+		if (n_loc != 10 || g == nullptr)
+			return false;
+		for (int q = 0; q < n_qp; ++q)
+		{
+			const double *G = g + size_t(q) * 30;
+			const bool ok = G[0] == G[1] && G[0] == G[2]        // phi_0: c (1,1,1)
+							&& G[4] == 0 && G[5] == 0             // phi_1: (a,0,0)
+							&& G[6] == 0 && G[8] == 0             // phi_2: (0,a,0)
+							&& G[9] == 0 && G[10] == 0            // phi_3: (0,0,a)
+							&& G[13] == G[14]                     // phi_4: (p,r,r)
+							&& G[17] == 0                         // phi_5: (a,b,0)
+							&& G[18] == G[20]                     // phi_6: (r,p,r)
+							&& G[21] == G[22]                     // phi_7: (r,r,p)
+							&& G[25] == 0                         // phi_8: (a,0,b)
+							&& G[27] == 0;                        // phi_9: (0,a,b)
+			if (!ok)
+				return false;
+		}
+		return true;
+	}
 
 	bool rowlane_applies(int material, int n_loc, int n_qp)
 	{
@@ -1388,6 +1582,8 @@ namespace pfa
 			{
 				if (kernel_name)
 					*kernel_name = "assemble_nh_rowlane_kernel<10,4>";
+				if (m.p2_structured && !PFA_RL_DENSE_COLUMNS)
+					return launch_rowlane<10, 4, PFA_RL_WARPS_P2, PFA_RL_MINB_P2, true>(m, a, sm_count, st);
 				return launch_rowlane<10, 4, PFA_RL_WARPS_P2, PFA_RL_MINB_P2>(m, a, sm_count, st);
 			}
 			if (m.n_loc == 4 && m.n_qp == 1)
@@ -1401,6 +1597,22 @@ namespace pfa
 			return linear ? launch_generic<PFA_LINEAR_ELASTICITY, true>(m, a, sm_count, st)
 						  : launch_generic<PFA_LINEAR_ELASTICITY, false>(m, a, sm_count, st);
 		case PFA_LAPLACIAN:
+			if (a.values != nullptr && !PFA_NO_LAPLACIAN_TILE)
+			{
+				cudaError_t err = cudaErrorInvalidConfiguration;
+				if (m.n_loc == 35)
+					err = launch_laplacian_tile<35>(m, a, sm_count, st);
+				else if (m.n_loc == 20)
+					err = launch_laplacian_tile<20>(m, a, sm_count, st);
+				else if (m.n_loc == 10)
+					err = launch_laplacian_tile<10>(m, a, sm_count, st);
+				if (err != cudaErrorInvalidConfiguration)
+				{
+					if (kernel_name)
+						*kernel_name = "assemble_laplacian_tile_kernel";
+					return err;
+				}
+			}
 			return launch_generic<PFA_LAPLACIAN, true>(m, a, sm_count, st);
 		default:
 			return cudaErrorInvalidValue;

@@ -114,6 +114,22 @@ def test_general_geometry_input_equals_affine(oracle):
     assert_values_close(H.outer, H.inner, v1, H.values)
 
 
+@pytest.mark.parametrize("p,n", [(3, 2), (4, 1)])
+def test_laplacian_tile_kernel_per_qp_geometry(oracle, p, n):
+    """The register-tiled Laplacian kernel with jac_it / da given per quadrature point."""
+    from polyfem_b200 import capi
+    mesh, x, t = make_case(n, p, jitter=0.2)
+    e = mesh.vertices[:, 1:, :] - mesh.vertices[:, :1, :]
+    jit = np.linalg.inv(e).transpose(0, 2, 1)
+    det = np.linalg.det(e)
+    nq = t["weights"].size
+    jac_it = np.repeat(jit[:, None, :, :], nq, axis=1).reshape(mesh.n_elements, nq, 9)
+    da = det[:, None] * t["weights"][None, :]
+    h = capi.Handle("Laplacian", mesh.conn, mesh.n_bases, t["weights"], t["grad"], jac_it=jac_it, da=da)
+    K = oracle.problem_from_mesh(mesh, "Laplacian").assemble()
+    assert_values_close(K.outer, K.inner, h.linear_stiffness(), K.values, what="laplacian per-qp geometry")
+
+
 def test_per_element_and_per_qp_materials(oracle):
     from polyfem_b200 import capi
     mesh, x, t = make_case(2, 2)
