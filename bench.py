@@ -42,6 +42,20 @@ def b_alg_bytes_per_element(n_loc, ndof, nnz, n_el):
     return 4 * n_loc + 80 + 16 + 8 * ndof / n_el + 8 * ndof / n_el + 8 * nnz / n_el
 
 
+def ncu_traffic(kernel_name, n_el, world):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the
+    committed ncu --set full capture (profiles/traffic.json, written from tools/ncu_summary.py
+    output). Only valid for the single-GPU headline workload it was captured on."""
+    path = os.path.join(ROOT, "profiles", "traffic.json")
+    if world != 1 or not os.path.exists(path):
+        return None
+    with open(path) as f:
+        rec = json.load(f)
+    if rec.get("elements") != n_el or not kernel_name or rec.get("kernel") not in kernel_name:
+        return None
+    return float(rec["dram_bytes_read"]) + float(rec["dram_bytes_write"])
+
+
 def measured_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -256,8 +270,9 @@ def main():
     peak, peak_src = measured_peaks()
     b_alg = b_alg_bytes_per_element(h.n_loc, h.ndof, h.nnz, h.n_elements)
     achieved = b_alg * h.n_elements / (kern_ms * 1e-3) / 1e9
+    kname = sorted({name for (name, ms) in recs if "assemble" in name})[0] if kern else None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "kernel": sorted({name for (name, ms) in recs if "assemble" in name})[0] if kern else None,
+                "traffic": ncu_traffic(kname, h.n_elements, world), "kernel": kname,
                 "kernel_ms": kern_ms,
                 "zero_fill_ms": float(np.mean(fill)) if fill else 0.0,
                 "algorithmic_bytes_per_element": b_alg, "peak_source": peak_src + " (of measured)"}

@@ -143,6 +143,31 @@ extern "C"
 	 * Any of energy / grad / values may be NULL to skip that output. */
 	int pfa_grad_hess(pfa_handle *h, const double *x, int project_to_psd, double *energy, double *grad, double *values);
 
+	/* ---- the step right after the assembly ---- */
+
+	/* ElasticForm::is_step_valid (solver/forms/ElasticForm.cpp:388-396): assembles the gradient at x into
+	 * device scratch and reports *valid = 0 when any entry is NaN (an inverted element under the
+	 * Discrete inversion check), 1 otherwise; 4 bytes come back instead of the gradient. When
+	 * energy != NULL the same kernel pass also returns assemble_energy(x), which the line search asks
+	 * for next (solver/NLProblem.cpp:565-590). NLAssembler materials only. */
+	int pfa_is_step_valid(pfa_handle *h, const double *x, int32_t *valid, double *energy);
+
+	/* Dirichlet projection, BCLagrangianForm (solver/forms/lagrangian/BCLagrangianForm.cpp). The list of
+	 * constrained dofs (boundary_nodes_, any order, host or device pointer) fixes not_constraints_ /
+	 * old_to_new_ (:96-118); the reduced CSC pattern and a gather map reduced nnz -> full nnz are
+	 * built once on the device. n == 0 is allowed (identity projection). */
+	int pfa_set_constrained_dofs(pfa_handle *h, const int32_t *dofs, int64_t n);
+	int pfa_reduced_sizes(const pfa_handle *h, int64_t *ndof_reduced, int64_t *nnz_reduced);
+	/* reduced CSC pattern, host copies owned by the handle: outer[ndof_reduced+1], inner[nnz_reduced]
+	 * (== the matrix project_hessian returns, :167-213) */
+	int pfa_reduced_pattern(pfa_handle *h, const int32_t **outer, const int32_t **inner);
+	int pfa_reduced_pattern_device(pfa_handle *h, const int32_t **outer_dev, const int32_t **inner_dev);
+	/* project_gradient (:149-155): grad_reduced[i] = scale * grad_full[not_constraints[i]] */
+	int pfa_project_gradient(pfa_handle *h, const double *grad_full, double scale, double *grad_reduced);
+	/* project_hessian (:167-213): values_reduced[k] = scale * values_full[map[k]]; scale carries
+	 * Form::second_derivative's weight() / scale_ (solver/forms/Form.hpp:42-56). Host or device pointers. */
+	int pfa_project_hessian(pfa_handle *h, const double *values_full, double scale, double *values_reduced);
+
 	/* waits for all work enqueued on the handle's stream */
 	int pfa_synchronize(pfa_handle *h);
 	/* cudaStream_t the handle launches on (as void*), so callers can order their own work */

@@ -217,6 +217,58 @@ def project_to_psd(a):
     return a
 
 
+def project_gradient(grad, constrained, n_dofs=None):
+    """BCLagrangianForm::project_gradient (solver/forms/lagrangian/BCLagrangianForm.cpp:149-155):
+    keeps the entries of the sorted not_constraints_ list (:96-118), in order."""
+    grad = np.asarray(grad, dtype=np.float64).reshape(-1)
+    n = grad.size if n_dofs is None else n_dofs
+    is_c = np.zeros(n, dtype=bool)
+    is_c[np.asarray(constrained, dtype=np.int64)] = True
+    not_constraints = np.flatnonzero(~is_c)
+    out = np.empty(not_constraints.size)
+    for i in range(not_constraints.size):  # the reference's loop, verbatim in meaning
+        out[i] = grad[not_constraints[i]]
+    return out
+
+
+def project_hessian(csc, constrained):
+    """BCLagrangianForm::project_hessian (BCLagrangianForm.cpp:167-213): two passes over the
+    ColMajor CSC storage, dropping rows and columns whose indices are constrained dofs; the
+    filtered rows stay ascending inside each kept column. Plain loops (small cases only)."""
+    n = csc.n
+    old_to_new = -np.ones(n, dtype=np.int64)
+    is_c = np.zeros(n, dtype=bool)
+    is_c[np.asarray(constrained, dtype=np.int64)] = True
+    not_constraints = np.flatnonzero(~is_c)
+    old_to_new[not_constraints] = np.arange(not_constraints.size)
+    n_red = not_constraints.size
+    total = 0
+    for k in range(n):  # pass 1: count
+        if old_to_new[k] < 0:
+            continue
+        for p in range(csc.outer[k], csc.outer[k + 1]):
+            if old_to_new[csc.inner[p]] >= 0:
+                total += 1
+    outer = np.zeros(n_red + 1, dtype=np.int32)
+    inner = np.zeros(total, dtype=np.int32)
+    values = np.zeros(total)
+    pos = 0
+    for k in range(n):  # pass 2: fill column by column
+        new_col = old_to_new[k]
+        if new_col < 0:
+            continue
+        outer[new_col] = pos
+        for p in range(csc.outer[k], csc.outer[k + 1]):
+            new_row = old_to_new[csc.inner[p]]
+            if new_row < 0:
+                continue
+            inner[pos] = new_row
+            values[pos] = csc.values[p]
+            pos += 1
+    outer[n_red] = pos
+    return CSC(n_red, outer, inner, values)
+
+
 class Cache:
     """SparseMatrixCache restatement (the reference's tests/test_matrix.cpp "cache" test)."""
 

@@ -28,6 +28,8 @@ EXPORTS = [
     "pfa_set_materials", "pfa_energy", "pfa_energy_per_element", "pfa_gradient", "pfa_hessian",
     "pfa_linear_stiffness", "pfa_grad_hess", "pfa_synchronize", "pfa_stream", "pfa_set_stream", "pfa_profile_enable",
     "pfa_profile_read", "pfa_launch_count", "pfa_setup_seconds",
+    "pfa_is_step_valid", "pfa_set_constrained_dofs", "pfa_reduced_sizes", "pfa_reduced_pattern", "pfa_reduced_pattern_device",
+    "pfa_project_gradient", "pfa_project_hessian",
 ]
 
 
@@ -78,6 +80,13 @@ def lib():
     L.pfa_hessian.argtypes = [vp, vp, c_int, vp]
     L.pfa_linear_stiffness.argtypes = [vp, vp]
     L.pfa_grad_hess.argtypes = [vp, vp, c_int, vp, vp, vp]
+    L.pfa_is_step_valid.argtypes = [vp, vp, ctypes.POINTER(ctypes.c_int32), vp]
+    L.pfa_set_constrained_dofs.argtypes = [vp, vp, i64]
+    L.pfa_reduced_sizes.argtypes = [vp, ctypes.POINTER(i64), ctypes.POINTER(i64)]
+    L.pfa_reduced_pattern.argtypes = [vp, ctypes.POINTER(_ip), ctypes.POINTER(_ip)]
+    L.pfa_reduced_pattern_device.argtypes = [vp, ctypes.POINTER(vp), ctypes.POINTER(vp)]
+    L.pfa_project_gradient.argtypes = [vp, vp, ctypes.c_double, vp]
+    L.pfa_project_hessian.argtypes = [vp, vp, ctypes.c_double, vp]
     L.pfa_synchronize.argtypes = [vp]
     L.pfa_stream.argtypes = [vp]
     L.pfa_stream.restype = vp
@@ -250,6 +259,52 @@ class Handle:
 
     def linear_stiffness_raw(self, values):
         self._check(lib().pfa_linear_stiffness(self._h, _ptr(values)))
+
+    # ---- the step after the assembly: line-search validity, Dirichlet projection ----
+    def is_step_valid(self, x, want_energy=True):
+        """(valid, energy): ElasticForm::is_step_valid plus assemble_energy from the same pass.
+        x: host numpy array or torch CUDA tensor."""
+        if isinstance(x, np.ndarray):
+            x = np.ascontiguousarray(x, dtype=np.float64).reshape(-1)
+        valid = ctypes.c_int32(-1)
+        e = np.zeros(1)
+        self._check(lib().pfa_is_step_valid(self._h, _ptr(x), ctypes.byref(valid), _ptr(e) if want_energy else None))
+        return bool(valid.value), (float(e[0]) if want_energy else None)
+
+    def set_constrained_dofs(self, dofs):
+        """BCLagrangianForm's boundary_nodes_: builds the reduced pattern and gather map on the device."""
+        dofs = np.ascontiguousarray(dofs, dtype=np.int32).reshape(-1)
+        self._check(lib().pfa_set_constrained_dofs(self._h, _ptr(dofs) if dofs.size else None, int(dofs.size)))
+        nd, nz = ctypes.c_int64(), ctypes.c_int64()
+        self._check(lib().pfa_reduced_sizes(self._h, ctypes.byref(nd), ctypes.byref(nz)))
+        self.ndof_reduced, self.nnz_reduced = nd.value, nz.value
+
+    def reduced_pattern(self):
+        po, pi = _ip(), _ip()
+        self._check(lib().pfa_reduced_pattern(self._h, ctypes.byref(po), ctypes.byref(pi)))
+        outer = np.ctypeslib.as_array(po, shape=(self.ndof_reduced + 1,)).copy()
+        inner = np.ctypeslib.as_array(pi, shape=(self.nnz_reduced,)).copy() if self.nnz_reduced else np.zeros(0, np.int32)
+        return outer, inner
+
+    def reduced_pattern_device_ptrs(self):
+        po, pi = ctypes.c_void_p(), ctypes.c_void_p()
+        self._check(lib().pfa_reduced_pattern_device(self._h, ctypes.byref(po), ctypes.byref(pi)))
+        return po.value, pi.value
+
+    def project_gradient(self, grad_full, scale=1.0, out=None):
+        """numpy in -> numpy out; with `out` given both may be torch CUDA tensors (nothing leaves the device)."""
+        if out is None:
+            grad_full = np.ascontiguousarray(grad_full, dtype=np.float64).reshape(-1)
+            out = np.zeros(self.ndof_reduced)
+        self._check(lib().pfa_project_gradient(self._h, _ptr(grad_full), float(scale), _ptr(out)))
+        return out
+
+    def project_hessian(self, values_full, scale=1.0, out=None):
+        if out is None:
+            values_full = np.ascontiguousarray(values_full, dtype=np.float64).reshape(-1)
+            out = np.zeros(self.nnz_reduced)
+        self._check(lib().pfa_project_hessian(self._h, _ptr(values_full), float(scale), _ptr(out)))
+        return out
 
     def synchronize(self):
         self._check(lib().pfa_synchronize(self._h))

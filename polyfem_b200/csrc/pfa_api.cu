@@ -9,6 +9,7 @@
 #include <new>
 #include <stdexcept>
 #include <string>
+#include <type_traits>
 #include <vector>
 
 using namespace pfa;
@@ -45,6 +46,17 @@ struct pfa_handle
 	double *d_energy = nullptr;
 	int *d_counter = nullptr;
 	int32_t epoch = 0; // in-kernel zero-fill generation (row-lane kernels)
+
+	// Dirichlet projection (pfa_set_constrained_dofs)
+	bool has_constraints = false;
+	int64_t ndof_red = 0, nnz_red = 0;
+	int32_t *d_old_to_new = nullptr, *d_not_constraints = nullptr, *d_outer_red = nullptr, *d_inner_red = nullptr, *d_map = nullptr;
+	std::vector<void *> owned_proj; // freed when the constraint set changes
+	std::vector<int32_t> h_outer_red, h_inner_red;
+	double *s_vec_in = nullptr, *s_vec_out = nullptr, *s_val_out = nullptr; // staging for host-pointer projection calls
+	int *d_flag = nullptr;
+	void *scan_scratch = nullptr;
+	size_t scan_scratch_bytes = 0;
 
 	std::vector<int32_t> h_outer, h_inner;
 	std::vector<int32_t> h_adj_off, h_adj;
@@ -552,6 +564,10 @@ extern "C"
 		prof_reset(h);
 		for (void *p : h->owned)
 			cudaFree(p);
+		for (void *p : h->owned_proj)
+			cudaFree(p);
+		if (h->scan_scratch)
+			cudaFree(h->scan_scratch);
 		if (h->stream && h->own_stream)
 			cudaStreamDestroy(h->stream);
 		delete h;
@@ -705,6 +721,228 @@ extern "C"
 		if (!energy && !grad && !values)
 			return fail(h, PFA_ERR_INVALID, "pfa_grad_hess: all outputs are NULL");
 		return run_assemble(h, false, x, project_to_psd, energy, nullptr, grad, values);
+	}
+
+	int pfa_is_step_valid(pfa_handle *h, const double *x, int32_t *valid, double *energy)
+	{
+		if (!h || !valid)
+			return fail(h, PFA_ERR_INVALID, "pfa_is_step_valid: NULL argument");
+		if (h->dm.material == PFA_LAPLACIAN)
+			return fail(h, PFA_ERR_UNSUPPORTED, "pfa_is_step_valid: Laplacian has no nonlinear gradient");
+		PFA_CUDA(h, cudaSetDevice(h->device));
+		int rc = ensure_staging(h, &h->s_grad, size_t(h->ndof));
+		if (rc != PFA_OK)
+			return rc;
+		if (!h->d_flag && (rc = dev_alloc(h, &h->d_flag, 1)) != PFA_OK)
+			return rc;
+		// gradient into device scratch (a device pointer: nothing is copied back), energy as asked
+		rc = run_assemble(h, false, x, 0, energy, nullptr, h->s_grad, nullptr);
+		if (rc != PFA_OK)
+			return rc;
+		PFA_CUDA(h, cudaMemsetAsync(h->d_flag, 0, sizeof(int), h->stream));
+		prof_begin(h, "any_nan_kernel");
+		cudaError_t ce = launch_any_nan(h->s_grad, h->ndof, h->d_flag, h->sm_count, h->stream);
+		prof_end(h);
+		if (ce != cudaSuccess)
+			return fail(h, PFA_ERR_CUDA, std::string("any_nan_kernel: ") + cudaGetErrorString(ce));
+		int flag = 0;
+		PFA_CUDA(h, cudaMemcpyAsync(&flag, h->d_flag, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+		PFA_CUDA(h, cudaStreamSynchronize(h->stream));
+		*valid = flag ? 0 : 1;
+		return PFA_OK;
+	}
+
+	int pfa_set_constrained_dofs(pfa_handle *h, const int32_t *dofs, int64_t n)
+	{
+		if (!h || n < 0 || (n > 0 && !dofs))
+			return fail(h, PFA_ERR_INVALID, "pfa_set_constrained_dofs: NULL list or negative count");
+		if (h->ndof >= (int64_t(1) << 31) - 1)
+			return fail(h, PFA_ERR_UNSUPPORTED, "pfa_set_constrained_dofs: ndof exceeds int32");
+		h->err.clear();
+		PFA_CUDA(h, cudaSetDevice(h->device));
+		PFA_CUDA(h, cudaStreamSynchronize(h->stream));
+		for (void *p : h->owned_proj)
+			cudaFree(p);
+		h->owned_proj.clear();
+		h->has_constraints = false;
+		h->h_outer_red.clear();
+		h->h_inner_red.clear();
+		h->s_vec_out = h->s_val_out = nullptr;
+		auto alloc = [&](auto **p, size_t count) -> int {
+			void *q = nullptr;
+			PFA_CUDA(h, cudaMalloc(&q, std::max<size_t>(count, 1) * sizeof(**p)));
+			h->owned_proj.push_back(q);
+			*p = static_cast<std::remove_reference_t<decltype(*p)>>(q);
+			return PFA_OK;
+		};
+		const int32_t ndof = int32_t(h->ndof);
+		int32_t *d_dofs = nullptr, *d_keep = nullptr, *d_rank = nullptr, *d_cnt = nullptr;
+		int rc;
+		if (!h->d_flag && (rc = dev_alloc(h, &h->d_flag, 1)) != PFA_OK)
+			return rc;
+		if ((rc = alloc(&d_keep, size_t(ndof) + 1)) != PFA_OK || (rc = alloc(&d_rank, size_t(ndof) + 1)) != PFA_OK
+			|| (rc = alloc(&h->d_old_to_new, size_t(ndof))) != PFA_OK)
+			return rc;
+		const int32_t *dofs_dev = dofs;
+		if (n > 0 && !is_device_ptr(dofs))
+		{
+			if ((rc = alloc(&d_dofs, size_t(n))) != PFA_OK)
+				return rc;
+			PFA_CUDA(h, cudaMemcpyAsync(d_dofs, dofs, size_t(n) * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
+			dofs_dev = d_dofs;
+		}
+		PFA_CUDA(h, cudaMemsetAsync(h->d_flag, 0, sizeof(int), h->stream));
+		h->launches += 2;
+		PFA_CUDA(h, launch_mark_constrained(dofs_dev, n, ndof, d_keep, h->d_flag, h->stream));
+		PFA_CUDA(h, cudaMemsetAsync(d_keep + ndof, 0, sizeof(int32_t), h->stream));
+		// rank of every dof among the kept ones; rank[ndof] = number of kept dofs
+		PFA_CUDA(h, exclusive_scan_i32(d_keep, d_rank, int64_t(ndof) + 1, &h->scan_scratch, &h->scan_scratch_bytes, h->stream));
+		int32_t n_red = 0;
+		int bad = 0;
+		PFA_CUDA(h, cudaMemcpyAsync(&n_red, d_rank + ndof, sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+		PFA_CUDA(h, cudaMemcpyAsync(&bad, h->d_flag, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+		PFA_CUDA(h, cudaStreamSynchronize(h->stream));
+		if (bad)
+			return fail(h, PFA_ERR_INVALID, "pfa_set_constrained_dofs: a constrained dof is outside [0, ndof)");
+		if ((rc = alloc(&h->d_not_constraints, size_t(n_red))) != PFA_OK || (rc = alloc(&d_cnt, size_t(n_red) + 1)) != PFA_OK
+			|| (rc = alloc(&h->d_outer_red, size_t(n_red) + 1)) != PFA_OK)
+			return rc;
+		h->launches += 2;
+		PFA_CUDA(h, launch_finish_maps(d_keep, d_rank, ndof, h->d_old_to_new, h->d_not_constraints, h->stream));
+		PFA_CUDA(h, cudaMemsetAsync(d_cnt, 0, (size_t(n_red) + 1) * sizeof(int32_t), h->stream));
+		PFA_CUDA(h, launch_count_kept(h->d_outer, h->d_inner, h->d_old_to_new, ndof, d_cnt, h->stream));
+		PFA_CUDA(h, exclusive_scan_i32(d_cnt, h->d_outer_red, int64_t(n_red) + 1, &h->scan_scratch, &h->scan_scratch_bytes, h->stream));
+		int32_t nnz_red = 0;
+		PFA_CUDA(h, cudaMemcpyAsync(&nnz_red, h->d_outer_red + n_red, sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+		PFA_CUDA(h, cudaStreamSynchronize(h->stream));
+		if ((rc = alloc(&h->d_inner_red, size_t(nnz_red))) != PFA_OK || (rc = alloc(&h->d_map, size_t(nnz_red))) != PFA_OK)
+			return rc;
+		++h->launches;
+		PFA_CUDA(h, launch_fill_reduced(h->d_outer, h->d_inner, h->d_old_to_new, ndof, h->d_outer_red, h->d_inner_red, h->d_map, h->stream));
+		PFA_CUDA(h, cudaStreamSynchronize(h->stream));
+		// d_keep / d_rank / d_cnt / d_dofs stay in owned_proj until the next call (small next to the map)
+		h->ndof_red = n_red;
+		h->nnz_red = nnz_red;
+		h->has_constraints = true;
+		return PFA_OK;
+	}
+
+	int pfa_reduced_sizes(const pfa_handle *h, int64_t *ndof_reduced, int64_t *nnz_reduced)
+	{
+		if (!h || !h->has_constraints)
+			return PFA_ERR_INVALID;
+		if (ndof_reduced)
+			*ndof_reduced = h->ndof_red;
+		if (nnz_reduced)
+			*nnz_reduced = h->nnz_red;
+		return PFA_OK;
+	}
+
+	int pfa_reduced_pattern(pfa_handle *h, const int32_t **outer, const int32_t **inner)
+	{
+		if (!h)
+			return PFA_ERR_INVALID;
+		if (!h->has_constraints)
+			return fail(h, PFA_ERR_INVALID, "pfa_reduced_pattern: call pfa_set_constrained_dofs first");
+		PFA_CUDA(h, cudaSetDevice(h->device));
+		if (h->h_outer_red.empty())
+		{
+			try
+			{
+				h->h_outer_red.resize(size_t(h->ndof_red) + 1);
+				h->h_inner_red.resize(size_t(h->nnz_red));
+			}
+			catch (const std::bad_alloc &)
+			{
+				h->h_outer_red.clear();
+				return fail(h, PFA_ERR_NOMEM, "pfa_reduced_pattern: out of host memory");
+			}
+			PFA_CUDA(h, cudaMemcpyAsync(h->h_outer_red.data(), h->d_outer_red, h->h_outer_red.size() * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+			PFA_CUDA(h, cudaMemcpyAsync(h->h_inner_red.data(), h->d_inner_red, h->h_inner_red.size() * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+			PFA_CUDA(h, cudaStreamSynchronize(h->stream));
+		}
+		if (outer)
+			*outer = h->h_outer_red.data();
+		if (inner)
+			*inner = h->h_inner_red.data();
+		return PFA_OK;
+	}
+
+	int pfa_reduced_pattern_device(pfa_handle *h, const int32_t **outer_dev, const int32_t **inner_dev)
+	{
+		if (!h || !h->has_constraints)
+			return PFA_ERR_INVALID;
+		if (outer_dev)
+			*outer_dev = h->d_outer_red;
+		if (inner_dev)
+			*inner_dev = h->d_inner_red;
+		return PFA_OK;
+	}
+
+	namespace
+	{
+		// shared by pfa_project_gradient / pfa_project_hessian: dst[t] = scale * src[map[t]]
+		int project_common(pfa_handle *h, const char *what, const double *src, size_t n_src, const int32_t *map, size_t n_dst, double scale,
+						   double *dst, double **stage_in, double **stage_out, bool out_in_proj)
+		{
+			if (!h)
+				return PFA_ERR_INVALID;
+			if (!h->has_constraints)
+				return fail(h, PFA_ERR_INVALID, std::string(what) + ": call pfa_set_constrained_dofs first");
+			if (!src || !dst)
+				return fail(h, PFA_ERR_INVALID, std::string(what) + ": NULL argument");
+			h->err.clear();
+			PFA_CUDA(h, cudaSetDevice(h->device));
+			const double *src_dev = src;
+			int rc;
+			if (!is_device_ptr(src))
+			{
+				if ((rc = ensure_staging(h, stage_in, n_src)) != PFA_OK)
+					return rc;
+				PFA_CUDA(h, cudaMemcpyAsync(*stage_in, src, n_src * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+				src_dev = *stage_in;
+			}
+			double *dst_dev = dst;
+			const bool to_host = !is_device_ptr(dst);
+			if (to_host)
+			{
+				if (!*stage_out)
+				{
+					void *q = nullptr;
+					PFA_CUDA(h, cudaMalloc(&q, std::max<size_t>(n_dst, 1) * sizeof(double)));
+					(out_in_proj ? h->owned_proj : h->owned).push_back(q);
+					*stage_out = static_cast<double *>(q);
+				}
+				dst_dev = *stage_out;
+			}
+			prof_begin(h, what);
+			cudaError_t ce = launch_gather_scale(src_dev, map, int64_t(n_dst), scale, dst_dev, h->sm_count, h->stream);
+			prof_end(h);
+			if (ce != cudaSuccess)
+				return fail(h, PFA_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(ce));
+			if (to_host)
+			{
+				PFA_CUDA(h, cudaMemcpyAsync(dst, dst_dev, n_dst * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+				PFA_CUDA(h, cudaStreamSynchronize(h->stream));
+			}
+			return PFA_OK;
+		}
+	} // namespace
+
+	int pfa_project_gradient(pfa_handle *h, const double *grad_full, double scale, double *grad_reduced)
+	{
+		if (!h)
+			return PFA_ERR_INVALID;
+		return project_common(h, "project_gradient(gather)", grad_full, size_t(h->ndof), h->d_not_constraints, size_t(h->ndof_red), scale, grad_reduced,
+							  &h->s_vec_in, &h->s_vec_out, true);
+	}
+
+	int pfa_project_hessian(pfa_handle *h, const double *values_full, double scale, double *values_reduced)
+	{
+		if (!h)
+			return PFA_ERR_INVALID;
+		return project_common(h, "project_hessian(gather)", values_full, size_t(h->nnz), h->d_map, size_t(h->nnz_red), scale, values_reduced,
+							  &h->s_values, &h->s_val_out, true);
 	}
 
 	int pfa_synchronize(pfa_handle *h)

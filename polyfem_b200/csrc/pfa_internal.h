@@ -86,6 +86,18 @@ namespace pfa
 	void build_zero_schedule(const int32_t *conn, int n_el, int n_loc, int n_bases, const std::vector<int32_t> &adj_off, int size, int batch_elements,
 							 std::vector<int32_t> &zoff, std::vector<int32_t> &zruns);
 
+	// ---- Dirichlet projection and NaN scan (pfa_project.cu) ----
+	cudaError_t exclusive_scan_i32(const int32_t *in, int32_t *out, int64_t n, void **scratch, size_t *scratch_bytes, cudaStream_t st);
+	// keep[d] = 1, then 0 for every listed dof; *bad = 1 when a listed dof is outside [0, ndof)
+	cudaError_t launch_mark_constrained(const int32_t *dofs_dev, int64_t n, int32_t ndof, int32_t *keep, int *bad, cudaStream_t st);
+	cudaError_t launch_finish_maps(const int32_t *keep, const int32_t *rank, int32_t ndof, int32_t *old_to_new, int32_t *not_constraints, cudaStream_t st);
+	cudaError_t launch_count_kept(const int32_t *outer, const int32_t *inner, const int32_t *old_to_new, int32_t ndof, int32_t *col_count, cudaStream_t st);
+	cudaError_t launch_fill_reduced(const int32_t *outer, const int32_t *inner, const int32_t *old_to_new, int32_t ndof, const int32_t *outer_red, int32_t *inner_red, int32_t *map, cudaStream_t st);
+	// dst[t] = scale * src[map[t]]
+	cudaError_t launch_gather_scale(const double *src, const int32_t *map, int64_t n, double scale, double *dst, int sm_count, cudaStream_t st);
+	// *flag = 1 when any entry is NaN (flag must be zeroed by the caller)
+	cudaError_t launch_any_nan(const double *v, int64_t n, int *flag, int sm_count, cudaStream_t st);
+
 	// ---- host-side pattern + slot map (pfa_pattern.cu) ----
 	struct HostPattern
 	{

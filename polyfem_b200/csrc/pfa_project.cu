@@ -1,0 +1,185 @@
+// Device side of the rows right after the assembly path:
+//
+//  * Dirichlet projection of gradient and Hessian, the job of
+//    BCLagrangianForm::project_gradient / project_hessian
+//    (solver/forms/lagrangian/BCLagrangianForm.cpp:149-155, 167-213) called from
+//    NLProblem::gradient / full_hessian_to_reduced_hessian (solver/NLProblem.cpp:596-633, 735-751):
+//    constrained dofs are dropped from the vector and from the rows and columns of the CSC
+//    matrix, kept entries keep their relative order. Here the reduced pattern and a gather map
+//    (reduced nnz -> full nnz) are built once per constraint set on the device; every Newton
+//    iteration is then one streaming gather, with the Form weight (Form.hpp:42-56) folded in.
+//  * NaN scan of a device vector for ElasticForm::is_step_valid (ElasticForm.cpp:388-396).
+#include "pfa_internal.h"
+
+#include <cub/cub.cuh>
+
+namespace pfa
+{
+	namespace
+	{
+		__global__ void mark_constrained_kernel(const int32_t *__restrict__ dofs, int64_t n, int32_t ndof, int32_t *__restrict__ keep, int *__restrict__ bad)
+		{
+			const int64_t t = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+			if (t >= n)
+				return;
+			const int32_t d = dofs[t];
+			if (d < 0 || d >= ndof)
+				*bad = 1;
+			else
+				keep[d] = 0;
+		}
+
+		__global__ void fill_int_kernel(int32_t *__restrict__ p, int64_t n, int32_t v)
+		{
+			const int64_t t = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+			if (t < n)
+				p[t] = v;
+		}
+
+		// old_to_new[d] = rank among kept dofs or -1 (BCLagrangianForm's old_to_new_); not_constraints[rank] = d
+		__global__ void finish_maps_kernel(const int32_t *__restrict__ keep, const int32_t *__restrict__ rank, int32_t ndof, int32_t *__restrict__ old_to_new, int32_t *__restrict__ not_constraints)
+		{
+			const int64_t t = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+			if (t >= ndof)
+				return;
+			if (keep[t])
+			{
+				old_to_new[t] = rank[t];
+				not_constraints[rank[t]] = int32_t(t);
+			}
+			else
+				old_to_new[t] = -1;
+		}
+
+		// pass 1 of project_hessian (BCLagrangianForm.cpp:180-190): kept entries per kept column; one warp per column
+		__global__ void count_kept_kernel(const int32_t *__restrict__ outer, const int32_t *__restrict__ inner, const int32_t *__restrict__ old_to_new, int32_t ndof, int32_t *__restrict__ col_count)
+		{
+			const int64_t c = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+			const int lane = threadIdx.x & 31;
+			if (c >= ndof)
+				return;
+			const int32_t nc = old_to_new[c];
+			if (nc < 0)
+				return;
+			int cnt = 0;
+			for (int64_t k = outer[c] + lane; k < outer[c + 1]; k += 32)
+				cnt += old_to_new[inner[k]] >= 0;
+#pragma unroll
+			for (int o = 16; o > 0; o >>= 1)
+				cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+			if (lane == 0)
+				col_count[nc] = cnt;
+		}
+
+		// pass 2 (BCLagrangianForm.cpp:196-209): ordered compaction of each kept column
+		__global__ void fill_reduced_kernel(const int32_t *__restrict__ outer, const int32_t *__restrict__ inner, const int32_t *__restrict__ old_to_new, int32_t ndof,
+											const int32_t *__restrict__ outer_red, int32_t *__restrict__ inner_red, int32_t *__restrict__ map)
+		{
+			const int64_t c = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+			const int lane = threadIdx.x & 31;
+			if (c >= ndof)
+				return;
+			const int32_t nc = old_to_new[c];
+			if (nc < 0)
+				return;
+			int64_t pos = outer_red[nc];
+			const int64_t k0 = outer[c], k1 = outer[c + 1];
+			for (int64_t base = k0; base < k1; base += 32)
+			{
+				const int64_t k = base + lane;
+				int32_t nr = -1;
+				if (k < k1)
+					nr = old_to_new[inner[k]];
+				const unsigned ballot = __ballot_sync(0xffffffffu, nr >= 0);
+				if (nr >= 0)
+				{
+					const int64_t p = pos + __popc(ballot & ((1u << lane) - 1u));
+					inner_red[p] = nr;
+					map[p] = int32_t(k);
+				}
+				pos += __popc(ballot);
+			}
+		}
+
+		__global__ void gather_scale_kernel(const double *__restrict__ src, const int32_t *__restrict__ map, int64_t n, double scale, double *__restrict__ dst)
+		{
+			const int64_t stride = int64_t(gridDim.x) * blockDim.x;
+			for (int64_t t = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; t < n; t += stride)
+				dst[t] = scale * src[map[t]];
+		}
+
+		__global__ void any_nan_kernel(const double *__restrict__ v, int64_t n, int *__restrict__ flag)
+		{
+			const int64_t stride = int64_t(gridDim.x) * blockDim.x;
+			bool bad = false;
+			for (int64_t t = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; t < n; t += stride)
+				bad |= isnan(v[t]);
+			if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0)
+				*flag = 1;
+		}
+
+		inline unsigned blocks_for(int64_t n, int threads) { return unsigned(std::max<int64_t>(1, (n + threads - 1) / threads)); }
+	} // namespace
+
+	cudaError_t exclusive_scan_i32(const int32_t *in, int32_t *out, int64_t n, void **scratch, size_t *scratch_bytes, cudaStream_t st)
+	{
+		size_t need = 0;
+		cudaError_t err = cub::DeviceScan::ExclusiveSum(nullptr, need, in, out, int(n), st);
+		if (err != cudaSuccess)
+			return err;
+		if (need > *scratch_bytes)
+		{
+			if (*scratch)
+				cudaFree(*scratch);
+			*scratch = nullptr;
+			*scratch_bytes = 0;
+			err = cudaMalloc(scratch, need);
+			if (err != cudaSuccess)
+				return err;
+			*scratch_bytes = need;
+		}
+		return cub::DeviceScan::ExclusiveSum(*scratch, need, in, out, int(n), st);
+	}
+
+	cudaError_t launch_mark_constrained(const int32_t *dofs_dev, int64_t n, int32_t ndof, int32_t *keep, int *bad, cudaStream_t st)
+	{
+		fill_int_kernel<<<blocks_for(ndof, 256), 256, 0, st>>>(keep, ndof, 1);
+		if (n > 0)
+			mark_constrained_kernel<<<blocks_for(n, 256), 256, 0, st>>>(dofs_dev, n, ndof, keep, bad);
+		return cudaGetLastError();
+	}
+
+	cudaError_t launch_finish_maps(const int32_t *keep, const int32_t *rank, int32_t ndof, int32_t *old_to_new, int32_t *not_constraints, cudaStream_t st)
+	{
+		finish_maps_kernel<<<blocks_for(ndof, 256), 256, 0, st>>>(keep, rank, ndof, old_to_new, not_constraints);
+		return cudaGetLastError();
+	}
+
+	cudaError_t launch_count_kept(const int32_t *outer, const int32_t *inner, const int32_t *old_to_new, int32_t ndof, int32_t *col_count, cudaStream_t st)
+	{
+		count_kept_kernel<<<blocks_for(int64_t(ndof) * 32, 256), 256, 0, st>>>(outer, inner, old_to_new, ndof, col_count);
+		return cudaGetLastError();
+	}
+
+	cudaError_t launch_fill_reduced(const int32_t *outer, const int32_t *inner, const int32_t *old_to_new, int32_t ndof, const int32_t *outer_red, int32_t *inner_red, int32_t *map, cudaStream_t st)
+	{
+		fill_reduced_kernel<<<blocks_for(int64_t(ndof) * 32, 256), 256, 0, st>>>(outer, inner, old_to_new, ndof, outer_red, inner_red, map);
+		return cudaGetLastError();
+	}
+
+	cudaError_t launch_gather_scale(const double *src, const int32_t *map, int64_t n, double scale, double *dst, int sm_count, cudaStream_t st)
+	{
+		if (n <= 0)
+			return cudaSuccess;
+		const unsigned grid = unsigned(std::min<int64_t>(blocks_for(n, 256), int64_t(sm_count) * 16));
+		gather_scale_kernel<<<grid, 256, 0, st>>>(src, map, n, scale, dst);
+		return cudaGetLastError();
+	}
+
+	cudaError_t launch_any_nan(const double *v, int64_t n, int *flag, int sm_count, cudaStream_t st)
+	{
+		const unsigned grid = unsigned(std::min<int64_t>(blocks_for(n, 256), int64_t(sm_count) * 8));
+		any_nan_kernel<<<grid, 256, 0, st>>>(v, n, flag);
+		return cudaGetLastError();
+	}
+} // namespace pfa

@@ -1,0 +1,100 @@
+"""GPU parity of the rows right after the assembly: Dirichlet projection of
+gradient / Hessian and the line-search validity probe, against the oracle restatements.
+Gathers are exact: projected values must be BIT-identical to scale * full values."""
+import numpy as np
+import pytest
+
+from helpers import REL_TOL, gpu_handle, make_case
+
+pytestmark = pytest.mark.gpu
+
+
+def _constraints(mesh, rng):
+    """Dirichlet set like a clamped face: all dofs of nodes on x = 0, plus single components elsewhere."""
+    on_face = np.flatnonzero(mesh.node_xyz[:, 0] < 1e-12)
+    dofs = (on_face[:, None] * 3 + np.arange(3)[None, :]).reshape(-1)
+    extra = rng.choice(mesh.n_bases * 3, size=7, replace=False)
+    return rng.permutation(np.union1d(dofs, extra)).astype(np.int32)
+
+
+@pytest.mark.parametrize("p,n", [(1, 4), (2, 3)])
+def test_projection_pattern_and_values(oracle, p, n):
+    mesh, x, t = make_case(n, p)
+    rng = np.random.default_rng(5)
+    h = gpu_handle(mesh, "NeoHookean", t)
+    e, g, v = h.grad_hess(x)
+    outer, inner = h.pattern()
+    full = oracle.CSC(h.ndof, outer, inner, v)
+    constrained = _constraints(mesh, rng)
+    h.set_constrained_dofs(constrained)
+    ref = oracle.project_hessian(full, constrained)
+    assert h.ndof_reduced == ref.n and h.nnz_reduced == ref.inner.size
+    o_r, i_r = h.reduced_pattern()
+    assert o_r.dtype == np.int32 and o_r.tobytes() == ref.outer.tobytes() and i_r.tobytes() == ref.inner.tobytes()
+    assert np.array_equal(h.project_hessian(v), ref.values)
+    assert np.array_equal(h.project_hessian(v, scale=0.37), 0.37 * ref.values)
+    g_ref = oracle.project_gradient(g, constrained)
+    assert np.array_equal(h.project_gradient(g), g_ref)
+    assert np.array_equal(h.project_gradient(g, scale=-2.5), -2.5 * g_ref)
+    # a second constraint set replaces the first; the empty set is the identity
+    h.set_constrained_dofs([])
+    assert h.ndof_reduced == h.ndof and h.nnz_reduced == h.nnz
+    o2, i2 = h.reduced_pattern()
+    assert o2.tobytes() == outer.tobytes() and i2.tobytes() == inner.tobytes()
+    assert np.array_equal(h.project_hessian(v), v)
+
+
+def test_projection_stays_on_the_device(oracle):
+    import torch
+    mesh, x, t = make_case(3, 2)
+    h = gpu_handle(mesh, "NeoHookean", t)
+    constrained = _constraints(mesh, np.random.default_rng(6))
+    h.set_constrained_dofs(constrained)
+    xd = torch.from_numpy(x).cuda()
+    e = torch.zeros(1, dtype=torch.float64, device="cuda")
+    g = torch.zeros(h.ndof, dtype=torch.float64, device="cuda")
+    v = torch.zeros(h.nnz, dtype=torch.float64, device="cuda")
+    h.grad_hess_raw(xd, e, g, v)
+    gr = torch.zeros(h.ndof_reduced, dtype=torch.float64, device="cuda")
+    vr = torch.zeros(h.nnz_reduced, dtype=torch.float64, device="cuda")
+    h.project_gradient(g, 1.0, out=gr)
+    h.project_hessian(v, 1.0, out=vr)
+    h.synchronize()
+    outer, inner = h.pattern()
+    ref = oracle.project_hessian(oracle.CSC(h.ndof, outer, inner, v.cpu().numpy()), constrained)
+    assert np.array_equal(vr.cpu().numpy(), ref.values)
+    assert np.array_equal(gr.cpu().numpy(), oracle.project_gradient(g.cpu().numpy(), constrained))
+    po, pi = h.reduced_pattern_device_ptrs()
+    assert po and pi
+
+
+def test_constraint_errors(oracle):
+    from polyfem_b200 import capi
+    mesh, x, t = make_case(2, 1)
+    h = gpu_handle(mesh, "NeoHookean", t)
+    with pytest.raises(capi.PfaError):
+        h.project_hessian(np.zeros(h.nnz), out=np.zeros(h.nnz))  # no constraint set yet
+    with pytest.raises(capi.PfaError) as ei:
+        h.set_constrained_dofs([0, h.ndof])  # out of range
+    assert ei.value.code == capi.PFA_ERR_INVALID
+
+
+@pytest.mark.parametrize("p,n", [(1, 4), (2, 3)])
+def test_is_step_valid_matches_gradient_nan_check(oracle, p, n):
+    """ElasticForm::is_step_valid: valid <=> the assembled gradient has no NaN; the energy of the
+    same pass equals assemble_energy."""
+    mesh, x, t = make_case(n, p)
+    ref = oracle.problem_from_mesh(mesh, "NeoHookean")
+    h = gpu_handle(mesh, "NeoHookean", t)
+    valid, e = h.is_step_valid(x)
+    assert valid and not np.isnan(ref.assemble_gradient(x)).any()
+    e_ref = ref.assemble_energy(x)
+    assert abs(e - e_ref) <= REL_TOL * abs(e_ref)
+    xi = x.copy()
+    nodes = mesh.conn[5]
+    xi.reshape(-1, 3)[nodes[1]] += 3.0 * (mesh.node_xyz[nodes[0]] - mesh.node_xyz[nodes[1]])  # inverts element 5
+    valid, e = h.is_step_valid(xi)
+    assert not valid and np.isnan(ref.assemble_gradient(xi)).any()
+    assert np.isnan(e) == np.isnan(ref.assemble_energy(xi))
+    valid, e = h.is_step_valid(x, want_energy=False)
+    assert valid and e is None
