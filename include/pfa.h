@@ -168,6 +168,13 @@ extern "C"
 	 * Form::second_derivative's weight() / scale_ (solver/forms/Form.hpp:42-56). Host or device pointers. */
 	int pfa_project_hessian(pfa_handle *h, const double *values_full, double scale, double *values_reduced);
 
+	/* Fused form of pfa_grad_hess + pfa_project_gradient + pfa_project_hessian (NeoHookean P1/P2 tets):
+	 * the kernels scatter straight into the reduced CSC values / reduced gradient (contributions to
+	 * constrained rows and columns are dropped at the source) and multiply energy, gradient and
+	 * values by `scale` (Form::value / first_derivative / second_derivative weight, Form.hpp:30-56).
+	 * Neither the full matrix nor the gather pass exist in this mode. Outputs may be NULL. */
+	int pfa_grad_hess_reduced(pfa_handle *h, const double *x, int project_to_psd, double scale, double *energy, double *grad_reduced, double *values_reduced);
+
 	/* waits for all work enqueued on the handle's stream */
 	int pfa_synchronize(pfa_handle *h);
 	/* cudaStream_t the handle launches on (as void*), so callers can order their own work */

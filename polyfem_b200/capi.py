@@ -29,7 +29,7 @@ EXPORTS = [
     "pfa_linear_stiffness", "pfa_grad_hess", "pfa_synchronize", "pfa_stream", "pfa_set_stream", "pfa_profile_enable",
     "pfa_profile_read", "pfa_launch_count", "pfa_setup_seconds",
     "pfa_is_step_valid", "pfa_set_constrained_dofs", "pfa_reduced_sizes", "pfa_reduced_pattern", "pfa_reduced_pattern_device",
-    "pfa_project_gradient", "pfa_project_hessian",
+    "pfa_project_gradient", "pfa_project_hessian", "pfa_grad_hess_reduced",
 ]
 
 
@@ -87,6 +87,7 @@ def lib():
     L.pfa_reduced_pattern_device.argtypes = [vp, ctypes.POINTER(vp), ctypes.POINTER(vp)]
     L.pfa_project_gradient.argtypes = [vp, vp, ctypes.c_double, vp]
     L.pfa_project_hessian.argtypes = [vp, vp, ctypes.c_double, vp]
+    L.pfa_grad_hess_reduced.argtypes = [vp, vp, c_int, ctypes.c_double, vp, vp, vp]
     L.pfa_synchronize.argtypes = [vp]
     L.pfa_stream.argtypes = [vp]
     L.pfa_stream.restype = vp
@@ -305,6 +306,16 @@ class Handle:
             out = np.zeros(self.nnz_reduced)
         self._check(lib().pfa_project_hessian(self._h, _ptr(values_full), float(scale), _ptr(out)))
         return out
+
+    def grad_hess_reduced(self, x, scale=1.0, project_to_psd=False):
+        """(energy, grad_reduced, values_reduced) numpy: fused assembly into the Dirichlet-reduced system."""
+        x = np.ascontiguousarray(x, dtype=np.float64).reshape(-1)
+        e, g, v = np.zeros(1), np.zeros(self.ndof_reduced), np.zeros(self.nnz_reduced)
+        self._check(lib().pfa_grad_hess_reduced(self._h, _ptr(x), int(bool(project_to_psd)), float(scale), _ptr(e), _ptr(g), _ptr(v)))
+        return float(e[0]), g, v
+
+    def grad_hess_reduced_raw(self, x, scale=1.0, energy=None, grad=None, values=None, project_to_psd=False):
+        self._check(lib().pfa_grad_hess_reduced(self._h, _ptr(x), int(bool(project_to_psd)), float(scale), _ptr(energy), _ptr(grad), _ptr(values)))
 
     def synchronize(self):
         self._check(lib().pfa_synchronize(self._h))

@@ -51,6 +51,7 @@ struct pfa_handle
 	bool has_constraints = false;
 	int64_t ndof_red = 0, nnz_red = 0;
 	int32_t *d_old_to_new = nullptr, *d_not_constraints = nullptr, *d_outer_red = nullptr, *d_inner_red = nullptr, *d_map = nullptr;
+	int32_t *d_entry_red = nullptr, *d_cstride_red = nullptr; // row-lane tables of the reduced matrix (pfa_grad_hess_reduced)
 	std::vector<void *> owned_proj; // freed when the constraint set changes
 	std::vector<int32_t> h_outer_red, h_inner_red;
 	double *s_vec_in = nullptr, *s_vec_out = nullptr, *s_val_out = nullptr; // staging for host-pointer projection calls
@@ -188,7 +189,9 @@ namespace
 		size_t count = 0;
 	};
 
-	int stage_output(pfa_handle *h, double *user, size_t count, double **staging, OutBuf &o)
+	// `capacity` (>= count) is what the staging buffer is allocated with on first use: the same buffer
+	// serves the full-size and the Dirichlet-reduced outputs
+	int stage_output(pfa_handle *h, double *user, size_t count, double **staging, OutBuf &o, size_t capacity = 0)
 	{
 		o.user = user;
 		o.count = count;
@@ -199,7 +202,7 @@ namespace
 			o.dev = user;
 			return PFA_OK;
 		}
-		int rc = ensure_staging(h, staging, count);
+		int rc = ensure_staging(h, staging, std::max(count, capacity));
 		if (rc != PFA_OK)
 			return rc;
 		o.dev = *staging;
@@ -216,16 +219,22 @@ namespace
 
 	// the one place that launches the assembly kernels
 	int run_assemble(pfa_handle *h, bool linear, const double *x, int project_to_psd,
-					 double *energy, double *energy_per_el, double *grad, double *values)
+					 double *energy, double *energy_per_el, double *grad, double *values, double scale = 1.0, bool reduced = false)
 	{
 		h->err.clear();
 		PFA_CUDA(h, cudaSetDevice(h->device));
+		if (reduced && (!h->has_constraints || h->d_entry_red == nullptr))
+			return fail(h, h->has_constraints ? PFA_ERR_UNSUPPORTED : PFA_ERR_INVALID,
+						h->has_constraints ? "the fused Dirichlet-reduced assembly exists for NeoHookean P1/P2 tets only (use pfa_project_*)"
+										   : "call pfa_set_constrained_dofs first");
 		if (project_to_psd && !(values != nullptr && rowlane_applies(h->dm.material, h->dm.n_loc, h->dm.n_qp)))
 		{
 			if (values != nullptr)
 				return fail(h, PFA_ERR_UNSUPPORTED, "project_to_psd is implemented for NeoHookean P1/P2 tets only");
 			project_to_psd = 0; // no Hessian requested: nothing to project
 		}
+		if (scale != 1.0 && !rowlane_applies(h->dm.material, h->dm.n_loc, h->dm.n_qp))
+			return fail(h, PFA_ERR_UNSUPPORTED, "a Form weight other than 1 is fused for NeoHookean P1/P2 tets only");
 		if (h->dm.material == PFA_LAPLACIAN && !linear)
 			return fail(h, PFA_ERR_UNSUPPORTED, "Laplacian is a LinearAssembler: only pfa_linear_stiffness applies");
 		if (h->dm.material == PFA_NEOHOOKEAN && linear)
@@ -244,15 +253,27 @@ namespace
 			return rc;
 		if ((rc = stage_output(h, energy_per_el, size_t(h->dm.n_el), &h->s_epe, op)) != PFA_OK)
 			return rc;
-		if ((rc = stage_output(h, grad, size_t(h->ndof), &h->s_grad, og)) != PFA_OK)
+		const size_t n_grad = reduced ? size_t(h->ndof_red) : size_t(h->ndof);
+		const size_t n_val = reduced ? size_t(h->nnz_red) : size_t(h->nnz);
+		// the full-size staging buffers are large enough for the reduced outputs as well
+		if ((rc = stage_output(h, grad, n_grad, &h->s_grad, og, size_t(h->ndof))) != PFA_OK)
 			return rc;
-		if ((rc = stage_output(h, values, size_t(h->nnz), &h->s_values, ov)) != PFA_OK)
+		if ((rc = stage_output(h, values, n_val, &h->s_values, ov, size_t(h->nnz))) != PFA_OK)
 			return rc;
 		a.energy = oe.dev;
 		a.energy_per_el = op.dev;
 		a.grad = og.dev;
 		a.values = ov.dev;
 		a.project_to_psd = project_to_psd;
+		a.scale = scale;
+		DeviceMesh dm = h->dm;
+		if (reduced)
+		{
+			a.old_to_new = h->d_old_to_new;
+			dm.entry = h->d_entry_red;
+			dm.cstride = h->d_cstride_red;
+			dm.zoff = nullptr; // values[] of the reduced matrix is cleared by a memset
+		}
 		a.work_counter = h->d_counter;
 		PFA_CUDA(h, cudaMemsetAsync(h->d_counter, 0, 4 * sizeof(int), h->stream));
 
@@ -264,17 +285,17 @@ namespace
 			if (a.energy)
 				PFA_CUDA(h, cudaMemsetAsync(a.energy, 0, sizeof(double), h->stream));
 			if (a.grad)
-				PFA_CUDA(h, cudaMemsetAsync(a.grad, 0, size_t(h->ndof) * sizeof(double), h->stream));
-			if (a.values && h->dm.zoff != nullptr && !linear && !project_to_psd)
+				PFA_CUDA(h, cudaMemsetAsync(a.grad, 0, n_grad * sizeof(double), h->stream));
+			if (a.values && dm.zoff != nullptr && !linear && !project_to_psd)
 				a.epoch = ++h->epoch; // the row-lane kernel clears values[] itself, block by block, just ahead of the scatter
 			else if (a.values)
-				PFA_CUDA(h, cudaMemsetAsync(a.values, 0, size_t(h->nnz) * sizeof(double), h->stream));
+				PFA_CUDA(h, cudaMemsetAsync(a.values, 0, n_val * sizeof(double), h->stream));
 			prof_end(h);
 		}
 
 		const char *kname = "assemble";
 		prof_begin(h, kname);
-		cudaError_t ce = launch_assemble(h->dm, a, linear, h->sm_count, h->stream, &kname);
+		cudaError_t ce = launch_assemble(dm, a, linear, h->sm_count, h->stream, &kname);
 		if (h->profiling && !h->prof.empty() && !h->prof.back().stop_recorded)
 			h->prof.back().name = kname;
 		prof_end(h);
@@ -475,7 +496,7 @@ extern "C"
 				{
 					const int32_t gj = conn_in[e * nl + j];
 					const int32_t off = hp.adj_off[size_t(gj)], deg = hp.adj_off[size_t(gj) + 1] - off;
-					cstride[e * nl + j] = 3 * deg;
+					cstride[e * nl + j] = (3 * deg) | (7 << 28); // all three components of the node exist
 					for (size_t i = 0; i < nl; ++i)
 					{
 						int32_t &sl = hp.slot[e * nl * nl + i * nl + j];
@@ -768,6 +789,7 @@ extern "C"
 		h->h_outer_red.clear();
 		h->h_inner_red.clear();
 		h->s_vec_out = h->s_val_out = nullptr;
+		h->d_entry_red = h->d_cstride_red = nullptr;
 		auto alloc = [&](auto **p, size_t count) -> int {
 			void *q = nullptr;
 			PFA_CUDA(h, cudaMalloc(&q, std::max<size_t>(count, 1) * sizeof(**p)));
@@ -820,6 +842,18 @@ extern "C"
 		++h->launches;
 		PFA_CUDA(h, launch_fill_reduced(h->d_outer, h->d_inner, h->d_old_to_new, ndof, h->d_outer_red, h->d_inner_red, h->d_map, h->stream));
 		PFA_CUDA(h, cudaStreamSynchronize(h->stream));
+		h->d_entry_red = h->d_cstride_red = nullptr;
+		if (rowlane_applies(h->dm.material, h->dm.n_loc, h->dm.n_qp) && h->dm.entry != nullptr)
+		{
+			const size_t nb = size_t(h->dm.n_bases), ne = size_t(h->dm.n_el), nl = size_t(h->dm.n_loc);
+			int32_t *node_mask = nullptr, *rowprefix = nullptr, *cs_red = nullptr, *cbase_red = nullptr;
+			if ((rc = alloc(&node_mask, nb)) != PFA_OK || (rc = alloc(&rowprefix, size_t(h->h_adj.size()))) != PFA_OK || (rc = alloc(&cs_red, nb)) != PFA_OK
+				|| (rc = alloc(&cbase_red, nb)) != PFA_OK || (rc = alloc(&h->d_entry_red, ne * nl * nl)) != PFA_OK || (rc = alloc(&h->d_cstride_red, ne * nl)) != PFA_OK)
+				return rc;
+			h->launches += 3;
+			PFA_CUDA(h, launch_reduced_tables(h->dm, d_keep, h->d_old_to_new, h->d_outer_red, node_mask, rowprefix, cs_red, cbase_red, h->d_entry_red, h->d_cstride_red, h->stream));
+			PFA_CUDA(h, cudaStreamSynchronize(h->stream));
+		}
 		// d_keep / d_rank / d_cnt / d_dofs stay in owned_proj until the next call (small next to the map)
 		h->ndof_red = n_red;
 		h->nnz_red = nnz_red;
@@ -943,6 +977,15 @@ extern "C"
 			return PFA_ERR_INVALID;
 		return project_common(h, "project_hessian(gather)", values_full, size_t(h->nnz), h->d_map, size_t(h->nnz_red), scale, values_reduced,
 							  &h->s_values, &h->s_val_out, true);
+	}
+
+	int pfa_grad_hess_reduced(pfa_handle *h, const double *x, int project_to_psd, double scale, double *energy, double *grad_reduced, double *values_reduced)
+	{
+		if (!h)
+			return PFA_ERR_INVALID;
+		if (!energy && !grad_reduced && !values_reduced)
+			return fail(h, PFA_ERR_INVALID, "pfa_grad_hess_reduced: all outputs are NULL");
+		return run_assemble(h, false, x, project_to_psd, energy, nullptr, grad_reduced, values_reduced, scale, true);
 	}
 
 	int pfa_synchronize(pfa_handle *h)

@@ -38,7 +38,8 @@ namespace pfa
 		const int32_t *slot = nullptr;
 		// row-lane kernels (size 3): entry[e][i*n_loc+j] = 9*adj_off[g_j] + 3*k, k = position of g_i in
 		// adj(g_j): values index of H[(g_i,0),(g_j,0)]; cstride[e][j] = 3*deg(g_j), the distance between
-		// the three scalar columns of node g_j. When these are set, `slot` is not uploaded.
+		// the three scalar columns of node g_j, in bits 0..27, and in bits 28..30 the mask of existing
+		// components of node g_j (7 for the full matrix). When these are set, `slot` is not uploaded.
 		const int32_t *entry = nullptr;
 		const int32_t *cstride = nullptr;
 		// in-kernel zero fill of values[] (row-lane kernels): the column blocks first touched by warp
@@ -61,6 +62,11 @@ namespace pfa
 		double *grad = nullptr;          // [ndof] (accumulated, zeroed by caller)
 		double *values = nullptr;        // [nnz]  (accumulated, zeroed by caller)
 		int project_to_psd = 0;
+		// row-lane / psd kernels only: every output is multiplied by `scale` (Form weight); with
+		// old_to_new set, gradient entries go to their Dirichlet-reduced position (or are dropped) and
+		// DeviceMesh::entry / cstride must be the tables built for the reduced matrix
+		double scale = 1.0;
+		const int32_t *old_to_new = nullptr;
 		int *work_counter = nullptr; // device int, zeroed before the launch (dynamic batch hand-out)
 		int32_t epoch = 0;           // > 0: values[] is zero-filled inside the kernel (see DeviceMesh::zoff)
 	};
@@ -93,6 +99,9 @@ namespace pfa
 	cudaError_t launch_finish_maps(const int32_t *keep, const int32_t *rank, int32_t ndof, int32_t *old_to_new, int32_t *not_constraints, cudaStream_t st);
 	cudaError_t launch_count_kept(const int32_t *outer, const int32_t *inner, const int32_t *old_to_new, int32_t ndof, int32_t *col_count, cudaStream_t st);
 	cudaError_t launch_fill_reduced(const int32_t *outer, const int32_t *inner, const int32_t *old_to_new, int32_t ndof, const int32_t *outer_red, int32_t *inner_red, int32_t *map, cudaStream_t st);
+	// entry / cstride tables of the row-lane kernels for the Dirichlet-reduced matrix (pfa_grad_hess_reduced)
+	cudaError_t launch_reduced_tables(const DeviceMesh &m, const int32_t *keep, const int32_t *old_to_new, const int32_t *outer_red,
+									  int32_t *node_mask, int32_t *rowprefix, int32_t *cs_red, int32_t *cbase_red, int32_t *entry_red, int32_t *cstride_red, cudaStream_t st);
 	// dst[t] = scale * src[map[t]]
 	cudaError_t launch_gather_scale(const double *src, const int32_t *map, int64_t n, double scale, double *dst, int sm_count, cudaStream_t st);
 	// *flag = 1 when any entry is NaN (flag must be zeroed by the caller)

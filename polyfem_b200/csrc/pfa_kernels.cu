@@ -63,6 +63,36 @@ namespace pfa
 			return r;
 		}
 
+		// Scatter of the three column components of one (row lane, column node) pair. `stride_word` is
+		// DeviceMesh::cstride: bits 0..27 the distance between the scalar columns of the column node,
+		// bits 28..30 which of its three columns exist (all of them unless the tables were built for a
+		// Dirichlet-reduced matrix, pfa_grad_hess_reduced); row_kept says whether this lane's row exists.
+		__device__ __forceinline__ void scatter3(double *dst, unsigned stride_word, bool row_kept, double o0, double o1, double o2)
+		{
+			const unsigned mj = stride_word >> 28;
+			const size_t cs = size_t(stride_word & 0x0fffffffu);
+			if (row_kept && (mj & 1u))
+				red_add(dst, o0);
+			if (row_kept && (mj & 2u))
+				red_add(dst + (mj & 1u) * cs, o1);
+			if (row_kept && (mj & 4u))
+				red_add(dst + __popc(mj & 3u) * cs, o2);
+		}
+
+		// gradient entry of dof `dof` (full numbering); with a Dirichlet map the entry goes to its
+		// reduced position or is dropped
+		__device__ __forceinline__ void add_gradient(const AssembleArgs &a, size_t dof, double g)
+		{
+			if (a.old_to_new != nullptr)
+			{
+				const int32_t r = a.old_to_new[dof];
+				if (r >= 0)
+					atomicAdd(a.grad + r, g * a.scale);
+			}
+			else
+				atomicAdd(a.grad + dof, g * a.scale);
+		}
+
 		// cofactor matrix C = dJ/dF (row-major), columns are cross products of the columns of F
 		__device__ __forceinline__ void cofactor3(const double *F, double *C)
 		{
@@ -798,37 +828,40 @@ namespace pfa
 								}
 							}
 							if (want_g)
-								atomicAdd(a.grad + size_t(sG[el2 * NL + ri]) * 3 + mm, g_row);
+								add_gradient(a, size_t(sG[el2 * NL + ri]) * 3 + mm, g_row);
 							if (want_h)
 							{
 								const int *ent = sEnt + el2 * NL * NL + ri * NL;
 								const int *st = sStride + el2 * NL;
+								// this lane's row (node ri, component mm) inside the (possibly reduced) column
+								const unsigned mi = unsigned(st[ri]) >> 28;
+								const bool row_kept = (mi >> mm) & 1u;
+								const int row_off = __popc(mi & ((1u << mm) - 1u));
+								const double sc = a.scale;
 #if PFA_EXP_MODE & 4 // timing experiment: no scatter (the condition is never true)
 								double ssum = 0.0;
 #pragma unroll
 								for (int j = 0; j < NL; ++j)
 									ssum += acc[j][0] + acc[j][1] + acc[j][2];
 								if (ssum == 12345.6789)
-									red_add(a.values + ent[0] + st[0], ssum);
+									red_add(a.values + ent[0] + (st[0] & 0x0fffffff), ssum);
 #else
 #pragma unroll
 								for (int j = 0; j < NL; ++j)
 								{
-									double *dst = a.values + (size_t(ent[j]) + mm);
-									const size_t cs = size_t(st[j]);
+									double *dst = a.values + (size_t(ent[j]) + row_off);
 									// undo the rotation with selects so that one instruction still writes one column
 									// component n for all lanes (runs of 3 consecutive doubles per node)
-									const double o0 = sel(is0, acc[j][0], sel(is1, acc[j][2], acc[j][1]));
-									const double o1 = sel(is0, acc[j][1], sel(is1, acc[j][0], acc[j][2]));
-									const double o2 = sel(is0, acc[j][2], sel(is1, acc[j][1], acc[j][0]));
+									const double o0 = sc * sel(is0, acc[j][0], sel(is1, acc[j][2], acc[j][1]));
+									const double o1 = sc * sel(is0, acc[j][1], sel(is1, acc[j][0], acc[j][2]));
+									const double o2 = sc * sel(is0, acc[j][2], sel(is1, acc[j][1], acc[j][0]));
 #if PFA_EXP_MODE & 8 // timing experiment: plain stores instead of reductions (wrong values)
+									const size_t cs = size_t(unsigned(st[j]) & 0x0fffffffu);
 									dst[0] = o0;
 									dst[cs] = o1;
 									dst[2 * cs] = o2;
 #else
-									red_add(dst, o0);
-									red_add(dst + cs, o1);
-									red_add(dst + 2 * cs, o2);
+									scatter3(dst, unsigned(st[j]), row_kept, o0, o1, o2);
 #endif
 								}
 #endif
@@ -853,7 +886,7 @@ namespace pfa
 					double t = 0.0;
 					for (int w = 0; w < WARPS; ++w)
 						t += s_e[w];
-					atomicAdd(a.energy, t);
+					atomicAdd(a.energy, t * a.scale);
 				}
 			}
 		}
@@ -1249,17 +1282,18 @@ namespace pfa
 				if (row_lane)
 				{
 					if (want_g)
-						atomicAdd(a.grad + size_t(sG[ri]) * 3 + mm, g_row);
+						add_gradient(a, size_t(sG[ri]) * 3 + mm, g_row);
 					if (a.values != nullptr)
 					{
+						const unsigned mi = unsigned(sStride[ri]) >> 28;
+						const bool row_kept = (mi >> mm) & 1u;
+						const int row_off = __popc(mi & ((1u << mm) - 1u));
+						const double sc = a.scale;
 #pragma unroll
 						for (int j = 0; j < NL; ++j)
 						{
-							double *dst = a.values + (size_t(sEnt[ri * NL + j]) + mm);
-							const size_t cs = size_t(sStride[j]);
-							red_add(dst, acc[j][0]);
-							red_add(dst + cs, acc[j][1]);
-							red_add(dst + 2 * cs, acc[j][2]);
+							double *dst = a.values + (size_t(sEnt[ri * NL + j]) + row_off);
+							scatter3(dst, unsigned(sStride[j]), row_kept, sc * acc[j][0], sc * acc[j][1], sc * acc[j][2]);
 						}
 					}
 				}
@@ -1280,7 +1314,7 @@ namespace pfa
 					double t = 0.0;
 					for (int w = 0; w < WARPS; ++w)
 						t += s_e[w];
-					atomicAdd(a.energy, t);
+					atomicAdd(a.energy, t * a.scale);
 				}
 			}
 		}

@@ -118,6 +118,69 @@ namespace pfa
 				*flag = 1;
 		}
 
+		// ---- tables of the row-lane kernels for the reduced matrix ----
+		// node_mask[b]: which of the 3 dofs of node b are kept
+		__global__ void node_mask_kernel(const int32_t *__restrict__ keep, int32_t n_bases, int32_t *__restrict__ node_mask)
+		{
+			const int64_t b = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+			if (b < n_bases)
+				node_mask[b] = (keep[3 * b] ? 1 : 0) | (keep[3 * b + 1] ? 2 : 0) | (keep[3 * b + 2] ? 4 : 0);
+		}
+
+		// one warp per column node b: rowprefix[p] = kept rows before row node adj[p] inside a column of b,
+		// cs_red[b] = kept rows of such a column, cbase_red[b] = reduced values index of its first kept column
+		__global__ void column_prefix_kernel(const int32_t *__restrict__ adj_off, const int32_t *__restrict__ adj, const int32_t *__restrict__ node_mask,
+											 const int32_t *__restrict__ old_to_new, const int32_t *__restrict__ outer_red, int32_t n_bases,
+											 int32_t *__restrict__ rowprefix, int32_t *__restrict__ cs_red, int32_t *__restrict__ cbase_red)
+		{
+			const int64_t b = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+			const int lane = threadIdx.x & 31;
+			if (b >= n_bases)
+				return;
+			int run = 0;
+			for (int p0 = adj_off[b]; p0 < adj_off[b + 1]; p0 += 32)
+			{
+				const int p = p0 + lane;
+				const int c = p < adj_off[b + 1] ? __popc(node_mask[adj[p]]) : 0;
+				int incl = c;
+#pragma unroll
+				for (int o = 1; o < 32; o <<= 1)
+				{
+					const int v = __shfl_up_sync(0xffffffffu, incl, o);
+					if (lane >= o)
+						incl += v;
+				}
+				if (p < adj_off[b + 1])
+					rowprefix[p] = run + incl - c;
+				run += __shfl_sync(0xffffffffu, incl, 31);
+			}
+			if (lane == 0)
+			{
+				cs_red[b] = run;
+				const int mb = node_mask[b];
+				cbase_red[b] = mb ? outer_red[old_to_new[3 * b + (__ffs(mb) - 1)]] : 0;
+			}
+		}
+
+		__global__ void reduced_entry_kernel(const int32_t *__restrict__ conn, const int32_t *__restrict__ entry, const int32_t *__restrict__ adj_off,
+											 const int32_t *__restrict__ node_mask, const int32_t *__restrict__ rowprefix, const int32_t *__restrict__ cs_red,
+											 const int32_t *__restrict__ cbase_red, int64_t n_el, int n_loc, int32_t *__restrict__ entry_red, int32_t *__restrict__ cstride_red)
+		{
+			const int64_t t = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+			const int64_t per_el = int64_t(n_loc) * n_loc;
+			if (t >= n_el * per_el)
+				return;
+			const int64_t e = t / per_el;
+			const int ij = int(t - e * per_el);
+			const int i = ij / n_loc, j = ij - i * n_loc;
+			const int32_t gj = conn[e * n_loc + j];
+			const int32_t off = adj_off[gj];
+			const int32_t p = off + (entry[t] - 9 * off) / 3; // position of the pair in adj
+			entry_red[t] = cbase_red[gj] + rowprefix[p];
+			if (i == 0)
+				cstride_red[e * n_loc + j] = cs_red[gj] | (node_mask[gj] << 28);
+		}
+
 		inline unsigned blocks_for(int64_t n, int threads) { return unsigned(std::max<int64_t>(1, (n + threads - 1) / threads)); }
 	} // namespace
 
@@ -164,6 +227,16 @@ namespace pfa
 	cudaError_t launch_fill_reduced(const int32_t *outer, const int32_t *inner, const int32_t *old_to_new, int32_t ndof, const int32_t *outer_red, int32_t *inner_red, int32_t *map, cudaStream_t st)
 	{
 		fill_reduced_kernel<<<blocks_for(int64_t(ndof) * 32, 256), 256, 0, st>>>(outer, inner, old_to_new, ndof, outer_red, inner_red, map);
+		return cudaGetLastError();
+	}
+
+	cudaError_t launch_reduced_tables(const DeviceMesh &m, const int32_t *keep, const int32_t *old_to_new, const int32_t *outer_red,
+									  int32_t *node_mask, int32_t *rowprefix, int32_t *cs_red, int32_t *cbase_red, int32_t *entry_red, int32_t *cstride_red, cudaStream_t st)
+	{
+		node_mask_kernel<<<blocks_for(m.n_bases, 256), 256, 0, st>>>(keep, m.n_bases, node_mask);
+		column_prefix_kernel<<<blocks_for(int64_t(m.n_bases) * 32, 256), 256, 0, st>>>(m.adj_off, m.adj, node_mask, old_to_new, outer_red, m.n_bases, rowprefix, cs_red, cbase_red);
+		const int64_t total = int64_t(m.n_el) * m.n_loc * m.n_loc;
+		reduced_entry_kernel<<<blocks_for(total, 256), 256, 0, st>>>(m.conn, m.entry, m.adj_off, node_mask, rowprefix, cs_red, cbase_red, m.n_el, m.n_loc, entry_red, cstride_red);
 		return cudaGetLastError();
 	}
 

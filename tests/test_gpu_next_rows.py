@@ -98,3 +98,41 @@ def test_is_step_valid_matches_gradient_nan_check(oracle, p, n):
     assert np.isnan(e) == np.isnan(ref.assemble_energy(xi))
     valid, e = h.is_step_valid(x, want_energy=False)
     assert valid and e is None
+
+
+@pytest.mark.parametrize("p,n", [(1, 4), (2, 3)])
+@pytest.mark.parametrize("psd", [False, True])
+def test_fused_reduced_assembly_equals_assemble_then_project(oracle, p, n, psd):
+    """pfa_grad_hess_reduced == project(pfa_grad_hess): same reduced pattern, values within the
+    summation-order tolerance, gradient / energy scaled by the Form weight."""
+    from helpers import assert_values_close, assert_vector_close
+    mesh, x, t = make_case(n, p, scale=0.12 if psd else 0.05)
+    h = gpu_handle(mesh, "NeoHookean", t)
+    constrained = _constraints(mesh, np.random.default_rng(8))
+    h.set_constrained_dofs(constrained)
+    w = 0.25
+    e_full, g_full, v_full = h.grad_hess(x, project_to_psd=psd)
+    outer, inner = h.pattern()
+    ref = oracle.project_hessian(oracle.CSC(h.ndof, outer, inner, w * v_full), constrained)
+    g_ref = oracle.project_gradient(w * g_full, constrained)
+    e, g, v = h.grad_hess_reduced(x, scale=w, project_to_psd=psd)
+    assert abs(e - w * e_full) <= REL_TOL * abs(e_full)
+    assert_vector_close(g, g_ref)
+    assert_values_close(ref.outer, ref.inner, v, ref.values, what="fused reduced hessian")
+    # against the oracle's own assembly as well
+    H = oracle.problem_from_mesh(mesh, "NeoHookean").assemble_hessian(x, project_to_psd=psd)
+    ref2 = oracle.project_hessian(oracle.CSC(h.ndof, H.outer, H.inner, w * H.values), constrained)
+    assert_values_close(ref2.outer, ref2.inner, v, ref2.values, what="fused reduced hessian vs oracle")
+    # full-size call after a reduced one still works (shared staging buffers)
+    e2, g2, v2 = h.grad_hess(x, project_to_psd=psd)
+    assert_values_close(outer, inner, v2, v_full)
+
+
+def test_fused_reduced_assembly_unsupported_paths(oracle):
+    from polyfem_b200 import capi
+    mesh, x, t = make_case(2, 3)
+    h = gpu_handle(mesh, "NeoHookean", t)
+    h.set_constrained_dofs([0, 1, 2])
+    with pytest.raises(capi.PfaError) as ei:
+        h.grad_hess_reduced(x)
+    assert ei.value.code == capi.PFA_ERR_UNSUPPORTED  # P3 goes through the generic kernel: use pfa_project_*

@@ -57,6 +57,14 @@ if a.project:
         h.project_gradient(g, 0.5, out=gr)
         h.is_step_valid(xd)
     recs = h.profile_read()
+    for _ in range(2):
+        h.grad_hess_reduced_raw(xd, 0.5, e, gr, vr)
+    h.synchronize()
+    h.profile_enable(True)
+    for _ in range(a.reps):
+        h.grad_hess_reduced_raw(xd, 0.5, e, gr, vr)
+    fr = h.profile_read()
+    print("fused reduced assembly:", {nm: round(float(np.mean([ms for (k, ms) in fr if k == nm])), 4) for nm in sorted({r[0] for r in fr})})
     names = sorted({r[0] for r in recs})
     out = {nm: round(float(np.mean([ms for (k, ms) in recs if k == nm])), 4) for nm in names}
     gb = (8 * h.nnz_reduced * 2 + 4 * h.nnz_reduced) / 1e9
