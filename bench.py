@@ -188,6 +188,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--cpu-sample-n", type=int, default=12)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-overlap", action="store_true", help="multi-GPU: exchange after the whole assembly instead of under it")
     ap.add_argument("--flags", type=int, default=0, help="pfa_mesh_desc.flags (1 = keep the caller's element order)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -215,7 +216,8 @@ def main():
     lam, mu = lame_from_E_nu(E_MOD, NU)
     part = pdist.partition_elements(mesh, rank, world)
     h = capi.Handle("NeoHookean", part.conn, part.n_bases, t["weights"], t["grad"], vertices=part.vertices,
-                    lam=lam, mu=mu, device=local_rank, n_ghost_elements=part.n_ghost_elements, flags=args.flags)
+                    lam=lam, mu=mu, device=local_rank, n_ghost_elements=part.n_ghost_elements, flags=args.flags,
+                    n_first_elements=part.n_interface_elements)
     h.set_stream(torch.cuda.current_stream().cuda_stream)
     exch = pdist.InterfaceExchange(h, part, rank, world, dev) if world > 1 else None
 
@@ -226,9 +228,18 @@ def main():
     v_d = torch.zeros(h.nnz, dtype=torch.float64, device=dev)
 
     def step():
-        h.grad_hess_raw(xd, e_d, g_d, v_d)
-        if exch is not None:
+        if exch is None:
+            h.grad_hess_raw(xd, e_d, g_d, v_d)
+        elif args.no_overlap:
+            h.grad_hess_raw(xd, e_d, g_d, v_d)
             exch.reduce(e_d, g_d, v_d)
+        else:
+            # interface elements first; their partial sums travel to the owners on a side stream
+            # while the remaining elements are assembled
+            h.grad_hess_part_raw(xd, e_d, g_d, v_d, 1)
+            exch.start(g_d, v_d)
+            h.grad_hess_part_raw(xd, e_d, g_d, v_d, 2)
+            exch.finish(e_d)
 
     def barrier():
         if world > 1:
@@ -335,7 +346,8 @@ def main():
                                    f"{mesh.n_bases * 3} dofs, fused energy+gradient+Hessian (pfa_grad_hess)",
                        "material": "E=1e5 nu=0.3", "displacement": "0.05*h*U(-1,1) seed 42",
                        "l2": "outputs (values[] %.2f GB per GPU) exceed the 126 MB L2, no flush needed" % (8 * h.nnz / 1e9),
-                       "parallelism": f"element partition x{world}" if world > 1 else "single GPU",
+                       "parallelism": (f"element partition x{world}, interface exchange "
+                                       + ("after" if args.no_overlap else "under") + " the assembly") if world > 1 else "single GPU",
                        "nnz": int(h.nnz) if world == 1 else None},
             "nnz_per_s": (h.nnz / (ms_step * 1e-3)) if world == 1 else None,
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,

@@ -92,6 +92,11 @@ extern "C"
 		 * node this rank owns) only widen the sparsity pattern so that owned columns have their
 		 * full global row set; they are never evaluated and need no geometry/material entries. */
 		int32_t n_ghost_elements;
+		/* The first n_first_elements rows of conn form a group that pfa_grad_hess_part can assemble on
+		 * its own (multi-GPU: the elements touching nodes owned by another rank, so that the interface
+		 * exchange runs under the assembly of the rest). The internal re-ordering keeps the two groups
+		 * apart. 0 = no split. */
+		int32_t n_first_elements;
 	} pfa_mesh_desc;
 
 /* pfa_mesh_desc.flags: keep the caller's element order internally (default: elements are
@@ -174,6 +179,14 @@ extern "C"
 	 * values by `scale` (Form::value / first_derivative / second_derivative weight, Form.hpp:30-56).
 	 * Neither the full matrix nor the gather pass exist in this mode. Outputs may be NULL. */
 	int pfa_grad_hess_reduced(pfa_handle *h, const double *x, int project_to_psd, double scale, double *energy, double *grad_reduced, double *values_reduced);
+
+	/* pfa_grad_hess in two launches (device pointers only): part = PFA_PART_FIRST clears the outputs and
+	 * assembles elements [0, n_first_elements); PFA_PART_REST adds the remaining elements to the same
+	 * outputs; PFA_PART_ALL is pfa_grad_hess. */
+#define PFA_PART_ALL 0
+#define PFA_PART_FIRST 1
+#define PFA_PART_REST 2
+	int pfa_grad_hess_part(pfa_handle *h, const double *x, int project_to_psd, double *energy, double *grad, double *values, int part);
 
 	/* waits for all work enqueued on the handle's stream */
 	int pfa_synchronize(pfa_handle *h);

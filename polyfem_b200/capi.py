@@ -29,7 +29,7 @@ EXPORTS = [
     "pfa_linear_stiffness", "pfa_grad_hess", "pfa_synchronize", "pfa_stream", "pfa_set_stream", "pfa_profile_enable",
     "pfa_profile_read", "pfa_launch_count", "pfa_setup_seconds",
     "pfa_is_step_valid", "pfa_set_constrained_dofs", "pfa_reduced_sizes", "pfa_reduced_pattern", "pfa_reduced_pattern_device",
-    "pfa_project_gradient", "pfa_project_hessian", "pfa_grad_hess_reduced",
+    "pfa_project_gradient", "pfa_project_hessian", "pfa_grad_hess_reduced", "pfa_grad_hess_part",
 ]
 
 
@@ -41,7 +41,7 @@ class MeshDesc(ctypes.Structure):
         ("vertices", _dp), ("jac_it", _dp), ("da", _dp),
         ("lambda_", _dp), ("mu", _dp),
         ("material_stride", ctypes.c_int32), ("device", ctypes.c_int32), ("flags", ctypes.c_int32),
-        ("n_ghost_elements", ctypes.c_int32),
+        ("n_ghost_elements", ctypes.c_int32), ("n_first_elements", ctypes.c_int32),
     ]
 
 
@@ -87,6 +87,7 @@ def lib():
     L.pfa_reduced_pattern_device.argtypes = [vp, ctypes.POINTER(vp), ctypes.POINTER(vp)]
     L.pfa_project_gradient.argtypes = [vp, vp, ctypes.c_double, vp]
     L.pfa_project_hessian.argtypes = [vp, vp, ctypes.c_double, vp]
+    L.pfa_grad_hess_part.argtypes = [vp, vp, c_int, vp, vp, vp, c_int]
     L.pfa_grad_hess_reduced.argtypes = [vp, vp, c_int, ctypes.c_double, vp, vp, vp]
     L.pfa_synchronize.argtypes = [vp]
     L.pfa_stream.argtypes = [vp]
@@ -121,7 +122,7 @@ class Handle:
     """One pfa_handle: one mesh + material on one GPU."""
 
     def __init__(self, material, conn, n_bases, quad_weights, ref_grads, vertices=None, jac_it=None, da=None,
-                 lam=None, mu=None, device=0, n_ghost_elements=0, flags=0):
+                 lam=None, mu=None, device=0, n_ghost_elements=0, flags=0, n_first_elements=0):
         L = lib()
         self.material = MATERIAL_IDS[material] if isinstance(material, str) else int(material)
         conn = np.ascontiguousarray(conn, dtype=np.int32)
@@ -162,6 +163,7 @@ class Handle:
             keep += [lam, mu]
         d.material_stride, d.device, d.flags = stride, int(device), int(flags)
         d.n_ghost_elements = int(n_ghost_elements)
+        d.n_first_elements = int(n_first_elements)
         h = ctypes.c_void_p()
         rc = L.pfa_create(ctypes.byref(d), ctypes.byref(h))
         if rc != PFA_OK:
@@ -257,6 +259,10 @@ class Handle:
     # ---- raw pointer entry (host numpy arrays or torch CUDA tensors, any may be None) ----
     def grad_hess_raw(self, x, energy=None, grad=None, values=None, project_to_psd=False):
         self._check(lib().pfa_grad_hess(self._h, _ptr(x), int(bool(project_to_psd)), _ptr(energy), _ptr(grad), _ptr(values)))
+
+    def grad_hess_part_raw(self, x, energy, grad, values, part, project_to_psd=False):
+        """part 1: clear outputs + elements [0, n_first_elements); part 2: add the rest (device tensors only)."""
+        self._check(lib().pfa_grad_hess_part(self._h, _ptr(x), int(bool(project_to_psd)), _ptr(energy), _ptr(grad), _ptr(values), int(part)))
 
     def linear_stiffness_raw(self, values):
         self._check(lib().pfa_linear_stiffness(self._h, _ptr(values)))

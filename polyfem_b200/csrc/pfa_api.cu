@@ -219,7 +219,7 @@ namespace
 
 	// the one place that launches the assembly kernels
 	int run_assemble(pfa_handle *h, bool linear, const double *x, int project_to_psd,
-					 double *energy, double *energy_per_el, double *grad, double *values, double scale = 1.0, bool reduced = false)
+					 double *energy, double *energy_per_el, double *grad, double *values, double scale = 1.0, bool reduced = false, int part = PFA_PART_ALL)
 	{
 		h->err.clear();
 		PFA_CUDA(h, cudaSetDevice(h->device));
@@ -275,11 +275,19 @@ namespace
 			dm.zoff = nullptr; // values[] of the reduced matrix is cleared by a memset
 		}
 		a.work_counter = h->d_counter;
+		a.e_begin = part == PFA_PART_REST ? h->dm.n_first : 0;
+		a.e_end = part == PFA_PART_FIRST ? h->dm.n_first : h->dm.n_el;
+		if (part != PFA_PART_ALL)
+		{
+			if (oe.to_host || op.to_host || og.to_host || ov.to_host || (x != nullptr && a.x != x))
+				return fail(h, PFA_ERR_INVALID, "pfa_grad_hess_part works on device pointers only");
+			dm.zoff = nullptr;
+		}
 		PFA_CUDA(h, cudaMemsetAsync(h->d_counter, 0, 4 * sizeof(int), h->stream));
 
 		// outputs are accumulated with atomics: zero them first (rhs.setZero / set_zero,
 		// Assembler.cpp:586-587, 666-667)
-		if (a.energy || a.grad || a.values)
+		if ((a.energy || a.grad || a.values) && part != PFA_PART_REST)
 		{
 			prof_begin(h, "zero_fill(cudaMemsetAsync)", false);
 			if (a.energy)
@@ -293,6 +301,8 @@ namespace
 			prof_end(h);
 		}
 
+		if (a.e_end <= a.e_begin)
+			return PFA_OK; // empty part: outputs are cleared (or left), nothing to launch
 		const char *kname = "assemble";
 		prof_begin(h, kname);
 		cudaError_t ce = launch_assemble(dm, a, linear, h->sm_count, h->stream, &kname);
@@ -324,6 +334,8 @@ extern "C"
 			return fail(nullptr, PFA_ERR_INVALID, "pfa_create: unknown material");
 		if (d->n_elements <= 0 || d->n_loc <= 0 || d->n_bases <= 0 || d->n_qp <= 0 || d->n_ghost_elements < 0)
 			return fail(nullptr, PFA_ERR_INVALID, "pfa_create: n_elements, n_loc, n_bases and n_qp must be positive");
+		if (d->n_first_elements < 0 || d->n_first_elements > d->n_elements)
+			return fail(nullptr, PFA_ERR_INVALID, "pfa_create: n_first_elements must lie in [0, n_elements]");
 		if (!d->conn || !d->quad_weights || !d->ref_grads)
 			return fail(nullptr, PFA_ERR_INVALID, "pfa_create: conn, quad_weights and ref_grads are required");
 		const bool affine = d->vertices != nullptr;
@@ -381,6 +393,7 @@ extern "C"
 		m.material = d->material;
 		m.size = d->material == PFA_LAPLACIAN ? 1 : 3;
 		m.n_el = d->n_elements;
+		m.n_first = d->n_first_elements;
 		m.n_loc = d->n_loc;
 		m.n_bases = d->n_bases;
 		m.n_qp = d->n_qp;
@@ -403,7 +416,21 @@ extern "C"
 		{
 			if (affine && !(d->flags & PFA_FLAG_KEEP_ELEMENT_ORDER) && d->n_elements > 1)
 			{
-				spatial_element_order(d->vertices, d->n_elements, perm);
+				// the two element groups of pfa_grad_hess_part are ordered separately
+				const int nf = d->n_first_elements;
+				std::vector<int32_t> p2;
+				if (nf > 1)
+					spatial_element_order(d->vertices, nf, perm);
+				else
+					for (int e = 0; e < nf; ++e)
+						perm.push_back(e);
+				if (d->n_elements - nf > 1)
+					spatial_element_order(d->vertices + size_t(nf) * 12, d->n_elements - nf, p2);
+				else
+					for (int e = 0; e < d->n_elements - nf; ++e)
+						p2.push_back(e);
+				for (int32_t v : p2)
+					perm.push_back(v + nf);
 				const size_t ne_ = size_t(d->n_elements), nl_ = size_t(d->n_loc), ng_ = size_t(d->n_ghost_elements);
 				conn_p.resize((ne_ + ng_) * nl_);
 				vert_p.resize(ne_ * 12);
@@ -977,6 +1004,17 @@ extern "C"
 			return PFA_ERR_INVALID;
 		return project_common(h, "project_hessian(gather)", values_full, size_t(h->nnz), h->d_map, size_t(h->nnz_red), scale, values_reduced,
 							  &h->s_values, &h->s_val_out, true);
+	}
+
+	int pfa_grad_hess_part(pfa_handle *h, const double *x, int project_to_psd, double *energy, double *grad, double *values, int part)
+	{
+		if (!h)
+			return PFA_ERR_INVALID;
+		if (part < PFA_PART_ALL || part > PFA_PART_REST)
+			return fail(h, PFA_ERR_INVALID, "pfa_grad_hess_part: unknown part");
+		if (!energy && !grad && !values)
+			return fail(h, PFA_ERR_INVALID, "pfa_grad_hess_part: all outputs are NULL");
+		return run_assemble(h, false, x, project_to_psd, energy, nullptr, grad, values, 1.0, false, part);
 	}
 
 	int pfa_grad_hess_reduced(pfa_handle *h, const double *x, int project_to_psd, double scale, double *energy, double *grad_reduced, double *values_reduced)

@@ -16,6 +16,7 @@ namespace pfa
 		int32_t material = 0;
 		int32_t size = 3; // dofs per node: 3 (elasticity) or 1 (Laplacian)
 		int32_t n_el = 0, n_loc = 0, n_bases = 0, n_qp = 0;
+		int32_t n_first = 0;     // elements [0, n_first) can be assembled on their own (pfa_grad_hess_part)
 		int32_t geom_per_qp = 0; // 0: affine, one J^-T/det per element; 1: one per (element, qp)
 		int32_t mat_stride = 1;  // 1 or n_qp
 
@@ -62,6 +63,7 @@ namespace pfa
 		double *grad = nullptr;          // [ndof] (accumulated, zeroed by caller)
 		double *values = nullptr;        // [nnz]  (accumulated, zeroed by caller)
 		int project_to_psd = 0;
+		int32_t e_begin = 0, e_end = 0; // (internal) element range of this launch
 		// row-lane / psd kernels only: every output is multiplied by `scale` (Form weight); with
 		// old_to_new set, gradient entries go to their Dirichlet-reduced position (or are dropped) and
 		// DeviceMesh::entry / cstride must be the tables built for the reduced matrix

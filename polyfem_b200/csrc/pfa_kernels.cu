@@ -222,7 +222,7 @@ namespace pfa
 			const bool want_g = !LINEAR && a.grad != nullptr;
 			const bool want_e = !LINEAR && (a.energy != nullptr || a.energy_per_el != nullptr);
 
-			for (int e = blockIdx.x * kWarps + warp; e < m.n_el; e += warps_total)
+			for (int e = a.e_begin + blockIdx.x * kWarps + warp; e < a.e_end; e += warps_total)
 			{
 				// ---- 1. gather connectivity, displacement, geometry ----
 				for (int j = lane; j < n_loc; j += 32)
@@ -588,17 +588,17 @@ namespace pfa
 			// fetched before the current batch is processed so that its latency is hidden
 			int batch = 0;
 			if (lane == 0)
-				batch = atomicAdd(a.work_counter, EB);
+				batch = a.e_begin + atomicAdd(a.work_counter, EB);
 			batch = __shfl_sync(0xffffffffu, batch, 0);
 			if (a.epoch > 0)
 				zero_duty(m, a, batch / EB, lane);
-			while (batch < m.n_el)
+			while (batch < a.e_end)
 			{
 				int next = 0;
 				if (lane == 0)
-					next = atomicAdd(a.work_counter, EB);
+					next = a.e_begin + atomicAdd(a.work_counter, EB);
 				// ---- connectivity and entry offsets of the batch ----
-				const int n_batch = min(EB, m.n_el - batch);
+				const int n_batch = min(EB, a.e_end - batch);
 				for (int t = lane; t < n_batch * NL; t += 32)
 				{
 					sG[t] = m.conn[size_t(batch) * NL + t];
@@ -618,7 +618,7 @@ namespace pfa
 
 				// ---- phase 1 ----
 				const int e = batch + el;
-				const bool valid = lane < EB * NQ && e < m.n_el;
+				const bool valid = lane < EB * NQ && e < a.e_end;
 				double e_q = 0.0;
 #if PFA_EXP_MODE & 1
 				if (valid)
@@ -749,7 +749,7 @@ namespace pfa
 					{
 						const int el2 = eb + sub;
 						const int e2 = batch + el2;
-						if (row_lane && e2 < m.n_el)
+						if (row_lane && e2 < a.e_end)
 						{
 							double acc[NL][3];
 #pragma unroll
@@ -987,7 +987,7 @@ namespace pfa
 			const int ra = (mm + 1) % 3, rb = (mm + 2) % 3;
 			const bool row_lane = lane < N;
 
-			for (int e = blockIdx.x * WARPS + warp; e < m.n_el; e += gridDim.x * WARPS)
+			for (int e = a.e_begin + blockIdx.x * WARPS + warp; e < a.e_end; e += gridDim.x * WARPS)
 			{
 				for (int t = lane; t < NL; t += 32)
 				{
@@ -1385,7 +1385,7 @@ namespace pfa
 			const bool tile_lane = lane < 25;
 			const int gq = m.geom_per_qp ? n_qp : 1;
 
-			for (int e = blockIdx.x * WARPS + warp; e < m.n_el; e += gridDim.x * WARPS)
+			for (int e = a.e_begin + blockIdx.x * WARPS + warp; e < a.e_end; e += gridDim.x * WARPS)
 			{
 				for (int t = lane; t < gq * 9; t += 32)
 					sJ[t] = m.jit[size_t(e) * gq * 9 + t];

@@ -33,7 +33,8 @@ class Partition:
     n_bases: int             # local nodes
     l2g: np.ndarray          # [n_bases] global node id of each local node
     owner: np.ndarray        # [n_bases] owning rank of each local node
-    own_elements: np.ndarray  # global element ids of the own block
+    own_elements: np.ndarray  # global element ids of the own block (interface elements first)
+    n_interface_elements: int = 0  # leading own elements that touch a node owned by another rank
 
 
 def element_ranges(n_elements: int, world: int):
@@ -51,13 +52,17 @@ def partition_elements(mesh: TetMesh, rank: int, world: int) -> Partition:
     node_owner = np.full(mesh.n_bases, world, dtype=np.int32)
     np.minimum.at(node_owner, mesh.conn.reshape(-1), np.repeat(elem_rank, mesh.n_loc))
     own = np.arange(bounds[rank], bounds[rank + 1], dtype=np.int64)
+    # interface elements first: they are the only ones that write into columns / dofs of other
+    # ranks, so they are assembled first and the exchange runs under the assembly of the rest
+    is_iface = (node_owner[mesh.conn[own]] != rank).any(axis=1)
+    own = np.concatenate([own[is_iface], own[~is_iface]])
     touches_owned = (node_owner[mesh.conn] == rank).any(axis=1) & (elem_rank != rank)
     ghost = np.nonzero(touches_owned)[0].astype(np.int64)
     elems = np.concatenate([own, ghost])
     conn_local, l2g = first_touch_numbering(mesh.conn[elems].astype(np.int64))
     return Partition(rank, world, np.ascontiguousarray(conn_local), int(own.size), int(ghost.size),
                      np.ascontiguousarray(mesh.vertices[own]), int(l2g.size), l2g.astype(np.int64),
-                     node_owner[l2g].astype(np.int32), own)
+                     node_owner[l2g].astype(np.int32), own, int(is_iface.sum()))
 
 
 def block_pattern_numpy(conn: np.ndarray, n_bases: int):
@@ -96,6 +101,7 @@ class InterfaceExchange:
         self.torch, self.dist = torch, dist
         self.rank, self.world, self.device, self.size = rank, world, device, size
         self.launches = 0
+        self._side, self._done, self._send_bufs = None, None, []
         adj_off, adj = block_pattern if block_pattern is not None else handle.block_pattern()
         nb = part.n_bases
         conn_own = part.conn[:part.n_own_elements].astype(np.int64)
@@ -164,22 +170,54 @@ class InterfaceExchange:
                          for s in self.peers_recv}
         self.interface_bytes = 8 * sum(self.send_vidx[s].numel() + self.send_gidx[s].numel() for s in self.peers_send)
 
-    def reduce(self, energy, grad, values):
-        """energy: all-reduce; grad / values: partial sums of non-owned entries go to the owner."""
+    def _post(self, grad, values):
         torch, dist = self.torch, self.dist
-        ops, send_bufs = [], []
+        ops, self._send_bufs = [], []
         for s in self.peers_recv:
             ops.append(dist.P2POp(dist.irecv, self.recv_buf[s], s))
         for s in self.peers_send:
             buf = torch.cat([values[self.send_vidx[s]], grad[self.send_gidx[s]]])
-            send_bufs.append(buf)
+            self._send_bufs.append(buf)
             ops.append(dist.P2POp(dist.isend, buf, s))
-        reqs = dist.batch_isend_irecv(ops) if ops else []
-        if energy is not None:
-            dist.all_reduce(energy)
+        return dist.batch_isend_irecv(ops) if ops else []
+
+    def _add_received(self, reqs, grad, values):
         for r in reqs:
             r.wait()
         for s in self.peers_recv:
             nv = self.recv_vidx[s].numel()
             values.index_add_(0, self.recv_vidx[s], self.recv_buf[s][:nv])
             grad.index_add_(0, self.recv_gidx[s], self.recv_buf[s][nv:])
+
+    def reduce(self, energy, grad, values):
+        """energy: all-reduce; grad / values: partial sums of non-owned entries go to the owner."""
+        reqs = self._post(grad, values)
+        if energy is not None:
+            self.dist.all_reduce(energy)
+        self._add_received(reqs, grad, values)
+
+    # ---- overlapped form (CUDA): start() after the interface elements, finish() after the rest ----
+    def start(self, grad, values):
+        """Call when the interface elements (Partition.n_interface_elements, assembled first) are in
+        grad / values: packs and sends their partial sums on a side stream while the caller goes on
+        assembling the remaining elements on the current stream. Received sums are added with atomics
+        (index_add_), which may run concurrently with the assembly kernel's own reductions."""
+        torch = self.torch
+        if self._side is None:
+            self._side = torch.cuda.Stream(device=self.device)
+        main = torch.cuda.current_stream(self.device)
+        ev = torch.cuda.Event()
+        ev.record(main)
+        with torch.cuda.stream(self._side):
+            self._side.wait_event(ev)
+            reqs = self._post(grad, values)
+            self._add_received(reqs, grad, values)
+            self._done = torch.cuda.Event()
+            self._done.record(self._side)
+
+    def finish(self, energy):
+        """Joins the side stream and all-reduces the energy (complete only after the last element)."""
+        main = self.torch.cuda.current_stream(self.device)
+        main.wait_event(self._done)
+        if energy is not None:
+            self.dist.all_reduce(energy)

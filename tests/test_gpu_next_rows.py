@@ -136,3 +136,41 @@ def test_fused_reduced_assembly_unsupported_paths(oracle):
     with pytest.raises(capi.PfaError) as ei:
         h.grad_hess_reduced(x)
     assert ei.value.code == capi.PFA_ERR_UNSUPPORTED  # P3 goes through the generic kernel: use pfa_project_*
+
+
+@pytest.mark.parametrize("p,n,n_first", [(1, 4, 37), (2, 3, 50), (2, 3, 0), (3, 2, 11)])
+def test_two_part_assembly_equals_one_launch(oracle, p, n, n_first):
+    """pfa_grad_hess_part(FIRST) + (REST) == pfa_grad_hess (row-lane and generic kernels); the
+    internal re-ordering keeps the two element groups apart."""
+    import torch
+    from helpers import assert_values_close, assert_vector_close
+    from polyfem_b200 import capi, mesh as M
+    mesh, x, t = make_case(n, p, jitter=0.1, scale=0.05 if p < 3 else 0.01)  # P3 overshoots: keep det F > 0
+    lam, mu = M.lame_from_E_nu(1e5, 0.3)
+    h = capi.Handle("NeoHookean", mesh.conn, mesh.n_bases, t["weights"], t["grad"], vertices=mesh.vertices, lam=lam, mu=mu,
+                    n_first_elements=n_first)
+    e_ref, g_ref, v_ref = h.grad_hess(x)
+    assert np.isfinite(e_ref)
+    H = oracle.problem_from_mesh(mesh, "NeoHookean").assemble_hessian(x)
+    assert_values_close(H.outer, H.inner, v_ref, H.values)
+    xd = torch.from_numpy(x).cuda()
+    e = torch.full((1,), 7.0, dtype=torch.float64, device="cuda")
+    g = torch.full((h.ndof,), 7.0, dtype=torch.float64, device="cuda")
+    v = torch.full((h.nnz,), 7.0, dtype=torch.float64, device="cuda")
+    h.grad_hess_part_raw(xd, e, g, v, 1)
+    h.synchronize()
+    if n_first == 0:
+        assert float(e.item()) == 0.0 and not v.any() and not g.any()
+    else:
+        # the first part alone is the assembly of the first n_first elements
+        sub = oracle.OracleProblem("NeoHookean", mesh.conn[:n_first], mesh.vertices[:n_first], mesh.n_bases,
+                                   t["points"], t["weights"], t["grad"], lam=lam, mu=mu)
+        assert_vector_close(g.cpu().numpy(), sub.assemble_gradient(x))
+    h.grad_hess_part_raw(xd, e, g, v, 2)
+    h.synchronize()
+    assert abs(float(e.item()) - e_ref) <= REL_TOL * abs(e_ref)
+    assert_vector_close(g.cpu().numpy(), g_ref)
+    outer, inner = h.pattern()
+    assert_values_close(outer, inner, v.cpu().numpy(), v_ref)
+    with pytest.raises(capi.PfaError):
+        h.grad_hess_part_raw(x, np.zeros(1), np.zeros(h.ndof), np.zeros(h.nnz), 1)  # host pointers
