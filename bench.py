@@ -189,6 +189,7 @@ def main():
     ap.add_argument("--cpu-sample-n", type=int, default=12)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-overlap", action="store_true", help="multi-GPU: exchange after the whole assembly instead of under it")
+    ap.add_argument("--no-graph", action="store_true", help="multi-GPU: issue every launch of a step from Python instead of replaying a CUDA graph")
     ap.add_argument("--flags", type=int, default=0, help="pfa_mesh_desc.flags (1 = keep the caller's element order)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -246,6 +247,35 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    # multi-GPU steps are a dozen short launches (memset, two kernels, pack, NCCL send/recv, unpack,
+    # all-reduce): host-bound when issued one by one, so the step is captured once in a CUDA graph
+    # and replayed (bench.py --no-graph: eager)
+    graph = None
+    if world > 1 and not args.no_graph:
+        eager_step = step
+        try:
+            cap = torch.cuda.Stream(device=dev)
+            h.set_stream(cap.cuda_stream)
+            with torch.cuda.stream(cap):
+                for _ in range(2):  # NCCL communicators and staging buffers are set up outside the capture
+                    eager_step()
+            cap.synchronize()
+            dist.barrier()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph, stream=cap):
+                eager_step()
+            step = graph.replay
+        except Exception as ex:  # capture not possible on this stack: measure the eager path and say so
+            sys.stderr.write(f"[bench] CUDA graph capture failed on rank {rank} ({type(ex).__name__}: {ex}); eager steps\n")
+            graph = None
+            step = eager_step
+            h.set_stream(torch.cuda.current_stream().cuda_stream)
+        ok = torch.tensor([1 if graph is not None else 0], device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if int(ok.item()) == 0 and graph is not None:  # all ranks or none
+            graph, step = None, eager_step
+            h.set_stream(torch.cuda.current_stream().cuda_stream)
+
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
@@ -266,6 +296,20 @@ def main():
     recs = h.profile_read()
     h.profile_enable(False)
     launches = h.launch_count() + (exch.launches if exch else 0) - launches0
+    prof_steps = args.steps
+    if graph is not None:
+        # a replayed graph does not pass through the library: per-kernel times and the launch count
+        # of one step come from a few eager steps after the timed region
+        h.set_stream(torch.cuda.current_stream().cuda_stream)
+        prof_steps = 3
+        h.profile_enable(True)
+        l0 = h.launch_count()
+        for _ in range(prof_steps):
+            eager_step()
+        barrier()
+        recs = h.profile_read()
+        h.profile_enable(False)
+        launches = (h.launch_count() - l0) // prof_steps * args.steps
     if world > 1:
         tt = torch.tensor([ms_total], dtype=torch.float64, device=dev)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
@@ -277,7 +321,7 @@ def main():
     # dominant kernel: average launch duration from the library's own CUDA events (same stream)
     kern = [ms for (name, ms) in recs if "assemble" in name]
     fill = [ms for (name, ms) in recs if "zero_fill" in name]
-    kern_ms = float(np.mean(kern)) if kern else float("nan")
+    kern_ms = float(np.sum(kern)) / prof_steps if kern else float("nan")  # per step (two launches when the step is split)
     peak, peak_src = measured_peaks()
     b_alg = b_alg_bytes_per_element(h.n_loc, h.ndof, h.nnz, h.n_elements)
     achieved = b_alg * h.n_elements / (kern_ms * 1e-3) / 1e9
@@ -285,7 +329,7 @@ def main():
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": ncu_traffic(kname, h.n_elements, world), "kernel": kname,
                 "kernel_ms": kern_ms,
-                "zero_fill_ms": float(np.mean(fill)) if fill else 0.0,
+                "zero_fill_ms": float(np.sum(fill)) / prof_steps if fill else 0.0,
                 "algorithmic_bytes_per_element": b_alg, "peak_source": peak_src + " (of measured)"}
 
     # e2e through the C ABI with pinned HOST buffers (H2D x, D2H E + grad + values every step)
@@ -347,7 +391,8 @@ def main():
                        "material": "E=1e5 nu=0.3", "displacement": "0.05*h*U(-1,1) seed 42",
                        "l2": "outputs (values[] %.2f GB per GPU) exceed the 126 MB L2, no flush needed" % (8 * h.nnz / 1e9),
                        "parallelism": (f"element partition x{world}, interface exchange "
-                                       + ("after" if args.no_overlap else "under") + " the assembly") if world > 1 else "single GPU",
+                                       + ("after" if args.no_overlap else "under") + " the assembly, "
+                                       + ("step replayed from a CUDA graph" if graph is not None else "eager launches")) if world > 1 else "single GPU",
                        "nnz": int(h.nnz) if world == 1 else None},
             "nnz_per_s": (h.nnz / (ms_step * 1e-3)) if world == 1 else None,
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,

@@ -52,7 +52,10 @@ extern "C"
 	{
 		PFA_NEOHOOKEAN = 0,        /* assembler/NeoHookeanElasticity.cpp, name() == "NeoHookean" */
 		PFA_LINEAR_ELASTICITY = 1, /* assembler/LinearElasticity.cpp,    name() == "LinearElasticity" */
-		PFA_LAPLACIAN = 2          /* assembler/Laplacian.cpp,           name() == "Laplacian" */
+		PFA_LAPLACIAN = 2,         /* assembler/Laplacian.cpp,           name() == "Laplacian" */
+		PFA_MASS = 3               /* assembler/Mass.cpp (LinearAssembler, size 3): rho phi_i phi_j on the block diagonal; the
+		                            * mass matrix of InertiaForm. Needs ref_vals + density; quadrature is the
+		                            * mass rule of order 2p (AssemblerUtils.cpp:204-211). */
 	} pfa_material;
 
 	/* What the shim reads out of std::vector<basis::ElementBases> bases / gbases and the
@@ -97,6 +100,11 @@ extern "C"
 		 * exchange runs under the assembly of the rest). The internal re-ordering keeps the two groups
 		 * apart. 0 = no split. */
 		int32_t n_first_elements;
+		/* PFA_MASS only: basis values [n_qp][n_loc] = basis_values[j].val(q) and the density
+		 * (Mass::density_, evaluated by the host like lambda / mu) with the layout material_stride says.
+		 * ref_grads, lambda and mu may be NULL for PFA_MASS. */
+		const double *ref_vals;
+		const double *density;
 	} pfa_mesh_desc;
 
 /* pfa_mesh_desc.flags: keep the caller's element order internally (default: elements are
@@ -187,6 +195,18 @@ extern "C"
 #define PFA_PART_FIRST 1
 #define PFA_PART_REST 2
 	int pfa_grad_hess_part(pfa_handle *h, const double *x, int project_to_psd, double *energy, double *grad, double *values, int part);
+
+	/* ---- InertiaForm (solver/forms/InertiaForm.cpp:17-34) on a PFA_MASS handle ----
+	 * y = A x for the symmetric CSC matrix (pattern of the handle, `values` as returned by
+	 * pfa_linear_stiffness / pfa_hessian); host or device pointers. */
+	int pfa_symv(pfa_handle *h, const double *values, const double *x, double *y);
+	/* value_unweighted and first_derivative_unweighted in one pass: d = x - x_tilde,
+	 * grad = M d (may be NULL), *energy = 0.5 d^T M d (may be NULL). second_derivative is `mass_values`
+	 * itself. x_tilde = x_prev + dt v_prev is the caller's (ImplicitEuler.cpp:13-16). */
+	int pfa_inertia(pfa_handle *h, const double *mass_values, const double *x, const double *x_tilde, double *energy, double *grad);
+	/* y[k] += a * x[k], k < n: e.g. Hessian of the time-stepping problem = dt^2-weighted elastic values
+	 * + mass values (same pattern when both handles come from the same connectivity) */
+	int pfa_axpy(pfa_handle *h, int64_t n, double a, const double *x, double *y);
 
 	/* waits for all work enqueued on the handle's stream */
 	int pfa_synchronize(pfa_handle *h);

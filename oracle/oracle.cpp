@@ -246,6 +246,7 @@ namespace
 		std::vector<int> global;      // [n_loc]  basis_values[j].global[0].index  (weight 1)
 		std::vector<double> grad;     // [n_loc][n_qp][3]  basis_values[j].grad
 		std::vector<double> grad_t_m; // [n_loc][n_qp][3]  basis_values[j].grad_t_m
+		std::vector<double> val;      // [n_loc][n_qp]     basis_values[j].val (only when the table is given)
 		std::vector<double> jac_it;   // [n_qp][9] row-major
 		std::vector<double> det;      // [n_qp]
 		std::vector<double> weights;  // [n_qp] quadrature.weights
@@ -264,7 +265,7 @@ namespace
 		oracle_desc d;
 		int size = 3; // Assembler::size()
 		std::vector<int32_t> conn, lattice;
-		std::vector<double> vertices, qpts, qw, ref_grads, lambda, mu;
+		std::vector<double> vertices, qpts, qw, ref_grads, lambda, mu, ref_vals, density;
 		// AssemblyValsCache (AssemblyValsCache.cpp:11-67)
 		std::vector<ElementAssemblyValues> cache;
 
@@ -316,6 +317,15 @@ namespace
 				for (int j = 0; j < n_loc; ++j)
 					for (int c = 0; c < 3; ++c)
 						vals.grad[(size_t(j) * n_qp + q) * 3 + c] = pb.ref_grads[(size_t(q) * n_loc + j) * 3 + c];
+		}
+
+		// basis.evaluate_bases(pts, basis_values) (ElementAssemblyValues.cpp:178-180): from the table
+		if (!pb.ref_vals.empty())
+		{
+			vals.val.resize(size_t(n_loc) * n_qp);
+			for (int q = 0; q < n_qp; ++q)
+				for (int j = 0; j < n_loc; ++j)
+					vals.val[size_t(j) * n_qp + q] = pb.ref_vals[size_t(q) * n_loc + j];
 		}
 
 		// finalize3d (ElementAssemblyValues.cpp:65-104): geometric bases are P1, gradients
@@ -676,6 +686,18 @@ namespace
 			res += (gi[0] * gj[0] + gi[1] * gj[1] + gi[2] * gj[2]) * da[k];
 		}
 		return res;
+	}
+
+	// Mass.cpp:5-23: tmp = sum_q rho * phi_i(q) * phi_j(q) * da(q) on the diagonal of the size x size block
+	void mass_local(const ElementAssemblyValues &vals, const std::vector<double> &da, int i, int j, double rho, int size, double *blk)
+	{
+		double tmp = 0;
+		for (int q = 0; q < vals.n_qp; ++q)
+			tmp += rho * vals.val[size_t(i) * vals.n_qp + q] * vals.val[size_t(j) * vals.n_qp + q] * da[q];
+		for (int k = 0; k < size * size; ++k)
+			blk[k] = 0.0;
+		for (int k = 0; k < size; ++k)
+			blk[k * size + k] = tmp;
 	}
 
 	// LinearElasticity.cpp:106-134 compute_energy_aux<T>
@@ -1172,6 +1194,12 @@ extern "C"
 			pb.lambda.assign(desc->lambda, desc->lambda + ne);
 		if (desc->mu)
 			pb.mu.assign(desc->mu, desc->mu + ne);
+		if (desc->ref_vals)
+			pb.ref_vals.assign(desc->ref_vals, desc->ref_vals + nq * nl);
+		if (desc->density)
+			pb.density.assign(desc->density, desc->density + ne);
+		if (pb.density.empty())
+			pb.density.assign(ne, 1.0);
 		if (pb.lambda.empty())
 			pb.lambda.assign(ne, 0.0);
 		if (pb.mu.empty())
@@ -1359,6 +1387,8 @@ extern "C"
 						double blk[9];
 						if (pb.d.material == ORACLE_LAPLACIAN)
 							blk[0] = laplacian_local(vals, ls.da, i, j);
+						else if (pb.d.material == ORACLE_MASS)
+							mass_local(vals, ls.da, i, j, pb.density[e], size, blk);
 						else
 							linear_elasticity_local(vals, ls.da, i, j, pb.lambda[e], pb.mu[e], blk);
 						for (int n = 0; n < size; ++n)

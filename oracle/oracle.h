@@ -31,7 +31,8 @@ extern "C"
 	{
 		ORACLE_NEOHOOKEAN = 0,
 		ORACLE_LINEAR_ELASTICITY = 1,
-		ORACLE_LAPLACIAN = 2
+		ORACLE_LAPLACIAN = 2,
+		ORACLE_MASS = 3 /* assembler/Mass.cpp: LinearAssembler with rho * phi_i * phi_j on the block diagonal */
 	};
 
 	typedef struct
@@ -52,6 +53,8 @@ extern "C"
 		const double *mu;            /* [n_elements] */
 		int32_t use_cache;           /* 1: AssemblyValsCache::init, 0: init_empty (recompute per call) */
 		int32_t n_threads;           /* stand-in for TBB's thread count */
+		const double *ref_vals;      /* [n_qp][n_loc] basis values basis_values[j].val(q) (ORACLE_MASS only) */
+		const double *density;       /* [n_elements] rho (ORACLE_MASS only) */
 	} oracle_desc;
 
 	typedef struct oracle_problem oracle_problem;

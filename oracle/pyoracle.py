@@ -14,8 +14,8 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = None
 
-NEOHOOKEAN, LINEAR_ELASTICITY, LAPLACIAN = 0, 1, 2
-MATERIAL_IDS = {"NeoHookean": NEOHOOKEAN, "LinearElasticity": LINEAR_ELASTICITY, "Laplacian": LAPLACIAN}
+NEOHOOKEAN, LINEAR_ELASTICITY, LAPLACIAN, MASS = 0, 1, 2, 3
+MATERIAL_IDS = {"NeoHookean": NEOHOOKEAN, "LinearElasticity": LINEAR_ELASTICITY, "Laplacian": LAPLACIAN, "Mass": MASS}
 
 _dp = ctypes.POINTER(ctypes.c_double)
 _ip = ctypes.POINTER(ctypes.c_int32)
@@ -28,6 +28,7 @@ class _Desc(ctypes.Structure):
         ("node_lattice", _ip), ("conn", _ip), ("vertices", _dp), ("quad_points", _dp),
         ("quad_weights", _dp), ("ref_grads", _dp), ("lambda_", _dp), ("mu", _dp),
         ("use_cache", ctypes.c_int32), ("n_threads", ctypes.c_int32),
+        ("ref_vals", _dp), ("density", _dp),
     ]
 
 
@@ -116,7 +117,8 @@ class OracleProblem:
     """One assembler + FE space, as the reference's NLAssembler/LinearAssembler sees it."""
 
     def __init__(self, material, conn, vertices, n_bases, quad_points, quad_weights, ref_grads,
-                 lam=None, mu=None, basis_order=1, node_lattice=None, use_cache=True, n_threads=1):
+                 lam=None, mu=None, basis_order=1, node_lattice=None, use_cache=True, n_threads=1,
+                 ref_vals=None, density=None):
         L = lib()
         self.material = MATERIAL_IDS[material] if isinstance(material, str) else int(material)
         self.conn = np.ascontiguousarray(conn, dtype=np.int32)
@@ -137,6 +139,12 @@ class OracleProblem:
         d.quad_points, d.quad_weights, d.ref_grads = _d(self.qp), _d(self.qw), _d(self.rg)
         d.lambda_, d.mu = _d(self.lam), _d(self.mu)
         d.use_cache, d.n_threads = int(bool(use_cache)), int(n_threads)
+        if self.material == MATERIAL_IDS["Mass"]:
+            assert ref_vals is not None, "Mass needs the basis values at the (mass) quadrature points"
+            self.rv = np.ascontiguousarray(ref_vals, dtype=np.float64)
+            assert self.rv.shape == (self.qw.size, nl)
+            self.rho = np.ascontiguousarray(np.broadcast_to(1.0 if density is None else density, (ne,)), dtype=np.float64)
+            d.ref_vals, d.density = _d(self.rv), _d(self.rho)
         self._h = L.oracle_create(ctypes.byref(d))
         self.size = L.oracle_size(self._h)
         self.ndof = self.n_bases * self.size
@@ -215,6 +223,15 @@ def project_to_psd(a):
     a = np.array(a, dtype=np.float64, order="C")
     lib().oracle_project_to_psd(a.shape[0], _d(a))
     return a
+
+
+def inertia(mass_csc, x, x_tilde):
+    """InertiaForm::value_unweighted / first_derivative_unweighted (solver/forms/InertiaForm.cpp:17-29):
+    (0.5 tmp^T M tmp, M tmp) with tmp = x - x_tilde; the Hessian is M itself (:31-34)."""
+    tmp = np.asarray(x, dtype=np.float64).reshape(-1) - np.asarray(x_tilde, dtype=np.float64).reshape(-1)
+    M = mass_csc.to_scipy()
+    g = M @ tmp
+    return 0.5 * float(tmp @ g), g
 
 
 def project_gradient(grad, constrained, n_dofs=None):
@@ -301,10 +318,15 @@ class Cache:
         return CSC(self.size, outer, inner, vals)
 
 
-def problem_from_mesh(mesh, material, E=1e5, nu=0.3, order=None, **kw):
-    """Convenience: oracle problem on a polyfem_b200.mesh.TetMesh with a single material."""
+def problem_from_mesh(mesh, material, E=1e5, nu=0.3, order=None, rho=1.0, **kw):
+    """Convenience: oracle problem on a polyfem_b200.mesh.TetMesh with a single material.
+    Mass uses the mass quadrature order 2p of AssemblerUtils.cpp:204-211 unless `order` is given."""
     from polyfem_b200 import tables
     from polyfem_b200.mesh import lame_from_E_nu
+    if material == "Mass":
+        t = tables.reference_tables(mesh.p, order if order is not None else tables.quadrature_order(mesh.p, is_mass=True))
+        return OracleProblem(material, mesh.conn, mesh.vertices, mesh.n_bases, t["points"], t["weights"], t["grad"],
+                             basis_order=mesh.p, ref_vals=t["val"], density=rho, **kw)
     t = tables.reference_tables(mesh.p, order)
     lam, mu = lame_from_E_nu(E, nu)
     return OracleProblem(material, mesh.conn, mesh.vertices, mesh.n_bases, t["points"], t["weights"], t["grad"],

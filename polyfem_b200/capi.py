@@ -16,8 +16,8 @@ LIB_PATH = os.environ.get("PFA_LIB", os.path.join(_HERE, "libpfa.so"))  # PFA_LI
 
 PFA_OK = 0
 PFA_ERR_INVALID, PFA_ERR_UNSUPPORTED, PFA_ERR_CUDA, PFA_ERR_NOMEM, PFA_ERR_NO_DEVICE = -1, -2, -3, -4, -5
-NEOHOOKEAN, LINEAR_ELASTICITY, LAPLACIAN = 0, 1, 2
-MATERIAL_IDS = {"NeoHookean": NEOHOOKEAN, "LinearElasticity": LINEAR_ELASTICITY, "Laplacian": LAPLACIAN}
+NEOHOOKEAN, LINEAR_ELASTICITY, LAPLACIAN, MASS = 0, 1, 2, 3
+MATERIAL_IDS = {"NeoHookean": NEOHOOKEAN, "LinearElasticity": LINEAR_ELASTICITY, "Laplacian": LAPLACIAN, "Mass": MASS}
 
 _dp = ctypes.POINTER(ctypes.c_double)
 _ip = ctypes.POINTER(ctypes.c_int32)
@@ -30,6 +30,7 @@ EXPORTS = [
     "pfa_profile_read", "pfa_launch_count", "pfa_setup_seconds",
     "pfa_is_step_valid", "pfa_set_constrained_dofs", "pfa_reduced_sizes", "pfa_reduced_pattern", "pfa_reduced_pattern_device",
     "pfa_project_gradient", "pfa_project_hessian", "pfa_grad_hess_reduced", "pfa_grad_hess_part",
+    "pfa_symv", "pfa_inertia", "pfa_axpy",
 ]
 
 
@@ -42,6 +43,7 @@ class MeshDesc(ctypes.Structure):
         ("lambda_", _dp), ("mu", _dp),
         ("material_stride", ctypes.c_int32), ("device", ctypes.c_int32), ("flags", ctypes.c_int32),
         ("n_ghost_elements", ctypes.c_int32), ("n_first_elements", ctypes.c_int32),
+        ("ref_vals", _dp), ("density", _dp),
     ]
 
 
@@ -87,6 +89,9 @@ def lib():
     L.pfa_reduced_pattern_device.argtypes = [vp, ctypes.POINTER(vp), ctypes.POINTER(vp)]
     L.pfa_project_gradient.argtypes = [vp, vp, ctypes.c_double, vp]
     L.pfa_project_hessian.argtypes = [vp, vp, ctypes.c_double, vp]
+    L.pfa_symv.argtypes = [vp, vp, vp, vp]
+    L.pfa_inertia.argtypes = [vp, vp, vp, vp, vp, vp]
+    L.pfa_axpy.argtypes = [vp, i64, ctypes.c_double, vp, vp]
     L.pfa_grad_hess_part.argtypes = [vp, vp, c_int, vp, vp, vp, c_int]
     L.pfa_grad_hess_reduced.argtypes = [vp, vp, c_int, ctypes.c_double, vp, vp, vp]
     L.pfa_synchronize.argtypes = [vp]
@@ -122,23 +127,32 @@ class Handle:
     """One pfa_handle: one mesh + material on one GPU."""
 
     def __init__(self, material, conn, n_bases, quad_weights, ref_grads, vertices=None, jac_it=None, da=None,
-                 lam=None, mu=None, device=0, n_ghost_elements=0, flags=0, n_first_elements=0):
+                 lam=None, mu=None, device=0, n_ghost_elements=0, flags=0, n_first_elements=0, ref_vals=None, density=None):
         L = lib()
         self.material = MATERIAL_IDS[material] if isinstance(material, str) else int(material)
         conn = np.ascontiguousarray(conn, dtype=np.int32)
         qw = np.ascontiguousarray(quad_weights, dtype=np.float64)
-        rg = np.ascontiguousarray(ref_grads, dtype=np.float64)
         ne, nl = conn.shape
         ne -= int(n_ghost_elements)  # trailing rows of conn are pattern-only ghost elements
         nq = qw.size
-        assert rg.shape == (nq, nl, 3), f"ref_grads must be [n_qp, n_loc, 3], got {rg.shape}"
+        rg = None if ref_grads is None else np.ascontiguousarray(ref_grads, dtype=np.float64)
+        assert rg is None or rg.shape == (nq, nl, 3), f"ref_grads must be [n_qp, n_loc, 3], got {rg.shape}"
         d = MeshDesc()
         d.struct_size = ctypes.sizeof(MeshDesc)
         d.material, d.n_elements, d.n_loc, d.n_bases, d.n_qp = self.material, ne, nl, int(n_bases), nq
         keep = [conn, qw, rg]
         d.conn = conn.ctypes.data_as(_ip)
         d.quad_weights = qw.ctypes.data_as(_dp)
-        d.ref_grads = rg.ctypes.data_as(_dp)
+        if rg is not None:
+            d.ref_grads = rg.ctypes.data_as(_dp)
+        if self.material == MASS:
+            rv = np.ascontiguousarray(ref_vals, dtype=np.float64)
+            assert rv.shape == (nq, nl), f"ref_vals must be [n_qp, n_loc], got {rv.shape}"
+            rho = np.asarray(1.0 if density is None else density, dtype=np.float64)
+            rho = np.ascontiguousarray(np.full(ne, float(rho)) if rho.ndim == 0 else rho)
+            assert rho.size in (ne, ne * nq)
+            d.ref_vals, d.density = rv.ctypes.data_as(_dp), rho.ctypes.data_as(_dp)
+            keep += [rv, rho]
         if vertices is not None:
             v = np.ascontiguousarray(vertices, dtype=np.float64).reshape(ne, 4, 3)
             d.vertices = v.ctypes.data_as(_dp)
@@ -149,7 +163,9 @@ class Handle:
             d.jac_it, d.da = j.ctypes.data_as(_dp), a.ctypes.data_as(_dp)
             keep += [j, a]
         stride = 1
-        if self.material != LAPLACIAN:
+        if self.material == MASS:
+            stride = 1 if rho.size == ne else nq
+        elif self.material != LAPLACIAN:
             lam = np.asarray(lam, dtype=np.float64)
             mu = np.asarray(mu, dtype=np.float64)
             if lam.ndim == 0:
@@ -259,6 +275,30 @@ class Handle:
     # ---- raw pointer entry (host numpy arrays or torch CUDA tensors, any may be None) ----
     def grad_hess_raw(self, x, energy=None, grad=None, values=None, project_to_psd=False):
         self._check(lib().pfa_grad_hess(self._h, _ptr(x), int(bool(project_to_psd)), _ptr(energy), _ptr(grad), _ptr(values)))
+
+    # ---- InertiaForm on a Mass handle ----
+    def symv(self, values, x):
+        x = np.ascontiguousarray(x, dtype=np.float64).reshape(-1)
+        values = np.ascontiguousarray(values, dtype=np.float64)
+        y = np.zeros(self.ndof)
+        self._check(lib().pfa_symv(self._h, _ptr(values), _ptr(x), _ptr(y)))
+        return y
+
+    def inertia(self, mass_values, x, x_tilde):
+        """(0.5 d^T M d, M d), d = x - x_tilde (InertiaForm::value / first_derivative)."""
+        x = np.ascontiguousarray(x, dtype=np.float64).reshape(-1)
+        xt = np.ascontiguousarray(x_tilde, dtype=np.float64).reshape(-1)
+        mass_values = np.ascontiguousarray(mass_values, dtype=np.float64)
+        e, g = np.zeros(1), np.zeros(self.ndof)
+        self._check(lib().pfa_inertia(self._h, _ptr(mass_values), _ptr(x), _ptr(xt), _ptr(e), _ptr(g)))
+        return float(e[0]), g
+
+    def inertia_raw(self, mass_values, x, x_tilde, energy, grad):
+        self._check(lib().pfa_inertia(self._h, _ptr(mass_values), _ptr(x), _ptr(x_tilde), _ptr(energy), _ptr(grad)))
+
+    def axpy(self, a, x, y):
+        """y += a * x on device tensors of equal length."""
+        self._check(lib().pfa_axpy(self._h, int(x.numel()), float(a), _ptr(x), _ptr(y)))
 
     def grad_hess_part_raw(self, x, energy, grad, values, part, project_to_psd=False):
         """part 1: clear outputs + elements [0, n_first_elements); part 2: add the rest (device tensors only)."""

@@ -5,6 +5,7 @@
 
 #include <chrono>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <stdexcept>
@@ -124,6 +125,10 @@ namespace
 	}
 
 	constexpr size_t kMaxProfRecords = 8192;
+#ifndef PFA_REST_BATCH_QUOTA
+#define PFA_REST_BATCH_QUOTA 4
+#endif
+	constexpr int kRestBatchQuota = PFA_REST_BATCH_QUOTA; // pfa_grad_hess_part(PFA_PART_REST): warp batches per warp
 
 	void prof_begin(pfa_handle *h, const char *name, bool is_kernel = true)
 	{
@@ -235,8 +240,8 @@ namespace
 		}
 		if (scale != 1.0 && !rowlane_applies(h->dm.material, h->dm.n_loc, h->dm.n_qp))
 			return fail(h, PFA_ERR_UNSUPPORTED, "a Form weight other than 1 is fused for NeoHookean P1/P2 tets only");
-		if (h->dm.material == PFA_LAPLACIAN && !linear)
-			return fail(h, PFA_ERR_UNSUPPORTED, "Laplacian is a LinearAssembler: only pfa_linear_stiffness applies");
+		if ((h->dm.material == PFA_LAPLACIAN || h->dm.material == PFA_MASS) && !linear)
+			return fail(h, PFA_ERR_UNSUPPORTED, "Laplacian and Mass are LinearAssemblers: only pfa_linear_stiffness applies");
 		if (h->dm.material == PFA_NEOHOOKEAN && linear)
 			return fail(h, PFA_ERR_UNSUPPORTED, "NeoHookean is an NLAssembler: pfa_linear_stiffness does not apply");
 
@@ -282,6 +287,13 @@ namespace
 			if (oe.to_host || op.to_host || og.to_host || ov.to_host || (x != nullptr && a.x != x))
 				return fail(h, PFA_ERR_INVALID, "pfa_grad_hess_part works on device pointers only");
 			dm.zoff = nullptr;
+			// the second part is meant to run next to the interface exchange of another stream
+			if (part == PFA_PART_REST)
+			{
+				// PFA_REST_QUOTA (environment, experiments): 0 = persistent warps
+				static const int quota = [] { const char *v = std::getenv("PFA_REST_QUOTA"); return v ? std::atoi(v) : kRestBatchQuota; }();
+				a.batch_quota = quota;
+			}
 		}
 		PFA_CUDA(h, cudaMemsetAsync(h->d_counter, 0, 4 * sizeof(int), h->stream));
 
@@ -330,18 +342,25 @@ extern "C"
 		*out = nullptr;
 		if (d->struct_size != int32_t(sizeof(pfa_mesh_desc)))
 			return fail(nullptr, PFA_ERR_INVALID, "pfa_create: struct_size does not match this library's pfa_mesh_desc");
-		if (d->material < PFA_NEOHOOKEAN || d->material > PFA_LAPLACIAN)
+		if (d->material < PFA_NEOHOOKEAN || d->material > PFA_MASS)
 			return fail(nullptr, PFA_ERR_INVALID, "pfa_create: unknown material");
 		if (d->n_elements <= 0 || d->n_loc <= 0 || d->n_bases <= 0 || d->n_qp <= 0 || d->n_ghost_elements < 0)
 			return fail(nullptr, PFA_ERR_INVALID, "pfa_create: n_elements, n_loc, n_bases and n_qp must be positive");
 		if (d->n_first_elements < 0 || d->n_first_elements > d->n_elements)
 			return fail(nullptr, PFA_ERR_INVALID, "pfa_create: n_first_elements must lie in [0, n_elements]");
-		if (!d->conn || !d->quad_weights || !d->ref_grads)
+		const bool is_mass = d->material == PFA_MASS;
+		if (!d->conn || !d->quad_weights || (!is_mass && !d->ref_grads))
 			return fail(nullptr, PFA_ERR_INVALID, "pfa_create: conn, quad_weights and ref_grads are required");
+		if (is_mass && (!d->ref_vals || !d->density))
+			return fail(nullptr, PFA_ERR_INVALID, "pfa_create: PFA_MASS needs ref_vals and density");
+		if (is_mass && d->n_loc != 4 && d->n_loc != 10 && d->n_loc != 20 && d->n_loc != 35)
+			return fail(nullptr, PFA_ERR_UNSUPPORTED, "pfa_create: PFA_MASS is implemented for P1..P4 tets");
+		// Lame parameters, or the density in both slots
+		const double *lam_src = is_mass ? d->density : d->lambda, *mu_src = is_mass ? d->density : d->mu;
 		const bool affine = d->vertices != nullptr;
 		if (!affine && !(d->jac_it && d->da))
 			return fail(nullptr, PFA_ERR_INVALID, "pfa_create: give either vertices (affine) or jac_it + da");
-		if (d->material != PFA_LAPLACIAN && (!d->lambda || !d->mu))
+		if (d->material != PFA_LAPLACIAN && (!lam_src || !mu_src))
 			return fail(nullptr, PFA_ERR_INVALID, "pfa_create: lambda and mu are required for elastic materials");
 		if (d->material != PFA_LAPLACIAN && d->material_stride != 1 && d->material_stride != d->n_qp)
 			return fail(nullptr, PFA_ERR_INVALID, "pfa_create: material_stride must be 1 or n_qp");
@@ -399,7 +418,7 @@ extern "C"
 		m.n_qp = d->n_qp;
 		m.geom_per_qp = affine ? 0 : 1;
 		m.mat_stride = d->material == PFA_LAPLACIAN ? 1 : d->material_stride;
-		if (!assemble_supported(m))
+		if (!is_mass && !assemble_supported(m))
 		{
 			h->err = "pfa_create: n_loc x n_qp too large for the shared-memory staging of this build";
 			return bail(PFA_ERR_UNSUPPORTED);
@@ -411,7 +430,7 @@ extern "C"
 		std::vector<int32_t> conn_p;
 		std::vector<double> vert_p, lam_p, mu_p;
 		const int32_t *conn_in = d->conn;
-		const double *vert_in = d->vertices, *lam_in = d->lambda, *mu_in = d->mu;
+		const double *vert_in = d->vertices, *lam_in = lam_src, *mu_in = mu_src;
 		try
 		{
 			if (affine && !(d->flags & PFA_FLAG_KEEP_ELEMENT_ORDER) && d->n_elements > 1)
@@ -451,8 +470,8 @@ extern "C"
 					for (size_t e = 0; e < ne_; ++e)
 						for (size_t k = 0; k < st_; ++k)
 						{
-							lam_p[e * st_ + k] = d->lambda[size_t(perm[e]) * st_ + k];
-							mu_p[e * st_ + k] = d->mu[size_t(perm[e]) * st_ + k];
+							lam_p[e * st_ + k] = lam_src[size_t(perm[e]) * st_ + k];
+							mu_p[e * st_ + k] = mu_src[size_t(perm[e]) * st_ + k];
 						}
 					lam_in = lam_p.data();
 					mu_in = mu_p.data();
@@ -507,10 +526,15 @@ extern "C"
 			UP(h->d_elem_id, perm.data(), ne, int32_t);
 			m.elem_id = h->d_elem_id;
 		}
-		UP(m.ref_grads, d->ref_grads, nq * nl * 3, double);
-		h->h_ref_grads.assign(d->ref_grads, d->ref_grads + nq * nl * 3);
-		m.ref_grads_host = h->h_ref_grads.data();
-		m.p2_structured = p2_table_structured(m.ref_grads_host, m.n_loc, m.n_qp) ? 1 : 0;
+		if (d->ref_grads)
+		{
+			UP(m.ref_grads, d->ref_grads, nq * nl * 3, double);
+			h->h_ref_grads.assign(d->ref_grads, d->ref_grads + nq * nl * 3);
+			m.ref_grads_host = h->h_ref_grads.data();
+			m.p2_structured = p2_table_structured(m.ref_grads_host, m.n_loc, m.n_qp) ? 1 : 0;
+		}
+		if (is_mass)
+			UP(m.ref_vals, d->ref_vals, nq * nl, double);
 		UP(m.qweights, d->quad_weights, nq, double);
 		UP(m.adj_off, hp.adj_off.data(), hp.adj_off.size(), int32_t);
 		UP(m.adj, hp.adj.data(), hp.adj.size(), int32_t);
@@ -699,6 +723,8 @@ extern "C"
 			return PFA_ERR_INVALID;
 		if (h->dm.material == PFA_LAPLACIAN)
 			return PFA_OK;
+		if (h->dm.material == PFA_MASS && lambda && !mu)
+			mu = lambda; // the density lives in both slots
 		if (!lambda || !mu || material_stride != h->dm.mat_stride)
 			return fail(h, PFA_ERR_INVALID, "pfa_set_materials: NULL array or material_stride differs from pfa_create");
 		PFA_CUDA(h, cudaSetDevice(h->device));
@@ -1004,6 +1030,78 @@ extern "C"
 			return PFA_ERR_INVALID;
 		return project_common(h, "project_hessian(gather)", values_full, size_t(h->nnz), h->d_map, size_t(h->nnz_red), scale, values_reduced,
 							  &h->s_values, &h->s_val_out, true);
+	}
+
+	namespace
+	{
+		// device view of a read-only vector argument (host data is staged into *staging)
+		int in_dev(pfa_handle *h, const double *p, size_t n, double **staging, const double **out)
+		{
+			if (is_device_ptr(p))
+			{
+				*out = p;
+				return PFA_OK;
+			}
+			int rc = ensure_staging(h, staging, n);
+			if (rc != PFA_OK)
+				return rc;
+			PFA_CUDA(h, cudaMemcpyAsync(*staging, p, n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+			*out = *staging;
+			return PFA_OK;
+		}
+	} // namespace
+
+	int pfa_inertia(pfa_handle *h, const double *mass_values, const double *x, const double *x_tilde, double *energy, double *grad)
+	{
+		if (!h || !mass_values || !x)
+			return fail(h, PFA_ERR_INVALID, "pfa_inertia / pfa_symv: NULL argument");
+		if (!energy && !grad)
+			return fail(h, PFA_ERR_INVALID, "pfa_inertia: all outputs are NULL");
+		h->err.clear();
+		PFA_CUDA(h, cudaSetDevice(h->device));
+		const double *v_dev, *x_dev, *xt_dev = nullptr;
+		int rc;
+		if ((rc = in_dev(h, mass_values, size_t(h->nnz), &h->s_values, &v_dev)) != PFA_OK || (rc = in_dev(h, x, size_t(h->ndof), &h->s_x, &x_dev)) != PFA_OK)
+			return rc;
+		if (x_tilde && (rc = in_dev(h, x_tilde, size_t(h->ndof), &h->s_vec_in, &xt_dev)) != PFA_OK)
+			return rc;
+		OutBuf oe, og;
+		if ((rc = stage_output(h, energy, 1, &h->d_energy, oe)) != PFA_OK || (rc = stage_output(h, grad, size_t(h->ndof), &h->s_grad, og)) != PFA_OK)
+			return rc;
+		if (oe.dev)
+			PFA_CUDA(h, cudaMemsetAsync(oe.dev, 0, sizeof(double), h->stream));
+		prof_begin(h, "symv_kernel");
+		cudaError_t ce = launch_symv(h->d_outer, h->d_inner, v_dev, x_dev, xt_dev, int32_t(h->ndof), og.dev, oe.dev, h->stream);
+		prof_end(h);
+		if (ce != cudaSuccess)
+			return fail(h, PFA_ERR_CUDA, std::string("symv_kernel: ") + cudaGetErrorString(ce));
+		if ((rc = finish_output(h, oe)) != PFA_OK || (rc = finish_output(h, og)) != PFA_OK)
+			return rc;
+		if (oe.to_host || og.to_host)
+			PFA_CUDA(h, cudaStreamSynchronize(h->stream));
+		return PFA_OK;
+	}
+
+	int pfa_symv(pfa_handle *h, const double *values, const double *x, double *y)
+	{
+		if (!y)
+			return fail(h, PFA_ERR_INVALID, "pfa_symv: NULL argument");
+		return pfa_inertia(h, values, x, nullptr, nullptr, y);
+	}
+
+	int pfa_axpy(pfa_handle *h, int64_t n, double a, const double *x, double *y)
+	{
+		if (!h || !x || !y || n < 0)
+			return fail(h, PFA_ERR_INVALID, "pfa_axpy: NULL argument");
+		if (!is_device_ptr(x) || !is_device_ptr(y))
+			return fail(h, PFA_ERR_INVALID, "pfa_axpy works on device pointers");
+		PFA_CUDA(h, cudaSetDevice(h->device));
+		prof_begin(h, "axpy_kernel");
+		cudaError_t ce = launch_axpy(n, a, x, y, h->sm_count, h->stream);
+		prof_end(h);
+		if (ce != cudaSuccess)
+			return fail(h, PFA_ERR_CUDA, std::string("axpy_kernel: ") + cudaGetErrorString(ce));
+		return PFA_OK;
 	}
 
 	int pfa_grad_hess_part(pfa_handle *h, const double *x, int project_to_psd, double *energy, double *grad, double *values, int part)

@@ -25,6 +25,7 @@ namespace pfa
 		const double *detj = nullptr;      // [n_el][gq]   affine: det(J) ; per-qp: da = det*w
 		const double *lambda = nullptr;    // [n_el][mat_stride]
 		const double *mu = nullptr;        // [n_el][mat_stride]
+		const double *ref_vals = nullptr;  // [n_qp][n_loc] basis values (PFA_MASS)
 		const double *ref_grads = nullptr; // [n_qp][n_loc][3]
 		const double *qweights = nullptr;  // [n_qp]
 		const double *ref_grads_host = nullptr; // host copy of ref_grads (owned by the handle): source of the __constant__ table
@@ -64,6 +65,7 @@ namespace pfa
 		double *values = nullptr;        // [nnz]  (accumulated, zeroed by caller)
 		int project_to_psd = 0;
 		int32_t e_begin = 0, e_end = 0; // (internal) element range of this launch
+		int32_t batch_quota = 0;        // row-lane kernels: warp batches per warp before it retires (0 = persistent)
 		// row-lane / psd kernels only: every output is multiplied by `scale` (Form weight); with
 		// old_to_new set, gradient entries go to their Dirichlet-reduced position (or are dropped) and
 		// DeviceMesh::entry / cstride must be the tables built for the reduced matrix
@@ -106,6 +108,11 @@ namespace pfa
 									  int32_t *node_mask, int32_t *rowprefix, int32_t *cs_red, int32_t *cbase_red, int32_t *entry_red, int32_t *cstride_red, cudaStream_t st);
 	// dst[t] = scale * src[map[t]]
 	cudaError_t launch_gather_scale(const double *src, const int32_t *map, int64_t n, double scale, double *dst, int sm_count, cudaStream_t st);
+	// y = A (x - x_tilde) for the symmetric CSC matrix (x_tilde may be NULL), *energy += 0.5 (x - x_tilde)^T y;
+	// y and energy may be NULL
+	cudaError_t launch_symv(const int32_t *outer, const int32_t *inner, const double *values, const double *x, const double *x_tilde, int32_t ndof,
+							double *y, double *energy, cudaStream_t st);
+	cudaError_t launch_axpy(int64_t n, double a, const double *x, double *y, int sm_count, cudaStream_t st);
 	// *flag = 1 when any entry is NaN (flag must be zeroed by the caller)
 	cudaError_t launch_any_nan(const double *v, int64_t n, int *flag, int sm_count, cudaStream_t st);
 

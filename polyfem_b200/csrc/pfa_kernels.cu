@@ -592,10 +592,15 @@ namespace pfa
 			batch = __shfl_sync(0xffffffffu, batch, 0);
 			if (a.epoch > 0)
 				zero_duty(m, a, batch / EB, lane);
+			// batch_quota > 0: a warp retires after that many batches (the grid is sized to cover the range),
+			// so that CTAs of kernels on other streams - the interface exchange of the multi-GPU path -
+			// get SM slots while this kernel is running; 0: persistent warps
+			int left = a.batch_quota > 0 ? a.batch_quota : 0x7fffffff;
 			while (batch < a.e_end)
 			{
-				int next = 0;
-				if (lane == 0)
+				int next = a.e_end; // a warp that has used up its quota draws nothing more
+				--left;
+				if (lane == 0 && left > 0)
 					next = a.e_begin + atomicAdd(a.work_counter, EB);
 				// ---- connectivity and entry offsets of the batch ----
 				const int n_batch = min(EB, a.e_end - batch);
@@ -933,8 +938,11 @@ namespace pfa
 				return err;
 			if (per_sm < 1)
 				per_sm = 1;
-			const int64_t need = (int64_t(m.n_el) + WARPS * RL::EB - 1) / (WARPS * RL::EB);
-			const int grid = int(std::max<int64_t>(1, std::min<int64_t>(need, int64_t(sm_count) * per_sm)));
+			const int64_t n_range = std::max<int64_t>(1, int64_t(a.e_end) - a.e_begin);
+			const int64_t need = (n_range + WARPS * RL::EB - 1) / (WARPS * RL::EB);
+			int grid = int(std::max<int64_t>(1, std::min<int64_t>(need, int64_t(sm_count) * per_sm)));
+			if (a.batch_quota > 0 && a.epoch == 0) // retiring warps: enough CTAs for every batch of the range
+				grid = int(std::max<int64_t>(grid, (need + a.batch_quota - 1) / a.batch_quota));
 			kern<<<grid, WARPS * 32, smem, st>>>(m, a);
 			return cudaGetLastError();
 		}
@@ -1480,6 +1488,119 @@ namespace pfa
 			return cudaGetLastError();
 		}
 
+		// ------------------------------------------------------------------------------------
+		// Mass matrix (Mass.cpp:5-23 through LinearAssembler::assemble, Assembler.cpp:157-384), size 3:
+		// M[(i,m),(j,m)] = sum_q rho phi_i(q) phi_j(q) da_q, the other entries of the 3x3 block are
+		// stored zeros. Same register tiling as the Laplacian kernel with scalar operands; the basis
+		// values are one CTA-wide table (they do not depend on the element).
+		// ------------------------------------------------------------------------------------
+		template <int NL, int WARPS>
+		__global__ void __launch_bounds__(WARPS * 32) assemble_mass_tile_kernel(const DeviceMesh m, const AssembleArgs a)
+		{
+			constexpr int T = LapTile<NL>::T, NLP = LapTile<NL>::NLP;
+			extern __shared__ double smem[];
+			const int n_qp = m.n_qp;
+			const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+			double *s_phi = smem;             // [n_qp][NLP], zero beyond NL
+			double *s_w = s_phi + n_qp * NLP; // [n_qp]
+			double *sC = s_w + n_qp + warp * n_qp; // [n_qp] rho * da of the warp's element
+			for (int t = threadIdx.x; t < n_qp * NLP; t += WARPS * 32)
+			{
+				const int q = t / NLP, i = t - q * NLP;
+				s_phi[t] = i < NL ? m.ref_vals[q * NL + i] : 0.0;
+			}
+			for (int t = threadIdx.x; t < n_qp; t += WARPS * 32)
+				s_w[t] = m.qweights[t];
+			__syncthreads();
+			const int ti = lane / 5, tj = lane % 5;
+			const bool tile_lane = lane < 25;
+
+			for (int e = a.e_begin + blockIdx.x * WARPS + warp; e < a.e_end; e += gridDim.x * WARPS)
+			{
+				for (int q = lane; q < n_qp; q += 32)
+				{
+					const double da = m.geom_per_qp ? m.detj[size_t(e) * n_qp + q] : m.detj[e] * s_w[q];
+					sC[q] = m.lambda[size_t(e) * m.mat_stride + (m.mat_stride == 1 ? 0 : q)] * da;
+				}
+				__syncwarp();
+				if (tile_lane)
+				{
+					double acc[T][T];
+#pragma unroll
+					for (int r = 0; r < T; ++r)
+#pragma unroll
+						for (int c = 0; c < T; ++c)
+							acc[r][c] = 0.0;
+#pragma unroll 1
+					for (int q = 0; q < n_qp; ++q)
+					{
+						const double *ph = s_phi + q * NLP;
+						const double cq = sC[q];
+						double cj[T];
+#pragma unroll
+						for (int c = 0; c < T; ++c)
+							cj[c] = cq * ph[tj * T + c];
+#pragma unroll
+						for (int r = 0; r < T; ++r)
+						{
+							const double pr = ph[ti * T + r];
+#pragma unroll
+							for (int c = 0; c < T; ++c)
+								acc[r][c] = fma(pr, cj[c], acc[r][c]);
+						}
+					}
+					const int32_t *slot = m.slot + size_t(e) * NL * NL;
+					const int32_t *conn = m.conn + size_t(e) * NL;
+#pragma unroll
+					for (int c = 0; c < T; ++c)
+					{
+						const int j = tj * T + c;
+						if (j >= NL)
+							continue;
+						const int gj = conn[j];
+						const int off = m.adj_off[gj], deg = m.adj_off[gj + 1] - off;
+#pragma unroll
+						for (int r = 0; r < T; ++r)
+						{
+							const int i = ti * T + r;
+							if (i < NL)
+							{
+								// (row (g_i, mm), column (g_j, mm)) for mm = 0, 1, 2
+								double *dst = a.values + (size_t(off) * 9 + size_t(slot[i * NL + j] - off) * 3);
+								red_add(dst, acc[r][c]);
+								red_add(dst + 3 * deg + 1, acc[r][c]);
+								red_add(dst + 6 * deg + 2, acc[r][c]);
+							}
+						}
+					}
+				}
+				__syncwarp();
+			}
+		}
+
+		template <int NL>
+		cudaError_t launch_mass_tile(const DeviceMesh &m, const AssembleArgs &a, int sm_count, cudaStream_t st)
+		{
+			constexpr int WARPS = 8;
+			const size_t smem = sizeof(double) * (size_t(m.n_qp) * LapTile<NL>::NLP + m.n_qp + size_t(WARPS) * m.n_qp);
+			if (smem > 227 * 1024)
+				return cudaErrorInvalidConfiguration;
+			auto kern = assemble_mass_tile_kernel<NL, WARPS>;
+			cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+			if (err != cudaSuccess)
+				return err;
+			int per_sm = 1;
+			err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, WARPS * 32, smem);
+			if (err != cudaSuccess)
+				return err;
+			if (per_sm < 1)
+				per_sm = 1;
+			const int64_t need = (int64_t(m.n_el) + WARPS - 1) / WARPS;
+			const int grid = int(std::max<int64_t>(1, std::min<int64_t>(need, int64_t(sm_count) * per_sm)));
+			kern<<<grid, WARPS * 32, smem, st>>>(m, a);
+			return cudaGetLastError();
+		}
+
 		constexpr size_t kMaxSmem = 227 * 1024;
 
 		size_t generic_smem_bytes(int n_loc, int n_qp, int warps)
@@ -1630,6 +1751,24 @@ namespace pfa
 		case PFA_LINEAR_ELASTICITY:
 			return linear ? launch_generic<PFA_LINEAR_ELASTICITY, true>(m, a, sm_count, st)
 						  : launch_generic<PFA_LINEAR_ELASTICITY, false>(m, a, sm_count, st);
+		case PFA_MASS:
+			if (kernel_name)
+				*kernel_name = "assemble_mass_tile_kernel";
+			if (a.values == nullptr)
+				return cudaErrorInvalidValue;
+			switch (m.n_loc)
+			{
+			case 4:
+				return launch_mass_tile<4>(m, a, sm_count, st);
+			case 10:
+				return launch_mass_tile<10>(m, a, sm_count, st);
+			case 20:
+				return launch_mass_tile<20>(m, a, sm_count, st);
+			case 35:
+				return launch_mass_tile<35>(m, a, sm_count, st);
+			default:
+				return cudaErrorNotSupported;
+			}
 		case PFA_LAPLACIAN:
 			if (a.values != nullptr && !PFA_NO_LAPLACIAN_TILE)
 			{

@@ -118,6 +118,55 @@ namespace pfa
 				*flag = 1;
 		}
 
+		// y[c] = sum_k values[k] * d[inner[k]] over column c of the symmetric matrix (a CSC column read as
+		// the CSR row): one warp per column, no atomics on y; energy by one atomic per CTA
+		__global__ void symv_kernel(const int32_t *__restrict__ outer, const int32_t *__restrict__ inner, const double *__restrict__ values,
+									const double *__restrict__ x, const double *__restrict__ x_tilde, int32_t ndof, double *__restrict__ y, double *__restrict__ energy)
+		{
+			const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+			const int64_t c = int64_t(blockIdx.x) * (blockDim.x >> 5) + warp;
+			double part = 0.0;
+			if (c < ndof)
+			{
+				double s = 0.0;
+				for (int64_t k = outer[c] + lane; k < outer[c + 1]; k += 32)
+				{
+					const int32_t r = inner[k];
+					s += values[k] * (x_tilde ? x[r] - x_tilde[r] : x[r]);
+				}
+#pragma unroll
+				for (int o = 16; o > 0; o >>= 1)
+					s += __shfl_xor_sync(0xffffffffu, s, o);
+				if (lane == 0)
+				{
+					if (y)
+						y[c] = s;
+					part = 0.5 * s * (x_tilde ? x[c] - x_tilde[c] : x[c]);
+				}
+			}
+			if (energy)
+			{
+				__shared__ double sh[32];
+				if (lane == 0)
+					sh[warp] = part;
+				__syncthreads();
+				if (threadIdx.x == 0)
+				{
+					double t = 0.0;
+					for (int w = 0; w < int(blockDim.x >> 5); ++w)
+						t += sh[w];
+					atomicAdd(energy, t);
+				}
+			}
+		}
+
+		__global__ void axpy_kernel(int64_t n, double a, const double *__restrict__ x, double *__restrict__ y)
+		{
+			const int64_t stride = int64_t(gridDim.x) * blockDim.x;
+			for (int64_t t = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; t < n; t += stride)
+				y[t] += a * x[t];
+		}
+
 		// ---- tables of the row-lane kernels for the reduced matrix ----
 		// node_mask[b]: which of the 3 dofs of node b are kept
 		__global__ void node_mask_kernel(const int32_t *__restrict__ keep, int32_t n_bases, int32_t *__restrict__ node_mask)
@@ -246,6 +295,23 @@ namespace pfa
 			return cudaSuccess;
 		const unsigned grid = unsigned(std::min<int64_t>(blocks_for(n, 256), int64_t(sm_count) * 16));
 		gather_scale_kernel<<<grid, 256, 0, st>>>(src, map, n, scale, dst);
+		return cudaGetLastError();
+	}
+
+	cudaError_t launch_symv(const int32_t *outer, const int32_t *inner, const double *values, const double *x, const double *x_tilde, int32_t ndof,
+							double *y, double *energy, cudaStream_t st)
+	{
+		const int warps = 8;
+		symv_kernel<<<blocks_for(ndof, warps), warps * 32, 0, st>>>(outer, inner, values, x, x_tilde, ndof, y, energy);
+		return cudaGetLastError();
+	}
+
+	cudaError_t launch_axpy(int64_t n, double a, const double *x, double *y, int sm_count, cudaStream_t st)
+	{
+		if (n <= 0)
+			return cudaSuccess;
+		const unsigned grid = unsigned(std::min<int64_t>(blocks_for(n, 256), int64_t(sm_count) * 16));
+		axpy_kernel<<<grid, 256, 0, st>>>(n, a, x, y);
 		return cudaGetLastError();
 	}
 

@@ -204,7 +204,7 @@ class InterfaceExchange:
         (index_add_), which may run concurrently with the assembly kernel's own reductions."""
         torch = self.torch
         if self._side is None:
-            self._side = torch.cuda.Stream(device=self.device)
+            self._side = torch.cuda.Stream(device=self.device, priority=-1)  # ahead of the assembly kernel's pending CTAs
         main = torch.cuda.current_stream(self.device)
         ev = torch.cuda.Event()
         ev.record(main)

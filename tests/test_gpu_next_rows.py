@@ -174,3 +174,58 @@ def test_two_part_assembly_equals_one_launch(oracle, p, n, n_first):
     assert_values_close(outer, inner, v.cpu().numpy(), v_ref)
     with pytest.raises(capi.PfaError):
         h.grad_hess_part_raw(x, np.zeros(1), np.zeros(h.ndof), np.zeros(h.nnz), 1)  # host pointers
+
+
+def _mass_handle(mesh, rho, **kw):
+    from polyfem_b200 import capi, tables
+    t = tables.reference_tables(mesh.p, tables.quadrature_order(mesh.p, is_mass=True))
+    return capi.Handle("Mass", mesh.conn, mesh.n_bases, t["weights"], None, vertices=mesh.vertices,
+                       ref_vals=t["val"], density=rho, **kw), t
+
+
+@pytest.mark.parametrize("p,n", [(1, 4), (2, 3), (3, 2), (4, 1)])
+def test_mass_matrix(oracle, p, n):
+    from helpers import assert_values_close
+    mesh, x, t = make_case(n, p, jitter=0.2)
+    rng = np.random.default_rng(11)
+    rho = 1.0 + rng.random(mesh.n_elements)  # per-element density
+    ref = oracle.problem_from_mesh(mesh, "Mass", rho=rho).assemble()
+    h, tm = _mass_handle(mesh, rho)
+    assert h.size == 3 and h.nnz == ref.inner.size
+    outer, inner = h.pattern()
+    assert outer.tobytes() == ref.outer.tobytes() and inner.tobytes() == ref.inner.tobytes()
+    v = h.linear_stiffness()
+    assert_values_close(ref.outer, ref.inner, v, ref.values, what="mass")
+    assert np.array_equal(v == 0.0, ref.values == 0.0)  # stored zeros off the block diagonal
+
+
+def test_inertia_form_on_device(oracle):
+    import torch
+    from helpers import assert_vector_close
+    mesh, x, t = make_case(3, 2, jitter=0.1)
+    h, tm = _mass_handle(mesh, 1000.0)
+    ref = oracle.problem_from_mesh(mesh, "Mass", rho=1000.0).assemble()
+    Mv = h.linear_stiffness()
+    rng = np.random.default_rng(12)
+    xt = x + 1e-3 * rng.standard_normal(x.size)
+    e_ref, g_ref = oracle.inertia(ref, x, xt)
+    e, g = h.inertia(Mv, x, xt)
+    assert abs(e - e_ref) <= REL_TOL * abs(e_ref)
+    assert_vector_close(g, g_ref)
+    assert_vector_close(h.symv(Mv, x), ref.to_scipy() @ x, what="symv")
+    # device-resident: Newton matrix of an implicit-Euler step = dt^2 * elastic + mass, same pattern
+    he = gpu_handle(mesh, "NeoHookean", t)
+    assert he.nnz == h.nnz
+    dt = 1e-3
+    _, _, Hv = he.grad_hess(x)
+    Hd = torch.from_numpy(dt * dt * Hv).cuda()
+    Md = torch.from_numpy(Mv).cuda()
+    h.axpy(1.0, Md, Hd)
+    h.synchronize()
+    assert np.array_equal(Hd.cpu().numpy(), dt * dt * Hv + Mv)
+    ed = torch.zeros(1, dtype=torch.float64, device="cuda")
+    gd = torch.zeros(h.ndof, dtype=torch.float64, device="cuda")
+    h.inertia_raw(Md, torch.from_numpy(x).cuda(), torch.from_numpy(xt).cuda(), ed, gd)
+    h.synchronize()
+    assert abs(float(ed.item()) - e_ref) <= REL_TOL * abs(e_ref)
+    assert_vector_close(gd.cpu().numpy(), g_ref)

@@ -29,7 +29,9 @@ CFG = {
     "3s": ("NeoHookean", 2, 40, False, "NeoHookean P2 n=40 E+g+H (small cfg 3)"),
     "4L": ("Laplacian", 4, 32, True, "cfg 4 Laplacian P4 n=32 stiffness"),
     "4E": ("LinearElasticity", 4, 16, True, "cfg 4 LinearElasticity P4 n=16 stiffness (n=32 has nnz > 2^31)"),
-    "5s": ("NeoHookean", 1, 108, False, "cfg 5 per-GPU share: NeoHookean P1 n=108 (1.26 M tets = 10.1 M / 8) E+g+H"),
+    "5s": ("NeoHookean", 1, 60, False, "cfg 5 per-GPU share: NeoHookean P1 n=60 (1.30 M tets ~ 10.1 M / 8) E+g+H"),
+    "5m": ("Mass", 1, 60, True, "cfg 5 per-GPU share: Mass P1 n=60 (1.30 M tets), mass quadrature order 2"),
+    "3m": ("Mass", 2, 40, True, "Mass P2 n=40 (384 k tets), mass quadrature order 4"),
 }
 
 
@@ -47,8 +49,12 @@ def main():
     for key in a.cfg:
         material, p, n, linear, label = CFG[key]
         mesh = M.kuhn_cube(n, p)
-        t = tables.reference_tables(p)
-        h = capi.Handle(material, mesh.conn, mesh.n_bases, t["weights"], t["grad"], vertices=mesh.vertices, lam=lam, mu=mu)
+        if material == "Mass":
+            t = tables.reference_tables(p, tables.quadrature_order(p, is_mass=True))
+            h = capi.Handle(material, mesh.conn, mesh.n_bases, t["weights"], None, vertices=mesh.vertices, ref_vals=t["val"], density=1000.0)
+        else:
+            t = tables.reference_tables(p)
+            h = capi.Handle(material, mesh.conn, mesh.n_bases, t["weights"], t["grad"], vertices=mesh.vertices, lam=lam, mu=mu)
         x = M.random_displacement(mesh)
         xd = torch.from_numpy(np.ascontiguousarray(x[: h.ndof])).cuda()
         e = torch.zeros(1, dtype=torch.float64, device="cuda")
@@ -70,7 +76,9 @@ def main():
         size = h.size
         b_alg = 4 * n_loc + 80 + (16 if material != "Laplacian" else 0) + (0 if linear else 16 * h.ndof / n_el) + 8 * h.nnz / n_el
         N = n_loc * size
-        if material == "Laplacian":
+        if material == "Mass":
+            f_alg = n_qp * n_loc * n_loc
+        elif material == "Laplacian":
             f_alg = n_qp * 3 * n_loc * n_loc
         elif linear:
             f_alg = n_qp * (72 * N + 6 * N * N)

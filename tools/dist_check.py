@@ -24,6 +24,7 @@ def main():
     ap.add_argument("--cells", dest="n", type=int, default=6)
     ap.add_argument("--order", dest="p", type=int, default=2)
     ap.add_argument("--no-overlap", action="store_true")
+    ap.add_argument("--graph", action="store_true", help="capture the step in a CUDA graph and replay it")
     a = ap.parse_args()
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
@@ -42,7 +43,7 @@ def main():
     e = torch.zeros(1, dtype=torch.float64, device=dev)
     g = torch.zeros(h.ndof, dtype=torch.float64, device=dev)
     v = torch.zeros(h.nnz, dtype=torch.float64, device=dev)
-    for _ in range(3):  # repeated steps must give the same answer (buffers are re-cleared)
+    def step():
         if a.no_overlap:
             h.grad_hess_raw(xd, e, g, v)
             ex.reduce(e, g, v)
@@ -51,6 +52,26 @@ def main():
             ex.start(g, v)
             h.grad_hess_part_raw(xd, e, g, v, 2)
             ex.finish(e)
+
+    if a.graph:  # the way bench.py runs multi-GPU steps: captured once, replayed
+        cap = torch.cuda.Stream(device=dev)
+        h.set_stream(cap.cuda_stream)
+        with torch.cuda.stream(cap):
+            for _ in range(2):
+                step()
+        cap.synchronize()
+        dist.barrier()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, stream=cap):
+            step()
+        e.fill_(7.0)
+        g.fill_(7.0)
+        v.fill_(7.0)
+        for _ in range(3):
+            graph.replay()
+    else:
+        for _ in range(3):  # repeated steps must give the same answer (buffers are re-cleared)
+            step()
     torch.cuda.synchronize()
 
     hf = capi.Handle("NeoHookean", mesh.conn, mesh.n_bases, t["weights"], t["grad"], vertices=mesh.vertices, lam=lam, mu=mu, device=local)
