@@ -188,8 +188,11 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--cpu-sample-n", type=int, default=12)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-overlap", action="store_true", help="multi-GPU: exchange after the whole assembly instead of under it")
-    ap.add_argument("--no-graph", action="store_true", help="multi-GPU: issue every launch of a step from Python instead of replaying a CUDA graph")
+    ap.add_argument("--no-align", action="store_true", help="multi-GPU: cut the element range evenly instead of on whole cell layers")
+    ap.add_argument("--graph", action="store_true", help="multi-GPU, experimental: capture the step in a CUDA graph and replay it "
+                    "(hung on the round-1 stack: NCCL 2.28 point-to-point under capture; never the default)")
+    ap.add_argument("--overlap", action="store_true", help="multi-GPU: interface elements first, exchange on a side stream under the "
+                    "assembly of the rest (measured no faster than the plain order in round 1)")
     ap.add_argument("--flags", type=int, default=0, help="pfa_mesh_desc.flags (1 = keep the caller's element order)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -211,29 +214,35 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        # the interface rows go point-to-point to the neighbouring slab: let NCCL use more channels
+        # than its 1-2 default for send/recv over NVSwitch
+        os.environ.setdefault("NCCL_MIN_P2P_NCHANNELS", "16")
+        os.environ.setdefault("NCCL_MAX_P2P_NCHANNELS", "32")
         dist.init_process_group("nccl", device_id=dev)
 
     mesh, x_host, t = build_workload(args.n, args.p)
     lam, mu = lame_from_E_nu(E_MOD, NU)
-    part = pdist.partition_elements(mesh, rank, world)
+    # cuts on whole layers of cells (6 n^2 tets): the interface stays one node plane thick
+    part = pdist.partition_elements(mesh, rank, world, align=1 if args.no_align else 6 * args.n * args.n)
     h = capi.Handle("NeoHookean", part.conn, part.n_bases, t["weights"], t["grad"], vertices=part.vertices,
                     lam=lam, mu=mu, device=local_rank, n_ghost_elements=part.n_ghost_elements, flags=args.flags,
                     n_first_elements=part.n_interface_elements)
     h.set_stream(torch.cuda.current_stream().cuda_stream)
-    exch = pdist.InterfaceExchange(h, part, rank, world, dev) if world > 1 else None
+    exch = pdist.InterfaceExchange(h, part, rank, world, dev, grad_offset=h.nnz) if world > 1 else None
 
     x_loc = np.ascontiguousarray(x_host.reshape(-1, 3)[part.l2g].reshape(-1))
     xd = torch.from_numpy(x_loc).to(dev)
     e_d = torch.zeros(1, dtype=torch.float64, device=dev)
-    g_d = torch.zeros(h.ndof, dtype=torch.float64, device=dev)
-    v_d = torch.zeros(h.nnz, dtype=torch.float64, device=dev)
+    # values[] and the gradient share one allocation so that the interface exchange packs both at once
+    vg_d = torch.zeros(h.nnz + h.ndof, dtype=torch.float64, device=dev)
+    v_d, g_d = vg_d[:h.nnz], vg_d[h.nnz:]
 
     def step():
         if exch is None:
             h.grad_hess_raw(xd, e_d, g_d, v_d)
-        elif args.no_overlap:
+        elif not args.overlap:
             h.grad_hess_raw(xd, e_d, g_d, v_d)
-            exch.reduce(e_d, g_d, v_d)
+            exch.reduce_combined(e_d, vg_d)
         else:
             # interface elements first; their partial sums travel to the owners on a side stream
             # while the remaining elements are assembled
@@ -247,11 +256,10 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    # multi-GPU steps are a dozen short launches (memset, two kernels, pack, NCCL send/recv, unpack,
-    # all-reduce): host-bound when issued one by one, so the step is captured once in a CUDA graph
-    # and replayed (bench.py --no-graph: eager)
+    # experimental (--graph): capture the dozen short launches of a multi-GPU step (memset, kernels,
+    # pack, NCCL send/recv, unpack, all-reduce) once in a CUDA graph and replay it
     graph = None
-    if world > 1 and not args.no_graph:
+    if world > 1 and args.graph:
         eager_step = step
         try:
             cap = torch.cuda.Stream(device=dev)
@@ -391,7 +399,7 @@ def main():
                        "material": "E=1e5 nu=0.3", "displacement": "0.05*h*U(-1,1) seed 42",
                        "l2": "outputs (values[] %.2f GB per GPU) exceed the 126 MB L2, no flush needed" % (8 * h.nnz / 1e9),
                        "parallelism": (f"element partition x{world}, interface exchange "
-                                       + ("after" if args.no_overlap else "under") + " the assembly, "
+                                       + ("under" if args.overlap else "after") + " the assembly, "
                                        + ("step replayed from a CUDA graph" if graph is not None else "eager launches")) if world > 1 else "single GPU",
                        "nnz": int(h.nnz) if world == 1 else None},
             "nnz_per_s": (h.nnz / (ms_step * 1e-3)) if world == 1 else None,

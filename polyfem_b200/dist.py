@@ -37,17 +37,22 @@ class Partition:
     n_interface_elements: int = 0  # leading own elements that touch a node owned by another rank
 
 
-def element_ranges(n_elements: int, world: int):
-    return [(n_elements * r) // world for r in range(world + 1)]
+def element_ranges(n_elements: int, world: int, align: int = 1):
+    """Contiguous element blocks; with align > 1 the cuts fall on multiples of `align` elements
+    (one layer of cells of a structured mesh), which keeps the interface one node plane thick."""
+    if align <= 1 or n_elements % align != 0 or n_elements // align < world:
+        return [(n_elements * r) // world for r in range(world + 1)]
+    layers = n_elements // align
+    return [((layers * r) // world) * align for r in range(world + 1)]
 
 
-def partition_elements(mesh: TetMesh, rank: int, world: int) -> Partition:
+def partition_elements(mesh: TetMesh, rank: int, world: int, align: int = 1) -> Partition:
     ne = mesh.n_elements
     if world == 1:
         return Partition(0, 1, mesh.conn, ne, 0, mesh.vertices, mesh.n_bases,
                          np.arange(mesh.n_bases, dtype=np.int64), np.zeros(mesh.n_bases, dtype=np.int32),
                          np.arange(ne, dtype=np.int64))
-    bounds = element_ranges(ne, world)
+    bounds = element_ranges(ne, world, align)
     elem_rank = np.searchsorted(np.asarray(bounds[1:]), np.arange(ne), side="right").astype(np.int32)
     node_owner = np.full(mesh.n_bases, world, dtype=np.int32)
     np.minimum.at(node_owner, mesh.conn.reshape(-1), np.repeat(elem_rank, mesh.n_loc))
@@ -95,7 +100,9 @@ class InterfaceExchange:
     """Moves partial sums of non-owned columns / dofs to their owners and adds them in."""
 
     def __init__(self, handle, part: Partition, rank: int, world: int, device, size: int = 3,
-                 block_pattern=None):
+                 block_pattern=None, grad_offset=None):
+        """grad_offset: when values[] and the gradient live in ONE tensor (gradient starting at this
+        element offset), reduce_combined() packs / adds both with a single gather / index_add."""
         import torch
         import torch.distributed as dist
         self.torch, self.dist = torch, dist
@@ -168,6 +175,12 @@ class InterfaceExchange:
         self.peers_recv = sorted(self.recv_vidx)
         self.recv_buf = {s: torch.empty(self.recv_vidx[s].numel() + self.recv_gidx[s].numel(), dtype=torch.float64, device=device)
                          for s in self.peers_recv}
+        self.send_idx, self.recv_idx = {}, {}
+        if grad_offset is not None:
+            for s in self.peers_send:
+                self.send_idx[s] = torch.cat([self.send_vidx[s], self.send_gidx[s] + int(grad_offset)])
+            for s in self.peers_recv:
+                self.recv_idx[s] = torch.cat([self.recv_vidx[s], self.recv_gidx[s] + int(grad_offset)])
         self.interface_bytes = 8 * sum(self.send_vidx[s].numel() + self.send_gidx[s].numel() for s in self.peers_send)
 
     def _post(self, grad, values):
@@ -195,6 +208,25 @@ class InterfaceExchange:
         if energy is not None:
             self.dist.all_reduce(energy)
         self._add_received(reqs, grad, values)
+
+    def reduce_combined(self, energy, vg):
+        """reduce() for values and gradient stored in one tensor `vg` (see grad_offset): one gather,
+        one grouped send/recv, one index_add per peer."""
+        dist = self.dist
+        ops, self._send_bufs = [], []
+        for s in self.peers_recv:
+            ops.append(dist.P2POp(dist.irecv, self.recv_buf[s], s))
+        for s in self.peers_send:
+            buf = vg[self.send_idx[s]]
+            self._send_bufs.append(buf)
+            ops.append(dist.P2POp(dist.isend, buf, s))
+        reqs = dist.batch_isend_irecv(ops) if ops else []
+        if energy is not None:
+            dist.all_reduce(energy)
+        for r in reqs:
+            r.wait()
+        for s in self.peers_recv:
+            vg.index_add_(0, self.recv_idx[s], self.recv_buf[s])
 
     # ---- overlapped form (CUDA): start() after the interface elements, finish() after the rest ----
     def start(self, grad, values):

@@ -13,7 +13,7 @@ import torch.multiprocessing as mp
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _worker(rank, world, port, n, p, out_dir):
+def _worker(rank, world, port, n, p, out_dir, combined=False):
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     os.environ["MASTER_ADDR"] = "127.0.0.1"
@@ -26,7 +26,7 @@ def _worker(rank, world, port, n, p, out_dir):
         x = M.random_displacement(mesh)
         t = tables.reference_tables(p)
         lam, mu = M.lame_from_E_nu(1e5, 0.3)
-        part = pdist.partition_elements(mesh, rank, world)
+        part = pdist.partition_elements(mesh, rank, world, align=6 * n * n if combined else 1)
         adj_off, adj = pdist.block_pattern_numpy(part.conn, part.n_bases)
         nb = part.n_bases
         # local assembly of own elements with the oracle, in local numbering
@@ -51,23 +51,29 @@ def _worker(rank, world, port, n, p, out_dir):
             lst = adj[adj_off[b]:adj_off[b + 1]]
             k = np.searchsorted(lst, rows // 3)
             values[outer_w[col] + 3 * k + rows % 3] = H.values[H.outer[col]:H.outer[col + 1]]
-        ex = pdist.InterfaceExchange(None, part, rank, world, torch.device("cpu"), block_pattern=(adj_off, adj))
         e_t = torch.tensor([e_loc], dtype=torch.float64)
         g_t = torch.from_numpy(g_loc.copy())
         v_t = torch.from_numpy(values)
-        ex.reduce(e_t, g_t, v_t)
+        if combined:  # values and gradient in one tensor, cuts on whole cell layers (bench.py's multi-GPU path)
+            vg = torch.cat([v_t, g_t])
+            ex = pdist.InterfaceExchange(None, part, rank, world, torch.device("cpu"), block_pattern=(adj_off, adj), grad_offset=nnz)
+            ex.reduce_combined(e_t, vg)
+            v_t, g_t = vg[:nnz].clone(), vg[nnz:].clone()
+        else:
+            ex = pdist.InterfaceExchange(None, part, rank, world, torch.device("cpu"), block_pattern=(adj_off, adj))
+            ex.reduce(e_t, g_t, v_t)
         np.savez(os.path.join(out_dir, f"rank{rank}.npz"), e=e_t.numpy(), g=g_t.numpy(), v=v_t.numpy(), adj_off=adj_off, adj=adj,
                  l2g=part.l2g, owner=part.owner, n_own=part.n_own_elements, n_ghost=part.n_ghost_elements)
     finally:
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world", [2, 3])
-def test_partition_exchange_matches_single_process(tmp_path, oracle, world):
+@pytest.mark.parametrize("world,combined", [(2, False), (3, False), (2, True)])
+def test_partition_exchange_matches_single_process(tmp_path, oracle, world, combined):
     from polyfem_b200 import mesh as M
     n, p = 3, 2
-    port = 29650 + world
-    mp.spawn(_worker, args=(world, port, n, p, str(tmp_path)), nprocs=world, join=True)
+    port = 29650 + world + (10 if combined else 0)
+    mp.spawn(_worker, args=(world, port, n, p, str(tmp_path), combined), nprocs=world, join=True)
     mesh = M.kuhn_cube(n, p, jitter=0.1)
     x = M.random_displacement(mesh)
     ref = oracle.problem_from_mesh(mesh, "NeoHookean")
