@@ -216,6 +216,8 @@ def main():
     if world > 1:
         # the interface rows go point-to-point to the neighbouring slab: let NCCL use more channels
         # than its 1-2 default for send/recv over NVSwitch
+        if args.overlap:
+            os.environ.setdefault("TORCH_NCCL_HIGH_PRIORITY", "1")  # NCCL's stream ahead of the assembly kernel's pending CTAs
         os.environ.setdefault("NCCL_MIN_P2P_NCHANNELS", "16")
         os.environ.setdefault("NCCL_MAX_P2P_NCHANNELS", "32")
         dist.init_process_group("nccl", device_id=dev)
@@ -270,7 +272,7 @@ def main():
             cap.synchronize()
             dist.barrier()
             graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph, stream=cap):
+            with torch.cuda.graph(graph, stream=cap, capture_error_mode="thread_local"):  # NCCL's watchdog thread also calls CUDA
                 eager_step()
             step = graph.replay
         except Exception as ex:  # capture not possible on this stack: measure the eager path and say so
@@ -408,6 +410,15 @@ def main():
         }
         print(json.dumps(line))
     if world > 1:
+        if graph is not None:
+            # tearing the NCCL communicator down while a captured graph still references its kernels
+            # hangs on this stack: release the graph, finish all GPU work and leave without the teardown
+            graph = None
+            step = None
+            torch.cuda.synchronize()
+            sys.stdout.flush()
+            sys.stderr.flush()
+            os._exit(0)
         dist.destroy_process_group()
     return 0
 

@@ -24,6 +24,7 @@ def main():
     ap.add_argument("--cells", dest="n", type=int, default=6)
     ap.add_argument("--order", dest="p", type=int, default=2)
     ap.add_argument("--no-overlap", action="store_true")
+    ap.add_argument("--bench-path", action="store_true", help="bench.py's default multi-GPU step: cuts on cell layers, one-tensor exchange after the assembly")
     ap.add_argument("--graph", action="store_true", help="capture the step in a CUDA graph and replay it")
     a = ap.parse_args()
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ.get("LOCAL_RANK", "0"))
@@ -34,17 +35,20 @@ def main():
     x = M.random_displacement(mesh)
     t = tables.reference_tables(a.p)
     lam, mu = M.lame_from_E_nu(1e5, 0.3)
-    part = pdist.partition_elements(mesh, rank, world)
+    part = pdist.partition_elements(mesh, rank, world, align=6 * a.n * a.n if a.bench_path else 1)
     h = capi.Handle("NeoHookean", part.conn, part.n_bases, t["weights"], t["grad"], vertices=part.vertices, lam=lam, mu=mu,
                     device=local, n_ghost_elements=part.n_ghost_elements, n_first_elements=part.n_interface_elements)
     h.set_stream(torch.cuda.current_stream().cuda_stream)
-    ex = pdist.InterfaceExchange(h, part, rank, world, dev)
+    ex = pdist.InterfaceExchange(h, part, rank, world, dev, grad_offset=h.nnz)
     xd = torch.from_numpy(np.ascontiguousarray(x.reshape(-1, 3)[part.l2g].reshape(-1))).to(dev)
     e = torch.zeros(1, dtype=torch.float64, device=dev)
-    g = torch.zeros(h.ndof, dtype=torch.float64, device=dev)
-    v = torch.zeros(h.nnz, dtype=torch.float64, device=dev)
+    vg = torch.zeros(h.nnz + h.ndof, dtype=torch.float64, device=dev)
+    v, g = vg[:h.nnz], vg[h.nnz:]
     def step():
-        if a.no_overlap:
+        if a.bench_path:
+            h.grad_hess_raw(xd, e, g, v)
+            ex.reduce_combined(e, vg)
+        elif a.no_overlap:
             h.grad_hess_raw(xd, e, g, v)
             ex.reduce(e, g, v)
         else:
@@ -62,7 +66,7 @@ def main():
         cap.synchronize()
         dist.barrier()
         graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph, stream=cap):
+        with torch.cuda.graph(graph, stream=cap, capture_error_mode="thread_local"):  # NCCL's watchdog thread also calls CUDA
             step()
         e.fill_(7.0)
         g.fill_(7.0)
@@ -102,8 +106,13 @@ def main():
           flush=True)
     flag = torch.tensor([0 if ok else 1], device=dev)
     dist.all_reduce(flag)
+    rc = 1 if int(flag.item()) else 0
+    if a.graph:  # communicator teardown hangs while a captured graph references its kernels
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        os._exit(rc)
     dist.destroy_process_group()
-    sys.exit(1 if int(flag.item()) else 0)
+    sys.exit(rc)
 
 
 if __name__ == "__main__":
