@@ -98,7 +98,7 @@ class Assembler:
         self.size_ = size
 
     def is_linear(self) -> bool:
-        return self._material in ("LinearElasticity", "Laplacian")
+        return self._material in ("LinearElasticity", "Laplacian", "Mass")
 
     def add_multimaterial(self, index: int, params: dict):
         """JSON material spec (MatParams.cpp:403-446): E|young + nu, or lambda + mu."""
@@ -196,6 +196,41 @@ class LinearAssembler(Assembler):
         return self._as_matrix(h, values, None)
 
 
+class Mass(LinearAssembler):
+    """assembler/Mass.{hpp,cpp}: rho * phi_i * phi_j on the block diagonal, assembled with the mass
+    quadrature (`AssemblyValsCache(p, is_mass_=True)`, AssemblerUtils.cpp:204-211); the matrix of
+    InertiaForm. JSON parameter: "rho" (Mass::add_multimaterial, Mass.cpp:33-38)."""
+    _material = "Mass"
+
+    def add_multimaterial(self, index: int, params: dict):
+        if "rho" not in params:
+            log_and_throw_error("Mass needs rho")
+        self._materials[int(params.get("id", index))] = float(params["rho"])
+        self._materials.setdefault("default", float(params["rho"]))
+
+    def _density(self, bases: FESpace):
+        if not self._materials:
+            log_and_throw_error("Mass: no density set")
+        if bases.body_ids is None:
+            return np.full(len(bases), self._materials["default"])
+        return np.array([self._materials.get(int(b), self._materials["default"]) for b in bases.body_ids])
+
+    def _get_handle(self, n_basis, bases, gbases, cache):
+        key = (id(bases), id(cache), n_basis)
+        if self._handle is not None and self._handle_key == key:
+            return self._handle
+        if not cache.is_mass():
+            log_and_throw_error("Mass::assemble needs the mass quadrature (AssemblyValsCache with is_mass)")
+        try:
+            h = capi.Handle("Mass", bases.conn, n_basis, cache.t["weights"], None, vertices=gbases.vertices,
+                            ref_vals=cache.t["val"], density=self._density(bases), device=self.device)
+        except capi.PfaError as ex:
+            log_and_throw_error(str(ex))
+        self.invalidate()
+        self._handle, self._handle_key = h, key
+        return h
+
+
 class NLAssembler(Assembler):
     """Assembler.hpp:236-300, NLAssembler::assemble_* (Assembler.cpp:495-771)."""
 
@@ -262,8 +297,8 @@ class Laplacian(LinearAssembler):
 
 
 def make_assembler(formulation: str, device: int = 0) -> Assembler:
-    """AssemblerUtils::make_assembler (AssemblerUtils.cpp:55-122) for the three hot-path names."""
-    table = {"NeoHookean": NeoHookeanElasticity, "LinearElasticity": LinearElasticity, "Laplacian": Laplacian}
+    """AssemblerUtils::make_assembler (AssemblerUtils.cpp:55-122) for the hot-path names."""
+    table = {"NeoHookean": NeoHookeanElasticity, "LinearElasticity": LinearElasticity, "Laplacian": Laplacian, "Mass": Mass}
     if formulation not in table:
         log_and_throw_error(f"Unsupported assembler on the B200 path: {formulation}")
     return table[formulation](device)

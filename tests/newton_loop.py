@@ -45,3 +45,37 @@ def newton_solve(assemble, x0, free, max_it=30, rel_grad_tol=1e-8, c1=1e-4, max_
         x = xt
         hist.append((gn, alpha, halvings))
     return x, hist
+
+
+def newton_solve_reduced(assemble_reduced, probe, x0, free, max_it=30, rel_grad_tol=1e-8, c1=1e-4, max_ls=30):
+    """The same loop on the Dirichlet-reduced system, the way NLProblem drives its forms
+    (solver/NLProblem.cpp:565-640): assemble_reduced(x_full) -> (energy, reduced gradient, reduced
+    csc Hessian) is NLProblem::value/gradient/hessian after BCLagrangianForm::project_*;
+    probe(x_full) -> (is_step_valid, energy) is the line-search trial (is_step_valid + value).
+    `free` = not_constraints_ (sorted). Returns (x, history) like newton_solve."""
+    x = x0.copy()
+    hist = []
+    gn0 = None
+    for _ in range(max_it):
+        e, gf, Hff = assemble_reduced(x)
+        gn = float(np.abs(gf).max())
+        gn0 = gn if gn0 is None else gn0
+        if gn <= rel_grad_tol * gn0:
+            hist.append((gn, 0.0, 0))
+            break
+        dx = spla.spsolve(Hff.tocsc(), -gf)
+        if not np.all(np.isfinite(dx)) or float(dx @ gf) >= 0.0:
+            dx = -gf
+        slope = float(dx @ gf)
+        alpha, halvings = 1.0, 0
+        while halvings < max_ls:
+            xt = x.copy()
+            xt[free] += alpha * dx
+            ok, et = probe(xt)
+            if ok and np.isfinite(et) and et <= e + c1 * alpha * slope:
+                break
+            alpha *= 0.5
+            halvings += 1
+        x = xt
+        hist.append((gn, alpha, halvings))
+    return x, hist

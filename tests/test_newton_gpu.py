@@ -70,3 +70,42 @@ def test_newton_iteration_counts_match(oracle, p, n, stretch, linear_init):
     if stretch == 2.5:
         assert any(s[2] > 0 for s in hist_ref), "this case is meant to exercise the line search"
     assert np.abs(x_gpu - x_ref).max() <= 1e-9 * max(1.0, np.abs(x_ref).max())
+
+
+@pytest.mark.parametrize("p,n,stretch,linear_init", [CASES[1], CASES[3]])
+def test_newton_on_the_reduced_system(oracle, p, n, stretch, linear_init):
+    """The loop NLProblem runs: Dirichlet-reduced gradient / Hessian and the is_step_valid probe.
+    CPU side: oracle assembly + the oracle's BCLagrangianForm::project_* restatement;
+    GPU side: pfa_grad_hess_reduced (fused projection) + pfa_is_step_valid. Same iteration
+    counts, step sizes and solution."""
+    from newton_loop import newton_solve_reduced
+    mesh, _, t = make_case(n, p)
+    x0, free = _problem(mesh, stretch, linear_init)
+    ndof = mesh.n_bases * 3
+    constrained = np.setdiff1d(np.arange(ndof), free)
+    ref = oracle.problem_from_mesh(mesh, "NeoHookean", n_threads=2)
+    h = gpu_handle(mesh, "NeoHookean", t)
+    h.set_constrained_dofs(constrained)
+    o_r, i_r = h.reduced_pattern()
+    nred = h.ndof_reduced
+    assert nred == free.size
+
+    def asm_ref(x):
+        e, g, H = ref.assemble_energy(x), ref.assemble_gradient(x), ref.assemble_hessian(x)
+        R = oracle.project_hessian(H, constrained)
+        return e, oracle.project_gradient(g, constrained), sp.csc_matrix((R.values, R.inner, R.outer), shape=(nred, nred))
+
+    def probe_ref(x):
+        g = ref.assemble_gradient(x)  # ElasticForm::is_step_valid: gradient, then NaN check
+        return (not np.isnan(g).any()), ref.assemble_energy(x)
+
+    def asm_gpu(x):
+        e, g, v = h.grad_hess_reduced(x)
+        return e, g, sp.csc_matrix((v, i_r, o_r), shape=(nred, nred))
+
+    x_ref, hist_ref = newton_solve_reduced(asm_ref, probe_ref, x0, free)
+    x_gpu, hist_gpu = newton_solve_reduced(asm_gpu, h.is_step_valid, x0, free)
+    assert len(hist_ref) >= 3 and hist_ref[-1][1] == 0.0
+    assert len(hist_gpu) == len(hist_ref), (hist_ref, hist_gpu)
+    assert [s_[1:] for s_ in hist_gpu] == [s_[1:] for s_ in hist_ref], (hist_ref, hist_gpu)
+    assert np.abs(x_gpu - x_ref).max() <= 1e-9 * max(1.0, np.abs(x_ref).max())
