@@ -16,6 +16,7 @@
 #include <polyfem/assembler/AssemblyValsCache.hpp>
 #include <polyfem/assembler/Laplacian.hpp>
 #include <polyfem/assembler/LinearElasticity.hpp>
+#include <polyfem/assembler/Mass.hpp>
 #include <polyfem/assembler/NeoHookeanElasticity.hpp>
 #include <polyfem/basis/ElementBases.hpp>
 #include <polyfem/utils/Logger.hpp>
@@ -62,8 +63,19 @@ namespace polyfem::assembler::b200
 			const int n_loc = int(vals.basis_values.size());
 			const int n_qp = int(vals.quadrature.weights.size());
 
+			// straight meshes keep P1 geometry (VarForm.cpp:88-93, 358-366): J^-T and det are constant
+			// per element, the library computes them from the 4 vertices, stores 10 doubles per element
+			// instead of 10 per quadrature point and may re-order the elements along a space-filling curve
+			bool affine = true;
+			for (int e = 0; e < n_el && affine; ++e)
+				affine = gbases[e].bases.size() == 4;
+			std::vector<double> vertices(affine ? size_t(n_el) * 12 : 0);
+
 			std::vector<int32_t> conn(size_t(n_el) * n_loc);
-			std::vector<double> jac_it(size_t(n_el) * n_qp * 9), da(size_t(n_el) * n_qp);
+			std::vector<double> jac_it(affine ? 0 : size_t(n_el) * n_qp * 9), da(affine ? 0 : size_t(n_el) * n_qp);
+			std::vector<double> ref_vals(material == PFA_MASS ? size_t(n_qp) * n_loc : 0);
+			for (size_t k = 0; k < ref_vals.size(); ++k)
+				ref_vals[k] = vals.basis_values[k % n_loc].val(k / n_loc);
 			std::vector<double> lambda(size_t(n_el) * n_qp), mu(size_t(n_el) * n_qp);
 			std::vector<double> ref_grads(size_t(n_qp) * n_loc * 3), weights(n_qp);
 			for (int q = 0; q < n_qp; ++q)
@@ -85,13 +97,21 @@ namespace polyfem::assembler::b200
 						log_and_throw_error("B200 assembly path: non-conforming bases (Local2Global lists) are not supported");
 					conn[size_t(e) * n_loc + j] = g[0].index;
 				}
+				if (affine)
+					for (int k = 0; k < 4; ++k)
+						for (int c = 0; c < 3; ++c)
+							vertices[(size_t(e) * 4 + k) * 3 + c] = gbases[e].bases[k].global()[0].node(c);
 				for (int q = 0; q < n_qp; ++q)
 				{
-					const Eigen::Matrix3d jit = vals.jac_it[q];
-					for (int r = 0; r < 3; ++r)
-						for (int c = 0; c < 3; ++c)
-							jac_it[(size_t(e) * n_qp + q) * 9 + r * 3 + c] = jit(r, c);
-					da[size_t(e) * n_qp + q] = vals.det(q) * vals.quadrature.weights(q);
+					if (!affine)
+					{
+						const Eigen::Matrix3d jit = vals.jac_it[q];
+						for (int r = 0; r < 3; ++r)
+							for (int c = 0; c < 3; ++c)
+								jac_it[(size_t(e) * n_qp + q) * 9 + r * 3 + c] = jit(r, c);
+						da[size_t(e) * n_qp + q] = vals.det(q) * vals.quadrature.weights(q);
+					}
+					// (lambda, mu), or for PFA_MASS the density in `lambda`
 					lame(vals, q, lambda[size_t(e) * n_qp + q], mu[size_t(e) * n_qp + q]);
 				}
 			}
@@ -106,10 +126,20 @@ namespace polyfem::assembler::b200
 			d.conn = conn.data();
 			d.quad_weights = weights.data();
 			d.ref_grads = ref_grads.data();
-			d.jac_it = jac_it.data(); // general form: works for affine and isoparametric geometry
-			d.da = da.data();
+			if (affine)
+				d.vertices = vertices.data();
+			else
+			{
+				d.jac_it = jac_it.data(); // isoparametric geometry: J^-T and det*w per quadrature point
+				d.da = da.data();
+			}
 			d.lambda = lambda.data();
 			d.mu = mu.data();
+			if (material == PFA_MASS)
+			{
+				d.ref_vals = ref_vals.data();
+				d.density = lambda.data();
+			}
 			d.material_stride = n_qp;
 			d.device = 0;
 			if (pfa_create(&d, &h_) != PFA_OK)
@@ -233,6 +263,71 @@ namespace polyfem::assembler::b200
 	private:
 		DeviceAssembly dev_;
 		mutable std::vector<double> values_;
+	};
+
+	/// Drop-in for Mass ("Mass"): the matrix InertiaForm is built with (State::build_mass_matrix /
+	/// SolveData::init_forms). The caller's AssemblyValsCache must be the mass one (is_mass() quadrature).
+	class MassB200 : public Mass
+	{
+	public:
+		void assemble(const bool is_volume, const int n_basis, const std::vector<basis::ElementBases> &bases,
+					  const std::vector<basis::ElementBases> &gbases, const AssemblyValsCache &cache, const double t,
+					  StiffnessMatrix &stiffness, const bool is_mass = false) const override
+		{
+			if (size() != 3)
+				return Mass::assemble(is_volume, n_basis, bases, gbases, cache, t, stiffness, is_mass);
+			pfa_handle *h = dev_.get(PFA_MASS, is_volume, n_basis, bases, gbases, cache,
+									 [&](const ElementAssemblyValues &vals, const int q, double &rho, double &unused) {
+										 rho = density()(vals.quadrature.points.row(q), vals.val.row(q), t, vals.element_id);
+										 unused = 0;
+									 });
+			int64_t nnz;
+			pfa_sizes(h, nullptr, nullptr, &nnz);
+			values_.resize(nnz);
+			DeviceAssembly::check(h, pfa_linear_stiffness(h, values_.data()));
+			DeviceAssembly::to_eigen(h, values_, stiffness);
+		}
+
+	private:
+		DeviceAssembly dev_;
+		mutable std::vector<double> values_;
+	};
+
+	/// Optional: the Newton system of NLProblem straight from the device (fourth edit).
+	/// Replaces FullNLProblem::hessian + BCLagrangianForm::project_hessian / project_gradient
+	/// (solver/NLProblem.cpp:596-640, 735-751) for a problem whose only assembled form is the elastic one.
+	struct ReducedNewtonSystem
+	{
+		/// boundary_nodes = BCLagrangianForm::boundary_nodes_ (constrained dofs, any order)
+		static void set_constraints(pfa_handle *h, const std::vector<int> &boundary_nodes)
+		{
+			std::vector<int32_t> dofs(boundary_nodes.begin(), boundary_nodes.end());
+			DeviceAssembly::check(h, pfa_set_constrained_dofs(h, dofs.data(), int64_t(dofs.size())));
+		}
+
+		/// weight = Form::weight() / scale_ (solver/forms/Form.hpp:30-56); x is the FULL vector
+		static double assemble(pfa_handle *h, const Eigen::VectorXd &x_full, const bool project_to_psd, const double weight,
+							   Eigen::VectorXd &grad_reduced, StiffnessMatrix &hessian_reduced, std::vector<double> &values)
+		{
+			int64_t ndof_r, nnz_r;
+			DeviceAssembly::check(h, pfa_reduced_sizes(h, &ndof_r, &nnz_r));
+			grad_reduced.resize(ndof_r);
+			values.resize(nnz_r);
+			double energy = 0;
+			DeviceAssembly::check(h, pfa_grad_hess_reduced(h, x_full.data(), project_to_psd ? 1 : 0, weight, &energy, grad_reduced.data(), values.data()));
+			const int32_t *outer, *inner;
+			DeviceAssembly::check(h, pfa_reduced_pattern(h, &outer, &inner));
+			hessian_reduced = Eigen::Map<const StiffnessMatrix>(ndof_r, ndof_r, nnz_r, outer, inner, values.data());
+			return energy;
+		}
+
+		/// ElasticForm::is_step_valid (solver/forms/ElasticForm.cpp:388-396) + the energy of the same pass
+		static bool is_step_valid(pfa_handle *h, const Eigen::VectorXd &x1, double &energy)
+		{
+			int32_t valid = 0;
+			DeviceAssembly::check(h, pfa_is_step_valid(h, x1.data(), &valid, &energy));
+			return valid != 0;
+		}
 	};
 
 	/// Drop-in for LinearElasticity ("LinearElasticity"): linear `assemble` plus the NL
