@@ -535,6 +535,13 @@ extern "C"
 		}
 		if (is_mass)
 			UP(m.ref_vals, d->ref_vals, nq * nl, double);
+		if ((m.material == PFA_LAPLACIAN || m.material == PFA_LINEAR_ELASTICITY) && affine && m.mat_stride == 1)
+		{
+			std::vector<double> mom;
+			reference_moments(d->ref_grads, d->quad_weights, m.n_loc, m.n_qp, mom);
+			UP(m.ref_moments, mom.data(), mom.size(), double);
+			PFA_CUDA(h, cudaStreamSynchronize(h->stream)); // mom is a local
+		}
 		UP(m.qweights, d->quad_weights, nq, double);
 		UP(m.adj_off, hp.adj_off.data(), hp.adj_off.size(), int32_t);
 		UP(m.adj, hp.adj.data(), hp.adj.size(), int32_t);

@@ -26,6 +26,9 @@ namespace pfa
 		const double *lambda = nullptr;    // [n_el][mat_stride]
 		const double *mu = nullptr;        // [n_el][mat_stride]
 		const double *ref_vals = nullptr;  // [n_qp][n_loc] basis values (PFA_MASS)
+		// [9][n_loc][n_loc] reference moment matrices S^{cd}_{ij} = sum_q w_q ghat_i[c](q) ghat_j[d](q) (linear
+		// assemblers on affine elements, assemble_affine_linear_kernel)
+		const double *ref_moments = nullptr;
 		const double *ref_grads = nullptr; // [n_qp][n_loc][3]
 		const double *qweights = nullptr;  // [n_qp]
 		const double *ref_grads_host = nullptr; // host copy of ref_grads (owned by the handle): source of the __constant__ table
@@ -86,6 +89,9 @@ namespace pfa
 	bool rowlane_applies(int material, int n_loc, int n_qp);
 	// exact structural zeros / equal components of the P2 tet basis gradients in a [n_qp][10][3] table
 	bool p2_table_structured(const double *ref_grads, int n_loc, int n_qp);
+	bool affine_linear_applies(const DeviceMesh &m);
+	// S^{cd}_{ij} = sum_q w_q ghat_i[c](q) ghat_j[d](q), layout [c*3+d][i][j]
+	void reference_moments(const double *ref_grads, const double *weights, int n_loc, int n_qp, std::vector<double> &out);
 	// elements per warp batch of the row-lane kernel for this element type
 	int rowlane_batch_elements(int n_loc, int n_qp);
 #ifndef PFA_ZERO_LOOKAHEAD

@@ -16,6 +16,7 @@
 #include <cstdio>
 #include <cstring>
 #include <mutex>
+#include <vector>
 
 #ifndef PFA_RL_UNROLL_Q
 #define PFA_RL_UNROLL_Q 1 // qp loop of phase 2: 1 keeps register pressure low (c_refgrad is read with LDC)
@@ -30,6 +31,9 @@
 // the scatter, or scatter with plain stores
 #ifndef PFA_RL_DENSE_COLUMNS // 1: never use the structured (P2S) column loop
 #define PFA_RL_DENSE_COLUMNS 0
+#endif
+#ifndef PFA_NO_AFFINE_LINEAR // 1: never use the reference-moment kernel for linear stiffness on affine elements
+#define PFA_NO_AFFINE_LINEAR 0
 #endif
 #ifndef PFA_NO_LAPLACIAN_TILE // 1: Laplacian always through the generic kernel
 #define PFA_NO_LAPLACIAN_TILE 0
@@ -1601,6 +1605,136 @@ namespace pfa
 			return cudaGetLastError();
 		}
 
+		// ------------------------------------------------------------------------------------
+		// Linear stiffness on AFFINE elements with per-element constant coefficients (Laplacian.cpp:13-26,
+		// LinearElasticity.cpp:30-63 through LinearAssembler::assemble): the quadrature sum factors out
+		// of the element loop. With g_i = ghat_i J^-T,
+		//     sum_q w_q g_i[a] g_j[b] = (J^-T^T S_ij J^-T)[a][b],   S_ij[c][d] = sum_q w_q ghat_i[c](q) ghat_j[d](q),
+		// and the nine NL x NL reference moment matrices S^{cd} do not depend on the element: they are
+		// built once per handle (DeviceMesh::ref_moments) and live in shared memory. Per node pair the
+		// element then costs 9 (Laplacian) or ~70 (elasticity) DFMAs instead of n_qp times that
+		// (P4: 23 quadrature points) - the kernel is bound by the scatter, not by the FP64 pipe.
+		// One warp per element, lanes over the NL^2 node pairs.
+		// ------------------------------------------------------------------------------------
+		template <int MAT, int WARPS>
+		__global__ void __launch_bounds__(WARPS * 32) assemble_affine_linear_kernel(const DeviceMesh m, const AssembleArgs a)
+		{
+			extern __shared__ double smem[];
+			const int NL = m.n_loc, NP = NL * NL;
+			const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+			double *sS = smem; // [9][NP]
+			for (int t = threadIdx.x; t < 9 * NP; t += WARPS * 32)
+				sS[t] = m.ref_moments[t];
+			__syncthreads();
+
+			for (int e = a.e_begin + blockIdx.x * WARPS + warp; e < a.e_end; e += gridDim.x * WARPS)
+			{
+				double J[9];
+#pragma unroll
+				for (int k = 0; k < 9; ++k)
+					J[k] = m.jit[size_t(e) * 9 + k];
+				const double det = m.detj[e]; // quadrature weights are inside the moments
+				const int32_t *slot = m.slot + size_t(e) * NP;
+				if (MAT == PFA_LAPLACIAN)
+				{
+					// M = det * J^-T J^-T^T  (D_i . D_j = ghat_i^T M ghat_j)
+					double M[9];
+#pragma unroll
+					for (int c = 0; c < 3; ++c)
+#pragma unroll
+						for (int d = 0; d < 3; ++d)
+							M[c * 3 + d] = det * (J[c * 3 + 0] * J[d * 3 + 0] + J[c * 3 + 1] * J[d * 3 + 1] + J[c * 3 + 2] * J[d * 3 + 2]);
+					for (int p = lane; p < NP; p += 32)
+					{
+						double v = 0.0;
+#pragma unroll
+						for (int k = 0; k < 9; ++k)
+							v = fma(M[k], sS[k * NP + p], v);
+						red_add(a.values + slot[p], v);
+					}
+				}
+				else
+				{
+					// lane <-> (node pair, row component aa): 10 pairs per warp pass; one RED instruction then
+					// writes, for a fixed column component b, runs of 3 consecutive doubles (aa = 0, 1, 2)
+					const double mu = m.mu[e] * det, lam = m.lambda[e] * det;
+					const int32_t *conn = m.conn + size_t(e) * NL;
+					const int aa = lane % 3, sub = lane / 3;
+					// column aa of J^-T (lane-dependent, built once per element with selects)
+					const double ja0 = aa == 0 ? J[0] : (aa == 1 ? J[1] : J[2]);
+					const double ja1 = aa == 0 ? J[3] : (aa == 1 ? J[4] : J[5]);
+					const double ja2 = aa == 0 ? J[6] : (aa == 1 ? J[7] : J[8]);
+					// M = J^-T J^-T^T for the trace: tr P = sum_cd S[c][d] M[c][d]
+					double M[9];
+#pragma unroll
+					for (int c = 0; c < 3; ++c)
+#pragma unroll
+						for (int d = 0; d < 3; ++d)
+							M[c * 3 + d] = J[c * 3 + 0] * J[d * 3 + 0] + J[c * 3 + 1] * J[d * 3 + 1] + J[c * 3 + 2] * J[d * 3 + 2];
+					for (int p0 = 0; p0 < NP; p0 += 10)
+					{
+						const int p = p0 + sub;
+						if (lane >= 30 || p >= NP)
+							continue;
+						const int i = p / NL, j = p - i * NL;
+						(void)i;
+						double S[9];
+#pragma unroll
+						for (int k = 0; k < 9; ++k)
+							S[k] = sS[k * NP + p];
+						// P[a][b] = sum_cd J[c][a] S[c][d] J[d][b] = sum_q w g_i[a] g_j[b]
+						// row aa of P:    U[d] = sum_c J[c][aa] S[c][d],   P[aa][b] = sum_d U[d] J[d][b]
+						const double u0 = ja0 * S[0] + ja1 * S[3] + ja2 * S[6];
+						const double u1 = ja0 * S[1] + ja1 * S[4] + ja2 * S[7];
+						const double u2 = ja0 * S[2] + ja1 * S[5] + ja2 * S[8];
+						// column aa of P: V[c] = sum_d S[c][d] J[d][aa],   P[b][aa] = sum_c J[c][b] V[c]
+						const double v0 = S[0] * ja0 + S[1] * ja1 + S[2] * ja2;
+						const double v1 = S[3] * ja0 + S[4] * ja1 + S[5] * ja2;
+						const double v2 = S[6] * ja0 + S[7] * ja1 + S[8] * ja2;
+						double tr = 0.0;
+#pragma unroll
+						for (int k = 0; k < 9; ++k)
+							tr = fma(S[k], M[k], tr);
+						tr *= mu;
+						const int gj = conn[j];
+						const int off = m.adj_off[gj], deg = m.adj_off[gj + 1] - off;
+						double *dst = a.values + (size_t(off) * 9 + size_t(slot[p] - off) * 3 + aa);
+						// K[(i,aa),(j,b)] = mu P[b][aa] + lambda P[aa][b] + mu tr(P) delta  (LinearElasticity.cpp:40-60)
+#pragma unroll
+						for (int b = 0; b < 3; ++b)
+						{
+							const double row = u0 * J[0 * 3 + b] + u1 * J[1 * 3 + b] + u2 * J[2 * 3 + b]; // P[aa][b]
+							const double col = J[0 * 3 + b] * v0 + J[1 * 3 + b] * v1 + J[2 * 3 + b] * v2; // P[b][aa]
+							red_add(dst + size_t(b) * 3 * deg, mu * col + lam * row + (aa == b ? tr : 0.0));
+						}
+					}
+				}
+			}
+		}
+
+		template <int MAT>
+		cudaError_t launch_affine_linear(const DeviceMesh &m, const AssembleArgs &a, int sm_count, cudaStream_t st)
+		{
+			constexpr int WARPS = MAT == PFA_LAPLACIAN ? 16 : 8; // elasticity needs more than 64 registers per thread
+			const size_t smem = sizeof(double) * 9 * size_t(m.n_loc) * m.n_loc;
+			if (smem > 200 * 1024)
+				return cudaErrorInvalidConfiguration;
+			auto kern = assemble_affine_linear_kernel<MAT, WARPS>;
+			cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+			if (err != cudaSuccess)
+				return err;
+			int per_sm = 1;
+			err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, WARPS * 32, smem);
+			if (err != cudaSuccess)
+				return err;
+			if (per_sm < 1)
+				per_sm = 1;
+			const int64_t need = (int64_t(m.n_el) + WARPS - 1) / WARPS;
+			const int grid = int(std::max<int64_t>(1, std::min<int64_t>(need, int64_t(sm_count) * per_sm)));
+			kern<<<grid, WARPS * 32, smem, st>>>(m, a);
+			return cudaGetLastError();
+		}
+
 		constexpr size_t kMaxSmem = 227 * 1024;
 
 		size_t generic_smem_bytes(int n_loc, int n_qp, int warps)
@@ -1656,6 +1790,28 @@ namespace pfa
 			}
 		}
 	} // namespace
+
+	// affine geometry, one (lambda, mu) per element, reference moments present
+	bool affine_linear_applies(const DeviceMesh &m)
+	{
+		return !PFA_NO_AFFINE_LINEAR && m.geom_per_qp == 0 && m.mat_stride == 1 && m.ref_moments != nullptr && m.slot != nullptr;
+	}
+
+	void reference_moments(const double *ref_grads, const double *weights, int n_loc, int n_qp, std::vector<double> &out)
+	{
+		const size_t np = size_t(n_loc) * n_loc;
+		out.assign(9 * np, 0.0);
+		for (int c = 0; c < 3; ++c)
+			for (int d = 0; d < 3; ++d)
+				for (int i = 0; i < n_loc; ++i)
+					for (int j = 0; j < n_loc; ++j)
+					{
+						double s = 0.0;
+						for (int q = 0; q < n_qp; ++q)
+							s += weights[q] * (ref_grads[(size_t(q) * n_loc + i) * 3 + c] * ref_grads[(size_t(q) * n_loc + j) * 3 + d]);
+						out[size_t(c * 3 + d) * np + size_t(i) * n_loc + j] = s;
+					}
+	}
 
 	bool p2_table_structured(const double *g, int n_loc, int n_qp)
 	{
@@ -1749,6 +1905,16 @@ namespace pfa
 			}
 			return launch_generic<PFA_NEOHOOKEAN, false>(m, a, sm_count, st);
 		case PFA_LINEAR_ELASTICITY:
+			if (linear && affine_linear_applies(m) && a.values != nullptr)
+			{
+				cudaError_t err = launch_affine_linear<PFA_LINEAR_ELASTICITY>(m, a, sm_count, st);
+				if (err != cudaErrorInvalidConfiguration)
+				{
+					if (kernel_name)
+						*kernel_name = "assemble_affine_linear_kernel";
+					return err;
+				}
+			}
 			return linear ? launch_generic<PFA_LINEAR_ELASTICITY, true>(m, a, sm_count, st)
 						  : launch_generic<PFA_LINEAR_ELASTICITY, false>(m, a, sm_count, st);
 		case PFA_MASS:
@@ -1770,6 +1936,16 @@ namespace pfa
 				return cudaErrorNotSupported;
 			}
 		case PFA_LAPLACIAN:
+			if (affine_linear_applies(m) && a.values != nullptr)
+			{
+				cudaError_t err = launch_affine_linear<PFA_LAPLACIAN>(m, a, sm_count, st);
+				if (err != cudaErrorInvalidConfiguration)
+				{
+					if (kernel_name)
+						*kernel_name = "assemble_affine_linear_kernel";
+					return err;
+				}
+			}
 			if (a.values != nullptr && !PFA_NO_LAPLACIAN_TILE)
 			{
 				cudaError_t err = cudaErrorInvalidConfiguration;
