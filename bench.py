@@ -320,10 +320,37 @@ def main():
         recs = h.profile_read()
         h.profile_enable(False)
         launches = (h.launch_count() - l0) // prof_steps * args.steps
+    per_rank = None
     if world > 1:
         tt = torch.tensor([ms_total], dtype=torch.float64, device=dev)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         ms_total = float(tt.item())
+        # where a multi-GPU step goes, rank by rank (outside the timed region): assembly launches vs the
+        # interface exchange, each bracketed by CUDA events on the launching stream, 5 plain steps
+        try:
+            if graph is None and not args.overlap:
+                ka, kb, kc = [], [], []
+                for _ in range(5):
+                    e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+                    e0.record()
+                    h.grad_hess_raw(xd, e_d, g_d, v_d)
+                    e1.record()
+                    exch.reduce_combined(e_d, vg_d)
+                    e2.record()
+                    ka.append((e0, e1))
+                    kb.append((e1, e2))
+                torch.cuda.synchronize()
+                mine = torch.tensor([np.median([a.elapsed_time(b) for a, b in ka]), np.median([a.elapsed_time(b) for a, b in kb]),
+                                     float(h.n_elements), float(part.n_interface_elements), float(h.nnz)], dtype=torch.float64, device=dev)
+                allr = [torch.zeros_like(mine) for _ in range(world)]
+                dist.all_gather(allr, mine)
+                per_rank = {"assembly_ms": [round(float(t[0]), 4) for t in allr], "exchange_ms": [round(float(t[1]), 4) for t in allr],
+                            "elements": [int(t[2]) for t in allr], "interface_elements": [int(t[3]) for t in allr],
+                            "nnz": [int(t[4]) for t in allr],
+                            "note": "exchange_ms includes waiting for the neighbours and the energy all-reduce"}
+        except Exception as ex:  # diagnostics must never cost the bench line
+            sys.stderr.write(f"[bench] per-rank breakdown skipped on rank {rank}: {type(ex).__name__}: {ex}\n")
+            per_rank = None
     ms_step = ms_total / args.steps
     n_el_total = mesh.n_elements
     value = n_el_total / (ms_step * 1e-3)
@@ -408,6 +435,8 @@ def main():
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
             "setup_seconds": h.setup_seconds(),
         }
+        if per_rank is not None:
+            line["per_rank"] = per_rank
         print(json.dumps(line))
     if world > 1:
         if graph is not None:

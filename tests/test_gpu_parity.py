@@ -84,6 +84,32 @@ def test_linear_elasticity_stiffness_and_nl_path(oracle, p, n):
         assert_values_close(H.outer, H.inner, h.hessian(x), H.values)
 
 
+@pytest.mark.parametrize("p,n", [(1, 3), (2, 2), (3, 1)])
+def test_linear_elasticity_quadrature_kernels(oracle, p, n):
+    """The stiffness kernels that keep the quadrature loop (generic kernel): reached with per-qp
+    geometry input or per-qp materials; the affine / per-element case goes through the
+    reference-moment kernel and is covered by the test above. All must agree with the oracle."""
+    from polyfem_b200 import capi, mesh as M
+    mesh, x, t = make_case(n, p, jitter=0.2)
+    rng = np.random.default_rng(21)
+    lam = rng.uniform(4e4, 8e4, mesh.n_elements)
+    mu = rng.uniform(2e4, 5e4, mesh.n_elements)
+    K = oracle.OracleProblem("LinearElasticity", mesh.conn, mesh.vertices, mesh.n_bases, t["points"], t["weights"], t["grad"],
+                             lam=lam, mu=mu).assemble()
+    nq = t["weights"].size
+    e = mesh.vertices[:, 1:, :] - mesh.vertices[:, :1, :]
+    jit = np.linalg.inv(e).transpose(0, 2, 1)
+    jac_it = np.repeat(jit[:, None, :, :], nq, axis=1).reshape(mesh.n_elements, nq, 9)
+    da = np.linalg.det(e)[:, None] * t["weights"][None, :]
+    h_geo = capi.Handle("LinearElasticity", mesh.conn, mesh.n_bases, t["weights"], t["grad"], jac_it=jac_it, da=da, lam=lam, mu=mu)
+    assert_values_close(K.outer, K.inner, h_geo.linear_stiffness(), K.values, what="stiffness, per-qp geometry")
+    h_mat = capi.Handle("LinearElasticity", mesh.conn, mesh.n_bases, t["weights"], t["grad"], vertices=mesh.vertices,
+                        lam=np.repeat(lam, nq), mu=np.repeat(mu, nq))
+    assert_values_close(K.outer, K.inner, h_mat.linear_stiffness(), K.values, what="stiffness, per-qp materials")
+    h_aff = capi.Handle("LinearElasticity", mesh.conn, mesh.n_bases, t["weights"], t["grad"], vertices=mesh.vertices, lam=lam, mu=mu)
+    assert_values_close(K.outer, K.inner, h_aff.linear_stiffness(), K.values, what="stiffness, reference moments")
+
+
 @pytest.mark.parametrize("p,n", CASES)
 def test_laplacian_stiffness(oracle, p, n):
     mesh, x, t = make_case(n, p, jitter=0.2)
