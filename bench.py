@@ -85,6 +85,21 @@ class ClockSampler:
         except Exception:
             self.proc = None
 
+    def wait_first_sample(self, timeout=8.0):
+        """nvidia-smi's start-up (NVML initialisation over all GPUs of the box) briefly stalls CUDA work on
+        every device; a multi-GPU timed region is only tens of milliseconds long, so wait until the
+        sampler is in its steady polling loop before any step is issued."""
+        if self.proc is None:
+            return
+        t0 = time.perf_counter()
+        while time.perf_counter() - t0 < timeout:
+            try:
+                if os.path.getsize(self.path) > 0:
+                    return
+            except OSError:
+                return
+            time.sleep(0.05)
+
     def stop(self):
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
         if self.proc is None:
@@ -289,6 +304,13 @@ def main():
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+        sampler.wait_first_sample()
+    if world > 1:
+        # set-up, not warm-up: NCCL opens its point-to-point channels and the caching allocator its
+        # blocks during the first exchanges
+        for _ in range(10):
+            step()
+    barrier()
     for _ in range(args.warmup):
         step()
     barrier()
