@@ -2,7 +2,7 @@
 """How much would combining the contributions of B consecutive (Morton-ordered) P2 elements in shared
 memory save before the scatter reaches L2? (CPU only, no GPU needed.)
 
-  python tools/combine_study.py [cells per side, default 14]
+  python tools/combine_study.py [cells per side, default 14] [basis order, default 2]
 
 For clusters of B elements: contributions per unique values[] entry, distinct 32-byte sectors touched per
 element today (one RED instruction = one column component of one column node, 10 runs of 3 doubles) against
@@ -11,7 +11,8 @@ import numpy as np, sys
 sys.path.insert(0,'/root/repo')
 from polyfem_b200 import mesh as M, dist as D
 n=int(sys.argv[1]) if len(sys.argv)>1 else 14
-mesh=M.kuhn_cube(n,2)
+p=int(sys.argv[2]) if len(sys.argv)>2 else 2
+mesh=M.kuhn_cube(n,p)
 conn=mesh.conn.astype(np.int64); ne,nl=conn.shape; nb=mesh.n_bases
 adj_off,adj=D.block_pattern_numpy(mesh.conn, nb)
 deg=np.diff(adj_off)
@@ -56,8 +57,8 @@ def study(B):
                     sec_now+=s.size
         uniq=np.unique(idx_all.reshape(-1))
         sec_comb=np.unique(uniq//4).size
-        tot_contrib+=B*900; tot_unique+=uniq.size; tot_sec_now+=sec_now; tot_sec_comb+=sec_comb
+        tot_contrib+=B*9*nl*nl; tot_unique+=uniq.size; tot_sec_now+=sec_now; tot_sec_comb+=sec_comb
         smem.append(uniq.size*8)
     print(f"B={B:3d}: contributions/unique doubles = {tot_contrib/tot_unique:.2f}, sector-ops/element now {tot_sec_now/(len(smem)*B):.0f} -> combined {tot_sec_comb/(len(smem)*B):.0f} ({tot_sec_now/tot_sec_comb:.2f}x), smem for unique doubles {np.mean(smem)/1024:.0f} KB (max {np.max(smem)/1024:.0f})")
-for B in (1,2,4,6,8,12,16,24,48):
+for B in ((1,2,4,6,8,12,16,24,48) if p==2 else (1,6,12,24,48,96,192,384)):
     study(B)
