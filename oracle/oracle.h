@@ -15,6 +15,8 @@
  *     synthetic cube (closed form == autodiff 1e-12, NL Hessian == linear stiffness 1e-8,
  *     gradient/Hessian vs finite differences); numeric end-to-end values are UNPINNED.
  *   - project_to_psd (ipc-toolkit, source absent): UNPINNED, documented behaviour restated.
+ *   - Mass (assembler/Mass.cpp:5-23): pinned by closed forms (P1 local mass rho*V/20*(1+delta_ij), total mass,
+ *     stored zeros off the block diagonal; tests/test_oracle_mass.py) - the reference has no unit test for it.
  *
  * Every function cites the reference file:line it follows (paths relative to
  * /root/reference/src/polyfem/).
