@@ -38,7 +38,7 @@
 #ifndef PFA_NO_LAPLACIAN_TILE // 1: Laplacian always through the generic kernel
 #define PFA_NO_LAPLACIAN_TILE 0
 #endif
-#ifndef PFA_EXP_MODE // bit 0: no phase-1 math, bit 1: no phase-2 math, bit 2: no scatter, bit 3: plain stores
+#ifndef PFA_EXP_MODE // bit 0: no phase-1 math, bit 1: no phase-2 math, bit 2: no scatter, bit 3: plain stores, bit 4: lean scatter
 #define PFA_EXP_MODE 0
 #endif
 
@@ -864,6 +864,16 @@ namespace pfa
 									const double o0 = sc * sel(is0, acc[j][0], sel(is1, acc[j][2], acc[j][1]));
 									const double o1 = sc * sel(is0, acc[j][1], sel(is1, acc[j][0], acc[j][2]));
 									const double o2 = sc * sel(is0, acc[j][2], sel(is1, acc[j][1], acc[j][0]));
+#if PFA_EXP_MODE & 16 // timing experiment: scatter without un-rotation, masks and scale (wrong columns, same addresses)
+									{
+										const size_t cs16 = size_t(unsigned(st[j]) & 0x0fffffffu);
+										double *d16 = a.values + (size_t(ent[j]) + mm);
+										red_add(d16, acc[j][0]);
+										red_add(d16 + cs16, acc[j][1]);
+										red_add(d16 + 2 * cs16, acc[j][2]);
+										continue;
+									}
+#endif
 #if PFA_EXP_MODE & 8 // timing experiment: plain stores instead of reductions (wrong values)
 									const size_t cs = size_t(unsigned(st[j]) & 0x0fffffffu);
 									dst[0] = o0;
