@@ -201,7 +201,7 @@ def main():
     ap.add_argument("--n", type=int, default=69, help="cells per side (69 -> 1 971 054 tets, BASELINE cfg 3)")
     ap.add_argument("--p", type=int, default=2)
     ap.add_argument("--e2e-steps", type=int, default=2)
-    ap.add_argument("--cpu-sample-n", type=int, default=12)
+    ap.add_argument("--cpu-sample-n", type=int, default=20, help="cells per side of the bounded CPU sample (20 -> 48 000 P2 tets, ~10-20 s of host work)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-align", action="store_true", help="multi-GPU: cut the element range evenly instead of on whole cell layers")
     ap.add_argument("--graph", action="store_true", help="multi-GPU, experimental: capture the step in a CUDA graph and replay it "
