@@ -1,0 +1,59 @@
+"""The PolyFEM-side C++ binding (polyfem_b200/host/assembler_shim.hpp) cannot be built here
+(no Eigen, no PolyFEM), but it can be syntax- and type-checked against declaration-only
+stand-ins of the reference types it touches (tests/stubs/, signatures transcribed from the
+reference headers): every `override` must match a virtual of the base class, every pfa_* call
+must match include/pfa.h."""
+import os
+import shutil
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+TU = r"""
+#include <assembler_shim.hpp>
+using namespace polyfem;
+using namespace polyfem::assembler;
+int main()
+{
+	b200::NeoHookeanElasticityB200 nh;
+	b200::LinearElasticityB200 le;
+	b200::LaplacianB200 lap;
+	b200::MassB200 mass;
+	std::vector<basis::ElementBases> bases, gbases;
+	AssemblyValsCache cache;
+	Eigen::MatrixXd x, rhs;
+	StiffnessMatrix K;
+	utils::MatrixCache mc;
+	const Assembler &a = nh; // what ElasticForm holds (ElasticForm.hpp:107)
+	double e = a.assemble_energy(true, bases, gbases, cache, 0.0, 1.0, x, x);
+	Eigen::VectorXd epe = a.assemble_energy_per_element(true, bases, gbases, cache, 0.0, 1.0, x, x);
+	a.assemble_gradient(true, 1, bases, gbases, cache, 0.0, 1.0, x, x, rhs);
+	a.assemble_hessian(true, 1, false, bases, gbases, cache, 0.0, 1.0, x, x, mc, K);
+	static_cast<const Assembler &>(le).assemble(true, 1, bases, gbases, cache, 0.0, K);
+	static_cast<const Assembler &>(lap).assemble(true, 1, bases, gbases, cache, 0.0, K);
+	static_cast<const Assembler &>(mass).assemble(true, 1, bases, gbases, cache, 0.0, K, true);
+	pfa_handle *h = nullptr;
+	std::vector<int> bn;
+	std::vector<double> values;
+	Eigen::VectorXd xf, g;
+	b200::ReducedNewtonSystem::set_constraints(h, bn);
+	e += b200::ReducedNewtonSystem::assemble(h, xf, false, 1.0, g, K, values);
+	bool ok = b200::ReducedNewtonSystem::is_step_valid(h, xf, e);
+	return ok && epe.size() ? 0 : 1;
+}
+"""
+
+
+def test_shim_compiles_against_reference_signatures(tmp_path):
+    gxx = shutil.which("g++")
+    if gxx is None:
+        pytest.skip("g++ not available")
+    src = tmp_path / "shim_check.cpp"
+    src.write_text(TU)
+    cmd = [gxx, "-std=c++17", "-fsyntax-only", "-Wall", "-Wextra", "-Werror=overloaded-virtual",
+           "-I", os.path.join(ROOT, "include"), "-I", os.path.join(ROOT, "polyfem_b200", "host"),
+           "-I", os.path.join(ROOT, "tests", "stubs"), str(src)]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-4000:]
