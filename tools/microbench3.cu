@@ -119,8 +119,9 @@ __global__ void smem_update_kernel(double *out, int iters, int mode, int pattern
 		out[0] = sum;
 }
 
-int main()
+int main(int argc, char **argv)
 {
+	const bool quick = argc > 1; // any argument: the short list (one working set, fewer run lengths)
 	cudaDeviceProp prop;
 	CK(cudaGetDeviceProperties(&prop, 0));
 	const int sms = prop.multiProcessorCount;
@@ -134,6 +135,8 @@ int main()
 	std::vector<uint32_t> h_idx(n_threads * per_thread);
 	for (size_t ws_mb : {size_t(64), size_t(4096)})
 	{
+		if (quick && ws_mb != 64)
+			continue;
 		const size_t n_doubles = ws_mb * 1024 * 1024 / 8;
 		double *d_dst;
 		CK(cudaMalloc(&d_dst, n_doubles * sizeof(double)));
@@ -142,6 +145,8 @@ int main()
 			for (int L : {1, 3, 4, 8, 32})
 			{
 				if (aligned && (L == 1 || L == 3))
+					continue;
+				if (quick && !((L == 3 && !aligned) || (L == 4 && aligned) || (L == 32 && aligned) || (L == 1)))
 					continue;
 				// consecutive lanes of a warp form runs of L doubles; runs start at random positions inside a
 				// 2 KB window that moves with the warp (the locality of one column block)
@@ -177,6 +182,8 @@ int main()
 		for (int pattern = 0; pattern < 3; ++pattern)
 			for (int warps : {4, 8, 16})
 			{
+				if (quick && warps == 4)
+					continue;
 				const int iters = 2000;
 				const float ms = best_ms([&] { smem_update_kernel<<<sms * 2, warps * 32, n_acc * 8>>>(d_out, iters, mode, pattern, n_acc); });
 				const double upd = double(sms) * 2 * warps * 32 * iters * 8;
