@@ -1,0 +1,245 @@
+// TEST INFRASTRUCTURE: a small dense-matrix stand-in for the part of Eigen's API that the reference's
+// NeoHookean "fast" gradient / Hessian functions use (assembler/NeoHookeanElasticity.cpp:419-658), so that
+// THOSE FUNCTION BODIES can be compiled from /root/reference and executed here, where Eigen is not installed
+// (oracle/refmath/extract_nh.py + nh_glue.cpp -> oracle/_ref/libnhref.so). Every operation is eager and
+// returns a plain column-major matrix (`Dense`); fixed-size template arguments only provide default shapes.
+// This is not Eigen and shares no code with it.
+#pragma once
+#include <cassert>
+#include <cmath>
+#include <cstddef>
+#include <type_traits>
+#include <vector>
+
+namespace Eigen
+{
+	constexpr int Dynamic = -1;
+
+	class Dense
+	{
+	public:
+		Dense() = default;
+		Dense(long r, long c) : r_(int(r)), c_(int(c)), d_(size_t(r) * size_t(c), 0.0) {}
+
+		long rows() const { return r_; }
+		long cols() const { return c_; }
+		long size() const { return long(r_) * c_; }
+		double *data() { return d_.data(); }
+		const double *data() const { return d_.data(); }
+		void resize(long r, long c)
+		{
+			r_ = int(r);
+			c_ = int(c);
+			d_.assign(size_t(r) * size_t(c), 0.0);
+		}
+		void setZero() { d_.assign(d_.size(), 0.0); }
+
+		double &operator()(long i, long j) { return d_[size_t(j) * r_ + i]; }
+		double operator()(long i, long j) const { return d_[size_t(j) * r_ + i]; }
+		double &operator()(long i) { return d_[size_t(i)]; } // vectors (and column-major linear access)
+		double operator()(long i) const { return d_[size_t(i)]; }
+
+		Dense transpose() const
+		{
+			Dense t(c_, r_);
+			for (int i = 0; i < r_; ++i)
+				for (int j = 0; j < c_; ++j)
+					t(j, i) = (*this)(i, j);
+			return t;
+		}
+		double trace() const
+		{
+			double s = 0;
+			for (int i = 0; i < r_ && i < c_; ++i)
+				s += (*this)(i, i);
+			return s;
+		}
+		double determinant() const
+		{
+			const Dense &m = *this;
+			assert(r_ == c_ && r_ >= 1 && r_ <= 3);
+			if (r_ == 1)
+				return m(0, 0);
+			if (r_ == 2)
+				return m(0, 0) * m(1, 1) - m(0, 1) * m(1, 0);
+			return m(0, 0) * (m(1, 1) * m(2, 2) - m(1, 2) * m(2, 1)) - m(0, 1) * (m(1, 0) * m(2, 2) - m(1, 2) * m(2, 0))
+				   + m(0, 2) * (m(1, 0) * m(2, 1) - m(1, 1) * m(2, 0));
+		}
+		Dense &noalias() { return *this; }
+		Dense &operator+=(const Dense &o)
+		{
+			assert(r_ == o.r_ && c_ == o.c_);
+			for (size_t k = 0; k < d_.size(); ++k)
+				d_[k] += o.d_[k];
+			return *this;
+		}
+
+		// ---- writable views ----
+		struct RowProxy
+		{
+			Dense &m;
+			long i;
+			RowProxy &operator=(const Dense &v)
+			{
+				assert(v.size() == m.cols());
+				for (long j = 0; j < m.cols(); ++j)
+					m(i, j) = v(j);
+				return *this;
+			}
+			RowProxy &operator=(const RowProxy &o) { return *this = Dense(o); }
+			RowProxy &operator+=(const Dense &v)
+			{
+				assert(v.size() == m.cols());
+				for (long j = 0; j < m.cols(); ++j)
+					m(i, j) += v(j);
+				return *this;
+			}
+			operator Dense() const
+			{
+				Dense r(1, m.cols());
+				for (long j = 0; j < m.cols(); ++j)
+					r(0, j) = m(i, j);
+				return r;
+			}
+			Dense transpose() const { return Dense(*this).transpose(); }
+		};
+		struct ColProxy
+		{
+			Dense &m;
+			long j;
+			ColProxy &operator=(const Dense &v)
+			{
+				assert(v.size() == m.rows());
+				for (long i = 0; i < m.rows(); ++i)
+					m(i, j) = v(i);
+				return *this;
+			}
+			operator Dense() const
+			{
+				Dense r(m.rows(), 1);
+				for (long i = 0; i < m.rows(); ++i)
+					r(i, 0) = m(i, j);
+				return r;
+			}
+		};
+		struct BlockProxy
+		{
+			Dense &m;
+			long i0, j0, br, bc;
+			BlockProxy &operator=(const Dense &v)
+			{
+				assert(v.rows() == br && v.cols() == bc);
+				for (long i = 0; i < br; ++i)
+					for (long j = 0; j < bc; ++j)
+						m(i0 + i, j0 + j) = v(i, j);
+				return *this;
+			}
+			operator Dense() const
+			{
+				Dense r(br, bc);
+				for (long i = 0; i < br; ++i)
+					for (long j = 0; j < bc; ++j)
+						r(i, j) = m(i0 + i, j0 + j);
+				return r;
+			}
+			Dense transpose() const { return Dense(*this).transpose(); }
+		};
+		RowProxy row(long i) { return RowProxy{*this, i}; }
+		Dense row(long i) const { return Dense(RowProxy{const_cast<Dense &>(*this), i}); }
+		ColProxy col(long j) { return ColProxy{*this, j}; }
+		Dense col(long j) const { return Dense(ColProxy{const_cast<Dense &>(*this), j}); }
+		template <int BR, int BC>
+		BlockProxy block(long i, long j) { return BlockProxy{*this, i, j, BR, BC}; }
+		template <int BR, int BC>
+		Dense block(long i, long j) const { return Dense(BlockProxy{const_cast<Dense &>(*this), i, j, BR, BC}); }
+
+	protected:
+		int r_ = 0, c_ = 0;
+		std::vector<double> d_;
+	};
+
+	inline Dense operator+(const Dense &a, const Dense &b)
+	{
+		assert(a.rows() == b.rows() && a.cols() == b.cols());
+		Dense r(a.rows(), a.cols());
+		for (long k = 0; k < a.size(); ++k)
+			r(k) = a(k) + b(k);
+		return r;
+	}
+	inline Dense operator-(const Dense &a, const Dense &b)
+	{
+		assert(a.rows() == b.rows() && a.cols() == b.cols());
+		Dense r(a.rows(), a.cols());
+		for (long k = 0; k < a.size(); ++k)
+			r(k) = a(k) - b(k);
+		return r;
+	}
+	inline Dense operator-(const Dense &a)
+	{
+		Dense r(a.rows(), a.cols());
+		for (long k = 0; k < a.size(); ++k)
+			r(k) = -a(k);
+		return r;
+	}
+	inline Dense operator*(const Dense &a, const Dense &b)
+	{
+		assert(a.cols() == b.rows());
+		Dense r(a.rows(), b.cols());
+		for (long i = 0; i < a.rows(); ++i)
+			for (long j = 0; j < b.cols(); ++j)
+			{
+				double s = 0;
+				for (long k = 0; k < a.cols(); ++k)
+					s += a(i, k) * b(k, j);
+				r(i, j) = s;
+			}
+		return r;
+	}
+	inline Dense operator*(double s, const Dense &a)
+	{
+		Dense r(a.rows(), a.cols());
+		for (long k = 0; k < a.size(); ++k)
+			r(k) = s * a(k);
+		return r;
+	}
+	inline Dense operator*(const Dense &a, double s) { return s * a; }
+
+	template <typename S, int R, int C, int Opt = 0, int MR = R, int MC = C>
+	class Matrix : public Dense
+	{
+	public:
+		Matrix() : Dense(R == Dynamic ? 0 : R, C == Dynamic ? 0 : C) {}
+		template <typename I, typename J, typename = std::enable_if_t<std::is_integral_v<I> && std::is_integral_v<J>>>
+		Matrix(I r, J c) : Dense(long(r), long(c)) {}
+		template <typename I, typename = std::enable_if_t<std::is_integral_v<I>>>
+		explicit Matrix(I n) : Dense(C == 1 ? long(n) : 1, C == 1 ? 1 : long(n)) {}
+		Matrix(const Dense &o) : Dense(o) {}
+		Matrix &operator=(const Dense &o)
+		{
+			Dense::operator=(o);
+			return *this;
+		}
+		static Dense Identity(long r, long c)
+		{
+			Dense m(r, c);
+			for (long i = 0; i < r && i < c; ++i)
+				m(i, i) = 1.0;
+			return m;
+		}
+		static Dense Zero(long r, long c) { return Dense(r, c); }
+	};
+	using MatrixXd = Matrix<double, Dynamic, Dynamic>;
+	using VectorXd = Matrix<double, Dynamic, 1>;
+
+	// Map<T>(ptr, n): the reference only reads through it (a column vector of n entries)
+	template <typename T>
+	class Map : public Dense
+	{
+	public:
+		Map(const double *p, long n) : Dense(n, 1)
+		{
+			for (long k = 0; k < n; ++k)
+				(*this)(k) = p[k];
+		}
+	};
+} // namespace Eigen

@@ -1,0 +1,166 @@
+// TEST INFRASTRUCTURE: C entry points over the reference's OWN NeoHookean gradient / Hessian function bodies
+// (assembler/NeoHookeanElasticity.cpp:419-658), extracted at build time into ../_ref/nh_extracted.inc and compiled
+// verbatim against mini_eigen.hpp. Used by tools/make_golden.py to write tests/golden/nh_local.npz and by
+// tests/test_oracle_reference_math.py to pin oracle/oracle.cpp's local math against the reference itself.
+#include "mini_eigen.hpp"
+
+#include <cmath>
+#include <vector>
+
+using std::log;
+
+namespace polyfem::assembler
+{
+	// the few members of the reference types that the extracted functions touch
+	struct Local2Global // basis/Basis.hpp:21-38
+	{
+		int index;
+		double val;
+	};
+	struct AssemblyValues // assembler/AssemblyValues.hpp
+	{
+		std::vector<Local2Global> global;
+		Eigen::MatrixXd grad; // n_qp x dim reference gradients
+	};
+	struct QuadratureStub
+	{
+		Eigen::MatrixXd points;
+	};
+	struct ElementAssemblyValues // assembler/ElementAssemblyValues.hpp:12-61
+	{
+		std::vector<AssemblyValues> basis_values;
+		std::vector<Eigen::MatrixXd> jac_it;
+		QuadratureStub quadrature;
+		Eigen::MatrixXd val;
+		int element_id = 0;
+		Eigen::VectorXd eval_deformed_jacobian_determinant(const Eigen::MatrixXd &) const { return Eigen::VectorXd(); }
+	};
+	struct NonLinearAssemblerData // assembler/AssemblerData.hpp
+	{
+		const ElementAssemblyValues &vals;
+		double t;
+		double dt;
+		const Eigen::MatrixXd &x;
+		const Eigen::MatrixXd &x_prev;
+		const Eigen::VectorXd &da;
+	};
+	struct LameParameters // assembler/MatParams.hpp:83
+	{
+		double lambda = 0, mu = 0;
+		void lambda_mu(const Eigen::Dense &, const Eigen::Dense &, double, int, double &l, double &m) const
+		{
+			l = lambda;
+			m = mu;
+		}
+	};
+
+	class NeoHookeanElasticity
+	{
+	public:
+		int size() const { return 3; }
+		bool use_robust_jacobian = false;
+		LameParameters params_;
+		template <int n_basis, int dim>
+		void compute_energy_aux_gradient_fast(const NonLinearAssemblerData &data, Eigen::Matrix<double, Eigen::Dynamic, 1> &G_flattened) const;
+		template <int n_basis, int dim>
+		void compute_energy_hessian_aux_fast(const NonLinearAssemblerData &data, Eigen::MatrixXd &H) const;
+	};
+
+#include "../_ref/nh_extracted.inc"
+} // namespace polyfem::assembler
+
+using namespace polyfem::assembler;
+
+namespace
+{
+	struct Inputs
+	{
+		ElementAssemblyValues vals;
+		Eigen::MatrixXd x, x_prev;
+		Eigen::VectorXd da;
+	};
+
+	// u[n_basis][3] nodal displacements, grads[n_qp][n_basis][3], jac_it[n_qp][9] row-major, da[n_qp]
+	void fill(Inputs &in, int n_basis, int n_qp, const double *u, const double *grads, const double *jac_it, const double *da)
+	{
+		in.x.resize(long(n_basis) * 3, 1);
+		for (int k = 0; k < n_basis * 3; ++k)
+			in.x(k) = u[k];
+		in.x_prev.resize(long(n_basis) * 3, 1);
+		in.da.resize(n_qp, 1);
+		in.vals.quadrature.points.resize(n_qp, 3);
+		in.vals.val.resize(n_qp, 3);
+		in.vals.basis_values.resize(n_basis);
+		for (int i = 0; i < n_basis; ++i)
+		{
+			in.vals.basis_values[i].global = {Local2Global{i, 1.0}};
+			in.vals.basis_values[i].grad.resize(n_qp, 3);
+			for (int q = 0; q < n_qp; ++q)
+				for (int c = 0; c < 3; ++c)
+					in.vals.basis_values[i].grad(q, c) = grads[(size_t(q) * n_basis + i) * 3 + c];
+		}
+		in.vals.jac_it.resize(n_qp);
+		for (int q = 0; q < n_qp; ++q)
+		{
+			in.da(q) = da[q];
+			in.vals.jac_it[q].resize(3, 3);
+			for (int r = 0; r < 3; ++r)
+				for (int c = 0; c < 3; ++c)
+					in.vals.jac_it[q](r, c) = jac_it[size_t(q) * 9 + r * 3 + c];
+		}
+	}
+} // namespace
+
+extern "C"
+{
+	// out[n_basis*3], node-major (NeoHookeanElasticity.cpp:540-544). The instantiation follows the reference's own
+	// dispatch on the number of bases (assemble_gradient: 4, 10, 20 fixed, anything else dynamic).
+	int ref_nh_gradient(int n_basis, int n_qp, const double *u, const double *grads, const double *jac_it, const double *da, double lambda, double mu, double *out)
+	{
+		Inputs in;
+		fill(in, n_basis, n_qp, u, grads, jac_it, da);
+		NeoHookeanElasticity nh;
+		nh.params_.lambda = lambda;
+		nh.params_.mu = mu;
+		const NonLinearAssemblerData data{in.vals, 0.0, 1.0, in.x, in.x_prev, in.da};
+		Eigen::Matrix<double, Eigen::Dynamic, 1> g;
+		if (n_basis == 4)
+			nh.compute_energy_aux_gradient_fast<4, 3>(data, g);
+		else if (n_basis == 10)
+			nh.compute_energy_aux_gradient_fast<10, 3>(data, g);
+		else if (n_basis == 20)
+			nh.compute_energy_aux_gradient_fast<20, 3>(data, g);
+		else
+			nh.compute_energy_aux_gradient_fast<Eigen::Dynamic, 3>(data, g);
+		if (g.size() != long(n_basis) * 3)
+			return -1;
+		for (int k = 0; k < n_basis * 3; ++k)
+			out[k] = g(k);
+		return 0;
+	}
+
+	// out[N*N] row-major, N = n_basis*3, H(i*3+a, j*3+b) (NeoHookeanElasticity.cpp:652-656)
+	int ref_nh_hessian(int n_basis, int n_qp, const double *u, const double *grads, const double *jac_it, const double *da, double lambda, double mu, double *out)
+	{
+		Inputs in;
+		fill(in, n_basis, n_qp, u, grads, jac_it, da);
+		NeoHookeanElasticity nh;
+		nh.params_.lambda = lambda;
+		nh.params_.mu = mu;
+		const NonLinearAssemblerData data{in.vals, 0.0, 1.0, in.x, in.x_prev, in.da};
+		const long N = long(n_basis) * 3;
+		Eigen::MatrixXd H(N, N); // the caller zero-initialises it (Assembler.cpp / assemble_hessian: hessian.setZero())
+		if (n_basis == 4)
+			nh.compute_energy_hessian_aux_fast<4, 3>(data, H);
+		else if (n_basis == 10)
+			nh.compute_energy_hessian_aux_fast<10, 3>(data, H);
+		else if (n_basis == 20)
+			nh.compute_energy_hessian_aux_fast<20, 3>(data, H);
+		else
+			nh.compute_energy_hessian_aux_fast<Eigen::Dynamic, 3>(data, H);
+		for (long r = 0; r < N; ++r)
+			for (long c = 0; c < N; ++c)
+				out[r * N + c] = H(r, c);
+		return 0;
+	}
+}

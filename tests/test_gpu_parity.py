@@ -279,3 +279,31 @@ def test_project_to_psd(oracle, p, n, scale):
     h3 = gpu_handle(M3 := make_case(2, 3)[0], "NeoHookean")
     with pytest.raises(capi.PfaError):
         h3.hessian(np.zeros(h3.ndof), project_to_psd=True)
+
+
+@pytest.mark.parametrize("k", range(12))
+def test_against_the_reference_own_function_outputs(oracle, k):
+    """CUDA path vs tests/golden/nh_local.npz: gradient and Hessian of single-element meshes as returned by
+    the reference's own compute_energy_aux_gradient_fast / compute_energy_hessian_aux_fast (compiled from
+    /root/reference, tests/test_oracle_reference_math.py). 1e-12 of the largest entry; NaN <=> NaN."""
+    import os
+    from polyfem_b200 import capi, tables
+    gold = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "nh_local.npz"))
+    p = int(gold[f"p_{k}"])
+    t = tables.reference_tables(p)
+    u = gold[f"u_{k}"]
+    nl = u.shape[0]
+    conn = np.arange(nl, dtype=np.int32)[None, :]
+    h = capi.Handle("NeoHookean", conn, nl, t["weights"], t["grad"], vertices=gold[f"vertices_{k}"][None],
+                    lam=float(gold["lambda"]), mu=float(gold["mu"]))
+    e, g, v = h.grad_hess(u.reshape(-1))
+    outer, inner = h.pattern()
+    assert h.nnz == (3 * nl) ** 2  # one element: the matrix is the dense local Hessian
+    H = np.zeros((3 * nl, 3 * nl))
+    col = np.repeat(np.arange(3 * nl), np.diff(outer))
+    H[inner, col] = v
+    for got, ref in ((g, gold[f"gradient_{k}"]), (H, gold[f"hessian_{k}"])):
+        assert np.array_equal(np.isnan(got), np.isnan(ref))
+        ok = ~np.isnan(ref)
+        if ok.any():
+            assert np.abs(got[ok] - ref[ok]).max() <= REL_TOL * np.abs(ref[ok]).max()

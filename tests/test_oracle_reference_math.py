@@ -1,0 +1,89 @@
+"""The oracle's NeoHookean local gradient / Hessian against the REFERENCE'S OWN function bodies.
+
+`oracle/refmath/` compiles `compute_energy_aux_gradient_fast` / `compute_energy_hessian_aux_fast` (with `hat`,
+`cross`; assembler/NeoHookeanElasticity.cpp:419-658) verbatim from /root/reference against a small dense-matrix
+stand-in (Eigen is not installed) into oracle/_ref/libnhref.so. `tools/make_golden.py` ran them on 12
+single-element cases (P1..P4, jittered tets, one inverted element) and committed inputs and outputs as
+tests/golden/nh_local.npz, which is what travels to the GPU box. Tolerance: 1e-13 of the largest entry
+(the two sides order their sums differently)."""
+import ctypes
+import os
+
+import numpy as np
+import pytest
+
+from polyfem_b200 import tables
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = np.load(os.path.join(ROOT, "tests", "golden", "nh_local.npz"))
+TOL = 1e-13
+
+
+def cases():
+    return range(int(GOLD["n_cases"]))
+
+
+def one_element_problem(oracle, k):
+    p = int(GOLD[f"p_{k}"])
+    t = tables.reference_tables(p)
+    verts = GOLD[f"vertices_{k}"]
+    u = GOLD[f"u_{k}"]
+    nl = u.shape[0]
+    conn = np.arange(nl, dtype=np.int32)[None, :]
+    prob = oracle.OracleProblem("NeoHookean", conn, verts[None], nl, t["points"], t["weights"], t["grad"],
+                                lam=float(GOLD["lambda"]), mu=float(GOLD["mu"]))
+    return prob, u.reshape(-1), nl
+
+
+def close(a, b):
+    assert np.array_equal(np.isnan(a), np.isnan(b)), "NaN pattern differs"
+    ok = ~np.isnan(b)
+    if ok.any():
+        assert np.abs(a[ok] - b[ok]).max() <= TOL * np.abs(b[ok]).max()
+
+
+@pytest.mark.parametrize("k", cases())
+def test_oracle_local_math_equals_reference_functions(oracle, k):
+    prob, x, nl = one_element_problem(oracle, k)
+    close(prob.local_gradient(0, x), GOLD[f"gradient_{k}"])
+    close(prob.local_hessian(0, x).reshape(3 * nl, 3 * nl), GOLD[f"hessian_{k}"])
+    # and through the global loops + SparseMatrixCache scatter: a one-element mesh assembles to H_e itself
+    H = prob.assemble_hessian(x)
+    close(np.asarray(H.to_scipy().todense()), GOLD[f"hessian_{k}"])
+    close(prob.assemble_gradient(x), GOLD[f"gradient_{k}"])
+
+
+def test_golden_has_the_inverted_case():
+    assert any(np.isnan(GOLD[f"gradient_{k}"]).any() for k in cases())
+
+
+def test_live_against_libnhref_when_present(oracle):
+    """More random elements, directly against oracle/_ref/libnhref.so (build container only)."""
+    path = os.path.join(ROOT, "oracle", "_ref", "libnhref.so")
+    if not os.path.exists(path):
+        pytest.skip("oracle/_ref/libnhref.so not built (no reference tree)")
+    from polyfem_b200 import mesh as M
+    lib = ctypes.CDLL(path)
+    dp = ctypes.POINTER(ctypes.c_double)
+    for f in (lib.ref_nh_gradient, lib.ref_nh_hessian):
+        f.argtypes = [ctypes.c_int, ctypes.c_int, dp, dp, dp, dp, ctypes.c_double, ctypes.c_double, dp]
+
+    def P(a):
+        return a.ctypes.data_as(dp)
+    lam, mu = M.lame_from_E_nu(1e5, 0.3)
+    for p, n in [(1, 2), (2, 2), (3, 1)]:
+        mesh = M.kuhn_cube(n, p, jitter=0.2)
+        x = M.random_displacement(mesh, scale=0.05 if p < 3 else 0.01)
+        t = tables.reference_tables(p)
+        ref = oracle.problem_from_mesh(mesh, "NeoHookean")
+        nl, nq = mesh.conn.shape[1], t["weights"].size
+        for e in range(min(mesh.n_elements, 10)):
+            edges = mesh.vertices[e][1:] - mesh.vertices[e][0]
+            jac_it = np.ascontiguousarray(np.repeat(np.linalg.inv(edges).T[None], nq, 0).reshape(nq, 9))
+            da = np.ascontiguousarray(np.linalg.det(edges) * t["weights"])
+            u = np.ascontiguousarray(x.reshape(-1, 3)[mesh.conn[e]].reshape(-1))
+            g, H = np.zeros(nl * 3), np.zeros((nl * 3, nl * 3))
+            assert lib.ref_nh_gradient(nl, nq, P(u), P(np.ascontiguousarray(t["grad"])), P(jac_it), P(da), lam, mu, P(g)) == 0
+            assert lib.ref_nh_hessian(nl, nq, P(u), P(np.ascontiguousarray(t["grad"])), P(jac_it), P(da), lam, mu, P(H)) == 0
+            close(ref.local_gradient(e, x), g)
+            close(ref.local_hessian(e, x).reshape(3 * nl, 3 * nl), H)

@@ -66,6 +66,64 @@ def ref_basis(lib, p, pts):
     return val, grad
 
 
+def load_nhref():
+    """oracle/_ref/libnhref.so: the reference's own NeoHookean gradient / Hessian function bodies (oracle/refmath)."""
+    lib = ctypes.CDLL(os.path.join(ROOT, "oracle", "_ref", "libnhref.so"))
+    dp = ctypes.POINTER(ctypes.c_double)
+    for f in (lib.ref_nh_gradient, lib.ref_nh_hessian):
+        f.argtypes = [ctypes.c_int, ctypes.c_int, dp, dp, dp, dp, ctypes.c_double, ctypes.c_double, dp]
+    return lib
+
+
+def nh_reference_local(lib, vertices, u, grads, weights, lam, mu):
+    """(gradient[n_loc*3], hessian[N,N]) of one affine element from the reference's own functions; the
+    geometry (J^-T, det, ElementAssemblyValues.cpp:81-103) is evaluated here with numpy."""
+    edges = vertices[1:] - vertices[0]
+    jit = np.linalg.inv(edges).T
+    nq, nl = weights.size, grads.shape[1]
+    jac_it = np.ascontiguousarray(np.repeat(jit[None], nq, 0).reshape(nq, 9))
+    da = np.ascontiguousarray(np.linalg.det(edges) * weights)
+    u = np.ascontiguousarray(u, dtype=np.float64).reshape(-1)
+    grads = np.ascontiguousarray(grads)
+    g = np.zeros(nl * 3)
+    H = np.zeros((nl * 3, nl * 3))
+    assert lib.ref_nh_gradient(nl, nq, ptr(u), ptr(grads), ptr(jac_it), ptr(da), lam, mu, ptr(g)) == 0
+    assert lib.ref_nh_hessian(nl, nq, ptr(u), ptr(grads), ptr(jac_it), ptr(da), lam, mu, ptr(H)) == 0
+    return g, H
+
+
+def write_nh_golden():
+    """tests/golden/nh_local.npz: single-element NeoHookean cases (P1..P4, jittered tets, random displacement,
+    one inverted element) with the gradient and Hessian returned by the reference's own function bodies."""
+    sys.path.insert(0, ROOT)
+    from polyfem_b200 import tables
+    lib = load_nhref()
+    rng = np.random.default_rng(424242)
+    lam, mu = 57692.307692307695, 38461.53846153846  # E = 1e5, nu = 0.3 (MatParams.cpp:11-22)
+    gold = {"lambda": lam, "mu": mu}
+    k = 0
+    for p in (1, 2, 3, 4):
+        t = tables.reference_tables(p)
+        nodes = tables.p_nodes(p)  # reference-element positions of the local nodes
+        for rep in range(3):
+            verts = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0], [0, 0, 1]], dtype=np.float64)
+            verts = 0.3 * (verts + 0.25 * rng.uniform(-1, 1, (4, 3))) + rng.uniform(-1, 1, 3)
+            scale = (0.05 if p < 3 else 0.01) * 0.3
+            u = scale * rng.uniform(-1, 1, (nodes.shape[0], 3))
+            if p == 2 and rep == 2:  # inverted: log(J <= 0) -> NaN must propagate exactly as in the reference
+                u[1] += 3.0 * (verts[0] - verts[1])
+            g, H = nh_reference_local(lib, verts, u, t["grad"], t["weights"], lam, mu)
+            gold[f"p_{k}"] = p
+            gold[f"vertices_{k}"] = verts
+            gold[f"u_{k}"] = u
+            gold[f"gradient_{k}"] = g
+            gold[f"hessian_{k}"] = H
+            k += 1
+    gold["n_cases"] = k
+    np.savez_compressed(os.path.join(ROOT, "tests", "golden", "nh_local.npz"), **gold)
+    print(f"wrote tests/golden/nh_local.npz ({k} cases)")
+
+
 def main():
     lib = load_ref()
     quad = {"source": "polyfem autogen/auto_tetrahedron.ipp via quadrature/TetQuadrature.cpp (weights /= 6)",
@@ -97,6 +155,7 @@ def main():
     os.makedirs(os.path.join(ROOT, "tests", "golden"), exist_ok=True)
     np.savez_compressed(os.path.join(ROOT, "tests", "golden", "ref_tables.npz"), **gold)
     print("wrote tet_quadrature.json and tests/golden/ref_tables.npz")
+    write_nh_golden()
 
 
 if __name__ == "__main__":
