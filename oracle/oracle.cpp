@@ -1490,6 +1490,8 @@ extern "C"
 		compute_da(vals, da);
 		if (op->pb.d.material == ORACLE_LAPLACIAN)
 			blk[0] = laplacian_local(vals, da, i, j);
+		else if (op->pb.d.material == ORACLE_MASS)
+			mass_local(vals, da, i, j, op->pb.density[e], op->pb.size, blk);
 		else
 			linear_elasticity_local(vals, da, i, j, op->pb.lambda[e], op->pb.mu[e], blk);
 	}

@@ -1,5 +1,6 @@
 // TEST INFRASTRUCTURE: a small dense-matrix stand-in for the part of Eigen's API that the reference's
-// NeoHookean "fast" gradient / Hessian functions use (assembler/NeoHookeanElasticity.cpp:419-658), so that
+// NeoHookean "fast" gradient / Hessian functions (assembler/NeoHookeanElasticity.cpp:419-658) and the linear local
+// blocks (LinearElasticity.cpp:29-63, Laplacian.cpp:13-26, Mass.cpp:5-23) use, so that
 // THOSE FUNCTION BODIES can be compiled from /root/reference and executed here, where Eigen is not installed
 // (oracle/refmath/extract_nh.py + nh_glue.cpp -> oracle/_ref/libnhref.so). Every operation is eager and
 // returns a plain column-major matrix (`Dense`); fixed-size template arguments only provide default shapes.
@@ -64,6 +65,14 @@ namespace Eigen
 				return m(0, 0) * m(1, 1) - m(0, 1) * m(1, 0);
 			return m(0, 0) * (m(1, 1) * m(2, 2) - m(1, 2) * m(2, 1)) - m(0, 1) * (m(1, 0) * m(2, 2) - m(1, 2) * m(2, 0))
 				   + m(0, 2) * (m(1, 0) * m(2, 1) - m(1, 1) * m(2, 0));
+		}
+		double dot(const Dense &o) const
+		{
+			assert(size() == o.size());
+			double s = 0;
+			for (long k = 0; k < size(); ++k)
+				s += d_[size_t(k)] * o(k);
+			return s;
 		}
 		Dense &noalias() { return *this; }
 		Dense &operator+=(const Dense &o)
@@ -227,6 +236,13 @@ namespace Eigen
 			return m;
 		}
 		static Dense Zero(long r, long c) { return Dense(r, c); }
+		static Dense Constant(double v) // fixed-size form only
+		{
+			Dense m(R, C);
+			for (long k = 0; k < m.size(); ++k)
+				m(k) = v;
+			return m;
+		}
 	};
 	using MatrixXd = Matrix<double, Dynamic, Dynamic>;
 	using VectorXd = Matrix<double, Dynamic, 1>;

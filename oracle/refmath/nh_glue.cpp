@@ -20,7 +20,9 @@ namespace polyfem::assembler
 	struct AssemblyValues // assembler/AssemblyValues.hpp
 	{
 		std::vector<Local2Global> global;
-		Eigen::MatrixXd grad; // n_qp x dim reference gradients
+		Eigen::MatrixXd grad;     // n_qp x dim reference gradients
+		Eigen::MatrixXd grad_t_m; // n_qp x dim physical gradients (grad * jac_it)
+		Eigen::VectorXd val;      // n_qp basis values
 	};
 	struct QuadratureStub
 	{
@@ -52,6 +54,39 @@ namespace polyfem::assembler
 			l = lambda;
 			m = mu;
 		}
+	};
+
+	struct LinearAssemblerData // assembler/AssemblerData.hpp
+	{
+		const ElementAssemblyValues &vals;
+		double t;
+		int i, j;
+		const Eigen::VectorXd &da;
+	};
+	struct Density // assembler/MatParams.hpp (call form of Mass.cpp:13)
+	{
+		double rho = 1;
+		double operator()(const Eigen::Dense &, const Eigen::Dense &, double, int) const { return rho; }
+	};
+	class LinearElasticity
+	{
+	public:
+		int size() const { return 3; }
+		LameParameters params_;
+		Eigen::Matrix<double, Eigen::Dynamic, 1, 0, 9, 1> assemble(const LinearAssemblerData &data) const;
+	};
+	class Laplacian
+	{
+	public:
+		int size() const { return 1; }
+		Eigen::Matrix<double, Eigen::Dynamic, 1, 0, 9, 1> assemble(const LinearAssemblerData &data) const;
+	};
+	class Mass
+	{
+	public:
+		int size() const { return 3; }
+		Density density_;
+		Eigen::Matrix<double, Eigen::Dynamic, 1, 0, 9, 1> assemble(const LinearAssemblerData &data) const;
 	};
 
 	class NeoHookeanElasticity
@@ -161,6 +196,76 @@ extern "C"
 		for (long r = 0; r < N; ++r)
 			for (long c = 0; c < N; ++c)
 				out[r * N + c] = H(r, c);
+		return 0;
+	}
+
+	// ---- linear local blocks: res[size*size] with index n*size + m (LinearAssembler::assemble, Assembler.cpp:228-236) ----
+	// gi / gj: grad_t_m of bases i and j, [n_qp][3]; vi / vj: basis values [n_qp]
+	static void fill_pair(ElementAssemblyValues &vals, Eigen::VectorXd &dav, int n_qp, const double *gi, const double *gj, const double *vi, const double *vj, const double *da)
+	{
+		vals.basis_values.resize(2);
+		vals.quadrature.points.resize(n_qp, 3);
+		vals.val.resize(n_qp, 3);
+		dav.resize(n_qp, 1);
+		for (int b = 0; b < 2; ++b)
+		{
+			vals.basis_values[b].grad_t_m.resize(n_qp, 3);
+			vals.basis_values[b].val.resize(n_qp, 1);
+		}
+		for (int q = 0; q < n_qp; ++q)
+		{
+			dav(q) = da[q];
+			for (int c = 0; c < 3; ++c)
+			{
+				vals.basis_values[0].grad_t_m(q, c) = gi ? gi[q * 3 + c] : 0.0;
+				vals.basis_values[1].grad_t_m(q, c) = gj ? gj[q * 3 + c] : 0.0;
+			}
+			vals.basis_values[0].val(q) = vi ? vi[q] : 0.0;
+			vals.basis_values[1].val(q) = vj ? vj[q] : 0.0;
+		}
+	}
+
+	int ref_linear_elasticity_block(int n_qp, const double *gi, const double *gj, const double *da, double lambda, double mu, double *out9)
+	{
+		ElementAssemblyValues vals;
+		Eigen::VectorXd dav;
+		fill_pair(vals, dav, n_qp, gi, gj, nullptr, nullptr, da);
+		LinearElasticity le;
+		le.params_.lambda = lambda;
+		le.params_.mu = mu;
+		const auto res = le.assemble(LinearAssemblerData{vals, 0.0, 0, 1, dav});
+		if (res.size() != 9)
+			return -1;
+		for (int k = 0; k < 9; ++k)
+			out9[k] = res(k);
+		return 0;
+	}
+
+	int ref_laplacian_block(int n_qp, const double *gi, const double *gj, const double *da, double *out1)
+	{
+		ElementAssemblyValues vals;
+		Eigen::VectorXd dav;
+		fill_pair(vals, dav, n_qp, gi, gj, nullptr, nullptr, da);
+		Laplacian lap;
+		const auto res = lap.assemble(LinearAssemblerData{vals, 0.0, 0, 1, dav});
+		if (res.size() != 1)
+			return -1;
+		out1[0] = res(0);
+		return 0;
+	}
+
+	int ref_mass_block(int n_qp, const double *vi, const double *vj, const double *da, double rho, double *out9)
+	{
+		ElementAssemblyValues vals;
+		Eigen::VectorXd dav;
+		fill_pair(vals, dav, n_qp, nullptr, nullptr, vi, vj, da);
+		Mass mass;
+		mass.density_.rho = rho;
+		const auto res = mass.assemble(LinearAssemblerData{vals, 0.0, 0, 1, dav});
+		if (res.size() != 9)
+			return -1;
+		for (int k = 0; k < 9; ++k)
+			out9[k] = res(k);
 		return 0;
 	}
 }

@@ -87,3 +87,40 @@ def test_live_against_libnhref_when_present(oracle):
             assert lib.ref_nh_hessian(nl, nq, P(u), P(np.ascontiguousarray(t["grad"])), P(jac_it), P(da), lam, mu, P(H)) == 0
             close(ref.local_gradient(e, x), g)
             close(ref.local_hessian(e, x).reshape(3 * nl, 3 * nl), H)
+
+
+@pytest.mark.parametrize("p", [1, 2, 3, 4])
+def test_linear_local_blocks_equal_reference_functions(oracle, p):
+    """LinearElasticity::assemble / Laplacian::assemble / Mass::assemble(LinearAssemblerData) of the reference
+    (LinearElasticity.cpp:29-63, Laplacian.cpp:13-26, Mass.cpp:5-23, compiled verbatim like the NeoHookean functions)
+    against the oracle's local blocks, and against the assembled matrix of the one-element mesh."""
+    verts = GOLD[f"lin_vertices_p{p}"]
+    t = tables.reference_tables(p)
+    tm = tables.reference_tables(p, tables.quadrature_order(p, is_mass=True))
+    nl = t["grad"].shape[1]
+    conn = np.arange(nl, dtype=np.int32)[None, :]
+    lam, mu, rho = float(GOLD["lambda"]), float(GOLD["mu"]), float(GOLD["rho"])
+    le = oracle.OracleProblem("LinearElasticity", conn, verts[None], nl, t["points"], t["weights"], t["grad"], lam=lam, mu=mu)
+    lap = oracle.OracleProblem("Laplacian", conn, verts[None], nl, t["points"], t["weights"], t["grad"])
+    mass = oracle.OracleProblem("Mass", conn, verts[None], nl, tm["points"], tm["weights"], tm["grad"], ref_vals=tm["val"], density=rho)
+    g_le, g_lap, g_mass = GOLD[f"le_blocks_p{p}"], GOLD[f"lap_blocks_p{p}"], GOLD[f"mass_blocks_p{p}"]
+    s_le, s_lap, s_mass = np.abs(g_le).max(), np.abs(g_lap).max(), np.abs(g_mass).max()
+    for i in range(nl):
+        for j in range(nl):
+            assert np.abs(le.local_stiffness(0, i, j) - g_le[i, j]).max() <= TOL * s_le
+            assert abs(lap.local_stiffness(0, i, j)[0] - g_lap[i, j]) <= TOL * s_lap
+            assert np.abs(mass.local_stiffness(0, i, j) - g_mass[i, j]).max() <= TOL * s_mass
+    # LinearAssembler::assemble (Assembler.cpp:228-250): entry (g_i*size + m, g_j*size + n) = block(n*size + m), j <= i
+    # computed and mirrored; on a one-element mesh the assembled matrix is exactly that table
+    for prob, blocks, size in ((le, g_le, 3), (mass, g_mass, 3)):
+        K = np.asarray(prob.assemble().to_scipy().todense())
+        ref = np.zeros_like(K)
+        for i in range(nl):
+            for j in range(i + 1):
+                blk = blocks[i, j].reshape(size, size)  # [n][m]
+                ref[i * size:(i + 1) * size, j * size:(j + 1) * size] = blk.T
+                ref[j * size:(j + 1) * size, i * size:(i + 1) * size] = blk
+        assert np.abs(K - ref).max() <= TOL * np.abs(ref).max()
+    K = np.asarray(lap.assemble().to_scipy().todense())
+    ref = np.tril(g_lap) + np.tril(g_lap, -1).T
+    assert np.abs(K - ref).max() <= TOL * np.abs(ref).max()

@@ -72,7 +72,36 @@ def load_nhref():
     dp = ctypes.POINTER(ctypes.c_double)
     for f in (lib.ref_nh_gradient, lib.ref_nh_hessian):
         f.argtypes = [ctypes.c_int, ctypes.c_int, dp, dp, dp, dp, ctypes.c_double, ctypes.c_double, dp]
+    lib.ref_linear_elasticity_block.argtypes = [ctypes.c_int, dp, dp, dp, ctypes.c_double, ctypes.c_double, dp]
+    lib.ref_laplacian_block.argtypes = [ctypes.c_int, dp, dp, dp, dp]
+    lib.ref_mass_block.argtypes = [ctypes.c_int, dp, dp, dp, ctypes.c_double, dp]
     return lib
+
+
+def linear_reference_blocks(lib, vertices, t, t_mass, lam, mu, rho):
+    """All local blocks of one affine element from the reference's own LinearElasticity / Laplacian / Mass
+    ::assemble(LinearAssemblerData): (le[n_loc][n_loc][9], lap[n_loc][n_loc], mass[n_loc][n_loc][9]), block entries
+    in the reference's index n*size + m. grad_t_m = grad * J^-T and da = det * w are evaluated here with numpy."""
+    edges = vertices[1:] - vertices[0]
+    jit = np.linalg.inv(edges).T
+    det = np.linalg.det(edges)
+    gt = np.einsum("qic,cd->qid", t["grad"], jit)
+    da = np.ascontiguousarray(det * t["weights"])
+    dam = np.ascontiguousarray(det * t_mass["weights"])
+    nl = t["grad"].shape[1]
+    le, lap, mass = np.zeros((nl, nl, 9)), np.zeros((nl, nl)), np.zeros((nl, nl, 9))
+    for i in range(nl):
+        gi = np.ascontiguousarray(gt[:, i, :])
+        vi = np.ascontiguousarray(t_mass["val"][:, i])
+        for j in range(nl):
+            gj = np.ascontiguousarray(gt[:, j, :])
+            vj = np.ascontiguousarray(t_mass["val"][:, j])
+            o1 = np.zeros(1)
+            assert lib.ref_linear_elasticity_block(da.size, ptr(gi), ptr(gj), ptr(da), lam, mu, ptr(le[i, j])) == 0
+            assert lib.ref_laplacian_block(da.size, ptr(gi), ptr(gj), ptr(da), ptr(o1)) == 0
+            lap[i, j] = o1[0]
+            assert lib.ref_mass_block(dam.size, ptr(vi), ptr(vj), ptr(dam), rho, ptr(mass[i, j])) == 0
+    return le, lap, mass
 
 
 def nh_reference_local(lib, vertices, u, grads, weights, lam, mu):
@@ -94,7 +123,8 @@ def nh_reference_local(lib, vertices, u, grads, weights, lam, mu):
 
 def write_nh_golden():
     """tests/golden/nh_local.npz: single-element NeoHookean cases (P1..P4, jittered tets, random displacement,
-    one inverted element) with the gradient and Hessian returned by the reference's own function bodies."""
+    one inverted element) with the gradient and Hessian returned by the reference's own function bodies, and
+    all LinearElasticity / Laplacian / Mass local blocks of one element per order."""
     sys.path.insert(0, ROOT)
     from polyfem_b200 import tables
     lib = load_nhref()
@@ -120,6 +150,18 @@ def write_nh_golden():
             gold[f"hessian_{k}"] = H
             k += 1
     gold["n_cases"] = k
+    # linear assemblers: every local block of one jittered element per order
+    gold["rho"] = 2.5
+    for p in (1, 2, 3, 4):
+        verts = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0], [0, 0, 1]], dtype=np.float64)
+        verts = 0.4 * (verts + 0.25 * rng.uniform(-1, 1, (4, 3))) + rng.uniform(-1, 1, 3)
+        t = tables.reference_tables(p)
+        tm = tables.reference_tables(p, tables.quadrature_order(p, is_mass=True))
+        le, lap, mass = linear_reference_blocks(lib, verts, t, tm, lam, mu, 2.5)
+        gold[f"lin_vertices_p{p}"] = verts
+        gold[f"le_blocks_p{p}"] = le
+        gold[f"lap_blocks_p{p}"] = lap
+        gold[f"mass_blocks_p{p}"] = mass
     np.savez_compressed(os.path.join(ROOT, "tests", "golden", "nh_local.npz"), **gold)
     print(f"wrote tests/golden/nh_local.npz ({k} cases)")
 
