@@ -9,12 +9,12 @@
  *     (oracle/_ref, tests/golden/ref_tables.npz).
  *   - SparseMatrixCache semantics: PINNED by the reference's self-contained known-answer test
  *     tests/test_matrix.cpp:202-249 ("cache"), restated in tests/test_oracle_cache.py.
- *   - NeoHookean local gradient and Hessian: PINNED against the reference's own function bodies
- *     (NeoHookeanElasticity.cpp:419-658 compiled verbatim from /root/reference against oracle/refmath/mini_eigen.hpp
+ *   - NeoHookean local energy, gradient and Hessian: PINNED against the reference's own function bodies
+ *     (NeoHookeanElasticity.cpp:338-658 compiled verbatim from /root/reference against oracle/refmath/mini_eigen.hpp
  *     into oracle/_ref/libnhref.so; outputs committed as tests/golden/nh_local.npz; tests/test_oracle_reference_math.py).
  *   - LinearElasticity / Laplacian / Mass local blocks: PINNED the same way (LinearElasticity.cpp:29-63,
  *     Laplacian.cpp:13-26, Mass.cpp:5-23 compiled verbatim; golden blocks in tests/golden/nh_local.npz).
- *   - the energy and the global loops on multi-element meshes: the reference
+ *   - the global loops on multi-element meshes: the reference
  *     cannot be compiled here (Eigen, TBB, spdlog, ... are not vendored) and its tests for this
  *     path are property tests on a mesh from polyfem-data (absent). They are restated on the
  *     synthetic cube (closed form == autodiff 1e-12, NL Hessian == linear stiffness 1e-8,

@@ -66,6 +66,13 @@ namespace Eigen
 			return m(0, 0) * (m(1, 1) * m(2, 2) - m(1, 2) * m(2, 1)) - m(0, 1) * (m(1, 0) * m(2, 2) - m(1, 2) * m(2, 0))
 				   + m(0, 2) * (m(1, 0) * m(2, 1) - m(1, 1) * m(2, 0));
 		}
+		double squaredNorm() const
+		{
+			double s = 0;
+			for (double v : d_)
+				s += v * v;
+			return s;
+		}
 		double dot(const Dense &o) const
 		{
 			assert(size() == o.size());

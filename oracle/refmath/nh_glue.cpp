@@ -9,6 +9,13 @@
 
 using std::log;
 
+namespace polyfem::utils
+{
+	// named (qualified) in the autodiff branch of compute_energy_aux, which is never instantiated here
+	template <typename M>
+	double determinant(const M &m) { return m.determinant(); }
+} // namespace polyfem::utils
+
 namespace polyfem::assembler
 {
 	// the few members of the reference types that the extracted functions touch
@@ -95,6 +102,8 @@ namespace polyfem::assembler
 		int size() const { return 3; }
 		bool use_robust_jacobian = false;
 		LameParameters params_;
+		template <typename T, int n_basis, int dim>
+		T compute_energy_aux(const NonLinearAssemblerData &data) const;
 		template <int n_basis, int dim>
 		void compute_energy_aux_gradient_fast(const NonLinearAssemblerData &data, Eigen::Matrix<double, Eigen::Dynamic, 1> &G_flattened) const;
 		template <int n_basis, int dim>
@@ -148,6 +157,26 @@ namespace
 
 extern "C"
 {
+	// NeoHookeanElasticity::compute_energy -> compute_energy_aux<double, n_basis, dim> (NeoHookeanElasticity.cpp:304-388)
+	int ref_nh_energy(int n_basis, int n_qp, const double *u, const double *grads, const double *jac_it, const double *da, double lambda, double mu, double *out)
+	{
+		Inputs in;
+		fill(in, n_basis, n_qp, u, grads, jac_it, da);
+		NeoHookeanElasticity nh;
+		nh.params_.lambda = lambda;
+		nh.params_.mu = mu;
+		const NonLinearAssemblerData data{in.vals, 0.0, 1.0, in.x, in.x_prev, in.da};
+		if (n_basis == 4)
+			*out = nh.compute_energy_aux<double, 4, 3>(data);
+		else if (n_basis == 10)
+			*out = nh.compute_energy_aux<double, 10, 3>(data);
+		else if (n_basis == 20)
+			*out = nh.compute_energy_aux<double, 20, 3>(data);
+		else
+			*out = nh.compute_energy_aux<double, Eigen::Dynamic, 3>(data);
+		return 0;
+	}
+
 	// out[n_basis*3], node-major (NeoHookeanElasticity.cpp:540-544). The instantiation follows the reference's own
 	// dispatch on the number of bases (assemble_gradient: 4, 10, 20 fixed, anything else dynamic).
 	int ref_nh_gradient(int n_basis, int n_qp, const double *u, const double *grads, const double *jac_it, const double *da, double lambda, double mu, double *out)

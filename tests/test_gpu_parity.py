@@ -298,6 +298,8 @@ def test_against_the_reference_own_function_outputs(oracle, k):
                     lam=float(gold["lambda"]), mu=float(gold["mu"]))
     e, g, v = h.grad_hess(u.reshape(-1))
     outer, inner = h.pattern()
+    e_ref = float(gold[f"energy_{k}"])
+    assert np.isnan(e) == np.isnan(e_ref) and (np.isnan(e_ref) or abs(e - e_ref) <= REL_TOL * abs(e_ref))
     assert h.nnz == (3 * nl) ** 2  # one element: the matrix is the dense local Hessian
     H = np.zeros((3 * nl, 3 * nl))
     col = np.repeat(np.arange(3 * nl), np.diff(outer))

@@ -1,7 +1,7 @@
 """The oracle's NeoHookean local gradient / Hessian against the REFERENCE'S OWN function bodies.
 
-`oracle/refmath/` compiles `compute_energy_aux_gradient_fast` / `compute_energy_hessian_aux_fast` (with `hat`,
-`cross`; assembler/NeoHookeanElasticity.cpp:419-658) verbatim from /root/reference against a small dense-matrix
+`oracle/refmath/` compiles `compute_energy_aux`, `compute_energy_aux_gradient_fast`, `compute_energy_hessian_aux_fast`
+(with `hat`, `cross`; assembler/NeoHookeanElasticity.cpp:338-658) verbatim from /root/reference against a small dense-matrix
 stand-in (Eigen is not installed) into oracle/_ref/libnhref.so. `tools/make_golden.py` ran them on 12
 single-element cases (P1..P4, jittered tets, one inverted element) and committed inputs and outputs as
 tests/golden/nh_local.npz, which is what travels to the GPU box. Tolerance: 1e-13 of the largest entry
@@ -45,6 +45,9 @@ def close(a, b):
 @pytest.mark.parametrize("k", cases())
 def test_oracle_local_math_equals_reference_functions(oracle, k):
     prob, x, nl = one_element_problem(oracle, k)
+    e_ref = float(GOLD[f"energy_{k}"])
+    for e in (prob.local_energy(0, x), prob.assemble_energy(x)):
+        assert np.isnan(e) == np.isnan(e_ref) and (np.isnan(e_ref) or abs(e - e_ref) <= TOL * abs(e_ref))
     close(prob.local_gradient(0, x), GOLD[f"gradient_{k}"])
     close(prob.local_hessian(0, x).reshape(3 * nl, 3 * nl), GOLD[f"hessian_{k}"])
     # and through the global loops + SparseMatrixCache scatter: a one-element mesh assembles to H_e itself
@@ -65,7 +68,7 @@ def test_live_against_libnhref_when_present(oracle):
     from polyfem_b200 import mesh as M
     lib = ctypes.CDLL(path)
     dp = ctypes.POINTER(ctypes.c_double)
-    for f in (lib.ref_nh_gradient, lib.ref_nh_hessian):
+    for f in (lib.ref_nh_energy, lib.ref_nh_gradient, lib.ref_nh_hessian):
         f.argtypes = [ctypes.c_int, ctypes.c_int, dp, dp, dp, dp, ctypes.c_double, ctypes.c_double, dp]
 
     def P(a):
@@ -87,6 +90,9 @@ def test_live_against_libnhref_when_present(oracle):
             assert lib.ref_nh_hessian(nl, nq, P(u), P(np.ascontiguousarray(t["grad"])), P(jac_it), P(da), lam, mu, P(H)) == 0
             close(ref.local_gradient(e, x), g)
             close(ref.local_hessian(e, x).reshape(3 * nl, 3 * nl), H)
+            en = np.zeros(1)
+            assert lib.ref_nh_energy(nl, nq, P(u), P(np.ascontiguousarray(t["grad"])), P(jac_it), P(da), lam, mu, P(en)) == 0
+            assert abs(ref.local_energy(e, x) - en[0]) <= TOL * abs(en[0])
 
 
 @pytest.mark.parametrize("p", [1, 2, 3, 4])

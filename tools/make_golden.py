@@ -70,7 +70,7 @@ def load_nhref():
     """oracle/_ref/libnhref.so: the reference's own NeoHookean gradient / Hessian function bodies (oracle/refmath)."""
     lib = ctypes.CDLL(os.path.join(ROOT, "oracle", "_ref", "libnhref.so"))
     dp = ctypes.POINTER(ctypes.c_double)
-    for f in (lib.ref_nh_gradient, lib.ref_nh_hessian):
+    for f in (lib.ref_nh_energy, lib.ref_nh_gradient, lib.ref_nh_hessian):
         f.argtypes = [ctypes.c_int, ctypes.c_int, dp, dp, dp, dp, ctypes.c_double, ctypes.c_double, dp]
     lib.ref_linear_elasticity_block.argtypes = [ctypes.c_int, dp, dp, dp, ctypes.c_double, ctypes.c_double, dp]
     lib.ref_laplacian_block.argtypes = [ctypes.c_int, dp, dp, dp, dp]
@@ -105,7 +105,7 @@ def linear_reference_blocks(lib, vertices, t, t_mass, lam, mu, rho):
 
 
 def nh_reference_local(lib, vertices, u, grads, weights, lam, mu):
-    """(gradient[n_loc*3], hessian[N,N]) of one affine element from the reference's own functions; the
+    """(energy, gradient[n_loc*3], hessian[N,N]) of one affine element from the reference's own functions; the
     geometry (J^-T, det, ElementAssemblyValues.cpp:81-103) is evaluated here with numpy."""
     edges = vertices[1:] - vertices[0]
     jit = np.linalg.inv(edges).T
@@ -116,9 +116,11 @@ def nh_reference_local(lib, vertices, u, grads, weights, lam, mu):
     grads = np.ascontiguousarray(grads)
     g = np.zeros(nl * 3)
     H = np.zeros((nl * 3, nl * 3))
+    e = np.zeros(1)
+    assert lib.ref_nh_energy(nl, nq, ptr(u), ptr(grads), ptr(jac_it), ptr(da), lam, mu, ptr(e)) == 0
     assert lib.ref_nh_gradient(nl, nq, ptr(u), ptr(grads), ptr(jac_it), ptr(da), lam, mu, ptr(g)) == 0
     assert lib.ref_nh_hessian(nl, nq, ptr(u), ptr(grads), ptr(jac_it), ptr(da), lam, mu, ptr(H)) == 0
-    return g, H
+    return float(e[0]), g, H
 
 
 def write_nh_golden():
@@ -142,7 +144,8 @@ def write_nh_golden():
             u = scale * rng.uniform(-1, 1, (nodes.shape[0], 3))
             if p == 2 and rep == 2:  # inverted: log(J <= 0) -> NaN must propagate exactly as in the reference
                 u[1] += 3.0 * (verts[0] - verts[1])
-            g, H = nh_reference_local(lib, verts, u, t["grad"], t["weights"], lam, mu)
+            e, g, H = nh_reference_local(lib, verts, u, t["grad"], t["weights"], lam, mu)
+            gold[f"energy_{k}"] = e
             gold[f"p_{k}"] = p
             gold[f"vertices_{k}"] = verts
             gold[f"u_{k}"] = u
