@@ -1496,6 +1496,21 @@ extern "C"
 			linear_elasticity_local(vals, da, i, j, op->pb.lambda[e], op->pb.mu[e], blk);
 	}
 
+	void oracle_assembly_values(oracle_problem *op, int e, double *det, double *jac_it, double *grad_t_m)
+	{
+		ElementAssemblyValues vals;
+		op->pb.cache_compute(e, vals);
+		for (int q = 0; q < vals.n_qp; ++q)
+		{
+			det[q] = vals.det[q];
+			for (int k = 0; k < 9; ++k)
+				jac_it[size_t(q) * 9 + k] = vals.jac_it[size_t(q) * 9 + k];
+			for (int j = 0; j < vals.n_loc; ++j)
+				for (int c = 0; c < 3; ++c)
+					grad_t_m[(size_t(q) * vals.n_loc + j) * 3 + c] = vals.gt(j, q)[c];
+		}
+	}
+
 	void oracle_project_to_psd(int n, double *a)
 	{
 		std::vector<double> A(a, a + size_t(n) * n);

@@ -94,6 +94,10 @@ extern "C"
 	void oracle_local_hessian(oracle_problem *p, int e, const double *x, int autodiff, double *h /*[N*N] row-major*/);
 	void oracle_local_stiffness(oracle_problem *p, int e, int i, int j, double *blk /*[size*size], index n*size+m*/);
 
+	/* ElementAssemblyValues of element e as the assemblers see them (ElementAssemblyValues.cpp:65-104):
+	 * det[n_qp], jac_it[n_qp][9] row-major, grad_t_m[n_qp][n_loc][3] */
+	void oracle_assembly_values(oracle_problem *p, int e, double *det, double *jac_it, double *grad_t_m);
+
 	/* ipc::project_to_psd restatement on a dense symmetric n x n matrix (row-major, in place) */
 	void oracle_project_to_psd(int n, double *a);
 

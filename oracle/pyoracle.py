@@ -73,6 +73,8 @@ def lib():
     L.oracle_local_gradient.argtypes = [vp, ctypes.c_int, _dp, ctypes.c_int, _dp]
     L.oracle_local_hessian.argtypes = [vp, ctypes.c_int, _dp, ctypes.c_int, _dp]
     L.oracle_local_stiffness.argtypes = [vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, _dp]
+    L.oracle_assembly_values.argtypes = [vp, ctypes.c_int, _dp, _dp, _dp]
+    L.oracle_assembly_values.restype = None
     L.oracle_project_to_psd.argtypes = [ctypes.c_int, _dp]
     L.oracle_cache_new.restype = vp
     L.oracle_cache_new.argtypes = [ctypes.c_int]
@@ -212,6 +214,13 @@ class OracleProblem:
         h = np.zeros((n, n))
         lib().oracle_local_hessian(self._h, int(e), _d(x), int(autodiff), _d(h))
         return h
+
+    def assembly_values(self, e):
+        """(det[n_qp], jac_it[n_qp,3,3], grad_t_m[n_qp,n_loc,3]) of element e (ElementAssemblyValues.cpp:65-104)."""
+        nq = int(self.qw.size)
+        det, jit, gt = np.zeros(nq), np.zeros((nq, 3, 3)), np.zeros((nq, self.n_loc, 3))
+        lib().oracle_assembly_values(self._h, int(e), _d(det), _d(jit), _d(gt))
+        return det, jit, gt
 
     def local_stiffness(self, e, i, j):
         blk = np.zeros(self.size * self.size)

@@ -66,6 +66,35 @@ namespace Eigen
 			return m(0, 0) * (m(1, 1) * m(2, 2) - m(1, 2) * m(2, 1)) - m(0, 1) * (m(1, 0) * m(2, 2) - m(1, 2) * m(2, 0))
 				   + m(0, 2) * (m(1, 0) * m(2, 1) - m(1, 1) * m(2, 0));
 		}
+		Dense inverse() const // closed forms of utils/MatrixUtils.hpp:37-80 (Eigen's own 3x3 inverse differs only in rounding)
+		{
+			const Dense &m = *this;
+			assert(r_ == c_ && r_ >= 1 && r_ <= 3);
+			Dense inv(r_, c_);
+			const double det = determinant();
+			if (r_ == 1)
+				inv(0, 0) = 1.0 / m(0, 0);
+			else if (r_ == 2)
+			{
+				inv(0, 0) = m(1, 1) / det;
+				inv(0, 1) = -m(0, 1) / det;
+				inv(1, 0) = -m(1, 0) / det;
+				inv(1, 1) = m(0, 0) / det;
+			}
+			else
+			{
+				inv(0, 0) = (-m(1, 2) * m(2, 1) + m(1, 1) * m(2, 2)) / det;
+				inv(0, 1) = (m(0, 2) * m(2, 1) - m(0, 1) * m(2, 2)) / det;
+				inv(0, 2) = (-m(0, 2) * m(1, 1) + m(0, 1) * m(1, 2)) / det;
+				inv(1, 0) = (m(1, 2) * m(2, 0) - m(1, 0) * m(2, 2)) / det;
+				inv(1, 1) = (-m(0, 2) * m(2, 0) + m(0, 0) * m(2, 2)) / det;
+				inv(1, 2) = (m(0, 2) * m(1, 0) - m(0, 0) * m(1, 2)) / det;
+				inv(2, 0) = (-m(1, 1) * m(2, 0) + m(1, 0) * m(2, 1)) / det;
+				inv(2, 1) = (m(0, 1) * m(2, 0) - m(0, 0) * m(2, 1)) / det;
+				inv(2, 2) = (-m(0, 1) * m(1, 0) + m(0, 0) * m(1, 1)) / det;
+			}
+			return inv;
+		}
 		double squaredNorm() const
 		{
 			double s = 0;
@@ -253,6 +282,7 @@ namespace Eigen
 	};
 	using MatrixXd = Matrix<double, Dynamic, Dynamic>;
 	using VectorXd = Matrix<double, Dynamic, 1>;
+	using Matrix3d = Matrix<double, 3, 3>;
 
 	// Map<T>(ptr, n): the reference only reads through it (a column vector of n entries)
 	template <typename T>

@@ -130,3 +130,21 @@ def test_linear_local_blocks_equal_reference_functions(oracle, p):
     K = np.asarray(lap.assemble().to_scipy().todense())
     ref = np.tril(g_lap) + np.tril(g_lap, -1).T
     assert np.abs(K - ref).max() <= TOL * np.abs(ref).max()
+
+
+@pytest.mark.parametrize("p", [1, 2, 3, 4])
+def test_geometry_equals_reference_finalize3d(oracle, p):
+    """det, J^-T and grad_t_m of the oracle against the reference's own ElementAssemblyValues::finalize3d
+    (ElementAssemblyValues.cpp:65-104, compiled verbatim; its 3x3 inverse is the stand-in's cofactor formula)."""
+    verts = GOLD[f"lin_vertices_p{p}"]
+    t = tables.reference_tables(p)
+    nl = t["grad"].shape[1]
+    conn = np.arange(nl, dtype=np.int32)[None, :]
+    prob = oracle.OracleProblem("Laplacian", conn, verts[None], nl, t["points"], t["weights"], t["grad"])
+    det, jit, gt = prob.assembly_values(0)
+    for got, ref in ((det, GOLD[f"geo_det_p{p}"]), (jit, GOLD[f"geo_jac_it_p{p}"]), (gt, GOLD[f"geo_grad_t_m_p{p}"])):
+        assert np.abs(got - ref).max() <= TOL * np.abs(ref).max()
+    # and the numpy form the parity tests feed to the library as "general geometry" input
+    edges = verts[1:] - verts[0]
+    assert np.abs(np.linalg.inv(edges).T - GOLD[f"geo_jac_it_p{p}"][0]).max() <= 1e-12 * np.abs(GOLD[f"geo_jac_it_p{p}"][0]).max()
+    assert abs(np.linalg.det(edges) - GOLD[f"geo_det_p{p}"][0]) <= 1e-13 * abs(GOLD[f"geo_det_p{p}"][0])

@@ -165,6 +165,17 @@ def write_nh_golden():
         gold[f"le_blocks_p{p}"] = le
         gold[f"lap_blocks_p{p}"] = lap
         gold[f"mass_blocks_p{p}"] = mass
+    # geometry: the reference's own ElementAssemblyValues::finalize3d on the same elements
+    geo = ctypes.CDLL(os.path.join(ROOT, "oracle", "_ref", "libgeomref.so"))
+    dp = ctypes.POINTER(ctypes.c_double)
+    geo.ref_finalize3d.argtypes = [ctypes.c_int, ctypes.c_int, dp, dp, dp, dp, dp]
+    for p in (1, 2, 3, 4):
+        t = tables.reference_tables(p)
+        nq, nl = t["weights"].size, t["grad"].shape[1]
+        verts = np.ascontiguousarray(gold[f"lin_vertices_p{p}"])
+        det, jit, gt = np.zeros(nq), np.zeros((nq, 3, 3)), np.zeros((nq, nl, 3))
+        assert geo.ref_finalize3d(nl, nq, ptr(verts), ptr(np.ascontiguousarray(t["grad"])), ptr(det), ptr(jit), ptr(gt)) == 0
+        gold[f"geo_det_p{p}"], gold[f"geo_jac_it_p{p}"], gold[f"geo_grad_t_m_p{p}"] = det, jit, gt
     np.savez_compressed(os.path.join(ROOT, "tests", "golden", "nh_local.npz"), **gold)
     print(f"wrote tests/golden/nh_local.npz ({k} cases)")
 
