@@ -1534,6 +1534,8 @@ extern "C"
 	void oracle_cache_free(oracle_cache *c) { delete c; }
 	void oracle_cache_add_value(oracle_cache *c, int e, int i, int j, double v) { c->c.add_value(e, i, j, v); }
 	void oracle_cache_prune(oracle_cache *c) { c->c.prune(); }
+	void oracle_cache_set_zero(oracle_cache *c) { c->c.set_zero(); }
+	void oracle_cache_add(oracle_cache *dst, const oracle_cache *src) { dst->c += src->c; } // SparseMatrixCache::operator+= (MatrixCache.cpp:289-322)
 	int64_t oracle_cache_get_matrix(oracle_cache *c)
 	{
 		c->last = c->c.get_matrix();

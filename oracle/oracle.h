@@ -8,7 +8,9 @@
  *   - quadrature + basis tables: PINNED against the reference's own generated sources
  *     (oracle/_ref, tests/golden/ref_tables.npz).
  *   - SparseMatrixCache semantics: PINNED by the reference's self-contained known-answer test
- *     tests/test_matrix.cpp:202-249 ("cache"), restated in tests/test_oracle_cache.py.
+ *     tests/test_matrix.cpp:202-249 ("cache"), restated in tests/test_oracle_cache.py, and bit for bit against the
+ *     reference's own utils/MatrixCache.cpp compiled unmodified (oracle/_ref/libcacheref.so,
+ *     tests/test_oracle_cache_vs_reference.py, tests/golden/cache_sequences.npz).
  *   - NeoHookean local energy, gradient and Hessian: PINNED against the reference's own function bodies
  *     (NeoHookeanElasticity.cpp:338-658 compiled verbatim from /root/reference against oracle/refmath/mini_eigen.hpp
  *     into oracle/_ref/libnhref.so; outputs committed as tests/golden/nh_local.npz; tests/test_oracle_reference_math.py).
@@ -108,6 +110,8 @@ extern "C"
 	void oracle_cache_free(oracle_cache *c);
 	void oracle_cache_add_value(oracle_cache *c, int e, int i, int j, double v);
 	void oracle_cache_prune(oracle_cache *c);
+	void oracle_cache_set_zero(oracle_cache *c);
+	void oracle_cache_add(oracle_cache *dst, const oracle_cache *src); /* operator+= */
 	int64_t oracle_cache_get_matrix(oracle_cache *c); /* returns nnz; then read with the getters */
 	const int32_t *oracle_cache_outer(const oracle_cache *c);
 	const int32_t *oracle_cache_inner(const oracle_cache *c);

@@ -83,6 +83,8 @@ def lib():
     L.oracle_cache_free.argtypes = [vp]
     L.oracle_cache_add_value.argtypes = [vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_double]
     L.oracle_cache_prune.argtypes = [vp]
+    L.oracle_cache_set_zero.argtypes = [vp]
+    L.oracle_cache_add.argtypes = [vp, vp]
     L.oracle_cache_get_matrix.restype = ctypes.c_int64
     L.oracle_cache_get_matrix.argtypes = [vp]
     for name, rt in (("oracle_cache_outer", _ip), ("oracle_cache_inner", _ip), ("oracle_cache_values", _dp)):
@@ -317,6 +319,13 @@ class Cache:
 
     def prune(self):
         lib().oracle_cache_prune(self._h)
+
+    def set_zero(self):
+        lib().oracle_cache_set_zero(self._h)
+
+    def add(self, other):
+        """SparseMatrixCache::operator+= (merge of a thread copy, MatrixCache.cpp:289-322)."""
+        lib().oracle_cache_add(self._h, other._h)
 
     def get_matrix(self):
         L = lib()

@@ -15,6 +15,8 @@
 namespace Eigen
 {
 	constexpr int Dynamic = -1;
+	template <typename S, int Opt, typename I>
+	class SparseMatrix; // mini_sparse.hpp
 
 	class Dense
 	{
@@ -34,6 +36,7 @@ namespace Eigen
 			d_.assign(size_t(r) * size_t(c), 0.0);
 		}
 		void setZero() { d_.assign(d_.size(), 0.0); }
+		void setZero(long r, long c) { resize(r, c); }
 
 		double &operator()(long i, long j) { return d_[size_t(j) * r_ + i]; }
 		double operator()(long i, long j) const { return d_[size_t(j) * r_ + i]; }
@@ -111,6 +114,7 @@ namespace Eigen
 			return s;
 		}
 		Dense &noalias() { return *this; }
+		SparseMatrix<double, 0, int> sparseView() const; // defined in mini_sparse.hpp
 		Dense &operator+=(const Dense &o)
 		{
 			assert(r_ == o.r_ && c_ == o.c_);

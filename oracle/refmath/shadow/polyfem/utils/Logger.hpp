@@ -1,0 +1,23 @@
+// shadow of polyfem/utils/Logger.hpp for oracle/refmath: a logger that discards everything
+#pragma once
+namespace polyfem
+{
+	struct NullLogger
+	{
+		template <typename... A>
+		void trace(A &&...) {}
+		template <typename... A>
+		void debug(A &&...) {}
+		template <typename... A>
+		void info(A &&...) {}
+		template <typename... A>
+		void warn(A &&...) {}
+		template <typename... A>
+		void error(A &&...) {}
+	};
+	inline NullLogger &logger()
+	{
+		static NullLogger l;
+		return l;
+	}
+} // namespace polyfem

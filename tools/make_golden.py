@@ -180,6 +180,19 @@ def write_nh_golden():
     print(f"wrote tests/golden/nh_local.npz ({k} cases)")
 
 
+def write_cache_golden():
+    """tests/golden/cache_sequences.npz: the matrices the reference's own SparseMatrixCache (utils/MatrixCache.cpp compiled
+    unmodified, oracle/_ref/libcacheref.so) returns for the call sequences of tests/test_oracle_cache_vs_reference.py."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import test_oracle_cache_vs_reference as T
+    mats = T.golden_sequences(T.RefCache, lambda c: c.get_matrix())
+    gold = {"n": len(mats)}
+    for k, (o, i, v) in enumerate(mats):
+        gold[f"outer_{k}"], gold[f"inner_{k}"], gold[f"values_{k}"] = o, i, v
+    np.savez_compressed(os.path.join(ROOT, "tests", "golden", "cache_sequences.npz"), **gold)
+    print(f"wrote tests/golden/cache_sequences.npz ({len(mats)} matrices)")
+
+
 def main():
     lib = load_ref()
     quad = {"source": "polyfem autogen/auto_tetrahedron.ipp via quadrature/TetQuadrature.cpp (weights /= 6)",
@@ -212,6 +225,7 @@ def main():
     np.savez_compressed(os.path.join(ROOT, "tests", "golden", "ref_tables.npz"), **gold)
     print("wrote tet_quadrature.json and tests/golden/ref_tables.npz")
     write_nh_golden()
+    write_cache_golden()
 
 
 if __name__ == "__main__":
