@@ -40,6 +40,19 @@ namespace Eigen
 
 		double &operator()(long i, long j) { return d_[size_t(j) * r_ + i]; }
 		double operator()(long i, long j) const { return d_[size_t(j) * r_ + i]; }
+		double &operator[](long i) { return d_[size_t(i)]; }
+		double operator[](long i) const { return d_[size_t(i)]; }
+		void conservativeResize(long n) // vectors
+		{
+			d_.resize(size_t(n));
+			if (c_ == 1 || r_ == 0)
+			{
+				r_ = int(n);
+				c_ = 1;
+			}
+			else
+				c_ = int(n);
+		}
 		double &operator()(long i) { return d_[size_t(i)]; } // vectors (and column-major linear access)
 		double operator()(long i) const { return d_[size_t(i)]; }
 

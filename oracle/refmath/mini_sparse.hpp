@@ -47,6 +47,7 @@ namespace Eigen
 		{
 			rows_ = r;
 			cols_ = c;
+			filled_ = -1;
 			outer_.assign(size_t(c) + 1, 0);
 			inner_.clear();
 			val_.clear();
@@ -70,6 +71,51 @@ namespace Eigen
 		const I *outerIndexPtr() const { return outer_.data(); }
 		const I *innerIndexPtr() const { return inner_.data(); }
 		const S *valuePtr() const { return val_.data(); }
+
+		// column-by-column construction (startVec / insertBack / finalize) and read-out (InnerIterator)
+		void reserve(long n)
+		{
+			inner_.reserve(size_t(n));
+			val_.reserve(size_t(n));
+		}
+		void startVec(long c)
+		{
+			for (long k = filled_ + 1; k <= c; ++k)
+				outer_[size_t(k)] = I(inner_.size());
+			filled_ = c;
+		}
+		S &insertBack(long r, long c)
+		{
+			assert(c == filled_);
+			inner_.push_back(I(r));
+			val_.push_back(S(0));
+			return val_.back();
+		}
+		void finalize()
+		{
+			for (long k = filled_ + 1; k <= cols_; ++k)
+				outer_[size_t(k)] = I(inner_.size());
+			filled_ = cols_;
+		}
+		class InnerIterator
+		{
+		public:
+			InnerIterator(const SparseMatrix &m, long c) : m_(m), k_(m.outer_[size_t(c)]), end_(m.outer_[size_t(c) + 1]), c_(c) {}
+			explicit operator bool() const { return k_ < end_; }
+			InnerIterator &operator++()
+			{
+				++k_;
+				return *this;
+			}
+			I row() const { return m_.inner_[size_t(k_)]; }
+			I col() const { return I(c_); }
+			S value() const { return m_.val_[size_t(k_)]; }
+
+		private:
+			const SparseMatrix &m_;
+			I k_, end_;
+			long c_;
+		};
 
 		template <typename It>
 		void setFromTriplets(It begin, It end)
@@ -144,7 +190,7 @@ namespace Eigen
 		std::vector<S> val_;
 
 	private:
-		long rows_ = 0, cols_ = 0;
+		long rows_ = 0, cols_ = 0, filled_ = -1;
 	};
 
 	template <typename S, int Opt, typename I>

@@ -193,6 +193,20 @@ def write_cache_golden():
     print(f"wrote tests/golden/cache_sequences.npz ({len(mats)} matrices)")
 
 
+def write_bc_golden():
+    """tests/golden/bc_projection.npz: not_constraints_, old_to_new_, projected gradient and projected CSC matrix from the
+    reference's own BCLagrangianForm code (oracle/_ref/libbcref.so) for the cases of tests/test_oracle_projection.py."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import test_oracle_projection as T
+    gold = {}
+    for k, (csc, constrained, grad) in enumerate(T.golden_cases()):
+        nc, o2n, g, (o, i, v) = T.reference_projection(csc, constrained, grad)
+        gold[f"nc_{k}"], gold[f"o2n_{k}"], gold[f"g_{k}"] = nc, o2n, g
+        gold[f"outer_{k}"], gold[f"inner_{k}"], gold[f"values_{k}"] = o, i, v
+    np.savez_compressed(os.path.join(ROOT, "tests", "golden", "bc_projection.npz"), **gold)
+    print("wrote tests/golden/bc_projection.npz")
+
+
 def main():
     lib = load_ref()
     quad = {"source": "polyfem autogen/auto_tetrahedron.ipp via quadrature/TetQuadrature.cpp (weights /= 6)",
@@ -226,6 +240,7 @@ def main():
     print("wrote tet_quadrature.json and tests/golden/ref_tables.npz")
     write_nh_golden()
     write_cache_golden()
+    write_bc_golden()
 
 
 if __name__ == "__main__":
