@@ -106,3 +106,35 @@ def test_live_reference_lib_if_present():
         mp, mw = tables.tet_quadrature(order)
         assert n == mw.size
         assert np.array_equal(pts[:n], mp) and np.array_equal(w[:n], mw)
+
+
+def test_quadrature_order_and_lame_conversion_against_reference_functions():
+    """AssemblerUtils::quadrature_order (AssemblerUtils.cpp:201-245) and convert_to_lambda / convert_to_mu
+    (utils/ElasticityUtils.cpp:12-23), compiled verbatim from /root/reference (oracle/_ref/libmiscref.so): the values
+    below were produced by those functions (tools/make_golden.py prints them) and are checked live where the library
+    exists."""
+    import ctypes
+    import os
+    from polyfem_b200 import mesh as M, tables
+    golden_orders = {("Mass", 1): 2, ("Mass", 2): 4, ("Mass", 3): 6, ("Mass", 4): 8,
+                     ("NeoHookean", 1): 1, ("NeoHookean", 2): 2, ("NeoHookean", 3): 4, ("NeoHookean", 4): 6,
+                     ("Laplacian", 1): 1, ("Laplacian", 4): 6, ("LinearElasticity", 2): 2}
+    for (name, p), order in golden_orders.items():
+        assert tables.quadrature_order(p, is_mass=(name == "Mass")) == order
+    lam, mu = M.lame_from_E_nu(1e5, 0.3)
+    assert (lam, mu) == (57692.30769230769, 38461.53846153846)  # bit for bit what the reference functions return
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref", "libmiscref.so")
+    if os.path.exists(path):
+        L = ctypes.CDLL(path)
+        L.ref_quadrature_order.argtypes = [ctypes.c_char_p, ctypes.c_int, ctypes.c_int, ctypes.c_int]
+        L.ref_convert_to_lambda.argtypes = [ctypes.c_int, ctypes.c_double, ctypes.c_double]
+        L.ref_convert_to_lambda.restype = ctypes.c_double
+        L.ref_convert_to_mu.argtypes = [ctypes.c_double, ctypes.c_double]
+        L.ref_convert_to_mu.restype = ctypes.c_double
+        for (name, p), order in golden_orders.items():
+            assert L.ref_quadrature_order(name.encode(), p, 0, 3) == order
+        rng = np.random.default_rng(5)
+        for _ in range(50):
+            E, nu = float(rng.uniform(1, 1e7)), float(rng.uniform(-0.9, 0.49))
+            lam, mu = M.lame_from_E_nu(E, nu)
+            assert lam == L.ref_convert_to_lambda(1, E, nu) and mu == L.ref_convert_to_mu(E, nu)
