@@ -16,11 +16,13 @@
  *     into oracle/_ref/libnhref.so; outputs committed as tests/golden/nh_local.npz; tests/test_oracle_reference_math.py).
  *   - LinearElasticity / Laplacian / Mass local blocks: PINNED the same way (LinearElasticity.cpp:29-63,
  *     Laplacian.cpp:13-26, Mass.cpp:5-23 compiled verbatim; golden blocks in tests/golden/nh_local.npz).
- *   - the global loops on multi-element meshes: the reference
- *     cannot be compiled here (Eigen, TBB, spdlog, ... are not vendored) and its tests for this
- *     path are property tests on a mesh from polyfem-data (absent). They are restated on the
- *     synthetic cube (closed form == autodiff 1e-12, NL Hessian == linear stiffness 1e-8,
- *     gradient/Hessian vs finite differences); numeric end-to-end values are UNPINNED.
+ *   - the global nonlinear loops NLAssembler::assemble_energy / assemble_gradient / assemble_hessian with their
+ *     per-thread storages (Assembler.cpp:16-94, 495-771): PINNED against the reference's own loop bodies compiled verbatim
+ *     over its own local functions and its unmodified MatrixCache.cpp (oracle/_ref/libloopref.so, multi-element meshes,
+ *     1 and 3 thread storages, tests/golden/nl_loops.npz, tests/test_oracle_loops_vs_reference.py).
+ *   - the global linear loop LinearAssembler::assemble (local blocks and placement rule pinned, the loop itself only by
+ *     properties: NL Hessian == linear stiffness 1e-8, symmetry, finite differences); the whole reference cannot be
+ *     compiled here (Eigen, TBB, spdlog, ... are not vendored).
  *   - project_to_psd (ipc-toolkit, source absent): UNPINNED, documented behaviour restated.
  *   - Mass (assembler/Mass.cpp:5-23): pinned by closed forms (P1 local mass rho*V/20*(1+delta_ij), total mass,
  *     stored zeros off the block diagonal; tests/test_oracle_mass.py) - the reference has no unit test for it.

@@ -127,6 +127,11 @@ namespace Eigen
 			return s;
 		}
 		Dense &noalias() { return *this; }
+		struct ArrayView // .array(): element-wise view, only the product of two views is used (Assembler.cpp:518)
+		{
+			const Dense &m;
+		};
+		ArrayView array() const { return ArrayView{*this}; }
 		SparseMatrix<double, 0, int> sparseView() const; // defined in mini_sparse.hpp
 		Dense &operator+=(const Dense &o)
 		{
@@ -265,6 +270,14 @@ namespace Eigen
 		return r;
 	}
 	inline Dense operator*(const Dense &a, double s) { return s * a; }
+	inline Dense operator*(const Dense::ArrayView &a, const Dense::ArrayView &b)
+	{
+		assert(a.m.size() == b.m.size());
+		Dense r(a.m.rows(), a.m.cols());
+		for (long k = 0; k < r.size(); ++k)
+			r(k) = a.m(k) * b.m(k);
+		return r;
+	}
 
 	template <typename S, int R, int C, int Opt = 0, int MR = R, int MC = C>
 	class Matrix : public Dense

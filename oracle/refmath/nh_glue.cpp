@@ -2,113 +2,7 @@
 // (assembler/NeoHookeanElasticity.cpp:419-658), extracted at build time into ../_ref/nh_extracted.inc and compiled
 // verbatim against mini_eigen.hpp. Used by tools/make_golden.py to write tests/golden/nh_local.npz and by
 // tests/test_oracle_reference_math.py to pin oracle/oracle.cpp's local math against the reference itself.
-#include "mini_eigen.hpp"
-
-#include <cmath>
-#include <vector>
-
-using std::log;
-
-namespace polyfem::utils
-{
-	// named (qualified) in the autodiff branch of compute_energy_aux, which is never instantiated here
-	template <typename M>
-	double determinant(const M &m) { return m.determinant(); }
-} // namespace polyfem::utils
-
-namespace polyfem::assembler
-{
-	// the few members of the reference types that the extracted functions touch
-	struct Local2Global // basis/Basis.hpp:21-38
-	{
-		int index;
-		double val;
-	};
-	struct AssemblyValues // assembler/AssemblyValues.hpp
-	{
-		std::vector<Local2Global> global;
-		Eigen::MatrixXd grad;     // n_qp x dim reference gradients
-		Eigen::MatrixXd grad_t_m; // n_qp x dim physical gradients (grad * jac_it)
-		Eigen::VectorXd val;      // n_qp basis values
-	};
-	struct QuadratureStub
-	{
-		Eigen::MatrixXd points;
-	};
-	struct ElementAssemblyValues // assembler/ElementAssemblyValues.hpp:12-61
-	{
-		std::vector<AssemblyValues> basis_values;
-		std::vector<Eigen::MatrixXd> jac_it;
-		QuadratureStub quadrature;
-		Eigen::MatrixXd val;
-		int element_id = 0;
-		Eigen::VectorXd eval_deformed_jacobian_determinant(const Eigen::MatrixXd &) const { return Eigen::VectorXd(); }
-	};
-	struct NonLinearAssemblerData // assembler/AssemblerData.hpp
-	{
-		const ElementAssemblyValues &vals;
-		double t;
-		double dt;
-		const Eigen::MatrixXd &x;
-		const Eigen::MatrixXd &x_prev;
-		const Eigen::VectorXd &da;
-	};
-	struct LameParameters // assembler/MatParams.hpp:83
-	{
-		double lambda = 0, mu = 0;
-		void lambda_mu(const Eigen::Dense &, const Eigen::Dense &, double, int, double &l, double &m) const
-		{
-			l = lambda;
-			m = mu;
-		}
-	};
-
-	struct LinearAssemblerData // assembler/AssemblerData.hpp
-	{
-		const ElementAssemblyValues &vals;
-		double t;
-		int i, j;
-		const Eigen::VectorXd &da;
-	};
-	struct Density // assembler/MatParams.hpp (call form of Mass.cpp:13)
-	{
-		double rho = 1;
-		double operator()(const Eigen::Dense &, const Eigen::Dense &, double, int) const { return rho; }
-	};
-	class LinearElasticity
-	{
-	public:
-		int size() const { return 3; }
-		LameParameters params_;
-		Eigen::Matrix<double, Eigen::Dynamic, 1, 0, 9, 1> assemble(const LinearAssemblerData &data) const;
-	};
-	class Laplacian
-	{
-	public:
-		int size() const { return 1; }
-		Eigen::Matrix<double, Eigen::Dynamic, 1, 0, 9, 1> assemble(const LinearAssemblerData &data) const;
-	};
-	class Mass
-	{
-	public:
-		int size() const { return 3; }
-		Density density_;
-		Eigen::Matrix<double, Eigen::Dynamic, 1, 0, 9, 1> assemble(const LinearAssemblerData &data) const;
-	};
-
-	class NeoHookeanElasticity
-	{
-	public:
-		int size() const { return 3; }
-		bool use_robust_jacobian = false;
-		LameParameters params_;
-		template <typename T, int n_basis, int dim>
-		T compute_energy_aux(const NonLinearAssemblerData &data) const;
-		template <int n_basis, int dim>
-		void compute_energy_aux_gradient_fast(const NonLinearAssemblerData &data, Eigen::Matrix<double, Eigen::Dynamic, 1> &G_flattened) const;
-		template <int n_basis, int dim>
-		void compute_energy_hessian_aux_fast(const NonLinearAssemblerData &data, Eigen::MatrixXd &H) const;
-	};
+#include "nh_harness.hpp" // opens namespace polyfem::assembler
 
 #include "../_ref/nh_extracted.inc"
 } // namespace polyfem::assembler

@@ -1,8 +1,33 @@
-// shadow of polyfem/utils/MaybeParallelFor.hpp for oracle/refmath: the serial form of maybe_parallel_for
-// (MaybeParallelFor.tpp:18-29 without TBB): one range, thread id 0
+// shadow of polyfem/utils/MaybeParallelFor.hpp for oracle/refmath: maybe_parallel_for without a thread pool
+// (MaybeParallelFor.tpp:18-29): the index range is cut into ref_thread_count() consecutive chunks that run one after
+// the other with thread ids 0, 1, ... - the per-thread storages and their serial merge are exercised, the run stays
+// deterministic. Default 1 chunk = the reference's serial build.
 #pragma once
+#include <algorithm>
+#include <vector>
 namespace polyfem::utils
 {
+	inline int &ref_thread_count()
+	{
+		static int n = 1;
+		return n;
+	}
 	template <typename F>
-	inline void maybe_parallel_for(int size, const F &f) { f(0, size, 0); }
+	inline void maybe_parallel_for(int size, const F &f)
+	{
+		const int chunks = std::max(1, std::min(ref_thread_count(), size));
+		for (int t = 0; t < chunks; ++t)
+			f(int(long(size) * t / chunks), int(long(size) * (t + 1) / chunks), t);
+	}
+	// create_thread_storage / get_local_thread_storage (MaybeParallelFor.hpp:30-60): one copy of the exemplar per thread
+	template <typename T>
+	inline std::vector<T> create_thread_storage(const T &exemplar)
+	{
+		return std::vector<T>(size_t(std::max(1, ref_thread_count())), exemplar);
+	}
+	template <typename S>
+	inline auto &get_local_thread_storage(S &storage, int thread_id)
+	{
+		return storage[size_t(thread_id)];
+	}
 } // namespace polyfem::utils

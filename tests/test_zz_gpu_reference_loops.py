@@ -1,0 +1,30 @@
+"""CUDA path vs tests/golden/nl_loops.npz: energy, gradient and CSC Hessian of small multi-element meshes as returned by
+the reference's OWN global loops NLAssembler::assemble_energy / assemble_gradient / assemble_hessian (Assembler.cpp:495-771,
+compiled from /root/reference over its own NeoHookean local functions and its unmodified MatrixCache.cpp; see
+tests/test_oracle_loops_vs_reference.py for how the golden is made). Pattern bit-exact; values within 1e-12 (north_star's
+tolerance, tests/helpers.py); NaN <=> NaN on the mesh with inverted elements."""
+import os
+
+import numpy as np
+import pytest
+
+from helpers import REL_TOL, assert_values_close, assert_vector_close, gpu_handle
+from test_oracle_loops_vs_reference import GOLD_PATH, loop_cases
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("k", range(4))
+def test_cuda_path_equals_reference_global_loops(k):
+    G = np.load(GOLD_PATH)
+    name, mesh, x = loop_cases()[k]
+    assert np.array_equal(G[f"x_{name}"], x), "golden inputs are stale: rerun tools/make_golden.py"
+    h = gpu_handle(mesh, "NeoHookean")
+    outer, inner = h.pattern()
+    assert outer.tobytes() == G[f"outer_{name}"].astype(outer.dtype).tobytes()
+    assert inner.tobytes() == G[f"inner_{name}"].astype(inner.dtype).tobytes()
+    e_ref, g_ref, v_ref = float(G[f"energy_{name}_t1"]), G[f"gradient_{name}_t1"], G[f"values_{name}_t1"]
+    for e, g, v in (h.grad_hess(x), (h.energy(x), h.gradient(x), h.hessian(x))):
+        assert np.isnan(e) == np.isnan(e_ref) and (np.isnan(e_ref) or abs(e - e_ref) <= REL_TOL * abs(e_ref))
+        assert_vector_close(g, g_ref)
+        assert_values_close(outer, inner, v, v_ref)

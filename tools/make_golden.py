@@ -207,7 +207,30 @@ def write_bc_golden():
     print("wrote tests/golden/bc_projection.npz")
 
 
+def write_loop_golden():
+    """tests/golden/nl_loops.npz: energy, gradient and CSC Hessian of small multi-element meshes from the reference's own
+    global loops NLAssembler::assemble_* (oracle/_ref/libloopref.so) with 1 and 3 per-thread storages."""
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import test_oracle_loops_vs_reference as T
+    from oracle import pyoracle
+    pyoracle.build()
+    gold = {}
+    for name, mesh, x in T.loop_cases():
+        gold[f"x_{name}"] = x
+        for t in T.THREADS:
+            e, g, o, i, v = T.reference_loops(pyoracle, mesh, x, t)
+            gold[f"energy_{name}_t{t}"], gold[f"gradient_{name}_t{t}"], gold[f"values_{name}_t{t}"] = e, g, v
+            if f"outer_{name}" in gold:
+                assert np.array_equal(o, gold[f"outer_{name}"]) and np.array_equal(i, gold[f"inner_{name}"])
+            gold[f"outer_{name}"], gold[f"inner_{name}"] = o, i
+    np.savez_compressed(os.path.join(ROOT, "tests", "golden", "nl_loops.npz"), **gold)
+    print("wrote tests/golden/nl_loops.npz")
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "loops":
+        return write_loop_golden()
     lib = load_ref()
     quad = {"source": "polyfem autogen/auto_tetrahedron.ipp via quadrature/TetQuadrature.cpp (weights /= 6)",
             "orders": {}}
@@ -241,6 +264,7 @@ def main():
     write_nh_golden()
     write_cache_golden()
     write_bc_golden()
+    write_loop_golden()
 
 
 if __name__ == "__main__":
