@@ -289,6 +289,8 @@ namespace Eigen
 		template <typename I, typename = std::enable_if_t<std::is_integral_v<I>>>
 		explicit Matrix(I n) : Dense(C == 1 ? long(n) : 1, C == 1 ? 1 : long(n)) {}
 		Matrix(const Dense &o) : Dense(o) {}
+		template <typename S2, int O2, typename I2>
+		Matrix(const SparseMatrix<S2, O2, I2> &sp); // dense copy of a sparse matrix, defined in mini_sparse.hpp
 		Matrix &operator=(const Dense &o)
 		{
 			Dense::operator=(o);

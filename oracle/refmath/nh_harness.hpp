@@ -74,33 +74,14 @@ namespace polyfem::assembler
 		double t;
 		int i, j;
 		const Eigen::VectorXd &da;
+		LinearAssemblerData(const ElementAssemblyValues &vals_, double t_, int i_, int j_, const Eigen::VectorXd &da_)
+			: vals(vals_), t(t_), i(i_), j(j_), da(da_) {}
 	};
 	struct Density // assembler/MatParams.hpp (call form of Mass.cpp:13)
 	{
 		double rho = 1;
 		double operator()(const Eigen::Dense &, const Eigen::Dense &, double, int) const { return rho; }
 	};
-	class LinearElasticity
-	{
-	public:
-		int size() const { return 3; }
-		LameParameters params_;
-		Eigen::Matrix<double, Eigen::Dynamic, 1, 0, 9, 1> assemble(const LinearAssemblerData &data) const;
-	};
-	class Laplacian
-	{
-	public:
-		int size() const { return 1; }
-		Eigen::Matrix<double, Eigen::Dynamic, 1, 0, 9, 1> assemble(const LinearAssemblerData &data) const;
-	};
-	class Mass
-	{
-	public:
-		int size() const { return 3; }
-		Density density_;
-		Eigen::Matrix<double, Eigen::Dynamic, 1, 0, 9, 1> assemble(const LinearAssemblerData &data) const;
-	};
-
 #ifdef PFREF_LOOPS
 	// loop_glue.cpp (which has included the reference's utils/MatrixCache.hpp): what the global loops of
 	// NLAssembler (Assembler.cpp:495-771) name besides the types above
@@ -139,6 +120,8 @@ namespace polyfem::assembler
 	{
 	public:
 		std::vector<ElementAssemblyValues> cache;
+		bool is_mass_ = false;
+		bool is_mass() const { return is_mass_; }
 		void compute(const int el_index, const bool, const basis::ElementBases &, const basis::ElementBases &, ElementAssemblyValues &vals) const
 		{
 			vals = cache[size_t(el_index)];
@@ -165,10 +148,50 @@ namespace polyfem::assembler
 		virtual Eigen::VectorXd assemble_gradient(const NonLinearAssemblerData &data) const = 0;
 		virtual Eigen::MatrixXd assemble_hessian(const NonLinearAssemblerData &data) const = 0;
 	};
+	class LinearAssembler // assembler/Assembler.hpp:120-170: the members the linear loop uses
+	{
+	public:
+		virtual ~LinearAssembler() = default;
+		virtual int size() const = 0;
+		void assemble(const bool is_volume, const int n_basis, const std::vector<basis::ElementBases> &bases,
+					  const std::vector<basis::ElementBases> &gbases, const AssemblyValsCache &cache, const double t,
+					  StiffnessMatrix &stiffness, const bool is_mass = false) const;
+		virtual Eigen::Matrix<double, Eigen::Dynamic, 1, 0, 9, 1> assemble(const LinearAssemblerData &data) const = 0;
+	};
 #define PFREF_NL_BASE : public NLAssembler
+#define PFREF_LIN_BASE : public LinearAssembler
+#define PFREF_LIN_USING using LinearAssembler::assemble;
+#define PFREF_OVERRIDE override
 #else
 #define PFREF_NL_BASE
+#define PFREF_LIN_BASE
+#define PFREF_LIN_USING
+#define PFREF_OVERRIDE
 #endif
+	class LinearElasticity PFREF_LIN_BASE
+	{
+	public:
+		PFREF_LIN_USING
+		int size() const { return 3; }
+		LameParameters params_;
+		Eigen::Matrix<double, Eigen::Dynamic, 1, 0, 9, 1> assemble(const LinearAssemblerData &data) const PFREF_OVERRIDE;
+	};
+	class Laplacian PFREF_LIN_BASE
+	{
+	public:
+		PFREF_LIN_USING
+		int size() const { return 1; }
+		Eigen::Matrix<double, Eigen::Dynamic, 1, 0, 9, 1> assemble(const LinearAssemblerData &data) const PFREF_OVERRIDE;
+	};
+	class Mass PFREF_LIN_BASE
+	{
+	public:
+		PFREF_LIN_USING
+		int size() const { return 3; }
+		Density density_;
+		Eigen::Matrix<double, Eigen::Dynamic, 1, 0, 9, 1> assemble(const LinearAssemblerData &data) const PFREF_OVERRIDE;
+	};
+
 	class NeoHookeanElasticity PFREF_NL_BASE
 	{
 	public:

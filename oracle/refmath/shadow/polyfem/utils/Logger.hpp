@@ -1,5 +1,7 @@
 // shadow of polyfem/utils/Logger.hpp for oracle/refmath: a logger that discards everything
 #pragma once
+#include <stdexcept>
+#include <string>
 namespace polyfem
 {
 	struct NullLogger
@@ -19,5 +21,10 @@ namespace polyfem
 	{
 		static NullLogger l;
 		return l;
+	}
+	template <typename... A>
+	[[noreturn]] inline void log_and_throw_error(const std::string &msg, A &&...)
+	{
+		throw std::runtime_error(msg);
 	}
 } // namespace polyfem

@@ -4,7 +4,9 @@
 per-thread storage classes (assembler/Assembler.cpp:16-94, 495-531, 574-643, 645-771) verbatim from /root/reference, over
 the reference's own NeoHookean local functions and its utils/MatrixCache.cpp compiled unmodified, into
 oracle/_ref/libloopref.so. `tools/make_golden.py` ran them on the meshes of `loop_cases()` with 1 and 3 thread storages
-and committed the results as tests/golden/nl_loops.npz, which is what travels to the GPU box.
+and committed the results as tests/golden/nl_loops.npz, which is what travels to the GPU box. The linear loop
+LinearAssembler::assemble (Assembler.cpp:157-384) is compiled the same way over the reference's own LinearElasticity /
+Laplacian / Mass local functions: `linear_cases()` -> tests/golden/linear_loops.npz.
 
 Checked: the CSC pattern (outer, inner) is identical; energy, gradient and values agree to 1e-13 of the largest entry
 (the oracle and the reference cut the element range into different per-thread chunks, so sums are ordered differently);
@@ -85,6 +87,58 @@ def reference_loops(oracle, mesh, x, threads):
     return energy, grad, outer, inner, values
 
 
+LINEAR_GOLD_PATH = os.path.join(ROOT, "tests", "golden", "linear_loops.npz")
+LINEAR_IDS = {"LinearElasticity": 0, "Laplacian": 1, "Mass": 2}
+RHO = 1000.0
+
+
+def linear_cases():
+    """(name, material, mesh): the global linear loop LinearAssembler::assemble (Assembler.cpp:157-384) on jittered cubes."""
+    out = []
+    for material, p, n in (("LinearElasticity", 1, 3), ("LinearElasticity", 2, 2), ("Laplacian", 2, 2), ("Laplacian", 3, 1),
+                           ("Mass", 1, 3), ("Mass", 2, 1)):
+        out.append((f"{material}_p{p}", material, M.kuhn_cube(n, p, jitter=0.2)))
+    return out
+
+
+def reference_linear_loop(oracle, material, mesh, threads):
+    """Run the reference's own linear loop (build container only): (outer, inner, values) of the stiffness / mass matrix."""
+    lib = ctypes.CDLL(LIB_PATH)
+    dp, ip, vp = ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_int), ctypes.c_void_p
+    lib.refloop_linear_new.restype = vp
+    lib.refloop_linear_new.argtypes = [ctypes.c_int] * 5 + [ip, dp, dp, dp, dp, ctypes.c_double, ctypes.c_double, ctypes.c_double]
+    lib.refloop_free.argtypes = [vp]
+    lib.refloop_linear_assemble.restype = ctypes.c_long
+    lib.refloop_linear_assemble.argtypes = [vp, ctypes.c_int]
+    lib.refloop_cols.argtypes = [vp]
+    for name, rt in (("refloop_outer", ip), ("refloop_inner", ip), ("refloop_values", dp)):
+        getattr(lib, name).restype = rt
+        getattr(lib, name).argtypes = [vp]
+
+    prob = oracle.problem_from_mesh(mesh, material, rho=RHO)
+    is_mass = material == "Mass"
+    t = tables.reference_tables(mesh.p, tables.quadrature_order(mesh.p, is_mass=True) if is_mass else None)
+    ne, nl, nq = mesh.n_elements, mesh.conn.shape[1], t["weights"].size
+    det, gtm = np.zeros((ne, nq)), np.zeros((ne, nq, nl, 3))
+    for e in range(ne):
+        det[e], _, gtm[e] = prob.assembly_values(e)  # pinned against finalize3d by tests/test_oracle_reference_math.py
+    conn = np.ascontiguousarray(mesh.conn, dtype=np.int32)
+    w = np.ascontiguousarray(t["weights"])
+    vals = np.ascontiguousarray(t["val"]) if is_mass else None
+    lam, mu = M.lame_from_E_nu(1e5, 0.3)
+    h = lib.refloop_linear_new(LINEAR_IDS[material], ne, nl, nq, mesh.n_bases, _ptr(conn, ctypes.c_int), None if is_mass else _ptr(gtm),
+                               _ptr(vals) if is_mass else None, _ptr(det), _ptr(w), lam, mu, RHO)
+    try:
+        nnz = lib.refloop_linear_assemble(h, threads)
+        cols = lib.refloop_cols(h)
+        outer = np.ctypeslib.as_array(lib.refloop_outer(h), shape=(cols + 1,)).copy()
+        inner = np.ctypeslib.as_array(lib.refloop_inner(h), shape=(nnz,)).copy()
+        values = np.ctypeslib.as_array(lib.refloop_values(h), shape=(nnz,)).copy()
+    finally:
+        lib.refloop_free(h)
+    return outer, inner, values
+
+
 def golden():
     if not os.path.exists(GOLD_PATH):
         pytest.skip("tests/golden/nl_loops.npz missing (run tools/make_golden.py where the reference tree is mounted)")
@@ -138,3 +192,29 @@ def test_live_reference_loops_reproduce_the_golden(oracle):
             for a, b in ((v, G[f"values_{name}_t{t}"]), (g, G[f"gradient_{name}_t{t}"]),
                          (np.array([e]), np.array([float(G[f"energy_{name}_t{t}"])]))):
                 assert np.array_equal(a, b, equal_nan=True)
+
+
+@pytest.mark.parametrize("k", range(6))
+@pytest.mark.parametrize("n_threads", (1, 4))
+def test_oracle_linear_assembly_equals_reference_loop(oracle, k, n_threads):
+    """LinearAssembler::assemble: pattern identical (incl. the stored zeros of Mass off its block diagonal), values 1e-13."""
+    if not os.path.exists(LINEAR_GOLD_PATH):
+        pytest.skip("tests/golden/linear_loops.npz missing")
+    G = np.load(LINEAR_GOLD_PATH)
+    name, material, mesh = linear_cases()[k]
+    assert np.array_equal(G[f"vertices_{name}"], mesh.vertices), "golden inputs are stale: rerun tools/make_golden.py"
+    K = oracle.problem_from_mesh(mesh, material, rho=RHO, n_threads=n_threads).assemble()
+    assert np.array_equal(K.outer, G[f"outer_{name}"]) and np.array_equal(K.inner, G[f"inner_{name}"])
+    close(K.values, G[f"values_{name}"])
+
+
+def test_live_reference_linear_loop_reproduces_the_golden(oracle):
+    if not os.path.exists(LIB_PATH):
+        pytest.skip("oracle/_ref/libloopref.so not built (no reference tree)")
+    G = np.load(LINEAR_GOLD_PATH)
+    for name, material, mesh in linear_cases():
+        o, i, v = reference_linear_loop(oracle, material, mesh, 1)
+        assert np.array_equal(o, G[f"outer_{name}"]) and np.array_equal(i, G[f"inner_{name}"]) and np.array_equal(v, G[f"values_{name}"])
+        o3, i3, v3 = reference_linear_loop(oracle, material, mesh, 3)  # 3 thread storages: same pattern, merge order differs
+        assert np.array_equal(o, o3) and np.array_equal(i, i3)
+        close(v3, v)

@@ -28,3 +28,23 @@ def test_cuda_path_equals_reference_global_loops(k):
         assert np.isnan(e) == np.isnan(e_ref) and (np.isnan(e_ref) or abs(e - e_ref) <= REL_TOL * abs(e_ref))
         assert_vector_close(g, g_ref)
         assert_values_close(outer, inner, v, v_ref)
+
+
+@pytest.mark.parametrize("k", range(6))
+def test_cuda_path_equals_reference_linear_loop(k):
+    """pfa_linear_stiffness vs tests/golden/linear_loops.npz: the matrix the reference's own LinearAssembler::assemble
+    (Assembler.cpp:157-384) builds from its own LinearElasticity / Laplacian / Mass local blocks."""
+    from polyfem_b200 import capi, tables
+    from test_oracle_loops_vs_reference import LINEAR_GOLD_PATH, RHO, linear_cases
+    G = np.load(LINEAR_GOLD_PATH)
+    name, material, mesh = linear_cases()[k]
+    assert np.array_equal(G[f"vertices_{name}"], mesh.vertices), "golden inputs are stale: rerun tools/make_golden.py"
+    if material == "Mass":
+        t = tables.reference_tables(mesh.p, tables.quadrature_order(mesh.p, is_mass=True))
+        h = capi.Handle("Mass", mesh.conn, mesh.n_bases, t["weights"], None, vertices=mesh.vertices, ref_vals=t["val"], density=RHO)
+    else:
+        h = gpu_handle(mesh, material)
+    outer, inner = h.pattern()
+    assert outer.tobytes() == G[f"outer_{name}"].astype(outer.dtype).tobytes()
+    assert inner.tobytes() == G[f"inner_{name}"].astype(inner.dtype).tobytes()
+    assert_values_close(outer, inner, h.linear_stiffness(), G[f"values_{name}"], what=name)

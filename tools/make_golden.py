@@ -226,6 +226,12 @@ def write_loop_golden():
             gold[f"outer_{name}"], gold[f"inner_{name}"] = o, i
     np.savez_compressed(os.path.join(ROOT, "tests", "golden", "nl_loops.npz"), **gold)
     print("wrote tests/golden/nl_loops.npz")
+    gold = {}
+    for name, material, mesh in T.linear_cases():
+        gold[f"vertices_{name}"] = mesh.vertices
+        gold[f"outer_{name}"], gold[f"inner_{name}"], gold[f"values_{name}"] = T.reference_linear_loop(pyoracle, material, mesh, 1)
+    np.savez_compressed(os.path.join(ROOT, "tests", "golden", "linear_loops.npz"), **gold)
+    print("wrote tests/golden/linear_loops.npz")
 
 
 def main():
