@@ -16,13 +16,13 @@
  *     into oracle/_ref/libnhref.so; outputs committed as tests/golden/nh_local.npz; tests/test_oracle_reference_math.py).
  *   - LinearElasticity / Laplacian / Mass local blocks: PINNED the same way (LinearElasticity.cpp:29-63,
  *     Laplacian.cpp:13-26, Mass.cpp:5-23 compiled verbatim; golden blocks in tests/golden/nh_local.npz).
- *   - the global nonlinear loops NLAssembler::assemble_energy / assemble_gradient / assemble_hessian with their
+ *   - the global nonlinear loops NLAssembler::assemble_energy / _per_element / assemble_gradient / assemble_hessian with their
  *     per-thread storages (Assembler.cpp:16-94, 495-771): PINNED against the reference's own loop bodies compiled verbatim
  *     over its own local functions and its unmodified MatrixCache.cpp (oracle/_ref/libloopref.so, multi-element meshes,
  *     1 and 3 thread storages, tests/golden/nl_loops.npz, tests/test_oracle_loops_vs_reference.py).
  *   - the global linear loop LinearAssembler::assemble (Assembler.cpp:157-384): PINNED the same way over the reference's
  *     own LinearElasticity / Laplacian / Mass local functions (tests/golden/linear_loops.npz).
- *   - assemble_energy_per_element and the NL path of LinearElasticity (autodiff in the reference): property-pinned only
+ *   - the NL path of LinearElasticity (autodiff in the reference): property-pinned only
  *     (closed form == autodiff 1e-12, NL Hessian == linear stiffness 1e-8, finite differences); the whole reference
  *     cannot be compiled here (Eigen, TBB, spdlog, ... are not vendored).
  *   - project_to_psd (ipc-toolkit, source absent): UNPINNED, documented behaviour restated.

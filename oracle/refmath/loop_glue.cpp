@@ -103,6 +103,15 @@ extern "C"
 		polyfem::utils::ref_thread_count() = 1;
 		return e;
 	}
+	void refloop_energy_per_element(refloop *r, const double *x, int threads, double *out)
+	{
+		polyfem::utils::ref_thread_count() = threads;
+		const Eigen::MatrixXd d = column(x, long(r->n_bases) * 3), prev;
+		const Eigen::VectorXd v = r->nh.assemble_energy_per_element(true, r->bases, r->bases, r->vals, 0.0, 1.0, d, prev);
+		polyfem::utils::ref_thread_count() = 1;
+		for (long k = 0; k < v.size(); ++k)
+			out[k] = v(k);
+	}
 	void refloop_gradient(refloop *r, const double *x, int threads, double *out)
 	{
 		polyfem::utils::ref_thread_count() = threads;

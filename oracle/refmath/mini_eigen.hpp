@@ -111,6 +111,13 @@ namespace Eigen
 			}
 			return inv;
 		}
+		double sum() const
+		{
+			double s = 0;
+			for (double v : d_)
+				s += v;
+			return s;
+		}
 		double squaredNorm() const
 		{
 			double s = 0;

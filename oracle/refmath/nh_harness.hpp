@@ -135,6 +135,9 @@ namespace polyfem::assembler
 		double assemble_energy(const bool is_volume, const std::vector<basis::ElementBases> &bases, const std::vector<basis::ElementBases> &gbases,
 							   const AssemblyValsCache &cache, const double t, const double dt, const Eigen::MatrixXd &displacement,
 							   const Eigen::MatrixXd &displacement_prev) const;
+		Eigen::VectorXd assemble_energy_per_element(const bool is_volume, const std::vector<basis::ElementBases> &bases,
+													const std::vector<basis::ElementBases> &gbases, const AssemblyValsCache &cache, const double t,
+													const double dt, const Eigen::MatrixXd &displacement, const Eigen::MatrixXd &displacement_prev) const;
 		void assemble_gradient(const bool is_volume, const int n_basis, const std::vector<basis::ElementBases> &bases,
 							   const std::vector<basis::ElementBases> &gbases, const AssemblyValsCache &cache, const double t, const double dt,
 							   const Eigen::MatrixXd &displacement, const Eigen::MatrixXd &displacement_prev, Eigen::MatrixXd &rhs) const;

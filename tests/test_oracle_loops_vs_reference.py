@@ -41,7 +41,8 @@ def _ptr(a, t=ctypes.c_double):
 
 
 def reference_loops(oracle, mesh, x, threads):
-    """Run the reference's own loops (build container only): (energy, gradient, outer, inner, values). A second
+    """Run the reference's own loops (build container only): (energy, gradient, outer, inner, values, energy per
+    element [all NaN where the total is NaN: not run]). A second
     assemble_hessian through the same matrix cache must reproduce pattern and values bit for bit."""
     lib = ctypes.CDLL(LIB_PATH)
     dp, ip, vp = ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_int), ctypes.c_void_p
@@ -51,6 +52,7 @@ def reference_loops(oracle, mesh, x, threads):
     lib.refloop_energy.restype = ctypes.c_double
     lib.refloop_energy.argtypes = [vp, dp, ctypes.c_int]
     lib.refloop_gradient.argtypes = [vp, dp, ctypes.c_int, dp]
+    lib.refloop_energy_per_element.argtypes = [vp, dp, ctypes.c_int, dp]
     lib.refloop_hessian.restype = ctypes.c_long
     lib.refloop_hessian.argtypes = [vp, dp, ctypes.c_int]
     for name, rt in (("refloop_outer", ip), ("refloop_inner", ip), ("refloop_values", dp)):
@@ -73,6 +75,9 @@ def reference_loops(oracle, mesh, x, threads):
         energy = lib.refloop_energy(h, _ptr(x), threads)
         grad = np.zeros(mesh.n_bases * 3)
         lib.refloop_gradient(h, _ptr(x), threads, _ptr(grad))
+        epe = np.full(ne, np.nan)
+        if np.isfinite(energy):  # with a NaN energy the reference's own debug assert (Assembler.cpp:565-569) aborts
+            lib.refloop_energy_per_element(h, _ptr(x), threads, _ptr(epe))
         nnz = lib.refloop_hessian(h, _ptr(x), threads)
         outer = np.ctypeslib.as_array(lib.refloop_outer(h), shape=(mesh.n_bases * 3 + 1,)).copy()
         inner = np.ctypeslib.as_array(lib.refloop_inner(h), shape=(nnz,)).copy()
@@ -84,7 +89,7 @@ def reference_loops(oracle, mesh, x, threads):
         assert np.array_equal(inner, np.ctypeslib.as_array(lib.refloop_inner(h), shape=(nnz,)))
     finally:
         lib.refloop_free(h)
-    return energy, grad, outer, inner, values
+    return energy, grad, outer, inner, values, epe
 
 
 LINEAR_GOLD_PATH = os.path.join(ROOT, "tests", "golden", "linear_loops.npz")
@@ -169,6 +174,8 @@ def test_oracle_global_assembly_equals_reference_loops(oracle, k, n_threads):
     for t in THREADS:
         close(prob.assemble_gradient(x), G[f"gradient_{name}_t{t}"])
         close([prob.assemble_energy(x)], [float(G[f"energy_{name}_t{t}"])])
+    if np.isfinite(float(G[f"energy_{name}_t1"])):
+        close(prob.assemble_energy_per_element(x), G[f"energy_per_element_{name}"])
 
 
 def test_golden_covers_nan_and_thread_merge():
@@ -187,7 +194,8 @@ def test_live_reference_loops_reproduce_the_golden(oracle):
     G = golden()
     for name, mesh, x in loop_cases():
         for t in THREADS:
-            e, g, o, i, v = reference_loops(oracle, mesh, x, t)
+            e, g, o, i, v, epe = reference_loops(oracle, mesh, x, t)
+            assert np.array_equal(epe, G[f"energy_per_element_{name}"], equal_nan=True)
             assert np.array_equal(o, G[f"outer_{name}"]) and np.array_equal(i, G[f"inner_{name}"])
             for a, b in ((v, G[f"values_{name}_t{t}"]), (g, G[f"gradient_{name}_t{t}"]),
                          (np.array([e]), np.array([float(G[f"energy_{name}_t{t}"])]))):

@@ -28,6 +28,9 @@ def test_cuda_path_equals_reference_global_loops(k):
         assert np.isnan(e) == np.isnan(e_ref) and (np.isnan(e_ref) or abs(e - e_ref) <= REL_TOL * abs(e_ref))
         assert_vector_close(g, g_ref)
         assert_values_close(outer, inner, v, v_ref)
+    if np.isfinite(e_ref):  # assemble_energy_per_element (Assembler.cpp:533-572)
+        epe_ref = G[f"energy_per_element_{name}"]
+        assert np.abs(h.energy_per_element(x) - epe_ref).max() <= REL_TOL * np.abs(epe_ref).max()
 
 
 @pytest.mark.parametrize("k", range(6))

@@ -219,7 +219,8 @@ def write_loop_golden():
     for name, mesh, x in T.loop_cases():
         gold[f"x_{name}"] = x
         for t in T.THREADS:
-            e, g, o, i, v = T.reference_loops(pyoracle, mesh, x, t)
+            e, g, o, i, v, epe = T.reference_loops(pyoracle, mesh, x, t)
+            gold[f"energy_per_element_{name}"] = epe  # does not depend on the number of storages
             gold[f"energy_{name}_t{t}"], gold[f"gradient_{name}_t{t}"], gold[f"values_{name}_t{t}"] = e, g, v
             if f"outer_{name}" in gold:
                 assert np.array_equal(o, gold[f"outer_{name}"]) and np.array_equal(i, gold[f"inner_{name}"])
