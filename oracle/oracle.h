@@ -22,9 +22,10 @@
  *     1 and 3 thread storages, tests/golden/nl_loops.npz, tests/test_oracle_loops_vs_reference.py).
  *   - the global linear loop LinearAssembler::assemble (Assembler.cpp:157-384): PINNED the same way over the reference's
  *     own LinearElasticity / Laplacian / Mass local functions (tests/golden/linear_loops.npz).
- *   - the NL path of LinearElasticity (autodiff in the reference): property-pinned only
- *     (closed form == autodiff 1e-12, NL Hessian == linear stiffness 1e-8, finite differences); the whole reference
- *     cannot be compiled here (Eigen, TBB, spdlog, ... are not vendored).
+ *   - the NL path of LinearElasticity: energy PINNED against the reference's own compute_energy_aux<double>
+ *     (LinearElasticity.cpp:103-132, tests/golden/le_energy.npz); gradient / Hessian are autodiff of that function in the
+ *     reference (not compilable here) and property-pinned: closed form == autodiff 1e-12, Hessian == pinned linear
+ *     stiffness 1e-8, finite differences.
  *   - project_to_psd (ipc-toolkit, source absent): UNPINNED, documented behaviour restated.
  *   - Mass (assembler/Mass.cpp:5-23): pinned by closed forms (P1 local mass rho*V/20*(1+delta_ij), total mass,
  *     stored zeros off the block diagonal; tests/test_oracle_mass.py) - the reference has no unit test for it.

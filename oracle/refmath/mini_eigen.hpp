@@ -277,6 +277,13 @@ namespace Eigen
 		return r;
 	}
 	inline Dense operator*(const Dense &a, double s) { return s * a; }
+	inline Dense operator/(const Dense &a, double s)
+	{
+		Dense r(a.rows(), a.cols());
+		for (long k = 0; k < r.size(); ++k)
+			r(k) = a(k) / s;
+		return r;
+	}
 	inline Dense operator*(const Dense::ArrayView &a, const Dense::ArrayView &b)
 	{
 		assert(a.m.size() == b.m.size());
@@ -290,6 +297,7 @@ namespace Eigen
 	class Matrix : public Dense
 	{
 	public:
+		typedef S Scalar;
 		Matrix() : Dense(R == Dynamic ? 0 : R, C == Dynamic ? 0 : C) {}
 		template <typename I, typename J, typename = std::enable_if_t<std::is_integral_v<I> && std::is_integral_v<J>>>
 		Matrix(I r, J c) : Dense(long(r), long(c)) {}

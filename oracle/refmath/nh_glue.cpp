@@ -7,6 +7,29 @@
 #include "../_ref/nh_extracted.inc"
 } // namespace polyfem::assembler
 
+namespace polyfem
+{
+	// what utils/ElasticityUtils.hpp:70-136 names from utils/AutodiffTypes.hpp, for T = double
+	struct DiffScalarBase
+	{
+		static void setVariableCount(long) {}
+	};
+	template <typename T>
+	class AutoDiffAllocator;
+	template <>
+	class AutoDiffAllocator<double> // utils/AutodiffTypes.hpp: the double specialisation returns the value
+	{
+	public:
+		double operator()(const int, double v) const { return v; }
+	};
+#include "../_ref/elutil_extracted.inc"
+} // namespace polyfem
+
+namespace polyfem::assembler
+{
+#include "../_ref/le_energy_extracted.inc"
+} // namespace polyfem::assembler
+
 using namespace polyfem::assembler;
 
 namespace
@@ -119,6 +142,20 @@ extern "C"
 		for (long r = 0; r < N; ++r)
 			for (long c = 0; c < N; ++c)
 				out[r * N + c] = H(r, c);
+		return 0;
+	}
+
+	// LinearElasticity::compute_energy -> compute_energy_aux<double> (LinearElasticity.cpp:65-68, 103-132): the energy of a
+	// linear material inside a nonlinear solve, same inputs as ref_nh_energy
+	int ref_le_energy(int n_basis, int n_qp, const double *u, const double *grads, const double *jac_it, const double *da, double lambda, double mu, double *out)
+	{
+		Inputs in;
+		fill(in, n_basis, n_qp, u, grads, jac_it, da);
+		LinearElasticity le;
+		le.params_.lambda = lambda;
+		le.params_.mu = mu;
+		const NonLinearAssemblerData data{in.vals, 0.0, 1.0, in.x, in.x_prev, in.da};
+		*out = le.compute_energy_aux<double>(data);
 		return 0;
 	}
 

@@ -178,6 +178,8 @@ namespace polyfem::assembler
 		int size() const { return 3; }
 		LameParameters params_;
 		Eigen::Matrix<double, Eigen::Dynamic, 1, 0, 9, 1> assemble(const LinearAssemblerData &data) const PFREF_OVERRIDE;
+		template <typename T>
+		T compute_energy_aux(const NonLinearAssemblerData &data) const; // LinearElasticity.cpp:103-132
 	};
 	class Laplacian PFREF_LIN_BASE
 	{

@@ -148,3 +148,26 @@ def test_geometry_equals_reference_finalize3d(oracle, p):
     edges = verts[1:] - verts[0]
     assert np.abs(np.linalg.inv(edges).T - GOLD[f"geo_jac_it_p{p}"][0]).max() <= 1e-12 * np.abs(GOLD[f"geo_jac_it_p{p}"][0]).max()
     assert abs(np.linalg.det(edges) - GOLD[f"geo_det_p{p}"][0]) <= 1e-13 * abs(GOLD[f"geo_det_p{p}"][0])
+
+
+@pytest.mark.parametrize("k", cases())
+def test_linear_elasticity_energy_in_a_nonlinear_solve_equals_reference_function(oracle, k):
+    """LinearElasticity::compute_energy -> compute_energy_aux<double> (LinearElasticity.cpp:65-68, 103-132, with get_local_disp /
+    compute_disp_grad_at_quad of utils/ElasticityUtils.hpp:70-136, all compiled verbatim) against the oracle's energy of the
+    linear material on the same one-element meshes; and E = 1/2 u^T K u with the pinned stiffness, the closed form the
+    CUDA path evaluates. The gradient of this path is autodiff of the same function in the reference (exact derivative):
+    g = K u is checked against it by finite differences in tests/test_oracle_properties.py."""
+    LE = np.load(os.path.join(ROOT, "tests", "golden", "le_energy.npz"))
+    p = int(GOLD[f"p_{k}"])
+    t = tables.reference_tables(p)
+    verts, u = GOLD[f"vertices_{k}"], GOLD[f"u_{k}"]
+    nl = u.shape[0]
+    conn = np.arange(nl, dtype=np.int32)[None, :]
+    prob = oracle.OracleProblem("LinearElasticity", conn, verts[None], nl, t["points"], t["weights"], t["grad"],
+                                lam=float(GOLD["lambda"]), mu=float(GOLD["mu"]))
+    e_ref = float(LE[f"le_energy_{k}"])
+    x = u.reshape(-1)
+    assert np.isfinite(e_ref) and e_ref > 0
+    assert abs(prob.assemble_energy(x) - e_ref) <= TOL * e_ref
+    K = prob.assemble().to_scipy()
+    assert abs(0.5 * float(x @ (K @ x)) - e_ref) <= 1e-12 * e_ref

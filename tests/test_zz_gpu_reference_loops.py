@@ -51,3 +51,22 @@ def test_cuda_path_equals_reference_linear_loop(k):
     assert outer.tobytes() == G[f"outer_{name}"].astype(outer.dtype).tobytes()
     assert inner.tobytes() == G[f"inner_{name}"].astype(inner.dtype).tobytes()
     assert_values_close(outer, inner, h.linear_stiffness(), G[f"values_{name}"], what=name)
+
+
+@pytest.mark.parametrize("k", range(12))
+def test_cuda_linear_elasticity_energy_equals_reference_function(k):
+    """pfa_energy of a LinearElasticity handle (a linear material inside a nonlinear solve) vs tests/golden/le_energy.npz:
+    LinearElasticity::compute_energy of the reference (LinearElasticity.cpp:65-68, 103-132 compiled verbatim) on the
+    one-element meshes of nh_local.npz, P1-P4."""
+    from polyfem_b200 import capi, tables
+    here = os.path.dirname(os.path.abspath(__file__))
+    G = np.load(os.path.join(here, "golden", "nh_local.npz"))
+    LE = np.load(os.path.join(here, "golden", "le_energy.npz"))
+    t = tables.reference_tables(int(G[f"p_{k}"]))
+    u = G[f"u_{k}"]
+    nl = u.shape[0]
+    conn = np.arange(nl, dtype=np.int32)[None, :]
+    h = capi.Handle("LinearElasticity", conn, nl, t["weights"], t["grad"], vertices=G[f"vertices_{k}"][None],
+                    lam=float(G["lambda"]), mu=float(G["mu"]))
+    e_ref = float(LE[f"le_energy_{k}"])
+    assert abs(h.energy(u.reshape(-1)) - e_ref) <= REL_TOL * e_ref

@@ -180,6 +180,31 @@ def write_nh_golden():
     print(f"wrote tests/golden/nh_local.npz ({k} cases)")
 
 
+def write_le_energy_golden():
+    """tests/golden/le_energy.npz: LinearElasticity::compute_energy (the energy of a linear material inside a nonlinear solve,
+    LinearElasticity.cpp:65-68, 103-132, the reference's own function body via libnhref.so) on the non-inverted single-element
+    cases of nh_local.npz."""
+    lib = load_nhref()
+    dp = ctypes.POINTER(ctypes.c_double)
+    lib.ref_le_energy.argtypes = [ctypes.c_int, ctypes.c_int, dp, dp, dp, dp, ctypes.c_double, ctypes.c_double, dp]
+    sys.path.insert(0, ROOT)
+    from polyfem_b200 import tables
+    G = np.load(os.path.join(ROOT, "tests", "golden", "nh_local.npz"))
+    gold = {}
+    for k in range(int(G["n_cases"])):
+        t = tables.reference_tables(int(G[f"p_{k}"]))
+        verts, u = G[f"vertices_{k}"], np.ascontiguousarray(G[f"u_{k}"]).reshape(-1)
+        edges = verts[1:] - verts[0]
+        nq, nl = t["weights"].size, t["grad"].shape[1]
+        jac_it = np.ascontiguousarray(np.repeat(np.linalg.inv(edges).T[None], nq, 0).reshape(nq, 9))
+        da = np.ascontiguousarray(np.linalg.det(edges) * t["weights"])
+        e = np.zeros(1)
+        assert lib.ref_le_energy(nl, nq, ptr(u), ptr(np.ascontiguousarray(t["grad"])), ptr(jac_it), ptr(da), float(G["lambda"]), float(G["mu"]), ptr(e)) == 0
+        gold[f"le_energy_{k}"] = e[0]
+    np.savez_compressed(os.path.join(ROOT, "tests", "golden", "le_energy.npz"), **gold)
+    print("wrote tests/golden/le_energy.npz")
+
+
 def write_cache_golden():
     """tests/golden/cache_sequences.npz: the matrices the reference's own SparseMatrixCache (utils/MatrixCache.cpp compiled
     unmodified, oracle/_ref/libcacheref.so) returns for the call sequences of tests/test_oracle_cache_vs_reference.py."""
@@ -238,6 +263,8 @@ def write_loop_golden():
 def main():
     if len(sys.argv) > 1 and sys.argv[1] == "loops":
         return write_loop_golden()
+    if len(sys.argv) > 1 and sys.argv[1] == "le_energy":
+        return write_le_energy_golden()
     lib = load_ref()
     quad = {"source": "polyfem autogen/auto_tetrahedron.ipp via quadrature/TetQuadrature.cpp (weights /= 6)",
             "orders": {}}
@@ -269,6 +296,7 @@ def main():
     np.savez_compressed(os.path.join(ROOT, "tests", "golden", "ref_tables.npz"), **gold)
     print("wrote tet_quadrature.json and tests/golden/ref_tables.npz")
     write_nh_golden()
+    write_le_energy_golden()
     write_cache_golden()
     write_bc_golden()
     write_loop_golden()
