@@ -1,0 +1,110 @@
+// TEST INFRASTRUCTURE: CPU emulation of the column-lane kernels (polyfem_b200/csrc/pfa_collane.cu) built from the SAME
+// header (pfa_collane.h: record math, per-lane column math, host schedule). It walks groups, steps, slots and lanes the
+// way the kernel does - a lane-private strip per (slot, component), the same table words, the same address arithmetic -
+// so that tests/test_collane_emulation.py can compare the data flow with the oracle without a GPU. What it cannot check:
+// launch configuration, shared-memory sizing and synchronisation of the real kernel.
+#include "../polyfem_b200/csrc/pfa_collane.h"
+
+#include <cstring>
+
+using namespace pfa::collane;
+
+namespace
+{
+	struct HostTable
+	{
+		const double *p;
+		double operator[](int i) const { return p[i]; }
+	};
+
+	template <int NL, int NQ>
+	int emulate(int n_el, int n_bases, const int32_t *conn, const int32_t *adj_off, const int32_t *adj, const double *jit, const double *detj,
+				const double *qw, const double *ref_grads, double lam, double mu, const double *x, int small_rows, double *energy, double *grad,
+				double *values, int64_t *stats)
+	{
+		// (A) records
+		std::vector<double> rec(size_t(n_el) * NQ * kRec);
+		double e_sum = 0.0;
+		for (int e = 0; e < n_el; ++e)
+		{
+			double u[NL * 3];
+			for (int i = 0; i < NL; ++i)
+				for (int c = 0; c < 3; ++c)
+					u[i * 3 + c] = x[size_t(conn[size_t(e) * NL + i]) * 3 + c];
+			for (int q = 0; q < NQ; ++q)
+				e_sum += qp_record<NL>(jit + size_t(e) * 9, detj[e] * qw[q], lam, mu, u, ref_grads + size_t(q) * NL * 3, rec.data() + (size_t(e) * NQ + q) * kRec);
+		}
+		*energy = e_sum;
+		// (B) column lanes
+		const Schedule S = build_schedule(n_el, NL, n_bases, conn, adj_off, adj, small_rows);
+		const HostTable G{ref_grads};
+		const int n_groups = S.n_groups[0] + S.n_groups[1];
+		std::vector<double> strip;
+		for (int g = 0; g < n_groups; ++g)
+		{
+			const int rows = S.grp_rows[size_t(g)], s0 = S.grp_off[size_t(g)], s1 = S.grp_off[size_t(g) + 1];
+			if (rows > S.rows_max[g < S.n_groups[0] ? 0 : 1])
+				return -2;
+			for (int lane = 0; lane < 3 * kSlots; ++lane)
+			{
+				const int slot = lane / 3, m = lane - slot * 3;
+				const int b = S.grp_node[size_t(g) * kSlots + slot];
+				strip.assign(size_t(rows), 0.0); // strip[row] stands for strip[row*32 + lane]
+				double g_acc = 0.0;
+				for (int s = s0; s < s1; ++s)
+				{
+					const uint32_t *w = S.inc.data() + (size_t(s) * kSlots + slot) * 4;
+					if (w[0] == 0xffffffffu)
+						continue;
+					if (b < 0)
+						return -3;
+					const int e = int(w[0]);
+					const int ri = (w[3] >> 16) & 0xff;
+					if (conn[size_t(e) * NL + ri] != b)
+						return -4;
+					double acc[NL][3];
+					for (int j = 0; j < NL; ++j)
+						acc[j][0] = acc[j][1] = acc[j][2] = 0.0;
+					column_of_element<NL, NQ>(rec.data() + size_t(e) * NQ * kRec, ref_grads, ri, m, G, acc, g_acc);
+					for (int j = 0; j < NL; ++j)
+					{
+						const int k = (w[1 + j / 4] >> (8 * (j % 4))) & 0xff;
+						for (int sft = 0; sft < 3; ++sft)
+						{
+							const int n = (m + sft) % 3;
+							if (3 * k + n >= rows)
+								return -5;
+							strip[size_t(3 * k + n)] += acc[j][sft];
+						}
+					}
+				}
+				if (b < 0)
+					continue;
+				// flush: column 3b+m starts at 9*adj_off[b] + m*3*deg(b) and has 3*deg(b) rows
+				const int deg = adj_off[b + 1] - adj_off[b];
+				double *dst = values + size_t(adj_off[b]) * 9 + size_t(m) * 3 * deg;
+				for (int r = 0; r < 3 * deg; ++r)
+					dst[r] = strip[size_t(r)];
+				grad[size_t(b) * 3 + m] = g_acc;
+			}
+		}
+		stats[0] = S.n_groups[0];
+		stats[1] = S.n_groups[1];
+		stats[2] = S.rows_max[0];
+		stats[3] = S.rows_max[1];
+		stats[4] = S.total_steps;
+		stats[5] = S.busy_slots;
+		return 0;
+	}
+} // namespace
+
+extern "C" int collane_emulate(int n_loc, int n_qp, int n_el, int n_bases, const int32_t *conn, const int32_t *adj_off, const int32_t *adj,
+								 const double *jit, const double *detj, const double *qw, const double *ref_grads, double lam, double mu, const double *x,
+								 int small_rows, double *energy, double *grad, double *values, int64_t *stats)
+{
+	if (n_loc == 4 && n_qp == 1)
+		return emulate<4, 1>(n_el, n_bases, conn, adj_off, adj, jit, detj, qw, ref_grads, lam, mu, x, small_rows, energy, grad, values, stats);
+	if (n_loc == 10 && n_qp == 4)
+		return emulate<10, 4>(n_el, n_bases, conn, adj_off, adj, jit, detj, qw, ref_grads, lam, mu, x, small_rows, energy, grad, values, stats);
+	return -1;
+}

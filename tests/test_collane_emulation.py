@@ -1,0 +1,96 @@
+"""CPU emulation of the column-lane (owner-computes) kernels against the oracle.
+
+`polyfem_b200/csrc/pfa_collane.h` holds the record math, the per-lane column math and the host schedule of the opt-in
+column-lane kernels (`pfa_collane.cu`). `tests/collane_emul.cpp` walks groups / steps / slots / lanes on the
+CPU with exactly those functions and tables; here its energy, gradient and `values[]` are compared with the oracle
+(pattern layout = the library's: column 3b+m at 9*adj_off[b] + m*3*deg(b)), 1e-12 like the GPU parity tests.
+Each entry is summed in a fixed order, so two runs must agree bit for bit."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from helpers import REL_TOL, assert_values_close, assert_vector_close
+from polyfem_b200 import mesh as M, tables
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def emul(tmp_path_factory):
+    out = str(tmp_path_factory.mktemp("collane") / "libcollane_emul.so")
+    subprocess.run(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-ffp-contract=off", os.path.join(ROOT, "tests", "collane_emul.cpp"), "-o", out],
+                   check=True)
+    lib = ctypes.CDLL(out)
+    dp, ip = ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_int32)
+    lib.collane_emulate.argtypes = [ctypes.c_int] * 4 + [ip, ip, ip, dp, dp, dp, dp, ctypes.c_double, ctypes.c_double, dp, ctypes.c_int, dp, dp, dp,
+                                    ctypes.POINTER(ctypes.c_int64)]
+    return lib
+
+
+def node_adjacency(mesh):
+    """adj_off, adj (ascending, with the node itself): the node-block pattern the library builds on the device."""
+    nl = mesh.conn.shape[1]
+    a = np.repeat(mesh.conn, nl, axis=1).reshape(-1)
+    b = np.tile(mesh.conn, (1, nl)).reshape(-1)
+    pairs = np.unique(np.stack([a, b], axis=1), axis=0)  # sorted by (a, b)
+    adj_off = np.zeros(mesh.n_bases + 1, dtype=np.int32)
+    np.add.at(adj_off, pairs[:, 0] + 1, 1)
+    return np.cumsum(adj_off).astype(np.int32), np.ascontiguousarray(pairs[:, 1], dtype=np.int32)
+
+
+def run_emulation(lib, oracle, mesh, x, small_rows):
+    t = tables.reference_tables(mesh.p)
+    prob = oracle.problem_from_mesh(mesh, "NeoHookean")
+    ne, nl, nq = mesh.n_elements, mesh.conn.shape[1], t["weights"].size
+    jit, det = np.zeros((ne, 9)), np.zeros(ne)
+    for e in range(ne):
+        d, j, _ = prob.assembly_values(e)
+        jit[e], det[e] = j[0].reshape(9), d[0]
+    adj_off, adj = node_adjacency(mesh)
+    conn = np.ascontiguousarray(mesh.conn, dtype=np.int32)
+    lam, mu = M.lame_from_E_nu(1e5, 0.3)
+    nnz = 9 * adj.size
+    energy, grad, values, stats = np.zeros(1), np.zeros(mesh.n_bases * 3), np.full(nnz, np.nan), np.zeros(6, dtype=np.int64)
+    P = lambda a, ty=ctypes.c_double: a.ctypes.data_as(ctypes.POINTER(ty))  # noqa: E731
+    rc = lib.collane_emulate(nl, nq, ne, mesh.n_bases, P(conn, ctypes.c_int32), P(adj_off, ctypes.c_int32), P(adj, ctypes.c_int32), P(jit), P(det),
+                             P(np.ascontiguousarray(t["weights"])), P(np.ascontiguousarray(t["grad"])), lam, mu, P(np.ascontiguousarray(x)),
+                             small_rows, P(energy), P(grad), P(values), P(stats, ctypes.c_int64))
+    assert rc == 0, f"emulation failed with code {rc}"
+    return prob, float(energy[0]), grad, values, stats
+
+
+@pytest.mark.parametrize("p,n,small_rows", [(1, 3, 96), (2, 2, 96), (2, 3, 96), (2, 3, 1000), (2, 2, 0)])
+def test_column_lane_data_flow_equals_oracle(emul, oracle, p, n, small_rows):
+    mesh = M.kuhn_cube(n, p, jitter=0.2)
+    x = M.random_displacement(mesh)[: mesh.n_bases * 3]
+    prob, e, g, v, stats = run_emulation(emul, oracle, mesh, x, small_rows)
+    H = prob.assemble_hessian(x)
+    assert v.size == H.values.size and not np.isnan(v).any()  # every column was flushed exactly once
+    e_ref = prob.assemble_energy(x)
+    assert abs(e - e_ref) <= REL_TOL * abs(e_ref)
+    assert_vector_close(g, prob.assemble_gradient(x))
+    assert_values_close(H.outer, H.inner, v, H.values)
+    # schedule statistics: every (element, node) incidence is worked on exactly once
+    assert stats[5] == mesh.n_elements * mesh.conn.shape[1]
+    if small_rows == 0:
+        assert stats[0] == 0 and stats[1] > 0
+    if small_rows == 1000:
+        assert stats[1] == 0
+    # fixed summation order: bitwise reproducible
+    _, e2, g2, v2, _ = run_emulation(emul, oracle, mesh, x, small_rows)
+    assert e2 == e and np.array_equal(g2, g) and np.array_equal(v2, v)
+
+
+def test_column_lane_nan_propagation(emul, oracle):
+    mesh = M.kuhn_cube(2, 2)
+    x = M.random_displacement(mesh)[: mesh.n_bases * 3]
+    nodes = mesh.conn[5]
+    x.reshape(-1, 3)[nodes[1]] += 3.0 * (mesh.node_xyz[nodes[0]] - mesh.node_xyz[nodes[1]])
+    prob, e, g, v, _ = run_emulation(emul, oracle, mesh, x, 96)
+    H = prob.assemble_hessian(x)
+    assert np.isnan(e) and np.isnan(prob.assemble_energy(x))
+    assert_vector_close(g, prob.assemble_gradient(x))
+    assert_values_close(H.outer, H.inner, v, H.values)
