@@ -47,6 +47,12 @@ class MeshDesc(ctypes.Structure):
     ]
 
 
+# pfa_mesh_desc.flags (include/pfa.h)
+FLAG_KEEP_ELEMENT_ORDER = 1
+FLAG_INKERNEL_ZERO = 2
+FLAG_COLUMN_LANE = 4  # NeoHookean P1/P2: owner-computes kernels (bitwise reproducible, no zero fill); opt-in
+
+
 class PfaError(RuntimeError):
     def __init__(self, code, msg):
         super().__init__(f"pfa error {code}: {msg}")

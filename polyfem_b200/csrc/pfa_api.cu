@@ -1,6 +1,7 @@
 // C-ABI layer of libpfa.so (include/pfa.h): handle lifetime, host<->device staging,
 // error translation. No CPU fallback: every compute entry point runs the CUDA kernels or
 // fails with PFA_ERR_NO_DEVICE / PFA_ERR_CUDA.
+#include "pfa_collane.h"
 #include "pfa_internal.h"
 
 #include <chrono>
@@ -47,6 +48,7 @@ struct pfa_handle
 	double *d_energy = nullptr;
 	int *d_counter = nullptr;
 	int32_t epoch = 0; // in-kernel zero-fill generation (row-lane kernels)
+	ColumnLaneTables cl; // opt-in owner-computes path (PFA_FLAG_COLUMN_LANE)
 
 	// Dirichlet projection (pfa_set_constrained_dofs)
 	bool has_constraints = false;
@@ -296,6 +298,8 @@ namespace
 			}
 		}
 		PFA_CUDA(h, cudaMemsetAsync(h->d_counter, 0, 4 * sizeof(int), h->stream));
+		// owner-computes path: full matrix of a NeoHookean P1/P2 handle that opted in; writes every entry once
+		const bool use_cl = h->cl.enabled && !linear && !reduced && !project_to_psd && part == PFA_PART_ALL && a.values != nullptr;
 
 		// outputs are accumulated with atomics: zero them first (rhs.setZero / set_zero,
 		// Assembler.cpp:586-587, 666-667)
@@ -306,18 +310,20 @@ namespace
 				PFA_CUDA(h, cudaMemsetAsync(a.energy, 0, sizeof(double), h->stream));
 			if (a.grad)
 				PFA_CUDA(h, cudaMemsetAsync(a.grad, 0, n_grad * sizeof(double), h->stream));
-			if (a.values && dm.zoff != nullptr && !linear && !project_to_psd)
+			if (a.values && dm.zoff != nullptr && !linear && !project_to_psd && !use_cl)
 				a.epoch = ++h->epoch; // the row-lane kernel clears values[] itself, block by block, just ahead of the scatter
-			else if (a.values)
+			else if (a.values && !use_cl)
 				PFA_CUDA(h, cudaMemsetAsync(a.values, 0, n_val * sizeof(double), h->stream));
 			prof_end(h);
 		}
 
 		if (a.e_end <= a.e_begin)
 			return PFA_OK; // empty part: outputs are cleared (or left), nothing to launch
-		const char *kname = "assemble";
+		const char *kname = use_cl ? "assemble_nh_column_lane(records+columns)" : "assemble";
 		prof_begin(h, kname);
-		cudaError_t ce = launch_assemble(dm, a, linear, h->sm_count, h->stream, &kname);
+		cudaError_t ce = use_cl ? launch_column_lane(dm, a, h->cl, h->sm_count, h->stream) : launch_assemble(dm, a, linear, h->sm_count, h->stream, &kname);
+		if (use_cl)
+			h->launches += 1 + (h->cl.n_groups[0] > 0 && h->cl.n_groups[1] > 0 ? 1 : 0); // records + one column kernel per strip class
 		if (h->profiling && !h->prof.empty() && !h->prof.back().stop_recorded)
 			h->prof.back().name = kname;
 		prof_end(h);
@@ -581,6 +587,37 @@ extern "C"
 			PFA_CUDA(h, cudaMemsetAsync(m.zflag, 0, size_t(m.n_batches) * sizeof(int32_t), h->stream));
 			}
 			PFA_CUDA(h, cudaStreamSynchronize(h->stream)); // cstride, zoff, zruns are locals
+			// opt-in owner-computes path: schedule of (element, node) incidences + record buffer
+			static const bool cl_env = [] { const char *v = std::getenv("PFA_COLUMN_LANE"); return v && std::atoi(v) != 0; }();
+			int max_deg = 0;
+			for (size_t b = 0; b + 1 < hp.adj_off.size(); ++b)
+				max_deg = std::max(max_deg, hp.adj_off[b + 1] - hp.adj_off[b]);
+			if (((d->flags & PFA_FLAG_COLUMN_LANE) || cl_env) && affine && column_lane_applies(m.material, m.n_loc, m.n_qp) && max_deg < 256 && d->n_ghost_elements == 0)
+			{
+				try
+				{
+					// strips of at most 96 rows (24 KB per warp) form the first launch, the rest (P2 vertex nodes) the second
+					const collane::Schedule S = collane::build_schedule(m.n_el, m.n_loc, m.n_bases, conn_in, hp.adj_off.data(), hp.adj.data(), 96);
+					UP(h->cl.grp_node, S.grp_node.data(), S.grp_node.size(), int32_t);
+					UP(h->cl.grp_off, S.grp_off.data(), S.grp_off.size(), int32_t);
+					UP(h->cl.grp_rows, S.grp_rows.data(), S.grp_rows.size(), int32_t);
+					UP(h->cl.inc, S.inc.data(), S.inc.size(), uint32_t);
+					if ((rc = dev_alloc<double>(h, &h->cl.records, ne * nq * size_t(collane::kRec))) != PFA_OK)
+						return bail(rc);
+					for (int c = 0; c < 2; ++c)
+					{
+						h->cl.n_groups[c] = S.n_groups[c];
+						h->cl.rows_max[c] = S.rows_max[c];
+					}
+					h->cl.enabled = 1;
+					PFA_CUDA(h, cudaStreamSynchronize(h->stream)); // S is a local
+				}
+				catch (const std::bad_alloc &)
+				{
+					h->err = "pfa_create: out of host memory while building the column-lane schedule";
+					return bail(PFA_ERR_NOMEM);
+				}
+			}
 		}
 		else
 			UP(m.slot, hp.slot.data(), size_t(ne) * nl * nl, int32_t);

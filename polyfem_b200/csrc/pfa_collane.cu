@@ -1,0 +1,222 @@
+// Column-lane (owner-computes) NeoHookean assembly for P1 / P2 tets: opt-in alternative to the row-lane RED kernel
+// (PFA_FLAG_COLUMN_LANE or PFA_COLUMN_LANE=1; pfa_grad_hess / pfa_hessian with the full matrix, affine elements).
+// Math, record layout and schedule: pfa_collane.h (also compiled into the CPU emulation tests/collane_emul.cpp, which
+// is checked against the oracle). Written after the round-1 GPU budget was spent: NOT yet run on a GPU; the default
+// path does not use it.
+//
+//   collane_records_kernel   thread <-> (element, quadrature point): gathers x, writes the 34-double record to global
+//                            memory, reduces the energy
+//   collane_columns_kernel   warp <-> group of 10 nodes (3 lanes each); per step every slot takes one incident element
+//                            of its node, adds its 3*NL entries to the lane's private strip (shared memory, address
+//                            row*32 + lane: bank = lane, no conflicts, no atomics); after the last step the strip is the
+//                            finished CSC column and is streamed to values[], the gradient entry is stored: every output
+//                            is written exactly once, in a fixed summation order (bitwise reproducible), no zero fill
+#include "pfa_collane.h"
+#include "pfa_internal.h"
+
+#include <cstring>
+#include <mutex>
+
+namespace pfa
+{
+	namespace
+	{
+		using namespace collane;
+		constexpr int kSlotDoubles = 4 * 10 * 3;
+		__constant__ double c_cl_refgrad[2][kSlotDoubles]; // slot 0: P1 [1][4][3], slot 1: P2 [4][10][3]
+
+		template <int SLOT>
+		struct ConstTable
+		{
+			__device__ __forceinline__ double operator[](int i) const { return c_cl_refgrad[SLOT][i]; }
+		};
+
+		template <int NL, int NQ>
+		__global__ void __launch_bounds__(128) collane_records_kernel(const DeviceMesh m, const AssembleArgs a, double *__restrict__ rec_out)
+		{
+			static_assert(32 % NQ == 0, "the quadrature points of an element sit in one warp");
+			const int64_t t = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+			const int64_t e64 = t / NQ;
+			const int q = int(t - e64 * NQ);
+			const bool valid = e64 < m.n_el;
+			double e_q = 0.0;
+			if (valid)
+			{
+				const int e = int(e64);
+				double u[NL * 3];
+#pragma unroll
+				for (int i = 0; i < NL; ++i)
+				{
+					const size_t g = size_t(m.conn[size_t(e) * NL + i]);
+					u[i * 3 + 0] = a.x[g * 3 + 0];
+					u[i * 3 + 1] = a.x[g * 3 + 1];
+					u[i * 3 + 2] = a.x[g * 3 + 2];
+				}
+				double J[9];
+#pragma unroll
+				for (int k = 0; k < 9; ++k)
+					J[k] = m.jit[size_t(e) * 9 + k];
+				const double da = m.detj[e] * m.qweights[q];
+				const size_t mi = size_t(e) * m.mat_stride + (m.mat_stride == 1 ? 0 : q);
+				e_q = qp_record<NL>(J, da, m.lambda[mi], m.mu[mi], u, m.ref_grads + size_t(q) * NL * 3, rec_out + (size_t(e) * NQ + q) * kRec);
+			}
+			if (a.energy != nullptr || a.energy_per_el != nullptr)
+			{
+				double e_el = e_q;
+#pragma unroll
+				for (int k = 1; k < NQ; k <<= 1)
+					e_el += __shfl_xor_sync(0xffffffffu, e_el, k);
+				if (valid && q == 0 && a.energy_per_el != nullptr)
+					a.energy_per_el[m.elem_id ? m.elem_id[e64] : e64] = e_el;
+				if (a.energy != nullptr)
+				{
+					double w = e_q;
+#pragma unroll
+					for (int o = 16; o > 0; o >>= 1)
+						w += __shfl_xor_sync(0xffffffffu, w, o);
+					__shared__ double s_e[4];
+					if ((threadIdx.x & 31) == 0)
+						s_e[threadIdx.x >> 5] = w;
+					__syncthreads();
+					if (threadIdx.x == 0)
+						atomicAdd(a.energy, (s_e[0] + s_e[1] + s_e[2] + s_e[3]) * a.scale);
+				}
+			}
+		}
+
+		template <int NL, int NQ, int SLOT>
+		__global__ void __launch_bounds__(256) collane_columns_kernel(const DeviceMesh m, const AssembleArgs a, const ColumnLaneTables t, const double *__restrict__ rec, int g_begin,
+											   int g_end, int strip_rows)
+		{
+			extern __shared__ double smem[];
+			double *s_rg = smem; // [NQ][NL][3]: row-side reference gradients (lane-dependent index)
+			for (int k = threadIdx.x; k < NQ * NL * 3; k += blockDim.x)
+				s_rg[k] = m.ref_grads[k];
+			__syncthreads();
+			const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, warps = blockDim.x >> 5;
+			double *strip = smem + ((NQ * NL * 3 + 1) & ~1) + size_t(warp) * strip_rows * 32 + lane;
+			const int slot = lane / 3, mm = lane - slot * 3;
+			const bool active = lane < 3 * kSlots;
+			const uint4 *inc = reinterpret_cast<const uint4 *>(t.inc);
+			for (int g = g_begin + blockIdx.x * warps + warp; g < g_end; g += gridDim.x * warps)
+			{
+				const int rows = t.grp_rows[g], s0 = t.grp_off[g], s1 = t.grp_off[g + 1];
+				const int b = active ? t.grp_node[size_t(g) * kSlots + slot] : -1;
+				for (int r = 0; r < rows; ++r)
+					strip[r * 32] = 0.0;
+				double g_acc = 0.0;
+				for (int s = s0; s < s1; ++s)
+				{
+					if (!active)
+						continue;
+					const uint4 w = inc[size_t(s) * kSlots + slot];
+					if (w.x == 0xffffffffu)
+						continue;
+					const int ri = (w.w >> 16) & 0xff;
+					double acc[NL][3];
+#pragma unroll
+					for (int j = 0; j < NL; ++j)
+						acc[j][0] = acc[j][1] = acc[j][2] = 0.0;
+					column_of_element<NL, NQ>(rec + size_t(w.x) * NQ * kRec, s_rg, ri, mm, ConstTable<SLOT>(), acc, g_acc);
+					// column component n = (mm + shift) % 3 of column node j goes to row 3*k_j + n of this lane's column
+					const int n1 = mm == 2 ? 0 : mm + 1, n2 = mm == 0 ? 2 : mm - 1;
+#pragma unroll
+					for (int j = 0; j < NL; ++j)
+					{
+						const uint32_t word = j < 4 ? w.y : (j < 8 ? w.z : w.w);
+						const int k3 = 3 * int((word >> (8 * (j & 3))) & 0xffu);
+						strip[(k3 + mm) * 32] += acc[j][0];
+						strip[(k3 + n1) * 32] += acc[j][1];
+						strip[(k3 + n2) * 32] += acc[j][2];
+					}
+				}
+				if (b >= 0)
+				{
+					// column 3b+mm of values[] starts at 9*adj_off[b] + mm*3*deg(b) and has 3*deg(b) rows
+					const int off = m.adj_off[b], deg = m.adj_off[b + 1] - off;
+					if (a.values != nullptr)
+					{
+						double *dst = a.values + (size_t(off) * 9 + size_t(mm) * 3 * deg);
+						for (int r = 0; r < 3 * deg; ++r)
+							dst[r] = a.scale * strip[r * 32];
+					}
+					if (a.grad != nullptr)
+						a.grad[size_t(b) * 3 + mm] = a.scale * g_acc;
+				}
+			}
+		}
+
+		std::mutex g_cl_mutex;
+		double g_cl_shadow[16][2][kSlotDoubles];
+		bool g_cl_valid[16][2] = {};
+
+		cudaError_t ensure_cl_table(const DeviceMesh &m, int slot, cudaStream_t st)
+		{
+			int dev = 0;
+			cudaError_t err = cudaGetDevice(&dev);
+			if (err != cudaSuccess)
+				return err;
+			if (dev < 0 || dev >= 16 || m.ref_grads_host == nullptr)
+				return cudaErrorInvalidValue;
+			const size_t bytes = sizeof(double) * size_t(m.n_qp) * m.n_loc * 3;
+			std::lock_guard<std::mutex> lock(g_cl_mutex);
+			if (g_cl_valid[dev][slot] && std::memcmp(g_cl_shadow[dev][slot], m.ref_grads_host, bytes) == 0)
+				return cudaSuccess;
+			std::memcpy(g_cl_shadow[dev][slot], m.ref_grads_host, bytes);
+			g_cl_valid[dev][slot] = true;
+			return cudaMemcpyToSymbolAsync(c_cl_refgrad, g_cl_shadow[dev][slot], bytes, sizeof(double) * size_t(slot) * kSlotDoubles, cudaMemcpyHostToDevice, st);
+		}
+
+		template <int NL, int NQ, int SLOT>
+		cudaError_t launch_cl(const DeviceMesh &m, const AssembleArgs &a, const ColumnLaneTables &t, int sm_count, cudaStream_t st)
+		{
+			cudaError_t err = ensure_cl_table(m, SLOT, st);
+			if (err != cudaSuccess)
+				return err;
+			const int64_t threads = int64_t(m.n_el) * NQ;
+			collane_records_kernel<NL, NQ><<<unsigned((threads + 127) / 128), 128, 0, st>>>(m, a, t.records);
+			if ((err = cudaGetLastError()) != cudaSuccess)
+				return err;
+			if (a.values == nullptr && a.grad == nullptr)
+				return cudaSuccess;
+			auto kern = collane_columns_kernel<NL, NQ, SLOT>;
+			int dev = 0, smem_max = 0;
+			if ((err = cudaGetDevice(&dev)) != cudaSuccess || (err = cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev)) != cudaSuccess)
+				return err;
+			if ((err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max)) != cudaSuccess)
+				return err;
+			const size_t table_bytes = sizeof(double) * size_t((NQ * NL * 3 + 1) & ~1);
+			int g0 = 0;
+			for (int c = 0; c < 2; ++c)
+			{
+				const int ng = t.n_groups[c];
+				if (ng > 0)
+				{
+					const size_t strip_bytes = sizeof(double) * 32 * size_t(t.rows_max[c]);
+					int warps = int((size_t(smem_max) - table_bytes) / strip_bytes);
+					if (warps < 1)
+						return cudaErrorInvalidConfiguration;
+					warps = std::min(warps, 8);
+					const int grid = std::max(1, std::min((ng + warps - 1) / warps, sm_count));
+					kern<<<grid, warps * 32, table_bytes + size_t(warps) * strip_bytes, st>>>(m, a, t, t.records, g0, g0 + ng, t.rows_max[c]);
+					if ((err = cudaGetLastError()) != cudaSuccess)
+						return err;
+				}
+				g0 += ng;
+			}
+			return cudaSuccess;
+		}
+	} // namespace
+
+	bool column_lane_applies(int material, int n_loc, int n_qp)
+	{
+		return material == PFA_NEOHOOKEAN && ((n_loc == 4 && n_qp == 1) || (n_loc == 10 && n_qp == 4));
+	}
+
+	cudaError_t launch_column_lane(const DeviceMesh &m, const AssembleArgs &a, const ColumnLaneTables &t, int sm_count, cudaStream_t st)
+	{
+		if (m.n_loc == 4)
+			return launch_cl<4, 1, 0>(m, a, t, sm_count, st);
+		return launch_cl<10, 4, 1>(m, a, t, sm_count, st);
+	}
+} // namespace pfa

@@ -120,8 +120,10 @@ namespace pfa
 		PFA_HD void column_of_element(const double *rec_e, const double *rg, int ri, int mm, const ColTable &G, double (*acc)[3], double &g_row)
 		{
 			const int ra = (mm + 1) % 3, rb = (mm + 2) % 3;
+			// not unrolled on the device: keeps the register count of the column kernel at the row-lane kernel's level (the
+			// column table is then read with a uniform run-time index, LDC)
 #if defined(__CUDA_ARCH__)
-#pragma unroll
+#pragma unroll 1
 #endif
 			for (int qq = 0; qq < NQ; ++qq)
 			{

@@ -78,6 +78,24 @@ namespace pfa
 		int32_t epoch = 0;           // > 0: values[] is zero-filled inside the kernel (see DeviceMesh::zoff)
 	};
 
+	// Column-lane (owner-computes) tables of a handle (pfa_collane.h / pfa_collane.cu), built at create time when the
+	// handle opts in (PFA_FLAG_COLUMN_LANE or PFA_COLUMN_LANE=1); all pointers are device memory
+	struct ColumnLaneTables
+	{
+		int32_t enabled = 0;
+		int32_t n_groups[2] = {0, 0}; // class 0: small strips, class 1: large strips (groups of class 0 come first)
+		int32_t rows_max[2] = {0, 0}; // strip rows of the two launches
+		const int32_t *grp_node = nullptr; // [G][10]
+		const int32_t *grp_off = nullptr;  // [G+1]
+		const int32_t *grp_rows = nullptr; // [G]
+		const uint32_t *inc = nullptr;     // [total_steps][10][4]
+		double *records = nullptr;         // [n_el][n_qp][34]
+	};
+	bool column_lane_applies(int material, int n_loc, int n_qp);
+	// records kernel + one column kernel per strip class; writes every entry of values[] / grad[] exactly once (no zero
+	// fill needed), accumulates a.energy (zeroed by the caller)
+	cudaError_t launch_column_lane(const DeviceMesh &m, const AssembleArgs &a, const ColumnLaneTables &t, int sm_count, cudaStream_t st);
+
 	// kernel launchers (pfa_kernels.cu). Return cudaError_t of the launch.
 	cudaError_t launch_geometry_precompute(const double *vertices_dev, int n_el, double *jit, double *detj, cudaStream_t st);
 	cudaError_t launch_expand_inner(const DeviceMesh &m, int32_t *outer, int32_t *inner, cudaStream_t st);
