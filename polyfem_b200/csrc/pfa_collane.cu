@@ -84,7 +84,7 @@ namespace pfa
 			}
 		}
 
-		template <int NL, int NQ, int SLOT>
+		template <int NL, int NQ, int SLOT, bool P2S>
 		__global__ void __launch_bounds__(256) collane_columns_kernel(const DeviceMesh m, const AssembleArgs a, const ColumnLaneTables t, const double *__restrict__ rec, int g_begin,
 											   int g_end, int strip_rows)
 		{
@@ -117,7 +117,7 @@ namespace pfa
 #pragma unroll
 					for (int j = 0; j < NL; ++j)
 						acc[j][0] = acc[j][1] = acc[j][2] = 0.0;
-					column_of_element<NL, NQ>(rec + size_t(w.x) * NQ * kRec, s_rg, ri, mm, ConstTable<SLOT>(), acc, g_acc);
+					column_of_element<NL, NQ, P2S>(rec + size_t(w.x) * NQ * kRec, s_rg, ri, mm, ConstTable<SLOT>(), acc, g_acc);
 					// column component n = (mm + shift) % 3 of column node j goes to row 3*k_j + n of this lane's column
 					const int n1 = mm == 2 ? 0 : mm + 1, n2 = mm == 0 ? 2 : mm - 1;
 #pragma unroll
@@ -167,7 +167,7 @@ namespace pfa
 			return cudaMemcpyToSymbolAsync(c_cl_refgrad, g_cl_shadow[dev][slot], bytes, sizeof(double) * size_t(slot) * kSlotDoubles, cudaMemcpyHostToDevice, st);
 		}
 
-		template <int NL, int NQ, int SLOT>
+		template <int NL, int NQ, int SLOT, bool P2S>
 		cudaError_t launch_cl(const DeviceMesh &m, const AssembleArgs &a, const ColumnLaneTables &t, int sm_count, cudaStream_t st)
 		{
 			cudaError_t err = ensure_cl_table(m, SLOT, st);
@@ -179,7 +179,7 @@ namespace pfa
 				return err;
 			if (a.values == nullptr && a.grad == nullptr)
 				return cudaSuccess;
-			auto kern = collane_columns_kernel<NL, NQ, SLOT>;
+			auto kern = collane_columns_kernel<NL, NQ, SLOT, P2S>;
 			int dev = 0, smem_max = 0;
 			if ((err = cudaGetDevice(&dev)) != cudaSuccess || (err = cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev)) != cudaSuccess)
 				return err;
@@ -216,7 +216,8 @@ namespace pfa
 	cudaError_t launch_column_lane(const DeviceMesh &m, const AssembleArgs &a, const ColumnLaneTables &t, int sm_count, cudaStream_t st)
 	{
 		if (m.n_loc == 4)
-			return launch_cl<4, 1, 0>(m, a, t, sm_count, st);
-		return launch_cl<10, 4, 1>(m, a, t, sm_count, st);
+			return launch_cl<4, 1, 0, false>(m, a, t, sm_count, st);
+		// the structured column step needs the structural zeros of the P2 reference gradients (DeviceMesh::p2_structured)
+		return m.p2_structured ? launch_cl<10, 4, 1, true>(m, a, t, sm_count, st) : launch_cl<10, 4, 1, false>(m, a, t, sm_count, st);
 	}
 } // namespace pfa

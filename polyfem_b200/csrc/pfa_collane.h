@@ -116,7 +116,9 @@ namespace pfa
 		//   acc[j][s] += H[(ri, mm), (j, (mm + s) % 3)]   (rotated by mm, like the row-lane kernel)      g_row += G[(ri, mm)]
 		// rec: [NQ][kRec] of the element; rg: reference gradients [NQ][NL][3] (row side, index depends on the lane);
 		// G: the same table as the column operand (device: __constant__ memory, uniform index).
-		template <int NL, int NQ, class ColTable>
+		// P2S: the table has the structural zeros / equal components of the P2 tet basis (checked on the host by
+		// p2_table_structured, pfa_kernels.cu): 20 instead of 30 DFMA-pipe operations per (column component, quadrature point)
+		template <int NL, int NQ, bool P2S, class ColTable>
 		PFA_HD void column_of_element(const double *rec_e, const double *rg, int ri, int mm, const ColTable &G, double (*acc)[3], double &g_row)
 		{
 			const int ra = (mm + 1) % 3, rb = (mm + 2) % 3;
@@ -152,15 +154,40 @@ namespace pfa
 				Y[2][0] = fma(cA, c2r[0], a0);
 				Y[2][1] = fma(cA, c2r[1], a1);
 				Y[2][2] = fma(cA, c2r[2], a2);
+				if constexpr (P2S && NL == 10)
+				{
+					const int o = qq * NL * 3;
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
-				for (int j = 0; j < NL; ++j)
+					for (int n = 0; n < 3; ++n)
+					{
+						const double y0 = Y[n][0], y1 = Y[n][1], y2 = Y[n][2];
+						const double u12 = y1 + y2, u02 = y0 + y2, u01 = y0 + y1, sy = y0 + u12;
+						acc[0][n] = fma(sy, G[o + 0], acc[0][n]);
+						acc[1][n] = fma(y0, G[o + 3], acc[1][n]);
+						acc[2][n] = fma(y1, G[o + 7], acc[2][n]);
+						acc[3][n] = fma(y2, G[o + 11], acc[3][n]);
+						acc[4][n] = fma(y0, G[o + 12], fma(u12, G[o + 13], acc[4][n]));
+						acc[5][n] = fma(y0, G[o + 15], fma(y1, G[o + 16], acc[5][n]));
+						acc[6][n] = fma(y1, G[o + 19], fma(u02, G[o + 18], acc[6][n]));
+						acc[7][n] = fma(y2, G[o + 23], fma(u01, G[o + 21], acc[7][n]));
+						acc[8][n] = fma(y0, G[o + 24], fma(y2, G[o + 26], acc[8][n]));
+						acc[9][n] = fma(y1, G[o + 28], fma(y2, G[o + 29], acc[9][n]));
+					}
+				}
+				else
 				{
-					const double c0 = G[(qq * NL + j) * 3 + 0], c1 = G[(qq * NL + j) * 3 + 1], c2 = G[(qq * NL + j) * 3 + 2];
-					acc[j][0] = fma(Y[0][0], c0, fma(Y[0][1], c1, fma(Y[0][2], c2, acc[j][0])));
-					acc[j][1] = fma(Y[1][0], c0, fma(Y[1][1], c1, fma(Y[1][2], c2, acc[j][1])));
-					acc[j][2] = fma(Y[2][0], c0, fma(Y[2][1], c1, fma(Y[2][2], c2, acc[j][2])));
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+					for (int j = 0; j < NL; ++j)
+					{
+						const double c0 = G[(qq * NL + j) * 3 + 0], c1 = G[(qq * NL + j) * 3 + 1], c2 = G[(qq * NL + j) * 3 + 2];
+						acc[j][0] = fma(Y[0][0], c0, fma(Y[0][1], c1, fma(Y[0][2], c2, acc[j][0])));
+						acc[j][1] = fma(Y[1][0], c0, fma(Y[1][1], c1, fma(Y[1][2], c2, acc[j][1])));
+						acc[j][2] = fma(Y[2][0], c0, fma(Y[2][1], c1, fma(Y[2][2], c2, acc[j][2])));
+					}
 				}
 			}
 		}

@@ -17,7 +17,7 @@ namespace
 		double operator[](int i) const { return p[i]; }
 	};
 
-	template <int NL, int NQ>
+	template <int NL, int NQ, bool P2S>
 	int emulate(int n_el, int n_bases, const int32_t *conn, const int32_t *adj_off, const int32_t *adj, const double *jit, const double *detj,
 				const double *qw, const double *ref_grads, double lam, double mu, const double *x, int small_rows, double *energy, double *grad,
 				double *values, int64_t *stats)
@@ -65,7 +65,7 @@ namespace
 					double acc[NL][3];
 					for (int j = 0; j < NL; ++j)
 						acc[j][0] = acc[j][1] = acc[j][2] = 0.0;
-					column_of_element<NL, NQ>(rec.data() + size_t(e) * NQ * kRec, ref_grads, ri, m, G, acc, g_acc);
+					column_of_element<NL, NQ, P2S>(rec.data() + size_t(e) * NQ * kRec, ref_grads, ri, m, G, acc, g_acc);
 					for (int j = 0; j < NL; ++j)
 					{
 						const int k = (w[1 + j / 4] >> (8 * (j % 4))) & 0xff;
@@ -100,11 +100,13 @@ namespace
 
 extern "C" int collane_emulate(int n_loc, int n_qp, int n_el, int n_bases, const int32_t *conn, const int32_t *adj_off, const int32_t *adj,
 								 const double *jit, const double *detj, const double *qw, const double *ref_grads, double lam, double mu, const double *x,
-								 int small_rows, double *energy, double *grad, double *values, int64_t *stats)
+								 int small_rows, int structured, double *energy, double *grad, double *values, int64_t *stats)
 {
 	if (n_loc == 4 && n_qp == 1)
-		return emulate<4, 1>(n_el, n_bases, conn, adj_off, adj, jit, detj, qw, ref_grads, lam, mu, x, small_rows, energy, grad, values, stats);
+		return emulate<4, 1, false>(n_el, n_bases, conn, adj_off, adj, jit, detj, qw, ref_grads, lam, mu, x, small_rows, energy, grad, values, stats);
+	if (n_loc == 10 && n_qp == 4 && structured)
+		return emulate<10, 4, true>(n_el, n_bases, conn, adj_off, adj, jit, detj, qw, ref_grads, lam, mu, x, small_rows, energy, grad, values, stats);
 	if (n_loc == 10 && n_qp == 4)
-		return emulate<10, 4>(n_el, n_bases, conn, adj_off, adj, jit, detj, qw, ref_grads, lam, mu, x, small_rows, energy, grad, values, stats);
+		return emulate<10, 4, false>(n_el, n_bases, conn, adj_off, adj, jit, detj, qw, ref_grads, lam, mu, x, small_rows, energy, grad, values, stats);
 	return -1;
 }

@@ -25,7 +25,7 @@ def emul(tmp_path_factory):
                    check=True)
     lib = ctypes.CDLL(out)
     dp, ip = ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_int32)
-    lib.collane_emulate.argtypes = [ctypes.c_int] * 4 + [ip, ip, ip, dp, dp, dp, dp, ctypes.c_double, ctypes.c_double, dp, ctypes.c_int, dp, dp, dp,
+    lib.collane_emulate.argtypes = [ctypes.c_int] * 4 + [ip, ip, ip, dp, dp, dp, dp, ctypes.c_double, ctypes.c_double, dp, ctypes.c_int, ctypes.c_int, dp, dp, dp,
                                     ctypes.POINTER(ctypes.c_int64)]
     return lib
 
@@ -41,7 +41,7 @@ def node_adjacency(mesh):
     return np.cumsum(adj_off).astype(np.int32), np.ascontiguousarray(pairs[:, 1], dtype=np.int32)
 
 
-def run_emulation(lib, oracle, mesh, x, small_rows):
+def run_emulation(lib, oracle, mesh, x, small_rows, structured=0):
     t = tables.reference_tables(mesh.p)
     prob = oracle.problem_from_mesh(mesh, "NeoHookean")
     ne, nl, nq = mesh.n_elements, mesh.conn.shape[1], t["weights"].size
@@ -57,16 +57,17 @@ def run_emulation(lib, oracle, mesh, x, small_rows):
     P = lambda a, ty=ctypes.c_double: a.ctypes.data_as(ctypes.POINTER(ty))  # noqa: E731
     rc = lib.collane_emulate(nl, nq, ne, mesh.n_bases, P(conn, ctypes.c_int32), P(adj_off, ctypes.c_int32), P(adj, ctypes.c_int32), P(jit), P(det),
                              P(np.ascontiguousarray(t["weights"])), P(np.ascontiguousarray(t["grad"])), lam, mu, P(np.ascontiguousarray(x)),
-                             small_rows, P(energy), P(grad), P(values), P(stats, ctypes.c_int64))
+                             small_rows, structured, P(energy), P(grad), P(values), P(stats, ctypes.c_int64))
     assert rc == 0, f"emulation failed with code {rc}"
     return prob, float(energy[0]), grad, values, stats
 
 
-@pytest.mark.parametrize("p,n,small_rows", [(1, 3, 96), (2, 2, 96), (2, 3, 96), (2, 3, 1000), (2, 2, 0)])
-def test_column_lane_data_flow_equals_oracle(emul, oracle, p, n, small_rows):
+@pytest.mark.parametrize("p,n,small_rows,structured", [(1, 3, 96, 0), (2, 2, 96, 0), (2, 3, 96, 1), (2, 3, 1000, 0), (2, 2, 0, 1)])
+def test_column_lane_data_flow_equals_oracle(emul, oracle, p, n, small_rows, structured):
+    """structured = 1: the column step that uses the structural zeros of the P2 reference gradients (P2S)."""
     mesh = M.kuhn_cube(n, p, jitter=0.2)
     x = M.random_displacement(mesh)[: mesh.n_bases * 3]
-    prob, e, g, v, stats = run_emulation(emul, oracle, mesh, x, small_rows)
+    prob, e, g, v, stats = run_emulation(emul, oracle, mesh, x, small_rows, structured)
     H = prob.assemble_hessian(x)
     assert v.size == H.values.size and not np.isnan(v).any()  # every column was flushed exactly once
     e_ref = prob.assemble_energy(x)
@@ -80,7 +81,7 @@ def test_column_lane_data_flow_equals_oracle(emul, oracle, p, n, small_rows):
     if small_rows == 1000:
         assert stats[1] == 0
     # fixed summation order: bitwise reproducible
-    _, e2, g2, v2, _ = run_emulation(emul, oracle, mesh, x, small_rows)
+    _, e2, g2, v2, _ = run_emulation(emul, oracle, mesh, x, small_rows, structured)
     assert e2 == e and np.array_equal(g2, g) and np.array_equal(v2, v)
 
 
