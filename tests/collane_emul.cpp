@@ -110,3 +110,18 @@ extern "C" int collane_emulate(int n_loc, int n_qp, int n_el, int n_bases, const
 		return emulate<10, 4, false>(n_el, n_bases, conn, adj_off, adj, jit, detj, qw, ref_grads, lam, mu, x, small_rows, energy, grad, values, stats);
 	return -1;
 }
+
+// schedule statistics only (no math): n_groups[2], rows_max[2], total_steps, busy_slots, bytes of the incidence table
+extern "C" int collane_schedule_stats(int n_loc, int n_el, int n_bases, const int32_t *conn, const int32_t *adj_off, const int32_t *adj, int small_rows,
+										int64_t *stats)
+{
+	const Schedule S = build_schedule(n_el, n_loc, n_bases, conn, adj_off, adj, small_rows);
+	stats[0] = S.n_groups[0];
+	stats[1] = S.n_groups[1];
+	stats[2] = S.rows_max[0];
+	stats[3] = S.rows_max[1];
+	stats[4] = S.total_steps;
+	stats[5] = S.busy_slots;
+	stats[6] = int64_t(S.inc.size() * sizeof(uint32_t));
+	return 0;
+}
