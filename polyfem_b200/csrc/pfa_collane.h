@@ -112,38 +112,63 @@ namespace pfa
 			return (0.5 * mu * (sq - 3.0 - 2.0 * lJ) + 0.5 * lam * lJ * lJ) * da;
 		}
 
+		// The 25 entries of a record that the lane of component mm needs (lane-dependent ADDRESSES, fixed register names)
+		struct LaneRecord
+		{
+			double K[6], ta[3], tb[3], c0[3], c1[3], c2[3], pj[3], c1da;
+		};
+		PFA_HD void load_lane_record(const double *rec, int mm, int ra, int rb, LaneRecord &r)
+		{
+			for (int k = 0; k < 6; ++k)
+				r.K[k] = rec[k];
+			for (int k = 0; k < 3; ++k)
+			{
+				r.ta[k] = rec[6 + ra * 3 + k];
+				r.tb[k] = rec[6 + rb * 3 + k];
+				r.c0[k] = rec[15 + mm * 3 + k];
+				r.c1[k] = rec[15 + ra * 3 + k];
+				r.c2[k] = rec[15 + rb * 3 + k];
+				r.pj[k] = rec[24 + mm * 3 + k];
+			}
+			r.c1da = rec[33];
+		}
+
 		// One incident element's contribution to the column of dof (its local node ri, component mm):
 		//   acc[j][s] += H[(ri, mm), (j, (mm + s) % 3)]   (rotated by mm, like the row-lane kernel)      g_row += G[(ri, mm)]
 		// rec: [NQ][kRec] of the element; rg: reference gradients [NQ][NL][3] (row side, index depends on the lane);
 		// G: the same table as the column operand (device: __constant__ memory, uniform index).
+		// The record of the next quadrature point is loaded before the current one is used (software pipelining: the kernel
+		// runs 1-2 warps per scheduler, so the load latency has to be covered inside the warp).
 		// P2S: the table has the structural zeros / equal components of the P2 tet basis (checked on the host by
 		// p2_table_structured, pfa_kernels.cu): 20 instead of 30 DFMA-pipe operations per (column component, quadrature point)
 		template <int NL, int NQ, bool P2S, class ColTable>
 		PFA_HD void column_of_element(const double *rec_e, const double *rg, int ri, int mm, const ColTable &G, double (*acc)[3], double &g_row)
 		{
 			const int ra = (mm + 1) % 3, rb = (mm + 2) % 3;
-			// not unrolled on the device: keeps the register count of the column kernel at the row-lane kernel's level (the
-			// column table is then read with a uniform run-time index, LDC)
+			LaneRecord nxt;
+			load_lane_record(rec_e, mm, ra, rb, nxt);
+			// not unrolled on the device: keeps the register count of the column kernel near the row-lane kernel's (the column
+			// table is then read with a uniform run-time index, LDC)
 #if defined(__CUDA_ARCH__)
 #pragma unroll 1
 #endif
 			for (int qq = 0; qq < NQ; ++qq)
 			{
-				const double *rec = rec_e + qq * kRec;
+				const LaneRecord rec = nxt;
+				if (qq + 1 < NQ)
+					load_lane_record(rec_e + (qq + 1) * kRec, mm, ra, rb, nxt);
 				const double *gr = rg + (qq * NL + ri) * 3;
 				const double g0 = gr[0], g1 = gr[1], g2 = gr[2];
-				const double *pj = rec + 24 + mm * 3;
-				g_row = fma(g0, pj[0], fma(g1, pj[1], fma(g2, pj[2], g_row)));
-				const double K00 = rec[0], K01 = rec[1], K02 = rec[2], K11 = rec[3], K12 = rec[4], K22 = rec[5];
+				g_row = fma(g0, rec.pj[0], fma(g1, rec.pj[1], fma(g2, rec.pj[2], g_row)));
+				const double K00 = rec.K[0], K01 = rec.K[1], K02 = rec.K[2], K11 = rec.K[3], K12 = rec.K[4], K22 = rec.K[5];
 				const double v0 = K00 * g0 + K01 * g1 + K02 * g2;
 				const double v1 = K01 * g0 + K11 * g1 + K12 * g2;
 				const double v2 = K02 * g0 + K12 * g1 + K22 * g2;
-				const double *ta = rec + 6 + ra * 3, *tb = rec + 6 + rb * 3;
+				const double *ta = rec.ta, *tb = rec.tb;
 				const double b0 = tb[1] * g2 - tb[2] * g1, b1 = tb[2] * g0 - tb[0] * g2, b2 = tb[0] * g1 - tb[1] * g0; //  t_b x g
 				const double a0 = ta[2] * g1 - ta[1] * g2, a1 = ta[0] * g2 - ta[2] * g0, a2 = ta[1] * g0 - ta[0] * g1; // -t_a x g
-				const double *cj = rec + 15;
-				const double cA = rec[33] * (cj[mm * 3 + 0] * g0 + cj[mm * 3 + 1] * g1 + cj[mm * 3 + 2] * g2);
-				const double *c0r = cj + mm * 3, *c1r = cj + ra * 3, *c2r = cj + rb * 3;
+				const double cA = rec.c1da * (rec.c0[0] * g0 + rec.c0[1] * g1 + rec.c0[2] * g2);
+				const double *c0r = rec.c0, *c1r = rec.c1, *c2r = rec.c2;
 				double Y[3][3];
 				Y[0][0] = fma(cA, c0r[0], v0);
 				Y[0][1] = fma(cA, c0r[1], v1);
