@@ -7,7 +7,8 @@
 //   collane_records_kernel   thread <-> (element, quadrature point): gathers x, writes the 34-double record to global
 //                            memory, reduces the energy
 //   collane_columns_kernel   warp <-> group of 10 nodes (3 lanes each); per step every slot takes one incident element
-//                            of its node, adds its 3*NL entries to the lane's private strip (shared memory, address
+//                            of its node (the 10 records are staged in shared memory by coalesced copies, one step
+//                            ahead through registers), adds its 3*NL entries to the lane's private strip (shared memory, address
 //                            row*32 + lane: bank = lane, no conflicts, no atomics); after the last step the strip is the
 //                            finished CSC column and is streamed to values[], the gradient entry is stored: every output
 //                            is written exactly once, in a fixed summation order (bitwise reproducible), no zero fill
@@ -86,18 +87,24 @@ namespace pfa
 
 		template <int NL, int NQ, int SLOT, bool P2S>
 		__global__ void __launch_bounds__(256) collane_columns_kernel(const DeviceMesh m, const AssembleArgs a, const ColumnLaneTables t, const double *__restrict__ rec, int g_begin,
-											   int g_end, int strip_rows)
+																	  int g_end, int strip_rows)
 		{
+			using CL = ColLayout<NQ>;
+			constexpr int RECQ = CL::RECQ, SSTR = CL::SSTR, PER_LANE = CL::PER_LANE;
+			constexpr unsigned kFull = 0xffffffffu;
 			extern __shared__ double smem[];
 			double *s_rg = smem; // [NQ][NL][3]: row-side reference gradients (lane-dependent index)
 			for (int k = threadIdx.x; k < NQ * NL * 3; k += blockDim.x)
 				s_rg[k] = m.ref_grads[k];
 			__syncthreads();
 			const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, warps = blockDim.x >> 5;
-			double *strip = smem + ((NQ * NL * 3 + 1) & ~1) + size_t(warp) * strip_rows * 32 + lane;
+			double *wbase = smem + ((NQ * NL * 3 + 1) & ~1) + size_t(warp) * (size_t(CL::STAGE) + size_t(strip_rows) * 32);
+			double *stage = wbase;
+			double *strip = wbase + CL::STAGE + lane;
 			const int slot = lane / 3, mm = lane - slot * 3;
 			const bool active = lane < 3 * kSlots;
 			const uint4 *inc = reinterpret_cast<const uint4 *>(t.inc);
+			const uint4 idle = make_uint4(0xffffffffu, 0u, 0u, 0u);
 			for (int g = g_begin + blockIdx.x * warps + warp; g < g_end; g += gridDim.x * warps)
 			{
 				const int rows = t.grp_rows[g], s0 = t.grp_off[g], s1 = t.grp_off[g + 1];
@@ -105,30 +112,62 @@ namespace pfa
 				for (int r = 0; r < rows; ++r)
 					strip[r * 32] = 0.0;
 				double g_acc = 0.0;
+				// records of the first step -> registers (every lane takes PER_LANE consecutive-by-32 doubles of the 10 records)
+				uint4 w_nxt = (active && s0 < s1) ? inc[size_t(s0) * kSlots + slot] : idle;
+				double R[PER_LANE];
+#pragma unroll
+				for (int i = 0; i < PER_LANE; ++i)
+				{
+					int tt, kk;
+					CL::staged(lane, i, tt, kk);
+					const int et = __shfl_sync(kFull, int(w_nxt.x), min(3 * tt, 31));
+					R[i] = (tt < kSlots && et >= 0) ? rec[size_t(et) * RECQ + kk] : 0.0;
+				}
 				for (int s = s0; s < s1; ++s)
 				{
-					if (!active)
-						continue;
-					const uint4 w = inc[size_t(s) * kSlots + slot];
-					if (w.x == 0xffffffffu)
-						continue;
-					const int ri = (w.w >> 16) & 0xff;
-					double acc[NL][3];
+					const uint4 w = w_nxt;
 #pragma unroll
-					for (int j = 0; j < NL; ++j)
-						acc[j][0] = acc[j][1] = acc[j][2] = 0.0;
-					column_of_element<NL, NQ, P2S>(rec + size_t(w.x) * NQ * kRec, s_rg, ri, mm, ConstTable<SLOT>(), acc, g_acc);
-					// column component n = (mm + shift) % 3 of column node j goes to row 3*k_j + n of this lane's column
-					const int n1 = mm == 2 ? 0 : mm + 1, n2 = mm == 0 ? 2 : mm - 1;
-#pragma unroll
-					for (int j = 0; j < NL; ++j)
+					for (int i = 0; i < PER_LANE; ++i)
 					{
-						const uint32_t word = j < 4 ? w.y : (j < 8 ? w.z : w.w);
-						const int k3 = 3 * int((word >> (8 * (j & 3))) & 0xffu);
-						strip[(k3 + mm) * 32] += acc[j][0];
-						strip[(k3 + n1) * 32] += acc[j][1];
-						strip[(k3 + n2) * 32] += acc[j][2];
+						int tt, kk;
+						CL::staged(lane, i, tt, kk);
+						if (tt < kSlots)
+							stage[tt * SSTR + kk] = R[i];
 					}
+					__syncwarp();
+					if (s + 1 < s1) // warp-uniform: the next step's records travel while this step is computed
+					{
+						w_nxt = active ? inc[size_t(s + 1) * kSlots + slot] : idle;
+#pragma unroll
+						for (int i = 0; i < PER_LANE; ++i)
+						{
+							int tt, kk;
+							CL::staged(lane, i, tt, kk);
+							const int et = __shfl_sync(kFull, int(w_nxt.x), min(3 * tt, 31));
+							R[i] = (tt < kSlots && et >= 0) ? rec[size_t(et) * RECQ + kk] : 0.0;
+						}
+					}
+					if (active && w.x != 0xffffffffu)
+					{
+						const int ri = (w.w >> 16) & 0xff;
+						double acc[NL][3];
+#pragma unroll
+						for (int j = 0; j < NL; ++j)
+							acc[j][0] = acc[j][1] = acc[j][2] = 0.0;
+						column_of_element<NL, NQ, P2S, false>(stage + slot * SSTR, s_rg, ri, mm, ConstTable<SLOT>(), acc, g_acc);
+						// column component n = (mm + shift) % 3 of column node j goes to row 3*k_j + n of this lane's column
+						const int n1 = mm == 2 ? 0 : mm + 1, n2 = mm == 0 ? 2 : mm - 1;
+#pragma unroll
+						for (int j = 0; j < NL; ++j)
+						{
+							const uint32_t word = j < 4 ? w.y : (j < 8 ? w.z : w.w);
+							const int k3 = 3 * int((word >> (8 * (j & 3))) & 0xffu);
+							strip[(k3 + mm) * 32] += acc[j][0];
+							strip[(k3 + n1) * 32] += acc[j][1];
+							strip[(k3 + n2) * 32] += acc[j][2];
+						}
+					}
+					__syncwarp(); // the stage is overwritten at the top of the next step
 				}
 				if (b >= 0)
 				{
@@ -192,13 +231,13 @@ namespace pfa
 				const int ng = t.n_groups[c];
 				if (ng > 0)
 				{
-					const size_t strip_bytes = sizeof(double) * 32 * size_t(t.rows_max[c]);
-					int warps = int((size_t(smem_max) - table_bytes) / strip_bytes);
+					const size_t warp_bytes = ColLayout<NQ>::warp_bytes(t.rows_max[c]); // record stage + strips
+					int warps = int((size_t(smem_max) - table_bytes) / warp_bytes);
 					if (warps < 1)
 						return cudaErrorInvalidConfiguration;
 					warps = std::min(warps, 8);
 					const int grid = std::max(1, std::min((ng + warps - 1) / warps, sm_count));
-					kern<<<grid, warps * 32, table_bytes + size_t(warps) * strip_bytes, st>>>(m, a, t, t.records, g0, g0 + ng, t.rows_max[c]);
+					kern<<<grid, warps * 32, table_bytes + size_t(warps) * warp_bytes, st>>>(m, a, t, t.records, g0, g0 + ng, t.rows_max[c]);
 					if ((err = cudaGetLastError()) != cudaSuccess)
 						return err;
 				}

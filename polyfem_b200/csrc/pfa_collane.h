@@ -137,16 +137,17 @@ namespace pfa
 		//   acc[j][s] += H[(ri, mm), (j, (mm + s) % 3)]   (rotated by mm, like the row-lane kernel)      g_row += G[(ri, mm)]
 		// rec: [NQ][kRec] of the element; rg: reference gradients [NQ][NL][3] (row side, index depends on the lane);
 		// G: the same table as the column operand (device: __constant__ memory, uniform index).
-		// The record of the next quadrature point is loaded before the current one is used (software pipelining: the kernel
-		// runs 1-2 warps per scheduler, so the load latency has to be covered inside the warp).
 		// P2S: the table has the structural zeros / equal components of the P2 tet basis (checked on the host by
 		// p2_table_structured, pfa_kernels.cu): 20 instead of 30 DFMA-pipe operations per (column component, quadrature point)
-		template <int NL, int NQ, bool P2S, class ColTable>
+		// PIPE: load the next point's record entries before the current point's math (for records read from global memory;
+		// the kernel stages records in shared memory and uses PIPE = false)
+		template <int NL, int NQ, bool P2S, bool PIPE, class ColTable>
 		PFA_HD void column_of_element(const double *rec_e, const double *rg, int ri, int mm, const ColTable &G, double (*acc)[3], double &g_row)
 		{
 			const int ra = (mm + 1) % 3, rb = (mm + 2) % 3;
 			LaneRecord nxt;
-			load_lane_record(rec_e, mm, ra, rb, nxt);
+			if (PIPE)
+				load_lane_record(rec_e, mm, ra, rb, nxt);
 			// not unrolled on the device: keeps the register count of the column kernel near the row-lane kernel's (the column
 			// table is then read with a uniform run-time index, LDC)
 #if defined(__CUDA_ARCH__)
@@ -154,9 +155,15 @@ namespace pfa
 #endif
 			for (int qq = 0; qq < NQ; ++qq)
 			{
-				const LaneRecord rec = nxt;
-				if (qq + 1 < NQ)
-					load_lane_record(rec_e + (qq + 1) * kRec, mm, ra, rb, nxt);
+				LaneRecord rec;
+				if (PIPE)
+				{
+					rec = nxt;
+					if (qq + 1 < NQ)
+						load_lane_record(rec_e + (qq + 1) * kRec, mm, ra, rb, nxt);
+				}
+				else
+					load_lane_record(rec_e + qq * kRec, mm, ra, rb, rec);
 				const double *gr = rg + (qq * NL + ri) * 3;
 				const double g0 = gr[0], g1 = gr[1], g2 = gr[2];
 				g_row = fma(g0, rec.pj[0], fma(g1, rec.pj[1], fma(g2, rec.pj[2], g_row)));
@@ -216,6 +223,26 @@ namespace pfa
 				}
 			}
 		}
+
+		// Shared memory of one warp of the column kernel: the records of the (up to) 10 elements of the current step, staged
+		// cooperatively (a lane-private read of 10 different records costs 10 L1 wavefronts per load instruction; coalesced
+		// copies cost 2), followed by the strips. Slot stride odd: the 10 slots read their records conflict-free.
+		template <int NQ>
+		struct ColLayout
+		{
+			static constexpr int RECQ = NQ * kRec;                       // doubles per element record
+			static constexpr int SSTR = RECQ | 1;                        // slot stride in the stage
+			static constexpr int STAGE = (kSlots * SSTR + 1) & ~1;       // doubles per warp
+			static constexpr int PER_LANE = (kSlots * RECQ + 31) / 32;   // staged doubles per lane and step
+			// the i-th double lane `lane` stages: slot tt (>= kSlots: nothing), offset kk inside that slot's element record
+			static PFA_HD void staged(int lane, int i, int &tt, int &kk)
+			{
+				const int idx = lane + 32 * i;
+				tt = idx / RECQ;
+				kk = idx - tt * RECQ;
+			}
+			static PFA_HD size_t warp_bytes(int strip_rows) { return sizeof(double) * (size_t(STAGE) + size_t(strip_rows) * 32); }
+		};
 
 		// ---- host side: which lane works on which (element, node) incidence, in which order ----
 		// Nodes are put into groups of kSlots nodes (one per warp slot); a warp processes a group from its first to its last

@@ -45,6 +45,21 @@ namespace
 			const int rows = S.grp_rows[size_t(g)], s0 = S.grp_off[size_t(g)], s1 = S.grp_off[size_t(g) + 1];
 			if (rows > S.rows_max[g < S.n_groups[0] ? 0 : 1])
 				return -2;
+			// the kernel stages the records of a step in shared memory (ColLayout): 32 lanes x PER_LANE doubles
+			using CL = ColLayout<NQ>;
+			std::vector<double> stages(size_t(s1 - s0) * CL::STAGE, -12345.0);
+			for (int s = s0; s < s1; ++s)
+				for (int lane = 0; lane < 32; ++lane)
+					for (int i = 0; i < CL::PER_LANE; ++i)
+					{
+						int tt, kk;
+						CL::staged(lane, i, tt, kk);
+						if (tt >= kSlots)
+							continue;
+						const uint32_t e_t = S.inc[(size_t(s) * kSlots + tt) * 4];
+						if (e_t != 0xffffffffu)
+							stages[size_t(s - s0) * CL::STAGE + size_t(tt) * CL::SSTR + kk] = rec[size_t(e_t) * CL::RECQ + kk];
+					}
 			for (int lane = 0; lane < 3 * kSlots; ++lane)
 			{
 				const int slot = lane / 3, m = lane - slot * 3;
@@ -65,7 +80,7 @@ namespace
 					double acc[NL][3];
 					for (int j = 0; j < NL; ++j)
 						acc[j][0] = acc[j][1] = acc[j][2] = 0.0;
-					column_of_element<NL, NQ, P2S>(rec.data() + size_t(e) * NQ * kRec, ref_grads, ri, m, G, acc, g_acc);
+					column_of_element<NL, NQ, P2S, P2S>(stages.data() + size_t(s - s0) * CL::STAGE + size_t(slot) * CL::SSTR, ref_grads, ri, m, G, acc, g_acc);
 					for (int j = 0; j < NL; ++j)
 					{
 						const int k = (w[1 + j / 4] >> (8 * (j % 4))) & 0xff;
