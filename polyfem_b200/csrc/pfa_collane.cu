@@ -26,6 +26,11 @@ namespace pfa
 		constexpr int kSlotDoubles = 4 * 10 * 3;
 		__constant__ double c_cl_refgrad[2][kSlotDoubles]; // slot 0: P1 [1][4][3], slot 1: P2 [4][10][3]
 
+#ifndef PFA_CL_COOP_FLUSH
+#define PFA_CL_COOP_FLUSH 1 // 0: every lane streams its own column (30 sectors per store instruction)
+#endif
+		constexpr int kFlushLd = 33; // leading dimension of the 32 x 32 transposition block of the cooperative flush
+
 		template <int SLOT>
 		struct ConstTable
 		{
@@ -169,18 +174,40 @@ namespace pfa
 					}
 					__syncwarp(); // the stage is overwritten at the top of the next step
 				}
-				if (b >= 0)
+				// column 3b+mm of values[] starts at 9*adj_off[b] + mm*3*deg(b) and has 3*deg(b) rows
+				const int off = b >= 0 ? m.adj_off[b] : 0, deg = b >= 0 ? m.adj_off[b + 1] - off : 0;
+				if (b >= 0 && a.grad != nullptr)
+					a.grad[size_t(b) * 3 + mm] = a.scale * g_acc;
+				if (a.values != nullptr)
 				{
-					// column 3b+mm of values[] starts at 9*adj_off[b] + mm*3*deg(b) and has 3*deg(b) rows
-					const int off = m.adj_off[b], deg = m.adj_off[b + 1] - off;
-					if (a.values != nullptr)
+					if constexpr (CL::STAGE >= 32 * kFlushLd && PFA_CL_COOP_FLUSH)
+					{
+						// cooperative flush: a lane-private store touches 30 sectors per instruction. Blocks of 32 rows go through
+						// the (now idle) record stage with leading dimension 33 - written by columns, read by rows, both
+						// conflict-free - so that one store instruction writes 32 consecutive rows of ONE column
+						for (int r0 = 0; r0 < rows; r0 += 32)
+						{
+#pragma unroll 4
+							for (int rr = 0; rr < 32; ++rr)
+								if (r0 + rr < rows)
+									stage[rr * kFlushLd + lane] = strip[(r0 + rr) * 32];
+							__syncwarp();
+							for (int c = 0; c < 3 * kSlots; ++c)
+							{
+								const int off_c = __shfl_sync(kFull, off, c), deg_c = __shfl_sync(kFull, deg, c);
+								const int r = r0 + lane;
+								if (r < 3 * deg_c)
+									a.values[size_t(off_c) * 9 + size_t(c % 3) * 3 * deg_c + r] = a.scale * stage[lane * kFlushLd + c];
+							}
+							__syncwarp();
+						}
+					}
+					else if (b >= 0)
 					{
 						double *dst = a.values + (size_t(off) * 9 + size_t(mm) * 3 * deg);
 						for (int r = 0; r < 3 * deg; ++r)
 							dst[r] = a.scale * strip[r * 32];
 					}
-					if (a.grad != nullptr)
-						a.grad[size_t(b) * 3 + mm] = a.scale * g_acc;
 				}
 			}
 		}

@@ -39,7 +39,6 @@ namespace
 		const Schedule S = build_schedule(n_el, NL, n_bases, conn, adj_off, adj, small_rows);
 		const HostTable G{ref_grads};
 		const int n_groups = S.n_groups[0] + S.n_groups[1];
-		std::vector<double> strip;
 		for (int g = 0; g < n_groups; ++g)
 		{
 			const int rows = S.grp_rows[size_t(g)], s0 = S.grp_off[size_t(g)], s1 = S.grp_off[size_t(g) + 1];
@@ -60,11 +59,11 @@ namespace
 						if (e_t != 0xffffffffu)
 							stages[size_t(s - s0) * CL::STAGE + size_t(tt) * CL::SSTR + kk] = rec[size_t(e_t) * CL::RECQ + kk];
 					}
+			std::vector<double> strips(size_t(rows) * 32, 0.0); // [row][lane], as in shared memory
 			for (int lane = 0; lane < 3 * kSlots; ++lane)
 			{
 				const int slot = lane / 3, m = lane - slot * 3;
 				const int b = S.grp_node[size_t(g) * kSlots + slot];
-				strip.assign(size_t(rows), 0.0); // strip[row] stands for strip[row*32 + lane]
 				double g_acc = 0.0;
 				for (int s = s0; s < s1; ++s)
 				{
@@ -89,19 +88,49 @@ namespace
 							const int n = (m + sft) % 3;
 							if (3 * k + n >= rows)
 								return -5;
-							strip[size_t(3 * k + n)] += acc[j][sft];
+							strips[size_t(3 * k + n) * 32 + lane] += acc[j][sft];
 						}
 					}
 				}
-				if (b < 0)
-					continue;
-				// flush: column 3b+m starts at 9*adj_off[b] + m*3*deg(b) and has 3*deg(b) rows
-				const int deg = adj_off[b + 1] - adj_off[b];
-				double *dst = values + size_t(adj_off[b]) * 9 + size_t(m) * 3 * deg;
-				for (int r = 0; r < 3 * deg; ++r)
-					dst[r] = strip[size_t(r)];
-				grad[size_t(b) * 3 + m] = g_acc;
+				if (b >= 0)
+					grad[size_t(b) * 3 + m] = g_acc;
 			}
+			// flush. Column 3b+m starts at 9*adj_off[b] + m*3*deg(b) and has 3*deg(b) rows.
+			constexpr int kFlushLd = 33;
+			if (CL::STAGE >= 32 * kFlushLd)
+			{
+				// the kernel's cooperative flush: 32-row blocks through a 32 x 33 transposition buffer (the record stage)
+				std::vector<double> tb(size_t(CL::STAGE), -777.0);
+				for (int r0 = 0; r0 < rows; r0 += 32)
+				{
+					for (int lane = 0; lane < 32; ++lane)
+						for (int rr = 0; rr < 32; ++rr)
+							if (r0 + rr < rows)
+								tb[size_t(rr) * kFlushLd + lane] = strips[size_t(r0 + rr) * 32 + lane];
+					for (int c = 0; c < 3 * kSlots; ++c)
+					{
+						const int bc = S.grp_node[size_t(g) * kSlots + c / 3];
+						const int off_c = bc >= 0 ? adj_off[bc] : 0, deg_c = bc >= 0 ? adj_off[bc + 1] - off_c : 0;
+						for (int lane = 0; lane < 32; ++lane)
+						{
+							const int r = r0 + lane;
+							if (r < 3 * deg_c)
+								values[size_t(off_c) * 9 + size_t(c % 3) * 3 * deg_c + r] = tb[size_t(lane) * kFlushLd + c];
+						}
+					}
+				}
+			}
+			else
+				for (int lane = 0; lane < 3 * kSlots; ++lane)
+				{
+					const int b = S.grp_node[size_t(g) * kSlots + lane / 3], m = lane % 3;
+					if (b < 0)
+						continue;
+					const int deg = adj_off[b + 1] - adj_off[b];
+					double *dst = values + size_t(adj_off[b]) * 9 + size_t(m) * 3 * deg;
+					for (int r = 0; r < 3 * deg; ++r)
+						dst[r] = strips[size_t(r) * 32 + lane];
+				}
 		}
 		stats[0] = S.n_groups[0];
 		stats[1] = S.n_groups[1];
