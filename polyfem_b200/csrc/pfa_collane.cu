@@ -45,6 +45,8 @@ namespace pfa
 			const int64_t e64 = t / NQ;
 			const int q = int(t - e64 * NQ);
 			const bool valid = e64 < m.n_el;
+			constexpr int kRecLd = kRec + 1; // odd: conflict-free record-per-thread writes
+			__shared__ double s_rec[128 * kRecLd];
 			double e_q = 0.0;
 			if (valid)
 			{
@@ -64,7 +66,20 @@ namespace pfa
 					J[k] = m.jit[size_t(e) * 9 + k];
 				const double da = m.detj[e] * m.qweights[q];
 				const size_t mi = size_t(e) * m.mat_stride + (m.mat_stride == 1 ? 0 : q);
-				e_q = qp_record<NL>(J, da, m.lambda[mi], m.mu[mi], u, m.ref_grads + size_t(q) * NL * 3, rec_out + (size_t(e) * NQ + q) * kRec);
+				e_q = qp_record<NL>(J, da, m.lambda[mi], m.mu[mi], u, m.ref_grads + size_t(q) * NL * 3, s_rec + size_t(threadIdx.x) * kRecLd);
+			}
+			// the 32 records of a warp are contiguous in global memory: write them with coalesced stores (a thread storing its
+			// own record touches 32 lines per instruction)
+			__syncwarp();
+			{
+				const int lane = threadIdx.x & 31;
+				const int64_t t0 = t - lane; // first (element, qp) of this warp
+				const int64_t n_valid = min(int64_t(32), int64_t(m.n_el) * NQ - t0);
+				const double *src = s_rec + size_t(threadIdx.x - lane) * kRecLd;
+				double *dst = rec_out + size_t(t0) * kRec;
+				if (n_valid > 0)
+					for (int idx = lane; idx < int(n_valid) * kRec; idx += 32)
+						dst[idx] = src[(idx / kRec) * kRecLd + idx % kRec];
 			}
 			if (a.energy != nullptr || a.energy_per_el != nullptr)
 			{
