@@ -208,7 +208,7 @@ def main():
                     "(hung on the round-1 stack: NCCL 2.28 point-to-point under capture; never the default)")
     ap.add_argument("--overlap", action="store_true", help="multi-GPU: interface elements first, exchange on a side stream under the "
                     "assembly of the rest (measured no faster than the plain order in round 1)")
-    ap.add_argument("--flags", type=int, default=0, help="pfa_mesh_desc.flags (1 = keep the caller's element order)")
+    ap.add_argument("--flags", type=int, default=0, help="pfa_mesh_desc.flags (1 = keep the caller's element order, 2 = in-kernel zero fill, 4 = column-lane kernels, single GPU)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
