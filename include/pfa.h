@@ -115,8 +115,8 @@ extern "C"
  * on B200 in round 1: the cleared lines do not stay in L2 until their first RED) */
 #define PFA_FLAG_INKERNEL_ZERO 2
 /* NeoHookean P1/P2 on affine tets: pfa_grad_hess / pfa_hessian of the full (unreduced, unprojected) system run the
- * column-lane (owner-computes) kernels instead of the row-lane reduction kernel: every entry of values[] and of the
- * gradient is summed in a fixed order and written once - bitwise reproducible results, no zero fill. Costs a schedule
+ * column-lane (owner-computes) kernels instead of the row-lane reduction kernel: the energy and every entry of values[] and of the
+ * gradient are summed in a fixed order and written once - bitwise reproducible results, no zero fill. Costs a schedule
  * of 16 bytes per (element, local node) and a record buffer of 272 bytes per (element, quadrature point). Opt-in (also
  * PFA_COLUMN_LANE=1 in the environment); not the default until it has been measured on the GPU. */
 #define PFA_FLAG_COLUMN_LANE 4

@@ -323,7 +323,7 @@ namespace
 		prof_begin(h, kname);
 		cudaError_t ce = use_cl ? launch_column_lane(dm, a, h->cl, h->sm_count, h->stream) : launch_assemble(dm, a, linear, h->sm_count, h->stream, &kname);
 		if (use_cl)
-			h->launches += 1 + (h->cl.n_groups[0] > 0 && h->cl.n_groups[1] > 0 ? 1 : 0); // records + one column kernel per strip class
+			h->launches += 1 + (a.energy ? 1 : 0) + (h->cl.n_groups[0] > 0 && h->cl.n_groups[1] > 0 ? 1 : 0); // records (+ energy sum) + one column kernel per strip class
 		if (h->profiling && !h->prof.empty() && !h->prof.back().stop_recorded)
 			h->prof.back().name = kname;
 		prof_end(h);
@@ -602,7 +602,7 @@ extern "C"
 					UP(h->cl.grp_off, S.grp_off.data(), S.grp_off.size(), int32_t);
 					UP(h->cl.grp_rows, S.grp_rows.data(), S.grp_rows.size(), int32_t);
 					UP(h->cl.inc, S.inc.data(), S.inc.size(), uint32_t);
-					if ((rc = dev_alloc<double>(h, &h->cl.records, ne * nq * size_t(collane::kRec))) != PFA_OK)
+					if ((rc = dev_alloc<double>(h, &h->cl.records, ne * nq * size_t(collane::kRec))) != PFA_OK || (rc = dev_alloc<double>(h, &h->cl.block_energy, (ne * nq + 127) / 128)) != PFA_OK)
 						return bail(rc);
 					for (int c = 0; c < 2; ++c)
 					{

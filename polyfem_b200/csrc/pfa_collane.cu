@@ -38,7 +38,7 @@ namespace pfa
 		};
 
 		template <int NL, int NQ>
-		__global__ void __launch_bounds__(128) collane_records_kernel(const DeviceMesh m, const AssembleArgs a, double *__restrict__ rec_out)
+		__global__ void __launch_bounds__(128) collane_records_kernel(const DeviceMesh m, const AssembleArgs a, double *__restrict__ rec_out, double *__restrict__ block_energy)
 		{
 			static_assert(32 % NQ == 0, "the quadrature points of an element sit in one warp");
 			const int64_t t = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -99,10 +99,30 @@ namespace pfa
 					if ((threadIdx.x & 31) == 0)
 						s_e[threadIdx.x >> 5] = w;
 					__syncthreads();
-					if (threadIdx.x == 0)
-						atomicAdd(a.energy, (s_e[0] + s_e[1] + s_e[2] + s_e[3]) * a.scale);
+					if (threadIdx.x == 0) // per-block partial sums, added up in a fixed order by collane_energy_kernel
+						block_energy[blockIdx.x] = s_e[0] + s_e[1] + s_e[2] + s_e[3];
 				}
 			}
+		}
+
+		// energy = scale * sum of the per-block partial sums, in a fixed order (one block): like values[] and the gradient,
+		// the energy of the column-lane path is the same bit pattern from call to call
+		__global__ void __launch_bounds__(1024) collane_energy_kernel(const double *__restrict__ block_energy, int n_blocks, double scale, double *__restrict__ energy)
+		{
+			__shared__ double s[1024];
+			double t = 0.0;
+			for (int k = threadIdx.x; k < n_blocks; k += 1024)
+				t += block_energy[k];
+			s[threadIdx.x] = t;
+			__syncthreads();
+			for (int o = 512; o > 0; o >>= 1)
+			{
+				if (int(threadIdx.x) < o)
+					s[threadIdx.x] += s[threadIdx.x + o];
+				__syncthreads();
+			}
+			if (threadIdx.x == 0)
+				*energy = s[0] * scale;
 		}
 
 		template <int NL, int NQ, int SLOT, bool P2S>
@@ -255,9 +275,16 @@ namespace pfa
 			if (err != cudaSuccess)
 				return err;
 			const int64_t threads = int64_t(m.n_el) * NQ;
-			collane_records_kernel<NL, NQ><<<unsigned((threads + 127) / 128), 128, 0, st>>>(m, a, t.records);
+			const unsigned rec_blocks = unsigned((threads + 127) / 128);
+			collane_records_kernel<NL, NQ><<<rec_blocks, 128, 0, st>>>(m, a, t.records, t.block_energy);
 			if ((err = cudaGetLastError()) != cudaSuccess)
 				return err;
+			if (a.energy != nullptr)
+			{
+				collane_energy_kernel<<<1, 1024, 0, st>>>(t.block_energy, int(rec_blocks), a.scale, a.energy);
+				if ((err = cudaGetLastError()) != cudaSuccess)
+					return err;
+			}
 			if (a.values == nullptr && a.grad == nullptr)
 				return cudaSuccess;
 			auto kern = collane_columns_kernel<NL, NQ, SLOT, P2S>;

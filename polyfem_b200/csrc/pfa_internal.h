@@ -90,10 +90,11 @@ namespace pfa
 		const int32_t *grp_rows = nullptr; // [G]
 		const uint32_t *inc = nullptr;     // [total_steps][10][4]
 		double *records = nullptr;         // [n_el][n_qp][34]
+		double *block_energy = nullptr;    // [ceil(n_el * n_qp / 128)] partial energy sums of the records kernel
 	};
 	bool column_lane_applies(int material, int n_loc, int n_qp);
 	// records kernel + one column kernel per strip class; writes every entry of values[] / grad[] exactly once (no zero
-	// fill needed), accumulates a.energy (zeroed by the caller)
+	// fill needed) and stores a.energy (fixed summation order as well)
 	cudaError_t launch_column_lane(const DeviceMesh &m, const AssembleArgs &a, const ColumnLaneTables &t, int sm_count, cudaStream_t st);
 
 	// kernel launchers (pfa_kernels.cu). Return cudaError_t of the launch.

@@ -29,10 +29,10 @@ def test_column_lane_equals_oracle_and_is_reproducible(oracle, p, n, jitter):
     assert abs(e - e_ref) <= REL_TOL * abs(e_ref)
     assert_vector_close(g, g_ref)
     assert_values_close(H.outer, H.inner, v, H.values)
-    # Hessian-only entry and a second fused call: gradient and values bit for bit the same (fixed summation order)
+    # Hessian-only entry and a second fused call: energy, gradient and values bit for bit the same (fixed summation order)
     v2 = h.hessian(x)
     e3, g3, v3 = h.grad_hess(x)
-    assert np.array_equal(v2, v) and np.array_equal(v3, v) and np.array_equal(g3, g)
+    assert np.array_equal(v2, v) and np.array_equal(v3, v) and np.array_equal(g3, g) and e3 == e
     # and the default (row-lane) handle agrees to rounding
     h0 = gpu_handle(mesh, "NeoHookean", t)
     e0, g0, v0 = h0.grad_hess(x)
