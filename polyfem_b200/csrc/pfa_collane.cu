@@ -305,8 +305,12 @@ namespace pfa
 					if (warps < 1)
 						return cudaErrorInvalidConfiguration;
 					warps = std::min(warps, 8);
-					const int grid = std::max(1, std::min((ng + warps - 1) / warps, sm_count));
-					kern<<<grid, warps * 32, table_bytes + size_t(warps) * warp_bytes, st>>>(m, a, t, t.records, g0, g0 + ng, t.rows_max[c]);
+					const size_t smem = table_bytes + size_t(warps) * warp_bytes;
+					int per_sm = 1; // small strips (P1) leave room for more than one CTA per SM
+					if ((err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, warps * 32, smem)) != cudaSuccess)
+						return err;
+					const int grid = std::max(1, std::min((ng + warps - 1) / warps, sm_count * std::max(per_sm, 1)));
+					kern<<<grid, warps * 32, smem, st>>>(m, a, t, t.records, g0, g0 + ng, t.rows_max[c]);
 					if ((err = cudaGetLastError()) != cudaSuccess)
 						return err;
 				}
