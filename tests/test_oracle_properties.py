@@ -131,3 +131,24 @@ def test_project_to_psd_properties(oracle):
     wa, va = np.linalg.eigh(a)
     ref = (va * np.maximum(wa, 0)) @ va.T
     assert np.abs(p - ref).max() < 1e-10 * np.abs(a).max()
+
+
+def test_nodes_without_elements_give_empty_columns(oracle):
+    """n_bases larger than the nodes the elements touch (a sub-mesh of a bigger space, the local meshes of a partition): the
+    reference's matrix has size n_bases * dim with empty columns there (SparseMatrixCache::init(size), MatrixCache.cpp:28-47),
+    the gradient entries are zero and the values are those of the mesh without the extra nodes."""
+    from polyfem_b200 import mesh as M, tables
+    mesh = M.kuhn_cube(2, 2, jitter=0.2)
+    t = tables.reference_tables(2)
+    lam, mu = M.lame_from_E_nu(1e5, 0.3)
+    nb = mesh.n_bases + 3
+    x0 = M.random_displacement(mesh)[: mesh.n_bases * 3]
+    x = np.concatenate([x0, np.full(9, 9.0)])
+    big = oracle.OracleProblem("NeoHookean", mesh.conn, mesh.vertices, nb, t["points"], t["weights"], t["grad"], lam=lam, mu=mu)
+    ref = oracle.problem_from_mesh(mesh, "NeoHookean")
+    H, H0 = big.assemble_hessian(x), ref.assemble_hessian(x0)
+    assert H.outer.size == 3 * nb + 1 and np.all(H.outer[-10:] == H0.values.size)
+    assert np.array_equal(H.inner, H0.inner) and np.array_equal(H.values, H0.values)
+    g = big.assemble_gradient(x)
+    assert np.array_equal(g[: x0.size], ref.assemble_gradient(x0)) and not g[x0.size:].any()
+    assert big.assemble_energy(x) == ref.assemble_energy(x0)
