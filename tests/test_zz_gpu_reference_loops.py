@@ -71,24 +71,3 @@ def test_cuda_linear_elasticity_energy_equals_reference_function(k):
     e_ref = float(LE[f"le_energy_{k}"])
     assert abs(h.energy(u.reshape(-1)) - e_ref) <= REL_TOL * e_ref
 
-
-def test_nodes_without_elements_give_empty_columns(oracle):
-    """n_bases larger than the nodes the elements touch: empty columns, zero gradient entries, same values (the oracle's
-    behaviour, tests/test_oracle_properties.py::test_nodes_without_elements_give_empty_columns)."""
-    from polyfem_b200 import capi, mesh as M, tables
-    mesh = M.kuhn_cube(2, 2, jitter=0.2)
-    t = tables.reference_tables(2)
-    lam, mu = M.lame_from_E_nu(1e5, 0.3)
-    nb = mesh.n_bases + 3
-    x0 = M.random_displacement(mesh)[: mesh.n_bases * 3]
-    x = np.concatenate([x0, np.full(9, 9.0)])
-    ref = oracle.OracleProblem("NeoHookean", mesh.conn, mesh.vertices, nb, t["points"], t["weights"], t["grad"], lam=lam, mu=mu)
-    h = capi.Handle("NeoHookean", mesh.conn, nb, t["weights"], t["grad"], vertices=mesh.vertices, lam=lam, mu=mu)
-    H = ref.assemble_hessian(x)
-    outer, inner = h.pattern()
-    assert outer.tobytes() == H.outer.tobytes() and inner.tobytes() == H.inner.tobytes()
-    e, g, v = h.grad_hess(x)
-    assert abs(e - ref.assemble_energy(x)) <= REL_TOL * abs(e)
-    assert_vector_close(g, ref.assemble_gradient(x))
-    assert not g[x0.size:].any()
-    assert_values_close(outer, inner, v, H.values)
