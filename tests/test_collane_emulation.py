@@ -95,3 +95,47 @@ def test_column_lane_nan_propagation(emul, oracle):
     assert np.isnan(e) and np.isnan(prob.assemble_energy(x))
     assert_vector_close(g, prob.assemble_gradient(x))
     assert_values_close(H.outer, H.inner, v, H.values)
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_owned_columns_need_no_exchange(emul, oracle, world):
+    """The multi-GPU consequence of owner-computes columns: the element partition of polyfem_b200/dist.py gives
+    every rank all elements incident to its owned nodes (own + ghost elements), so the column-lane data flow run on a rank's
+    local mesh already yields the FINISHED columns and gradient entries of the nodes it owns - no interface exchange.
+    Checked per rank against the single-mesh oracle, matching rows through global node ids (local numbering differs)."""
+    from polyfem_b200 import dist as pdist
+    mesh = M.kuhn_cube(3, 2, jitter=0.2)
+    x = M.random_displacement(mesh)[: mesh.n_bases * 3]
+    ref = oracle.problem_from_mesh(mesh, "NeoHookean")
+    H = ref.assemble_hessian(x).to_scipy().tocsc()
+    g_ref = ref.assemble_gradient(x)
+    owned_total = 0
+    for rank in range(world):
+        part = pdist.partition_elements(mesh, rank, world)
+        # the local mesh with the geometry of own AND ghost elements (global element ids in partition order)
+        bounds = pdist.element_ranges(mesh.n_elements, world)
+        elem_rank = np.searchsorted(np.asarray(bounds[1:]), np.arange(mesh.n_elements), side="right")
+        node_owner = np.full(mesh.n_bases, world)
+        np.minimum.at(node_owner, mesh.conn.reshape(-1), np.repeat(elem_rank, mesh.conn.shape[1]))
+        ghost = np.nonzero((node_owner[mesh.conn] == rank).any(axis=1) & (elem_rank != rank))[0]
+        elems = np.concatenate([part.own_elements, ghost])
+        assert elems.size == part.conn.shape[0] and np.array_equal(part.l2g[part.conn], mesh.conn[elems])
+
+        class Local:  # what run_emulation reads of a mesh
+            p, conn, vertices, n_bases, n_elements = mesh.p, part.conn, mesh.vertices[elems], part.n_bases, elems.size
+        x_loc = np.ascontiguousarray(x.reshape(-1, 3)[part.l2g].reshape(-1))
+        _, _, g, v, _ = run_emulation(emul, oracle, Local, x_loc, 96, 1)
+        adj_off, adj = node_adjacency(Local)
+        for b in np.nonzero(part.owner == rank)[0]:
+            gb = int(part.l2g[b])
+            deg = adj_off[b + 1] - adj_off[b]
+            rows_g = part.l2g[adj[adj_off[b]:adj_off[b + 1]]]
+            for m in range(3):
+                col = H[:, 3 * gb + m]
+                assert col.nnz == 3 * deg, "an owned node misses neighbours on its rank"
+                mine = v[9 * adj_off[b] + m * 3 * deg: 9 * adj_off[b] + (m + 1) * 3 * deg].reshape(deg, 3)
+                want = np.asarray(H[(3 * rows_g[:, None] + np.arange(3)[None, :]).reshape(-1), 3 * gb + m].todense()).reshape(deg, 3)
+                assert np.abs(mine - want).max() <= REL_TOL * np.abs(want).max()
+            assert np.abs(g[3 * b:3 * b + 3] - g_ref[3 * gb:3 * gb + 3]).max() <= REL_TOL * np.abs(g_ref).max()
+            owned_total += 1
+    assert owned_total == mesh.n_bases  # every node is owned by exactly one rank
