@@ -115,11 +115,13 @@ extern "C"
  * on B200 in round 1: the cleared lines do not stay in L2 until their first RED) */
 #define PFA_FLAG_INKERNEL_ZERO 2
 /* NeoHookean P1/P2 on affine tets: pfa_grad_hess / pfa_hessian of the full (unreduced, unprojected) system run the
- * column-lane (owner-computes) kernels instead of the row-lane reduction kernel: the energy and every entry of values[] and of the
- * gradient are summed in a fixed order and written once - bitwise reproducible results, no zero fill. Costs a schedule
- * of 16 bytes per (element, local node) and a record buffer of 272 bytes per (element, quadrature point). Opt-in (also
- * PFA_COLUMN_LANE=1 in the environment); not the default until it has been measured on the GPU. */
+ * owner-computes (column-lane) kernels: the energy and every entry of values[] and of the gradient are summed in a fixed
+ * order and written exactly once - bitwise reproducible results, no atomics, no zero fill. Costs a schedule of 16 bytes
+ * per (element, local node) and a record buffer of 432 bytes per P2 element (144 per P1 element). This is the DEFAULT
+ * since round 2 (the flag is accepted and has no effect); PFA_FLAG_ROW_LANE (or PFA_ROW_LANE=1 in the environment)
+ * selects the round-1 row-lane reduction kernel (red.global.add.f64 into a zero-filled values[]) instead. */
 #define PFA_FLAG_COLUMN_LANE 4
+#define PFA_FLAG_ROW_LANE 8
 
 	typedef struct pfa_handle pfa_handle;
 

@@ -50,7 +50,8 @@ class MeshDesc(ctypes.Structure):
 # pfa_mesh_desc.flags (include/pfa.h)
 FLAG_KEEP_ELEMENT_ORDER = 1
 FLAG_INKERNEL_ZERO = 2
-FLAG_COLUMN_LANE = 4  # NeoHookean P1/P2: owner-computes kernels (bitwise reproducible, no zero fill); opt-in
+FLAG_COLUMN_LANE = 4  # accepted, no effect: the owner-computes kernels are the default for NeoHookean P1/P2
+FLAG_ROW_LANE = 8  # NeoHookean P1/P2: the round-1 row-lane reduction kernels (RED into a zero-filled values[])
 
 
 class PfaError(RuntimeError):

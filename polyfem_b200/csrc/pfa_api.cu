@@ -1,7 +1,7 @@
 // C-ABI layer of libpfa.so (include/pfa.h): handle lifetime, host<->device staging,
 // error translation. No CPU fallback: every compute entry point runs the CUDA kernels or
 // fails with PFA_ERR_NO_DEVICE / PFA_ERR_CUDA.
-#include "pfa_collane.h"
+#include "pfa_collane2.h"
 #include "pfa_internal.h"
 
 #include <chrono>
@@ -48,7 +48,7 @@ struct pfa_handle
 	double *d_energy = nullptr;
 	int *d_counter = nullptr;
 	int32_t epoch = 0; // in-kernel zero-fill generation (row-lane kernels)
-	ColumnLaneTables cl; // opt-in owner-computes path (PFA_FLAG_COLUMN_LANE)
+	ColumnLane2Tables cl; // owner-computes path (default for NeoHookean P1 / P2 on affine elements)
 
 	// Dirichlet projection (pfa_set_constrained_dofs)
 	bool has_constraints = false;
@@ -130,6 +130,15 @@ namespace
 #ifndef PFA_REST_BATCH_QUOTA
 #define PFA_REST_BATCH_QUOTA 4
 #endif
+	// owner-computes schedule (pfa_collane2.h): strip rows of the small class and steps per chunk; the environment
+	// variables are for tuning experiments only
+	inline int env_int(const char *name, int dflt)
+	{
+		const char *v = std::getenv(name);
+		return v ? std::atoi(v) : dflt;
+	}
+	const int kSmallRows = env_int("PFA_CL_SMALL_ROWS", 96);
+	const int kChunkSteps = env_int("PFA_CL_CHUNK_STEPS", 48);
 	constexpr int kRestBatchQuota = PFA_REST_BATCH_QUOTA; // pfa_grad_hess_part(PFA_PART_REST): warp batches per warp
 
 	void prof_begin(pfa_handle *h, const char *name, bool is_kernel = true)
@@ -321,9 +330,9 @@ namespace
 			return PFA_OK; // empty part: outputs are cleared (or left), nothing to launch
 		const char *kname = use_cl ? "assemble_nh_column_lane(records+columns)" : "assemble";
 		prof_begin(h, kname);
-		cudaError_t ce = use_cl ? launch_column_lane(dm, a, h->cl, h->sm_count, h->stream) : launch_assemble(dm, a, linear, h->sm_count, h->stream, &kname);
-		if (use_cl)
-			h->launches += 1 + (a.energy ? 1 : 0) + (h->cl.n_groups[0] > 0 && h->cl.n_groups[1] > 0 ? 1 : 0); // records (+ energy sum) + one column kernel per strip class
+		int cl_launches = 0;
+		cudaError_t ce = use_cl ? launch_column_lane2(dm, a, h->cl, h->sm_count, h->stream, &cl_launches) : launch_assemble(dm, a, linear, h->sm_count, h->stream, &kname);
+		h->launches += cl_launches; // records (+ energy sum) + one column kernel per strip class
 		if (h->profiling && !h->prof.empty() && !h->prof.back().stop_recorded)
 			h->prof.back().name = kname;
 		prof_end(h);
@@ -587,28 +596,31 @@ extern "C"
 			PFA_CUDA(h, cudaMemsetAsync(m.zflag, 0, size_t(m.n_batches) * sizeof(int32_t), h->stream));
 			}
 			PFA_CUDA(h, cudaStreamSynchronize(h->stream)); // cstride, zoff, zruns are locals
-			// opt-in owner-computes path: schedule of (element, node) incidences + record buffer
-			static const bool cl_env = [] { const char *v = std::getenv("PFA_COLUMN_LANE"); return v && std::atoi(v) != 0; }();
+			// owner-computes path (default): schedule of (element, node) incidences + record buffer
+			static const bool rl_env = [] { const char *v = std::getenv("PFA_ROW_LANE"); return v && std::atoi(v) != 0; }();
 			int max_deg = 0;
 			for (size_t b = 0; b + 1 < hp.adj_off.size(); ++b)
 				max_deg = std::max(max_deg, hp.adj_off[b + 1] - hp.adj_off[b]);
-			if (((d->flags & PFA_FLAG_COLUMN_LANE) || cl_env) && affine && column_lane_applies(m.material, m.n_loc, m.n_qp) && max_deg < 256 && d->n_ghost_elements == 0)
+			if (!(d->flags & PFA_FLAG_ROW_LANE) && !rl_env && affine && column_lane2_applies(m.material, m.n_loc, m.n_qp) && max_deg < 128 && d->n_ghost_elements == 0)
 			{
 				try
 				{
-					// strips of at most 96 rows (24 KB per warp) form the first launch, the rest (P2 vertex nodes) the second
-					const collane::Schedule S = collane::build_schedule(m.n_el, m.n_loc, m.n_bases, conn_in, hp.adj_off.data(), hp.adj.data(), 96);
-					UP(h->cl.grp_node, S.grp_node.data(), S.grp_node.size(), int32_t);
+					// columns of at most kSmallRows strip rows form the first launch, the rest (P2 vertex nodes) the second;
+					// chunks of about kChunkSteps steps are handed out to the warps
+					const cl2::Schedule S = cl2::build_schedule(m.n_el, m.n_loc, m.n_bases, conn_in, hp.adj_off.data(), hp.adj.data(), kSmallRows, kChunkSteps);
+					UP(h->cl.grp_info, S.grp_info.data(), S.grp_info.size(), int32_t);
 					UP(h->cl.grp_off, S.grp_off.data(), S.grp_off.size(), int32_t);
 					UP(h->cl.grp_rows, S.grp_rows.data(), S.grp_rows.size(), int32_t);
+					UP(h->cl.chunk_off, S.chunk_off.data(), S.chunk_off.size(), int32_t);
 					UP(h->cl.inc, S.inc.data(), S.inc.size(), uint32_t);
-					if ((rc = dev_alloc<double>(h, &h->cl.records, ne * nq * size_t(collane::kRec))) != PFA_OK || (rc = dev_alloc<double>(h, &h->cl.block_energy, (ne * nq + 127) / 128)) != PFA_OK)
+					if ((rc = dev_alloc<double>(h, &h->cl.records, ne * column_lane2_record_doubles(m.n_qp))) != PFA_OK || (rc = dev_alloc<double>(h, &h->cl.block_energy, (ne + 127) / 128)) != PFA_OK || (rc = dev_alloc<int>(h, &h->cl.counters, 2)) != PFA_OK)
 						return bail(rc);
 					for (int c = 0; c < 2; ++c)
 					{
-						h->cl.n_groups[c] = S.n_groups[c];
+						h->cl.n_chunks[c] = S.n_chunks[c];
 						h->cl.rows_max[c] = S.rows_max[c];
 					}
+					h->cl.n_record_elements = m.n_el;
 					h->cl.enabled = 1;
 					PFA_CUDA(h, cudaStreamSynchronize(h->stream)); // S is a local
 				}

@@ -1,0 +1,443 @@
+// Owner-computes (column-lane) NeoHookean assembly for affine P1 / P2 tets: the default path of pfa_grad_hess / pfa_hessian
+// for the full matrix. Math, record layout and schedule: pfa_collane2.h (also compiled into the CPU emulation
+// tests/collane2_emul.cpp, which is checked against the oracle).
+//
+//   cl2_records_kernel   thread <-> element: gathers x, writes the element record (54 doubles for P2: A = F J^-1, c1t, c2t,
+//                        mu*da per quadrature point and K = J J^T) to global memory through shared memory (coalesced),
+//                        reduces the energy in a fixed order
+//   cl2_columns_kernel   one warp per CTA <-> chunk of node groups. A group is 5 nodes; node slot s is served by lane
+//                        triples s (lanes 3s..3s+2) and 5+s (lanes 16+3s..), one lane per column component, each triple
+//                        on its own incident element per step. The 10 element records of a step are fetched by TMA
+//                        (cp.async.bulk, one copy per triple, completion on an mbarrier, two steps ahead in a
+//                        double-buffered stage); every lane adds its 3*NL entries to the strip column of its dof
+//                        (shared memory, address row*16 + column: bank = column; half-warp 0 updates before half-warp 1;
+//                        the first contribution to a row is a store, so strips are never cleared). After the last step
+//                        the strip is the finished CSC column: 16-row blocks are transposed through a 16 x 17 buffer
+//                        and written with coalesced stores; the gradient entry is stored. Every output is written
+//                        exactly once, in a fixed summation order (bitwise reproducible), no atomics, no zero fill.
+#include "pfa_collane2.h"
+#include "pfa_internal.h"
+
+#include <cstring>
+#include <mutex>
+
+namespace pfa
+{
+	namespace
+	{
+		using namespace cl2;
+		constexpr int kSlotDoubles = 4 * 10 * 3;
+		__constant__ double c_cl2_refgrad[2][kSlotDoubles]; // slot 0: P1 [1][4][3], slot 1: P2 [4][10][3]
+		constexpr unsigned kFull = 0xffffffffu;
+		constexpr int kTbLd = 17; // leading dimension of the 16 x 16 transposition block of the flush
+
+		template <int SLOT>
+		struct ConstTable
+		{
+			__device__ __forceinline__ double operator[](int i) const { return c_cl2_refgrad[SLOT][i]; }
+		};
+
+		// ---------------------------------------------------------------- records
+		template <int NL, int NQ, int SLOT>
+		__global__ void __launch_bounds__(128) cl2_records_kernel(const DeviceMesh m, const AssembleArgs a, const int n_own, double *__restrict__ rec_out, double *__restrict__ block_energy)
+		{
+			constexpr int RECD = Rec<NQ>::D;
+			constexpr int LD = RECD | 1; // odd: conflict-free record-per-thread writes
+			extern __shared__ __align__(16) double s_rec[];
+			const int64_t e64 = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+			const bool valid = e64 < m.n_el;
+			double e_el = 0.0;
+			if (valid)
+			{
+				const int e = int(e64);
+				double u[NL * 3];
+#pragma unroll
+				for (int i = 0; i < NL; ++i)
+				{
+					const size_t g = size_t(m.conn[size_t(e) * NL + i]);
+					u[i * 3 + 0] = a.x[g * 3 + 0];
+					u[i * 3 + 1] = a.x[g * 3 + 1];
+					u[i * 3 + 2] = a.x[g * 3 + 2];
+				}
+				double J[9];
+#pragma unroll
+				for (int k = 0; k < 9; ++k)
+					J[k] = m.jit[size_t(e) * 9 + k];
+				const size_t mi = size_t(e) * m.mat_stride;
+				e_el = element_record<NL, NQ>(J, m.detj[e], m.qweights, m.lambda + mi, m.mu + mi, m.mat_stride, u, ConstTable<SLOT>(), s_rec + size_t(threadIdx.x) * LD);
+				if (e >= n_own)
+					e_el = 0.0; // ghost element (multi-GPU): its record is needed, its energy belongs to another rank
+				else if (a.energy_per_el != nullptr)
+					a.energy_per_el[m.elem_id ? m.elem_id[e] : e] = e_el;
+			}
+			// the 32 records of a warp are contiguous in global memory: coalesced stores
+			__syncwarp();
+			{
+				const int lane = threadIdx.x & 31;
+				const int64_t e0 = e64 - lane;
+				const int n_valid = int(min(int64_t(32), int64_t(m.n_el) - e0));
+				const double *src = s_rec + size_t(threadIdx.x - lane) * LD;
+				double *dst = rec_out + size_t(e0) * RECD;
+				for (int idx = lane; idx < n_valid * RECD; idx += 32)
+					dst[idx] = src[(idx / RECD) * LD + idx % RECD];
+			}
+			if (a.energy != nullptr)
+			{
+				double w = e_el;
+#pragma unroll
+				for (int o = 16; o > 0; o >>= 1)
+					w += __shfl_xor_sync(kFull, w, o);
+				__shared__ double s_e[4];
+				if ((threadIdx.x & 31) == 0)
+					s_e[threadIdx.x >> 5] = w;
+				__syncthreads();
+				if (threadIdx.x == 0) // per-block partial sums, added up in a fixed order by cl2_energy_kernel
+					block_energy[blockIdx.x] = s_e[0] + s_e[1] + s_e[2] + s_e[3];
+			}
+		}
+
+		// energy = scale * sum of the per-block partial sums, in a fixed order (one block)
+		__global__ void __launch_bounds__(1024) cl2_energy_kernel(const double *__restrict__ block_energy, int n_blocks, double scale, double *__restrict__ energy)
+		{
+			__shared__ double s[1024];
+			double t = 0.0;
+			for (int k = threadIdx.x; k < n_blocks; k += 1024)
+				t += block_energy[k];
+			s[threadIdx.x] = t;
+			__syncthreads();
+			for (int o = 512; o > 0; o >>= 1)
+			{
+				if (int(threadIdx.x) < o)
+					s[threadIdx.x] += s[threadIdx.x + o];
+				__syncthreads();
+			}
+			if (threadIdx.x == 0)
+				*energy = s[0] * scale;
+		}
+
+		// ---------------------------------------------------------------- TMA / mbarrier primitives (sm_90+ PTX)
+		__device__ __forceinline__ uint32_t smem_u32(const void *p) { return uint32_t(__cvta_generic_to_shared(p)); }
+		__device__ __forceinline__ void mbar_init(uint32_t bar, int count)
+		{
+			asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+		}
+		__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes)
+		{
+			asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+		}
+		__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity)
+		{
+			uint32_t ok;
+			asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+						 : "=r"(ok)
+						 : "r"(bar), "r"(parity)
+						 : "memory");
+			return ok != 0;
+		}
+		// global -> shared bulk copy (TMA), bytes a multiple of 16, both addresses 16-byte aligned; completion = complete_tx on the mbarrier
+		__device__ __forceinline__ void tma_load(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar)
+		{
+			asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
+						 : "memory");
+		}
+
+		// shared memory of the one-warp CTA, in doubles
+		template <int NL, int NQ>
+		struct WarpLayout
+		{
+			static constexpr int RECD = Rec<NQ>::D;
+			static constexpr int STAGE = kTriples * RECD;     // one buffer: 10 element records (each 16-byte aligned: RECD is even)
+			static constexpr int BARS = 0;                    // 2 mbarriers (2 doubles)
+			static constexpr int STAGES = 2;                  // buffers
+			static constexpr int OFF_STAGE = 2;
+			static constexpr int OFF_TB = OFF_STAGE + STAGES * STAGE;
+			static constexpr int OFF_RG = OFF_TB + ((16 * kTbLd + 1) & ~1);
+			static constexpr int OFF_INFO = OFF_RG + NL * NQ * 4; // 5 x 4 ints = 10 doubles
+			static constexpr int OFF_STRIP = OFF_INFO + 10;
+			static_assert(RECD % 2 == 0 && OFF_STAGE % 2 == 0 && OFF_RG % 2 == 0 && OFF_STRIP % 2 == 0, "16-byte alignment");
+			static size_t bytes(int strip_rows) { return sizeof(double) * (size_t(OFF_STRIP) + size_t(strip_rows) * kStripLd); }
+		};
+
+		template <int NL, int NQ, int SLOT, bool P2S>
+		__global__ void __launch_bounds__(32) cl2_columns_kernel(const DeviceMesh m, const AssembleArgs a, const ColumnLane2Tables t, const int cls, const int chunk_begin,
+																 const int chunk_end)
+		{
+			using L = WarpLayout<NL, NQ>;
+			constexpr int RECD = L::RECD;
+			constexpr uint32_t REC_BYTES = RECD * sizeof(double);
+			extern __shared__ __align__(16) double smem[];
+			const int lane = threadIdx.x;
+			const int half = lane >> 4, within = lane & 15;
+			const bool active = within < 15;
+			const int ns = active ? within / 3 : 0;
+			const int mm = within - 3 * (within / 3);
+			const int tr = half * kNodes + ns;
+			const bool leader = active && mm == 0;
+			double *stage = smem + L::OFF_STAGE;
+			double *tb = smem + L::OFF_TB;
+			double *s_rg = smem + L::OFF_RG;
+			int *s_info = reinterpret_cast<int *>(smem + L::OFF_INFO);
+			double *strip = smem + L::OFF_STRIP + within;
+			const uint32_t bar0 = smem_u32(smem), bar1 = bar0 + 8;
+			if (lane == 0)
+			{
+				mbar_init(bar0, 1);
+				mbar_init(bar1, 1);
+				asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+			}
+			// own-node reference gradients, padded rows [ri][q][4]
+			for (int k = lane; k < NL * NQ * 4; k += 32)
+			{
+				const int c = k & 3, q = (k >> 2) % NQ, i = (k >> 2) / NQ;
+				s_rg[k] = c < 3 ? m.ref_grads[(q * NL + i) * 3 + c] : 0.0;
+			}
+			asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+			__syncwarp();
+
+			const uint4 *inc = reinterpret_cast<const uint4 *>(t.inc);
+			const uint4 idle = make_uint4(kIdle, 0u, 0u, 0u);
+			const uint32_t stage_u32 = smem_u32(stage);
+			// one TMA copy per busy triple into buffer `buf`; lane 0 arms the barrier with the byte count first
+			auto issue = [&](const uint4 &w, int buf) {
+				const bool want = leader && w.x != kIdle;
+				const unsigned mask = __ballot_sync(kFull, want);
+				const uint32_t bar = buf ? bar1 : bar0;
+				if (lane == 0)
+					mbar_arrive_expect_tx(bar, uint32_t(__popc(mask)) * REC_BYTES);
+				__syncwarp();
+				if (want)
+					tma_load(stage_u32 + uint32_t(buf * L::STAGE + tr * RECD) * 8u, t.records + size_t(w.x) * RECD, REC_BYTES, bar);
+			};
+
+			unsigned it = 0; // steps this warp has consumed: buffer = it & 1, barrier parity = (it >> 1) & 1
+			for (;;)
+			{
+				int chunk = 0;
+				if (lane == 0)
+					chunk = chunk_begin + atomicAdd(t.counters + cls, 1);
+				chunk = __shfl_sync(kFull, chunk, 0);
+				if (chunk >= chunk_end)
+					break;
+				int g = t.chunk_off[chunk];
+				const int g_end = t.chunk_off[chunk + 1];
+				const int s_begin = t.grp_off[g], s_end = t.grp_off[g_end];
+				const int4 *grp_info = reinterpret_cast<const int4 *>(t.grp_info);
+				int g_last = t.grp_off[g + 1]; // first step after group g
+				// node of my slot in the current group: (node, 9*adj_off, 3*deg, -); the next group's words are loaded one group ahead
+				int4 info = active ? grp_info[size_t(g) * kNodes + ns] : make_int4(-1, 0, 0, 0);
+				int rows_g = t.grp_rows[g];
+				int4 info_n = (active && g + 1 < g_end) ? grp_info[size_t(g + 1) * kNodes + ns] : make_int4(-1, 0, 0, 0);
+				int rows_n = g + 1 < g_end ? t.grp_rows[g + 1] : 0;
+				int last_n = g + 1 < g_end ? t.grp_off[g + 2] : 0;
+				uint4 w0 = active ? inc[size_t(s_begin) * kTriples + tr] : idle;
+				uint4 w1 = (active && s_begin + 1 < s_end) ? inc[size_t(s_begin + 1) * kTriples + tr] : idle;
+				issue(w0, int(it & 1));
+				if (s_begin + 1 < s_end)
+					issue(w1, int((it + 1) & 1));
+				double g_acc = 0.0;
+				for (int s = s_begin; s < s_end; ++s, ++it)
+				{
+					const int buf = int(it & 1);
+					const uint32_t bar = buf ? bar1 : bar0, parity = (it >> 1) & 1;
+					// the step after next: its words are needed when its copies are issued, at the end of this step
+					const uint4 w2 = (active && s + 2 < s_end) ? inc[size_t(s + 2) * kTriples + tr] : idle;
+					while (!mbar_try_wait(bar, parity))
+					{
+					}
+					const bool busy = active && w0.x != kIdle;
+					double acc[NL][3];
+#pragma unroll
+					for (int j = 0; j < NL; ++j)
+						acc[j][0] = acc[j][1] = acc[j][2] = 0.0;
+					if (busy)
+					{
+						const int ri = (w0.w >> 16) & 0xff;
+						column_of_element<NL, NQ, P2S>(stage + buf * L::STAGE + tr * RECD, s_rg + ri * (NQ * 4), mm, ConstTable<SLOT>(), acc, g_acc);
+					}
+					__syncwarp(); // every lane has read its record: the buffer can be refilled
+					if (s + 2 < s_end)
+						issue(w2, buf);
+					// strip update: row 3*k_j + (mm + shift) % 3 of my column; half-warp 0 first, then half-warp 1 (same columns)
+					const int n1 = mm == 2 ? 0 : mm + 1, n2 = mm == 0 ? 2 : mm - 1;
+#pragma unroll
+					for (int ph = 0; ph < 2; ++ph)
+					{
+						if (busy && half == ph)
+						{
+#pragma unroll
+							for (int jb = 0; jb < NL; jb += 5)
+							{
+								constexpr int JB = NL < 5 ? NL : 5;
+								double old[JB][3];
+								double *p[JB];
+#pragma unroll
+								for (int jj = 0; jj < JB; ++jj)
+								{
+									const int j = jb + jj;
+									const uint32_t word = j < 4 ? w0.y : (j < 8 ? w0.z : w0.w);
+									const uint32_t kb = (word >> (8 * (j & 3))) & 0xffu;
+									p[jj] = strip + 3 * int(kb & 0x7fu) * kStripLd;
+									const bool first = (kb & 0x80u) != 0;
+									old[jj][0] = first ? 0.0 : p[jj][mm * kStripLd];
+									old[jj][1] = first ? 0.0 : p[jj][n1 * kStripLd];
+									old[jj][2] = first ? 0.0 : p[jj][n2 * kStripLd];
+								}
+#pragma unroll
+								for (int jj = 0; jj < JB; ++jj)
+								{
+									p[jj][mm * kStripLd] = old[jj][0] + acc[jb + jj][0];
+									p[jj][n1 * kStripLd] = old[jj][1] + acc[jb + jj][1];
+									p[jj][n2 * kStripLd] = old[jj][2] + acc[jb + jj][2];
+								}
+							}
+						}
+						__syncwarp();
+					}
+					w0 = w1;
+					w1 = w2;
+					if (s + 1 == g_last)
+					{
+						// ---- group finished: gradient entries and the 15 columns ----
+						const double g_tot = g_acc + __shfl_xor_sync(kFull, g_acc, 16);
+						if (half == 0 && active && info.x >= 0 && a.grad != nullptr)
+							a.grad[size_t(info.x) * 3 + mm] = a.scale * g_tot;
+						if (half == 0 && active && mm == 0)
+							reinterpret_cast<int4 *>(s_info)[ns] = info;
+						__syncwarp();
+						for (int r0 = 0; r0 < rows_g; r0 += 16)
+						{
+#pragma unroll
+							for (int i = 0; i < 8; ++i)
+							{
+								const int rr = 2 * i + half;
+								tb[rr * kTbLd + within] = r0 + rr < rows_g ? smem[L::OFF_STRIP + (r0 + rr) * kStripLd + within] : 0.0;
+							}
+							__syncwarp();
+							const int rr = lane & 15, r = r0 + rr;
+#pragma unroll
+							for (int pp = 0; pp < 8; ++pp)
+							{
+								const int c = 2 * pp + half;
+								if (c < 15)
+								{
+									const int4 nf = reinterpret_cast<const int4 *>(s_info)[c / 3];
+									if (nf.x >= 0 && r < nf.z)
+										a.values[size_t(nf.y) + size_t(c % 3) * nf.z + r] = a.scale * tb[rr * kTbLd + c];
+								}
+							}
+							__syncwarp();
+						}
+						g_acc = 0.0;
+						++g;
+						info = info_n;
+						rows_g = rows_n;
+						g_last = last_n;
+						if (g + 1 < g_end)
+						{
+							info_n = active ? grp_info[size_t(g + 1) * kNodes + ns] : make_int4(-1, 0, 0, 0);
+							rows_n = t.grp_rows[g + 1];
+							last_n = t.grp_off[g + 2];
+						}
+					}
+				}
+			}
+		}
+
+		std::mutex g_cl2_mutex;
+		double g_cl2_shadow[16][2][kSlotDoubles];
+		bool g_cl2_valid[16][2] = {};
+
+		cudaError_t ensure_table(const DeviceMesh &m, int slot, cudaStream_t st)
+		{
+			int dev = 0;
+			cudaError_t err = cudaGetDevice(&dev);
+			if (err != cudaSuccess)
+				return err;
+			if (dev < 0 || dev >= 16 || m.ref_grads_host == nullptr)
+				return cudaErrorInvalidValue;
+			const size_t bytes = sizeof(double) * size_t(m.n_qp) * m.n_loc * 3;
+			std::lock_guard<std::mutex> lock(g_cl2_mutex);
+			if (g_cl2_valid[dev][slot] && std::memcmp(g_cl2_shadow[dev][slot], m.ref_grads_host, bytes) == 0)
+				return cudaSuccess;
+			std::memcpy(g_cl2_shadow[dev][slot], m.ref_grads_host, bytes);
+			g_cl2_valid[dev][slot] = true;
+			return cudaMemcpyToSymbolAsync(c_cl2_refgrad, g_cl2_shadow[dev][slot], bytes, sizeof(double) * size_t(slot) * kSlotDoubles, cudaMemcpyHostToDevice, st);
+		}
+
+		template <int NL, int NQ, int SLOT, bool P2S>
+		cudaError_t launch_cl2(const DeviceMesh &m, const AssembleArgs &a, const ColumnLane2Tables &t, int sm_count, cudaStream_t st, int *launches)
+		{
+			cudaError_t err = ensure_table(m, SLOT, st);
+			if (err != cudaSuccess)
+				return err;
+			constexpr int RECD = Rec<NQ>::D;
+			const int n_rec = t.n_record_elements;
+			const unsigned rec_blocks = unsigned((n_rec + 127) / 128);
+			{
+				auto rk = cl2_records_kernel<NL, NQ, SLOT>;
+				const size_t rec_smem = sizeof(double) * 128 * size_t(RECD | 1);
+				if ((err = cudaFuncSetAttribute(rk, cudaFuncAttributeMaxDynamicSharedMemorySize, int(rec_smem))) != cudaSuccess)
+					return err;
+				DeviceMesh mr = m;
+				mr.n_el = n_rec; // own + ghost elements
+				rk<<<rec_blocks, 128, rec_smem, st>>>(mr, a, m.n_el, t.records, t.block_energy);
+				if ((err = cudaGetLastError()) != cudaSuccess)
+					return err;
+				++*launches;
+			}
+			if (a.energy != nullptr)
+			{
+				cl2_energy_kernel<<<1, 1024, 0, st>>>(t.block_energy, int(rec_blocks), a.scale, a.energy);
+				if ((err = cudaGetLastError()) != cudaSuccess)
+					return err;
+				++*launches;
+			}
+			if (a.values == nullptr)
+				return cudaSuccess;
+			if ((err = cudaMemsetAsync(t.counters, 0, 2 * sizeof(int), st)) != cudaSuccess)
+				return err;
+			auto kern = cl2_columns_kernel<NL, NQ, SLOT, P2S>;
+			int dev = 0, smem_max = 0;
+			if ((err = cudaGetDevice(&dev)) != cudaSuccess || (err = cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev)) != cudaSuccess)
+				return err;
+			if ((err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max)) != cudaSuccess)
+				return err;
+			int c0 = 0;
+			for (int c = 0; c < 2; ++c)
+			{
+				const int nc = t.n_chunks[c];
+				if (nc > 0)
+				{
+					const size_t smem = WarpLayout<NL, NQ>::bytes(t.rows_max[c]);
+					if (smem > size_t(smem_max))
+						return cudaErrorInvalidConfiguration;
+					int per_sm = 1;
+					if ((err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 32, smem)) != cudaSuccess)
+						return err;
+					const int grid = std::max(1, std::min(nc, sm_count * std::max(per_sm, 1)));
+					kern<<<grid, 32, smem, st>>>(m, a, t, c, c0, c0 + nc);
+					if ((err = cudaGetLastError()) != cudaSuccess)
+						return err;
+					++*launches;
+				}
+				c0 += nc;
+			}
+			return cudaSuccess;
+		}
+	} // namespace
+
+	bool column_lane2_applies(int material, int n_loc, int n_qp)
+	{
+		return material == PFA_NEOHOOKEAN && ((n_loc == 4 && n_qp == 1) || (n_loc == 10 && n_qp == 4));
+	}
+
+	size_t column_lane2_record_doubles(int n_qp) { return size_t(n_qp) * kQpRec + 6; }
+
+	cudaError_t launch_column_lane2(const DeviceMesh &m, const AssembleArgs &a, const ColumnLane2Tables &t, int sm_count, cudaStream_t st, int *launches)
+	{
+		if (m.n_loc == 4)
+			return launch_cl2<4, 1, 0, false>(m, a, t, sm_count, st, launches);
+		// the structured column step needs the structural zeros of the P2 reference gradients (DeviceMesh::p2_structured)
+		return m.p2_structured ? launch_cl2<10, 4, 1, true>(m, a, t, sm_count, st, launches) : launch_cl2<10, 4, 1, false>(m, a, t, sm_count, st, launches);
+	}
+} // namespace pfa

@@ -78,24 +78,28 @@ namespace pfa
 		int32_t epoch = 0;           // > 0: values[] is zero-filled inside the kernel (see DeviceMesh::zoff)
 	};
 
-	// Column-lane (owner-computes) tables of a handle (pfa_collane.h / pfa_collane.cu), built at create time when the
-	// handle opts in (PFA_FLAG_COLUMN_LANE or PFA_COLUMN_LANE=1); all pointers are device memory
-	struct ColumnLaneTables
+	// Owner-computes (column-lane) tables of a handle (pfa_collane2.h / pfa_collane2.cu), built at create time for NeoHookean
+	// P1 / P2 handles on affine elements unless PFA_FLAG_ROW_LANE is given; all pointers are device memory
+	struct ColumnLane2Tables
 	{
 		int32_t enabled = 0;
-		int32_t n_groups[2] = {0, 0}; // class 0: small strips, class 1: large strips (groups of class 0 come first)
+		int32_t n_chunks[2] = {0, 0}; // class 0: small strips, class 1: large strips (chunks of class 0 come first)
 		int32_t rows_max[2] = {0, 0}; // strip rows of the two launches
-		const int32_t *grp_node = nullptr; // [G][10]
-		const int32_t *grp_off = nullptr;  // [G+1]
-		const int32_t *grp_rows = nullptr; // [G]
-		const uint32_t *inc = nullptr;     // [total_steps][10][4]
-		double *records = nullptr;         // [n_el][n_qp][34]
-		double *block_energy = nullptr;    // [ceil(n_el * n_qp / 128)] partial energy sums of the records kernel
+		int32_t n_record_elements = 0; // own + ghost elements: every element incident to a scheduled node
+		const int32_t *grp_info = nullptr;  // [G][5][4]: node, 9*adj_off, 3*deg, -
+		const int32_t *grp_off = nullptr;   // [G+1] first step of each group
+		const int32_t *grp_rows = nullptr;  // [G]
+		const int32_t *chunk_off = nullptr; // [C+1] first group of each chunk
+		const uint32_t *inc = nullptr;      // [total_steps][10][4]
+		double *records = nullptr;          // [n_record_elements][n_qp*12 + 6]
+		double *block_energy = nullptr;     // [ceil(n_record_elements / 128)] partial energy sums of the records kernel
+		int *counters = nullptr;            // [2] chunk hand-out of the two launches
 	};
-	bool column_lane_applies(int material, int n_loc, int n_qp);
-	// records kernel + one column kernel per strip class; writes every entry of values[] / grad[] exactly once (no zero
-	// fill needed) and stores a.energy (fixed summation order as well)
-	cudaError_t launch_column_lane(const DeviceMesh &m, const AssembleArgs &a, const ColumnLaneTables &t, int sm_count, cudaStream_t st);
+	bool column_lane2_applies(int material, int n_loc, int n_qp);
+	size_t column_lane2_record_doubles(int n_qp);
+	// records kernel (+ energy sum) + one column kernel per strip class; writes every entry of values[] / grad[] of the
+	// scheduled nodes exactly once (no zero fill needed) and stores a.energy (fixed summation order as well)
+	cudaError_t launch_column_lane2(const DeviceMesh &m, const AssembleArgs &a, const ColumnLane2Tables &t, int sm_count, cudaStream_t st, int *launches);
 
 	// kernel launchers (pfa_kernels.cu). Return cudaError_t of the launch.
 	cudaError_t launch_geometry_precompute(const double *vertices_dev, int n_el, double *jit, double *detj, cudaStream_t st);

@@ -1,8 +1,9 @@
-"""CPU emulation of the column-lane (owner-computes) kernels against the oracle.
+"""CPU emulation of the owner-computes (column-lane) kernels against the oracle.
 
-`polyfem_b200/csrc/pfa_collane.h` holds the record math, the per-lane column math and the host schedule of the opt-in
-column-lane kernels (`pfa_collane.cu`). `tests/collane_emul.cpp` walks groups / steps / slots / lanes on the
-CPU with exactly those functions and tables; here its energy, gradient and `values[]` are compared with the oracle
+`polyfem_b200/csrc/pfa_collane2.h` holds the element record, the per-lane column math and the host schedule of the
+owner-computes kernels (`pfa_collane2.cu`, the default NeoHookean P1/P2 path). `tests/collane2_emul.cpp` walks
+chunks / groups / steps / triples / lanes on the CPU with exactly those functions and tables (strips start as NaN: first
+contributions are stored, not added); here its energy, gradient and `values[]` are compared with the oracle
 (pattern layout = the library's: column 3b+m at 9*adj_off[b] + m*3*deg(b)), 1e-12 like the GPU parity tests.
 Each entry is summed in a fixed order, so two runs must agree bit for bit."""
 import ctypes
@@ -20,13 +21,13 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 @pytest.fixture(scope="module")
 def emul(tmp_path_factory):
-    out = str(tmp_path_factory.mktemp("collane") / "libcollane_emul.so")
-    subprocess.run(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-ffp-contract=off", os.path.join(ROOT, "tests", "collane_emul.cpp"), "-o", out],
+    out = str(tmp_path_factory.mktemp("collane") / "libcollane2_emul.so")
+    subprocess.run(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-ffp-contract=off", os.path.join(ROOT, "tests", "collane2_emul.cpp"), "-o", out],
                    check=True)
     lib = ctypes.CDLL(out)
     dp, ip = ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_int32)
-    lib.collane_emulate.argtypes = [ctypes.c_int] * 4 + [ip, ip, ip, dp, dp, dp, dp, ctypes.c_double, ctypes.c_double, dp, ctypes.c_int, ctypes.c_int, dp, dp, dp,
-                                    ctypes.POINTER(ctypes.c_int64)]
+    lib.collane2_emulate.argtypes = [ctypes.c_int] * 4 + [ip, ip, ip, dp, dp, dp, dp, dp, dp, ctypes.c_int, dp, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                     ctypes.POINTER(ctypes.c_uint8), ctypes.c_double, dp, dp, dp, ctypes.POINTER(ctypes.c_int64)]
     return lib
 
 
@@ -41,7 +42,7 @@ def node_adjacency(mesh):
     return np.cumsum(adj_off).astype(np.int32), np.ascontiguousarray(pairs[:, 1], dtype=np.int32)
 
 
-def run_emulation(lib, oracle, mesh, x, small_rows, structured=0):
+def run_emulation(lib, oracle, mesh, x, small_rows, structured=0, chunk_steps=24, owned=None, scale=1.0, lam_mu=None):
     t = tables.reference_tables(mesh.p)
     prob = oracle.problem_from_mesh(mesh, "NeoHookean")
     ne, nl, nq = mesh.n_elements, mesh.conn.shape[1], t["weights"].size
@@ -51,13 +52,18 @@ def run_emulation(lib, oracle, mesh, x, small_rows, structured=0):
         jit[e], det[e] = j[0].reshape(9), d[0]
     adj_off, adj = node_adjacency(mesh)
     conn = np.ascontiguousarray(mesh.conn, dtype=np.int32)
-    lam, mu = M.lame_from_E_nu(1e5, 0.3)
+    if lam_mu is None:
+        l0, m0 = M.lame_from_E_nu(1e5, 0.3)
+        lam_mu = (np.full(ne, l0), np.full(ne, m0))
+    lam, mu = (np.ascontiguousarray(a, dtype=np.float64) for a in lam_mu)
+    mstride = lam.size // ne
     nnz = 9 * adj.size
-    energy, grad, values, stats = np.zeros(1), np.zeros(mesh.n_bases * 3), np.full(nnz, np.nan), np.zeros(6, dtype=np.int64)
+    energy, grad, values, stats = np.zeros(1), np.full(mesh.n_bases * 3, np.nan), np.full(nnz, np.nan), np.zeros(8, dtype=np.int64)
     P = lambda a, ty=ctypes.c_double: a.ctypes.data_as(ctypes.POINTER(ty))  # noqa: E731
-    rc = lib.collane_emulate(nl, nq, ne, mesh.n_bases, P(conn, ctypes.c_int32), P(adj_off, ctypes.c_int32), P(adj, ctypes.c_int32), P(jit), P(det),
-                             P(np.ascontiguousarray(t["weights"])), P(np.ascontiguousarray(t["grad"])), lam, mu, P(np.ascontiguousarray(x)),
-                             small_rows, structured, P(energy), P(grad), P(values), P(stats, ctypes.c_int64))
+    own = None if owned is None else P(np.ascontiguousarray(owned, dtype=np.uint8), ctypes.c_uint8)
+    rc = lib.collane2_emulate(nl, nq, ne, mesh.n_bases, P(conn, ctypes.c_int32), P(adj_off, ctypes.c_int32), P(adj, ctypes.c_int32), P(jit), P(det),
+                              P(np.ascontiguousarray(t["weights"])), P(np.ascontiguousarray(t["grad"])), P(lam), P(mu), mstride, P(np.ascontiguousarray(x)),
+                              small_rows, chunk_steps, structured, own, scale, P(energy), P(grad), P(values), P(stats, ctypes.c_int64))
     assert rc == 0, f"emulation failed with code {rc}"
     return prob, float(energy[0]), grad, values, stats
 
@@ -124,8 +130,11 @@ def test_owned_columns_need_no_exchange(emul, oracle, world):
         class Local:  # what run_emulation reads of a mesh
             p, conn, vertices, n_bases, n_elements = mesh.p, part.conn, mesh.vertices[elems], part.n_bases, elems.size
         x_loc = np.ascontiguousarray(x.reshape(-1, 3)[part.l2g].reshape(-1))
-        _, _, g, v, _ = run_emulation(emul, oracle, Local, x_loc, 96, 1)
+        # only the columns of owned nodes are scheduled (what a rank of the multi-GPU path does); the rest stays untouched
+        _, _, g, v, _ = run_emulation(emul, oracle, Local, x_loc, 96, 1, owned=(part.owner == rank))
         adj_off, adj = node_adjacency(Local)
+        for b in np.nonzero(part.owner != rank)[0]:
+            assert np.isnan(v[9 * adj_off[b]:9 * adj_off[b + 1]]).all() and np.isnan(g[3 * b:3 * b + 3]).all()
         for b in np.nonzero(part.owner == rank)[0]:
             gb = int(part.l2g[b])
             deg = adj_off[b + 1] - adj_off[b]
@@ -139,3 +148,26 @@ def test_owned_columns_need_no_exchange(emul, oracle, world):
             assert np.abs(g[3 * b:3 * b + 3] - g_ref[3 * gb:3 * gb + 3]).max() <= REL_TOL * np.abs(g_ref).max()
             owned_total += 1
     assert owned_total == mesh.n_bases  # every node is owned by exactly one rank
+
+
+def test_scale_chunks_and_per_quadrature_point_materials(emul, oracle):
+    """Form weight (scale), the chunk size of the group hand-out (results must not depend on it, bit for bit) and
+    (lambda, mu) given per (element, quadrature point)."""
+    mesh = M.kuhn_cube(2, 2, jitter=0.2)
+    x = M.random_displacement(mesh)[: mesh.n_bases * 3]
+    rng = np.random.default_rng(3)
+    ne, nq = mesh.n_elements, 4
+    l0, m0 = M.lame_from_E_nu(1e5, 0.3)
+    # the oracle takes one (lambda, mu) per element: replicate them over the quadrature points for the [element][qp] layout
+    lam_e, mu_e = l0 * (1.0 + 0.3 * rng.random(ne)), m0 * (1.0 + 0.3 * rng.random(ne))
+    lam, mu = np.repeat(lam_e[:, None], nq, axis=1), np.repeat(mu_e[:, None], nq, axis=1)
+    prob, e, g, v, _ = run_emulation(emul, oracle, mesh, x, 96, 1, chunk_steps=1, scale=0.25, lam_mu=(lam, mu))
+    _, e2, g2, v2, st = run_emulation(emul, oracle, mesh, x, 96, 1, chunk_steps=10 ** 6, scale=0.25, lam_mu=(lam, mu))
+    assert e2 == e and np.array_equal(g2, g) and np.array_equal(v2, v) and st[6] + st[7] <= 2
+    from polyfem_b200 import tables as T
+    t = T.reference_tables(2)
+    prob = type(prob)("NeoHookean", mesh.conn, mesh.vertices, mesh.n_bases, t["points"], t["weights"], t["grad"], lam=lam_e, mu=mu_e, basis_order=2)
+    H = prob.assemble_hessian(x)
+    assert abs(e - 0.25 * prob.assemble_energy(x)) <= REL_TOL * abs(e)
+    assert_vector_close(g, 0.25 * prob.assemble_gradient(x))
+    assert_values_close(H.outer, H.inner, v, 0.25 * H.values)

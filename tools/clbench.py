@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Row-lane (default) against column-lane (PFA_FLAG_COLUMN_LANE) NeoHookean assembly on one GPU, device-resident buffers.
+"""Row-lane (PFA_FLAG_ROW_LANE) against column-lane (default) NeoHookean assembly on one GPU, device-resident buffers.
 
   python tools/clbench.py [--n 69] [--p 2] [--reps 10] > profiles/clbench_rNN.jsonl
 
@@ -29,7 +29,7 @@ def main():
     lam, mu = M.lame_from_E_nu(1e5, 0.3)
     x = M.random_displacement(mesh)
     out = {}
-    for name, flags in (("row_lane", 0), ("column_lane", capi.FLAG_COLUMN_LANE)):
+    for name, flags in (("row_lane", capi.FLAG_ROW_LANE), ("column_lane", 0)):
         h = capi.Handle("NeoHookean", mesh.conn, mesh.n_bases, t["weights"], t["grad"], vertices=mesh.vertices, lam=lam, mu=mu, flags=flags)
         xd = torch.from_numpy(np.ascontiguousarray(x[: h.ndof])).cuda()
         e = torch.zeros(1, dtype=torch.float64, device="cuda")
