@@ -29,7 +29,11 @@ namespace pfa
 		constexpr int kSlotDoubles = 4 * 10 * 3;
 		__constant__ double c_cl2_refgrad[2][kSlotDoubles]; // slot 0: P1 [1][4][3], slot 1: P2 [4][10][3]
 		constexpr unsigned kFull = 0xffffffffu;
-		constexpr int kTbLd = 17; // leading dimension of the 16 x 16 transposition block of the flush
+		// flush: blocks of kFlushRows strip rows x 15 columns are transposed through shared memory; with the odd leading dimension
+		// 15 the column-wise writes (16 lanes, consecutive columns) and the row-wise reads (32 lanes, consecutive rows) are both
+		// conflict-free
+		constexpr int kFlushRows = 32;
+		constexpr int kTbLd = 15;
 
 		template <int SLOT>
 		struct ConstTable
@@ -146,20 +150,27 @@ namespace pfa
 		struct WarpLayout
 		{
 			static constexpr int RECD = Rec<NQ>::D;
-			static constexpr int STAGE = kTriples * RECD;     // one buffer: 10 element records (each 16-byte aligned: RECD is even)
-			static constexpr int BARS = 0;                    // 2 mbarriers (2 doubles)
-			static constexpr int STAGES = 2;                  // buffers
-			static constexpr int OFF_STAGE = 2;
+			static constexpr int STAGE = kTriples * RECD; // one buffer: 10 element records (each 16-byte aligned: RECD is even)
+			static constexpr int STAGES = 2;              // buffers
+			static constexpr int TB = kFlushRows * kTbLd; // transposition block of the flush
+			// the flush of a group runs after the last step of the group has consumed its records and before that buffer is
+			// refilled: when a buffer is large enough (P2) the transposition block lives there
+			static constexpr bool TB_ALIAS = STAGE >= TB;
+			static constexpr int OFF_STAGE = 2; // after the 2 mbarriers
 			static constexpr int OFF_TB = OFF_STAGE + STAGES * STAGE;
-			static constexpr int OFF_RG = OFF_TB + ((16 * kTbLd + 1) & ~1);
+			static constexpr int OFF_RG = OFF_TB + (TB_ALIAS ? 0 : ((TB + 1) & ~1));
 			static constexpr int OFF_INFO = OFF_RG + NL * NQ * 4; // 5 x 4 ints = 10 doubles
 			static constexpr int OFF_STRIP = OFF_INFO + 10;
 			static_assert(RECD % 2 == 0 && OFF_STAGE % 2 == 0 && OFF_RG % 2 == 0 && OFF_STRIP % 2 == 0, "16-byte alignment");
-			static size_t bytes(int strip_rows) { return sizeof(double) * (size_t(OFF_STRIP) + size_t(strip_rows) * kStripLd); }
+			// strips in whole kFlushRows-row blocks (the flush reads whole blocks)
+			static size_t bytes(int strip_rows) { return sizeof(double) * (size_t(OFF_STRIP) + size_t((strip_rows + kFlushRows - 1) / kFlushRows * kFlushRows) * kStripLd); }
 		};
 
+#ifndef PFA_CL2_MINBLOCKS
+#define PFA_CL2_MINBLOCKS 1 // CTAs (= warps) per SM the register allocation must allow (experiments: 12 caps at 168 registers)
+#endif
 		template <int NL, int NQ, int SLOT, bool P2S>
-		__global__ void __launch_bounds__(32) cl2_columns_kernel(const DeviceMesh m, const AssembleArgs a, const ColumnLane2Tables t, const int cls, const int chunk_begin,
+		__global__ void __launch_bounds__(32, PFA_CL2_MINBLOCKS) cl2_columns_kernel(const DeviceMesh m, const AssembleArgs a, const ColumnLane2Tables t, const int cls, const int chunk_begin,
 																 const int chunk_end)
 		{
 			using L = WarpLayout<NL, NQ>;
@@ -173,8 +184,9 @@ namespace pfa
 			const int mm = within - 3 * (within / 3);
 			const int tr = half * kNodes + ns;
 			const bool leader = active && mm == 0;
+			// strip rows (times the leading dimension) of my three entries per row position: components mm, mm+1, mm+2 (mod 3)
+			const int o0 = mm * kStripLd, o1 = (mm == 2 ? 0 : mm + 1) * kStripLd, o2 = (mm == 0 ? 2 : mm - 1) * kStripLd;
 			double *stage = smem + L::OFF_STAGE;
-			double *tb = smem + L::OFF_TB;
 			double *s_rg = smem + L::OFF_RG;
 			int *s_info = reinterpret_cast<int *>(smem + L::OFF_INFO);
 			double *strip = smem + L::OFF_STRIP + within;
@@ -241,61 +253,87 @@ namespace pfa
 					const uint32_t bar = buf ? bar1 : bar0, parity = (it >> 1) & 1;
 					// the step after next: its words are needed when its copies are issued, at the end of this step
 					const uint4 w2 = (active && s + 2 < s_end) ? inc[size_t(s + 2) * kTriples + tr] : idle;
-					while (!mbar_try_wait(bar, parity))
-					{
-					}
 					const bool busy = active && w0.x != kIdle;
+					// strip offsets of the NL row positions of this element (doubles, relative to my column); bit 7 of a position byte:
+					// first contribution to these rows
+					int ko[NL];
+					unsigned fm;
+#pragma unroll
+					for (int j = 0; j < NL; ++j)
+					{
+						const uint32_t word = j < 4 ? w0.y : (j < 8 ? w0.z : w0.w);
+						ko[j] = int(__byte_perm(word, 0u, 0x4440u + (j & 3)) & 0x7fu) * (3 * kStripLd);
+					}
+					// bit 7 of the four bytes of a word -> bits 0..3
+					fm = (((w0.y >> 7) & 0x01010101u) * 0x01020408u) >> 24;
+					if (NL > 4)
+						fm |= ((((w0.z >> 7) & 0x01010101u) * 0x01020408u) >> 24) << 4 | ((((w0.w >> 7) & 0x00000101u) * 0x01020408u) >> 24) << 8;
+					// half-warp 0 starts its sums from the strip (its update is then a plain store, issued before half-warp 1
+					// reads); rows touched for the first time start from zero: the strips are never cleared
+					const bool pre = busy && half == 0;
 					double acc[NL][3];
 #pragma unroll
 					for (int j = 0; j < NL; ++j)
-						acc[j][0] = acc[j][1] = acc[j][2] = 0.0;
+					{
+						const bool ld = pre && !((fm >> j) & 1u);
+						acc[j][0] = ld ? strip[ko[j] + o0] : 0.0;
+						acc[j][1] = ld ? strip[ko[j] + o1] : 0.0;
+						acc[j][2] = ld ? strip[ko[j] + o2] : 0.0;
+					}
+					while (!mbar_try_wait(bar, parity))
+					{
+					}
 					if (busy)
 					{
 						const int ri = (w0.w >> 16) & 0xff;
 						column_of_element<NL, NQ, P2S>(stage + buf * L::STAGE + tr * RECD, s_rg + ri * (NQ * 4), mm, ConstTable<SLOT>(), acc, g_acc);
 					}
 					__syncwarp(); // every lane has read its record: the buffer can be refilled
-					if (s + 2 < s_end)
+					const bool group_ends = s + 1 == g_last;
+					// (when the group ends here, the flush uses this buffer as its transposition block first)
+					if (s + 2 < s_end && !(L::TB_ALIAS && group_ends))
 						issue(w2, buf);
-					// strip update: row 3*k_j + (mm + shift) % 3 of my column; half-warp 0 first, then half-warp 1 (same columns)
-					const int n1 = mm == 2 ? 0 : mm + 1, n2 = mm == 0 ? 2 : mm - 1;
-#pragma unroll
-					for (int ph = 0; ph < 2; ++ph)
+					if (pre)
 					{
-						if (busy && half == ph)
+#pragma unroll
+						for (int j = 0; j < NL; ++j)
 						{
+							strip[ko[j] + o0] = acc[j][0];
+							strip[ko[j] + o1] = acc[j][1];
+							strip[ko[j] + o2] = acc[j][2];
+						}
+					}
+					__syncwarp();
+					if (busy && half == 1)
+					{
 #pragma unroll
-							for (int jb = 0; jb < NL; jb += 5)
+						for (int jb = 0; jb < NL; jb += 5)
+						{
+							constexpr int JB = NL < 5 ? NL : 5;
+							double old[JB][3];
+#pragma unroll
+							for (int jj = 0; jj < JB; ++jj)
 							{
-								constexpr int JB = NL < 5 ? NL : 5;
-								double old[JB][3];
-								double *p[JB];
+								const int j = jb + jj;
+								const bool ld = !((fm >> j) & 1u);
+								old[jj][0] = ld ? strip[ko[j] + o0] : 0.0;
+								old[jj][1] = ld ? strip[ko[j] + o1] : 0.0;
+								old[jj][2] = ld ? strip[ko[j] + o2] : 0.0;
+							}
 #pragma unroll
-								for (int jj = 0; jj < JB; ++jj)
-								{
-									const int j = jb + jj;
-									const uint32_t word = j < 4 ? w0.y : (j < 8 ? w0.z : w0.w);
-									const uint32_t kb = (word >> (8 * (j & 3))) & 0xffu;
-									p[jj] = strip + 3 * int(kb & 0x7fu) * kStripLd;
-									const bool first = (kb & 0x80u) != 0;
-									old[jj][0] = first ? 0.0 : p[jj][mm * kStripLd];
-									old[jj][1] = first ? 0.0 : p[jj][n1 * kStripLd];
-									old[jj][2] = first ? 0.0 : p[jj][n2 * kStripLd];
-								}
-#pragma unroll
-								for (int jj = 0; jj < JB; ++jj)
-								{
-									p[jj][mm * kStripLd] = old[jj][0] + acc[jb + jj][0];
-									p[jj][n1 * kStripLd] = old[jj][1] + acc[jb + jj][1];
-									p[jj][n2 * kStripLd] = old[jj][2] + acc[jb + jj][2];
-								}
+							for (int jj = 0; jj < JB; ++jj)
+							{
+								const int j = jb + jj;
+								strip[ko[j] + o0] = old[jj][0] + acc[j][0];
+								strip[ko[j] + o1] = old[jj][1] + acc[j][1];
+								strip[ko[j] + o2] = old[jj][2] + acc[j][2];
 							}
 						}
-						__syncwarp();
 					}
+					__syncwarp();
 					w0 = w1;
 					w1 = w2;
-					if (s + 1 == g_last)
+					if (group_ends)
 					{
 						// ---- group finished: gradient entries and the 15 columns ----
 						const double g_tot = g_acc + __shfl_xor_sync(kFull, g_acc, 16);
@@ -304,28 +342,44 @@ namespace pfa
 						if (half == 0 && active && mm == 0)
 							reinterpret_cast<int4 *>(s_info)[ns] = info;
 						__syncwarp();
-						for (int r0 = 0; r0 < rows_g; r0 += 16)
+						double *tb = L::TB_ALIAS ? stage + buf * L::STAGE : smem + L::OFF_TB;
+						// phase 2 of the flush: this lane stores row `lane` of the 32-row block, for all 15 columns
+						double *dst[15];
+						int lim[15];
+#pragma unroll
+						for (int c = 0; c < 15; ++c)
 						{
+							const int4 nf = reinterpret_cast<const int4 *>(s_info)[c / 3];
+							dst[c] = a.values + (size_t(nf.y) + size_t(c % 3) * nf.z + lane);
+							lim[c] = nf.x >= 0 ? nf.z - lane : 0;
+						}
+						for (int r0 = 0; r0 < rows_g; r0 += kFlushRows)
+						{
+							// the strips are allocated in whole 32-row blocks: rows past the group's last row are read, never stored
+							double v[16];
 #pragma unroll
-							for (int i = 0; i < 8; ++i)
+							for (int i = 0; i < 16; ++i)
+								v[i] = smem[L::OFF_STRIP + (r0 + 2 * i + half) * kStripLd + within];
+							if (active)
 							{
-								const int rr = 2 * i + half;
-								tb[rr * kTbLd + within] = r0 + rr < rows_g ? smem[L::OFF_STRIP + (r0 + rr) * kStripLd + within] : 0.0;
+#pragma unroll
+								for (int i = 0; i < 16; ++i)
+									tb[(2 * i + half) * kTbLd + within] = v[i];
 							}
 							__syncwarp();
-							const int rr = lane & 15, r = r0 + rr;
 #pragma unroll
-							for (int pp = 0; pp < 8; ++pp)
-							{
-								const int c = 2 * pp + half;
-								if (c < 15)
-								{
-									const int4 nf = reinterpret_cast<const int4 *>(s_info)[c / 3];
-									if (nf.x >= 0 && r < nf.z)
-										a.values[size_t(nf.y) + size_t(c % 3) * nf.z + r] = a.scale * tb[rr * kTbLd + c];
-								}
-							}
+							for (int c = 0; c < 15; ++c)
+								v[c] = tb[lane * kTbLd + c];
+#pragma unroll
+							for (int c = 0; c < 15; ++c)
+								if (r0 < lim[c])
+									dst[c][r0] = a.scale * v[c];
 							__syncwarp();
+						}
+						if (L::TB_ALIAS && s + 2 < s_end)
+						{
+							asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); // generic writes of the block before the TMA refill
+							issue(w2, buf);
 						}
 						g_acc = 0.0;
 						++g;

@@ -130,15 +130,15 @@ namespace pfa
 		//   acc[j][s] += H[(j, (mm + s) % 3), (ri, mm)]   (the column, by symmetry the row; rotated by mm)     g_row += G[(ri, mm)]
 		// rec: the element record; gri[q*4 + c]: reference gradient of the lane's own local node ri at point q (row of a padded
 		// table); G: reference gradients of all nodes with a uniform index (device: __constant__ memory).
-		// All three lanes of a triple read the SAME record addresses (one broadcast wavefront per load); the lane-dependent
-		// row order of A (mm, mm+1, mm+2) is produced by selects on the loaded values.
 		// P2S: the table has the structural zeros / equal components of the P2 tet basis (p2_table_structured).
 		template <int NL, int NQ, bool P2S, class CTab>
 		PFA2_HD void column_of_element(const double *rec, const double *gri, int mm, const CTab &G, double (*acc)[3], double &g_row)
 		{
 			const double K00 = rec[NQ * kQpRec + 0], K01 = rec[NQ * kQpRec + 1], K02 = rec[NQ * kQpRec + 2];
 			const double K11 = rec[NQ * kQpRec + 3], K12 = rec[NQ * kQpRec + 4], K22 = rec[NQ * kQpRec + 5];
-			const bool m0 = mm == 0, m1 = mm == 1;
+			// rows mm, mm+1, mm+2 (mod 3) of A: lane-dependent offsets into the record (the three lanes of a triple read the three
+			// rows in rotated order)
+			const int ro0 = 3 * mm, ro1 = mm == 2 ? 0 : ro0 + 3, ro2 = mm == 0 ? 6 : ro0 - 3;
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
@@ -151,10 +151,9 @@ namespace pfa
 #endif
 				for (int c = 0; c < 3; ++c)
 				{
-					const double x0 = a[c], x1 = a[3 + c], x2 = a[6 + c];
-					r0[c] = m0 ? x0 : (m1 ? x1 : x2);
-					r1[c] = m0 ? x1 : (m1 ? x2 : x0);
-					r2[c] = m0 ? x2 : (m1 ? x0 : x1);
+					r0[c] = a[ro0 + c];
+					r1[c] = a[ro1 + c];
+					r2[c] = a[ro2 + c];
 				}
 				const double c1t = a[9], c2t = a[10], muda = a[11];
 				double c0[3], c1[3], c2[3]; // rows mm, mm+1, mm+2 of cof(A)

@@ -2,7 +2,7 @@
 // header (pfa_collane2.h: element record, per-lane column math, host schedule). It walks chunks, groups, steps, triples
 // and lanes the way the kernel does - one strip column per (node slot, component) shared by the two triples of the slot,
 // half-warp 0 updating before half-warp 1, first contributions stored instead of added (the strips start as NaN, not 0),
-// the same table words, the same address arithmetic, the 16 x 17 transposition of the flush - so that
+// the same table words, the same address arithmetic, the 32 x 15 transposition of the flush - so that
 // tests/test_collane2_emulation.py can compare the data flow with the oracle without a GPU. What it cannot check:
 // launch configuration, shared-memory sizing, the TMA / mbarrier pipeline and synchronisation of the real kernel.
 #include "../polyfem_b200/csrc/pfa_collane2.h"
@@ -80,24 +80,31 @@ namespace
 							const int ri = (w[3] >> 16) & 0xff;
 							if (e >= n_el || conn[size_t(e) * NL + ri] != b)
 								return -4;
+							// half-warp 0 starts its sums from the strip and stores them back; half-warp 1 sums from zero and adds afterwards;
+							// rows touched for the first time start from zero (the strips are never cleared)
+							int krow[NL];
+							bool first[NL];
 							double acc[NL][3];
-							for (int j = 0; j < NL; ++j)
-								acc[j][0] = acc[j][1] = acc[j][2] = 0.0;
-							column_of_element<NL, NQ, P2S>(rec.data() + size_t(e) * RECD, rgp.data() + size_t(ri) * NQ * 4, mm, G, acc, g_acc[lane]);
 							for (int j = 0; j < NL; ++j)
 							{
 								const int kb = (w[1 + j / 4] >> (8 * (j % 4))) & 0xff;
-								const int k = kb & 0x7f;
-								const bool first = (kb & 0x80) != 0;
+								krow[j] = 3 * (kb & 0x7f);
+								first[j] = (kb & 0x80) != 0;
 								for (int sft = 0; sft < 3; ++sft)
 								{
 									const int n = (mm + sft) % 3;
-									if (3 * k + n >= rows)
+									if (krow[j] + n >= rows)
 										return -5;
-									double &dst = strip[size_t(3 * k + n) * kStripLd + within];
-									dst = (first ? 0.0 : dst) + acc[j][sft];
+									acc[j][sft] = (half == 0 && !first[j]) ? strip[size_t(krow[j] + n) * kStripLd + within] : 0.0;
 								}
 							}
+							column_of_element<NL, NQ, P2S>(rec.data() + size_t(e) * RECD, rgp.data() + size_t(ri) * NQ * 4, mm, G, acc, g_acc[lane]);
+							for (int j = 0; j < NL; ++j)
+								for (int sft = 0; sft < 3; ++sft)
+								{
+									double &dst = strip[size_t(krow[j] + (mm + sft) % 3) * kStripLd + within];
+									dst = half == 0 ? acc[j][sft] : (first[j] ? 0.0 : dst) + acc[j][sft];
+								}
 						}
 				// gradient: the two lanes of a column add their partial sums
 				for (int within = 0; within < 15; ++within)
@@ -106,29 +113,28 @@ namespace
 					if (b >= 0)
 						grad[size_t(b) * 3 + within % 3] = scale * (g_acc[within] + g_acc[16 + within]);
 				}
-				// flush: blocks of 16 strip rows through a 16 x 17 transposition buffer; column 3b+m starts at 9*adj_off[b] + m*3*deg(b)
-				double tb[16 * 17];
-				for (int r0 = 0; r0 < rows; r0 += 16)
+				// flush: blocks of 32 strip rows x 15 columns through a transposition buffer with leading dimension 15; column 3b+m
+				// starts at 9*adj_off[b] + m*3*deg(b)
+				double tb[32 * 15];
+				for (int r0 = 0; r0 < rows; r0 += 32)
 				{
 					for (int lane = 0; lane < 32; ++lane)
-						for (int i = 0; i < 8; ++i)
+						for (int i = 0; i < 16; ++i)
 						{
 							const int rr = 2 * i + (lane >> 4), c = lane & 15;
-							tb[rr * 17 + c] = r0 + rr < rows ? strip[size_t(r0 + rr) * kStripLd + c] : 0.0;
+							if (c < 15)
+								tb[rr * 15 + c] = r0 + rr < rows ? strip[size_t(r0 + rr) * kStripLd + c] : 0.0;
 						}
 					for (int lane = 0; lane < 32; ++lane)
-						for (int p = 0; p < 8; ++p)
+						for (int c = 0; c < 15; ++c)
 						{
-							const int rr = lane & 15, c = 2 * p + (lane >> 4);
-							if (c >= 15)
-								continue;
 							const int32_t *info = S.grp_info.data() + (size_t(g) * kNodes + c / 3) * 4;
-							const int r = r0 + rr;
+							const int r = r0 + lane;
 							if (info[0] >= 0 && r < info[2])
 							{
 								if (info[1] != 9 * adj_off[info[0]] || info[2] != 3 * (adj_off[info[0] + 1] - adj_off[info[0]]))
 									return -8;
-								values[size_t(info[1]) + size_t(c % 3) * info[2] + r] = scale * tb[rr * 17 + c];
+								values[size_t(info[1]) + size_t(c % 3) * info[2] + r] = scale * tb[lane * 15 + c];
 							}
 						}
 				}
