@@ -206,9 +206,11 @@ def main():
     ap.add_argument("--no-align", action="store_true", help="multi-GPU: cut the element range evenly instead of on whole cell layers")
     ap.add_argument("--graph", action="store_true", help="multi-GPU, experimental: capture the step in a CUDA graph and replay it "
                     "(hung on the round-1 stack: NCCL 2.28 point-to-point under capture; never the default)")
+    ap.add_argument("--exchange", action="store_true", help="multi-GPU: the round-1 form (row-lane kernels + NCCL point-to-point interface exchange) "
+                    "instead of the owner-computes form (no exchange, energy all-reduce only)")
     ap.add_argument("--overlap", action="store_true", help="multi-GPU: interface elements first, exchange on a side stream under the "
                     "assembly of the rest (measured no faster than the plain order in round 1)")
-    ap.add_argument("--flags", type=int, default=0, help="pfa_mesh_desc.flags (1 = keep the caller's element order, 2 = in-kernel zero fill, 4 = column-lane kernels, single GPU)")
+    ap.add_argument("--flags", type=int, default=0, help="pfa_mesh_desc.flags (1 = keep the caller's element order, 2 = in-kernel zero fill, 8 = round-1 row-lane RED kernels)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -239,13 +241,23 @@ def main():
 
     mesh, x_host, t = build_workload(args.n, args.p)
     lam, mu = lame_from_E_nu(E_MOD, NU)
-    # cuts on whole layers of cells (6 n^2 tets): the interface stays one node plane thick
-    part = pdist.partition_elements(mesh, rank, world, align=1 if args.no_align else 6 * args.n * args.n)
-    h = capi.Handle("NeoHookean", part.conn, part.n_bases, t["weights"], t["grad"], vertices=part.vertices,
-                    lam=lam, mu=mu, device=local_rank, n_ghost_elements=part.n_ghost_elements, flags=args.flags,
-                    n_first_elements=part.n_interface_elements)
+    exch = None
+    owner_mode = world > 1 and not args.exchange
+    if owner_mode:
+        # owner-computes form: the library's partition, ghost elements with geometry, every rank writes the
+        # finished columns / gradient entries of the nodes it owns; the only collective is the all-reduce of the energy
+        part = pdist.partition_owner_computes(mesh, rank, world)
+        h = pdist.owner_handle(part, t, lam, mu, device=local_rank, flags=args.flags)
+    else:
+        # round-1 form (--exchange, or one GPU): cuts on whole layers of cells (6 n^2 tets), partial sums of interface
+        # columns go point-to-point to their owners
+        part = pdist.partition_elements(mesh, rank, world, align=1 if args.no_align else 6 * args.n * args.n)
+        h = capi.Handle("NeoHookean", part.conn, part.n_bases, t["weights"], t["grad"], vertices=part.vertices,
+                        lam=lam, mu=mu, device=local_rank, n_ghost_elements=part.n_ghost_elements,
+                        flags=args.flags | (capi.FLAG_ROW_LANE if world > 1 else 0), n_first_elements=part.n_interface_elements)
     h.set_stream(torch.cuda.current_stream().cuda_stream)
-    exch = pdist.InterfaceExchange(h, part, rank, world, dev, grad_offset=h.nnz) if world > 1 else None
+    if world > 1 and not owner_mode:
+        exch = pdist.InterfaceExchange(h, part, rank, world, dev, grad_offset=h.nnz)
 
     x_loc = np.ascontiguousarray(x_host.reshape(-1, 3)[part.l2g].reshape(-1))
     xd = torch.from_numpy(x_loc).to(dev)
@@ -255,7 +267,10 @@ def main():
     v_d, g_d = vg_d[:h.nnz], vg_d[h.nnz:]
 
     def step():
-        if exch is None:
+        if owner_mode:
+            h.grad_hess_raw(xd, e_d, g_d, v_d)
+            dist.all_reduce(e_d)
+        elif exch is None:
             h.grad_hess_raw(xd, e_d, g_d, v_d)
         elif not args.overlap:
             h.grad_hess_raw(xd, e_d, g_d, v_d)
@@ -357,19 +372,26 @@ def main():
                     e0.record()
                     h.grad_hess_raw(xd, e_d, g_d, v_d)
                     e1.record()
-                    exch.reduce_combined(e_d, vg_d)
+                    if owner_mode:
+                        dist.all_reduce(e_d)
+                    else:
+                        exch.reduce_combined(e_d, vg_d)
                     e2.record()
                     ka.append((e0, e1))
                     kb.append((e1, e2))
                 torch.cuda.synchronize()
                 mine = torch.tensor([np.median([a.elapsed_time(b) for a, b in ka]), np.median([a.elapsed_time(b) for a, b in kb]),
-                                     float(h.n_elements), float(part.n_interface_elements), float(h.nnz)], dtype=torch.float64, device=dev)
+                                     float(h.n_elements), float(part.n_ghost_elements if owner_mode else part.n_interface_elements),
+                                     float(h.nnz if not owner_mode else 9 * int(np.diff(h.block_pattern()[0])[part.owned == 1].sum()))],
+                                    dtype=torch.float64, device=dev)
                 allr = [torch.zeros_like(mine) for _ in range(world)]
                 dist.all_gather(allr, mine)
                 per_rank = {"assembly_ms": [round(float(t[0]), 4) for t in allr], "exchange_ms": [round(float(t[1]), 4) for t in allr],
-                            "elements": [int(t[2]) for t in allr], "interface_elements": [int(t[3]) for t in allr],
-                            "nnz": [int(t[4]) for t in allr],
-                            "note": "exchange_ms includes waiting for the neighbours and the energy all-reduce"}
+                            "elements": [int(t[2]) for t in allr],
+                            ("ghost_elements" if owner_mode else "interface_elements"): [int(t[3]) for t in allr],
+                            ("owned_nnz" if owner_mode else "nnz"): [int(t[4]) for t in allr],
+                            "note": ("exchange_ms = the energy all-reduce (the only collective), including waiting for the slowest rank" if owner_mode
+                                     else "exchange_ms includes waiting for the neighbours and the energy all-reduce")}
         except Exception as ex:  # diagnostics must never cost the bench line
             sys.stderr.write(f"[bench] per-rank breakdown skipped on rank {rank}: {type(ex).__name__}: {ex}\n")
             per_rank = None
@@ -382,8 +404,16 @@ def main():
     fill = [ms for (name, ms) in recs if "zero_fill" in name]
     kern_ms = float(np.sum(kern)) / prof_steps if kern else float("nan")  # per step (two launches when the step is split)
     peak, peak_src = measured_peaks()
-    b_alg = b_alg_bytes_per_element(h.n_loc, h.ndof, h.nnz, h.n_elements)
-    achieved = b_alg * h.n_elements / (kern_ms * 1e-3) / 1e9
+    if world == 1:
+        b_alg = b_alg_bytes_per_element(h.n_loc, h.ndof, h.nnz, h.n_elements)
+        achieved = b_alg * h.n_elements / (kern_ms * 1e-3) / 1e9
+    else:
+        # per GPU: the whole mesh's compulsory bytes per element (closed-form nnz of the Kuhn cube) times this
+        # rank's share of the elements, over this rank's kernel time
+        nn = args.n
+        nnz_g = 9 * ((230 * nn ** 3 + 138 * nn ** 2 + 24 * nn + 1) if args.p == 2 else (15 * nn ** 3 + 21 * nn ** 2 + 9 * nn + 1))
+        b_alg = b_alg_bytes_per_element(h.n_loc, 3 * mesh.n_bases, nnz_g, mesh.n_elements)
+        achieved = b_alg * (mesh.n_elements / world) / (kern_ms * 1e-3) / 1e9
     kname = sorted({name for (name, ms) in recs if "assemble" in name})[0] if kern else None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": ncu_traffic(kname, h.n_elements, world), "kernel": kname,
@@ -449,9 +479,11 @@ def main():
                                    f"{mesh.n_bases * 3} dofs, fused energy+gradient+Hessian (pfa_grad_hess)",
                        "material": "E=1e5 nu=0.3", "displacement": "0.05*h*U(-1,1) seed 42",
                        "l2": "outputs (values[] %.2f GB per GPU) exceed the 126 MB L2, no flush needed" % (8 * h.nnz / 1e9),
-                       "parallelism": (f"element partition x{world}, interface exchange "
-                                       + ("under" if args.overlap else "after") + " the assembly, "
-                                       + ("step replayed from a CUDA graph" if graph is not None else "eager launches")) if world > 1 else "single GPU",
+                       "parallelism": ((f"element partition x{world} (pfa_partition_create), owner-computes columns with ghost elements: no interface "
+                                        "exchange, NCCL all-reduce of the energy only") if owner_mode else
+                                       (f"element partition x{world}, interface exchange "
+                                        + ("under" if args.overlap else "after") + " the assembly, "
+                                        + ("step replayed from a CUDA graph" if graph is not None else "eager launches"))) if world > 1 else "single GPU",
                        "nnz": int(h.nnz) if world == 1 else None},
             "nnz_per_s": (h.nnz / (ms_step * 1e-3)) if world == 1 else None,
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,

@@ -105,6 +105,14 @@ extern "C"
 		 * ref_grads, lambda and mu may be NULL for PFA_MASS. */
 		const double *ref_vals;
 		const double *density;
+		/* Multi-GPU, owner-computes form (NeoHookean P1/P2 on affine elements; SURVEY.md §8e "device list": one process and one
+		 * handle per GPU, the partition comes from pfa_partition_create): owned_nodes[n_bases] != 0 marks the nodes whose CSC
+		 * columns and gradient entries this handle produces. Together with PFA_FLAG_GHOST_GEOMETRY - vertices, lambda and mu
+		 * then cover the n_ghost_elements rows of conn as well - pfa_grad_hess / pfa_hessian write the FINISHED columns and
+		 * gradient entries of the owned nodes (all incident elements are present on this rank) and leave the rest of
+		 * values[] / grad[] untouched: no interface exchange, only the scalar energy (own elements) is summed over the ranks
+		 * by the caller. NULL = every node is owned. */
+		const uint8_t *owned_nodes;
 	} pfa_mesh_desc;
 
 /* pfa_mesh_desc.flags: keep the caller's element order internally (default: elements are
@@ -122,6 +130,9 @@ extern "C"
  * selects the round-1 row-lane reduction kernel (red.global.add.f64 into a zero-filled values[]) instead. */
 #define PFA_FLAG_COLUMN_LANE 4
 #define PFA_FLAG_ROW_LANE 8
+/* vertices (and lambda, mu, density) have n_elements + n_ghost_elements entries: the ghost elements carry geometry and
+ * material so that their records can be evaluated for the columns of owned nodes (see pfa_mesh_desc.owned_nodes) */
+#define PFA_FLAG_GHOST_GEOMETRY 16
 
 	typedef struct pfa_handle pfa_handle;
 
@@ -129,6 +140,22 @@ extern "C"
 	 * mesh (replaces AssemblyValsCache::init + the first-call pattern build of
 	 * SparseMatrixCache, MatrixCache.cpp:88-100,134-213). */
 	int pfa_create(const pfa_mesh_desc *desc, pfa_handle **out);
+
+	/* Element partition of a mesh over `world` GPUs for the owner-computes path (host only, no device needed; replaces the
+	 * per-thread element ranges of maybe_parallel_for, utils/MaybeParallelFor.tpp:18-68, and SURVEY.md §8e): contiguous element
+	 * blocks in the caller's order; a node is owned by the rank of the FIRST element that touches it; the cuts balance the
+	 * (element, node) incidences of the owned nodes, which is the work of the column kernels. Rank `rank` gets its own
+	 * elements followed by its ghost elements (elements of other ranks touching a node it owns), renumbered locally in
+	 * first-touch order. The arrays are owned by the partition object. */
+	typedef struct pfa_partition pfa_partition;
+	int pfa_partition_create(int32_t n_elements, int32_t n_loc, int32_t n_bases, const int32_t *conn, int32_t world, int32_t rank, pfa_partition **out);
+	/* n_own / n_ghost elements, local nodes, owned local nodes */
+	int pfa_partition_sizes(const pfa_partition *p, int32_t *n_own_elements, int32_t *n_ghost_elements, int32_t *n_local_bases, int32_t *n_owned_bases);
+	const int32_t *pfa_partition_elements(const pfa_partition *p); /* [n_own + n_ghost] caller's element ids, own first */
+	const int32_t *pfa_partition_conn(const pfa_partition *p);     /* [n_own + n_ghost][n_loc] local node ids */
+	const int32_t *pfa_partition_local_to_global(const pfa_partition *p);      /* [n_local_bases] caller's node id of each local node */
+	const uint8_t *pfa_partition_owned(const pfa_partition *p);    /* [n_local_bases] 1 = owned by this rank */
+	void pfa_partition_destroy(pfa_partition *p);
 	void pfa_destroy(pfa_handle *h);
 	/* message of the last failing call on this handle (or of pfa_create when h == NULL) */
 	const char *pfa_last_error(const pfa_handle *h);

@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libpfa.so")
 # experiment hook: PFA_DEFS="-DFOO=1 ..." PFA_LIB_SUFFIX=_foo builds polyfem_b200/libpfa_foo.so
-SOURCES = ["pfa_api.cu", "pfa_pattern.cu", "pfa_kernels.cu", "pfa_project.cu", "pfa_collane2.cu"]
+SOURCES = ["pfa_api.cu", "pfa_pattern.cu", "pfa_kernels.cu", "pfa_project.cu", "pfa_collane2.cu", "pfa_partition.cu"]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "--use_fast_math=false"]
 

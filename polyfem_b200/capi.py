@@ -31,6 +31,8 @@ EXPORTS = [
     "pfa_is_step_valid", "pfa_set_constrained_dofs", "pfa_reduced_sizes", "pfa_reduced_pattern", "pfa_reduced_pattern_device",
     "pfa_project_gradient", "pfa_project_hessian", "pfa_grad_hess_reduced", "pfa_grad_hess_part",
     "pfa_symv", "pfa_inertia", "pfa_axpy",
+    "pfa_partition_create", "pfa_partition_sizes", "pfa_partition_elements", "pfa_partition_conn", "pfa_partition_local_to_global",
+    "pfa_partition_owned", "pfa_partition_destroy",
 ]
 
 
@@ -44,6 +46,7 @@ class MeshDesc(ctypes.Structure):
         ("material_stride", ctypes.c_int32), ("device", ctypes.c_int32), ("flags", ctypes.c_int32),
         ("n_ghost_elements", ctypes.c_int32), ("n_first_elements", ctypes.c_int32),
         ("ref_vals", _dp), ("density", _dp),
+        ("owned_nodes", ctypes.POINTER(ctypes.c_uint8)),
     ]
 
 
@@ -52,6 +55,7 @@ FLAG_KEEP_ELEMENT_ORDER = 1
 FLAG_INKERNEL_ZERO = 2
 FLAG_COLUMN_LANE = 4  # accepted, no effect: the owner-computes kernels are the default for NeoHookean P1/P2
 FLAG_ROW_LANE = 8  # NeoHookean P1/P2: the round-1 row-lane reduction kernels (RED into a zero-filled values[])
+FLAG_GHOST_GEOMETRY = 16  # vertices / lambda / mu cover the ghost elements too (multi-GPU owner-computes form)
 
 
 class PfaError(RuntimeError):
@@ -111,6 +115,14 @@ def lib():
     L.pfa_launch_count.restype = i64
     L.pfa_setup_seconds.argtypes = [vp]
     L.pfa_setup_seconds.restype = ctypes.c_double
+    i32p, u8p = ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_uint8)
+    L.pfa_partition_create.argtypes = [ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, _ip, ctypes.c_int32, ctypes.c_int32, ctypes.POINTER(vp)]
+    L.pfa_partition_sizes.argtypes = [vp, i32p, i32p, i32p, i32p]
+    for name, rt in (("pfa_partition_elements", i32p), ("pfa_partition_conn", i32p), ("pfa_partition_local_to_global", i32p), ("pfa_partition_owned", u8p)):
+        getattr(L, name).argtypes = [vp]
+        getattr(L, name).restype = rt
+    L.pfa_partition_destroy.argtypes = [vp]
+    L.pfa_partition_destroy.restype = None
     _LIB = L
     return L
 
@@ -134,13 +146,16 @@ class Handle:
     """One pfa_handle: one mesh + material on one GPU."""
 
     def __init__(self, material, conn, n_bases, quad_weights, ref_grads, vertices=None, jac_it=None, da=None,
-                 lam=None, mu=None, device=0, n_ghost_elements=0, flags=0, n_first_elements=0, ref_vals=None, density=None):
+                 lam=None, mu=None, device=0, n_ghost_elements=0, flags=0, n_first_elements=0, ref_vals=None, density=None,
+                 owned_nodes=None):
         L = lib()
         self.material = MATERIAL_IDS[material] if isinstance(material, str) else int(material)
         conn = np.ascontiguousarray(conn, dtype=np.int32)
         qw = np.ascontiguousarray(quad_weights, dtype=np.float64)
         ne, nl = conn.shape
-        ne -= int(n_ghost_elements)  # trailing rows of conn are pattern-only ghost elements
+        ne -= int(n_ghost_elements)  # trailing rows of conn are ghost elements
+        # elements with geometry / material: with FLAG_GHOST_GEOMETRY the ghost elements as well
+        ngeo = ne + (int(n_ghost_elements) if (int(flags) & FLAG_GHOST_GEOMETRY) else 0)
         nq = qw.size
         rg = None if ref_grads is None else np.ascontiguousarray(ref_grads, dtype=np.float64)
         assert rg is None or rg.shape == (nq, nl, 3), f"ref_grads must be [n_qp, n_loc, 3], got {rg.shape}"
@@ -161,7 +176,7 @@ class Handle:
             d.ref_vals, d.density = rv.ctypes.data_as(_dp), rho.ctypes.data_as(_dp)
             keep += [rv, rho]
         if vertices is not None:
-            v = np.ascontiguousarray(vertices, dtype=np.float64).reshape(ne, 4, 3)
+            v = np.ascontiguousarray(vertices, dtype=np.float64).reshape(ngeo, 4, 3)
             d.vertices = v.ctypes.data_as(_dp)
             keep.append(v)
         if jac_it is not None:
@@ -176,17 +191,22 @@ class Handle:
             lam = np.asarray(lam, dtype=np.float64)
             mu = np.asarray(mu, dtype=np.float64)
             if lam.ndim == 0:
-                lam = np.full(ne, float(lam))
-                mu = np.full(ne, float(mu))
+                lam = np.full(ngeo, float(lam))
+                mu = np.full(ngeo, float(mu))
             lam = np.ascontiguousarray(lam)
             mu = np.ascontiguousarray(mu)
-            stride = 1 if lam.size == ne else nq
-            assert lam.size == ne * stride and mu.size == ne * stride
+            stride = 1 if lam.size == ngeo else nq
+            assert lam.size == ngeo * stride and mu.size == ngeo * stride
             d.lambda_, d.mu = lam.ctypes.data_as(_dp), mu.ctypes.data_as(_dp)
             keep += [lam, mu]
         d.material_stride, d.device, d.flags = stride, int(device), int(flags)
         d.n_ghost_elements = int(n_ghost_elements)
         d.n_first_elements = int(n_first_elements)
+        if owned_nodes is not None:
+            own = np.ascontiguousarray(owned_nodes, dtype=np.uint8)
+            assert own.size == int(n_bases)
+            d.owned_nodes = own.ctypes.data_as(ctypes.POINTER(ctypes.c_uint8))
+            keep.append(own)
         h = ctypes.c_void_p()
         rc = L.pfa_create(ctypes.byref(d), ctypes.byref(h))
         if rc != PFA_OK:
@@ -395,3 +415,30 @@ class Handle:
 
     def setup_seconds(self):
         return float(lib().pfa_setup_seconds(self._h))
+
+
+def partition(conn, n_bases, world, rank):
+    """pfa_partition_create (include/pfa.h): element partition for the multi-GPU owner-computes path. Returns a dict with
+    `elements` (caller's element ids, own first, then ghost), `n_own`, `n_ghost`, `conn` (local node ids, [n_own + n_ghost, n_loc]),
+    `l2g` (caller's node id per local node) and `owned` (uint8 per local node)."""
+    L = lib()
+    conn = np.ascontiguousarray(conn, dtype=np.int32)
+    ne, nl = conn.shape
+    p = ctypes.c_void_p()
+    rc = L.pfa_partition_create(ne, nl, int(n_bases), conn.ctypes.data_as(_ip), int(world), int(rank), ctypes.byref(p))
+    if rc != PFA_OK:
+        raise PfaError(rc, "pfa_partition_create failed")
+    try:
+        n_own, n_ghost, n_loc_b, n_owned = (ctypes.c_int32() for _ in range(4))
+        L.pfa_partition_sizes(p, ctypes.byref(n_own), ctypes.byref(n_ghost), ctypes.byref(n_loc_b), ctypes.byref(n_owned))
+        nt = n_own.value + n_ghost.value
+        out = {
+            "n_own": n_own.value, "n_ghost": n_ghost.value, "n_owned_bases": n_owned.value,
+            "elements": np.ctypeslib.as_array(L.pfa_partition_elements(p), shape=(nt,)).copy(),
+            "conn": np.ctypeslib.as_array(L.pfa_partition_conn(p), shape=(nt, nl)).copy(),
+            "l2g": np.ctypeslib.as_array(L.pfa_partition_local_to_global(p), shape=(n_loc_b.value,)).copy(),
+            "owned": np.ctypeslib.as_array(L.pfa_partition_owned(p), shape=(n_loc_b.value,)).copy(),
+        }
+    finally:
+        L.pfa_partition_destroy(p)
+    return out

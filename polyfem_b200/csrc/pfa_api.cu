@@ -48,6 +48,7 @@ struct pfa_handle
 	double *d_energy = nullptr;
 	int *d_counter = nullptr;
 	int32_t epoch = 0; // in-kernel zero-fill generation (row-lane kernels)
+	int32_t n_geo_elements = 0; // elements with geometry / material on the device: n_el (+ ghost elements with PFA_FLAG_GHOST_GEOMETRY)
 	ColumnLane2Tables cl; // owner-computes path (default for NeoHookean P1 / P2 on affine elements)
 
 	// Dirichlet projection (pfa_set_constrained_dofs)
@@ -389,6 +390,10 @@ extern "C"
 		if (d->device < 0 || d->device >= n_dev)
 			return fail(nullptr, PFA_ERR_INVALID, "pfa_create: device ordinal out of range");
 
+		// multi-GPU owner-computes form: ghost elements carry geometry and material too
+		const bool ghost_geom = (d->flags & PFA_FLAG_GHOST_GEOMETRY) != 0 && d->n_ghost_elements > 0;
+		if (ghost_geom && !affine)
+			return fail(nullptr, PFA_ERR_UNSUPPORTED, "pfa_create: PFA_FLAG_GHOST_GEOMETRY needs affine elements (vertices)");
 		const auto t0 = std::chrono::steady_clock::now();
 		pfa_handle *h = new (std::nothrow) pfa_handle();
 		if (!h)
@@ -466,23 +471,27 @@ extern "C"
 				for (int32_t v : p2)
 					perm.push_back(v + nf);
 				const size_t ne_ = size_t(d->n_elements), nl_ = size_t(d->n_loc), ng_ = size_t(d->n_ghost_elements);
+				const size_t ngeo_ = ne_ + (ghost_geom ? ng_ : 0); // elements with geometry / material
+				for (size_t e = ne_; e < ngeo_; ++e)
+					perm.push_back(int32_t(e)); // ghost elements keep their place after the own elements
 				conn_p.resize((ne_ + ng_) * nl_);
-				vert_p.resize(ne_ * 12);
-				for (size_t e = 0; e < ne_; ++e)
+				vert_p.resize(ngeo_ * 12);
+				for (size_t e = 0; e < ngeo_; ++e)
 				{
 					const size_t o = size_t(perm[e]);
 					std::memcpy(&conn_p[e * nl_], d->conn + o * nl_, nl_ * sizeof(int32_t));
 					std::memcpy(&vert_p[e * 12], d->vertices + o * 12, 12 * sizeof(double));
 				}
-				std::memcpy(conn_p.data() + ne_ * nl_, d->conn + ne_ * nl_, ng_ * nl_ * sizeof(int32_t));
+				if (!ghost_geom)
+					std::memcpy(conn_p.data() + ne_ * nl_, d->conn + ne_ * nl_, ng_ * nl_ * sizeof(int32_t));
 				conn_in = conn_p.data();
 				vert_in = vert_p.data();
 				if (d->material != PFA_LAPLACIAN)
 				{
 					const size_t st_ = size_t(d->material_stride);
-					lam_p.resize(ne_ * st_);
-					mu_p.resize(ne_ * st_);
-					for (size_t e = 0; e < ne_; ++e)
+					lam_p.resize(ngeo_ * st_);
+					mu_p.resize(ngeo_ * st_);
+					for (size_t e = 0; e < ngeo_; ++e)
 						for (size_t k = 0; k < st_; ++k)
 						{
 							lam_p[e * st_ + k] = lam_src[size_t(perm[e]) * st_ + k];
@@ -535,10 +544,12 @@ extern "C"
 		dst = tmp_;                                                        \
 	} while (0)
 		const size_t ne = size_t(m.n_el), nl = size_t(m.n_loc), nq = size_t(m.n_qp);
-		UP(m.conn, conn_in, ne * nl, int32_t);
+		const size_t ngeo = ne + (ghost_geom ? size_t(d->n_ghost_elements) : 0); // elements with geometry / material on the device
+		h->n_geo_elements = int32_t(ngeo);
+		UP(m.conn, conn_in, ngeo * nl, int32_t);
 		if (!perm.empty())
 		{
-			UP(h->d_elem_id, perm.data(), ne, int32_t);
+			UP(h->d_elem_id, perm.data(), ngeo, int32_t);
 			m.elem_id = h->d_elem_id;
 		}
 		if (d->ref_grads)
@@ -601,26 +612,32 @@ extern "C"
 			int max_deg = 0;
 			for (size_t b = 0; b + 1 < hp.adj_off.size(); ++b)
 				max_deg = std::max(max_deg, hp.adj_off[b + 1] - hp.adj_off[b]);
-			if (!(d->flags & PFA_FLAG_ROW_LANE) && !rl_env && affine && column_lane2_applies(m.material, m.n_loc, m.n_qp) && max_deg < 128 && d->n_ghost_elements == 0)
+			if (!(d->flags & PFA_FLAG_ROW_LANE) && !rl_env && affine && column_lane2_applies(m.material, m.n_loc, m.n_qp) && max_deg < 128 && (d->n_ghost_elements == 0 || ghost_geom))
 			{
 				try
 				{
 					// columns of at most kSmallRows strip rows form the first launch, the rest (P2 vertex nodes) the second;
 					// chunks of about kChunkSteps steps are handed out to the warps
-					const cl2::Schedule S = cl2::build_schedule(m.n_el, m.n_loc, m.n_bases, conn_in, hp.adj_off.data(), hp.adj.data(), kSmallRows, kChunkSteps);
+					const cl2::Schedule S = cl2::build_schedule(int(ngeo), m.n_loc, m.n_bases, conn_in, hp.adj_off.data(), hp.adj.data(), kSmallRows, kChunkSteps, d->owned_nodes);
 					UP(h->cl.grp_info, S.grp_info.data(), S.grp_info.size(), int32_t);
 					UP(h->cl.grp_off, S.grp_off.data(), S.grp_off.size(), int32_t);
 					UP(h->cl.grp_rows, S.grp_rows.data(), S.grp_rows.size(), int32_t);
 					UP(h->cl.chunk_off, S.chunk_off.data(), S.chunk_off.size(), int32_t);
 					UP(h->cl.inc, S.inc.data(), S.inc.size(), uint32_t);
-					if ((rc = dev_alloc<double>(h, &h->cl.records, ne * column_lane2_record_doubles(m.n_qp))) != PFA_OK || (rc = dev_alloc<double>(h, &h->cl.block_energy, (ne + 127) / 128)) != PFA_OK || (rc = dev_alloc<int>(h, &h->cl.counters, 2)) != PFA_OK)
+					std::vector<double> rgp(nl * nq * 4, 0.0);
+					for (size_t i = 0; i < nl; ++i)
+						for (size_t q = 0; q < nq; ++q)
+							for (size_t c = 0; c < 3; ++c)
+								rgp[(i * nq + q) * 4 + c] = d->ref_grads[(q * nl + i) * 3 + c];
+					UP(h->cl.rg_padded, rgp.data(), rgp.size(), double);
+					if ((rc = dev_alloc<double>(h, &h->cl.records, ngeo * column_lane2_record_doubles(m.n_qp))) != PFA_OK || (rc = dev_alloc<double>(h, &h->cl.block_energy, (ngeo + 127) / 128)) != PFA_OK || (rc = dev_alloc<int>(h, &h->cl.counters, 2)) != PFA_OK)
 						return bail(rc);
 					for (int c = 0; c < 2; ++c)
 					{
 						h->cl.n_chunks[c] = S.n_chunks[c];
 						h->cl.rows_max[c] = S.rows_max[c];
 					}
-					h->cl.n_record_elements = m.n_el;
+					h->cl.n_record_elements = int32_t(ngeo);
 					h->cl.enabled = 1;
 					PFA_CUDA(h, cudaStreamSynchronize(h->stream)); // S is a local
 				}
@@ -635,7 +652,7 @@ extern "C"
 			UP(m.slot, hp.slot.data(), size_t(ne) * nl * nl, int32_t);
 		if (m.material != PFA_LAPLACIAN)
 		{
-			const size_t cnt = ne * size_t(m.mat_stride);
+			const size_t cnt = ngeo * size_t(m.mat_stride);
 			if ((rc = dev_upload<double>(h, &h->d_lambda, lam_in, cnt)) != PFA_OK || (rc = dev_upload<double>(h, &h->d_mu, mu_in, cnt)) != PFA_OK)
 				return bail(rc);
 			m.lambda = h->d_lambda;
@@ -644,10 +661,10 @@ extern "C"
 		if (affine)
 		{
 			double *d_vert = nullptr, *jit = nullptr, *detj = nullptr;
-			if ((rc = dev_upload<double>(h, &d_vert, vert_in, ne * 12)) != PFA_OK || (rc = dev_alloc<double>(h, &jit, ne * 9)) != PFA_OK || (rc = dev_alloc<double>(h, &detj, ne)) != PFA_OK)
+			if ((rc = dev_upload<double>(h, &d_vert, vert_in, ngeo * 12)) != PFA_OK || (rc = dev_alloc<double>(h, &jit, ngeo * 9)) != PFA_OK || (rc = dev_alloc<double>(h, &detj, ngeo)) != PFA_OK)
 				return bail(rc);
 			++h->launches;
-			cudaError_t e = launch_geometry_precompute(d_vert, m.n_el, jit, detj, h->stream);
+			cudaError_t e = launch_geometry_precompute(d_vert, int(ngeo), jit, detj, h->stream);
 			if (e != cudaSuccess)
 			{
 				h->err = std::string("geometry precompute: ") + cudaGetErrorString(e);
@@ -784,7 +801,8 @@ extern "C"
 		if (!lambda || !mu || material_stride != h->dm.mat_stride)
 			return fail(h, PFA_ERR_INVALID, "pfa_set_materials: NULL array or material_stride differs from pfa_create");
 		PFA_CUDA(h, cudaSetDevice(h->device));
-		const size_t cnt = size_t(h->dm.n_el) * size_t(h->dm.mat_stride) * sizeof(double);
+		// (with PFA_FLAG_GHOST_GEOMETRY the arrays cover the ghost elements as well, like at pfa_create)
+		const size_t cnt = size_t(h->n_geo_elements) * size_t(h->dm.mat_stride) * sizeof(double);
 		if (h->d_elem_id == nullptr)
 		{
 			PFA_CUDA(h, cudaMemcpyAsync(h->d_lambda, lambda, cnt, cudaMemcpyDefault, h->stream));
@@ -802,7 +820,7 @@ extern "C"
 			{
 				PFA_CUDA(h, cudaMemcpyAsync(h->s_mat, src[k], cnt, cudaMemcpyDefault, h->stream));
 				++h->launches;
-				PFA_CUDA(h, launch_gather_rows(h->s_mat, h->d_elem_id, h->dm.n_el, h->dm.mat_stride, dst[k], h->stream));
+				PFA_CUDA(h, launch_gather_rows(h->s_mat, h->d_elem_id, h->n_geo_elements, h->dm.mat_stride, dst[k], h->stream));
 			}
 		}
 		PFA_CUDA(h, cudaStreamSynchronize(h->stream));

@@ -18,6 +18,7 @@
 #include "pfa_collane2.h"
 #include "pfa_internal.h"
 
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 
@@ -145,13 +146,33 @@ namespace pfa
 						 : "memory");
 		}
 
+		// Ampere-style asynchronous copy (LDGSTS): 16 bytes global -> shared without a register round trip; L2 only (.cg)
+		__device__ __forceinline__ void cp_async16(uint32_t dst, const void *src)
+		{
+			asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+		}
+		__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+		__device__ __forceinline__ void cp_async_wait_1() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
+
+		// Record staging, measured on B200 (profiles/clvar_r02f.jsonl): TMA bulk copies (one elected issue per triple, completion
+		// on an mbarrier) and cp.async (16 bytes per lane and instruction) are equally fast for the 432-byte P2 records
+		// (5.03 / 5.07 ms at cfg 3); for the 144-byte P1 records cp.async wins (0.224 / 0.263 ms at cfg 2). PFA_CL2_TMA
+		// overrides the per-element-type choice (experiments).
+#ifdef PFA_CL2_TMA
+		template <int NQ>
+		constexpr bool kUseTma = PFA_CL2_TMA != 0;
+#else
+		template <int NQ>
+		constexpr bool kUseTma = NQ > 1;
+#endif
+
 		// shared memory of the one-warp CTA, in doubles
 		template <int NL, int NQ>
 		struct WarpLayout
 		{
 			static constexpr int RECD = Rec<NQ>::D;
 			static constexpr int STAGE = kTriples * RECD; // one buffer: 10 element records (each 16-byte aligned: RECD is even)
-			static constexpr int STAGES = 2;              // buffers
+			static constexpr int STAGES = 2;              // buffers: copies are issued two steps ahead
 			static constexpr int TB = kFlushRows * kTbLd; // transposition block of the flush
 			// the flush of a group runs after the last step of the group has consumed its records and before that buffer is
 			// refilled: when a buffer is large enough (P2) the transposition block lives there
@@ -162,8 +183,7 @@ namespace pfa
 			static constexpr int OFF_INFO = OFF_RG + NL * NQ * 4; // 5 x 4 ints = 10 doubles
 			static constexpr int OFF_STRIP = OFF_INFO + 10;
 			static_assert(RECD % 2 == 0 && OFF_STAGE % 2 == 0 && OFF_RG % 2 == 0 && OFF_STRIP % 2 == 0, "16-byte alignment");
-			// strips in whole kFlushRows-row blocks (the flush reads whole blocks)
-			static size_t bytes(int strip_rows) { return sizeof(double) * (size_t(OFF_STRIP) + size_t((strip_rows + kFlushRows - 1) / kFlushRows * kFlushRows) * kStripLd); }
+			static size_t bytes(int strip_rows) { return sizeof(double) * (size_t(OFF_STRIP) + size_t(strip_rows) * kStripLd); }
 		};
 
 #ifndef PFA_CL2_MINBLOCKS
@@ -171,11 +191,12 @@ namespace pfa
 #endif
 		template <int NL, int NQ, int SLOT, bool P2S>
 		__global__ void __launch_bounds__(32, PFA_CL2_MINBLOCKS) cl2_columns_kernel(const DeviceMesh m, const AssembleArgs a, const ColumnLane2Tables t, const int cls, const int chunk_begin,
-																 const int chunk_end)
+																 const int chunk_end, const int strip_rows)
 		{
 			using L = WarpLayout<NL, NQ>;
 			constexpr int RECD = L::RECD;
 			constexpr uint32_t REC_BYTES = RECD * sizeof(double);
+			constexpr bool TMA = kUseTma<NQ>;
 			extern __shared__ __align__(16) double smem[];
 			const int lane = threadIdx.x;
 			const int half = lane >> 4, within = lane & 15;
@@ -199,26 +220,43 @@ namespace pfa
 			}
 			// own-node reference gradients, padded rows [ri][q][4]
 			for (int k = lane; k < NL * NQ * 4; k += 32)
-			{
-				const int c = k & 3, q = (k >> 2) % NQ, i = (k >> 2) / NQ;
-				s_rg[k] = c < 3 ? m.ref_grads[(q * NL + i) * 3 + c] : 0.0;
-			}
+				s_rg[k] = t.rg_padded[k];
 			asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 			__syncwarp();
 
 			const uint4 *inc = reinterpret_cast<const uint4 *>(t.inc);
 			const uint4 idle = make_uint4(kIdle, 0u, 0u, 0u);
 			const uint32_t stage_u32 = smem_u32(stage);
-			// one TMA copy per busy triple into buffer `buf`; lane 0 arms the barrier with the byte count first
-			auto issue = [&](const uint4 &w, int buf) {
-				const bool want = leader && w.x != kIdle;
-				const unsigned mask = __ballot_sync(kFull, want);
-				const uint32_t bar = buf ? bar1 : bar0;
-				if (lane == 0)
-					mbar_arrive_expect_tx(bar, uint32_t(__popc(mask)) * REC_BYTES);
-				__syncwarp();
-				if (want)
-					tma_load(stage_u32 + uint32_t(buf * L::STAGE + tr * RECD) * 8u, t.records + size_t(w.x) * RECD, REC_BYTES, bar);
+			// records of the busy triples of a step -> buffer `buf`
+			auto issue = [&](const uint4 &w, int buf, bool real) {
+				if constexpr (TMA)
+				{
+					// one TMA copy per busy triple; lane 0 arms the barrier with the byte count first
+					if (!real)
+						return;
+					const bool want = leader && w.x != kIdle;
+					const unsigned mask = __ballot_sync(kFull, want);
+					const uint32_t bar = buf ? bar1 : bar0;
+					if (lane == 0)
+						mbar_arrive_expect_tx(bar, uint32_t(__popc(mask)) * REC_BYTES);
+					__syncwarp();
+					if (want)
+						tma_load(stage_u32 + uint32_t(buf * L::STAGE + tr * RECD) * 8u, t.records + size_t(w.x) * RECD, REC_BYTES, bar);
+				}
+				else
+				{
+					// the three lanes of a triple copy its record, 16 bytes per lane and instruction (interleaved: consecutive lanes,
+					// consecutive chunks); every lane commits one group per step
+					if (real && active && w.x != kIdle)
+					{
+						const char *src = reinterpret_cast<const char *>(t.records + size_t(w.x) * RECD) + mm * 16;
+						const uint32_t dst = stage_u32 + uint32_t(buf * L::STAGE + tr * RECD) * 8u + uint32_t(mm) * 16u;
+#pragma unroll
+						for (int i = 0; i < RECD / 6; ++i)
+							cp_async16(dst + i * 48, src + i * 48);
+					}
+					cp_async_commit();
+				}
 			};
 
 			unsigned it = 0; // steps this warp has consumed: buffer = it & 1, barrier parity = (it >> 1) & 1
@@ -243,16 +281,15 @@ namespace pfa
 				int last_n = g + 1 < g_end ? t.grp_off[g + 2] : 0;
 				uint4 w0 = active ? inc[size_t(s_begin) * kTriples + tr] : idle;
 				uint4 w1 = (active && s_begin + 1 < s_end) ? inc[size_t(s_begin + 1) * kTriples + tr] : idle;
-				issue(w0, int(it & 1));
-				if (s_begin + 1 < s_end)
-					issue(w1, int((it + 1) & 1));
+				issue(w0, int(it & 1), true);
+				issue(w1, int((it + 1) & 1), s_begin + 1 < s_end);
 				double g_acc = 0.0;
 				for (int s = s_begin; s < s_end; ++s, ++it)
 				{
 					const int buf = int(it & 1);
-					const uint32_t bar = buf ? bar1 : bar0, parity = (it >> 1) & 1;
-					// the step after next: its words are needed when its copies are issued, at the end of this step
+					// the step whose copies are issued during this step (two steps ahead): its words are needed then
 					const uint4 w2 = (active && s + 2 < s_end) ? inc[size_t(s + 2) * kTriples + tr] : idle;
+					const bool issue_real = s + 2 < s_end;
 					const bool busy = active && w0.x != kIdle;
 					// strip offsets of the NL row positions of this element (doubles, relative to my column); bit 7 of a position byte:
 					// first contribution to these rows
@@ -280,8 +317,17 @@ namespace pfa
 						acc[j][1] = ld ? strip[ko[j] + o1] : 0.0;
 						acc[j][2] = ld ? strip[ko[j] + o2] : 0.0;
 					}
-					while (!mbar_try_wait(bar, parity))
+					if constexpr (TMA)
 					{
+						const uint32_t bar = buf ? bar1 : bar0, parity = (it >> 1) & 1;
+						while (!mbar_try_wait(bar, parity))
+						{
+						}
+					}
+					else
+					{
+						cp_async_wait_1(); // my copies of this step have landed (only the next step's group may be pending)
+						__syncwarp();      // ... and so have the other lanes'
 					}
 					if (busy)
 					{
@@ -291,8 +337,8 @@ namespace pfa
 					__syncwarp(); // every lane has read its record: the buffer can be refilled
 					const bool group_ends = s + 1 == g_last;
 					// (when the group ends here, the flush uses this buffer as its transposition block first)
-					if (s + 2 < s_end && !(L::TB_ALIAS && group_ends))
-						issue(w2, buf);
+					if (!(L::TB_ALIAS && group_ends))
+						issue(w2, buf, issue_real);
 					if (pre)
 					{
 #pragma unroll
@@ -355,11 +401,11 @@ namespace pfa
 						}
 						for (int r0 = 0; r0 < rows_g; r0 += kFlushRows)
 						{
-							// the strips are allocated in whole 32-row blocks: rows past the group's last row are read, never stored
+							// rows past the group's last row are never stored; rows past the allocation are not read
 							double v[16];
 #pragma unroll
 							for (int i = 0; i < 16; ++i)
-								v[i] = smem[L::OFF_STRIP + (r0 + 2 * i + half) * kStripLd + within];
+								v[i] = r0 + 2 * i + half < strip_rows ? smem[L::OFF_STRIP + (r0 + 2 * i + half) * kStripLd + within] : 0.0;
 							if (active)
 							{
 #pragma unroll
@@ -376,10 +422,11 @@ namespace pfa
 									dst[c][r0] = a.scale * v[c];
 							__syncwarp();
 						}
-						if (L::TB_ALIAS && s + 2 < s_end)
+						if (L::TB_ALIAS)
 						{
-							asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); // generic writes of the block before the TMA refill
-							issue(w2, buf);
+							if constexpr (TMA)
+								asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); // generic writes of the block before the TMA refill
+							issue(w2, buf, issue_real);
 						}
 						g_acc = 0.0;
 						++g;
@@ -468,8 +515,12 @@ namespace pfa
 					int per_sm = 1;
 					if ((err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 32, smem)) != cudaSuccess)
 						return err;
+					// PFA_CL_WARPS_PER_SM (environment, experiments): cap on resident warps per SM
+					static const int cap = [] { const char *v = std::getenv("PFA_CL_WARPS_PER_SM"); return v ? std::atoi(v) : 0; }();
+					if (cap > 0)
+						per_sm = std::min(per_sm, cap);
 					const int grid = std::max(1, std::min(nc, sm_count * std::max(per_sm, 1)));
-					kern<<<grid, 32, smem, st>>>(m, a, t, c, c0, c0 + nc);
+					kern<<<grid, 32, smem, st>>>(m, a, t, c, c0, c0 + nc, t.rows_max[c]);
 					if ((err = cudaGetLastError()) != cudaSuccess)
 						return err;
 					++*launches;

@@ -12,6 +12,13 @@ complete CSC columns (= rows, the pattern is symmetric) of the nodes it owns:
     the scalar energy is all-reduced. No replicated matrix, no full-vector all-reduce.
 
 `torch.distributed` is the plumbing (NCCL on GPUs, gloo in the CPU tests).
+
+Round 2 adds the OWNER-COMPUTES form (`partition_owner_computes`, `owner_handle`), which is what bench.py uses: the
+partition comes from the library (`pfa_partition_create`: contiguous element blocks cut so that the (element, node)
+incidences of the owned nodes are balanced, owner = rank of the first element touching a node), every rank holds the ghost
+elements around its owned nodes WITH their geometry (`PFA_FLAG_GHOST_GEOMETRY`) and the column-lane kernels produce the
+finished columns and gradient entries of the owned nodes - there is no interface exchange at all, only the scalar energy
+is all-reduced. The exchange form above stays for the row-lane kernels (`PFA_FLAG_ROW_LANE`) and the other materials.
 """
 from __future__ import annotations
 
@@ -253,3 +260,39 @@ class InterfaceExchange:
         main.wait_event(self._done)
         if energy is not None:
             self.dist.all_reduce(energy)
+
+
+# ---------------------------------------------------------------- owner-computes form (no interface exchange)
+@dataclass
+class OwnerPartition:
+    rank: int
+    world: int
+    conn: np.ndarray          # [n_own + n_ghost, n_loc] local node ids, own elements first
+    n_own_elements: int
+    n_ghost_elements: int
+    vertices: np.ndarray      # [n_own + n_ghost, 4, 3]: the ghost elements carry geometry
+    n_bases: int              # local nodes
+    l2g: np.ndarray           # [n_bases] global node id of each local node
+    owned: np.ndarray         # [n_bases] uint8, 1 = this rank produces the node's columns / gradient entries
+    elements: np.ndarray      # [n_own + n_ghost] global element ids
+
+
+def partition_owner_computes(mesh: TetMesh, rank: int, world: int) -> OwnerPartition:
+    """The library's partition (pfa_partition_create, include/pfa.h) applied to a TetMesh."""
+    from . import capi
+    p = capi.partition(mesh.conn, mesh.n_bases, world, rank)
+    el = p["elements"].astype(np.int64)
+    return OwnerPartition(rank, world, p["conn"], p["n_own"], p["n_ghost"], np.ascontiguousarray(mesh.vertices[el]),
+                          int(p["l2g"].size), p["l2g"].astype(np.int64), p["owned"], el)
+
+
+def owner_handle(part: OwnerPartition, tables_, lam, mu, device=0, material="NeoHookean", flags=0):
+    """One pfa handle per rank: pfa_grad_hess / pfa_hessian write the finished columns of the owned nodes."""
+    from . import capi
+    lam = np.asarray(lam, dtype=np.float64)
+    mu = np.asarray(mu, dtype=np.float64)
+    if lam.ndim > 0:  # per-element arrays of the whole mesh: take this rank's elements
+        lam, mu = lam[part.elements], mu[part.elements]
+    return capi.Handle(material, part.conn, part.n_bases, tables_["weights"], tables_["grad"], vertices=part.vertices, lam=lam, mu=mu,
+                       device=device, n_ghost_elements=part.n_ghost_elements, flags=flags | capi.FLAG_GHOST_GEOMETRY,
+                       owned_nodes=part.owned)
