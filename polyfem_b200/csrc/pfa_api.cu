@@ -48,6 +48,7 @@ struct pfa_handle
 	double *d_energy = nullptr;
 	int *d_counter = nullptr;
 	int32_t epoch = 0; // in-kernel zero-fill generation (row-lane kernels)
+	bool cl_partial = false;    // pfa_mesh_desc.owned_nodes was given: the column-lane path writes the owned nodes only
 	int32_t n_geo_elements = 0; // elements with geometry / material on the device: n_el (+ ghost elements with PFA_FLAG_GHOST_GEOMETRY)
 	ColumnLane2Tables cl; // owner-computes path (default for NeoHookean P1 / P2 on affine elements)
 
@@ -318,7 +319,8 @@ namespace
 			prof_begin(h, "zero_fill(cudaMemsetAsync)", false);
 			if (a.energy)
 				PFA_CUDA(h, cudaMemsetAsync(a.energy, 0, sizeof(double), h->stream));
-			if (a.grad)
+			// (owner-computes partition: the gradient entries of nodes owned by other ranks stay untouched, like their columns)
+			if (a.grad && !(use_cl && h->cl_partial))
 				PFA_CUDA(h, cudaMemsetAsync(a.grad, 0, n_grad * sizeof(double), h->stream));
 			if (a.values && dm.zoff != nullptr && !linear && !project_to_psd && !use_cl)
 				a.epoch = ++h->epoch; // the row-lane kernel clears values[] itself, block by block, just ahead of the scatter
@@ -638,6 +640,7 @@ extern "C"
 						h->cl.rows_max[c] = S.rows_max[c];
 					}
 					h->cl.n_record_elements = int32_t(ngeo);
+					h->cl_partial = d->owned_nodes != nullptr;
 					h->cl.enabled = 1;
 					PFA_CUDA(h, cudaStreamSynchronize(h->stream)); // S is a local
 				}
