@@ -405,6 +405,17 @@ extern "C"
 			pfa_destroy(h);
 			return rc;
 		};
+// inside pfa_create a CUDA failure must release the half-built handle and keep the message for pfa_last_error(NULL)
+#define PFA_CREATE_CUDA(call)                                                                              \
+	do                                                                                                     \
+	{                                                                                                      \
+		cudaError_t e_ = (call);                                                                           \
+		if (e_ != cudaSuccess)                                                                             \
+		{                                                                                                  \
+			h->err = std::string("pfa_create: " #call ": ") + cudaGetErrorString(e_);                      \
+			return bail(e_ == cudaErrorMemoryAllocation ? PFA_ERR_NOMEM : PFA_ERR_CUDA);                   \
+		}                                                                                                  \
+	} while (0)
 		h->device = d->device;
 		{
 			cudaError_t e = cudaSetDevice(d->device);
@@ -568,7 +579,7 @@ extern "C"
 			std::vector<double> mom;
 			reference_moments(d->ref_grads, d->quad_weights, m.n_loc, m.n_qp, mom);
 			UP(m.ref_moments, mom.data(), mom.size(), double);
-			PFA_CUDA(h, cudaStreamSynchronize(h->stream)); // mom is a local
+			PFA_CREATE_CUDA(cudaStreamSynchronize(h->stream)); // mom is a local
 		}
 		UP(m.qweights, d->quad_weights, nq, double);
 		UP(m.adj_off, hp.adj_off.data(), hp.adj_off.size(), int32_t);
@@ -606,9 +617,9 @@ extern "C"
 			}
 			if ((rc = dev_alloc<int32_t>(h, &m.zflag, size_t(m.n_batches))) != PFA_OK)
 				return bail(rc);
-			PFA_CUDA(h, cudaMemsetAsync(m.zflag, 0, size_t(m.n_batches) * sizeof(int32_t), h->stream));
+			PFA_CREATE_CUDA(cudaMemsetAsync(m.zflag, 0, size_t(m.n_batches) * sizeof(int32_t), h->stream));
 			}
-			PFA_CUDA(h, cudaStreamSynchronize(h->stream)); // cstride, zoff, zruns are locals
+			PFA_CREATE_CUDA(cudaStreamSynchronize(h->stream)); // cstride, zoff, zruns are locals
 			// owner-computes path (default): schedule of (element, node) incidences + record buffer
 			static const bool rl_env = [] { const char *v = std::getenv("PFA_ROW_LANE"); return v && std::atoi(v) != 0; }();
 			int max_deg = 0;
@@ -642,7 +653,7 @@ extern "C"
 					h->cl.n_record_elements = int32_t(ngeo);
 					h->cl_partial = d->owned_nodes != nullptr;
 					h->cl.enabled = 1;
-					PFA_CUDA(h, cudaStreamSynchronize(h->stream)); // S is a local
+					PFA_CREATE_CUDA(cudaStreamSynchronize(h->stream)); // S is a local
 				}
 				catch (const std::bad_alloc &)
 				{
@@ -682,6 +693,7 @@ extern "C"
 			UP(m.detj, d->da, ne * nq, double);
 		}
 #undef UP
+#undef PFA_CREATE_CUDA
 		if ((rc = dev_alloc<int32_t>(h, &h->d_outer, size_t(h->ndof) + 1)) != PFA_OK || (rc = dev_alloc<int32_t>(h, &h->d_inner, size_t(h->nnz))) != PFA_OK || (rc = dev_alloc<double>(h, &h->d_energy, 1)) != PFA_OK || (rc = dev_alloc<int>(h, &h->d_counter, 4)) != PFA_OK)
 			return bail(rc);
 		{

@@ -888,6 +888,9 @@ namespace pfa
 						}
 					}
 				}
+				// lanes without a row (lanes 30-31 for P2, 24-31 for P1, tail elements) must not run ahead into the next batch and
+				// overwrite the connectivity / stride / entry tables the row lanes are still reading
+				__syncwarp();
 				batch = next_batch;
 			}
 

@@ -43,16 +43,30 @@ namespace polyfem::assembler::b200
 			key_ = nullptr;
 		}
 
+		/// Call from add_multimaterial / set_materials / set_size overrides: the next assemble_* re-evaluates lambda, mu
+		/// (or the density) and uploads them with pfa_set_materials.
+		void invalidate_materials() const { ++material_version_; }
+
 		/// Reads what the hot path needs out of `bases` / `gbases` once per mesh.
 		/// `lame(e, q, lambda, mu)` evaluates LameParameters::lambda_mu for element e at qp q.
 		template <typename LameFn>
 		pfa_handle *get(const pfa_material material, const bool is_volume, const int n_basis,
 						const std::vector<basis::ElementBases> &bases,
 						const std::vector<basis::ElementBases> &gbases,
-						const AssemblyValsCache &cache, const LameFn &lame) const
+						const AssemblyValsCache &cache, const double t, const LameFn &lame) const
 		{
-			if (h_ && key_ == bases.data() && n_elements_ == int(bases.size()))
+			// The handle is keyed on the FE space (bases pointer, element count and the first element's basis count / first
+			// global index, which change when a vector is re-allocated at the same address for another space). The reference
+			// evaluates lambda_mu(..., t, ...) on every assemble_* call (MatParams.cpp:368-401): when t or the material
+			// version changed since the last upload, the parameters are re-evaluated and sent with pfa_set_materials.
+			const int first_global = bases.empty() || bases[0].bases.empty() ? -1 : bases[0].bases[0].global()[0].index;
+			const int first_count = bases.empty() ? 0 : int(bases[0].bases.size());
+			if (h_ && key_ == bases.data() && n_elements_ == int(bases.size()) && n_basis_ == n_basis && first_global_ == first_global && first_count_ == first_count)
+			{
+				if (t != t_ || material_version_ != uploaded_version_)
+					refresh_materials(material, is_volume, bases, gbases, cache, lame, t);
 				return h_;
+			}
 			const_cast<DeviceAssembly *>(this)->reset();
 			if (!is_volume)
 				log_and_throw_error("B200 assembly path: only volumetric (tetrahedral) meshes are supported");
@@ -146,7 +160,35 @@ namespace polyfem::assembler::b200
 				log_and_throw_error("B200 assembly path: {}", pfa_last_error(nullptr));
 			key_ = bases.data();
 			n_elements_ = n_el;
+			n_basis_ = n_basis;
+			first_global_ = first_global;
+			first_count_ = first_count;
+			n_qp_ = n_qp;
+			t_ = t;
+			uploaded_version_ = material_version_;
 			return h_;
+		}
+
+		/// lambda / mu (or the density) of every (element, quadrature point) again, for a new t or after a material change
+		template <typename LameFn>
+		void refresh_materials(const pfa_material material, const bool is_volume, const std::vector<basis::ElementBases> &bases,
+							   const std::vector<basis::ElementBases> &gbases, const AssemblyValsCache &cache, const LameFn &lame, const double t) const
+		{
+			if (material != PFA_LAPLACIAN)
+			{
+				const int n_el = int(bases.size());
+				std::vector<double> lambda(size_t(n_el) * n_qp_), mu(size_t(n_el) * n_qp_);
+				ElementAssemblyValues vals;
+				for (int e = 0; e < n_el; ++e)
+				{
+					cache.compute(e, is_volume, bases[e], gbases[e], vals);
+					for (int q = 0; q < n_qp_; ++q)
+						lame(vals, q, lambda[size_t(e) * n_qp_ + q], mu[size_t(e) * n_qp_ + q]);
+				}
+				check(h_, pfa_set_materials(h_, lambda.data(), material == PFA_MASS ? nullptr : mu.data(), n_qp_));
+			}
+			t_ = t;
+			uploaded_version_ = material_version_;
 		}
 
 		/// Wraps values[] in the reference's matrix type (pattern identical to SparseMatrixCache's).
@@ -172,7 +214,9 @@ namespace polyfem::assembler::b200
 	private:
 		mutable pfa_handle *h_ = nullptr;
 		mutable const void *key_ = nullptr;
-		mutable int n_elements_ = 0;
+		mutable int n_elements_ = 0, n_basis_ = 0, first_global_ = -1, first_count_ = 0, n_qp_ = 0;
+		mutable double t_ = 0;
+		mutable unsigned material_version_ = 0, uploaded_version_ = 0;
 	};
 
 	/// Drop-in for NeoHookeanElasticity ("NeoHookean" in AssemblerUtils::make_assembler).
@@ -197,6 +241,8 @@ namespace polyfem::assembler::b200
 													const double t, const double dt, const Eigen::MatrixXd &displacement,
 													const Eigen::MatrixXd &displacement_prev) const override
 		{
+			if (use_robust_jacobian) // the whole assembler forwards: energy, gradient and Hessian must use the same Jacobian
+				return NeoHookeanElasticity::assemble_energy_per_element(is_volume, bases, gbases, cache, t, dt, displacement, displacement_prev);
 			pfa_handle *h = handle(is_volume, int(displacement.size() / size()), bases, gbases, cache, t);
 			Eigen::VectorXd out(bases.size());
 			DeviceAssembly::check(h, pfa_energy_per_element(h, displacement.data(), out.data()));
@@ -208,6 +254,8 @@ namespace polyfem::assembler::b200
 							   const double t, const double dt, const Eigen::MatrixXd &displacement,
 							   const Eigen::MatrixXd &displacement_prev, Eigen::MatrixXd &rhs) const override
 		{
+			if (use_robust_jacobian) // NeoHookeanElasticity.cpp:475-498 uses jacs(p) * det(jac_it) in the gradient too
+				return NeoHookeanElasticity::assemble_gradient(is_volume, n_basis, bases, gbases, cache, t, dt, displacement, displacement_prev, rhs);
 			pfa_handle *h = handle(is_volume, n_basis, bases, gbases, cache, t);
 			rhs.resize(n_basis * size(), 1);
 			DeviceAssembly::check(h, pfa_gradient(h, displacement.data(), rhs.data()));
@@ -219,6 +267,8 @@ namespace polyfem::assembler::b200
 							  const Eigen::MatrixXd &displacement, const Eigen::MatrixXd &displacement_prev,
 							  utils::MatrixCache &mat_cache, StiffnessMatrix &hess) const override
 		{
+			if (use_robust_jacobian) // ... and in the Hessian (NeoHookeanElasticity.cpp:567-587)
+				return NeoHookeanElasticity::assemble_hessian(is_volume, n_basis, project_to_psd, bases, gbases, cache, t, dt, displacement, displacement_prev, mat_cache, hess);
 			pfa_handle *h = handle(is_volume, n_basis, bases, gbases, cache, t);
 			int64_t nnz;
 			pfa_sizes(h, nullptr, nullptr, &nnz);
@@ -228,11 +278,23 @@ namespace polyfem::assembler::b200
 			// mat_cache is caller-owned scratch (ElasticForm.hpp:116); it is left untouched and valid.
 		}
 
+		// material changes after the first assembly must reach the device (the handle caches lambda / mu)
+		void add_multimaterial(const int index, const json &params, const Units &units, const std::string &root_path) override
+		{
+			NeoHookeanElasticity::add_multimaterial(index, params, units, root_path);
+			dev_.invalidate_materials();
+		}
+		void set_size(const int size) override
+		{
+			NeoHookeanElasticity::set_size(size);
+			dev_.invalidate_materials();
+		}
+
 	private:
 		pfa_handle *handle(const bool is_volume, const int n_basis, const std::vector<basis::ElementBases> &bases,
 						   const std::vector<basis::ElementBases> &gbases, const AssemblyValsCache &cache, const double t) const
 		{
-			return dev_.get(PFA_NEOHOOKEAN, is_volume, n_basis, bases, gbases, cache,
+			return dev_.get(PFA_NEOHOOKEAN, is_volume, n_basis, bases, gbases, cache, t,
 							[&](const ElementAssemblyValues &vals, const int q, double &lambda, double &mu) {
 								lame_params().lambda_mu(vals.quadrature.points.row(q), vals.val.row(q), t, vals.element_id, lambda, mu);
 							});
@@ -251,7 +313,7 @@ namespace polyfem::assembler::b200
 		{
 			if (is_mass)
 				return Laplacian::assemble(is_volume, n_basis, bases, gbases, cache, t, stiffness, is_mass);
-			pfa_handle *h = dev_.get(PFA_LAPLACIAN, is_volume, n_basis, bases, gbases, cache,
+			pfa_handle *h = dev_.get(PFA_LAPLACIAN, is_volume, n_basis, bases, gbases, cache, t,
 									 [](const ElementAssemblyValues &, const int, double &lambda, double &mu) { lambda = mu = 0; });
 			int64_t nnz;
 			pfa_sizes(h, nullptr, nullptr, &nnz);
@@ -276,7 +338,7 @@ namespace polyfem::assembler::b200
 		{
 			if (size() != 3)
 				return Mass::assemble(is_volume, n_basis, bases, gbases, cache, t, stiffness, is_mass);
-			pfa_handle *h = dev_.get(PFA_MASS, is_volume, n_basis, bases, gbases, cache,
+			pfa_handle *h = dev_.get(PFA_MASS, is_volume, n_basis, bases, gbases, cache, t,
 									 [&](const ElementAssemblyValues &vals, const int q, double &rho, double &unused) {
 										 rho = density()(vals.quadrature.points.row(q), vals.val.row(q), t, vals.element_id);
 										 unused = 0;
@@ -372,7 +434,7 @@ namespace polyfem::assembler::b200
 		pfa_handle *handle(const bool is_volume, const int n_basis, const std::vector<basis::ElementBases> &bases,
 						   const std::vector<basis::ElementBases> &gbases, const AssemblyValsCache &cache, const double t) const
 		{
-			return dev_.get(PFA_LINEAR_ELASTICITY, is_volume, n_basis, bases, gbases, cache,
+			return dev_.get(PFA_LINEAR_ELASTICITY, is_volume, n_basis, bases, gbases, cache, t,
 							[&](const ElementAssemblyValues &vals, const int q, double &lambda, double &mu) {
 								lame_params().lambda_mu(vals.quadrature.points.row(q), vals.val.row(q), t, vals.element_id, lambda, mu);
 							});

@@ -45,6 +45,8 @@ namespace Eigen
 
 namespace polyfem
 {
+	struct json; // nlohmann::json (utils/Types.hpp / Common.hpp), only passed through by reference
+	class Units; // polyfem/Units.hpp
 	// utils/Types.hpp:24  typedef Eigen::SparseMatrix<double, Eigen::ColMajor> StiffnessMatrix;
 	struct StiffnessMatrix
 	{
@@ -125,6 +127,8 @@ namespace polyfem
 			virtual ~Assembler() = default;
 			virtual std::string name() const = 0;
 			int size() const;
+			virtual void set_size(const int size);                                                                                       // Assembler.hpp:64
+			virtual void add_multimaterial(const int index, const json &params, const Units &units, const std::string &root_path);       // Assembler.hpp:190
 			virtual void assemble(const bool is_volume, const int n_basis, const std::vector<basis::ElementBases> &bases,
 								  const std::vector<basis::ElementBases> &gbases, const AssemblyValsCache &cache, const double t,
 								  StiffnessMatrix &stiffness, const bool is_mass = false) const;
@@ -182,6 +186,7 @@ namespace polyfem
 		{
 		public:
 			std::string name() const override;
+			void add_multimaterial(const int index, const json &params, const Units &units, const std::string &root_path) override; // NeoHookeanElasticity.hpp:53
 			const LameParameters &lame_params() const; // :56
 		};
 		class LinearElasticity : public LinearAssembler, public ElasticityNLAssembler // LinearElasticity.hpp
