@@ -35,11 +35,52 @@ sys.path.insert(0, ROOT)
 METRIC = "elements/s (NeoHookean P2 grad+Hessian assembly)"
 UNIT = "elements/s"
 E_MOD, NU = 1e5, 0.3
+RHO, DT = 1000.0, 1e-3  # cfg 5
+
+# BASELINE.json configs[0..4] -> --config 1..5 (3 is the headline and the default; "4le" is the LinearElasticity half of
+# configs[3], at the largest n whose matrix fits int32 nnz - StiffnessMatrix uses int indices unless POLYSOLVE_LARGE_INDEX).
+#   mode: nl     fused energy + gradient + Hessian (pfa_grad_hess)
+#         linear LinearAssembler::assemble (pfa_linear_stiffness)
+#         euler  one implicit-Euler Newton assembly: dt^2-weighted elastic form + InertiaForm on the mass matrix
+# cpu_n: cells per side of the bounded CPU sample of the same material / order (about 1-3 s of host work per step)
+CONFIGS = {
+    "1": dict(material="LinearElasticity", p=1, n=20, mode="linear", cpu_n=20, what="stiffness assembly (pfa_linear_stiffness)"),
+    "2": dict(material="NeoHookean", p=1, n=44, mode="nl", cpu_n=30, what="fused energy+gradient+Hessian (pfa_grad_hess)"),
+    "3": dict(material="NeoHookean", p=2, n=69, mode="nl", cpu_n=24, what="fused energy+gradient+Hessian (pfa_grad_hess)"),
+    "4": dict(material="Laplacian", p=4, n=32, mode="linear", cpu_n=8, what="stiffness assembly (pfa_linear_stiffness)"),
+    "4le": dict(material="LinearElasticity", p=4, n=16, mode="linear", cpu_n=5, what="stiffness assembly (pfa_linear_stiffness)"),
+    "5": dict(material="NeoHookean", p=1, n=119, mode="euler", cpu_n=30,
+              what="implicit-Euler Newton assembly: dt^2-weighted pfa_grad_hess_weighted + pfa_inertia + H = dt^2 H_el + M"),
+}
+FP64_PEAK_TFLOPS = 36.9  # DFMA peak measured on this pool's B200 (tools/microbench5.cu, profiles/microbench5_r02.jsonl)
 
 
-def b_alg_bytes_per_element(n_loc, ndof, nnz, n_el):
-    """compulsory traffic per element (inputs once, outputs once)."""
-    return 4 * n_loc + 80 + 16 + 8 * ndof / n_el + 8 * ndof / n_el + 8 * nnz / n_el
+def metric_name(cfg):
+    if cfg["material"] == "NeoHookean" and cfg["p"] == 2 and cfg["mode"] == "nl":
+        return METRIC
+    what = {"nl": "grad+Hessian assembly", "linear": "stiffness assembly", "euler": "implicit-Euler grad+Hessian assembly"}[cfg["mode"]]
+    return f"elements/s ({cfg['material']} P{cfg['p']} {what})"
+
+
+def workload_name(cfg, mesh):
+    size = 1 if cfg["material"] == "Laplacian" else 3
+    return (f"{cfg['material']} P{cfg['p']} tets, Kuhn cube n={cfg['n']}: {mesh.n_elements} elements, {mesh.n_bases * size} dofs, {cfg['what']}")
+
+
+def b_alg_bytes_per_element(n_loc, ndof, nnz, n_el, linear=False, laplacian=False):
+    """compulsory traffic per element (inputs once, outputs once); the linear assemblers read no x and write
+    no gradient, the Laplacian has no Lame parameters."""
+    return 4 * n_loc + 80 + (0 if laplacian else 16) + (0 if linear else 2 * 8 * ndof / n_el) + 8 * nnz / n_el
+
+
+def f_alg_flops_per_element(material, n_loc, n_qp):
+    """SURVEY.md §8d algorithmic FLOPs per element (symmetric half of B^T D B for the linear forms)."""
+    if material == "Laplacian":
+        return n_qp * 3 * n_loc * n_loc
+    if material == "LinearElasticity":
+        N = 3 * n_loc
+        return n_qp * (72 * N + 6 * N * N)
+    return n_qp * (2 * (81 * n_loc + 27 * n_loc * (n_loc + 1) / 2) + 300)
 
 
 def ncu_traffic(kernel_name, n_el, world):
@@ -134,8 +175,7 @@ class ClockSampler:
 
 
 def build_workload(n, p, rank=0, world=1):
-    """Mesh + tables; for world > 1 the elements are split into `world` contiguous blocks
-    (x-slabs of the cube) and this rank keeps its block, renumbered locally."""
+    """Mesh + tables of the synthetic Kuhn cube."""
     from polyfem_b200 import mesh as M, tables
     mesh = M.kuhn_cube(n, p)
     x = M.random_displacement(mesh)
@@ -143,53 +183,93 @@ def build_workload(n, p, rank=0, world=1):
     return mesh, x, t
 
 
-def cpu_baseline_run(n_sample, p, steps, warmup, threads):
-    """Times the oracle (reference-algorithm port) on a bounded sample of the workload:
-    steady-state energy + gradient + Hessian per step (pattern build = first call, untimed)."""
+def cpu_baseline_run(cfg, n_sample, steps, warmup, threads, use_cache=False):
+    """Times the oracle (reference-algorithm port) on a bounded sample of the workload: the steady-state step of the config
+    (pattern build = first call, untimed, like pfa_create). use_cache=False: assembly values recomputed per call, which is
+    what the reference does at the headline size (the basis cache is dropped above 900 k bases,
+    varforms/ElasticVarForm.cpp:217-232)."""
     from oracle import pyoracle
     from polyfem_b200 import mesh as M
-    mesh = M.kuhn_cube(n_sample, p)
+    mesh = M.kuhn_cube(n_sample, cfg["p"])
     x = M.random_displacement(mesh)
-    prob = pyoracle.problem_from_mesh(mesh, "NeoHookean", E=E_MOD, nu=NU, n_threads=threads, use_cache=True)
+    prob = pyoracle.problem_from_mesh(mesh, cfg["material"], E=E_MOD, nu=NU, n_threads=threads, use_cache=use_cache)
+    nl = cfg["mode"] != "linear"
+    mass = pyoracle.problem_from_mesh(mesh, "Mass", rho=RHO, n_threads=threads) if cfg["mode"] == "euler" else None
+    M_mat = mass.assemble() if mass is not None else None
+    xt = 0.5 * x if mass is not None else None
+
+    def step():
+        if not nl:
+            prob.assemble()
+            return
+        prob.assemble_energy(x)
+        prob.assemble_gradient(x)
+        prob.assemble_hessian(x)
+        if mass is not None:
+            pyoracle.inertia(M_mat, x[: M_mat.outer.size - 1], xt[: M_mat.outer.size - 1])
+
     t0 = time.perf_counter()
-    prob.assemble_hessian(x)  # first call: triplets + pattern + slot map (one-off, like pfa_create)
+    step()  # first call: triplets + pattern + slot map (one-off)
     first = time.perf_counter() - t0
     for _ in range(warmup):
-        prob.assemble_energy(x)
-        prob.assemble_gradient(x)
-        prob.assemble_hessian(x)
+        step()
     t0 = time.perf_counter()
     for _ in range(steps):
-        prob.assemble_energy(x)
-        prob.assemble_gradient(x)
-        prob.assemble_hessian(x)
+        step()
     dt = (time.perf_counter() - t0) / max(steps, 1)
-    return {"elements": mesh.n_elements, "seconds_per_step": dt, "first_call_seconds": first,
-            "value": mesh.n_elements / dt}
+    return {"elements": mesh.n_elements, "seconds_per_step": dt, "first_call_seconds": first, "value": mesh.n_elements / dt}
 
 
-def run_reference(args):
+def cpu_sample_text(cfg, n_sample, r, use_cache, steps):
+    return (f"{cfg['material']} P{cfg['p']} Kuhn cube n={n_sample} ({r['elements']} elements), {steps} steady-state steps ({cfg['what']}), "
+            f"basis cache {'on' if use_cache else 'off (as the reference above 900 k bases)'}; first call (pattern build) {r['first_call_seconds']:.2f}s excluded")
+
+
+def run_reference(args, cfg):
+    """--impl reference: the CPU arm. Same metric / unit / config as our arm; every step is a bounded sample of that workload
+    (cpu_baseline.sample says which), all host threads, the same K and W."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
+    from polyfem_b200 import mesh as M
     threads = os.cpu_count() or 1
-    steps = max(args.steps, 1)
-    r = cpu_baseline_run(args.cpu_sample_n, args.p, steps, min(args.warmup, 1), threads)
-    sample = (f"NeoHookean P{args.p} Kuhn cube n={args.cpu_sample_n} ({r['elements']} elements), steady-state "
-              f"energy+gradient+Hessian per step; first call (pattern build) {r['first_call_seconds']:.2f}s excluded")
+    steps, warmup = max(args.steps, 1), max(args.warmup, 3)
+    n_sample = args.cpu_sample_n or cfg["cpu_n"]
+    r = cpu_baseline_run(cfg, n_sample, steps, warmup, threads, use_cache=False)
+    r_on = cpu_baseline_run(cfg, n_sample, 2, 1, threads, use_cache=True)
+    # the config line of our arm (sizes in closed form: the headline mesh itself is not built here)
+    n, p = cfg["n"], cfg["p"]
+    n_el = 6 * n ** 3
+    n_nodes = (p * n + 1) ** 3
+    size = 1 if cfg["material"] == "Laplacian" else 3
+
+    class Sizes:
+        n_elements, n_bases = n_el, n_nodes
     line = {
-        "impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
-        "steps": steps, "warmup": min(args.warmup, 1), "ms_per_step": r["seconds_per_step"] * 1e3,
+        "impl": "reference", "metric": metric_name(cfg), "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
+        "steps": steps, "warmup": warmup, "ms_per_step": r["seconds_per_step"] * 1e3,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"NeoHookean P{args.p} tets, Kuhn cube n={args.n} (bounded CPU sample n={args.cpu_sample_n})",
-                   "material": "E=1e5 nu=0.3", "displacement": "0.05*h*U(-1,1) seed 42"},
-        "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "config": config_dict(cfg, Sizes, None, 1, None),
+        "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": cpu_sample_text(cfg, n_sample, r, False, steps),
+                         "value_basis_cache_on": r_on["value"]},
         "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
-        "note": "CPU restatement of the reference algorithm (oracle/), not the PolyFEM binary: Eigen/TBB are not available offline",
+        "note": "CPU restatement of the reference algorithm (oracle/), not the PolyFEM binary: Eigen/TBB are not available offline; "
+                f"ms_per_step is the time of one step on the {r['elements']}-element sample",
     }
     print(json.dumps(line))
     return 0
+
+
+def config_dict(cfg, mesh, h, world, parallelism):
+    """`config` of the JSON line: identical for our arm and the reference arm (same workload, material, inputs)."""
+    d = {"workload": workload_name(cfg, mesh), "material": "E=1e5 nu=0.3" if cfg["material"] != "Laplacian" else "-",
+         "displacement": "0.05*h*U(-1,1) seed 42" if cfg["mode"] != "linear" else "-",
+         "l2": "outputs (values[]) exceed the 126 MB L2 for configs 3-5; configs 1, 2: an L2 flush (256 MB write) runs between timed steps"}
+    if cfg["mode"] == "euler":
+        d["time_integrator"] = f"implicit Euler dt={DT} rho={RHO}: elastic weight dt^2 (ImplicitEuler.cpp:28-31), InertiaForm on the mass matrix"
+    return d
 
 
 def main():
@@ -198,10 +278,11 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--n", type=int, default=69, help="cells per side (69 -> 1 971 054 tets, BASELINE cfg 3)")
-    ap.add_argument("--p", type=int, default=2)
+    ap.add_argument("--config", default="3", choices=sorted(CONFIGS), help="BASELINE.json configs[k-1]; 3 = the headline (NeoHookean P2, n=69)")
+    ap.add_argument("--n", type=int, default=None, help="cells per side, overrides the config's (69 -> 1 971 054 tets)")
+    ap.add_argument("--p", type=int, default=None, help="basis order, overrides the config's")
     ap.add_argument("--e2e-steps", type=int, default=2)
-    ap.add_argument("--cpu-sample-n", type=int, default=20, help="cells per side of the bounded CPU sample (20 -> 48 000 P2 tets, ~10-20 s of host work)")
+    ap.add_argument("--cpu-sample-n", type=int, default=None, help="cells per side of the bounded CPU sample (default: per config, about 1-3 s of host work per step)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-align", action="store_true", help="multi-GPU: cut the element range evenly instead of on whole cell layers")
     ap.add_argument("--graph", action="store_true", help="multi-GPU, experimental: capture the step in a CUDA graph and replay it "
@@ -212,10 +293,17 @@ def main():
                     "assembly of the rest (measured no faster than the plain order in round 1)")
     ap.add_argument("--flags", type=int, default=0, help="pfa_mesh_desc.flags (1 = keep the caller's element order, 2 = in-kernel zero fill, 8 = round-1 row-lane RED kernels)")
     args = ap.parse_args()
-    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    args.warmup = max(args.warmup, 3)
+    cfg = dict(CONFIGS[args.config])
+    if args.n is not None:
+        cfg["n"] = args.n
+    if args.p is not None:
+        cfg["p"] = args.p
+    args.n, args.p = cfg["n"], cfg["p"]
+    mode = cfg["mode"]
 
     if args.impl == "reference":
-        return run_reference(args)
+        return run_reference(args, cfg)
 
     import torch
     import torch.distributed as dist
@@ -242,6 +330,8 @@ def main():
     mesh, x_host, t = build_workload(args.n, args.p)
     lam, mu = lame_from_E_nu(E_MOD, NU)
     exch = None
+    if world > 1 and cfg["material"] != "NeoHookean":
+        raise SystemExit("bench.py: multi-GPU runs exist for the NeoHookean configs (2, 3, 5); the linear assemblers are single-GPU here")
     owner_mode = world > 1 and not args.exchange
     if owner_mode:
         # owner-computes form: the library's partition, ghost elements with geometry, every rank writes the
@@ -252,22 +342,59 @@ def main():
         # round-1 form (--exchange, or one GPU): cuts on whole layers of cells (6 n^2 tets), partial sums of interface
         # columns go point-to-point to their owners
         part = pdist.partition_elements(mesh, rank, world, align=1 if args.no_align else 6 * args.n * args.n)
-        h = capi.Handle("NeoHookean", part.conn, part.n_bases, t["weights"], t["grad"], vertices=part.vertices,
+        h = capi.Handle(cfg["material"], part.conn, part.n_bases, t["weights"], t["grad"], vertices=part.vertices,
                         lam=lam, mu=mu, device=local_rank, n_ghost_elements=part.n_ghost_elements,
                         flags=args.flags | (capi.FLAG_ROW_LANE if world > 1 else 0), n_first_elements=part.n_interface_elements)
     h.set_stream(torch.cuda.current_stream().cuda_stream)
     if world > 1 and not owner_mode:
         exch = pdist.InterfaceExchange(h, part, rank, world, dev, grad_offset=h.nnz)
 
-    x_loc = np.ascontiguousarray(x_host.reshape(-1, 3)[part.l2g].reshape(-1))
+    size = h.size
+    x_loc = np.ascontiguousarray(x_host.reshape(-1, 3)[part.l2g].reshape(-1))[: h.ndof] if size == 3 else np.zeros(h.ndof)
     xd = torch.from_numpy(x_loc).to(dev)
     e_d = torch.zeros(1, dtype=torch.float64, device=dev)
     # values[] and the gradient share one allocation so that the interface exchange packs both at once
     vg_d = torch.zeros(h.nnz + h.ndof, dtype=torch.float64, device=dev)
     v_d, g_d = vg_d[:h.nnz], vg_d[h.nnz:]
 
-    def step():
+    # cfg 5: the mass matrix (assembled once, like State::build_mass_matrix) and the InertiaForm buffers. In the
+    # owner-computes partition the mass handle takes own AND ghost elements as its elements, so that the columns of the
+    # owned nodes are complete without an exchange; the energy of the inertia term is summed over owned dofs only.
+    hm = m_d = xt_d = ei_d = gi_d = owned_dofs = None
+    if mode == "euler":
+        from polyfem_b200 import tables as T
+        tm = T.reference_tables(args.p, T.quadrature_order(args.p, is_mass=True))
+        hm = capi.Handle("Mass", part.conn, part.n_bases, tm["weights"], None, vertices=part.vertices if owner_mode else part.vertices,
+                         device=local_rank, ref_vals=tm["val"], density=RHO) if (owner_mode or world == 1) else None
+        if hm is None:
+            raise SystemExit("bench.py --config 5 runs on one GPU or in the owner-computes multi-GPU form")
+        hm.set_stream(torch.cuda.current_stream().cuda_stream)
+        assert hm.nnz == h.nnz  # same connectivity, same pattern: H = dt^2 H_el + M is one axpy
+        m_d = torch.zeros(h.nnz, dtype=torch.float64, device=dev)
+        hm.linear_stiffness_raw(m_d)
+        xt_d = (0.5 * xd).contiguous()  # x_tilde = x_prev + dt v_prev is the caller's (ImplicitEuler.cpp:13-16)
+        ei_d = torch.zeros(1, dtype=torch.float64, device=dev)
+        gi_d = torch.zeros(h.ndof, dtype=torch.float64, device=dev)
         if owner_mode:
+            owned_dofs = torch.from_numpy(np.repeat(part.owned.astype(bool), 3)).to(dev)
+
+    # configs whose outputs fit the 126 MB L2 (cfg 1, 2): flush L2 between timed steps
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev) if 8 * h.nnz < (200 << 20) else None
+
+    def step():
+        if mode == "linear":
+            h.linear_stiffness_raw(v_d)
+        elif mode == "euler":
+            h.grad_hess_weighted_raw(xd, DT * DT, e_d, g_d, v_d)            # dt^2 (E_el, g_el, H_el)
+            hm.inertia_raw(m_d, xd, xt_d, ei_d, gi_d)                        # 1/2 d^T M d, M d
+            h.axpy(1.0, gi_d, g_d)
+            h.axpy(1.0, m_d, v_d)                                           # H = dt^2 H_el + M
+            if owner_mode:
+                e_d.add_(0.5 * torch.dot((xd - xt_d)[owned_dofs], gi_d[owned_dofs]))
+                dist.all_reduce(e_d)
+            else:
+                e_d.add_(ei_d)
+        elif owner_mode:
             h.grad_hess_raw(xd, e_d, g_d, v_d)
             dist.all_reduce(e_d)
         elif exch is None:
@@ -333,12 +460,25 @@ def main():
     launches0 = h.launch_count() + (exch.launches if exch else 0)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
-    ev0.record()
-    for _ in range(args.steps):
-        step()
-    ev1.record()
-    barrier()
-    ms_total = ev0.elapsed_time(ev1)
+    if flush is None:
+        ev0.record()
+        for _ in range(args.steps):
+            step()
+        ev1.record()
+        barrier()
+        ms_total = ev0.elapsed_time(ev1)
+    else:
+        # small configs: an L2 flush (256 MB write) before every step, outside the per-step event pairs
+        pairs = []
+        for _ in range(args.steps):
+            flush.zero_()
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a0.record()
+            step()
+            a1.record()
+            pairs.append((a0, a1))
+        barrier()
+        ms_total = float(sum(a0.elapsed_time(a1) for a0, a1 in pairs))
     clocks = sampler.stop() if rank == 0 else None
     recs = h.profile_read()
     h.profile_enable(False)
@@ -404,8 +544,9 @@ def main():
     fill = [ms for (name, ms) in recs if "zero_fill" in name]
     kern_ms = float(np.sum(kern)) / prof_steps if kern else float("nan")  # per step (two launches when the step is split)
     peak, peak_src = measured_peaks()
+    linear = mode == "linear"
     if world == 1:
-        b_alg = b_alg_bytes_per_element(h.n_loc, h.ndof, h.nnz, h.n_elements)
+        b_alg = b_alg_bytes_per_element(h.n_loc, h.ndof, h.nnz, h.n_elements, linear, cfg["material"] == "Laplacian")
         achieved = b_alg * h.n_elements / (kern_ms * 1e-3) / 1e9
     else:
         # per GPU: the whole mesh's compulsory bytes per element (closed-form nnz of the Kuhn cube) times this
@@ -415,34 +556,47 @@ def main():
         b_alg = b_alg_bytes_per_element(h.n_loc, 3 * mesh.n_bases, nnz_g, mesh.n_elements)
         achieved = b_alg * (mesh.n_elements / world) / (kern_ms * 1e-3) / 1e9
     kname = sorted({name for (name, ms) in recs if "assemble" in name})[0] if kern else None
+    f_alg = f_alg_flops_per_element(cfg["material"], h.n_loc, h.n_qp)
+    fp64_tflops = f_alg * (h.n_elements if world == 1 else mesh.n_elements / world) / (kern_ms * 1e-3) / 1e12
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": ncu_traffic(kname, h.n_elements, world), "kernel": kname,
                 "kernel_ms": kern_ms,
                 "zero_fill_ms": float(np.sum(fill)) / prof_steps if fill else 0.0,
-                "algorithmic_bytes_per_element": b_alg, "peak_source": peak_src + " (of measured)"}
+                "algorithmic_bytes_per_element": b_alg, "peak_source": peak_src + " (of measured)",
+                # the FP64 side of the same launch (SURVEY.md §8d F_alg; DFMA peak measured by tools/microbench5.cu): the P4
+                # configs are specified FP64-bound, and the P2 headline sits above the FP64 ridge too (6.6 FLOP/B vs 5.6)
+                "fp64": {"achieved_tflops": fp64_tflops, "peak_tflops": FP64_PEAK_TFLOPS, "frac": fp64_tflops / FP64_PEAK_TFLOPS,
+                         "algorithmic_flops_per_element": f_alg}}
 
     # e2e through the C ABI with pinned HOST buffers (H2D x, D2H E + grad + values every step)
     e2e = None
     if args.e2e_steps <= 0:
         e2e = None
-    elif world == 1:
+    elif world == 1 and mode != "euler":
         xh = torch.from_numpy(x_loc).pin_memory()
         eh = torch.zeros(1, dtype=torch.float64).pin_memory()
         gh = torch.zeros(h.ndof, dtype=torch.float64).pin_memory()
         vh = torch.zeros(h.nnz, dtype=torch.float64).pin_memory()
-        h.grad_hess_raw(xh.numpy(), eh.numpy(), gh.numpy(), vh.numpy())
+
+        def host_call():
+            if linear:
+                h.linear_stiffness_raw(vh.numpy())
+            else:
+                h.grad_hess_raw(xh.numpy(), eh.numpy(), gh.numpy(), vh.numpy())
+        host_call()
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         for _ in range(args.e2e_steps):
-            h.grad_hess_raw(xh.numpy(), eh.numpy(), gh.numpy(), vh.numpy())
+            host_call()
         torch.cuda.synchronize()
         dt = (time.perf_counter() - t0) / args.e2e_steps
-        e2e = {"value": n_el_total / dt, "unit": UNIT, "h2d_bytes_per_step": int(8 * h.ndof),
-               "d2h_bytes_per_step": int(8 * (1 + h.ndof + h.nnz)), "ms_per_step": dt * 1e3, "steps": args.e2e_steps,
+        e2e = {"value": n_el_total / dt, "unit": UNIT, "h2d_bytes_per_step": 0 if linear else int(8 * h.ndof),
+               "d2h_bytes_per_step": int(8 * h.nnz) if linear else int(8 * (1 + h.ndof + h.nnz)), "ms_per_step": dt * 1e3, "steps": args.e2e_steps,
                "buffers": "pinned host"}
-        assert abs(float(eh[0]) - float(e_d.item())) <= 1e-9 * abs(float(e_d.item()))
+        if not linear:
+            assert abs(float(eh[0]) - float(e_d.item())) <= 1e-9 * abs(float(e_d.item()))
     else:
-        # multi-GPU: host buffers per rank, same call + exchange
+        # multi-GPU (and the implicit-Euler step): host buffers per rank, device step + copies
         xh = torch.from_numpy(x_loc).pin_memory()
         gh = torch.zeros(h.ndof, dtype=torch.float64).pin_memory()
         vh = torch.zeros(h.nnz, dtype=torch.float64).pin_memory()
@@ -457,7 +611,8 @@ def main():
         barrier()
         dt = (time.perf_counter() - t0) / args.e2e_steps
         tt = torch.tensor([dt], dtype=torch.float64, device=dev)
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         e2e = {"value": n_el_total / float(tt.item()), "unit": UNIT, "h2d_bytes_per_step": int(8 * h.ndof),
                "d2h_bytes_per_step": int(8 * (1 + h.ndof + h.nnz)), "ms_per_step": float(tt.item()) * 1e3,
                "steps": args.e2e_steps, "buffers": "pinned host, per rank"}
@@ -465,26 +620,22 @@ def main():
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
-        r = cpu_baseline_run(args.cpu_sample_n, args.p, 2, 1, threads)
-        cpu = {"value": r["value"], "unit": UNIT, "cores": threads, "kind": "port",
-               "sample": f"NeoHookean P{args.p} Kuhn cube n={args.cpu_sample_n} ({r['elements']} elements), 2 steady-state "
-                         f"steps of energy+gradient+Hessian, basis cache on; first call {r['first_call_seconds']:.2f}s excluded"}
+        n_sample = args.cpu_sample_n or cfg["cpu_n"]
+        r = cpu_baseline_run(cfg, n_sample, 2, 1, threads, use_cache=False)
+        cpu = {"value": r["value"], "unit": UNIT, "cores": threads, "kind": "port", "sample": cpu_sample_text(cfg, n_sample, r, False, 2)}
 
     if rank == 0:
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "metric": metric_name(cfg), "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"NeoHookean P{args.p} tets, Kuhn cube n={args.n}: {mesh.n_elements} elements, "
-                                   f"{mesh.n_bases * 3} dofs, fused energy+gradient+Hessian (pfa_grad_hess)",
-                       "material": "E=1e5 nu=0.3", "displacement": "0.05*h*U(-1,1) seed 42",
-                       "l2": "outputs (values[] %.2f GB per GPU) exceed the 126 MB L2, no flush needed" % (8 * h.nnz / 1e9),
-                       "parallelism": ((f"element partition x{world} (pfa_partition_create), owner-computes columns with ghost elements: no interface "
-                                        "exchange, NCCL all-reduce of the energy only") if owner_mode else
-                                       (f"element partition x{world}, interface exchange "
-                                        + ("under" if args.overlap else "after") + " the assembly, "
-                                        + ("step replayed from a CUDA graph" if graph is not None else "eager launches"))) if world > 1 else "single GPU",
-                       "nnz": int(h.nnz) if world == 1 else None},
+            "config": config_dict(cfg, mesh, h, world, None),
+            "parallelism": ((f"element partition x{world} (pfa_partition_create), owner-computes columns with ghost elements: no interface "
+                             "exchange, NCCL all-reduce of the energy only") if owner_mode else
+                            (f"element partition x{world}, interface exchange "
+                             + ("under" if args.overlap else "after") + " the assembly, "
+                             + ("step replayed from a CUDA graph" if graph is not None else "eager launches"))) if world > 1 else "single GPU",
+            "nnz": int(h.nnz) if world == 1 else None,
             "nnz_per_s": (h.nnz / (ms_step * 1e-3)) if world == 1 else None,
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
             "setup_seconds": h.setup_seconds(),

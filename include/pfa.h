@@ -190,6 +190,10 @@ extern "C"
 	/* Fused energy + gradient + Hessian of one Newton iteration (the benchmarked entry).
 	 * Any of energy / grad / values may be NULL to skip that output. */
 	int pfa_grad_hess(pfa_handle *h, const double *x, int project_to_psd, double *energy, double *grad, double *values);
+	/* The same with every output multiplied by `weight`: Form::value / first_derivative / second_derivative return
+	 * weight() * the unweighted quantity (solver/forms/Form.hpp:30-56); for implicit Euler the elastic form's weight is
+	 * dt^2 (time_integrator/ImplicitEuler.cpp:28-31, solver/SolveData.cpp:491). NeoHookean P1/P2 tets (fused in the kernels). */
+	int pfa_grad_hess_weighted(pfa_handle *h, const double *x, int project_to_psd, double weight, double *energy, double *grad, double *values);
 
 	/* ---- the step right after the assembly ---- */
 

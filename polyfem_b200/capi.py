@@ -26,7 +26,7 @@ _ip = ctypes.POINTER(ctypes.c_int32)
 EXPORTS = [
     "pfa_create", "pfa_destroy", "pfa_last_error", "pfa_sizes", "pfa_pattern", "pfa_block_pattern", "pfa_pattern_device",
     "pfa_set_materials", "pfa_energy", "pfa_energy_per_element", "pfa_gradient", "pfa_hessian",
-    "pfa_linear_stiffness", "pfa_grad_hess", "pfa_synchronize", "pfa_stream", "pfa_set_stream", "pfa_profile_enable",
+    "pfa_linear_stiffness", "pfa_grad_hess", "pfa_grad_hess_weighted", "pfa_synchronize", "pfa_stream", "pfa_set_stream", "pfa_profile_enable",
     "pfa_profile_read", "pfa_launch_count", "pfa_setup_seconds",
     "pfa_is_step_valid", "pfa_set_constrained_dofs", "pfa_reduced_sizes", "pfa_reduced_pattern", "pfa_reduced_pattern_device",
     "pfa_project_gradient", "pfa_project_hessian", "pfa_grad_hess_reduced", "pfa_grad_hess_part",
@@ -93,6 +93,7 @@ def lib():
     L.pfa_hessian.argtypes = [vp, vp, c_int, vp]
     L.pfa_linear_stiffness.argtypes = [vp, vp]
     L.pfa_grad_hess.argtypes = [vp, vp, c_int, vp, vp, vp]
+    L.pfa_grad_hess_weighted.argtypes = [vp, vp, c_int, ctypes.c_double, vp, vp, vp]
     L.pfa_is_step_valid.argtypes = [vp, vp, ctypes.POINTER(ctypes.c_int32), vp]
     L.pfa_set_constrained_dofs.argtypes = [vp, vp, i64]
     L.pfa_reduced_sizes.argtypes = [vp, ctypes.POINTER(i64), ctypes.POINTER(i64)]
@@ -302,6 +303,10 @@ class Handle:
     # ---- raw pointer entry (host numpy arrays or torch CUDA tensors, any may be None) ----
     def grad_hess_raw(self, x, energy=None, grad=None, values=None, project_to_psd=False):
         self._check(lib().pfa_grad_hess(self._h, _ptr(x), int(bool(project_to_psd)), _ptr(energy), _ptr(grad), _ptr(values)))
+
+    def grad_hess_weighted_raw(self, x, weight, energy=None, grad=None, values=None, project_to_psd=False):
+        """Every output times `weight` (Form::weight, e.g. dt^2 under implicit Euler)."""
+        self._check(lib().pfa_grad_hess_weighted(self._h, _ptr(x), int(bool(project_to_psd)), float(weight), _ptr(energy), _ptr(grad), _ptr(values)))
 
     # ---- InertiaForm on a Mass handle ----
     def symv(self, values, x):

@@ -886,6 +886,15 @@ extern "C"
 		return run_assemble(h, false, x, project_to_psd, energy, nullptr, grad, values);
 	}
 
+	int pfa_grad_hess_weighted(pfa_handle *h, const double *x, int project_to_psd, double weight, double *energy, double *grad, double *values)
+	{
+		if (!h)
+			return PFA_ERR_INVALID;
+		if (!energy && !grad && !values)
+			return fail(h, PFA_ERR_INVALID, "pfa_grad_hess_weighted: all outputs are NULL");
+		return run_assemble(h, false, x, project_to_psd, energy, nullptr, grad, values, weight);
+	}
+
 	int pfa_is_step_valid(pfa_handle *h, const double *x, int32_t *valid, double *energy)
 	{
 		if (!h || !valid)

@@ -1,12 +1,14 @@
 """BASELINE.json configs[2] at FULL size (NeoHookean P2, Kuhn cube n=69, 1 971 054 tets, 8.06 M dofs, 686 M nnz) on the GPU,
-checked through size-independent properties — the oracle would need hours at this size:
+checked through size-independent properties (the oracle comparison at configuration size is tests/test_zzz_gpu_config_size.py:
+cfg 1 and cfg 2 whole, cfg 3 at n = 30; at n = 69 the oracle mirrors the reference's memory design - a 7 GB slot map and one
+5.5 GB value buffer per thread - which is what rules it out here, not its run time of a few minutes):
 
 * the pattern size equals the closed form 9 (230 n^3 + 138 n^2 + 24 n + 1) (tests/test_oracle_properties.py pins it on the oracle);
 * energy > 0, every output finite;
 * translation invariance: the nodal forces sum to zero and H t = 0 for the three rigid translations t;
 * symmetry: a^T H^T b == a^T H b for random a, b (pfa_symv reads a CSC column as a row, i.e. multiplies by H^T);
 * the Hessian is the derivative of the gradient: (g(x + eps d) - g(x - eps d)) / (2 eps) == H d;
-* at x = 0 the gradient vanishes and the NeoHookean Hessian (row-lane kernel) equals the LinearElasticity stiffness
+* at x = 0 the gradient vanishes and the NeoHookean Hessian (owner-computes kernels) equals the LinearElasticity stiffness
   (reference-moment kernel) entry by entry: two independent kernels, same pattern, 1e-12 of the largest entry.
 
 Everything stays device-resident (torch tensors through the raw C-ABI entry points); this file sorts last on purpose."""
