@@ -141,6 +141,7 @@ namespace
 	}
 	const int kSmallRows = env_int("PFA_CL_SMALL_ROWS", 96);
 	const int kChunkSteps = env_int("PFA_CL_CHUNK_STEPS", 48);
+	const int kBucketElements = env_int("PFA_CL_BUCKET", 16384); // 7 MB of P2 records per bucket
 	constexpr int kRestBatchQuota = PFA_REST_BATCH_QUOTA; // pfa_grad_hess_part(PFA_PART_REST): warp batches per warp
 
 	void prof_begin(pfa_handle *h, const char *name, bool is_kernel = true)
@@ -631,7 +632,7 @@ extern "C"
 				{
 					// columns of at most kSmallRows strip rows form the first launch, the rest (P2 vertex nodes) the second;
 					// chunks of about kChunkSteps steps are handed out to the warps
-					const cl2::Schedule S = cl2::build_schedule(int(ngeo), m.n_loc, m.n_bases, conn_in, hp.adj_off.data(), hp.adj.data(), kSmallRows, kChunkSteps, d->owned_nodes);
+					const cl2::Schedule S = cl2::build_schedule(int(ngeo), m.n_loc, m.n_bases, conn_in, hp.adj_off.data(), hp.adj.data(), kSmallRows, kChunkSteps, d->owned_nodes, kBucketElements);
 					UP(h->cl.grp_info, S.grp_info.data(), S.grp_info.size(), int32_t);
 					UP(h->cl.grp_off, S.grp_off.data(), S.grp_off.size(), int32_t);
 					UP(h->cl.grp_rows, S.grp_rows.data(), S.grp_rows.size(), int32_t);
@@ -649,6 +650,7 @@ extern "C"
 					{
 						h->cl.n_chunks[c] = S.n_chunks[c];
 						h->cl.rows_max[c] = S.rows_max[c];
+						h->cl.n_steps[c] = S.n_steps[c];
 					}
 					h->cl.n_record_elements = int32_t(ngeo);
 					h->cl_partial = d->owned_nodes != nullptr;

@@ -419,7 +419,7 @@ namespace pfa
 #pragma unroll
 							for (int c = 0; c < 15; ++c)
 								if (r0 < lim[c])
-									dst[c][r0] = a.scale * v[c];
+									__stcs(dst[c] + r0, a.scale * v[c]); // written once, never read here: keep the records in L2 instead
 							__syncwarp();
 						}
 						if (L::TB_ALIAS)
@@ -503,6 +503,9 @@ namespace pfa
 				return err;
 			if ((err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max)) != cudaSuccess)
 				return err;
+			// The two strip classes are two launches, one after the other. (Running them side by side on two streams with the SMs
+			// shared 3 : 5 was measured slower on B200: 6.77 against 4.99 ms at cfg 3, profiles/clvar_r02m.jsonl.)
+			static const int cap = [] { const char *v = std::getenv("PFA_CL_WARPS_PER_SM"); return v ? std::atoi(v) : 0; }(); // experiments
 			int c0 = 0;
 			for (int c = 0; c < 2; ++c)
 			{
@@ -515,8 +518,6 @@ namespace pfa
 					int per_sm = 1;
 					if ((err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 32, smem)) != cudaSuccess)
 						return err;
-					// PFA_CL_WARPS_PER_SM (environment, experiments): cap on resident warps per SM
-					static const int cap = [] { const char *v = std::getenv("PFA_CL_WARPS_PER_SM"); return v ? std::atoi(v) : 0; }();
 					if (cap > 0)
 						per_sm = std::min(per_sm, cap);
 					const int grid = std::max(1, std::min(nc, sm_count * std::max(per_sm, 1)));

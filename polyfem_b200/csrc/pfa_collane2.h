@@ -227,6 +227,7 @@ namespace pfa
 			int n_groups[2] = {0, 0};
 			int rows_max[2] = {0, 0};
 			int n_chunks[2] = {0, 0};
+			int64_t n_steps[2] = {0, 0};
 			int64_t total_steps = 0;
 			int64_t busy = 0;                // (element, node) incidences = non-idle (step, triple) pairs
 			std::vector<int32_t> grp_info;  // [G][kNodes][4]: node (-1 = unused slot), 9*adj_off[node], 3*deg(node), 0
@@ -242,7 +243,7 @@ namespace pfa
 		// owned: optional per-node flag (multi-GPU: only the columns of owned nodes are produced); n_el counts every element
 		// whose record exists on this device (own + ghost elements)
 		inline Schedule build_schedule(int n_el, int NL, int n_bases, const int32_t *conn, const int32_t *adj_off, const int32_t *adj, int small_rows,
-									   int chunk_steps, const uint8_t *owned = nullptr)
+									   int chunk_steps, const uint8_t *owned = nullptr, int bucket_elements = 1 << 30)
 		{
 			Schedule S;
 			std::vector<int32_t> cnt(size_t(n_bases) + 1, 0);
@@ -260,8 +261,13 @@ namespace pfa
 			for (int b = 0; b < n_bases; ++b)
 				if (n_inc(b) > 0 && (owned == nullptr || owned[b]))
 					order[rows_of(b) <= small_rows ? 0 : 1].push_back(b);
+			// (the incidence lists are in element order: the first entry is the node's first incident element)
+			auto bucket = [&](int b) { return (inc_e[size_t(cnt[size_t(b)])] / NL) / std::max(bucket_elements, 1); };
 			for (int c = 0; c < 2; ++c)
-				std::stable_sort(order[c].begin(), order[c].end(), [&](int a, int b) { return n_inc(a) > n_inc(b); });
+				std::stable_sort(order[c].begin(), order[c].end(), [&](int a, int b) {
+					const int ba = bucket(a), bb = bucket(b);
+					return ba != bb ? ba < bb : n_inc(a) > n_inc(b);
+				});
 			S.grp_off.push_back(0);
 			S.chunk_off.push_back(0);
 			std::vector<uint8_t> seen;
@@ -314,6 +320,7 @@ namespace pfa
 						}
 					}
 					S.total_steps += steps;
+					S.n_steps[c] += steps;
 					S.grp_off.push_back(int32_t(S.total_steps));
 					S.grp_rows.push_back(rows);
 					S.rows_max[c] = std::max(S.rows_max[c], rows);

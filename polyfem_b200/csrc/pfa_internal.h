@@ -95,6 +95,7 @@ namespace pfa
 		double *block_energy = nullptr;     // [ceil(n_record_elements / 128)] partial energy sums of the records kernel
 		int *counters = nullptr;            // [2] chunk hand-out of the two launches
 		const double *rg_padded = nullptr;  // [n_loc][n_qp][4] own-node reference gradients, padded rows
+		int64_t n_steps[2] = {0, 0}; // steps of the two classes (their share of the work)
 	};
 	bool column_lane2_applies(int material, int n_loc, int n_qp);
 	size_t column_lane2_record_doubles(int n_qp);

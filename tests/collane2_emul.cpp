@@ -25,6 +25,7 @@ namespace
 				const double *qw, const double *ref_grads, const double *lam, const double *mu, int mstride, const double *x, int small_rows,
 				int chunk_steps, const uint8_t *owned, double scale, double *energy, double *grad, double *values, int64_t *stats)
 	{
+		const int bucket_elements = chunk_steps % 7 == 3 ? 5 : (1 << 30); // some test cases exercise the spatial buckets of the schedule
 		constexpr int RECD = Rec<NQ>::D;
 		const HostTable G{ref_grads};
 		// (A) records
@@ -47,7 +48,7 @@ namespace
 				for (int c = 0; c < 3; ++c)
 					rgp[(size_t(i) * NQ + q) * 4 + c] = ref_grads[(size_t(q) * NL + i) * 3 + c];
 		// (B) column lanes
-		const Schedule S = build_schedule(n_el, NL, n_bases, conn, adj_off, adj, small_rows, chunk_steps, owned);
+		const Schedule S = build_schedule(n_el, NL, n_bases, conn, adj_off, adj, small_rows, chunk_steps, owned, bucket_elements);
 		const int n_groups = S.n_groups[0] + S.n_groups[1];
 		if (int(S.chunk_off.size()) != S.n_chunks[0] + S.n_chunks[1] + 1 || S.chunk_off.back() != n_groups)
 			return -6;

@@ -161,7 +161,11 @@ def test_scale_chunks_and_per_quadrature_point_materials(emul, oracle):
     # the oracle takes one (lambda, mu) per element: replicate them over the quadrature points for the [element][qp] layout
     lam_e, mu_e = l0 * (1.0 + 0.3 * rng.random(ne)), m0 * (1.0 + 0.3 * rng.random(ne))
     lam, mu = np.repeat(lam_e[:, None], nq, axis=1), np.repeat(mu_e[:, None], nq, axis=1)
+    # (chunk_steps = 10 also switches the emulation's schedule to spatial buckets of 5 elements: same sums per entry in another
+    # node order - the values agree to rounding, not bit for bit, with the unbucketed order)
+    _, e_b, g_b, v_b, _ = run_emulation(emul, oracle, mesh, x, 96, 1, chunk_steps=10, scale=0.25, lam_mu=(lam, mu))
     prob, e, g, v, _ = run_emulation(emul, oracle, mesh, x, 96, 1, chunk_steps=1, scale=0.25, lam_mu=(lam, mu))
+    assert np.allclose(v_b, v, rtol=1e-13, atol=1e-13 * np.abs(v).max()) and np.allclose(g_b, g, rtol=1e-13, atol=1e-13 * np.abs(g).max())
     _, e2, g2, v2, st = run_emulation(emul, oracle, mesh, x, 96, 1, chunk_steps=10 ** 6, scale=0.25, lam_mu=(lam, mu))
     assert e2 == e and np.array_equal(g2, g) and np.array_equal(v2, v) and st[6] + st[7] <= 2
     from polyfem_b200 import tables as T
