@@ -2,6 +2,8 @@
 // error translation. No CPU fallback: every compute entry point runs the CUDA kernels or
 // fails with PFA_ERR_NO_DEVICE / PFA_ERR_CUDA.
 #include "pfa_collane2.h"
+
+#include <nvtx3/nvToolsExt.h> // header-only NVTX v3: ranges show up in Nsight Systems / ncu --nvtx (SURVEY.md §5 tracing)
 #include "pfa_internal.h"
 
 #include <chrono>
@@ -144,6 +146,15 @@ namespace
 	const int kBucketElements = env_int("PFA_CL_BUCKET", 16384); // 7 MB of P2 records per bucket
 	constexpr int kRestBatchQuota = PFA_REST_BATCH_QUOTA; // pfa_grad_hess_part(PFA_PART_REST): warp batches per warp
 
+	// NVTX range for the phases of a C-ABI call (H2D staging, zero fill, kernels, D2H); a no-op without a profiler attached
+	struct NvtxRange
+	{
+		explicit NvtxRange(const char *name) { nvtxRangePushA(name); }
+		~NvtxRange() { nvtxRangePop(); }
+		NvtxRange(const NvtxRange &) = delete;
+		NvtxRange &operator=(const NvtxRange &) = delete;
+	};
+
 	void prof_begin(pfa_handle *h, const char *name, bool is_kernel = true)
 	{
 		if (is_kernel)
@@ -192,6 +203,7 @@ namespace
 			*x_dev = x;
 			return PFA_OK;
 		}
+		NvtxRange range("pfa: H2D displacement");
 		int rc = ensure_staging(h, &h->s_x, size_t(h->ndof));
 		if (rc != PFA_OK)
 			return rc;
@@ -232,7 +244,10 @@ namespace
 	int finish_output(pfa_handle *h, const OutBuf &o)
 	{
 		if (o.to_host)
+		{
+			NvtxRange range("pfa: D2H result");
 			PFA_CUDA(h, cudaMemcpyAsync(o.user, o.dev, o.count * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+		}
 		return PFA_OK;
 	}
 
@@ -240,6 +255,7 @@ namespace
 	int run_assemble(pfa_handle *h, bool linear, const double *x, int project_to_psd,
 					 double *energy, double *energy_per_el, double *grad, double *values, double scale = 1.0, bool reduced = false, int part = PFA_PART_ALL)
 	{
+		NvtxRange call_range(linear ? "pfa: linear assembly" : "pfa: energy/gradient/Hessian assembly");
 		h->err.clear();
 		PFA_CUDA(h, cudaSetDevice(h->device));
 		if (reduced && (!h->has_constraints || h->d_entry_red == nullptr))
@@ -317,6 +333,7 @@ namespace
 		// Assembler.cpp:586-587, 666-667)
 		if ((a.energy || a.grad || a.values) && part != PFA_PART_REST)
 		{
+			NvtxRange range("pfa: zero fill");
 			prof_begin(h, "zero_fill(cudaMemsetAsync)", false);
 			if (a.energy)
 				PFA_CUDA(h, cudaMemsetAsync(a.energy, 0, sizeof(double), h->stream));
@@ -333,6 +350,7 @@ namespace
 		if (a.e_end <= a.e_begin)
 			return PFA_OK; // empty part: outputs are cleared (or left), nothing to launch
 		const char *kname = use_cl ? "assemble_nh_column_lane(records+columns)" : "assemble";
+		NvtxRange kernel_range(use_cl ? "pfa: owner-computes kernels (records + columns)" : "pfa: assembly kernel");
 		prof_begin(h, kname);
 		int cl_launches = 0;
 		cudaError_t ce = use_cl ? launch_column_lane2(dm, a, h->cl, h->sm_count, h->stream, &cl_launches) : launch_assemble(dm, a, linear, h->sm_count, h->stream, &kname);
@@ -355,6 +373,7 @@ extern "C"
 {
 	int pfa_create(const pfa_mesh_desc *d, pfa_handle **out)
 	{
+		NvtxRange create_range("pfa_create: pattern, schedule, geometry");
 		g_create_error.clear();
 		if (!d || !out)
 			return fail(nullptr, PFA_ERR_INVALID, "pfa_create: NULL argument");
