@@ -53,9 +53,13 @@ extern "C"
 		PFA_NEOHOOKEAN = 0,        /* assembler/NeoHookeanElasticity.cpp, name() == "NeoHookean" */
 		PFA_LINEAR_ELASTICITY = 1, /* assembler/LinearElasticity.cpp,    name() == "LinearElasticity" */
 		PFA_LAPLACIAN = 2,         /* assembler/Laplacian.cpp,           name() == "Laplacian" */
-		PFA_MASS = 3               /* assembler/Mass.cpp (LinearAssembler, size 3): rho phi_i phi_j on the block diagonal; the
+		PFA_MASS = 3,              /* assembler/Mass.cpp (LinearAssembler, size 3): rho phi_i phi_j on the block diagonal; the
 		                            * mass matrix of InertiaForm. Needs ref_vals + density; quadrature is the
 		                            * mass rule of order 2p (AssemblerUtils.cpp:204-211). */
+		PFA_SAINT_VENANT = 4       /* assembler/SaintVenantElasticity.cpp, name() == "SaintVenant", with the isotropic elasticity
+		                            * tensor of (lambda, mu) (MatParams.cpp:211-253): an ElasticityNLAssembler whose energy is
+		                            * differentiated by autodiff in the reference; here the closed forms
+		                            * P = F S, S = 2 mu E + lambda tr(E) I and its tangent. Any order P1..P4 (generic kernel). */
 	} pfa_material;
 
 	/* What the shim reads out of std::vector<basis::ElementBases> bases / gbases and the

@@ -264,8 +264,8 @@ namespace
 	{
 		oracle_desc d;
 		int size = 3; // Assembler::size()
-		std::vector<int32_t> conn, lattice;
-		std::vector<double> vertices, qpts, qw, ref_grads, lambda, mu, ref_vals, density;
+		std::vector<int32_t> conn, lattice, geom_lattice;
+		std::vector<double> vertices, qpts, qw, ref_grads, lambda, mu, ref_vals, density, geom_nodes;
 		// AssemblyValsCache (AssemblyValsCache.cpp:11-67)
 		std::vector<ElementAssemblyValues> cache;
 
@@ -328,17 +328,22 @@ namespace
 					vals.val[size_t(j) * n_qp + q] = pb.ref_vals[size_t(q) * n_loc + j];
 		}
 
-		// finalize3d (ElementAssemblyValues.cpp:65-104): geometric bases are P1, gradients
-		// (-1,-1,-1), e_x, e_y, e_z; tmp.row(c) += dN_j/dxi_c * node_j
+		// finalize3d (ElementAssemblyValues.cpp:65-104): tmp.row(c) += dN_j/dxi_c * node_j over the geometric bases; P1
+		// geometry (gradients (-1,-1,-1), e_x, e_y, e_z) unless isoparametric nodes were given
 		static const double gg[4][3] = {{-1, -1, -1}, {1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
-		const double *vx = &pb.vertices[size_t(e) * 12];
+		const bool iso = pb.d.geom_order > 1 && !pb.geom_nodes.empty();
+		const int ngl = iso ? pb.d.n_geom_loc : 4;
+		const double *vx = iso ? &pb.geom_nodes[size_t(e) * ngl * 3] : &pb.vertices[size_t(e) * 12];
+		std::vector<double> ggrad(iso ? size_t(ngl) * 3 : 0);
 		for (int k = 0; k < n_qp; ++k)
 		{
 			double tmp[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-			for (int j = 0; j < 4; ++j)
+			if (iso)
+				lagrange_grads(pb.d.geom_order, ngl, pb.geom_lattice.data(), &pb.qpts[size_t(k) * 3], ggrad.data());
+			for (int j = 0; j < ngl; ++j)
 				for (int c = 0; c < 3; ++c)
 					for (int d = 0; d < 3; ++d)
-						tmp[c * 3 + d] += gg[j][c] * vx[j * 3 + d];
+						tmp[c * 3 + d] += (iso ? ggrad[size_t(j) * 3 + c] : gg[j][c]) * vx[j * 3 + d];
 			vals.det[k] = det3(tmp);
 			double inv[9];
 			inverse3(tmp, inv);
@@ -723,6 +728,49 @@ namespace
 			energy = energy + val * T(data.da[p]);
 		}
 		return energy;
+	}
+
+	// SaintVenantElasticity.cpp:9-20, 219-266 compute_energy_aux<T> with the isotropic elasticity tensor of
+	// MatParams.cpp:211-253 (set_from_lambda_mu: C = lambda 1 (x) 1 + 2 mu I_sym in Voigt form with engineering shear):
+	// strain = (G^T G + G + G^T) / 2, stress = C : strain, energy = 1/2 sum_p (stress * strain).trace() da_p.
+	// Gradient and Hessian are the forward-mode derivatives of this function, as in the reference
+	// (gradient_from_energy / hessian_from_energy, SaintVenantElasticity.cpp:88-129).
+	template <typename T>
+	T saint_venant_energy(const NLData &data)
+	{
+		std::vector<T> local_disp;
+		get_local_disp<T>(data, 3, local_disp);
+		T energy = T(0.0);
+		T G[9];
+		const double C00 = 2.0 * data.mu + data.lambda, C01 = data.lambda, C33 = data.mu;
+		for (int p = 0; p < data.vals.n_qp; ++p)
+		{
+			compute_disp_grad_at_quad<T>(data, local_disp, p, G);
+			T strain[9]; // strain_from_disp_grad
+			for (int r = 0; r < 3; ++r)
+				for (int c = 0; c < 3; ++c)
+				{
+					T gtg = T(0.0);
+					for (int k = 0; k < 3; ++k)
+						gtg = gtg + G[k * 3 + r] * G[k * 3 + c];
+					strain[r * 3 + c] = (gtg + G[r * 3 + c] + G[c * 3 + r]) * T(0.5);
+				}
+			const T eps[6] = {strain[0], strain[4], strain[8], T(2.0) * strain[5], T(2.0) * strain[2], T(2.0) * strain[1]};
+			T sig[6]; // stress(elasticity_tensor, eps, j)
+			sig[0] = T(C00) * eps[0] + T(C01) * eps[1] + T(C01) * eps[2];
+			sig[1] = T(C01) * eps[0] + T(C00) * eps[1] + T(C01) * eps[2];
+			sig[2] = T(C01) * eps[0] + T(C01) * eps[1] + T(C00) * eps[2];
+			sig[3] = T(C33) * eps[3];
+			sig[4] = T(C33) * eps[4];
+			sig[5] = T(C33) * eps[5];
+			const T st[9] = {sig[0], sig[5], sig[4], sig[5], sig[1], sig[3], sig[4], sig[3], sig[2]};
+			T tr = T(0.0); // (stress_tensor * strain).trace()
+			for (int r = 0; r < 3; ++r)
+				for (int c = 0; c < 3; ++c)
+					tr = tr + st[r * 3 + c] * strain[c * 3 + r];
+			energy = energy + tr * T(data.da[p]);
+		}
+		return energy * T(0.5);
 	}
 
 	// =======================================================================================
@@ -1134,6 +1182,8 @@ namespace
 	{
 		if (pb.d.material == ORACLE_NEOHOOKEAN)
 			return neohookean_energy(data);
+		if (pb.d.material == ORACLE_SAINT_VENANT)
+			return saint_venant_energy<double>(data);
 		return linear_elasticity_energy<double>(data);
 	}
 	void local_gradient(const Problem &pb, const NLData &data, std::vector<double> &g)
@@ -1144,7 +1194,7 @@ namespace
 			return;
 		}
 		// utils/ElasticityUtils.cpp:81-... gradient_from_energy: autodiff gradient
-		const D1 e = linear_elasticity_energy<D1>(data);
+		const D1 e = pb.d.material == ORACLE_SAINT_VENANT ? saint_venant_energy<D1>(data) : linear_elasticity_energy<D1>(data);
 		g = e.g;
 	}
 	void local_hessian(const Problem &pb, const NLData &data, std::vector<double> &h)
@@ -1154,7 +1204,7 @@ namespace
 			neohookean_hessian(data, h);
 			return;
 		}
-		const D2 e = linear_elasticity_energy<D2>(data);
+		const D2 e = pb.d.material == ORACLE_SAINT_VENANT ? saint_venant_energy<D2>(data) : linear_elasticity_energy<D2>(data);
 		h = e.h;
 	}
 } // namespace
@@ -1198,6 +1248,11 @@ extern "C"
 			pb.ref_vals.assign(desc->ref_vals, desc->ref_vals + nq * nl);
 		if (desc->density)
 			pb.density.assign(desc->density, desc->density + ne);
+		if (desc->geom_order > 1 && desc->geom_nodes && desc->geom_lattice)
+		{
+			pb.geom_nodes.assign(desc->geom_nodes, desc->geom_nodes + ne * size_t(desc->n_geom_loc) * 3);
+			pb.geom_lattice.assign(desc->geom_lattice, desc->geom_lattice + size_t(desc->n_geom_loc) * 3);
+		}
 		if (pb.density.empty())
 			pb.density.assign(ne, 1.0);
 		if (pb.lambda.empty())

@@ -46,7 +46,8 @@ extern "C"
 		ORACLE_NEOHOOKEAN = 0,
 		ORACLE_LINEAR_ELASTICITY = 1,
 		ORACLE_LAPLACIAN = 2,
-		ORACLE_MASS = 3 /* assembler/Mass.cpp: LinearAssembler with rho * phi_i * phi_j on the block diagonal */
+		ORACLE_MASS = 3, /* assembler/Mass.cpp: LinearAssembler with rho * phi_i * phi_j on the block diagonal */
+		ORACLE_SAINT_VENANT = 4 /* assembler/SaintVenantElasticity.cpp with the isotropic tensor of (lambda, mu) */
 	};
 
 	typedef struct
@@ -69,6 +70,13 @@ extern "C"
 		int32_t n_threads;           /* stand-in for TBB's thread count */
 		const double *ref_vals;      /* [n_qp][n_loc] basis values basis_values[j].val(q) (ORACLE_MASS only) */
 		const double *density;       /* [n_elements] rho (ORACLE_MASS only) */
+		/* isoparametric geometry (optional): geometric bases of order geom_order > 1 with n_geom_loc nodes per element,
+		 * geom_nodes[n_elements][n_geom_loc][3] (gbases[e].bases[j].global()[0].node) and their lattice coordinates;
+		 * finalize3d sums over the geometric bases (ElementAssemblyValues.cpp:79-93). 0 / NULL: P1 geometry from `vertices`. */
+		int32_t geom_order;
+		int32_t n_geom_loc;
+		const int32_t *geom_lattice; /* [n_geom_loc][3] */
+		const double *geom_nodes;
 	} oracle_desc;
 
 	typedef struct oracle_problem oracle_problem;

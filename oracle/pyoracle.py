@@ -15,7 +15,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = None
 
 NEOHOOKEAN, LINEAR_ELASTICITY, LAPLACIAN, MASS = 0, 1, 2, 3
-MATERIAL_IDS = {"NeoHookean": NEOHOOKEAN, "LinearElasticity": LINEAR_ELASTICITY, "Laplacian": LAPLACIAN, "Mass": MASS}
+SAINT_VENANT = 4
+MATERIAL_IDS = {"NeoHookean": NEOHOOKEAN, "LinearElasticity": LINEAR_ELASTICITY, "Laplacian": LAPLACIAN, "Mass": MASS, "SaintVenant": SAINT_VENANT}
 
 _dp = ctypes.POINTER(ctypes.c_double)
 _ip = ctypes.POINTER(ctypes.c_int32)
@@ -29,6 +30,7 @@ class _Desc(ctypes.Structure):
         ("quad_weights", _dp), ("ref_grads", _dp), ("lambda_", _dp), ("mu", _dp),
         ("use_cache", ctypes.c_int32), ("n_threads", ctypes.c_int32),
         ("ref_vals", _dp), ("density", _dp),
+        ("geom_order", ctypes.c_int32), ("n_geom_loc", ctypes.c_int32), ("geom_lattice", _ip), ("geom_nodes", _dp),
     ]
 
 
@@ -122,7 +124,9 @@ class OracleProblem:
 
     def __init__(self, material, conn, vertices, n_bases, quad_points, quad_weights, ref_grads,
                  lam=None, mu=None, basis_order=1, node_lattice=None, use_cache=True, n_threads=1,
-                 ref_vals=None, density=None):
+                 ref_vals=None, density=None, geom_order=0, geom_lattice=None, geom_nodes=None):
+        """geom_order > 1 with geom_nodes [n_elements, n_geom_loc, 3] and geom_lattice [n_geom_loc, 3]: isoparametric geometry
+        (curved elements); otherwise P1 geometry from `vertices`."""
         L = lib()
         self.material = MATERIAL_IDS[material] if isinstance(material, str) else int(material)
         self.conn = np.ascontiguousarray(conn, dtype=np.int32)
@@ -149,6 +153,12 @@ class OracleProblem:
             assert self.rv.shape == (self.qw.size, nl)
             self.rho = np.ascontiguousarray(np.broadcast_to(1.0 if density is None else density, (ne,)), dtype=np.float64)
             d.ref_vals, d.density = _d(self.rv), _d(self.rho)
+        if geom_order and geom_order > 1:
+            self.gnodes = np.ascontiguousarray(geom_nodes, dtype=np.float64)
+            self.glat = np.ascontiguousarray(geom_lattice, dtype=np.int32)
+            assert self.gnodes.shape == (ne, self.glat.shape[0], 3) and quad_points is not None
+            d.geom_order, d.n_geom_loc = int(geom_order), int(self.glat.shape[0])
+            d.geom_lattice, d.geom_nodes = _i(self.glat), _d(self.gnodes)
         self._h = L.oracle_create(ctypes.byref(d))
         self.size = L.oracle_size(self._h)
         self.ndof = self.n_bases * self.size

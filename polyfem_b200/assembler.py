@@ -281,6 +281,12 @@ class NeoHookeanElasticity(NLAssembler):
     _material = "NeoHookean"
 
 
+class SaintVenantElasticity(NLAssembler):
+    """assembler/SaintVenantElasticity.{hpp,cpp} with the isotropic elasticity tensor of (E, nu) / (lambda, mu)
+    (MatParams.cpp:211-276); name() == "SaintVenant"."""
+    _material = "SaintVenant"
+
+
 class LinearElasticity(NLAssembler, LinearAssembler):
     """assembler/LinearElasticity.{hpp,cpp}: linear `assemble` plus the NL energy / gradient /
     Hessian used when a linear material sits inside a nonlinear solve."""
@@ -298,7 +304,8 @@ class Laplacian(LinearAssembler):
 
 def make_assembler(formulation: str, device: int = 0) -> Assembler:
     """AssemblerUtils::make_assembler (AssemblerUtils.cpp:55-122) for the hot-path names."""
-    table = {"NeoHookean": NeoHookeanElasticity, "LinearElasticity": LinearElasticity, "Laplacian": Laplacian, "Mass": Mass}
+    table = {"NeoHookean": NeoHookeanElasticity, "LinearElasticity": LinearElasticity, "Laplacian": Laplacian, "Mass": Mass,
+             "SaintVenant": SaintVenantElasticity}
     if formulation not in table:
         log_and_throw_error(f"Unsupported assembler on the B200 path: {formulation}")
     return table[formulation](device)

@@ -16,8 +16,8 @@ LIB_PATH = os.environ.get("PFA_LIB", os.path.join(_HERE, "libpfa.so"))  # PFA_LI
 
 PFA_OK = 0
 PFA_ERR_INVALID, PFA_ERR_UNSUPPORTED, PFA_ERR_CUDA, PFA_ERR_NOMEM, PFA_ERR_NO_DEVICE = -1, -2, -3, -4, -5
-NEOHOOKEAN, LINEAR_ELASTICITY, LAPLACIAN, MASS = 0, 1, 2, 3
-MATERIAL_IDS = {"NeoHookean": NEOHOOKEAN, "LinearElasticity": LINEAR_ELASTICITY, "Laplacian": LAPLACIAN, "Mass": MASS}
+NEOHOOKEAN, LINEAR_ELASTICITY, LAPLACIAN, MASS, SAINT_VENANT = 0, 1, 2, 3, 4
+MATERIAL_IDS = {"NeoHookean": NEOHOOKEAN, "LinearElasticity": LINEAR_ELASTICITY, "Laplacian": LAPLACIAN, "Mass": MASS, "SaintVenant": SAINT_VENANT}
 
 _dp = ctypes.POINTER(ctypes.c_double)
 _ip = ctypes.POINTER(ctypes.c_int32)

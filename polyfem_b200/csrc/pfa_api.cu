@@ -272,8 +272,8 @@ namespace
 			return fail(h, PFA_ERR_UNSUPPORTED, "a Form weight other than 1 is fused for NeoHookean P1/P2 tets only");
 		if ((h->dm.material == PFA_LAPLACIAN || h->dm.material == PFA_MASS) && !linear)
 			return fail(h, PFA_ERR_UNSUPPORTED, "Laplacian and Mass are LinearAssemblers: only pfa_linear_stiffness applies");
-		if (h->dm.material == PFA_NEOHOOKEAN && linear)
-			return fail(h, PFA_ERR_UNSUPPORTED, "NeoHookean is an NLAssembler: pfa_linear_stiffness does not apply");
+		if ((h->dm.material == PFA_NEOHOOKEAN || h->dm.material == PFA_SAINT_VENANT) && linear)
+			return fail(h, PFA_ERR_UNSUPPORTED, "NeoHookean / SaintVenant are NLAssemblers: pfa_linear_stiffness does not apply");
 
 		AssembleArgs a;
 		int rc;
@@ -380,7 +380,7 @@ extern "C"
 		*out = nullptr;
 		if (d->struct_size != int32_t(sizeof(pfa_mesh_desc)))
 			return fail(nullptr, PFA_ERR_INVALID, "pfa_create: struct_size does not match this library's pfa_mesh_desc");
-		if (d->material < PFA_NEOHOOKEAN || d->material > PFA_MASS)
+		if (d->material < PFA_NEOHOOKEAN || d->material > PFA_SAINT_VENANT)
 			return fail(nullptr, PFA_ERR_INVALID, "pfa_create: unknown material");
 		if (d->n_elements <= 0 || d->n_loc <= 0 || d->n_bases <= 0 || d->n_qp <= 0 || d->n_ghost_elements < 0)
 			return fail(nullptr, PFA_ERR_INVALID, "pfa_create: n_elements, n_loc, n_bases and n_qp must be positive");

@@ -173,7 +173,9 @@ namespace pfa
 			int U, D, A, Q, J, DA, I; // offsets in doubles (I: start of the int region, in doubles)
 			int total;                // doubles per warp
 		};
-		constexpr int kQRec = 30; // per-qp record: C[9] | P*da[9] | c2*da*F[9] | c1*da | mu*da | lambda*da
+		// per-qp record: C[9] | P*da[9] | c2*da*F[9] | c1*da | mu*da | lambda*da | (SaintVenant) mu*da*F F^T [6]
+		// SaintVenant uses the slots as: F[9] | P*da[9] | S*da[9] | - | mu*da | lambda*da | mu*da*F F^T (00 01 02 11 12 22)
+		constexpr int kQRec = 36;
 
 		__host__ __device__ inline WarpLayout warp_layout(int n_loc, int n_qp)
 		{
@@ -316,6 +318,39 @@ namespace pfa
 							rec[27] = (mu + lam * (1.0 - lJ)) * invJ * invJ * da; // c1 * da
 							e_loc += (0.5 * mu * (sq - 3.0 - 2.0 * lJ) + 0.5 * lam * lJ * lJ) * da;
 						}
+						else if (MAT == PFA_SAINT_VENANT)
+						{
+							// SaintVenantElasticity.cpp:219-266 in closed form: E = (F^T F - I) / 2, S = 2 mu E + lambda tr(E) I, P = F S,
+							// psi = mu E:E + lambda/2 tr(E)^2
+							F[0] += 1.0;
+							F[4] += 1.0;
+							F[8] += 1.0;
+							double E[9], S[9], trE = 0.0, EE = 0.0;
+							for (int r = 0; r < 3; ++r)
+								for (int c = 0; c < 3; ++c)
+									E[r * 3 + c] = 0.5 * (F[0 + r] * F[0 + c] + F[3 + r] * F[3 + c] + F[6 + r] * F[6 + c] - (r == c ? 1.0 : 0.0));
+							trE = E[0] + E[4] + E[8];
+							for (int k = 0; k < 9; ++k)
+							{
+								EE += E[k] * E[k];
+								S[k] = 2.0 * mu * E[k];
+							}
+							S[0] += lam * trE;
+							S[4] += lam * trE;
+							S[8] += lam * trE;
+							for (int r = 0; r < 3; ++r)
+								for (int c = 0; c < 3; ++c)
+								{
+									rec[r * 3 + c] = F[r * 3 + c];
+									rec[9 + r * 3 + c] = (F[r * 3 + 0] * S[0 + c] + F[r * 3 + 1] * S[3 + c] + F[r * 3 + 2] * S[6 + c]) * da;
+									rec[18 + r * 3 + c] = S[r * 3 + c] * da;
+								}
+							int k6 = 0;
+							for (int r = 0; r < 3; ++r)
+								for (int c = r; c < 3; ++c)
+									rec[30 + k6++] = mu * da * (F[r * 3 + 0] * F[c * 3 + 0] + F[r * 3 + 1] * F[c * 3 + 1] + F[r * 3 + 2] * F[c * 3 + 2]);
+							e_loc += (mu * EE + 0.5 * lam * trE * trE) * da;
+						}
 						else // LinearElasticity: F holds grad u
 						{
 							const double tr = F[0] + F[4] + F[8];
@@ -361,8 +396,9 @@ namespace pfa
 						atomicAdd(a.grad + size_t(sG[i]) * 3 + c, g);
 					}
 				}
-				if (want_h && MAT == PFA_NEOHOOKEAN && !LINEAR)
+				if (want_h && (MAT == PFA_NEOHOOKEAN || MAT == PFA_SAINT_VENANT) && !LINEAR)
 				{
+					// A_i = C D_i (NeoHookean: C = cof F) or F D_i (SaintVenant: the first record slot holds F)
 					for (int t = lane; t < n_qp * n_loc; t += 32)
 					{
 						const int q = t / n_loc;
@@ -432,6 +468,34 @@ namespace pfa
 							blk[5] += W0;
 							blk[6] += W1;
 							blk[7] -= W0;
+						}
+						else if (MAT == PFA_SAINT_VENANT && !LINEAR)
+						{
+							// H[(i,a),(j,b)] = sum_q [ (D_i . S D_j) delta_ab + mu (F D_j)_a (F D_i)_b + lambda (F D_i)_a (F D_j)_b
+							//                          + mu (F F^T)_ab (D_i . D_j) ] da     (tangent of P = F S(E))
+							for (int q = 0; q < n_qp; ++q)
+							{
+								const double *rec = sQ + q * kQRec;
+								const double *Di = sD + (q * n_loc + i) * 3, *Dj = sD + (q * n_loc + j) * 3;
+								const double *Ai = sA + (q * n_loc + i) * 3, *Aj = sA + (q * n_loc + j) * 3;
+								const double *S = rec + 18, *B = rec + 30;
+								const double mu = rec[28], lam = rec[29];
+								const double dsd = Di[0] * (S[0] * Dj[0] + S[1] * Dj[1] + S[2] * Dj[2]) + Di[1] * (S[3] * Dj[0] + S[4] * Dj[1] + S[5] * Dj[2])
+												   + Di[2] * (S[6] * Dj[0] + S[7] * Dj[1] + S[8] * Dj[2]);
+								const double dot = Di[0] * Dj[0] + Di[1] * Dj[1] + Di[2] * Dj[2];
+								for (int r = 0; r < 3; ++r)
+									for (int c = 0; c < 3; ++c)
+										blk[r * 3 + c] += mu * (Aj[r] * Ai[c]) + lam * (Ai[r] * Aj[c]);
+								blk[0] += dsd + B[0] * dot;
+								blk[1] += B[1] * dot;
+								blk[2] += B[2] * dot;
+								blk[3] += B[1] * dot;
+								blk[4] += dsd + B[3] * dot;
+								blk[5] += B[4] * dot;
+								blk[6] += B[2] * dot;
+								blk[7] += B[4] * dot;
+								blk[8] += dsd + B[5] * dot;
+							}
 						}
 						else // LinearElasticity stiffness block (LinearElasticity.cpp:40-60)
 						{
@@ -1917,6 +1981,12 @@ namespace pfa
 				return launch_rowlane<4, 1, 8, 2>(m, a, sm_count, st);
 			}
 			return launch_generic<PFA_NEOHOOKEAN, false>(m, a, sm_count, st);
+		case PFA_SAINT_VENANT:
+			if (linear || a.project_to_psd)
+				return cudaErrorNotSupported;
+			if (kernel_name)
+				*kernel_name = "assemble_generic_kernel<SaintVenant>";
+			return launch_generic<PFA_SAINT_VENANT, false>(m, a, sm_count, st);
 		case PFA_LINEAR_ELASTICITY:
 			if (linear && affine_linear_applies(m) && a.values != nullptr)
 			{
