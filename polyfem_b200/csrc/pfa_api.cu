@@ -262,12 +262,14 @@ namespace
 			return fail(h, h->has_constraints ? PFA_ERR_UNSUPPORTED : PFA_ERR_INVALID,
 						h->has_constraints ? "the fused Dirichlet-reduced assembly exists for NeoHookean P1/P2 tets only (use pfa_project_*)"
 										   : "call pfa_set_constrained_dofs first");
-		if (project_to_psd && !(values != nullptr && rowlane_applies(h->dm.material, h->dm.n_loc, h->dm.n_qp)))
-		{
-			if (values != nullptr)
-				return fail(h, PFA_ERR_UNSUPPORTED, "project_to_psd is implemented for NeoHookean P1/P2 tets only");
+		if (project_to_psd && values == nullptr)
 			project_to_psd = 0; // no Hessian requested: nothing to project
-		}
+		// The element stiffness of LinearElasticity is positive semi-definite by construction: ipc::project_to_psd returns such a
+		// matrix unchanged (its six rigid-body eigenvalues are zero up to rounding), so the flag has no effect there.
+		if (project_to_psd && h->dm.material == PFA_LINEAR_ELASTICITY)
+			project_to_psd = 0;
+		if (project_to_psd && h->dm.material != PFA_NEOHOOKEAN && h->dm.material != PFA_SAINT_VENANT)
+			return fail(h, PFA_ERR_UNSUPPORTED, "project_to_psd applies to the NLAssembler materials only");
 		if (scale != 1.0 && !rowlane_applies(h->dm.material, h->dm.n_loc, h->dm.n_qp))
 			return fail(h, PFA_ERR_UNSUPPORTED, "a Form weight other than 1 is fused for NeoHookean P1/P2 tets only");
 		if ((h->dm.material == PFA_LAPLACIAN || h->dm.material == PFA_MASS) && !linear)
@@ -358,6 +360,12 @@ namespace
 		if (h->profiling && !h->prof.empty() && !h->prof.back().stop_recorded)
 			h->prof.back().name = kname;
 		prof_end(h);
+		if (ce == cudaErrorNotSupported)
+		{
+			cudaGetLastError();
+			return fail(h, PFA_ERR_UNSUPPORTED, project_to_psd ? "project_to_psd needs 2 N (N|1) doubles of shared memory per warp with N = 3 n_loc even: P1..P3 elements (P4: N = 105)"
+																: "this material / element type combination is not implemented");
+		}
 		if (ce != cudaSuccess)
 			return fail(h, PFA_ERR_CUDA, std::string("assembly kernel launch: ") + cudaGetErrorString(ce));
 

@@ -171,13 +171,14 @@ namespace pfa
 		struct WarpLayout
 		{
 			int U, D, A, Q, J, DA, I; // offsets in doubles (I: start of the int region, in doubles)
+			int H = 0, V = 0, CS = 0, PQ = 0; // project_to_psd variant only
 			int total;                // doubles per warp
 		};
 		// per-qp record: C[9] | P*da[9] | c2*da*F[9] | c1*da | mu*da | lambda*da | (SaintVenant) mu*da*F F^T [6]
 		// SaintVenant uses the slots as: F[9] | P*da[9] | S*da[9] | - | mu*da | lambda*da | mu*da*F F^T (00 01 02 11 12 22)
 		constexpr int kQRec = 36;
 
-		__host__ __device__ inline WarpLayout warp_layout(int n_loc, int n_qp)
+		__host__ __device__ inline WarpLayout warp_layout(int n_loc, int n_qp, bool psd = false)
 		{
 			WarpLayout L;
 			int o = 0;
@@ -195,17 +196,182 @@ namespace pfa
 			o += n_qp;
 			L.I = o;
 			o += (3 * n_loc + 1) / 2;
+			if (psd)
+			{
+				// local matrix H and eigenvector matrix V [N][N|1], rotation parameters c, s [N/2] and pairs p, q [N/2] ints
+				const int N = 3 * n_loc, LD = N | 1, HALF = N / 2;
+				L.H = o;
+				o += N * LD;
+				L.V = o;
+				o += N * LD;
+				L.CS = o;
+				o += 2 * HALF;
+				L.PQ = o;
+				o += HALF + 1;
+			}
 			L.total = o;
 			return L;
 		}
 
-		template <int MAT, bool LINEAR, int kWarps>
+		// project_to_psd for the generic kernel (ipc::project_to_psd on the local Hessian, Assembler.cpp:693-694), any
+		// NLAssembler material with N = 3 n_loc even and N*(N|1) doubles x 2 of shared memory per warp (P1..P3): the local
+		// matrix sH (lower triangle mirrored, as the eigen-solver reads one triangle) is diagonalised by a parallel cyclic
+		// Jacobi method (round-robin ordering: N/2 disjoint rotations per step; lanes loop over rows) and, if its smallest
+		// eigenvalue is negative, rebuilt as V max(D, 0) V^T. Non-finite and already-PSD matrices are left unchanged.
+		// Returns true when the matrix was changed (then sH holds the projected matrix); false: the caller keeps the original.
+		__device__ inline bool psd_project_warp(double *sH, double *sV, int N, int LD, int *sP, int *sQ, double *sC, double *sS, int lane)
+		{
+			const int HALF = N / 2;
+			for (int r = lane; r < N; r += 32)
+				for (int c = r + 1; c < N; ++c)
+					sH[r * LD + c] = sH[c * LD + r];
+			__syncwarp();
+			bool finite = true, nonzero = false;
+			for (int r = lane; r < N; r += 32)
+				for (int c = 0; c < N; ++c)
+				{
+					const double v = sH[r * LD + c];
+					finite = finite && isfinite(v);
+					nonzero = nonzero || v != 0.0;
+					sV[r * LD + c] = c == r ? 1.0 : 0.0;
+				}
+			finite = __all_sync(0xffffffffu, finite);
+			nonzero = __any_sync(0xffffffffu, nonzero);
+			__syncwarp();
+			if (!finite || !nonzero)
+				return false;
+			for (int sweep = 0; sweep < 100; ++sweep)
+			{
+				double off = 0.0, diag = 0.0;
+				for (int r = lane; r < N; r += 32)
+					for (int c = 0; c < N; ++c)
+					{
+						const double v = sH[r * LD + c];
+						if (c == r)
+							diag += v * v;
+						else
+							off += v * v;
+					}
+				for (int o = 16; o > 0; o >>= 1)
+				{
+					off += __shfl_xor_sync(0xffffffffu, off, o);
+					diag += __shfl_xor_sync(0xffffffffu, diag, o);
+				}
+				if (off <= 1e-30 * diag || off == 0.0)
+					break;
+				for (int step = 0; step < N - 1; ++step)
+				{
+					for (int k = lane; k < HALF; k += 32)
+					{
+						int pp, qq;
+						if (k == 0)
+						{
+							pp = step;
+							qq = N - 1;
+						}
+						else
+						{
+							pp = (step + k) % (N - 1);
+							qq = (step - k + (N - 1)) % (N - 1);
+						}
+						if (pp > qq)
+						{
+							const int t = pp;
+							pp = qq;
+							qq = t;
+						}
+						const double apq = sH[pp * LD + qq];
+						double c = 1.0, sn = 0.0;
+						if (apq != 0.0)
+						{
+							const double app = sH[pp * LD + pp], aqq = sH[qq * LD + qq];
+							const double theta = (aqq - app) / (2.0 * apq);
+							const double t = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+							c = 1.0 / sqrt(t * t + 1.0);
+							sn = t * c;
+						}
+						sP[k] = pp;
+						sQ[k] = qq;
+						sC[k] = c;
+						sS[k] = sn;
+					}
+					__syncwarp();
+					for (int r = lane; r < N; r += 32) // H <- H J and V <- V J, row by row
+						for (int k = 0; k < HALF; ++k)
+						{
+							const int pp = sP[k], qq = sQ[k];
+							const double c = sC[k], sn = sS[k];
+							const double akp = sH[r * LD + pp], akq = sH[r * LD + qq];
+							sH[r * LD + pp] = c * akp - sn * akq;
+							sH[r * LD + qq] = sn * akp + c * akq;
+							const double vkp = sV[r * LD + pp], vkq = sV[r * LD + qq];
+							sV[r * LD + pp] = c * vkp - sn * vkq;
+							sV[r * LD + qq] = sn * vkp + c * vkq;
+						}
+					__syncwarp();
+					for (int cc = lane; cc < N; cc += 32) // H <- J^T H, column by column
+						for (int k = 0; k < HALF; ++k)
+						{
+							const int pp = sP[k], qq = sQ[k];
+							const double c = sC[k], sn = sS[k];
+							const double apk = sH[pp * LD + cc], aqk = sH[qq * LD + cc];
+							sH[pp * LD + cc] = c * apk - sn * aqk;
+							sH[qq * LD + cc] = sn * apk + c * aqk;
+						}
+					__syncwarp();
+				}
+			}
+			double wmin = 1e300;
+			for (int r = lane; r < N; r += 32)
+				wmin = fmin(wmin, sH[r * LD + r]);
+			for (int o = 16; o > 0; o >>= 1)
+				wmin = fmin(wmin, __shfl_xor_sync(0xffffffffu, wmin, o));
+			if (!(wmin < 0.0))
+				return false; // already PSD: the reference returns the matrix unchanged
+			// H = V max(D, 0) V^T. The (clamped) eigenvalues stay on the diagonal while the strictly lower triangle - which carries
+			// no information after convergence - is overwritten with the rebuilt entries; the diagonal follows in a second pass.
+			for (int r = lane; r < N; r += 32)
+				if (sH[r * LD + r] < 0.0)
+					sH[r * LD + r] = 0.0;
+			__syncwarp();
+			for (int r = lane; r < N; r += 32)
+				for (int c = 0; c < r; ++c)
+				{
+					double sum = 0.0;
+					for (int k = 0; k < N; ++k)
+						sum += sV[r * LD + k] * sH[k * LD + k] * sV[c * LD + k];
+					sH[r * LD + c] = sum;
+				}
+			__syncwarp();
+			// diagonal entries last (they hold the eigenvalues until here): each into a register, synchronise, then store
+			double dnew[4]; // N <= 128
+			int cnt = 0;
+			for (int r = lane; r < N; r += 32)
+			{
+				double sum = 0.0;
+				for (int k = 0; k < N; ++k)
+					sum += sV[r * LD + k] * sH[k * LD + k] * sV[r * LD + k];
+				dnew[cnt++] = sum;
+			}
+			__syncwarp();
+			cnt = 0;
+			for (int r = lane; r < N; r += 32)
+				sH[r * LD + r] = dnew[cnt++];
+			__syncwarp();
+			for (int r = lane; r < N; r += 32)
+				for (int c = r + 1; c < N; ++c)
+					sH[r * LD + c] = sH[c * LD + r];
+			__syncwarp();
+			return true;
+		}
+
+		template <int MAT, bool LINEAR, int kWarps, bool PSD = false>
 		__global__ void __launch_bounds__(kWarps * 32) assemble_generic_kernel(const DeviceMesh m, const AssembleArgs a)
 		{
 			extern __shared__ double smem[];
 			const int n_loc = m.n_loc, n_qp = m.n_qp;
 			const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-			const WarpLayout L = warp_layout(n_loc, n_qp);
+			const WarpLayout L = warp_layout(n_loc, n_qp, PSD);
 
 			// CTA-shared reference tables
 			double *s_rg = smem;                   // [n_qp][n_loc][3]
@@ -412,8 +578,18 @@ namespace pfa
 				__syncwarp();
 
 				// ---- 5. local Hessian / stiffness blocks and scatter ----
+				// project_to_psd: pass 0 puts the blocks into the local matrix, which is then projected; pass 1 scatters the projected
+				// blocks, or - when the projection left the matrix unchanged - recomputes and scatters them like the plain path
+				bool psd_changed = false;
 				if (want_h)
+				for (int pass = PSD ? 0 : 1; pass < 2; ++pass)
 				{
+					if (PSD && pass == 1)
+					{
+						__syncwarp();
+						psd_changed = psd_project_warp(ws + L.H, ws + L.V, 3 * n_loc, (3 * n_loc) | 1, reinterpret_cast<int *>(ws + L.PQ),
+													   reinterpret_cast<int *>(ws + L.PQ) + (3 * n_loc) / 2, ws + L.CS, ws + L.CS + (3 * n_loc) / 2, lane);
+					}
 					for (int b = lane; b < n_loc * n_loc; b += 32)
 					{
 						const int i = b / n_loc, j = b - i * n_loc;
@@ -430,7 +606,15 @@ namespace pfa
 							continue;
 						}
 						double blk[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}; // blk[a*3+b] = H[(i,a),(j,b)]
-						if (MAT == PFA_NEOHOOKEAN && !LINEAR)
+						if (PSD && pass == 1 && psd_changed)
+						{
+							const double *sH = ws + L.H;
+							const int LDh = (3 * n_loc) | 1;
+							for (int r = 0; r < 3; ++r)
+								for (int c = 0; c < 3; ++c)
+									blk[r * 3 + c] = sH[(i * 3 + r) * LDh + j * 3 + c];
+						}
+						else if (MAT == PFA_NEOHOOKEAN && !LINEAR)
 						{
 							double s = 0.0, W0 = 0.0, W1 = 0.0, W2 = 0.0;
 							for (int q = 0; q < n_qp; ++q)
@@ -512,6 +696,15 @@ namespace pfa
 								blk[4] += mu * dot;
 								blk[8] += mu * dot;
 							}
+						}
+						if (PSD && pass == 0)
+						{
+							double *sH = ws + L.H;
+							const int LDh = (3 * n_loc) | 1;
+							for (int r = 0; r < 3; ++r)
+								for (int c = 0; c < 3; ++c)
+									sH[(i * 3 + r) * LDh + j * 3 + c] = blk[r * 3 + c];
+							continue;
 						}
 						// values index of (row (g_i,m), col (g_j,n)) = 9*off_j + n*3*deg_j + 3*k + m
 						const int off = sOff[j], deg = sDeg[j];
@@ -1814,9 +2007,9 @@ namespace pfa
 
 		constexpr size_t kMaxSmem = 227 * 1024;
 
-		size_t generic_smem_bytes(int n_loc, int n_qp, int warps)
+		size_t generic_smem_bytes(int n_loc, int n_qp, int warps, bool psd = false)
 		{
-			const WarpLayout L = warp_layout(n_loc, n_qp);
+			const WarpLayout L = warp_layout(n_loc, n_qp, psd);
 			return sizeof(double) * (size_t(n_qp) * n_loc * 3 + n_qp + size_t(warps) * L.total);
 		}
 
@@ -1846,6 +2039,29 @@ namespace pfa
 			const int64_t need = (int64_t(m.n_el) + kWarps - 1) / kWarps;
 			const int grid = int(std::max<int64_t>(1, std::min<int64_t>(need, int64_t(sm_count) * per_sm)));
 			kern<<<grid, kWarps * 32, smem, st>>>(m, a);
+			return cudaGetLastError();
+		}
+
+		// project_to_psd through the generic kernel: one or two warps per CTA (the local matrices need 2 N (N|1) doubles per warp)
+		template <int MAT>
+		cudaError_t launch_generic_psd(const DeviceMesh &m, const AssembleArgs &a, int sm_count, cudaStream_t st)
+		{
+			if ((3 * m.n_loc) % 2 != 0 || 3 * m.n_loc > 128)
+				return cudaErrorNotSupported;
+			constexpr int kW = 2;
+			size_t smem = generic_smem_bytes(m.n_loc, m.n_qp, kW, true);
+			if (smem > kMaxSmem)
+				return cudaErrorNotSupported;
+			auto kern = assemble_generic_kernel<MAT, false, kW, true>;
+			cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+			if (err != cudaSuccess)
+				return err;
+			int per_sm = 1;
+			if ((err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kW * 32, smem)) != cudaSuccess)
+				return err;
+			const int64_t need = (int64_t(m.n_el) + kW - 1) / kW;
+			const int grid = int(std::max<int64_t>(1, std::min<int64_t>(need, int64_t(sm_count) * std::max(per_sm, 1))));
+			kern<<<grid, kW * 32, smem, st>>>(m, a);
 			return cudaGetLastError();
 		}
 
@@ -1960,11 +2176,13 @@ namespace pfa
 			{
 				if (kernel_name)
 					*kernel_name = "assemble_nh_psd_kernel";
-				if (m.n_loc == 10 && m.n_qp == 4)
+				if (m.n_loc == 10 && m.n_qp == 4 && m.entry != nullptr)
 					return launch_psd<10, 4, 8>(m, a, sm_count, st);
-				if (m.n_loc == 4 && m.n_qp == 1)
+				if (m.n_loc == 4 && m.n_qp == 1 && m.entry != nullptr)
 					return launch_psd<4, 1, 8>(m, a, sm_count, st);
-				return cudaErrorNotSupported;
+				if (kernel_name)
+					*kernel_name = "assemble_generic_kernel<NeoHookean,psd>";
+				return launch_generic_psd<PFA_NEOHOOKEAN>(m, a, sm_count, st);
 			}
 			if (m.n_loc == 10 && m.n_qp == 4)
 			{
@@ -1982,10 +2200,12 @@ namespace pfa
 			}
 			return launch_generic<PFA_NEOHOOKEAN, false>(m, a, sm_count, st);
 		case PFA_SAINT_VENANT:
-			if (linear || a.project_to_psd)
+			if (linear)
 				return cudaErrorNotSupported;
 			if (kernel_name)
-				*kernel_name = "assemble_generic_kernel<SaintVenant>";
+				*kernel_name = a.project_to_psd ? "assemble_generic_kernel<SaintVenant,psd>" : "assemble_generic_kernel<SaintVenant>";
+			if (a.project_to_psd)
+				return launch_generic_psd<PFA_SAINT_VENANT>(m, a, sm_count, st);
 			return launch_generic<PFA_SAINT_VENANT, false>(m, a, sm_count, st);
 		case PFA_LINEAR_ELASTICITY:
 			if (linear && affine_linear_applies(m) && a.values != nullptr)

@@ -274,11 +274,6 @@ def test_project_to_psd(oracle, p, n, scale):
     # a PSD-everywhere state (x = 0) is returned unchanged, to the last bit of the unprojected path
     z = np.zeros_like(x)
     assert np.array_equal(h.hessian(z, project_to_psd=True), h.hessian(z)) or np.abs(h.hessian(z, project_to_psd=True) - ref.assemble_hessian(z, project_to_psd=True).values).max() <= 1e-10 * np.abs(H0.values).max()
-    # unsupported combinations fail loudly instead of silently skipping the projection
-    from polyfem_b200 import capi
-    h3 = gpu_handle(M3 := make_case(2, 3)[0], "NeoHookean")
-    with pytest.raises(capi.PfaError):
-        h3.hessian(np.zeros(h3.ndof), project_to_psd=True)
 
 
 @pytest.mark.parametrize("k", range(12))

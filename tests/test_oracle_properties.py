@@ -152,3 +152,36 @@ def test_nodes_without_elements_give_empty_columns(oracle):
     g = big.assemble_gradient(x)
     assert np.array_equal(g[: x0.size], ref.assemble_gradient(x0)) and not g[x0.size:].any()
     assert big.assemble_energy(x) == ref.assemble_energy(x0)
+
+
+def test_project_to_psd_known_answers(oracle):
+    """Hand-computed answers for the restatement of ipc::project_to_psd (the library's source is absent: documented behaviour =
+    symmetric eigendecomposition, negative eigenvalues clamped to zero, a PSD input returned unchanged)."""
+    # 2 x 2, eigenvalues 3 and -1 with eigenvectors (1, 1)/sqrt(2), (1, -1)/sqrt(2): projection = 3 v v^T
+    out = oracle.project_to_psd(np.array([[1.0, 2.0], [2.0, 1.0]]))
+    assert np.abs(out - np.array([[1.5, 1.5], [1.5, 1.5]])).max() <= 1e-15
+    # diagonal: clamps entry by entry
+    out = oracle.project_to_psd(np.diag([2.0, -1.0, 0.5]))
+    assert np.abs(out - np.diag([2.0, 0.0, 0.5])).max() <= 1e-15
+    # 3 x 3 with a known spectrum: Q diag(4, -2, 1) Q^T for the rotation Q about (1, 1, 1)/sqrt(3) by 120 degrees composed
+    # with a Householder reflection - built here, answer = Q diag(4, 0, 1) Q^T
+    w = np.array([1.0, 2.0, 2.0]) / 3.0
+    Q = np.eye(3) - 2.0 * np.outer(w, w)
+    A = Q @ np.diag([4.0, -2.0, 1.0]) @ Q.T
+    out = oracle.project_to_psd(A)
+    assert np.abs(out - Q @ np.diag([4.0, 0.0, 1.0]) @ Q.T).max() <= 1e-14
+    # an indefinite 2 x 2 block embedded in a 6 x 6 matrix that is otherwise PSD and decoupled: only the block changes
+    B = np.zeros((6, 6))
+    B[0, 0], B[1, 1], B[4, 4], B[5, 5] = 3.0, 0.25, 7.0, 0.0
+    B[2:4, 2:4] = [[1.0, 2.0], [2.0, 1.0]]
+    out = oracle.project_to_psd(B)
+    want = B.copy()
+    want[2:4, 2:4] = 1.5
+    assert np.abs(out - want).max() <= 1e-15
+    # already PSD (including a zero eigenvalue): returned bit for bit
+    P = np.array([[2.0, 1.0, 0.0], [1.0, 2.0, 0.0], [0.0, 0.0, 0.0]])
+    assert np.array_equal(oracle.project_to_psd(P), P)
+    rng = np.random.default_rng(11)
+    G = rng.standard_normal((12, 12))
+    S = G @ G.T
+    assert np.array_equal(oracle.project_to_psd(S), S)
