@@ -42,6 +42,9 @@ struct pfa_handle
 	// owned device memory
 	std::vector<void *> owned;
 	int32_t *d_outer = nullptr, *d_inner = nullptr;
+	bool large_index = false; // PFA_FLAG_LARGE_INDEX: int64 pattern (built on first use), no int32 pattern
+	int64_t *d_outer64 = nullptr, *d_inner64 = nullptr;
+	std::vector<int64_t> h_outer64, h_inner64;
 	double *d_lambda = nullptr, *d_mu = nullptr;
 	int32_t *d_elem_id = nullptr; // internal -> caller element index (nullptr: identity)
 	double *s_mat = nullptr;      // staging for pfa_set_materials when elements are re-ordered
@@ -568,9 +571,15 @@ extern "C"
 		m.n_pairs = int64_t(hp.adj.size());
 		h->ndof = int64_t(m.n_bases) * m.size;
 		h->nnz = m.n_pairs * m.size * m.size;
-		if (h->nnz >= (int64_t(1) << 31))
+		h->large_index = (d->flags & PFA_FLAG_LARGE_INDEX) != 0;
+		if (h->nnz >= (int64_t(1) << 31) && !h->large_index)
 		{
-			h->err = "pfa_create: nnz exceeds int32 (StiffnessMatrix uses int indices unless POLYSOLVE_LARGE_INDEX)";
+			h->err = "pfa_create: nnz exceeds int32 (StiffnessMatrix uses int indices unless POLYSOLVE_LARGE_INDEX): pass PFA_FLAG_LARGE_INDEX";
+			return bail(PFA_ERR_UNSUPPORTED);
+		}
+		if (h->nnz >= (int64_t(1) << 31) && rowlane_applies(d->material, d->n_loc, d->n_qp))
+		{
+			h->err = "pfa_create: the NeoHookean P1/P2 kernels keep int32 entry tables: nnz must stay below 2^31";
 			return bail(PFA_ERR_UNSUPPORTED);
 		}
 
@@ -722,10 +731,12 @@ extern "C"
 			UP(m.detj, d->da, ne * nq, double);
 		}
 #undef UP
-#undef PFA_CREATE_CUDA
-		if ((rc = dev_alloc<int32_t>(h, &h->d_outer, size_t(h->ndof) + 1)) != PFA_OK || (rc = dev_alloc<int32_t>(h, &h->d_inner, size_t(h->nnz))) != PFA_OK || (rc = dev_alloc<double>(h, &h->d_energy, 1)) != PFA_OK || (rc = dev_alloc<int>(h, &h->d_counter, 4)) != PFA_OK)
+		if ((rc = dev_alloc<double>(h, &h->d_energy, 1)) != PFA_OK || (rc = dev_alloc<int>(h, &h->d_counter, 4)) != PFA_OK)
 			return bail(rc);
+		if (!h->large_index)
 		{
+			if ((rc = dev_alloc<int32_t>(h, &h->d_outer, size_t(h->ndof) + 1)) != PFA_OK || (rc = dev_alloc<int32_t>(h, &h->d_inner, size_t(h->nnz))) != PFA_OK)
+				return bail(rc);
 			++h->launches;
 			cudaError_t e = launch_expand_inner(m, h->d_outer, h->d_inner, h->stream);
 			if (e == cudaSuccess)
@@ -736,6 +747,9 @@ extern "C"
 				return bail(PFA_ERR_CUDA);
 			}
 		}
+		else
+			PFA_CREATE_CUDA(cudaStreamSynchronize(h->stream));
+#undef PFA_CREATE_CUDA
 		h->h_adj_off.swap(hp.adj_off);
 		h->h_adj.swap(hp.adj);
 		h->setup_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
@@ -780,10 +794,75 @@ extern "C"
 		return PFA_OK;
 	}
 
+	// the int64 pattern of a PFA_FLAG_LARGE_INDEX handle on the device, built on first use
+	static int ensure_pattern64(pfa_handle *h)
+	{
+		if (!h->large_index)
+			return fail(h, PFA_ERR_UNSUPPORTED, "pfa_pattern64: the handle was not created with PFA_FLAG_LARGE_INDEX");
+		if (h->d_outer64)
+			return PFA_OK;
+		PFA_CUDA(h, cudaSetDevice(h->device));
+		int rc;
+		if ((rc = dev_alloc<int64_t>(h, &h->d_outer64, size_t(h->ndof) + 1)) != PFA_OK || (rc = dev_alloc<int64_t>(h, &h->d_inner64, size_t(h->nnz))) != PFA_OK)
+			return rc;
+		++h->launches;
+		PFA_CUDA(h, launch_expand_inner64(h->dm, h->d_outer64, h->d_inner64, h->stream));
+		PFA_CUDA(h, cudaStreamSynchronize(h->stream));
+		return PFA_OK;
+	}
+
+	int pfa_pattern64(pfa_handle *h, int64_t *nnz, const int64_t **outer, const int64_t **inner)
+	{
+		if (!h)
+			return PFA_ERR_INVALID;
+		int rc = ensure_pattern64(h);
+		if (rc != PFA_OK)
+			return rc;
+		if (h->h_outer64.empty())
+		{
+			try
+			{
+				h->h_outer64.resize(size_t(h->ndof) + 1);
+				h->h_inner64.resize(size_t(h->nnz));
+			}
+			catch (const std::bad_alloc &)
+			{
+				h->h_outer64.clear();
+				return fail(h, PFA_ERR_NOMEM, "pfa_pattern64: out of host memory");
+			}
+			PFA_CUDA(h, cudaMemcpyAsync(h->h_outer64.data(), h->d_outer64, h->h_outer64.size() * sizeof(int64_t), cudaMemcpyDeviceToHost, h->stream));
+			PFA_CUDA(h, cudaMemcpyAsync(h->h_inner64.data(), h->d_inner64, h->h_inner64.size() * sizeof(int64_t), cudaMemcpyDeviceToHost, h->stream));
+			PFA_CUDA(h, cudaStreamSynchronize(h->stream));
+		}
+		if (nnz)
+			*nnz = h->nnz;
+		if (outer)
+			*outer = h->h_outer64.data();
+		if (inner)
+			*inner = h->h_inner64.data();
+		return PFA_OK;
+	}
+
+	int pfa_pattern64_device(pfa_handle *h, const int64_t **outer_dev, const int64_t **inner_dev)
+	{
+		if (!h)
+			return PFA_ERR_INVALID;
+		int rc = ensure_pattern64(h);
+		if (rc != PFA_OK)
+			return rc;
+		if (outer_dev)
+			*outer_dev = h->d_outer64;
+		if (inner_dev)
+			*inner_dev = h->d_inner64;
+		return PFA_OK;
+	}
+
 	int pfa_pattern(pfa_handle *h, int64_t *nnz, const int32_t **outer, const int32_t **inner)
 	{
 		if (!h)
 			return PFA_ERR_INVALID;
+		if (h->large_index)
+			return fail(h, PFA_ERR_UNSUPPORTED, "pfa_pattern: PFA_FLAG_LARGE_INDEX handle, use pfa_pattern64");
 		PFA_CUDA(h, cudaSetDevice(h->device));
 		if (h->h_outer.empty())
 		{
@@ -827,6 +906,8 @@ extern "C"
 	{
 		if (!h)
 			return PFA_ERR_INVALID;
+		if (h->large_index)
+			return fail(h, PFA_ERR_UNSUPPORTED, "pfa_pattern_device: PFA_FLAG_LARGE_INDEX handle, use pfa_pattern64_device");
 		if (outer_dev)
 			*outer_dev = h->d_outer;
 		if (inner_dev)
@@ -955,6 +1036,8 @@ extern "C"
 
 	int pfa_set_constrained_dofs(pfa_handle *h, const int32_t *dofs, int64_t n)
 	{
+		if (h && h->large_index)
+			return fail(h, PFA_ERR_UNSUPPORTED, "pfa_set_constrained_dofs: not available on a PFA_FLAG_LARGE_INDEX handle (int32 pattern arrays)");
 		if (!h || n < 0 || (n > 0 && !dofs))
 			return fail(h, PFA_ERR_INVALID, "pfa_set_constrained_dofs: NULL list or negative count");
 		if (h->ndof >= (int64_t(1) << 31) - 1)
@@ -1180,6 +1263,8 @@ extern "C"
 
 	int pfa_inertia(pfa_handle *h, const double *mass_values, const double *x, const double *x_tilde, double *energy, double *grad)
 	{
+		if (h && h->large_index)
+			return fail(h, PFA_ERR_UNSUPPORTED, "pfa_inertia: not available on a PFA_FLAG_LARGE_INDEX handle (int32 pattern arrays)");
 		if (!h || !mass_values || !x)
 			return fail(h, PFA_ERR_INVALID, "pfa_inertia / pfa_symv: NULL argument");
 		if (!energy && !grad)
@@ -1211,6 +1296,8 @@ extern "C"
 
 	int pfa_symv(pfa_handle *h, const double *values, const double *x, double *y)
 	{
+		if (h && h->large_index)
+			return fail(h, PFA_ERR_UNSUPPORTED, "pfa_symv: not available on a PFA_FLAG_LARGE_INDEX handle (int32 pattern arrays)");
 		if (!y)
 			return fail(h, PFA_ERR_INVALID, "pfa_symv: NULL argument");
 		return pfa_inertia(h, values, x, nullptr, nullptr, y);

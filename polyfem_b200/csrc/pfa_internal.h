@@ -106,6 +106,7 @@ namespace pfa
 	// kernel launchers (pfa_kernels.cu). Return cudaError_t of the launch.
 	cudaError_t launch_geometry_precompute(const double *vertices_dev, int n_el, double *jit, double *detj, cudaStream_t st);
 	cudaError_t launch_expand_inner(const DeviceMesh &m, int32_t *outer, int32_t *inner, cudaStream_t st);
+	cudaError_t launch_expand_inner64(const DeviceMesh &m, int64_t *outer, int64_t *inner, cudaStream_t st);
 	// fused per-element energy / gradient / Hessian with scatter (NLAssembler entry points);
 	// `linear` selects LinearAssembler::assemble semantics (x ignored).
 	cudaError_t launch_assemble(const DeviceMesh &m, const AssembleArgs &a, bool linear, int sm_count, cudaStream_t st, const char **kernel_name);

@@ -143,7 +143,8 @@ namespace pfa
 		}
 
 		// scalar CSC arrays from the node-block pattern: column (b,n) lists rows (a,m), a in adj(b)
-		__global__ void expand_inner_kernel(const int32_t *__restrict__ adj_off, const int32_t *__restrict__ adj, int n_bases, int size, int32_t *__restrict__ outer, int32_t *__restrict__ inner)
+		template <typename Index>
+		__global__ void expand_inner_kernel(const int32_t *__restrict__ adj_off, const int32_t *__restrict__ adj, int n_bases, int size, Index *__restrict__ outer, Index *__restrict__ inner)
 		{
 			const int b = blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32; // one warp per node column-block
 			const int lane = threadIdx.x & 31;
@@ -152,9 +153,9 @@ namespace pfa
 			const int off = adj_off[b], deg = adj_off[b + 1] - off;
 			const int64_t base = int64_t(off) * size * size;
 			for (int n = lane; n < size; n += 32)
-				outer[b * size + n] = int32_t(base + int64_t(n) * size * deg);
+				outer[b * size + n] = Index(base + int64_t(n) * size * deg);
 			if (b == n_bases - 1 && lane == 0)
-				outer[n_bases * size] = int32_t(int64_t(adj_off[n_bases]) * size * size);
+				outer[n_bases * size] = Index(int64_t(adj_off[n_bases]) * size * size);
 			const int per_col = deg * size;
 			for (int t = lane; t < per_col * size; t += 32)
 			{
@@ -2161,7 +2162,14 @@ namespace pfa
 	cudaError_t launch_expand_inner(const DeviceMesh &m, int32_t *outer, int32_t *inner, cudaStream_t st)
 	{
 		const int warps = 8;
-		expand_inner_kernel<<<(m.n_bases + warps - 1) / warps, warps * 32, 0, st>>>(m.adj_off, m.adj, m.n_bases, m.size, outer, inner);
+		expand_inner_kernel<int32_t><<<(m.n_bases + warps - 1) / warps, warps * 32, 0, st>>>(m.adj_off, m.adj, m.n_bases, m.size, outer, inner);
+		return cudaGetLastError();
+	}
+
+	cudaError_t launch_expand_inner64(const DeviceMesh &m, int64_t *outer, int64_t *inner, cudaStream_t st)
+	{
+		const int warps = 8;
+		expand_inner_kernel<int64_t><<<(m.n_bases + warps - 1) / warps, warps * 32, 0, st>>>(m.adj_off, m.adj, m.n_bases, m.size, outer, inner);
 		return cudaGetLastError();
 	}
 

@@ -156,6 +156,9 @@ namespace polyfem::assembler::b200
 			}
 			d.material_stride = n_qp;
 			d.device = 0;
+#ifdef POLYSOLVE_LARGE_INDEX
+			d.flags |= PFA_FLAG_LARGE_INDEX;
+#endif
 			if (pfa_create(&d, &h_) != PFA_OK)
 				log_and_throw_error("B200 assembly path: {}", pfa_last_error(nullptr));
 			key_ = bases.data();
@@ -191,16 +194,25 @@ namespace polyfem::assembler::b200
 			uploaded_version_ = material_version_;
 		}
 
-		/// Wraps values[] in the reference's matrix type (pattern identical to SparseMatrixCache's).
+		/// Wraps values[] in the reference's matrix type (pattern identical to SparseMatrixCache's). With POLYSOLVE_LARGE_INDEX
+		/// (utils/Types.hpp:21-25) StiffnessMatrix stores std::ptrdiff_t indices: the handle is then created with
+		/// PFA_FLAG_LARGE_INDEX and hands out the int64 pattern.
 		static void to_eigen(pfa_handle *h, const std::vector<double> &values, StiffnessMatrix &out)
 		{
 			int32_t size;
 			int64_t ndof, nnz;
-			const int32_t *outer, *inner;
 			pfa_sizes(h, &size, &ndof, &nnz);
+#ifdef POLYSOLVE_LARGE_INDEX
+			const int64_t *outer, *inner;
+			if (pfa_pattern64(h, &nnz, &outer, &inner) != PFA_OK)
+				log_and_throw_error("B200 assembly path: {}", pfa_last_error(h));
+			out = Eigen::Map<const StiffnessMatrix>(ndof, ndof, nnz, reinterpret_cast<const std::ptrdiff_t *>(outer), reinterpret_cast<const std::ptrdiff_t *>(inner), values.data());
+#else
+			const int32_t *outer, *inner;
 			if (pfa_pattern(h, &nnz, &outer, &inner) != PFA_OK)
 				log_and_throw_error("B200 assembly path: {}", pfa_last_error(h));
 			out = Eigen::Map<const StiffnessMatrix>(ndof, ndof, nnz, outer, inner, values.data());
+#endif
 		}
 
 		static void check(pfa_handle *h, const int rc)
