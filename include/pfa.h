@@ -138,7 +138,7 @@ extern "C"
  * material so that their records can be evaluated for the columns of owned nodes (see pfa_mesh_desc.owned_nodes) */
 #define PFA_FLAG_GHOST_GEOMETRY 16
 /* Large matrices (utils/Types.hpp:21-25: with POLYSOLVE_LARGE_INDEX StiffnessMatrix uses std::ptrdiff_t indices): the pattern is
- * handed out as int64 arrays by pfa_pattern64 / pfa_pattern64_device and nnz may exceed 2^31 (BASELINE cfg 4, LinearElasticity P4
+ * handed out as int64 arrays by pfa_pattern_wide / pfa_pattern_wide_device and nnz may exceed 2^31 (BASELINE cfg 4, LinearElasticity P4
  * n = 32: 2.5 G nnz). Without the flag pfa_create refuses such a mesh, as Eigen's int indices would. With the flag the int32
  * accessors (pfa_pattern*, the Dirichlet projection, pfa_symv / pfa_inertia) report PFA_ERR_UNSUPPORTED; the NeoHookean P1/P2
  * kernels keep int32 entry tables and are limited to nnz < 2^31 either way. */
@@ -180,9 +180,9 @@ extern "C"
 	 * position k is size*size*adj_off[b] + n*size*deg(b) + size*k + m. Host arrays owned by the handle. */
 	int pfa_block_pattern(pfa_handle *h, int64_t *n_pairs, const int32_t **adj_off, const int32_t **adj);
 	/* PFA_FLAG_LARGE_INDEX handles: the same pattern with 64-bit indices (Eigen::SparseMatrix<double, ColMajor, std::ptrdiff_t>);
-	 * built on first use (16 bytes per nnz on the device, and on the host for pfa_pattern64) */
-	int pfa_pattern64(pfa_handle *h, int64_t *nnz, const int64_t **outer, const int64_t **inner);
-	int pfa_pattern64_device(pfa_handle *h, const int64_t **outer_dev, const int64_t **inner_dev);
+	 * built on first use (16 bytes per nnz on the device, and on the host for pfa_pattern_wide) */
+	int pfa_pattern_wide(pfa_handle *h, int64_t *nnz, const int64_t **outer, const int64_t **inner);
+	int pfa_pattern_wide_device(pfa_handle *h, const int64_t **outer_dev, const int64_t **inner_dev);
 	/* same arrays in device memory (for a GPU linear solver / the multi-GPU exchange) */
 	int pfa_pattern_device(pfa_handle *h, const int32_t **outer_dev, const int32_t **inner_dev);
 

@@ -25,7 +25,7 @@ _ip = ctypes.POINTER(ctypes.c_int32)
 # every symbol include/pfa.h declares (tests check that the library exports all of them)
 EXPORTS = [
     "pfa_create", "pfa_destroy", "pfa_last_error", "pfa_sizes", "pfa_pattern", "pfa_block_pattern", "pfa_pattern_device",
-    "pfa_pattern64", "pfa_pattern64_device",
+    "pfa_pattern_wide", "pfa_pattern_wide_device",
     "pfa_set_materials", "pfa_energy", "pfa_energy_per_element", "pfa_gradient", "pfa_hessian",
     "pfa_linear_stiffness", "pfa_grad_hess", "pfa_grad_hess_weighted", "pfa_synchronize", "pfa_stream", "pfa_set_stream", "pfa_profile_enable",
     "pfa_profile_read", "pfa_launch_count", "pfa_setup_seconds",
@@ -89,8 +89,8 @@ def lib():
     L.pfa_block_pattern.argtypes = [vp, ctypes.POINTER(i64), ctypes.POINTER(_ip), ctypes.POINTER(_ip)]
     L.pfa_pattern_device.argtypes = [vp, ctypes.POINTER(vp), ctypes.POINTER(vp)]
     _lp = ctypes.POINTER(ctypes.c_int64)
-    L.pfa_pattern64.argtypes = [vp, ctypes.POINTER(i64), ctypes.POINTER(_lp), ctypes.POINTER(_lp)]
-    L.pfa_pattern64_device.argtypes = [vp, ctypes.POINTER(vp), ctypes.POINTER(vp)]
+    L.pfa_pattern_wide.argtypes = [vp, ctypes.POINTER(i64), ctypes.POINTER(_lp), ctypes.POINTER(_lp)]
+    L.pfa_pattern_wide_device.argtypes = [vp, ctypes.POINTER(vp), ctypes.POINTER(vp)]
     L.pfa_set_materials.argtypes = [vp, vp, vp, ctypes.c_int32]
     L.pfa_energy.argtypes = [vp, vp, vp]
     L.pfa_energy_per_element.argtypes = [vp, vp, vp]
@@ -251,12 +251,12 @@ class Handle:
         inner = np.ctypeslib.as_array(pi, shape=(nnz.value,)).copy()
         return outer, inner
 
-    def pattern64(self):
+    def pattern_wide(self):
         """(outer[ndof+1], inner[nnz]) int64 host arrays of a FLAG_LARGE_INDEX handle."""
         n = ctypes.c_int64()
         lp = ctypes.POINTER(ctypes.c_int64)
         po, pi = lp(), lp()
-        self._check(lib().pfa_pattern64(self._h, ctypes.byref(n), ctypes.byref(po), ctypes.byref(pi)))
+        self._check(lib().pfa_pattern_wide(self._h, ctypes.byref(n), ctypes.byref(po), ctypes.byref(pi)))
         return (np.ctypeslib.as_array(po, shape=(self.ndof + 1,)).copy(), np.ctypeslib.as_array(pi, shape=(n.value,)).copy())
 
     def block_pattern(self):

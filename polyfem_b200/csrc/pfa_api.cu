@@ -798,7 +798,7 @@ extern "C"
 	static int ensure_pattern64(pfa_handle *h)
 	{
 		if (!h->large_index)
-			return fail(h, PFA_ERR_UNSUPPORTED, "pfa_pattern64: the handle was not created with PFA_FLAG_LARGE_INDEX");
+			return fail(h, PFA_ERR_UNSUPPORTED, "pfa_pattern_wide: the handle was not created with PFA_FLAG_LARGE_INDEX");
 		if (h->d_outer64)
 			return PFA_OK;
 		PFA_CUDA(h, cudaSetDevice(h->device));
@@ -811,7 +811,7 @@ extern "C"
 		return PFA_OK;
 	}
 
-	int pfa_pattern64(pfa_handle *h, int64_t *nnz, const int64_t **outer, const int64_t **inner)
+	int pfa_pattern_wide(pfa_handle *h, int64_t *nnz, const int64_t **outer, const int64_t **inner)
 	{
 		if (!h)
 			return PFA_ERR_INVALID;
@@ -828,7 +828,7 @@ extern "C"
 			catch (const std::bad_alloc &)
 			{
 				h->h_outer64.clear();
-				return fail(h, PFA_ERR_NOMEM, "pfa_pattern64: out of host memory");
+				return fail(h, PFA_ERR_NOMEM, "pfa_pattern_wide: out of host memory");
 			}
 			PFA_CUDA(h, cudaMemcpyAsync(h->h_outer64.data(), h->d_outer64, h->h_outer64.size() * sizeof(int64_t), cudaMemcpyDeviceToHost, h->stream));
 			PFA_CUDA(h, cudaMemcpyAsync(h->h_inner64.data(), h->d_inner64, h->h_inner64.size() * sizeof(int64_t), cudaMemcpyDeviceToHost, h->stream));
@@ -843,7 +843,7 @@ extern "C"
 		return PFA_OK;
 	}
 
-	int pfa_pattern64_device(pfa_handle *h, const int64_t **outer_dev, const int64_t **inner_dev)
+	int pfa_pattern_wide_device(pfa_handle *h, const int64_t **outer_dev, const int64_t **inner_dev)
 	{
 		if (!h)
 			return PFA_ERR_INVALID;
@@ -862,7 +862,7 @@ extern "C"
 		if (!h)
 			return PFA_ERR_INVALID;
 		if (h->large_index)
-			return fail(h, PFA_ERR_UNSUPPORTED, "pfa_pattern: PFA_FLAG_LARGE_INDEX handle, use pfa_pattern64");
+			return fail(h, PFA_ERR_UNSUPPORTED, "pfa_pattern: PFA_FLAG_LARGE_INDEX handle, use pfa_pattern_wide");
 		PFA_CUDA(h, cudaSetDevice(h->device));
 		if (h->h_outer.empty())
 		{
@@ -907,7 +907,7 @@ extern "C"
 		if (!h)
 			return PFA_ERR_INVALID;
 		if (h->large_index)
-			return fail(h, PFA_ERR_UNSUPPORTED, "pfa_pattern_device: PFA_FLAG_LARGE_INDEX handle, use pfa_pattern64_device");
+			return fail(h, PFA_ERR_UNSUPPORTED, "pfa_pattern_device: PFA_FLAG_LARGE_INDEX handle, use pfa_pattern_wide_device");
 		if (outer_dev)
 			*outer_dev = h->d_outer;
 		if (inner_dev)

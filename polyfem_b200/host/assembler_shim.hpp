@@ -204,7 +204,7 @@ namespace polyfem::assembler::b200
 			pfa_sizes(h, &size, &ndof, &nnz);
 #ifdef POLYSOLVE_LARGE_INDEX
 			const int64_t *outer, *inner;
-			if (pfa_pattern64(h, &nnz, &outer, &inner) != PFA_OK)
+			if (pfa_pattern_wide(h, &nnz, &outer, &inner) != PFA_OK)
 				log_and_throw_error("B200 assembly path: {}", pfa_last_error(h));
 			out = Eigen::Map<const StiffnessMatrix>(ndof, ndof, nnz, reinterpret_cast<const std::ptrdiff_t *>(outer), reinterpret_cast<const std::ptrdiff_t *>(inner), values.data());
 #else

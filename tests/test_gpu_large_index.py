@@ -17,16 +17,17 @@ def test_int64_pattern_equals_int32_pattern(material, p, n):
     h32 = gpu_handle(mesh, material, t)
     h64 = gpu_handle(mesh, material, t, flags=capi.FLAG_LARGE_INDEX)
     o32, i32 = h32.pattern()
-    o64, i64 = h64.pattern64()
+    o64, i64 = h64.pattern_wide()
     assert o64.dtype == np.int64 and i64.dtype == np.int64
     assert np.array_equal(o32.astype(np.int64), o64) and np.array_equal(i32.astype(np.int64), i64)
     if material == "NeoHookean":
         xx = x[: mesh.n_bases * 3]
         assert np.array_equal(h32.hessian(xx), h64.hessian(xx))
     else:
-        assert np.array_equal(h32.linear_stiffness(), h64.linear_stiffness())
+        a, b = h32.linear_stiffness(), h64.linear_stiffness()  # RED accumulation: same sums in another order
+        assert np.abs(a - b).max() <= 1e-13 * np.abs(a).max()
     with pytest.raises(capi.PfaError) as ei:
         h64.pattern()
     assert ei.value.code == capi.PFA_ERR_UNSUPPORTED
     with pytest.raises(capi.PfaError):
-        h32.pattern64()
+        h32.pattern_wide()
