@@ -38,7 +38,7 @@ E_MOD, NU = 1e5, 0.3
 RHO, DT = 1000.0, 1e-3  # cfg 5
 
 # BASELINE.json configs[0..4] -> --config 1..5 (3 is the headline and the default; "4le" is the LinearElasticity half of
-# configs[3], at the largest n whose matrix fits int32 nnz - StiffnessMatrix uses int indices unless POLYSOLVE_LARGE_INDEX).
+# configs[3]: 1.43 G nnz, 11.5 GB of values[]; --flags 32 hands the pattern out with int64 indices, POLYSOLVE_LARGE_INDEX).
 #   mode: nl     fused energy + gradient + Hessian (pfa_grad_hess)
 #         linear LinearAssembler::assemble (pfa_linear_stiffness)
 #         euler  one implicit-Euler Newton assembly: dt^2-weighted elastic form + InertiaForm on the mass matrix
@@ -48,7 +48,7 @@ CONFIGS = {
     "2": dict(material="NeoHookean", p=1, n=44, mode="nl", cpu_n=30, what="fused energy+gradient+Hessian (pfa_grad_hess)"),
     "3": dict(material="NeoHookean", p=2, n=69, mode="nl", cpu_n=24, what="fused energy+gradient+Hessian (pfa_grad_hess)"),
     "4": dict(material="Laplacian", p=4, n=32, mode="linear", cpu_n=8, what="stiffness assembly (pfa_linear_stiffness)"),
-    "4le": dict(material="LinearElasticity", p=4, n=16, mode="linear", cpu_n=5, what="stiffness assembly (pfa_linear_stiffness)"),
+    "4le": dict(material="LinearElasticity", p=4, n=32, mode="linear", cpu_n=5, what="stiffness assembly (pfa_linear_stiffness)"),
     "5": dict(material="NeoHookean", p=1, n=119, mode="euler", cpu_n=30,
               what="implicit-Euler Newton assembly: dt^2-weighted pfa_grad_hess_weighted + pfa_inertia + H = dt^2 H_el + M"),
 }
@@ -570,8 +570,8 @@ def main():
 
     # e2e through the C ABI with pinned HOST buffers (H2D x, D2H E + grad + values every step)
     e2e = None
-    if args.e2e_steps <= 0:
-        e2e = None
+    if args.e2e_steps <= 0 or 8 * h.nnz > (8 << 30):
+        e2e = None  # (values[] beyond 8 GB: no pinned host copy of it here)
     elif world == 1 and mode != "euler":
         xh = torch.from_numpy(x_loc).pin_memory()
         eh = torch.zeros(1, dtype=torch.float64).pin_memory()
