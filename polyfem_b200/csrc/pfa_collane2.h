@@ -268,6 +268,16 @@ namespace pfa
 					const int ba = bucket(a), bb = bucket(b);
 					return ba != bb ? ba < bb : n_inc(a) > n_inc(b);
 				});
+			// chunk size: the requested number of steps, but never so large that a launch has fewer than ~16 chunks per resident
+			// warp (148 SMs x 8 warps): short schedules (a rank of an 8-GPU run) would otherwise end in an unbalanced tail
+			{
+				int64_t est_steps = 0;
+				for (int c = 0; c < 2; ++c)
+					for (int b : order[c])
+						est_steps += (n_inc(b) + 1) / 2;
+				est_steps /= kNodes;
+				chunk_steps = int(std::max<int64_t>(8, std::min<int64_t>(chunk_steps, est_steps / (148 * 8 * 16))));
+			}
 			S.grp_off.push_back(0);
 			S.chunk_off.push_back(0);
 			std::vector<uint8_t> seen;
