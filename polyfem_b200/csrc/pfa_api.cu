@@ -689,6 +689,13 @@ extern "C"
 						h->cl.n_steps[c] = S.n_steps[c];
 					}
 					h->cl.n_record_elements = int32_t(ngeo);
+					double za = 0.0, zb = 0.0;
+					if (cl2::p2_rule_weights(d->ref_grads, m.n_loc, m.n_qp, za, zb))
+					{
+						h->cl.p2z = 1;
+						h->cl.z4b = 4.0 * zb;
+						h->cl.zbeta = 4.0 * (za - zb);
+					}
 					h->cl_partial = d->owned_nodes != nullptr;
 					h->cl.enabled = 1;
 					PFA_CREATE_CUDA(cudaStreamSynchronize(h->stream)); // S is a local

@@ -189,7 +189,7 @@ namespace pfa
 #ifndef PFA_CL2_MINBLOCKS
 #define PFA_CL2_MINBLOCKS 1 // CTAs (= warps) per SM the register allocation must allow (experiments: 12 caps at 168 registers)
 #endif
-		template <int NL, int NQ, int SLOT, bool P2S>
+		template <int NL, int NQ, int SLOT, int MODE>
 		__global__ void __launch_bounds__(32, PFA_CL2_MINBLOCKS) cl2_columns_kernel(const DeviceMesh m, const AssembleArgs a, const ColumnLane2Tables t, const int cls, const int chunk_begin,
 																 const int chunk_end, const int strip_rows)
 		{
@@ -332,7 +332,7 @@ namespace pfa
 					if (busy)
 					{
 						const int ri = (w0.w >> 16) & 0xff;
-						column_of_element<NL, NQ, P2S>(stage + buf * L::STAGE + tr * RECD, s_rg + ri * (NQ * 4), mm, ConstTable<SLOT>(), acc, g_acc);
+						column_of_element<NL, NQ, MODE>(stage + buf * L::STAGE + tr * RECD, s_rg + ri * (NQ * 4), mm, ConstTable<SLOT>(), acc, g_acc, t.z4b, t.zbeta);
 					}
 					__syncwarp(); // every lane has read its record: the buffer can be refilled
 					const bool group_ends = s + 1 == g_last;
@@ -465,7 +465,7 @@ namespace pfa
 			return cudaMemcpyToSymbolAsync(c_cl2_refgrad, g_cl2_shadow[dev][slot], bytes, sizeof(double) * size_t(slot) * kSlotDoubles, cudaMemcpyHostToDevice, st);
 		}
 
-		template <int NL, int NQ, int SLOT, bool P2S>
+		template <int NL, int NQ, int SLOT, int MODE>
 		cudaError_t launch_cl2(const DeviceMesh &m, const AssembleArgs &a, const ColumnLane2Tables &t, int sm_count, cudaStream_t st, int *launches)
 		{
 			cudaError_t err = ensure_table(m, SLOT, st);
@@ -497,7 +497,7 @@ namespace pfa
 				return cudaSuccess;
 			if ((err = cudaMemsetAsync(t.counters, 0, 2 * sizeof(int), st)) != cudaSuccess)
 				return err;
-			auto kern = cl2_columns_kernel<NL, NQ, SLOT, P2S>;
+			auto kern = cl2_columns_kernel<NL, NQ, SLOT, MODE>;
 			int dev = 0, smem_max = 0;
 			if ((err = cudaGetDevice(&dev)) != cudaSuccess || (err = cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev)) != cudaSuccess)
 				return err;
@@ -542,8 +542,12 @@ namespace pfa
 	cudaError_t launch_column_lane2(const DeviceMesh &m, const AssembleArgs &a, const ColumnLane2Tables &t, int sm_count, cudaStream_t st, int *launches)
 	{
 		if (m.n_loc == 4)
-			return launch_cl2<4, 1, 0, false>(m, a, t, sm_count, st, launches);
-		// the structured column step needs the structural zeros of the P2 reference gradients (DeviceMesh::p2_structured)
-		return m.p2_structured ? launch_cl2<10, 4, 1, true>(m, a, t, sm_count, st, launches) : launch_cl2<10, 4, 1, false>(m, a, t, sm_count, st, launches);
+			return launch_cl2<4, 1, 0, 0>(m, a, t, sm_count, st, launches);
+		// entry step: vertex-weighted sums when the table is the P2 basis on the symmetric 4-point rule (p2_rule_weights),
+		// else the structural zeros of the P2 reference gradients (DeviceMesh::p2_structured), else the plain table
+		static const bool no_z = [] { const char *v = std::getenv("PFA_CL_NO_P2Z"); return v && std::atoi(v) != 0; }(); // experiments
+		if (t.p2z && !no_z)
+			return launch_cl2<10, 4, 1, 2>(m, a, t, sm_count, st, launches);
+		return m.p2_structured ? launch_cl2<10, 4, 1, 1>(m, a, t, sm_count, st, launches) : launch_cl2<10, 4, 1, 0>(m, a, t, sm_count, st, launches);
 	}
 } // namespace pfa

@@ -130,10 +130,20 @@ namespace pfa
 		//   acc[j][s] += H[(j, (mm + s) % 3), (ri, mm)]   (the column, by symmetry the row; rotated by mm)     g_row += G[(ri, mm)]
 		// rec: the element record; gri[q*4 + c]: reference gradient of the lane's own local node ri at point q (row of a padded
 		// table); G: reference gradients of all nodes with a uniform index (device: __constant__ memory).
-		// P2S: the table has the structural zeros / equal components of the P2 tet basis (p2_table_structured).
-		template <int NL, int NQ, bool P2S, class CTab>
-		PFA2_HD void column_of_element(const double *rec, const double *gri, int mm, const CTab &G, double (*acc)[3], double &g_row)
+		// MODE 0: any table. MODE 1 (P2S): the table has the structural zeros / equal components of the P2 tet basis
+		// (p2_table_structured): 20 instead of 30 FP64 operations per (component, point). MODE 2 (P2Z): the table is the P2 Lagrange
+		// basis on the symmetric 4-point rule (p2_rule_weights): the barycentric coordinates of point q are zb everywhere except za
+		// at vertex 3 - q, so with S = sum_q Y_q and V_v = 4 zb S + 4 (za - zb) Y_{3-v} (= 4 sum_q lambda_v(q) Y_q)
+		//   vertex node v:  grad lambda_v . (V_v - S),     edge node (a, b):  grad lambda_b . V_a + grad lambda_a . V_b,
+		// and grad lambda = (-1,-1,-1), e_x, e_y, e_z turns every dot product into a pick or a sum: 54 operations per component
+		// for all four points instead of 80, and no table loads. z4b = 4 zb, zbeta = 4 (za - zb).
+		template <int NL, int NQ, int MODE, class CTab>
+		PFA2_HD void column_of_element(const double *rec, const double *gri, int mm, const CTab &G, double (*acc)[3], double &g_row, double z4b = 0.0,
+									   double zbeta = 0.0)
 		{
+			constexpr bool P2S = MODE == 1;
+			constexpr bool P2Z = MODE == 2 && NL == 10 && NQ == 4;
+			double Yq[P2Z ? NQ : 1][3][3];
 			const double K00 = rec[NQ * kQpRec + 0], K01 = rec[NQ * kQpRec + 1], K02 = rec[NQ * kQpRec + 2];
 			const double K11 = rec[NQ * kQpRec + 3], K12 = rec[NQ * kQpRec + 4], K22 = rec[NQ * kQpRec + 5];
 			// rows mm, mm+1, mm+2 (mod 3) of A: lane-dependent offsets into the record (the three lanes of a triple read the three
@@ -178,7 +188,16 @@ namespace pfa
 				Y[2][0] = fma(cA, c2[0], r1[2] * s1 - r1[1] * s2); // -A[mm+1] x (c2t g)
 				Y[2][1] = fma(cA, c2[1], r1[0] * s2 - r1[2] * s0);
 				Y[2][2] = fma(cA, c2[2], r1[1] * s0 - r1[0] * s1);
-				if constexpr (P2S && NL == 10)
+				if constexpr (P2Z)
+				{
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+					for (int n = 0; n < 3; ++n)
+						for (int c = 0; c < 3; ++c)
+							Yq[qq][n][c] = Y[n][c];
+				}
+				else if constexpr (P2S && NL == 10)
 				{
 					const int o = qq * NL * 3;
 #if defined(__CUDA_ARCH__)
@@ -214,6 +233,72 @@ namespace pfa
 					}
 				}
 			}
+			if constexpr (P2Z)
+			{
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+				for (int n = 0; n < 3; ++n)
+				{
+					double S[3], V[4][3], sV[4];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+					for (int c = 0; c < 3; ++c)
+					{
+						S[c] = (Yq[0][n][c] + Yq[1][n][c]) + (Yq[2][n][c] + Yq[3][n][c]);
+						const double b4 = z4b * S[c];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+						for (int v = 0; v < 4; ++v)
+							V[v][c] = fma(zbeta, Yq[3 - v][n][c], b4); // point 3 - v carries the weight za at vertex v
+					}
+					for (int v = 0; v < 4; ++v)
+						sV[v] = V[v][0] + V[v][1] + V[v][2];
+					const double sS = S[0] + S[1] + S[2];
+					acc[0][n] += sS - sV[0];            // vertex 0: grad lambda_0 = -(1, 1, 1)
+					acc[1][n] += V[1][0] - S[0];        // vertex 1: e_x
+					acc[2][n] += V[2][1] - S[1];        // vertex 2: e_y
+					acc[3][n] += V[3][2] - S[2];        // vertex 3: e_z
+					acc[4][n] += V[0][0] - sV[1];       // edge (0, 1)
+					acc[5][n] += V[1][1] + V[2][0];     // edge (1, 2)
+					acc[6][n] += V[0][1] - sV[2];       // edge (2, 0)
+					acc[7][n] += V[0][2] - sV[3];       // edge (0, 3)
+					acc[8][n] += V[1][2] + V[3][0];     // edge (1, 3)
+					acc[9][n] += V[2][2] + V[3][1];     // edge (2, 3)
+				}
+			}
+		}
+
+		// The P2 Lagrange basis on the symmetric 4-point tet rule: true when ref_grads[4][10][3] equals, to 1e-14, the gradients
+		// generated from barycentric coordinates that are zb at every vertex except za at vertex 3 - q (the reference's point order,
+		// quadrature/TetQuadrature.cpp with auto_tetrahedron.ipp order 2); returns za, zb.
+		inline bool p2_rule_weights(const double *g, int n_loc, int n_qp, double &za, double &zb)
+		{
+			if (n_loc != 10 || n_qp != 4 || g == nullptr)
+				return false;
+			// lambda_1 = (d phi_1 / dx + 1) / 4 at point 0 (where vertex 3 carries za) is zb; at point 2 it is za
+			zb = (g[(0 * 10 + 1) * 3 + 0] + 1.0) / 4.0;
+			za = (g[(2 * 10 + 1) * 3 + 0] + 1.0) / 4.0;
+			static const int ev[6][2] = {{0, 1}, {1, 2}, {2, 0}, {0, 3}, {1, 3}, {2, 3}};
+			static const double gl[4][3] = {{-1, -1, -1}, {1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
+			for (int q = 0; q < 4; ++q)
+			{
+				double lam[4];
+				for (int v = 0; v < 4; ++v)
+					lam[v] = v == 3 - q ? za : zb;
+				if (std::fabs(lam[0] + lam[1] + lam[2] + lam[3] - 1.0) > 1e-14)
+					return false;
+				for (int j = 0; j < 10; ++j)
+					for (int c = 0; c < 3; ++c)
+					{
+						const double want = j < 4 ? (4.0 * lam[j] - 1.0) * gl[j][c] : 4.0 * (lam[ev[j - 4][0]] * gl[ev[j - 4][1]][c] + lam[ev[j - 4][1]] * gl[ev[j - 4][0]][c]);
+						if (std::fabs(g[(q * 10 + j) * 3 + c] - want) > 1e-14)
+							return false;
+					}
+			}
+			return true;
 		}
 
 		// ---- host side: which lane triple works on which (element, node) incidence, in which order ----

@@ -96,6 +96,8 @@ namespace pfa
 		int *counters = nullptr;            // [2] chunk hand-out of the two launches
 		const double *rg_padded = nullptr;  // [n_loc][n_qp][4] own-node reference gradients, padded rows
 		int64_t n_steps[2] = {0, 0}; // steps of the two classes (their share of the work)
+		int32_t p2z = 0;             // the reference table is the P2 basis on the symmetric 4-point rule (cl2::p2_rule_weights)
+		double z4b = 0.0, zbeta = 0.0; // 4 zb, 4 (za - zb)
 	};
 	bool column_lane2_applies(int material, int n_loc, int n_qp);
 	size_t column_lane2_record_doubles(int n_qp);

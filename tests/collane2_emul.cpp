@@ -20,11 +20,14 @@ namespace
 		double operator[](int i) const { return p[i]; }
 	};
 
-	template <int NL, int NQ, bool P2S>
+	template <int NL, int NQ, int MODE>
 	int emulate(int n_el, int n_bases, const int32_t *conn, const int32_t *adj_off, const int32_t *adj, const double *jit, const double *detj,
 				const double *qw, const double *ref_grads, const double *lam, const double *mu, int mstride, const double *x, int small_rows,
 				int chunk_steps, const uint8_t *owned, double scale, double *energy, double *grad, double *values, int64_t *stats)
 	{
+		double za = 0.0, zb = 0.0;
+		if (MODE == 2 && !p2_rule_weights(ref_grads, NL, NQ, za, zb))
+			return -9;
 		const int bucket_elements = chunk_steps % 7 == 3 ? 5 : (1 << 30); // some test cases exercise the spatial buckets of the schedule
 		constexpr int RECD = Rec<NQ>::D;
 		const HostTable G{ref_grads};
@@ -99,7 +102,7 @@ namespace
 									acc[j][sft] = (half == 0 && !first[j]) ? strip[size_t(krow[j] + n) * kStripLd + within] : 0.0;
 								}
 							}
-							column_of_element<NL, NQ, P2S>(rec.data() + size_t(e) * RECD, rgp.data() + size_t(ri) * NQ * 4, mm, G, acc, g_acc[lane]);
+							column_of_element<NL, NQ, MODE>(rec.data() + size_t(e) * RECD, rgp.data() + size_t(ri) * NQ * 4, mm, G, acc, g_acc[lane], 4.0 * zb, 4.0 * (za - zb));
 							for (int j = 0; j < NL; ++j)
 								for (int sft = 0; sft < 3; ++sft)
 								{
@@ -158,13 +161,16 @@ extern "C" int collane2_emulate(int n_loc, int n_qp, int n_el, int n_bases, cons
 								  double *energy, double *grad, double *values, int64_t *stats)
 {
 	if (n_loc == 4 && n_qp == 1)
-		return emulate<4, 1, false>(n_el, n_bases, conn, adj_off, adj, jit, detj, qw, ref_grads, lam, mu, mstride, x, small_rows, chunk_steps, owned, scale, energy,
+		return emulate<4, 1, 0>(n_el, n_bases, conn, adj_off, adj, jit, detj, qw, ref_grads, lam, mu, mstride, x, small_rows, chunk_steps, owned, scale, energy,
+									grad, values, stats);
+	if (n_loc == 10 && n_qp == 4 && structured == 2)
+		return emulate<10, 4, 2>(n_el, n_bases, conn, adj_off, adj, jit, detj, qw, ref_grads, lam, mu, mstride, x, small_rows, chunk_steps, owned, scale, energy,
 									grad, values, stats);
 	if (n_loc == 10 && n_qp == 4 && structured)
-		return emulate<10, 4, true>(n_el, n_bases, conn, adj_off, adj, jit, detj, qw, ref_grads, lam, mu, mstride, x, small_rows, chunk_steps, owned, scale, energy,
+		return emulate<10, 4, 1>(n_el, n_bases, conn, adj_off, adj, jit, detj, qw, ref_grads, lam, mu, mstride, x, small_rows, chunk_steps, owned, scale, energy,
 									grad, values, stats);
 	if (n_loc == 10 && n_qp == 4)
-		return emulate<10, 4, false>(n_el, n_bases, conn, adj_off, adj, jit, detj, qw, ref_grads, lam, mu, mstride, x, small_rows, chunk_steps, owned, scale, energy,
+		return emulate<10, 4, 0>(n_el, n_bases, conn, adj_off, adj, jit, detj, qw, ref_grads, lam, mu, mstride, x, small_rows, chunk_steps, owned, scale, energy,
 									 grad, values, stats);
 	return -1;
 }
