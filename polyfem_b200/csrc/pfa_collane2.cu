@@ -152,7 +152,8 @@ namespace pfa
 			asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
 		}
 		__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-		__device__ __forceinline__ void cp_async_wait_1() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
+		template <int N>
+		__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 		// Record staging, measured on B200 (profiles/clvar_r02f.jsonl): TMA bulk copies (one elected issue per triple, completion
 		// on an mbarrier) and cp.async (16 bytes per lane and instruction) are equally fast for the 432-byte P2 records
@@ -172,12 +173,15 @@ namespace pfa
 		{
 			static constexpr int RECD = Rec<NQ>::D;
 			static constexpr int STAGE = kTriples * RECD; // one buffer: 10 element records (each 16-byte aligned: RECD is even)
-			static constexpr int STAGES = 2;              // buffers: copies are issued two steps ahead
+			// record buffers = how many steps ahead the copies are issued: 2 for the 432-byte P2 records (shared memory is what
+			// limits the resident warps there), 4 for the 144-byte P1 records, whose steps are too short to cover the latency of the
+			// schedule-word load and of the copy with two
+			static constexpr int STAGES = NQ > 1 ? 2 : 4;
 			static constexpr int TB = kFlushRows * kTbLd; // transposition block of the flush
 			// the flush of a group runs after the last step of the group has consumed its records and before that buffer is
 			// refilled: when a buffer is large enough (P2) the transposition block lives there
 			static constexpr bool TB_ALIAS = STAGE >= TB;
-			static constexpr int OFF_STAGE = 2; // after the 2 mbarriers
+			static constexpr int OFF_STAGE = (STAGES + 1) & ~1; // after the mbarriers (one per buffer)
 			static constexpr int OFF_TB = OFF_STAGE + STAGES * STAGE;
 			static constexpr int OFF_RG = OFF_TB + (TB_ALIAS ? 0 : ((TB + 1) & ~1));
 			static constexpr int OFF_INFO = OFF_RG + NL * NQ * 4; // 5 x 4 ints = 10 doubles
@@ -211,11 +215,12 @@ namespace pfa
 			double *s_rg = smem + L::OFF_RG;
 			int *s_info = reinterpret_cast<int *>(smem + L::OFF_INFO);
 			double *strip = smem + L::OFF_STRIP + within;
-			const uint32_t bar0 = smem_u32(smem), bar1 = bar0 + 8;
+			constexpr int D = L::STAGES;
+			const uint32_t bar0 = smem_u32(smem); // mbarrier of buffer b at bar0 + 8 b
 			if (lane == 0)
 			{
-				mbar_init(bar0, 1);
-				mbar_init(bar1, 1);
+				for (int b = 0; b < D; ++b)
+					mbar_init(bar0 + 8 * b, 1);
 				asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 			}
 			// own-node reference gradients, padded rows [ri][q][4]
@@ -236,7 +241,7 @@ namespace pfa
 						return;
 					const bool want = leader && w.x != kIdle;
 					const unsigned mask = __ballot_sync(kFull, want);
-					const uint32_t bar = buf ? bar1 : bar0;
+					const uint32_t bar = bar0 + 8 * buf;
 					if (lane == 0)
 						mbar_arrive_expect_tx(bar, uint32_t(__popc(mask)) * REC_BYTES);
 					__syncwarp();
@@ -259,7 +264,7 @@ namespace pfa
 				}
 			};
 
-			unsigned it = 0; // steps this warp has consumed: buffer = it & 1, barrier parity = (it >> 1) & 1
+			unsigned it = 0; // steps this warp has consumed: buffer = it % D, barrier parity = (it / D) & 1
 			for (;;)
 			{
 				int chunk = 0;
@@ -279,17 +284,22 @@ namespace pfa
 				int4 info_n = (active && g + 1 < g_end) ? grp_info[size_t(g + 1) * kNodes + ns] : make_int4(-1, 0, 0, 0);
 				int rows_n = g + 1 < g_end ? t.grp_rows[g + 1] : 0;
 				int last_n = g + 1 < g_end ? t.grp_off[g + 2] : 0;
-				uint4 w0 = active ? inc[size_t(s_begin) * kTriples + tr] : idle;
-				uint4 w1 = (active && s_begin + 1 < s_end) ? inc[size_t(s_begin + 1) * kTriples + tr] : idle;
-				issue(w0, int(it & 1), true);
-				issue(w1, int((it + 1) & 1), s_begin + 1 < s_end);
+				// schedule words of this triple: W[0] = the current step ... W[D] = the step whose copies are issued during the current
+				// one; the word of step s + D + 1 is loaded during step s, a whole step before it is needed
+				uint4 W[D + 1];
+#pragma unroll
+				for (int k = 0; k <= D; ++k)
+					W[k] = (active && s_begin + k < s_end) ? inc[size_t(s_begin + k) * kTriples + tr] : idle;
+#pragma unroll
+				for (int k = 0; k < D; ++k)
+					issue(W[k], int((it + k) % D), s_begin + k < s_end);
 				double g_acc = 0.0;
 				for (int s = s_begin; s < s_end; ++s, ++it)
 				{
-					const int buf = int(it & 1);
-					// the step whose copies are issued during this step (two steps ahead): its words are needed then
-					const uint4 w2 = (active && s + 2 < s_end) ? inc[size_t(s + 2) * kTriples + tr] : idle;
-					const bool issue_real = s + 2 < s_end;
+					const int buf = int(it % D);
+					const uint4 w_next = (active && s + D + 1 < s_end) ? inc[size_t(s + D + 1) * kTriples + tr] : idle;
+					const uint4 w0 = W[0], w2 = W[D];
+					const bool issue_real = s + D < s_end;
 					const bool busy = active && w0.x != kIdle;
 					// strip offsets of the NL row positions of this element (doubles, relative to my column); bit 7 of a position byte:
 					// first contribution to these rows
@@ -319,14 +329,14 @@ namespace pfa
 					}
 					if constexpr (TMA)
 					{
-						const uint32_t bar = buf ? bar1 : bar0, parity = (it >> 1) & 1;
+						const uint32_t bar = bar0 + 8 * buf, parity = (it / D) & 1;
 						while (!mbar_try_wait(bar, parity))
 						{
 						}
 					}
 					else
 					{
-						cp_async_wait_1(); // my copies of this step have landed (only the next step's group may be pending)
+						cp_async_wait<D - 1>(); // my copies of this step have landed (only the groups of later steps may be pending)
 						__syncwarp();      // ... and so have the other lanes'
 					}
 					if (busy)
@@ -377,8 +387,10 @@ namespace pfa
 						}
 					}
 					__syncwarp();
-					w0 = w1;
-					w1 = w2;
+#pragma unroll
+					for (int k = 0; k < D; ++k)
+						W[k] = W[k + 1];
+					W[D] = w_next;
 					if (group_ends)
 					{
 						// ---- group finished: gradient entries and the 15 columns ----
