@@ -167,16 +167,23 @@ namespace pfa
 		constexpr bool kUseTma = NQ > 1;
 #endif
 
+#ifndef PFA_CL2_P1_STAGES
+#define PFA_CL2_P1_STAGES 4 // record buffers of the P1 kernel (experiments: 6, 8)
+#endif
 		// shared memory of the one-warp CTA, in doubles
 		template <int NL, int NQ>
 		struct WarpLayout
 		{
 			static constexpr int RECD = Rec<NQ>::D;
-			static constexpr int STAGE = kTriples * RECD; // one buffer: 10 element records (each 16-byte aligned: RECD is even)
+			// slot stride of a record inside a buffer (16-byte aligned: RECD is even). (Padding the 144-byte P1 record to 176 bytes
+			// so that the 16-byte cp.async writes of the ten triples spread over the bank groups - 4 instead of 20 wavefronts per
+			// instruction in ncu - did not change the P1 time: 0.203 / 0.202 ms at cfg 2, profiles/clvar_r02s.jsonl.)
+			static constexpr int SSTR = RECD;
+			static constexpr int STAGE = kTriples * SSTR; // one buffer: 10 element records
 			// record buffers = how many steps ahead the copies are issued: 2 for the 432-byte P2 records (shared memory is what
 			// limits the resident warps there), 4 for the 144-byte P1 records, whose steps are too short to cover the latency of the
 			// schedule-word load and of the copy with two
-			static constexpr int STAGES = NQ > 1 ? 2 : 4;
+			static constexpr int STAGES = NQ > 1 ? 2 : PFA_CL2_P1_STAGES;
 			static constexpr int TB = kFlushRows * kTbLd; // transposition block of the flush
 			// the flush of a group runs after the last step of the group has consumed its records and before that buffer is
 			// refilled: when a buffer is large enough (P2) the transposition block lives there
@@ -246,7 +253,7 @@ namespace pfa
 						mbar_arrive_expect_tx(bar, uint32_t(__popc(mask)) * REC_BYTES);
 					__syncwarp();
 					if (want)
-						tma_load(stage_u32 + uint32_t(buf * L::STAGE + tr * RECD) * 8u, t.records + size_t(w.x) * RECD, REC_BYTES, bar);
+						tma_load(stage_u32 + uint32_t(buf * L::STAGE + tr * L::SSTR) * 8u, t.records + size_t(w.x) * RECD, REC_BYTES, bar);
 				}
 				else
 				{
@@ -255,7 +262,7 @@ namespace pfa
 					if (real && active && w.x != kIdle)
 					{
 						const char *src = reinterpret_cast<const char *>(t.records + size_t(w.x) * RECD) + mm * 16;
-						const uint32_t dst = stage_u32 + uint32_t(buf * L::STAGE + tr * RECD) * 8u + uint32_t(mm) * 16u;
+						const uint32_t dst = stage_u32 + uint32_t(buf * L::STAGE + tr * L::SSTR) * 8u + uint32_t(mm) * 16u;
 #pragma unroll
 						for (int i = 0; i < RECD / 6; ++i)
 							cp_async16(dst + i * 48, src + i * 48);
@@ -342,7 +349,7 @@ namespace pfa
 					if (busy)
 					{
 						const int ri = (w0.w >> 16) & 0xff;
-						column_of_element<NL, NQ, MODE>(stage + buf * L::STAGE + tr * RECD, s_rg + ri * (NQ * 4), mm, ConstTable<SLOT>(), acc, g_acc, t.z4b, t.zbeta);
+						column_of_element<NL, NQ, MODE>(stage + buf * L::STAGE + tr * L::SSTR, s_rg + ri * (NQ * 4), mm, ConstTable<SLOT>(), acc, g_acc, t.z4b, t.zbeta);
 					}
 					__syncwarp(); // every lane has read its record: the buffer can be refilled
 					const bool group_ends = s + 1 == g_last;
