@@ -145,7 +145,7 @@ namespace
 		return v ? std::atoi(v) : dflt;
 	}
 	const int kSmallRows = env_int("PFA_CL_SMALL_ROWS", 96);
-	const int kChunkSteps = env_int("PFA_CL_CHUNK_STEPS", 48);
+	const int kChunkSteps = env_int("PFA_CL_CHUNK_STEPS", 24);
 	const int kBucketElements = env_int("PFA_CL_BUCKET", 16384); // 7 MB of P2 records per bucket
 	constexpr int kRestBatchQuota = PFA_REST_BATCH_QUOTA; // pfa_grad_hess_part(PFA_PART_REST): warp batches per warp
 

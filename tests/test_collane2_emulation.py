@@ -177,3 +177,18 @@ def test_scale_chunks_and_per_quadrature_point_materials(emul, oracle):
     assert abs(e - 0.25 * prob.assemble_energy(x)) <= REL_TOL * abs(e)
     assert_vector_close(g, 0.25 * prob.assemble_gradient(x))
     assert_values_close(H.outer, H.inner, v, 0.25 * H.values)
+
+
+@pytest.mark.parametrize("p,structured", [(1, 0), (2, 2)])
+def test_unstructured_mesh(emul, oracle, p, structured):
+    """A Delaunay mesh with elements in random order: vertex valences from 1 to 30+ incident tets, odd incidence counts (idle
+    half-steps), node degrees the Kuhn cube does not have."""
+    from unstructured import delaunay_mesh
+    mesh = delaunay_mesh(150, p)
+    x = 0.02 * np.random.default_rng(1).uniform(-1, 1, mesh.n_bases * 3) * mesh.h
+    prob, e, g, v, stats = run_emulation(emul, oracle, mesh, x, 96, structured, chunk_steps=10)
+    H = prob.assemble_hessian(x)
+    assert not np.isnan(v).any() and stats[5] == mesh.n_elements * mesh.conn.shape[1]
+    assert abs(e - prob.assemble_energy(x)) <= REL_TOL * abs(e)
+    assert_vector_close(g, prob.assemble_gradient(x))
+    assert_values_close(H.outer, H.inner, v, H.values)

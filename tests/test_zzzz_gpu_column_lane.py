@@ -53,3 +53,26 @@ def test_column_lane_nan_propagation(oracle):
     assert_vector_close(g, ref.assemble_gradient(xi))
     H = ref.assemble_hessian(xi)
     assert_values_close(H.outer, H.inner, v, H.values)
+
+
+@pytest.mark.parametrize("p,n_points", [(1, 400), (2, 250)])
+def test_unstructured_mesh_on_the_gpu(oracle, p, n_points):
+    """Delaunay mesh, elements in random order (tests/unstructured.py): irregular valences, both strip classes, idle half-steps."""
+    from polyfem_b200 import tables
+    from unstructured import delaunay_mesh
+    mesh = delaunay_mesh(n_points, p)
+    t = tables.reference_tables(p)
+    x = 0.02 * np.random.default_rng(1).uniform(-1, 1, mesh.n_bases * 3) * mesh.h
+    ref = oracle.problem_from_mesh(mesh, "NeoHookean", n_threads=4)
+    h = gpu_handle(mesh, "NeoHookean", t)
+    h.profile_enable(True)
+    e, g, v = h.grad_hess(x)
+    assert any("column_lane" in k for (k, ms) in h.profile_read())
+    H = ref.assemble_hessian(x)
+    outer, inner = h.pattern()
+    assert outer.tobytes() == H.outer.tobytes() and inner.tobytes() == H.inner.tobytes()
+    assert abs(e - ref.assemble_energy(x)) <= REL_TOL * abs(e)
+    assert_vector_close(g, ref.assemble_gradient(x))
+    assert_values_close(H.outer, H.inner, v, H.values)
+    e2, g2, v2 = h.grad_hess(x)
+    assert e2 == e and np.array_equal(g2, g) and np.array_equal(v2, v)
