@@ -366,7 +366,7 @@ namespace
 		if (ce == cudaErrorNotSupported)
 		{
 			cudaGetLastError();
-			return fail(h, PFA_ERR_UNSUPPORTED, project_to_psd ? "project_to_psd needs 2 N (N|1) doubles of shared memory per warp with N = 3 n_loc even: P1..P3 elements (P4: N = 105)"
+			return fail(h, PFA_ERR_UNSUPPORTED, project_to_psd ? "project_to_psd needs 2 N (N|1) doubles of shared memory per warp, N = 3 n_loc (rounded up to even) <= 128: P1..P4 tets, Q1/Q2 hexes"
 																: "this material / element type combination is not implemented");
 		}
 		if (ce != cudaSuccess)

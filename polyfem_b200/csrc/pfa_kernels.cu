@@ -179,6 +179,9 @@ namespace pfa
 		// SaintVenant uses the slots as: F[9] | P*da[9] | S*da[9] | - | mu*da | lambda*da | mu*da*F F^T (00 01 02 11 12 22)
 		constexpr int kQRec = 36;
 
+		// dimension of the local matrix as project_to_psd sees it: 3 n_loc, plus one zero row and column when that is odd
+		__host__ __device__ inline int psd_dim(int n_loc) { return 3 * n_loc + ((3 * n_loc) & 1); }
+
 		__host__ __device__ inline WarpLayout warp_layout(int n_loc, int n_qp, bool psd = false)
 		{
 			WarpLayout L;
@@ -199,8 +202,9 @@ namespace pfa
 			o += (3 * n_loc + 1) / 2;
 			if (psd)
 			{
-				// local matrix H and eigenvector matrix V [N][N|1], rotation parameters c, s [N/2] and pairs p, q [N/2] ints
-				const int N = 3 * n_loc, LD = N | 1, HALF = N / 2;
+				// local matrix H and eigenvector matrix V [Np][Np|1] (Np = N rounded up to even: the round-robin ordering pairs all
+				// indices), rotation parameters c, s [Np/2] and pairs p, q [Np/2] ints
+				const int N = psd_dim(n_loc), LD = N | 1, HALF = N / 2;
 				L.H = o;
 				o += N * LD;
 				L.V = o;
@@ -215,14 +219,22 @@ namespace pfa
 		}
 
 		// project_to_psd for the generic kernel (ipc::project_to_psd on the local Hessian, Assembler.cpp:693-694), any
-		// NLAssembler material with N = 3 n_loc even and N*(N|1) doubles x 2 of shared memory per warp (P1..P3): the local
+		// NLAssembler material whose 2 Np (Np|1) doubles fit the shared memory of one warp (Np = psd_dim: P1..P4 tets, Q1/Q2
+		// hexes). n = 3 n_loc is the size of the matrix; when n is odd the caller's N = n + 1 and row/column n is a zero
+		// padding (its rotations are identities, its eigenvalue 0 never counts as negative). The local
 		// matrix sH (lower triangle mirrored, as the eigen-solver reads one triangle) is diagonalised by a parallel cyclic
 		// Jacobi method (round-robin ordering: N/2 disjoint rotations per step; lanes loop over rows) and, if its smallest
 		// eigenvalue is negative, rebuilt as V max(D, 0) V^T. Non-finite and already-PSD matrices are left unchanged.
 		// Returns true when the matrix was changed (then sH holds the projected matrix); false: the caller keeps the original.
-		__device__ inline bool psd_project_warp(double *sH, double *sV, int N, int LD, int *sP, int *sQ, double *sC, double *sS, int lane)
+		__device__ inline bool psd_project_warp(double *sH, double *sV, int n, int N, int LD, int *sP, int *sQ, double *sC, double *sS, int lane)
 		{
 			const int HALF = N / 2;
+			if (N > n)
+			{
+				for (int k = lane; k < N; k += 32)
+					sH[n * LD + k] = sH[k * LD + n] = 0.0;
+				__syncwarp();
+			}
 			for (int r = lane; r < N; r += 32)
 				for (int c = r + 1; c < N; ++c)
 					sH[r * LD + c] = sH[c * LD + r];
@@ -588,8 +600,8 @@ namespace pfa
 					if (PSD && pass == 1)
 					{
 						__syncwarp();
-						psd_changed = psd_project_warp(ws + L.H, ws + L.V, 3 * n_loc, (3 * n_loc) | 1, reinterpret_cast<int *>(ws + L.PQ),
-													   reinterpret_cast<int *>(ws + L.PQ) + (3 * n_loc) / 2, ws + L.CS, ws + L.CS + (3 * n_loc) / 2, lane);
+						psd_changed = psd_project_warp(ws + L.H, ws + L.V, 3 * n_loc, psd_dim(n_loc), psd_dim(n_loc) | 1, reinterpret_cast<int *>(ws + L.PQ),
+													   reinterpret_cast<int *>(ws + L.PQ) + psd_dim(n_loc) / 2, ws + L.CS, ws + L.CS + psd_dim(n_loc) / 2, lane);
 					}
 					for (int b = lane; b < n_loc * n_loc; b += 32)
 					{
@@ -610,7 +622,7 @@ namespace pfa
 						if (PSD && pass == 1 && psd_changed)
 						{
 							const double *sH = ws + L.H;
-							const int LDh = (3 * n_loc) | 1;
+							const int LDh = psd_dim(n_loc) | 1;
 							for (int r = 0; r < 3; ++r)
 								for (int c = 0; c < 3; ++c)
 									blk[r * 3 + c] = sH[(i * 3 + r) * LDh + j * 3 + c];
@@ -701,7 +713,7 @@ namespace pfa
 						if (PSD && pass == 0)
 						{
 							double *sH = ws + L.H;
-							const int LDh = (3 * n_loc) | 1;
+							const int LDh = psd_dim(n_loc) | 1;
 							for (int r = 0; r < 3; ++r)
 								for (int c = 0; c < 3; ++c)
 									sH[(i * 3 + r) * LDh + j * 3 + c] = blk[r * 3 + c];
@@ -2043,14 +2055,12 @@ namespace pfa
 			return cudaGetLastError();
 		}
 
-		// project_to_psd through the generic kernel: one or two warps per CTA (the local matrices need 2 N (N|1) doubles per warp)
-		template <int MAT>
-		cudaError_t launch_generic_psd(const DeviceMesh &m, const AssembleArgs &a, int sm_count, cudaStream_t st)
+		// project_to_psd through the generic kernel: two warps per CTA, one when the two local matrices (2 Np (Np|1) doubles per
+		// warp) of two warps do not fit the shared memory
+		template <int MAT, int kW>
+		cudaError_t launch_generic_psd_w(const DeviceMesh &m, const AssembleArgs &a, int sm_count, cudaStream_t st)
 		{
-			if ((3 * m.n_loc) % 2 != 0 || 3 * m.n_loc > 128)
-				return cudaErrorNotSupported;
-			constexpr int kW = 2;
-			size_t smem = generic_smem_bytes(m.n_loc, m.n_qp, kW, true);
+			const size_t smem = generic_smem_bytes(m.n_loc, m.n_qp, kW, true);
 			if (smem > kMaxSmem)
 				return cudaErrorNotSupported;
 			auto kern = assemble_generic_kernel<MAT, false, kW, true>;
@@ -2064,6 +2074,16 @@ namespace pfa
 			const int grid = int(std::max<int64_t>(1, std::min<int64_t>(need, int64_t(sm_count) * std::max(per_sm, 1))));
 			kern<<<grid, kW * 32, smem, st>>>(m, a);
 			return cudaGetLastError();
+		}
+
+		template <int MAT>
+		cudaError_t launch_generic_psd(const DeviceMesh &m, const AssembleArgs &a, int sm_count, cudaStream_t st)
+		{
+			if (psd_dim(m.n_loc) > 128) // the diagonal of the rebuilt matrix is held in four registers per lane
+				return cudaErrorNotSupported;
+			if (generic_smem_bytes(m.n_loc, m.n_qp, 2, true) <= kMaxSmem)
+				return launch_generic_psd_w<MAT, 2>(m, a, sm_count, st);
+			return launch_generic_psd_w<MAT, 1>(m, a, sm_count, st);
 		}
 
 		template <int MAT, bool LINEAR>

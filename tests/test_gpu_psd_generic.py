@@ -1,5 +1,6 @@
 """project_to_psd (Assembler.cpp:693-694: ipc::project_to_psd on every local Hessian of an NLAssembler) beyond the NeoHookean
-P1 / P2 kernels of round 1: the generic kernel's projection for NeoHookean P3 and SaintVenant P1 .. P3, and LinearElasticity,
+P1 / P2 kernels of round 1: the generic kernel's projection for NeoHookean P3 / P4 and SaintVenant P1 .. P4 (P4: N = 105 is odd, the matrix is padded
+with a zero row and column for the round-robin Jacobi ordering, one warp per CTA), and LinearElasticity,
 where the flag has no effect (its element stiffness is PSD). The oracle's restatement (own Jacobi eigen-solver, pinned by
 hand-computed answers in tests/test_oracle_properties.py since ipc-toolkit's source is absent) is the checker; both are
 non-expansive maps of the same local matrices computed by different eigen-solvers, so the bar is 1e-10 of the row scale."""
@@ -11,7 +12,8 @@ from helpers import REL_TOL, assert_values_close, assert_vector_close, gpu_handl
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("material,p,n,scale", [("NeoHookean", 3, 2, 0.02), ("SaintVenant", 1, 4, 0.2), ("SaintVenant", 2, 3, 0.2), ("SaintVenant", 3, 2, 0.2)])
+@pytest.mark.parametrize("material,p,n,scale", [("NeoHookean", 3, 2, 0.02), ("SaintVenant", 1, 4, 0.2), ("SaintVenant", 2, 3, 0.2), ("SaintVenant", 3, 2, 0.2),
+                                                  ("NeoHookean", 4, 1, 0.02), ("SaintVenant", 4, 1, 0.2)])
 def test_generic_projection_equals_oracle(oracle, material, p, n, scale):
     mesh, x, t = make_case(n, p, jitter=0.1, scale=scale)
     x = x[: mesh.n_bases * 3]
@@ -33,7 +35,7 @@ def test_generic_projection_equals_oracle(oracle, material, p, n, scale):
     assert_values_close(H0.outer, H0.inner, h.hessian(z, project_to_psd=True), h.hessian(z), tol=1e-13, what="PSD state")
 
 
-def test_linear_elasticity_ignores_the_flag_and_p4_fails_loudly(oracle):
+def test_linear_elasticity_ignores_the_flag_and_p5_fails_loudly(oracle):
     from polyfem_b200 import capi
     mesh, x, t = make_case(3, 2, jitter=0.1)
     x = x[: mesh.n_bases * 3]
@@ -41,8 +43,14 @@ def test_linear_elasticity_ignores_the_flag_and_p4_fails_loudly(oracle):
     ref = oracle.problem_from_mesh(mesh, "LinearElasticity")
     H1 = ref.assemble_hessian(x, project_to_psd=True)
     assert_values_close(H1.outer, H1.inner, h.hessian(x, project_to_psd=True), H1.values, tol=1e-12, what="LinearElasticity, projected")
-    m4, x4, t4 = make_case(1, 4)
-    h4 = gpu_handle(m4, "NeoHookean", t4)
+    # a 44-node element (N = 132 > 128; P5 would be 168): the two local matrices do not fit the shared memory of an SM - refused,
+    # never silently unprojected. (Synthetic element: one cell, made-up gradients; the refusal comes before any launch.)
+    rng = np.random.default_rng(0)
+    nl, nq = 44, 4
+    conn = np.arange(nl, dtype=np.int32)[None, :]
+    verts = np.array([[[0, 0, 0], [1, 0, 0], [0, 1, 0], [0, 0, 1]]], dtype=np.float64)
+    lam, mu = 57692.3, 38461.5
+    h5 = capi.Handle("NeoHookean", conn, nl, np.full(nq, 1.0 / 24), rng.standard_normal((nq, nl, 3)), vertices=verts, lam=lam, mu=mu)
     with pytest.raises(capi.PfaError) as ei:
-        h4.hessian(np.zeros(h4.ndof), project_to_psd=True)
+        h5.hessian(np.zeros(h5.ndof), project_to_psd=True)
     assert ei.value.code == capi.PFA_ERR_UNSUPPORTED
