@@ -378,7 +378,7 @@ namespace pfa
 			return true;
 		}
 
-		template <int MAT, bool LINEAR, int kWarps, bool PSD = false>
+		template <int MAT, bool LINEAR, int kWarps, bool PSD = false, bool TABLES_SHARED = true>
 		__global__ void __launch_bounds__(kWarps * 32) assemble_generic_kernel(const DeviceMesh m, const AssembleArgs a)
 		{
 			extern __shared__ double smem[];
@@ -387,15 +387,22 @@ namespace pfa
 			const WarpLayout L = warp_layout(n_loc, n_qp, PSD);
 
 			// CTA-shared reference tables
-			double *s_rg = smem;                   // [n_qp][n_loc][3]
-			double *s_w = s_rg + n_qp * n_loc * 3; // [n_qp]
-			for (int t = threadIdx.x; t < n_qp * n_loc * 3; t += blockDim.x)
-				s_rg[t] = m.ref_grads[t];
-			for (int t = threadIdx.x; t < n_qp; t += blockDim.x)
-				s_w[t] = m.qweights[t];
-			__syncthreads();
-
-			double *ws = s_w + n_qp + warp * L.total;
+			// (TABLES_SHARED false: read through the cache from global memory instead - the P4 projection needs the space)
+			const double *s_rg = m.ref_grads; // [n_qp][n_loc][3]
+			const double *s_w = m.qweights;   // [n_qp]
+			double *ws = smem + warp * L.total;
+			if (TABLES_SHARED)
+			{
+				double *t_rg = smem, *t_w = smem + n_qp * n_loc * 3;
+				for (int t = threadIdx.x; t < n_qp * n_loc * 3; t += blockDim.x)
+					t_rg[t] = m.ref_grads[t];
+				for (int t = threadIdx.x; t < n_qp; t += blockDim.x)
+					t_w[t] = m.qweights[t];
+				__syncthreads();
+				s_rg = t_rg;
+				s_w = t_w;
+				ws = t_w + n_qp + warp * L.total;
+			}
 			double *sU = ws + L.U, *sD = ws + L.D, *sA = ws + L.A, *sQ = ws + L.Q, *sJ = ws + L.J, *sDA = ws + L.DA;
 			int *sG = reinterpret_cast<int *>(ws + L.I); // [n_loc] global node
 			int *sOff = sG + n_loc;                      // [n_loc] adj_off of that node
@@ -2020,10 +2027,10 @@ namespace pfa
 
 		constexpr size_t kMaxSmem = 227 * 1024;
 
-		size_t generic_smem_bytes(int n_loc, int n_qp, int warps, bool psd = false)
+		size_t generic_smem_bytes(int n_loc, int n_qp, int warps, bool psd = false, bool tables_shared = true)
 		{
 			const WarpLayout L = warp_layout(n_loc, n_qp, psd);
-			return sizeof(double) * (size_t(n_qp) * n_loc * 3 + n_qp + size_t(warps) * L.total);
+			return sizeof(double) * ((tables_shared ? size_t(n_qp) * n_loc * 3 + n_qp : size_t(0)) + size_t(warps) * L.total);
 		}
 
 		// warps per CTA: the largest of 8/4/2/1 whose staging fits in shared memory
@@ -2057,13 +2064,13 @@ namespace pfa
 
 		// project_to_psd through the generic kernel: two warps per CTA, one when the two local matrices (2 Np (Np|1) doubles per
 		// warp) of two warps do not fit the shared memory
-		template <int MAT, int kW>
+		template <int MAT, int kW, bool TABLES_SHARED>
 		cudaError_t launch_generic_psd_w(const DeviceMesh &m, const AssembleArgs &a, int sm_count, cudaStream_t st)
 		{
-			const size_t smem = generic_smem_bytes(m.n_loc, m.n_qp, kW, true);
+			const size_t smem = generic_smem_bytes(m.n_loc, m.n_qp, kW, true, TABLES_SHARED);
 			if (smem > kMaxSmem)
 				return cudaErrorNotSupported;
-			auto kern = assemble_generic_kernel<MAT, false, kW, true>;
+			auto kern = assemble_generic_kernel<MAT, false, kW, true, TABLES_SHARED>;
 			cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
 			if (err != cudaSuccess)
 				return err;
@@ -2076,14 +2083,18 @@ namespace pfa
 			return cudaGetLastError();
 		}
 
+		// two warps per CTA; one when the local matrices (2 Np (Np|1) doubles per warp) of two do not fit the shared memory; P4
+		// (23 points x 35 nodes) fits only with the reference tables left in global memory
 		template <int MAT>
 		cudaError_t launch_generic_psd(const DeviceMesh &m, const AssembleArgs &a, int sm_count, cudaStream_t st)
 		{
 			if (psd_dim(m.n_loc) > 128) // the diagonal of the rebuilt matrix is held in four registers per lane
 				return cudaErrorNotSupported;
 			if (generic_smem_bytes(m.n_loc, m.n_qp, 2, true) <= kMaxSmem)
-				return launch_generic_psd_w<MAT, 2>(m, a, sm_count, st);
-			return launch_generic_psd_w<MAT, 1>(m, a, sm_count, st);
+				return launch_generic_psd_w<MAT, 2, true>(m, a, sm_count, st);
+			if (generic_smem_bytes(m.n_loc, m.n_qp, 1, true) <= kMaxSmem)
+				return launch_generic_psd_w<MAT, 1, true>(m, a, sm_count, st);
+			return launch_generic_psd_w<MAT, 1, false>(m, a, sm_count, st);
 		}
 
 		template <int MAT, bool LINEAR>
