@@ -56,10 +56,14 @@ extern "C"
 		PFA_MASS = 3,              /* assembler/Mass.cpp (LinearAssembler, size 3): rho phi_i phi_j on the block diagonal; the
 		                            * mass matrix of InertiaForm. Needs ref_vals + density; quadrature is the
 		                            * mass rule of order 2p (AssemblerUtils.cpp:204-211). */
-		PFA_SAINT_VENANT = 4       /* assembler/SaintVenantElasticity.cpp, name() == "SaintVenant", with the isotropic elasticity
+		PFA_SAINT_VENANT = 4,      /* assembler/SaintVenantElasticity.cpp, name() == "SaintVenant", with the isotropic elasticity
 		                            * tensor of (lambda, mu) (MatParams.cpp:211-253): an ElasticityNLAssembler whose energy is
 		                            * differentiated by autodiff in the reference; here the closed forms
 		                            * P = F S, S = 2 mu E + lambda tr(E) I and its tangent. Any order P1..P4 (generic kernel). */
+		PFA_MOONEY_RIVLIN = 5      /* assembler/MooneyRivlinElasticity.hpp, name() == "MooneyRivlin" (GenericElastic, autodiff in the
+		                            * reference): psi = c1 (I1~ - 3) + c2 (I2~ - 3) + k/2 ln^2 J on the isochoric invariants. Parameters
+		                            * (c1, c2, k) = (lambda[], mu[], param3[]). Here: the chain rule over (I1, I2, J) of F in closed
+		                            * form (generic kernel, any order P1..P4). */
 	} pfa_material;
 
 	/* What the shim reads out of std::vector<basis::ElementBases> bases / gbases and the
@@ -117,6 +121,8 @@ extern "C"
 		 * values[] / grad[] untouched: no interface exchange, only the scalar energy (own elements) is summed over the ranks
 		 * by the caller. NULL = every node is owned. */
 		const uint8_t *owned_nodes;
+		/* third material parameter, laid out like lambda / mu (PFA_MOONEY_RIVLIN: k; NULL for the other materials) */
+		const double *param3;
 	} pfa_mesh_desc;
 
 /* pfa_mesh_desc.flags: keep the caller's element order internally (default: elements are
@@ -188,6 +194,8 @@ extern "C"
 
 	/* Re-upload Lame parameters when t changes (Assembler::set_materials, Assembler.cpp:97-151). */
 	int pfa_set_materials(pfa_handle *h, const double *lambda, const double *mu, int32_t material_stride);
+	/* the same for materials with three parameters (PFA_MOONEY_RIVLIN: c1, c2, k) */
+	int pfa_set_material_params(pfa_handle *h, const double *p1, const double *p2, const double *p3, int32_t material_stride);
 
 	/* NLAssembler::assemble_energy (Assembler.cpp:495-531) */
 	int pfa_energy(pfa_handle *h, const double *x, double *energy);

@@ -102,6 +102,15 @@ namespace
 		return r;
 	}
 
+	D1 pow(const D1 &a, double p)
+	{
+		D1 r(std::pow(a.v, p));
+		const double d1 = p * std::pow(a.v, p - 1.0);
+		for (int i = 0; i < g_nvars; ++i)
+			r.g[i] = d1 * a.g[i];
+		return r;
+	}
+
 	struct D2
 	{
 		double v = 0;
@@ -160,6 +169,19 @@ namespace
 		for (int i = 0; i < n; ++i)
 			for (int j = 0; j < n; ++j)
 				r.h[size_t(i) * n + j] = a.h[size_t(i) * n + j] / a.v - a.g[i] * a.g[j] / (a.v * a.v);
+		return r;
+	}
+
+	D2 pow(const D2 &a, double p)
+	{
+		const int n = g_nvars;
+		D2 r(std::pow(a.v, p));
+		const double d1 = p * std::pow(a.v, p - 1.0), d2 = p * (p - 1.0) * std::pow(a.v, p - 2.0);
+		for (int i = 0; i < n; ++i)
+			r.g[i] = d1 * a.g[i];
+		for (int i = 0; i < n; ++i)
+			for (int j = 0; j < n; ++j)
+				r.h[size_t(i) * n + j] = d1 * a.h[size_t(i) * n + j] + d2 * a.g[i] * a.g[j];
 		return r;
 	}
 
@@ -265,7 +287,7 @@ namespace
 		oracle_desc d;
 		int size = 3; // Assembler::size()
 		std::vector<int32_t> conn, lattice, geom_lattice;
-		std::vector<double> vertices, qpts, qw, ref_grads, lambda, mu, ref_vals, density, geom_nodes;
+		std::vector<double> vertices, qpts, qw, ref_grads, lambda, mu, param3, ref_vals, density, geom_nodes;
 		// AssemblyValsCache (AssemblyValsCache.cpp:11-67)
 		std::vector<ElementAssemblyValues> cache;
 
@@ -368,6 +390,7 @@ namespace
 		const double *x;
 		const std::vector<double> &da;
 		double lambda, mu; // params_.lambda_mu(...) for a per-element constant material
+		double param3 = 0.0; // MooneyRivlin: (c1, c2, k) = (lambda, mu, param3)
 	};
 
 	// =======================================================================================
@@ -771,6 +794,52 @@ namespace
 			energy = energy + tr * T(data.da[p]);
 		}
 		return energy * T(0.5);
+	}
+
+	// MooneyRivlinElasticity.hpp:26-47 elastic_energy inside GenericElastic::compute_energy_aux (GenericElastic.hpp:93-132):
+	// def_grad = I + grad u, J = det, F~ = def_grad / J^(1/3), C~ = F~ F~^T, I1~ = tr C~, I2~ = (tr^2 - tr(C~ C~)) / 2
+	// (utils/ElasticityUtils.hpp:139-150), val = c1 (I1~ - 3) + c2 (I2~ - 3) + k/2 ln^2 J; energy = sum_p val da_p.
+	// Gradient and Hessian by forward-mode autodiff over the local dofs (AutodiffType::FULL, GenericElastic.cpp:137-175).
+	template <typename T>
+	T mooney_rivlin_energy(const NLData &data)
+	{
+		using std::log;
+		using std::pow;
+		std::vector<T> local_disp;
+		get_local_disp<T>(data, 3, local_disp);
+		T energy = T(0.0);
+		T F[9];
+		const double c1 = data.lambda, c2 = data.mu, k = data.param3;
+		for (int p = 0; p < data.vals.n_qp; ++p)
+		{
+			compute_disp_grad_at_quad<T>(data, local_disp, p, F);
+			F[0] = F[0] + T(1.0);
+			F[4] = F[4] + T(1.0);
+			F[8] = F[8] + T(1.0);
+			const T J = det3(F);
+			const T log_J = log(J);
+			const T scale = pow(J, 1.0 / 3.0);
+			T Ft[9], C[9];
+			for (int i = 0; i < 9; ++i)
+				Ft[i] = F[i] / scale;
+			for (int r = 0; r < 3; ++r)
+				for (int c = 0; c < 3; ++c)
+				{
+					T sum = T(0.0);
+					for (int m = 0; m < 3; ++m)
+						sum = sum + Ft[r * 3 + m] * Ft[c * 3 + m];
+					C[r * 3 + c] = sum;
+				}
+			const T I1 = C[0] + C[4] + C[8];
+			T trCC = T(0.0);
+			for (int r = 0; r < 3; ++r)
+				for (int m = 0; m < 3; ++m)
+					trCC = trCC + C[r * 3 + m] * C[m * 3 + r];
+			const T I2 = T(0.5) * (I1 * I1 - trCC);
+			const T val = T(c1) * (I1 - T(3.0)) + T(c2) * (I2 - T(3.0)) + T(k / 2) * (log_J * log_J);
+			energy = energy + val * T(data.da[p]);
+		}
+		return energy;
 	}
 
 	// =======================================================================================
@@ -1184,6 +1253,8 @@ namespace
 			return neohookean_energy(data);
 		if (pb.d.material == ORACLE_SAINT_VENANT)
 			return saint_venant_energy<double>(data);
+		if (pb.d.material == ORACLE_MOONEY_RIVLIN)
+			return mooney_rivlin_energy<double>(data);
 		return linear_elasticity_energy<double>(data);
 	}
 	void local_gradient(const Problem &pb, const NLData &data, std::vector<double> &g)
@@ -1194,7 +1265,9 @@ namespace
 			return;
 		}
 		// utils/ElasticityUtils.cpp:81-... gradient_from_energy: autodiff gradient
-		const D1 e = pb.d.material == ORACLE_SAINT_VENANT ? saint_venant_energy<D1>(data) : linear_elasticity_energy<D1>(data);
+		const D1 e = pb.d.material == ORACLE_SAINT_VENANT   ? saint_venant_energy<D1>(data)
+					 : pb.d.material == ORACLE_MOONEY_RIVLIN ? mooney_rivlin_energy<D1>(data)
+															 : linear_elasticity_energy<D1>(data);
 		g = e.g;
 	}
 	void local_hessian(const Problem &pb, const NLData &data, std::vector<double> &h)
@@ -1204,7 +1277,9 @@ namespace
 			neohookean_hessian(data, h);
 			return;
 		}
-		const D2 e = pb.d.material == ORACLE_SAINT_VENANT ? saint_venant_energy<D2>(data) : linear_elasticity_energy<D2>(data);
+		const D2 e = pb.d.material == ORACLE_SAINT_VENANT   ? saint_venant_energy<D2>(data)
+					 : pb.d.material == ORACLE_MOONEY_RIVLIN ? mooney_rivlin_energy<D2>(data)
+															 : linear_elasticity_energy<D2>(data);
 		h = e.h;
 	}
 } // namespace
@@ -1244,6 +1319,8 @@ extern "C"
 			pb.lambda.assign(desc->lambda, desc->lambda + ne);
 		if (desc->mu)
 			pb.mu.assign(desc->mu, desc->mu + ne);
+		if (desc->material == ORACLE_MOONEY_RIVLIN && desc->param3)
+			pb.param3.assign(desc->param3, desc->param3 + ne);
 		if (desc->ref_vals)
 			pb.ref_vals.assign(desc->ref_vals, desc->ref_vals + nq * nl);
 		if (desc->density)
@@ -1259,6 +1336,8 @@ extern "C"
 			pb.lambda.assign(ne, 0.0);
 		if (pb.mu.empty())
 			pb.mu.assign(ne, 0.0);
+		if (pb.param3.empty())
+			pb.param3.assign(ne, 0.0);
 		pb.d.conn = nullptr;
 		if (desc->use_cache)
 		{
@@ -1289,7 +1368,7 @@ extern "C"
 			{
 				pb.cache_compute(e, vals);
 				compute_da(vals, da);
-				local += local_energy(pb, NLData{vals, x, da, pb.lambda[e], pb.mu[e]});
+				local += local_energy(pb, NLData{vals, x, da, pb.lambda[e], pb.mu[e], pb.param3[e]});
 			}
 			partial[tid] = local;
 		});
@@ -1310,7 +1389,7 @@ extern "C"
 			{
 				pb.cache_compute(e, vals);
 				compute_da(vals, da);
-				out[e] = local_energy(pb, NLData{vals, x, da, pb.lambda[e], pb.mu[e]});
+				out[e] = local_energy(pb, NLData{vals, x, da, pb.lambda[e], pb.mu[e], pb.param3[e]});
 			}
 		});
 	}
@@ -1331,7 +1410,7 @@ extern "C"
 			{
 				pb.cache_compute(e, vals);
 				compute_da(vals, da);
-				local_gradient(pb, NLData{vals, x, da, pb.lambda[e], pb.mu[e]}, val);
+				local_gradient(pb, NLData{vals, x, da, pb.lambda[e], pb.mu[e], pb.param3[e]}, val);
 				for (int j = 0; j < vals.n_loc; ++j)
 					for (int m = 0; m < size; ++m)
 						vec[size_t(vals.global[j]) * size + m] += val[size_t(j) * size + m] * 1.0; // (:616-629)
@@ -1380,7 +1459,7 @@ extern "C"
 				pb.cache_compute(e, vals);
 				compute_da(vals, ls.da);
 				const int n_loc = vals.n_loc, N = n_loc * size;
-				local_hessian(pb, NLData{vals, x, ls.da, pb.lambda[e], pb.mu[e]}, H);
+				local_hessian(pb, NLData{vals, x, ls.da, pb.lambda[e], pb.mu[e], pb.param3[e]}, H);
 				if (psd)
 					project_to_psd(N, H); // (:693-694)
 				for (int i = 0; i < n_loc; ++i)
@@ -1500,7 +1579,7 @@ extern "C"
 	{
 		pb.cache_compute(e, vals);
 		compute_da(vals, da);
-		return NLData{vals, x, da, pb.lambda[e], pb.mu[e]};
+		return NLData{vals, x, da, pb.lambda[e], pb.mu[e], pb.param3[e]};
 	}
 
 	double oracle_local_energy(oracle_problem *op, int e, const double *x, int autodiff)

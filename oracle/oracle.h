@@ -47,7 +47,9 @@ extern "C"
 		ORACLE_LINEAR_ELASTICITY = 1,
 		ORACLE_LAPLACIAN = 2,
 		ORACLE_MASS = 3, /* assembler/Mass.cpp: LinearAssembler with rho * phi_i * phi_j on the block diagonal */
-		ORACLE_SAINT_VENANT = 4 /* assembler/SaintVenantElasticity.cpp with the isotropic tensor of (lambda, mu) */
+		ORACLE_SAINT_VENANT = 4, /* assembler/SaintVenantElasticity.cpp with the isotropic tensor of (lambda, mu) */
+		/* assembler/MooneyRivlinElasticity.hpp through GenericElastic (full autodiff): parameters c1 = lambda[], c2 = mu[], k = param3[] */
+		ORACLE_MOONEY_RIVLIN = 5
 	};
 
 	typedef struct
@@ -77,6 +79,7 @@ extern "C"
 		int32_t n_geom_loc;
 		const int32_t *geom_lattice; /* [n_geom_loc][3] */
 		const double *geom_nodes;
+		const double *param3; /* [n_elements] third material parameter (ORACLE_MOONEY_RIVLIN: k); NULL otherwise */
 	} oracle_desc;
 
 	typedef struct oracle_problem oracle_problem;

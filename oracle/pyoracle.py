@@ -16,7 +16,9 @@ _LIB = None
 
 NEOHOOKEAN, LINEAR_ELASTICITY, LAPLACIAN, MASS = 0, 1, 2, 3
 SAINT_VENANT = 4
-MATERIAL_IDS = {"NeoHookean": NEOHOOKEAN, "LinearElasticity": LINEAR_ELASTICITY, "Laplacian": LAPLACIAN, "Mass": MASS, "SaintVenant": SAINT_VENANT}
+MOONEY_RIVLIN = 5
+MATERIAL_IDS = {"NeoHookean": NEOHOOKEAN, "LinearElasticity": LINEAR_ELASTICITY, "Laplacian": LAPLACIAN, "Mass": MASS, "SaintVenant": SAINT_VENANT,
+                "MooneyRivlin": MOONEY_RIVLIN}
 
 _dp = ctypes.POINTER(ctypes.c_double)
 _ip = ctypes.POINTER(ctypes.c_int32)
@@ -31,6 +33,7 @@ class _Desc(ctypes.Structure):
         ("use_cache", ctypes.c_int32), ("n_threads", ctypes.c_int32),
         ("ref_vals", _dp), ("density", _dp),
         ("geom_order", ctypes.c_int32), ("n_geom_loc", ctypes.c_int32), ("geom_lattice", _ip), ("geom_nodes", _dp),
+        ("param3", _dp),
     ]
 
 
@@ -124,8 +127,8 @@ class OracleProblem:
 
     def __init__(self, material, conn, vertices, n_bases, quad_points, quad_weights, ref_grads,
                  lam=None, mu=None, basis_order=1, node_lattice=None, use_cache=True, n_threads=1,
-                 ref_vals=None, density=None, geom_order=0, geom_lattice=None, geom_nodes=None):
-        """geom_order > 1 with geom_nodes [n_elements, n_geom_loc, 3] and geom_lattice [n_geom_loc, 3]: isoparametric geometry
+                 ref_vals=None, density=None, geom_order=0, geom_lattice=None, geom_nodes=None, param3=None):
+        """MooneyRivlin: (c1, c2, k) = (lam, mu, param3). geom_order > 1 with geom_nodes [n_elements, n_geom_loc, 3] and geom_lattice [n_geom_loc, 3]: isoparametric geometry
         (curved elements); otherwise P1 geometry from `vertices`."""
         L = lib()
         self.material = MATERIAL_IDS[material] if isinstance(material, str) else int(material)
@@ -146,6 +149,8 @@ class OracleProblem:
         d.conn, d.vertices = _i(self.conn), _d(self.vertices)
         d.quad_points, d.quad_weights, d.ref_grads = _d(self.qp), _d(self.qw), _d(self.rg)
         d.lambda_, d.mu = _d(self.lam), _d(self.mu)
+        self.p3 = np.ascontiguousarray(np.broadcast_to(0.0 if param3 is None else param3, (ne,)), dtype=np.float64)
+        d.param3 = _d(self.p3)
         d.use_cache, d.n_threads = int(bool(use_cache)), int(n_threads)
         if self.material == MATERIAL_IDS["Mass"]:
             assert ref_vals is not None, "Mass needs the basis values at the (mass) quadrature points"
@@ -357,6 +362,12 @@ def problem_from_mesh(mesh, material, E=1e5, nu=0.3, order=None, rho=1.0, **kw):
                              basis_order=mesh.p, ref_vals=t["val"], density=rho, **kw)
     t = tables.reference_tables(mesh.p, order)
     lam, mu = lame_from_E_nu(E, nu)
+    if material == "MooneyRivlin":  # c1, c2, k given explicitly (keywords), else a split of mu = 2 (c1 + c2), k = bulk modulus
+        c1 = kw.pop("c1", 0.3 * mu)
+        c2 = kw.pop("c2", 0.2 * mu)
+        k = kw.pop("k", lam + 2.0 * mu / 3.0)
+        lam, mu = c1, c2
+        kw["param3"] = k
     return OracleProblem(material, mesh.conn, mesh.vertices, mesh.n_bases, t["points"], t["weights"], t["grad"],
                          lam=lam, mu=mu, basis_order=mesh.p,
                          node_lattice=np.array(tables.P_NODES_LATTICE[mesh.p], dtype=np.int32), **kw)

@@ -146,6 +146,10 @@ class Assembler:
             lam[e], mu[e] = self._materials.get(int(b), self._materials["default"])
         return lam, mu
 
+    def _param3(self, bases: FESpace):
+        """third per-element material parameter (MooneyRivlin: k); None for the Lame materials"""
+        return None
+
     def _get_handle(self, n_basis, bases: FESpace, gbases: FESpace, cache: AssemblyValsCache) -> capi.Handle:
         key = (id(bases), id(cache), n_basis)
         if self._handle is not None and self._handle_key == key:
@@ -157,7 +161,7 @@ class Assembler:
         lam, mu = self._lame(bases)
         try:
             h = capi.Handle(self._material, bases.conn, n_basis, cache.t["weights"], cache.t["grad"],
-                            vertices=gbases.vertices, lam=lam, mu=mu, device=self.device)
+                            vertices=gbases.vertices, lam=lam, mu=mu, device=self.device, param3=self._param3(bases))
         except capi.PfaError as ex:
             log_and_throw_error(str(ex))
         self.invalidate()
@@ -287,6 +291,34 @@ class SaintVenantElasticity(NLAssembler):
     _material = "SaintVenant"
 
 
+class MooneyRivlinElasticity(NLAssembler):
+    """assembler/MooneyRivlinElasticity.{hpp,cpp} (GenericElastic<MooneyRivlinElasticity>); name() == "MooneyRivlin".
+    Material JSON: c1, c2, k (GenericMatParam, MooneyRivlinElasticity.cpp:5-15)."""
+    _material = "MooneyRivlin"
+
+    def add_multimaterial(self, index: int, params: dict):
+        for key in ("c1", "c2", "k"):
+            if key not in params:
+                log_and_throw_error("MooneyRivlin material needs c1, c2 and k")
+        val = (float(params["c1"]), float(params["c2"]), float(params["k"]))
+        self._materials[int(params.get("id", index))] = val
+        self._materials.setdefault("default", val)
+
+    def _per_element(self, bases: FESpace, slot: int):
+        if not self._materials:
+            log_and_throw_error(f"{self.name()}: no material set")
+        ne = len(bases)
+        if bases.body_ids is None:
+            return np.full(ne, self._materials["default"][slot])
+        return np.array([self._materials.get(int(b), self._materials["default"])[slot] for b in bases.body_ids], dtype=np.float64)
+
+    def _lame(self, bases: FESpace):
+        return self._per_element(bases, 0), self._per_element(bases, 1)
+
+    def _param3(self, bases: FESpace):
+        return self._per_element(bases, 2)
+
+
 class LinearElasticity(NLAssembler, LinearAssembler):
     """assembler/LinearElasticity.{hpp,cpp}: linear `assemble` plus the NL energy / gradient /
     Hessian used when a linear material sits inside a nonlinear solve."""
@@ -305,7 +337,7 @@ class Laplacian(LinearAssembler):
 def make_assembler(formulation: str, device: int = 0) -> Assembler:
     """AssemblerUtils::make_assembler (AssemblerUtils.cpp:55-122) for the hot-path names."""
     table = {"NeoHookean": NeoHookeanElasticity, "LinearElasticity": LinearElasticity, "Laplacian": Laplacian, "Mass": Mass,
-             "SaintVenant": SaintVenantElasticity}
+             "SaintVenant": SaintVenantElasticity, "MooneyRivlin": MooneyRivlinElasticity}
     if formulation not in table:
         log_and_throw_error(f"Unsupported assembler on the B200 path: {formulation}")
     return table[formulation](device)

@@ -16,8 +16,9 @@ LIB_PATH = os.environ.get("PFA_LIB", os.path.join(_HERE, "libpfa.so"))  # PFA_LI
 
 PFA_OK = 0
 PFA_ERR_INVALID, PFA_ERR_UNSUPPORTED, PFA_ERR_CUDA, PFA_ERR_NOMEM, PFA_ERR_NO_DEVICE = -1, -2, -3, -4, -5
-NEOHOOKEAN, LINEAR_ELASTICITY, LAPLACIAN, MASS, SAINT_VENANT = 0, 1, 2, 3, 4
-MATERIAL_IDS = {"NeoHookean": NEOHOOKEAN, "LinearElasticity": LINEAR_ELASTICITY, "Laplacian": LAPLACIAN, "Mass": MASS, "SaintVenant": SAINT_VENANT}
+NEOHOOKEAN, LINEAR_ELASTICITY, LAPLACIAN, MASS, SAINT_VENANT, MOONEY_RIVLIN = 0, 1, 2, 3, 4, 5
+MATERIAL_IDS = {"NeoHookean": NEOHOOKEAN, "LinearElasticity": LINEAR_ELASTICITY, "Laplacian": LAPLACIAN, "Mass": MASS, "SaintVenant": SAINT_VENANT,
+                "MooneyRivlin": MOONEY_RIVLIN}
 
 _dp = ctypes.POINTER(ctypes.c_double)
 _ip = ctypes.POINTER(ctypes.c_int32)
@@ -26,7 +27,7 @@ _ip = ctypes.POINTER(ctypes.c_int32)
 EXPORTS = [
     "pfa_create", "pfa_destroy", "pfa_last_error", "pfa_sizes", "pfa_pattern", "pfa_block_pattern", "pfa_pattern_device",
     "pfa_pattern_wide", "pfa_pattern_wide_device",
-    "pfa_set_materials", "pfa_energy", "pfa_energy_per_element", "pfa_gradient", "pfa_hessian",
+    "pfa_set_materials", "pfa_set_material_params", "pfa_energy", "pfa_energy_per_element", "pfa_gradient", "pfa_hessian",
     "pfa_linear_stiffness", "pfa_grad_hess", "pfa_grad_hess_weighted", "pfa_synchronize", "pfa_stream", "pfa_set_stream", "pfa_profile_enable",
     "pfa_profile_read", "pfa_launch_count", "pfa_setup_seconds",
     "pfa_is_step_valid", "pfa_set_constrained_dofs", "pfa_reduced_sizes", "pfa_reduced_pattern", "pfa_reduced_pattern_device",
@@ -48,6 +49,7 @@ class MeshDesc(ctypes.Structure):
         ("n_ghost_elements", ctypes.c_int32), ("n_first_elements", ctypes.c_int32),
         ("ref_vals", _dp), ("density", _dp),
         ("owned_nodes", ctypes.POINTER(ctypes.c_uint8)),
+        ("param3", _dp),
     ]
 
 
@@ -92,6 +94,7 @@ def lib():
     L.pfa_pattern_wide.argtypes = [vp, ctypes.POINTER(i64), ctypes.POINTER(_lp), ctypes.POINTER(_lp)]
     L.pfa_pattern_wide_device.argtypes = [vp, ctypes.POINTER(vp), ctypes.POINTER(vp)]
     L.pfa_set_materials.argtypes = [vp, vp, vp, ctypes.c_int32]
+    L.pfa_set_material_params.argtypes = [vp, vp, vp, vp, ctypes.c_int32]
     L.pfa_energy.argtypes = [vp, vp, vp]
     L.pfa_energy_per_element.argtypes = [vp, vp, vp]
     L.pfa_gradient.argtypes = [vp, vp, vp]
@@ -153,7 +156,7 @@ class Handle:
 
     def __init__(self, material, conn, n_bases, quad_weights, ref_grads, vertices=None, jac_it=None, da=None,
                  lam=None, mu=None, device=0, n_ghost_elements=0, flags=0, n_first_elements=0, ref_vals=None, density=None,
-                 owned_nodes=None):
+                 owned_nodes=None, param3=None):
         L = lib()
         self.material = MATERIAL_IDS[material] if isinstance(material, str) else int(material)
         conn = np.ascontiguousarray(conn, dtype=np.int32)
@@ -205,6 +208,12 @@ class Handle:
             assert lam.size == ngeo * stride and mu.size == ngeo * stride
             d.lambda_, d.mu = lam.ctypes.data_as(_dp), mu.ctypes.data_as(_dp)
             keep += [lam, mu]
+            if param3 is not None:  # MooneyRivlin: (c1, c2, k) = (lam, mu, param3)
+                p3 = np.asarray(param3, dtype=np.float64)
+                p3 = np.ascontiguousarray(np.full(ngeo * stride, float(p3)) if p3.ndim == 0 else p3)
+                assert p3.size == ngeo * stride
+                d.param3 = p3.ctypes.data_as(_dp)
+                keep.append(p3)
         d.material_stride, d.device, d.flags = stride, int(device), int(flags)
         d.n_ghost_elements = int(n_ghost_elements)
         d.n_first_elements = int(n_first_elements)
@@ -272,9 +281,13 @@ class Handle:
         self._check(lib().pfa_pattern_device(self._h, ctypes.byref(po), ctypes.byref(pi)))
         return po.value, pi.value
 
-    def set_materials(self, lam, mu, stride=1):
+    def set_materials(self, lam, mu, stride=1, param3=None):
         lam = np.ascontiguousarray(lam, dtype=np.float64)
         mu = np.ascontiguousarray(mu, dtype=np.float64)
+        if param3 is not None:
+            p3 = np.ascontiguousarray(param3, dtype=np.float64)
+            self._check(lib().pfa_set_material_params(self._h, _ptr(lam), _ptr(mu), _ptr(p3), int(stride)))
+            return
         self._check(lib().pfa_set_materials(self._h, _ptr(lam), _ptr(mu), int(stride)))
 
     # ---- host-array convenience wrappers (numpy in, numpy out) ----

@@ -45,7 +45,7 @@ struct pfa_handle
 	bool large_index = false; // PFA_FLAG_LARGE_INDEX: int64 pattern (built on first use), no int32 pattern
 	int64_t *d_outer64 = nullptr, *d_inner64 = nullptr;
 	std::vector<int64_t> h_outer64, h_inner64;
-	double *d_lambda = nullptr, *d_mu = nullptr;
+	double *d_lambda = nullptr, *d_mu = nullptr, *d_param3 = nullptr;
 	int32_t *d_elem_id = nullptr; // internal -> caller element index (nullptr: identity)
 	double *s_mat = nullptr;      // staging for pfa_set_materials when elements are re-ordered
 	// staging for host-pointer calls (allocated on first use)
@@ -271,13 +271,13 @@ namespace
 		// matrix unchanged (its six rigid-body eigenvalues are zero up to rounding), so the flag has no effect there.
 		if (project_to_psd && h->dm.material == PFA_LINEAR_ELASTICITY)
 			project_to_psd = 0;
-		if (project_to_psd && h->dm.material != PFA_NEOHOOKEAN && h->dm.material != PFA_SAINT_VENANT)
+		if (project_to_psd && h->dm.material != PFA_NEOHOOKEAN && h->dm.material != PFA_SAINT_VENANT && h->dm.material != PFA_MOONEY_RIVLIN)
 			return fail(h, PFA_ERR_UNSUPPORTED, "project_to_psd applies to the NLAssembler materials only");
 		if (scale != 1.0 && !rowlane_applies(h->dm.material, h->dm.n_loc, h->dm.n_qp))
 			return fail(h, PFA_ERR_UNSUPPORTED, "a Form weight other than 1 is fused for NeoHookean P1/P2 tets only");
 		if ((h->dm.material == PFA_LAPLACIAN || h->dm.material == PFA_MASS) && !linear)
 			return fail(h, PFA_ERR_UNSUPPORTED, "Laplacian and Mass are LinearAssemblers: only pfa_linear_stiffness applies");
-		if ((h->dm.material == PFA_NEOHOOKEAN || h->dm.material == PFA_SAINT_VENANT) && linear)
+		if ((h->dm.material == PFA_NEOHOOKEAN || h->dm.material == PFA_SAINT_VENANT || h->dm.material == PFA_MOONEY_RIVLIN) && linear)
 			return fail(h, PFA_ERR_UNSUPPORTED, "NeoHookean / SaintVenant are NLAssemblers: pfa_linear_stiffness does not apply");
 
 		AssembleArgs a;
@@ -391,7 +391,7 @@ extern "C"
 		*out = nullptr;
 		if (d->struct_size != int32_t(sizeof(pfa_mesh_desc)))
 			return fail(nullptr, PFA_ERR_INVALID, "pfa_create: struct_size does not match this library's pfa_mesh_desc");
-		if (d->material < PFA_NEOHOOKEAN || d->material > PFA_SAINT_VENANT)
+		if (d->material < PFA_NEOHOOKEAN || d->material > PFA_MOONEY_RIVLIN)
 			return fail(nullptr, PFA_ERR_INVALID, "pfa_create: unknown material");
 		if (d->n_elements <= 0 || d->n_loc <= 0 || d->n_bases <= 0 || d->n_qp <= 0 || d->n_ghost_elements < 0)
 			return fail(nullptr, PFA_ERR_INVALID, "pfa_create: n_elements, n_loc, n_bases and n_qp must be positive");
@@ -413,6 +413,9 @@ extern "C"
 			return fail(nullptr, PFA_ERR_INVALID, "pfa_create: lambda and mu are required for elastic materials");
 		if (d->material != PFA_LAPLACIAN && d->material_stride != 1 && d->material_stride != d->n_qp)
 			return fail(nullptr, PFA_ERR_INVALID, "pfa_create: material_stride must be 1 or n_qp");
+		const bool three_params = d->material == PFA_MOONEY_RIVLIN;
+		if (three_params && !d->param3)
+			return fail(nullptr, PFA_ERR_INVALID, "pfa_create: PFA_MOONEY_RIVLIN needs param3 (k) besides lambda (c1) and mu (c2)");
 
 		int n_dev = 0;
 		if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev <= 0)
@@ -492,7 +495,8 @@ extern "C"
 		// are known; the caller's order otherwise
 		std::vector<int32_t> perm;
 		std::vector<int32_t> conn_p;
-		std::vector<double> vert_p, lam_p, mu_p;
+		std::vector<double> vert_p, lam_p, mu_p, p3_p;
+		const double *p3_in = three_params ? d->param3 : nullptr;
 		const int32_t *conn_in = d->conn;
 		const double *vert_in = d->vertices, *lam_in = lam_src, *mu_in = mu_src;
 		try
@@ -543,6 +547,14 @@ extern "C"
 						}
 					lam_in = lam_p.data();
 					mu_in = mu_p.data();
+					if (three_params)
+					{
+						p3_p.resize(ngeo_ * st_);
+						for (size_t e = 0; e < ngeo_; ++e)
+							for (size_t k = 0; k < st_; ++k)
+								p3_p[e * st_ + k] = d->param3[size_t(perm[e]) * st_ + k];
+						p3_in = p3_p.data();
+					}
 				}
 			}
 		}
@@ -716,6 +728,12 @@ extern "C"
 				return bail(rc);
 			m.lambda = h->d_lambda;
 			m.mu = h->d_mu;
+			if (three_params)
+			{
+				if ((rc = dev_upload<double>(h, &h->d_param3, p3_in, cnt)) != PFA_OK)
+					return bail(rc);
+				m.param3 = h->d_param3;
+			}
 		}
 		if (affine)
 		{
@@ -922,7 +940,7 @@ extern "C"
 		return PFA_OK;
 	}
 
-	int pfa_set_materials(pfa_handle *h, const double *lambda, const double *mu, int32_t material_stride)
+	int pfa_set_material_params(pfa_handle *h, const double *lambda, const double *mu, const double *p3, int32_t material_stride)
 	{
 		if (!h)
 			return PFA_ERR_INVALID;
@@ -932,13 +950,19 @@ extern "C"
 			mu = lambda; // the density lives in both slots
 		if (!lambda || !mu || material_stride != h->dm.mat_stride)
 			return fail(h, PFA_ERR_INVALID, "pfa_set_materials: NULL array or material_stride differs from pfa_create");
+		const bool three = h->dm.material == PFA_MOONEY_RIVLIN;
+		if (three && !p3)
+			return fail(h, PFA_ERR_INVALID, "pfa_set_material_params: this material has three parameters (use pfa_set_material_params with p3)");
 		PFA_CUDA(h, cudaSetDevice(h->device));
 		// (with PFA_FLAG_GHOST_GEOMETRY the arrays cover the ghost elements as well, like at pfa_create)
 		const size_t cnt = size_t(h->n_geo_elements) * size_t(h->dm.mat_stride) * sizeof(double);
+		const double *src[3] = {lambda, mu, p3};
+		double *dst[3] = {h->d_lambda, h->d_mu, h->d_param3};
+		const int n_arrays = three ? 3 : 2;
 		if (h->d_elem_id == nullptr)
 		{
-			PFA_CUDA(h, cudaMemcpyAsync(h->d_lambda, lambda, cnt, cudaMemcpyDefault, h->stream));
-			PFA_CUDA(h, cudaMemcpyAsync(h->d_mu, mu, cnt, cudaMemcpyDefault, h->stream));
+			for (int k = 0; k < n_arrays; ++k)
+				PFA_CUDA(h, cudaMemcpyAsync(dst[k], src[k], cnt, cudaMemcpyDefault, h->stream));
 		}
 		else
 		{
@@ -946,9 +970,7 @@ extern "C"
 			int rc = ensure_staging(h, &h->s_mat, cnt / sizeof(double));
 			if (rc != PFA_OK)
 				return rc;
-			const double *src[2] = {lambda, mu};
-			double *dst[2] = {h->d_lambda, h->d_mu};
-			for (int k = 0; k < 2; ++k)
+			for (int k = 0; k < n_arrays; ++k)
 			{
 				PFA_CUDA(h, cudaMemcpyAsync(h->s_mat, src[k], cnt, cudaMemcpyDefault, h->stream));
 				++h->launches;
@@ -957,6 +979,11 @@ extern "C"
 		}
 		PFA_CUDA(h, cudaStreamSynchronize(h->stream));
 		return PFA_OK;
+	}
+
+	int pfa_set_materials(pfa_handle *h, const double *lambda, const double *mu, int32_t material_stride)
+	{
+		return pfa_set_material_params(h, lambda, mu, nullptr, material_stride);
 	}
 
 	int pfa_energy(pfa_handle *h, const double *x, double *energy)

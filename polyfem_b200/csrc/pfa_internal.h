@@ -25,6 +25,7 @@ namespace pfa
 		const double *detj = nullptr;      // [n_el][gq]   affine: det(J) ; per-qp: da = det*w
 		const double *lambda = nullptr;    // [n_el][mat_stride]
 		const double *mu = nullptr;        // [n_el][mat_stride]
+		const double *param3 = nullptr;    // [n_el][mat_stride] (PFA_MOONEY_RIVLIN: k; lambda, mu hold c1, c2)
 		const double *ref_vals = nullptr;  // [n_qp][n_loc] basis values (PFA_MASS)
 		// [9][n_loc][n_loc] reference moment matrices S^{cd}_{ij} = sum_q w_q ghat_i[c](q) ghat_j[d](q) (linear
 		// assemblers on affine elements, assemble_affine_linear_kernel)

@@ -178,11 +178,13 @@ namespace pfa
 		// per-qp record: C[9] | P*da[9] | c2*da*F[9] | c1*da | mu*da | lambda*da | (SaintVenant) mu*da*F F^T [6]
 		// SaintVenant uses the slots as: F[9] | P*da[9] | S*da[9] | - | mu*da | lambda*da | mu*da*F F^T (00 01 02 11 12 22)
 		constexpr int kQRec = 36;
+		// MooneyRivlin: F | P da | F M | cof F | F F^T (6) | M (6) | psi_1, psi_2, psi_J, psi_1J, psi_2J, psi_JJ (x da)
+		__host__ __device__ constexpr int qrec_of(int material) { return material == PFA_MOONEY_RIVLIN ? 54 : kQRec; }
 
 		// dimension of the local matrix as project_to_psd sees it: 3 n_loc, plus one zero row and column when that is odd
 		__host__ __device__ inline int psd_dim(int n_loc) { return 3 * n_loc + ((3 * n_loc) & 1); }
 
-		__host__ __device__ inline WarpLayout warp_layout(int n_loc, int n_qp, bool psd = false)
+		__host__ __device__ inline WarpLayout warp_layout(int n_loc, int n_qp, bool psd = false, int qrec = kQRec)
 		{
 			WarpLayout L;
 			int o = 0;
@@ -193,7 +195,7 @@ namespace pfa
 			L.A = o;
 			o += n_qp * n_loc * 3;
 			L.Q = o;
-			o += n_qp * kQRec;
+			o += n_qp * qrec;
 			L.J = o;
 			o += n_qp * 9;
 			L.DA = o;
@@ -384,7 +386,8 @@ namespace pfa
 			extern __shared__ double smem[];
 			const int n_loc = m.n_loc, n_qp = m.n_qp;
 			const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-			const WarpLayout L = warp_layout(n_loc, n_qp, PSD);
+			constexpr int QR = qrec_of(MAT);
+			const WarpLayout L = warp_layout(n_loc, n_qp, PSD, QR);
 
 			// CTA-shared reference tables
 			// (TABLES_SHARED false: read through the cache from global memory instead - the P4 projection needs the space)
@@ -462,9 +465,12 @@ namespace pfa
 						lam = m.lambda[size_t(e) * m.mat_stride + ms];
 						mu = m.mu[size_t(e) * m.mat_stride + ms];
 					}
-					double *rec = sQ + q * kQRec;
-					rec[28] = mu * da;
-					rec[29] = lam * da;
+					double *rec = sQ + q * QR;
+					if (MAT != PFA_MOONEY_RIVLIN)
+					{
+						rec[28] = mu * da;
+						rec[29] = lam * da;
+					}
 					if (!LINEAR && MAT != PFA_LAPLACIAN)
 					{
 						double F[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
@@ -503,6 +509,65 @@ namespace pfa
 							}
 							rec[27] = (mu + lam * (1.0 - lJ)) * invJ * invJ * da; // c1 * da
 							e_loc += (0.5 * mu * (sq - 3.0 - 2.0 * lJ) + 0.5 * lam * lJ * lJ) * da;
+						}
+						else if (MAT == PFA_MOONEY_RIVLIN)
+						{
+							// MooneyRivlinElasticity.hpp:26-47: psi = c1 (J^-2/3 I1 - 3) + c2 (J^-4/3 I2 - 3) + k/2 ln^2 J with I1 = tr C,
+							// I2 = (I1^2 - tr C^2) / 2, C = F^T F (the invariants of F~ F~^T are those of C scaled by powers of J). The
+							// reference differentiates this by autodiff; here the chain rule over (I1, I2, J):
+							//   dI1 = 2 F, dI2 = 2 F M (M = I1 I - C), dJ = cof F;  P = 2 psi_1 F + 2 psi_2 F M + psi_J cof F.
+							// (c1, c2, k) = (lambda, mu, param3). Record: F | P da | F M | cof F | F F^T (6) | M (6) | 9 scalars x da.
+							F[0] += 1.0;
+							F[4] += 1.0;
+							F[8] += 1.0;
+							const double c1 = lam, c2 = mu, kk = m.param3[size_t(e) * m.mat_stride + ms];
+							double C[9], G[9];
+							cofactor3(F, G);
+							const double J = det3(F);
+							const double lJ = log(J); // NaN for J <= 0, propagates like the reference
+							for (int r = 0; r < 3; ++r)
+								for (int c = 0; c < 3; ++c)
+									C[r * 3 + c] = F[0 + r] * F[0 + c] + F[3 + r] * F[3 + c] + F[6 + r] * F[6 + c];
+							const double I1 = C[0] + C[4] + C[8];
+							double trCC = 0.0;
+							for (int k9 = 0; k9 < 9; ++k9)
+								trCC += C[k9] * C[k9];
+							const double I2 = 0.5 * (I1 * I1 - trCC);
+							const double ja = pow(J, -2.0 / 3.0), jb = ja * ja, iJ = 1.0 / J;
+							const double p1 = c1 * ja, p2 = c2 * jb;
+							const double p1J = c1 * (-2.0 / 3.0) * ja * iJ, p2J = c2 * (-4.0 / 3.0) * jb * iJ;
+							const double pJ = I1 * p1J + I2 * p2J + kk * lJ * iJ;
+							const double pJJ = (c1 * I1 * (10.0 / 9.0) * ja + c2 * I2 * (28.0 / 9.0) * jb + kk * (1.0 - lJ)) * iJ * iJ;
+							double Mm[9];
+							for (int k9 = 0; k9 < 9; ++k9)
+								Mm[k9] = -C[k9];
+							Mm[0] += I1;
+							Mm[4] += I1;
+							Mm[8] += I1;
+							for (int r = 0; r < 3; ++r)
+								for (int c = 0; c < 3; ++c)
+								{
+									const double fm = F[r * 3 + 0] * Mm[0 + c] + F[r * 3 + 1] * Mm[3 + c] + F[r * 3 + 2] * Mm[6 + c];
+									rec[r * 3 + c] = F[r * 3 + c];
+									rec[18 + r * 3 + c] = fm;
+									rec[27 + r * 3 + c] = G[r * 3 + c];
+									rec[9 + r * 3 + c] = (2.0 * p1 * F[r * 3 + c] + 2.0 * p2 * fm + pJ * G[r * 3 + c]) * da;
+								}
+							int k6 = 0;
+							for (int r = 0; r < 3; ++r)
+								for (int c = r; c < 3; ++c)
+								{
+									rec[36 + k6] = F[r * 3 + 0] * F[c * 3 + 0] + F[r * 3 + 1] * F[c * 3 + 1] + F[r * 3 + 2] * F[c * 3 + 2];
+									rec[42 + k6] = Mm[r * 3 + c];
+									++k6;
+								}
+							rec[48] = p1 * da;
+							rec[49] = p2 * da;
+							rec[50] = pJ * da;
+							rec[51] = p1J * da;
+							rec[52] = p2J * da;
+							rec[53] = pJJ * da;
+							e_loc += (c1 * (ja * I1 - 3.0) + c2 * (jb * I2 - 3.0) + 0.5 * kk * lJ * lJ) * da;
 						}
 						else if (MAT == PFA_SAINT_VENANT)
 						{
@@ -576,7 +641,7 @@ namespace pfa
 						for (int q = 0; q < n_qp; ++q)
 						{
 							const double *Di = sD + (q * n_loc + i) * 3;
-							const double *P = sQ + q * kQRec + 9 + c * 3;
+							const double *P = sQ + q * QR + 9 + c * 3;
 							g += Di[0] * P[0] + Di[1] * P[1] + Di[2] * P[2];
 						}
 						atomicAdd(a.grad + size_t(sG[i]) * 3 + c, g);
@@ -588,7 +653,7 @@ namespace pfa
 					for (int t = lane; t < n_qp * n_loc; t += 32)
 					{
 						const int q = t / n_loc;
-						const double *C = sQ + q * kQRec;
+						const double *C = sQ + q * QR;
 						const double *Di = sD + t * 3;
 						sA[t * 3 + 0] = C[0] * Di[0] + C[1] * Di[1] + C[2] * Di[2];
 						sA[t * 3 + 1] = C[3] * Di[0] + C[4] * Di[1] + C[5] * Di[2];
@@ -639,7 +704,7 @@ namespace pfa
 							double s = 0.0, W0 = 0.0, W1 = 0.0, W2 = 0.0;
 							for (int q = 0; q < n_qp; ++q)
 							{
-								const double *rec = sQ + q * kQRec;
+								const double *rec = sQ + q * QR;
 								const double *Di = sD + (q * n_loc + i) * 3, *Dj = sD + (q * n_loc + j) * 3;
 								const double *Ai = sA + (q * n_loc + i) * 3, *Aj = sA + (q * n_loc + j) * 3;
 								s += rec[28] * (Di[0] * Dj[0] + Di[1] * Dj[1] + Di[2] * Dj[2]);
@@ -673,13 +738,70 @@ namespace pfa
 							blk[6] += W1;
 							blk[7] -= W0;
 						}
+						else if (MAT == PFA_MOONEY_RIVLIN && !LINEAR)
+						{
+							// with f = F D, n = F M D, c = cof(F) D (per node), z = D_i x D_j:
+							//   H[(i,a),(j,b)] = sum_q da [ p_i[a]^T Psi'' p_j[b]   (p = (2 f, 2 n, c); Psi'' has only the J row / column)
+							//        + delta_ab (2 psi_1 D_i.D_j + 2 psi_2 D_i.M D_j) + psi_2 (4 f_i[a] f_j[b] - 2 f_j[a] f_i[b] - 2 (F F^T)_ab D_i.D_j)
+							//        - psi_J hat(F z)_ab ]
+							// (d2I1 = 2 I, d2I2[ij,kl] = 4 F_ij F_kl + 2 I1 d_ik d_jl - 2 (d_ik C_lj + F_il F_kj + d_jl B_ik), d2J = the hat blocks)
+							for (int q = 0; q < n_qp; ++q)
+							{
+								const double *rec = sQ + q * QR;
+								const double *Di = sD + (q * n_loc + i) * 3, *Dj = sD + (q * n_loc + j) * 3;
+								const double *F = rec, *FM = rec + 18, *G = rec + 27, *B = rec + 36, *Mm = rec + 42;
+								const double w1 = rec[48], w2 = rec[49], wJ = rec[50], w1J = rec[51], w2J = rec[52], wJJ = rec[53];
+								double fi[3], fj[3], ni[3], nj[3], ci[3], cj[3];
+								for (int r = 0; r < 3; ++r)
+								{
+									fi[r] = F[r * 3] * Di[0] + F[r * 3 + 1] * Di[1] + F[r * 3 + 2] * Di[2];
+									fj[r] = F[r * 3] * Dj[0] + F[r * 3 + 1] * Dj[1] + F[r * 3 + 2] * Dj[2];
+									ni[r] = FM[r * 3] * Di[0] + FM[r * 3 + 1] * Di[1] + FM[r * 3 + 2] * Di[2];
+									nj[r] = FM[r * 3] * Dj[0] + FM[r * 3 + 1] * Dj[1] + FM[r * 3 + 2] * Dj[2];
+									ci[r] = G[r * 3] * Di[0] + G[r * 3 + 1] * Di[1] + G[r * 3 + 2] * Di[2];
+									cj[r] = G[r * 3] * Dj[0] + G[r * 3 + 1] * Dj[1] + G[r * 3 + 2] * Dj[2];
+								}
+								const double dot = Di[0] * Dj[0] + Di[1] * Dj[1] + Di[2] * Dj[2];
+								const double dMd = Di[0] * (Mm[0] * Dj[0] + Mm[1] * Dj[1] + Mm[2] * Dj[2]) + Di[1] * (Mm[1] * Dj[0] + Mm[3] * Dj[1] + Mm[4] * Dj[2])
+												   + Di[2] * (Mm[2] * Dj[0] + Mm[4] * Dj[1] + Mm[5] * Dj[2]);
+								for (int r = 0; r < 3; ++r)
+								{
+									// column operand of the rank part: Psi'' p_j (psi_11 = psi_12 = psi_22 = 0)
+									const double pi1 = 2.0 * fi[r], pi2 = 2.0 * ni[r], pi3 = ci[r];
+									for (int c = 0; c < 3; ++c)
+									{
+										const double q1 = w1J * cj[c], q2 = w2J * cj[c], q3 = w1J * 2.0 * fj[c] + w2J * 2.0 * nj[c] + wJJ * cj[c];
+										blk[r * 3 + c] += pi1 * q1 + pi2 * q2 + pi3 * q3 + w2 * (4.0 * fi[r] * fj[c] - 2.0 * fj[r] * fi[c]);
+									}
+								}
+								const double dg = 2.0 * w1 * dot + 2.0 * w2 * dMd, bd = 2.0 * w2 * dot;
+								blk[0] += dg - bd * B[0];
+								blk[1] -= bd * B[1];
+								blk[2] -= bd * B[2];
+								blk[3] -= bd * B[1];
+								blk[4] += dg - bd * B[3];
+								blk[5] -= bd * B[4];
+								blk[6] -= bd * B[2];
+								blk[7] -= bd * B[4];
+								blk[8] += dg - bd * B[5];
+								const double z0 = Di[1] * Dj[2] - Di[2] * Dj[1], z1 = Di[2] * Dj[0] - Di[0] * Dj[2], z2 = Di[0] * Dj[1] - Di[1] * Dj[0];
+								const double W0 = wJ * (F[0] * z0 + F[1] * z1 + F[2] * z2), W1 = wJ * (F[3] * z0 + F[4] * z1 + F[5] * z2),
+											 W2 = wJ * (F[6] * z0 + F[7] * z1 + F[8] * z2);
+								blk[1] += W2;
+								blk[2] -= W1;
+								blk[3] -= W2;
+								blk[5] += W0;
+								blk[6] += W1;
+								blk[7] -= W0;
+							}
+						}
 						else if (MAT == PFA_SAINT_VENANT && !LINEAR)
 						{
 							// H[(i,a),(j,b)] = sum_q [ (D_i . S D_j) delta_ab + mu (F D_j)_a (F D_i)_b + lambda (F D_i)_a (F D_j)_b
 							//                          + mu (F F^T)_ab (D_i . D_j) ] da     (tangent of P = F S(E))
 							for (int q = 0; q < n_qp; ++q)
 							{
-								const double *rec = sQ + q * kQRec;
+								const double *rec = sQ + q * QR;
 								const double *Di = sD + (q * n_loc + i) * 3, *Dj = sD + (q * n_loc + j) * 3;
 								const double *Ai = sA + (q * n_loc + i) * 3, *Aj = sA + (q * n_loc + j) * 3;
 								const double *S = rec + 18, *B = rec + 30;
@@ -705,7 +827,7 @@ namespace pfa
 						{
 							for (int q = 0; q < n_qp; ++q)
 							{
-								const double *rec = sQ + q * kQRec;
+								const double *rec = sQ + q * QR;
 								const double *Di = sD + (q * n_loc + i) * 3, *Dj = sD + (q * n_loc + j) * 3;
 								const double mu = rec[28], lam = rec[29];
 								const double dot = Di[0] * Dj[0] + Di[1] * Dj[1] + Di[2] * Dj[2];
@@ -2027,17 +2149,17 @@ namespace pfa
 
 		constexpr size_t kMaxSmem = 227 * 1024;
 
-		size_t generic_smem_bytes(int n_loc, int n_qp, int warps, bool psd = false, bool tables_shared = true)
+		size_t generic_smem_bytes(int n_loc, int n_qp, int warps, bool psd = false, bool tables_shared = true, int qrec = kQRec)
 		{
-			const WarpLayout L = warp_layout(n_loc, n_qp, psd);
+			const WarpLayout L = warp_layout(n_loc, n_qp, psd, qrec);
 			return sizeof(double) * ((tables_shared ? size_t(n_qp) * n_loc * 3 + n_qp : size_t(0)) + size_t(warps) * L.total);
 		}
 
 		// warps per CTA: the largest of 8/4/2/1 whose staging fits in shared memory
-		int pick_warps(int n_loc, int n_qp)
+		int pick_warps(int n_loc, int n_qp, int qrec = kQRec)
 		{
 			for (int w = 8; w >= 1; w >>= 1)
-				if (generic_smem_bytes(n_loc, n_qp, w) <= kMaxSmem)
+				if (generic_smem_bytes(n_loc, n_qp, w, false, true, qrec) <= kMaxSmem)
 					return w;
 			return 0;
 		}
@@ -2045,7 +2167,7 @@ namespace pfa
 		template <int MAT, bool LINEAR, int kWarps>
 		cudaError_t launch_generic_w(const DeviceMesh &m, const AssembleArgs &a, int sm_count, cudaStream_t st)
 		{
-			const size_t smem = generic_smem_bytes(m.n_loc, m.n_qp, kWarps);
+			const size_t smem = generic_smem_bytes(m.n_loc, m.n_qp, kWarps, false, true, qrec_of(MAT));
 			auto kern = assemble_generic_kernel<MAT, LINEAR, kWarps>;
 			cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
 			if (err != cudaSuccess)
@@ -2067,7 +2189,7 @@ namespace pfa
 		template <int MAT, int kW, bool TABLES_SHARED>
 		cudaError_t launch_generic_psd_w(const DeviceMesh &m, const AssembleArgs &a, int sm_count, cudaStream_t st)
 		{
-			const size_t smem = generic_smem_bytes(m.n_loc, m.n_qp, kW, true, TABLES_SHARED);
+			const size_t smem = generic_smem_bytes(m.n_loc, m.n_qp, kW, true, TABLES_SHARED, qrec_of(MAT));
 			if (smem > kMaxSmem)
 				return cudaErrorNotSupported;
 			auto kern = assemble_generic_kernel<MAT, false, kW, true, TABLES_SHARED>;
@@ -2090,9 +2212,9 @@ namespace pfa
 		{
 			if (psd_dim(m.n_loc) > 128) // the diagonal of the rebuilt matrix is held in four registers per lane
 				return cudaErrorNotSupported;
-			if (generic_smem_bytes(m.n_loc, m.n_qp, 2, true) <= kMaxSmem)
+			if (generic_smem_bytes(m.n_loc, m.n_qp, 2, true, true, qrec_of(MAT)) <= kMaxSmem)
 				return launch_generic_psd_w<MAT, 2, true>(m, a, sm_count, st);
-			if (generic_smem_bytes(m.n_loc, m.n_qp, 1, true) <= kMaxSmem)
+			if (generic_smem_bytes(m.n_loc, m.n_qp, 1, true, true, qrec_of(MAT)) <= kMaxSmem)
 				return launch_generic_psd_w<MAT, 1, true>(m, a, sm_count, st);
 			return launch_generic_psd_w<MAT, 1, false>(m, a, sm_count, st);
 		}
@@ -2100,7 +2222,7 @@ namespace pfa
 		template <int MAT, bool LINEAR>
 		cudaError_t launch_generic(const DeviceMesh &m, const AssembleArgs &a, int sm_count, cudaStream_t st)
 		{
-			switch (pick_warps(m.n_loc, m.n_qp))
+			switch (pick_warps(m.n_loc, m.n_qp, qrec_of(MAT)))
 			{
 			case 8:
 				return launch_generic_w<MAT, LINEAR, 8>(m, a, sm_count, st);
@@ -2246,6 +2368,14 @@ namespace pfa
 			if (a.project_to_psd)
 				return launch_generic_psd<PFA_SAINT_VENANT>(m, a, sm_count, st);
 			return launch_generic<PFA_SAINT_VENANT, false>(m, a, sm_count, st);
+		case PFA_MOONEY_RIVLIN:
+			if (linear)
+				return cudaErrorNotSupported;
+			if (kernel_name)
+				*kernel_name = a.project_to_psd ? "assemble_generic_kernel<MooneyRivlin,psd>" : "assemble_generic_kernel<MooneyRivlin>";
+			if (a.project_to_psd)
+				return launch_generic_psd<PFA_MOONEY_RIVLIN>(m, a, sm_count, st);
+			return launch_generic<PFA_MOONEY_RIVLIN, false>(m, a, sm_count, st);
 		case PFA_LINEAR_ELASTICITY:
 			if (linear && affine_linear_applies(m) && a.values != nullptr)
 			{

@@ -26,7 +26,7 @@ namespace
 				int chunk_steps, const uint8_t *owned, double scale, double *energy, double *grad, double *values, int64_t *stats)
 	{
 		double za = 0.0, zb = 0.0;
-		if (MODE == 2 && !p2_rule_weights(ref_grads, NL, NQ, za, zb))
+		if (MODE >= 2 && !p2_rule_weights(ref_grads, NL, NQ, za, zb))
 			return -9;
 		const int bucket_elements = chunk_steps % 7 == 3 ? 5 : (1 << 30); // some test cases exercise the spatial buckets of the schedule
 		constexpr int RECD = Rec<NQ>::D;
@@ -162,6 +162,9 @@ extern "C" int collane2_emulate(int n_loc, int n_qp, int n_el, int n_bases, cons
 {
 	if (n_loc == 4 && n_qp == 1)
 		return emulate<4, 1, 0>(n_el, n_bases, conn, adj_off, adj, jit, detj, qw, ref_grads, lam, mu, mstride, x, small_rows, chunk_steps, owned, scale, energy,
+									grad, values, stats);
+	if (n_loc == 10 && n_qp == 4 && structured == 3)
+		return emulate<10, 4, 3>(n_el, n_bases, conn, adj_off, adj, jit, detj, qw, ref_grads, lam, mu, mstride, x, small_rows, chunk_steps, owned, scale, energy,
 									grad, values, stats);
 	if (n_loc == 10 && n_qp == 4 && structured == 2)
 		return emulate<10, 4, 2>(n_el, n_bases, conn, adj_off, adj, jit, detj, qw, ref_grads, lam, mu, mstride, x, small_rows, chunk_steps, owned, scale, energy,

@@ -69,10 +69,10 @@ def run_emulation(lib, oracle, mesh, x, small_rows, structured=0, chunk_steps=24
 
 
 @pytest.mark.parametrize("p,n,small_rows,structured", [(1, 3, 96, 0), (2, 2, 96, 0), (2, 3, 96, 1), (2, 3, 1000, 0), (2, 2, 0, 1), (2, 5, 96, 1), (1, 7, 96, 0),
-                                                       (2, 3, 96, 2), (2, 4, 0, 2)])
+                                                       (2, 3, 96, 2), (2, 4, 0, 2), (2, 3, 96, 3), (2, 4, 0, 3)])
 def test_column_lane_data_flow_equals_oracle(emul, oracle, p, n, small_rows, structured):
     """structured = 1: the column step that uses the structural zeros of the P2 reference gradients (P2S); 2: the vertex-weighted
-    entry step for the symmetric 4-point rule (P2Z)."""
+    entry step for the symmetric 4-point rule (P2Z); 3: the same, streamed."""
     mesh = M.kuhn_cube(n, p, jitter=0.2)
     x = M.random_displacement(mesh)[: mesh.n_bases * 3]
     prob, e, g, v, stats = run_emulation(emul, oracle, mesh, x, small_rows, structured)
