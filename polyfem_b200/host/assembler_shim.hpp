@@ -17,11 +17,14 @@
 #include <polyfem/assembler/Laplacian.hpp>
 #include <polyfem/assembler/LinearElasticity.hpp>
 #include <polyfem/assembler/Mass.hpp>
+#include <polyfem/assembler/MooneyRivlinElasticity.hpp>
 #include <polyfem/assembler/NeoHookeanElasticity.hpp>
+#include <polyfem/assembler/SaintVenantElasticity.hpp>
 #include <polyfem/basis/ElementBases.hpp>
 #include <polyfem/utils/Logger.hpp>
 #include <polyfem/utils/MatrixCache.hpp>
 
+#include <cmath>
 #include <memory>
 #include <vector>
 
@@ -48,7 +51,8 @@ namespace polyfem::assembler::b200
 		void invalidate_materials() const { ++material_version_; }
 
 		/// Reads what the hot path needs out of `bases` / `gbases` once per mesh.
-		/// `lame(e, q, lambda, mu)` evaluates LameParameters::lambda_mu for element e at qp q.
+		/// `lame(vals, q, p1, p2, p3)` evaluates the material parameters of the element behind `vals` at quadrature point q:
+		/// (lambda, mu) from LameParameters::lambda_mu, the density for PFA_MASS, (c1, c2, k) for PFA_MOONEY_RIVLIN.
 		template <typename LameFn>
 		pfa_handle *get(const pfa_material material, const bool is_volume, const int n_basis,
 						const std::vector<basis::ElementBases> &bases,
@@ -90,7 +94,7 @@ namespace polyfem::assembler::b200
 			std::vector<double> ref_vals(material == PFA_MASS ? size_t(n_qp) * n_loc : 0);
 			for (size_t k = 0; k < ref_vals.size(); ++k)
 				ref_vals[k] = vals.basis_values[k % n_loc].val(k / n_loc);
-			std::vector<double> lambda(size_t(n_el) * n_qp), mu(size_t(n_el) * n_qp);
+			std::vector<double> lambda(size_t(n_el) * n_qp), mu(size_t(n_el) * n_qp), third(material == PFA_MOONEY_RIVLIN ? size_t(n_el) * n_qp : 0);
 			std::vector<double> ref_grads(size_t(n_qp) * n_loc * 3), weights(n_qp);
 			for (int q = 0; q < n_qp; ++q)
 			{
@@ -126,7 +130,10 @@ namespace polyfem::assembler::b200
 						da[size_t(e) * n_qp + q] = vals.det(q) * vals.quadrature.weights(q);
 					}
 					// (lambda, mu), or for PFA_MASS the density in `lambda`
-					lame(vals, q, lambda[size_t(e) * n_qp + q], mu[size_t(e) * n_qp + q]);
+					double p3 = 0;
+					lame(vals, q, lambda[size_t(e) * n_qp + q], mu[size_t(e) * n_qp + q], p3);
+					if (!third.empty())
+						third[size_t(e) * n_qp + q] = p3;
 				}
 			}
 
@@ -154,6 +161,8 @@ namespace polyfem::assembler::b200
 				d.ref_vals = ref_vals.data();
 				d.density = lambda.data();
 			}
+			if (!third.empty())
+				d.param3 = third.data();
 			d.material_stride = n_qp;
 			d.device = 0;
 #ifdef POLYSOLVE_LARGE_INDEX
@@ -180,15 +189,23 @@ namespace polyfem::assembler::b200
 			if (material != PFA_LAPLACIAN)
 			{
 				const int n_el = int(bases.size());
-				std::vector<double> lambda(size_t(n_el) * n_qp_), mu(size_t(n_el) * n_qp_);
+				std::vector<double> lambda(size_t(n_el) * n_qp_), mu(size_t(n_el) * n_qp_), third(material == PFA_MOONEY_RIVLIN ? size_t(n_el) * n_qp_ : 0);
 				ElementAssemblyValues vals;
 				for (int e = 0; e < n_el; ++e)
 				{
 					cache.compute(e, is_volume, bases[e], gbases[e], vals);
 					for (int q = 0; q < n_qp_; ++q)
-						lame(vals, q, lambda[size_t(e) * n_qp_ + q], mu[size_t(e) * n_qp_ + q]);
+					{
+						double p3 = 0;
+						lame(vals, q, lambda[size_t(e) * n_qp_ + q], mu[size_t(e) * n_qp_ + q], p3);
+						if (!third.empty())
+							third[size_t(e) * n_qp_ + q] = p3;
+					}
 				}
-				check(h_, pfa_set_materials(h_, lambda.data(), material == PFA_MASS ? nullptr : mu.data(), n_qp_));
+				if (!third.empty())
+					check(h_, pfa_set_material_params(h_, lambda.data(), mu.data(), third.data(), n_qp_));
+				else
+					check(h_, pfa_set_materials(h_, lambda.data(), material == PFA_MASS ? nullptr : mu.data(), n_qp_));
 			}
 			t_ = t;
 			uploaded_version_ = material_version_;
@@ -231,8 +248,12 @@ namespace polyfem::assembler::b200
 		mutable unsigned material_version_ = 0, uploaded_version_ = 0;
 	};
 
-	/// Drop-in for NeoHookeanElasticity ("NeoHookean" in AssemblerUtils::make_assembler).
-	class NeoHookeanElasticityB200 : public NeoHookeanElasticity
+	/// The four NLAssembler virtuals (Assembler.cpp:495-771) through the C ABI, for the reference assembler class `Base` whose
+	/// local math the library implements as MATERIAL. A drop-in derives from this, evaluates its material parameters in
+	/// material_params() and may veto the device path per object state in on_device() (then every virtual forwards to Base:
+	/// energy, gradient and Hessian must come from the same implementation).
+	template <class Base, pfa_material MATERIAL>
+	class NLAssemblerB200 : public Base
 	{
 	public:
 		double assemble_energy(const bool is_volume, const std::vector<basis::ElementBases> &bases,
@@ -240,9 +261,9 @@ namespace polyfem::assembler::b200
 							   const double t, const double dt, const Eigen::MatrixXd &displacement,
 							   const Eigen::MatrixXd &displacement_prev) const override
 		{
-			if (use_robust_jacobian) // Bezier evaluator (NeoHookeanElasticity.cpp:357-359): CPU path
-				return NeoHookeanElasticity::assemble_energy(is_volume, bases, gbases, cache, t, dt, displacement, displacement_prev);
-			pfa_handle *h = handle(is_volume, int(displacement.size() / size()), bases, gbases, cache, t);
+			if (!on_device())
+				return Base::assemble_energy(is_volume, bases, gbases, cache, t, dt, displacement, displacement_prev);
+			pfa_handle *h = handle(is_volume, int(displacement.size() / this->size()), bases, gbases, cache, t);
 			double e = 0;
 			DeviceAssembly::check(h, pfa_energy(h, displacement.data(), &e));
 			return e;
@@ -253,9 +274,9 @@ namespace polyfem::assembler::b200
 													const double t, const double dt, const Eigen::MatrixXd &displacement,
 													const Eigen::MatrixXd &displacement_prev) const override
 		{
-			if (use_robust_jacobian) // the whole assembler forwards: energy, gradient and Hessian must use the same Jacobian
-				return NeoHookeanElasticity::assemble_energy_per_element(is_volume, bases, gbases, cache, t, dt, displacement, displacement_prev);
-			pfa_handle *h = handle(is_volume, int(displacement.size() / size()), bases, gbases, cache, t);
+			if (!on_device())
+				return Base::assemble_energy_per_element(is_volume, bases, gbases, cache, t, dt, displacement, displacement_prev);
+			pfa_handle *h = handle(is_volume, int(displacement.size() / this->size()), bases, gbases, cache, t);
 			Eigen::VectorXd out(bases.size());
 			DeviceAssembly::check(h, pfa_energy_per_element(h, displacement.data(), out.data()));
 			return out;
@@ -266,10 +287,10 @@ namespace polyfem::assembler::b200
 							   const double t, const double dt, const Eigen::MatrixXd &displacement,
 							   const Eigen::MatrixXd &displacement_prev, Eigen::MatrixXd &rhs) const override
 		{
-			if (use_robust_jacobian) // NeoHookeanElasticity.cpp:475-498 uses jacs(p) * det(jac_it) in the gradient too
-				return NeoHookeanElasticity::assemble_gradient(is_volume, n_basis, bases, gbases, cache, t, dt, displacement, displacement_prev, rhs);
+			if (!on_device())
+				return Base::assemble_gradient(is_volume, n_basis, bases, gbases, cache, t, dt, displacement, displacement_prev, rhs);
 			pfa_handle *h = handle(is_volume, n_basis, bases, gbases, cache, t);
-			rhs.resize(n_basis * size(), 1);
+			rhs.resize(n_basis * this->size(), 1);
 			DeviceAssembly::check(h, pfa_gradient(h, displacement.data(), rhs.data()));
 		}
 
@@ -279,8 +300,8 @@ namespace polyfem::assembler::b200
 							  const Eigen::MatrixXd &displacement, const Eigen::MatrixXd &displacement_prev,
 							  utils::MatrixCache &mat_cache, StiffnessMatrix &hess) const override
 		{
-			if (use_robust_jacobian) // ... and in the Hessian (NeoHookeanElasticity.cpp:567-587)
-				return NeoHookeanElasticity::assemble_hessian(is_volume, n_basis, project_to_psd, bases, gbases, cache, t, dt, displacement, displacement_prev, mat_cache, hess);
+			if (!on_device())
+				return Base::assemble_hessian(is_volume, n_basis, project_to_psd, bases, gbases, cache, t, dt, displacement, displacement_prev, mat_cache, hess);
 			pfa_handle *h = handle(is_volume, n_basis, bases, gbases, cache, t);
 			int64_t nnz;
 			pfa_sizes(h, nullptr, nullptr, &nnz);
@@ -290,29 +311,89 @@ namespace polyfem::assembler::b200
 			// mat_cache is caller-owned scratch (ElasticForm.hpp:116); it is left untouched and valid.
 		}
 
-		// material changes after the first assembly must reach the device (the handle caches lambda / mu)
+		// material changes after the first assembly must reach the device (the handle caches the parameters)
 		void add_multimaterial(const int index, const json &params, const Units &units, const std::string &root_path) override
 		{
-			NeoHookeanElasticity::add_multimaterial(index, params, units, root_path);
+			Base::add_multimaterial(index, params, units, root_path);
 			dev_.invalidate_materials();
 		}
 		void set_size(const int size) override
 		{
-			NeoHookeanElasticity::set_size(size);
+			Base::set_size(size);
 			dev_.invalidate_materials();
 		}
 
-	private:
+	protected:
+		virtual bool on_device() const { return true; }
+		/// parameters of the element behind `vals` at quadrature point q, evaluated like the reference does inside its local
+		/// assembly (p3 only for three-parameter materials)
+		virtual void material_params(const ElementAssemblyValues &vals, const int q, const double t, double &p1, double &p2, double &p3) const = 0;
+
 		pfa_handle *handle(const bool is_volume, const int n_basis, const std::vector<basis::ElementBases> &bases,
 						   const std::vector<basis::ElementBases> &gbases, const AssemblyValsCache &cache, const double t) const
 		{
-			return dev_.get(PFA_NEOHOOKEAN, is_volume, n_basis, bases, gbases, cache, t,
-							[&](const ElementAssemblyValues &vals, const int q, double &lambda, double &mu) {
-								lame_params().lambda_mu(vals.quadrature.points.row(q), vals.val.row(q), t, vals.element_id, lambda, mu);
-							});
+			return dev_.get(MATERIAL, is_volume, n_basis, bases, gbases, cache, t,
+							[&](const ElementAssemblyValues &vals, const int q, double &p1, double &p2, double &p3) { material_params(vals, q, t, p1, p2, p3); });
 		}
 		DeviceAssembly dev_;
 		mutable std::vector<double> values_;
+	};
+
+	/// Drop-in for NeoHookeanElasticity ("NeoHookean" in AssemblerUtils::make_assembler).
+	class NeoHookeanElasticityB200 : public NLAssemblerB200<NeoHookeanElasticity, PFA_NEOHOOKEAN>
+	{
+	protected:
+		// Bezier evaluator of the Jacobian (NeoHookeanElasticity.cpp:357-359, 475-498, 567-587): energy, gradient and Hessian
+		// all use it, so the whole assembler stays on the CPU path when it is enabled
+		bool on_device() const override { return !use_robust_jacobian; }
+		void material_params(const ElementAssemblyValues &vals, const int q, const double t, double &lambda, double &mu, double &) const override
+		{
+			lame_params().lambda_mu(vals.quadrature.points.row(q), vals.val.row(q), t, vals.element_id, lambda, mu);
+		}
+	};
+
+	/// Drop-in for SaintVenantElasticity ("SaintVenant") when its elasticity tensor is the isotropic one of (lambda, mu)
+	/// (ElasticityTensor::set_from_lambda_mu / set_from_young_poisson, MatParams.cpp:211-276: C_ii = lambda + 2 mu, C_ij = lambda
+	/// for i != j < 3, C_kk = mu for k >= 3, zero otherwise). Any other tensor (set_from_entries, orthotropic, rotated by a
+	/// fiber direction) keeps the CPU path.
+	class SaintVenantElasticityB200 : public NLAssemblerB200<SaintVenantElasticity, PFA_SAINT_VENANT>
+	{
+	protected:
+		bool on_device() const override
+		{
+			if (size() != 3)
+				return false;
+			const double lambda = stifness_tensor(0, 1), mu = stifness_tensor(3, 3);
+			const double tol = 1e-14 * (std::abs(lambda) + std::abs(mu));
+			for (int i = 0; i < 6; ++i)
+				for (int j = 0; j < 6; ++j)
+				{
+					const double want = i == j ? (i < 3 ? lambda + 2 * mu : mu) : (i < 3 && j < 3 ? lambda : 0.0);
+					if (std::abs(stifness_tensor(i, j) - want) > tol)
+						return false;
+				}
+			return true;
+		}
+		void material_params(const ElementAssemblyValues &, const int, const double, double &lambda, double &mu, double &) const override
+		{
+			lambda = stifness_tensor(0, 1);
+			mu = stifness_tensor(3, 3);
+		}
+	};
+
+	/// Drop-in for MooneyRivlinElasticity ("MooneyRivlin", a GenericElastic): c1, c2, k are evaluated per element as in
+	/// MooneyRivlinElasticity::elastic_energy (MooneyRivlinElasticity.hpp:32-34: GenericMatParam(p, t, el_id) with
+	/// p = vals.val.row(q)).
+	class MooneyRivlinElasticityB200 : public NLAssemblerB200<MooneyRivlinElasticity, PFA_MOONEY_RIVLIN>
+	{
+	protected:
+		bool on_device() const override { return size() == 3; }
+		void material_params(const ElementAssemblyValues &vals, const int q, const double t, double &p1, double &p2, double &p3) const override
+		{
+			p1 = c1()(vals.val.row(q), t, vals.element_id);
+			p2 = c2()(vals.val.row(q), t, vals.element_id);
+			p3 = k()(vals.val.row(q), t, vals.element_id);
+		}
 	};
 
 	/// Drop-in for Laplacian ("Laplacian"): LinearAssembler::assemble only.
@@ -326,7 +407,7 @@ namespace polyfem::assembler::b200
 			if (is_mass)
 				return Laplacian::assemble(is_volume, n_basis, bases, gbases, cache, t, stiffness, is_mass);
 			pfa_handle *h = dev_.get(PFA_LAPLACIAN, is_volume, n_basis, bases, gbases, cache, t,
-									 [](const ElementAssemblyValues &, const int, double &lambda, double &mu) { lambda = mu = 0; });
+									 [](const ElementAssemblyValues &, const int, double &lambda, double &mu, double &) { lambda = mu = 0; });
 			int64_t nnz;
 			pfa_sizes(h, nullptr, nullptr, &nnz);
 			values_.resize(nnz);
@@ -351,7 +432,7 @@ namespace polyfem::assembler::b200
 			if (size() != 3)
 				return Mass::assemble(is_volume, n_basis, bases, gbases, cache, t, stiffness, is_mass);
 			pfa_handle *h = dev_.get(PFA_MASS, is_volume, n_basis, bases, gbases, cache, t,
-									 [&](const ElementAssemblyValues &vals, const int q, double &rho, double &unused) {
+									 [&](const ElementAssemblyValues &vals, const int q, double &rho, double &unused, double &) {
 										 rho = density()(vals.quadrature.points.row(q), vals.val.row(q), t, vals.element_id);
 										 unused = 0;
 									 });
@@ -447,7 +528,7 @@ namespace polyfem::assembler::b200
 						   const std::vector<basis::ElementBases> &gbases, const AssemblyValsCache &cache, const double t) const
 		{
 			return dev_.get(PFA_LINEAR_ELASTICITY, is_volume, n_basis, bases, gbases, cache, t,
-							[&](const ElementAssemblyValues &vals, const int q, double &lambda, double &mu) {
+							[&](const ElementAssemblyValues &vals, const int q, double &lambda, double &mu, double &) {
 								lame_params().lambda_mu(vals.quadrature.points.row(q), vals.val.row(q), t, vals.element_id, lambda, mu);
 							});
 		}

@@ -189,6 +189,27 @@ namespace polyfem
 			void add_multimaterial(const int index, const json &params, const Units &units, const std::string &root_path) override; // NeoHookeanElasticity.hpp:53
 			const LameParameters &lame_params() const; // :56
 		};
+		class SaintVenantElasticity : public ElasticityNLAssembler // SaintVenantElasticity.hpp:11-53
+		{
+		public:
+			std::string name() const override;
+			void set_size(const int size) override;                                                                                // :26
+			double stifness_tensor(int i, int j) const;                                                                            // :29
+			void add_multimaterial(const int index, const json &params, const Units &units, const std::string &root_path) override; // :31
+		};
+		struct GenericMatParam // assembler/MatParams.hpp (call form of MooneyRivlinElasticity.hpp:32-34)
+		{
+			double operator()(const Eigen::RowStub &p, double t, int el_id) const;
+		};
+		class MooneyRivlinElasticity : public ElasticityNLAssembler // MooneyRivlinElasticity.hpp:9-54 (GenericElastic<...>)
+		{
+		public:
+			std::string name() const override;
+			void add_multimaterial(const int index, const json &params, const Units &units, const std::string &root_path) override; // :16
+			const GenericMatParam &c1() const;                                                                                     // :18
+			const GenericMatParam &c2() const;
+			const GenericMatParam &k() const;
+		};
 		class LinearElasticity : public LinearAssembler, public ElasticityNLAssembler // LinearElasticity.hpp
 		{
 		public:

@@ -21,6 +21,8 @@ int main()
 	b200::LinearElasticityB200 le;
 	b200::LaplacianB200 lap;
 	b200::MassB200 mass;
+	b200::SaintVenantElasticityB200 sv;
+	b200::MooneyRivlinElasticityB200 mr;
 	std::vector<basis::ElementBases> bases, gbases;
 	AssemblyValsCache cache;
 	Eigen::MatrixXd x, rhs;
@@ -32,6 +34,12 @@ int main()
 	a.assemble_gradient(true, 1, bases, gbases, cache, 0.0, 1.0, x, x, rhs);
 	a.assemble_hessian(true, 1, false, bases, gbases, cache, 0.0, 1.0, x, x, mc, K);
 	static_cast<const Assembler &>(le).assemble(true, 1, bases, gbases, cache, 0.0, K);
+	for (const Assembler *nl : {static_cast<const Assembler *>(&sv), static_cast<const Assembler *>(&mr)})
+	{
+		e += nl->assemble_energy(true, bases, gbases, cache, 0.0, 1.0, x, x);
+		nl->assemble_gradient(true, 1, bases, gbases, cache, 0.0, 1.0, x, x, rhs);
+		nl->assemble_hessian(true, 1, true, bases, gbases, cache, 0.0, 1.0, x, x, mc, K);
+	}
 	static_cast<const Assembler &>(lap).assemble(true, 1, bases, gbases, cache, 0.0, K);
 	static_cast<const Assembler &>(mass).assemble(true, 1, bases, gbases, cache, 0.0, K, true);
 	pfa_handle *h = nullptr;
