@@ -272,6 +272,25 @@ def config_dict(cfg, mesh, h, world, parallelism):
     return d
 
 
+def bind_to_gpu_cpus(index):
+    """Multi-rank runs: pin this process to the CPUs NVML reports as closest to its GPU, so that the pinned host buffers of the
+    end-to-end leg are first touched on that GPU's NUMA node (the D2H copies of 8 ranks otherwise cross the socket link).
+    Best effort: returns the number of CPUs bound to, or None."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        hdl = pynvml.nvmlDeviceGetHandleByIndex(index)
+        words = pynvml.nvmlDeviceGetCpuAffinity(hdl, (os.cpu_count() + 63) // 64)
+        cpus = [64 * w + b for w, word in enumerate(words) for b in range(64) if (word >> b) & 1]
+        allowed = sorted(set(cpus) & set(os.sched_getaffinity(0)))
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            return len(allowed)
+    except Exception:
+        pass
+    return None
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -318,6 +337,7 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: the assembly path has no CPU fallback")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    numa = bind_to_gpu_cpus(local_rank) if world > 1 else None
     if world > 1:
         # the interface rows go point-to-point to the neighbouring slab: let NCCL use more channels
         # than its 1-2 default for send/recv over NVSwitch
@@ -615,7 +635,7 @@ def main():
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         e2e = {"value": n_el_total / float(tt.item()), "unit": UNIT, "h2d_bytes_per_step": int(8 * h.ndof),
                "d2h_bytes_per_step": int(8 * (1 + h.ndof + h.nnz)), "ms_per_step": float(tt.item()) * 1e3,
-               "steps": args.e2e_steps, "buffers": "pinned host, per rank"}
+               "steps": args.e2e_steps, "buffers": "pinned host, per rank", "cpus_bound_per_rank": numa}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
