@@ -60,10 +60,16 @@ extern "C"
 		                            * tensor of (lambda, mu) (MatParams.cpp:211-253): an ElasticityNLAssembler whose energy is
 		                            * differentiated by autodiff in the reference; here the closed forms
 		                            * P = F S, S = 2 mu E + lambda tr(E) I and its tangent. Any order P1..P4 (generic kernel). */
-		PFA_MOONEY_RIVLIN = 5      /* assembler/MooneyRivlinElasticity.hpp, name() == "MooneyRivlin" (GenericElastic, autodiff in the
+		PFA_MOONEY_RIVLIN = 5,     /* assembler/MooneyRivlinElasticity.hpp, name() == "MooneyRivlin" (GenericElastic, autodiff in the
 		                            * reference): psi = c1 (I1~ - 3) + c2 (I2~ - 3) + k/2 ln^2 J on the isochoric invariants. Parameters
 		                            * (c1, c2, k) = (lambda[], mu[], param3[]). Here: the chain rule over (I1, I2, J) of F in closed
 		                            * form (generic kernel, any order P1..P4). */
+		PFA_VISCOUS_DAMPING = 6    /* assembler/ViscousDamping.cpp, name() == "ViscousDamping": R = psi |dE/dt|^2 + phi/2 tr(dE/dt)^2,
+		                            * dE/dt = sym(dF/dt^T F), dF/dt = (F - F_prev) / dt; (psi, phi) = (lambda[], mu[]). The previous
+		                            * displacement and dt of the NLAssembler virtuals come through pfa_set_previous; until it is
+		                            * called every result is zero (the reference's x_prev.size() != x.size() branch). Closed form:
+		                            * with A = 2 F - F_prev the tangent is SaintVenant's with F -> A, mu -> psi / dt^2,
+		                            * lambda -> phi / dt^2, S -> 2 (2 psi dE/dt + phi tr(dE/dt) I) / dt. */
 	} pfa_material;
 
 	/* What the shim reads out of std::vector<basis::ElementBases> bases / gbases and the
@@ -194,6 +200,9 @@ extern "C"
 
 	/* Re-upload Lame parameters when t changes (Assembler::set_materials, Assembler.cpp:97-151). */
 	int pfa_set_materials(pfa_handle *h, const double *lambda, const double *mu, int32_t material_stride);
+	/* displacement_prev and dt of the NLAssembler virtuals (Assembler.hpp:79-125), read by PFA_VISCOUS_DAMPING only: x_prev[ndof]
+	 * (host or device pointer) is copied; NULL = no previous displacement. */
+	int pfa_set_previous(pfa_handle *h, const double *x_prev, double dt);
 	/* the same for materials with three parameters (PFA_MOONEY_RIVLIN: c1, c2, k) */
 	int pfa_set_material_params(pfa_handle *h, const double *p1, const double *p2, const double *p3, int32_t material_stride);
 

@@ -291,6 +291,10 @@ namespace
 		// AssemblyValsCache (AssemblyValsCache.cpp:11-67)
 		std::vector<ElementAssemblyValues> cache;
 
+		// displacement_prev / dt of the NL entry points (ViscousDamping)
+		std::vector<double> x_prev;
+		double dt = 1.0;
+
 		// result of the last matrix assembly
 		std::vector<int32_t> outer, inner;
 		std::vector<double> values;
@@ -391,6 +395,8 @@ namespace
 		const std::vector<double> &da;
 		double lambda, mu; // params_.lambda_mu(...) for a per-element constant material
 		double param3 = 0.0; // MooneyRivlin: (c1, c2, k) = (lambda, mu, param3)
+		const double *x_prev = nullptr; // displacement_prev (ViscousDamping); nullptr: sizes differ in the reference's terms
+		double dt = 1.0;
 	};
 
 	// =======================================================================================
@@ -843,6 +849,180 @@ namespace
 	}
 
 	// =======================================================================================
+	// ViscousDamping (assembler/ViscousDamping.cpp): R = psi |dE/dt|^2 + phi/2 tr(dE/dt)^2 with
+	// dE/dt = sym(dF/dt^T F), dF/dt = (F - F_prev) / dt. (psi, phi) = (data.lambda, data.mu).
+	// =======================================================================================
+	struct VdPoint
+	{
+		double F[9], Fd[9], Ed[9]; // def_grad, dFdt, dEdt (row-major)
+	};
+
+	// local_disp / local_prev_disp / local_vel and, per point, def_grad = local_disp^T delF_delU + I, dFdt = local_vel^T delF_delU
+	// (ViscousDamping.cpp:127-160, 304-334), delF_delU = grad * jac_it = grad_t_m
+	void vd_point(const NLData &data, const std::vector<double> &u, const std::vector<double> &vel, int p, VdPoint &pt)
+	{
+		for (int k = 0; k < 9; ++k)
+			pt.F[k] = pt.Fd[k] = 0.0;
+		for (int i = 0; i < data.vals.n_loc; ++i)
+		{
+			const double *gt = data.vals.gt(i, p);
+			for (int a = 0; a < 3; ++a)
+				for (int d = 0; d < 3; ++d)
+				{
+					pt.F[a * 3 + d] += u[size_t(i) * 3 + a] * gt[d];
+					pt.Fd[a * 3 + d] += vel[size_t(i) * 3 + a] * gt[d];
+				}
+		}
+		pt.F[0] += 1.0;
+		pt.F[4] += 1.0;
+		pt.F[8] += 1.0;
+		double M[9]; // dFdt^T F
+		for (int r = 0; r < 3; ++r)
+			for (int c = 0; c < 3; ++c)
+				M[r * 3 + c] = pt.Fd[0 + r] * pt.F[0 + c] + pt.Fd[3 + r] * pt.F[3 + c] + pt.Fd[6 + r] * pt.F[6 + c];
+		for (int r = 0; r < 3; ++r)
+			for (int c = 0; c < 3; ++c)
+				pt.Ed[r * 3 + c] = (M[r * 3 + c] + M[c * 3 + r]) / 2.;
+	}
+
+	void vd_local_fields(const NLData &data, std::vector<double> &u, std::vector<double> &vel)
+	{
+		const int n_loc = data.vals.n_loc;
+		u.assign(size_t(n_loc) * 3, 0.0);
+		vel.assign(size_t(n_loc) * 3, 0.0);
+		for (int i = 0; i < n_loc; ++i)
+			for (int d = 0; d < 3; ++d)
+			{
+				const size_t g = size_t(data.vals.global[i]) * 3 + d;
+				u[size_t(i) * 3 + d] = data.x[g];
+				vel[size_t(i) * 3 + d] = (data.x[g] - data.x_prev[g]) / data.dt;
+			}
+	}
+
+	// ViscousDamping.cpp:297-342 compute_energy
+	double viscous_damping_energy(const NLData &data)
+	{
+		if (data.x_prev == nullptr)
+			return 0.0;
+		std::vector<double> u, vel;
+		vd_local_fields(data, u, vel);
+		double energy = 0.0;
+		for (int p = 0; p < data.vals.n_qp; ++p)
+		{
+			VdPoint pt;
+			vd_point(data, u, vel, p, pt);
+			double sq = 0.0;
+			for (int k = 0; k < 9; ++k)
+				sq += pt.Ed[k] * pt.Ed[k];
+			const double tr = pt.Ed[0] + pt.Ed[4] + pt.Ed[8];
+			energy += (data.lambda * sq + 0.5 * data.mu * tr * tr) * data.da[p];
+		}
+		return energy;
+	}
+
+	// ViscousDamping.cpp:122-170 assemble_gradient: G += delF_delU ((dFdt + F / dt) tmp)^T da, tmp = 2 psi dEdt + phi tr(dEdt) I
+	void viscous_damping_gradient(const NLData &data, std::vector<double> &g)
+	{
+		const int n_loc = data.vals.n_loc;
+		g.assign(size_t(n_loc) * 3, 0.0);
+		if (data.x_prev == nullptr)
+			return;
+		std::vector<double> u, vel;
+		vd_local_fields(data, u, vel);
+		for (int p = 0; p < data.vals.n_qp; ++p)
+		{
+			VdPoint pt;
+			vd_point(data, u, vel, p, pt);
+			const double tr = pt.Ed[0] + pt.Ed[4] + pt.Ed[8];
+			double tmp[9], lhs[9], S[9];
+			for (int k = 0; k < 9; ++k)
+			{
+				tmp[k] = 2 * data.lambda * pt.Ed[k] + (k % 4 == 0 ? data.mu * tr : 0.0);
+				lhs[k] = pt.Fd[k] + pt.F[k] / data.dt;
+			}
+			for (int r = 0; r < 3; ++r)
+				for (int c = 0; c < 3; ++c)
+					S[r * 3 + c] = lhs[r * 3 + 0] * tmp[0 + c] + lhs[r * 3 + 1] * tmp[3 + c] + lhs[r * 3 + 2] * tmp[6 + c];
+			for (int i = 0; i < n_loc; ++i)
+			{
+				const double *gt = data.vals.gt(i, p);
+				for (int a = 0; a < 3; ++a)
+					g[size_t(i) * 3 + a] += (gt[0] * S[a * 3 + 0] + gt[1] * S[a * 3 + 1] + gt[2] * S[a * 3 + 2]) * data.da[p];
+			}
+		}
+	}
+
+	// ViscousDamping.cpp:16-62 compute_stress_grad_aux: the three 9 x 9 second derivatives of R with respect to (F, dF/dt),
+	// F(i, j) at index i * 3 + j
+	void vd_second_derivatives(const VdPoint &pt, double psi, double phi, double *RFF, double *RFD, double *RDD)
+	{
+		double dEdF[81], dEdD[81]; // d dEdt(i,j) / d F(p,q), / d dFdt(p,q)
+		for (int k = 0; k < 81; ++k)
+			dEdF[k] = dEdD[k] = RFF[k] = RFD[k] = RDD[k] = 0.0;
+		for (int i = 0; i < 3; ++i)
+			for (int j = 0; j < 3; ++j)
+				for (int p = 0; p < 3; ++p)
+				{
+					dEdF[(i * 3 + j) * 9 + p * 3 + j] += pt.Fd[p * 3 + i] / 2.;
+					dEdD[(i * 3 + j) * 9 + p * 3 + j] += pt.F[p * 3 + i] / 2.;
+					dEdF[(i * 3 + j) * 9 + p * 3 + i] += pt.Fd[p * 3 + j] / 2.;
+					dEdD[(i * 3 + j) * 9 + p * 3 + i] += pt.F[p * 3 + j] / 2.;
+				}
+		for (int i = 0; i < 3; ++i)
+			for (int j = 0; j < 3; ++j)
+			{
+				const int idx = i * 3 + j;
+				for (int k = 0; k < 3; ++k)
+				{
+					for (int c = 0; c < 9; ++c)
+					{
+						RFF[idx * 9 + c] += (2 * psi) * pt.Fd[i * 3 + k] * dEdF[(k * 3 + j) * 9 + c] + phi * pt.Fd[i * 3 + j] * dEdF[(k * 3 + k) * 9 + c];
+						RDD[idx * 9 + c] += (2 * psi) * pt.F[i * 3 + k] * dEdD[(k * 3 + j) * 9 + c] + phi * pt.F[i * 3 + j] * dEdD[(k * 3 + k) * 9 + c];
+						RFD[idx * 9 + c] += (2 * psi) * (pt.Fd[i * 3 + k] * dEdD[(k * 3 + j) * 9 + c]) + phi * (dEdD[(k * 3 + k) * 9 + c] * pt.Fd[i * 3 + j]);
+					}
+					RFD[idx * 9 + i * 3 + k] += 2 * psi * pt.Ed[k * 3 + j];
+					RFD[idx * 9 + idx] += phi * pt.Ed[k * 3 + k];
+				}
+			}
+	}
+
+	// ViscousDamping.cpp:173-229 assemble_hessian: sum_p B^T (RFF + (RFD + RFD^T) / dt + RDD / dt^2) B da with
+	// B(3 j + d, 3 i + j) = delF_delU(i, d)
+	void viscous_damping_hessian(const NLData &data, std::vector<double> &h)
+	{
+		const int n_loc = data.vals.n_loc, N = 3 * n_loc;
+		h.assign(size_t(N) * N, 0.0);
+		if (data.x_prev == nullptr)
+			return;
+		std::vector<double> u, vel;
+		vd_local_fields(data, u, vel);
+		for (int p = 0; p < data.vals.n_qp; ++p)
+		{
+			VdPoint pt;
+			vd_point(data, u, vel, p, pt);
+			double RFF[81], RFD[81], RDD[81], T[81];
+			vd_second_derivatives(pt, data.lambda, data.mu, RFF, RFD, RDD);
+			for (int r = 0; r < 9; ++r)
+				for (int c = 0; c < 9; ++c)
+					T[r * 9 + c] = RFF[r * 9 + c] + (1. / data.dt) * (RFD[r * 9 + c] + RFD[c * 9 + r]) + (1. / data.dt / data.dt) * RDD[r * 9 + c];
+			for (int i = 0; i < n_loc; ++i)
+				for (int j = 0; j < n_loc; ++j)
+				{
+					const double *gi = data.vals.gt(i, p), *gj = data.vals.gt(j, p);
+					for (int a = 0; a < 3; ++a)
+						for (int b = 0; b < 3; ++b)
+						{
+							double s = 0.0;
+							for (int d = 0; d < 3; ++d)
+								for (int d2 = 0; d2 < 3; ++d2)
+									s += gi[d] * T[(a * 3 + d) * 9 + b * 3 + d2] * gj[d2];
+							h[size_t(i * 3 + a) * N + j * 3 + b] += s * data.da[p];
+						}
+				}
+		}
+	}
+
+	// =======================================================================================
 	// ipc::project_to_psd (ipc-toolkit, source not in /root/reference; called at
 	// assembler/Assembler.cpp:693-694). Documented behaviour: symmetric eigendecomposition,
 	// return A unchanged if the smallest eigenvalue is >= 0, else clamp negative eigenvalues
@@ -1255,6 +1435,8 @@ namespace
 			return saint_venant_energy<double>(data);
 		if (pb.d.material == ORACLE_MOONEY_RIVLIN)
 			return mooney_rivlin_energy<double>(data);
+		if (pb.d.material == ORACLE_VISCOUS_DAMPING)
+			return viscous_damping_energy(data);
 		return linear_elasticity_energy<double>(data);
 	}
 	void local_gradient(const Problem &pb, const NLData &data, std::vector<double> &g)
@@ -1262,6 +1444,11 @@ namespace
 		if (pb.d.material == ORACLE_NEOHOOKEAN)
 		{
 			neohookean_gradient(data, g);
+			return;
+		}
+		if (pb.d.material == ORACLE_VISCOUS_DAMPING)
+		{
+			viscous_damping_gradient(data, g);
 			return;
 		}
 		// utils/ElasticityUtils.cpp:81-... gradient_from_energy: autodiff gradient
@@ -1275,6 +1462,11 @@ namespace
 		if (pb.d.material == ORACLE_NEOHOOKEAN)
 		{
 			neohookean_hessian(data, h);
+			return;
+		}
+		if (pb.d.material == ORACLE_VISCOUS_DAMPING)
+		{
+			viscous_damping_hessian(data, h);
 			return;
 		}
 		const D2 e = pb.d.material == ORACLE_SAINT_VENANT   ? saint_venant_energy<D2>(data)
@@ -1300,6 +1492,15 @@ struct oracle_cache
 
 extern "C"
 {
+	void oracle_set_previous(oracle_problem *op, const double *x_prev, double dt)
+	{
+		Problem &pb = op->pb;
+		pb.x_prev.clear();
+		if (x_prev)
+			pb.x_prev.assign(x_prev, x_prev + size_t(pb.d.n_bases) * pb.size);
+		pb.dt = dt;
+	}
+
 	oracle_problem *oracle_create(const oracle_desc *desc)
 	{
 		auto *op = new oracle_problem();
@@ -1368,7 +1569,7 @@ extern "C"
 			{
 				pb.cache_compute(e, vals);
 				compute_da(vals, da);
-				local += local_energy(pb, NLData{vals, x, da, pb.lambda[e], pb.mu[e], pb.param3[e]});
+				local += local_energy(pb, NLData{vals, x, da, pb.lambda[e], pb.mu[e], pb.param3[e], pb.x_prev.empty() ? nullptr : pb.x_prev.data(), pb.dt});
 			}
 			partial[tid] = local;
 		});
@@ -1389,7 +1590,7 @@ extern "C"
 			{
 				pb.cache_compute(e, vals);
 				compute_da(vals, da);
-				out[e] = local_energy(pb, NLData{vals, x, da, pb.lambda[e], pb.mu[e], pb.param3[e]});
+				out[e] = local_energy(pb, NLData{vals, x, da, pb.lambda[e], pb.mu[e], pb.param3[e], pb.x_prev.empty() ? nullptr : pb.x_prev.data(), pb.dt});
 			}
 		});
 	}
@@ -1410,7 +1611,7 @@ extern "C"
 			{
 				pb.cache_compute(e, vals);
 				compute_da(vals, da);
-				local_gradient(pb, NLData{vals, x, da, pb.lambda[e], pb.mu[e], pb.param3[e]}, val);
+				local_gradient(pb, NLData{vals, x, da, pb.lambda[e], pb.mu[e], pb.param3[e], pb.x_prev.empty() ? nullptr : pb.x_prev.data(), pb.dt}, val);
 				for (int j = 0; j < vals.n_loc; ++j)
 					for (int m = 0; m < size; ++m)
 						vec[size_t(vals.global[j]) * size + m] += val[size_t(j) * size + m] * 1.0; // (:616-629)
@@ -1459,7 +1660,7 @@ extern "C"
 				pb.cache_compute(e, vals);
 				compute_da(vals, ls.da);
 				const int n_loc = vals.n_loc, N = n_loc * size;
-				local_hessian(pb, NLData{vals, x, ls.da, pb.lambda[e], pb.mu[e], pb.param3[e]}, H);
+				local_hessian(pb, NLData{vals, x, ls.da, pb.lambda[e], pb.mu[e], pb.param3[e], pb.x_prev.empty() ? nullptr : pb.x_prev.data(), pb.dt}, H);
 				if (psd)
 					project_to_psd(N, H); // (:693-694)
 				for (int i = 0; i < n_loc; ++i)
@@ -1579,7 +1780,7 @@ extern "C"
 	{
 		pb.cache_compute(e, vals);
 		compute_da(vals, da);
-		return NLData{vals, x, da, pb.lambda[e], pb.mu[e], pb.param3[e]};
+		return NLData{vals, x, da, pb.lambda[e], pb.mu[e], pb.param3[e], pb.x_prev.empty() ? nullptr : pb.x_prev.data(), pb.dt};
 	}
 
 	double oracle_local_energy(oracle_problem *op, int e, const double *x, int autodiff)

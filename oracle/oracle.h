@@ -49,7 +49,11 @@ extern "C"
 		ORACLE_MASS = 3, /* assembler/Mass.cpp: LinearAssembler with rho * phi_i * phi_j on the block diagonal */
 		ORACLE_SAINT_VENANT = 4, /* assembler/SaintVenantElasticity.cpp with the isotropic tensor of (lambda, mu) */
 		/* assembler/MooneyRivlinElasticity.hpp through GenericElastic (full autodiff): parameters c1 = lambda[], c2 = mu[], k = param3[] */
-		ORACLE_MOONEY_RIVLIN = 5
+		ORACLE_MOONEY_RIVLIN = 5,
+		/* assembler/ViscousDamping.cpp (NLAssembler that depends on the previous displacement and dt): parameters
+		 * (psi, phi) = (lambda[], mu[]); oracle_set_previous supplies x_prev and dt, without it every result is zero
+		 * (the reference's `data.x_prev.size() != data.x.size()` branch) */
+		ORACLE_VISCOUS_DAMPING = 6
 	};
 
 	typedef struct
@@ -87,6 +91,10 @@ extern "C"
 	oracle_problem *oracle_create(const oracle_desc *desc);
 	void oracle_destroy(oracle_problem *p);
 	int oracle_size(const oracle_problem *p); /* Assembler::size(): 3, or 1 for Laplacian */
+
+	/* displacement_prev and dt of the NLAssembler entry points (Assembler.hpp:79-125), used by ORACLE_VISCOUS_DAMPING only;
+	 * x_prev NULL: no previous displacement */
+	void oracle_set_previous(oracle_problem *p, const double *x_prev, double dt);
 
 	/* NLAssembler entry points (assembler/Assembler.cpp:495-771) */
 	double oracle_assemble_energy(oracle_problem *p, const double *x);

@@ -17,8 +17,9 @@ _LIB = None
 NEOHOOKEAN, LINEAR_ELASTICITY, LAPLACIAN, MASS = 0, 1, 2, 3
 SAINT_VENANT = 4
 MOONEY_RIVLIN = 5
+VISCOUS_DAMPING = 6
 MATERIAL_IDS = {"NeoHookean": NEOHOOKEAN, "LinearElasticity": LINEAR_ELASTICITY, "Laplacian": LAPLACIAN, "Mass": MASS, "SaintVenant": SAINT_VENANT,
-                "MooneyRivlin": MOONEY_RIVLIN}
+                "MooneyRivlin": MOONEY_RIVLIN, "ViscousDamping": VISCOUS_DAMPING}
 
 _dp = ctypes.POINTER(ctypes.c_double)
 _ip = ctypes.POINTER(ctypes.c_int32)
@@ -57,6 +58,8 @@ def lib():
     L.oracle_create.argtypes = [ctypes.POINTER(_Desc)]
     L.oracle_destroy.argtypes = [vp]
     L.oracle_size.argtypes = [vp]
+    L.oracle_set_previous.restype = None
+    L.oracle_set_previous.argtypes = [vp, _dp, ctypes.c_double]
     L.oracle_assemble_energy.restype = ctypes.c_double
     L.oracle_assemble_energy.argtypes = [vp, _dp]
     L.oracle_assemble_energy_per_element.argtypes = [vp, _dp, _dp]
@@ -177,6 +180,10 @@ class OracleProblem:
         x = np.ascontiguousarray(x, dtype=np.float64).reshape(-1)
         assert x.size == self.ndof
         return x
+
+    def set_previous(self, x_prev, dt):
+        """displacement_prev and dt of the NL entry points (ViscousDamping); x_prev None: no previous displacement"""
+        lib().oracle_set_previous(self._h, None if x_prev is None else _d(self._x(x_prev)), float(dt))
 
     def assemble_energy(self, x):
         x = self._x(x)
@@ -368,6 +375,8 @@ def problem_from_mesh(mesh, material, E=1e5, nu=0.3, order=None, rho=1.0, **kw):
         k = kw.pop("k", lam + 2.0 * mu / 3.0)
         lam, mu = c1, c2
         kw["param3"] = k
+    if material == "ViscousDamping":  # (psi, phi) in the (lam, mu) slots
+        lam, mu = kw.pop("psi", 30.0), kw.pop("phi", 20.0)
     return OracleProblem(material, mesh.conn, mesh.vertices, mesh.n_bases, t["points"], t["weights"], t["grad"],
                          lam=lam, mu=mu, basis_order=mesh.p,
                          node_lattice=np.array(tables.P_NODES_LATTICE[mesh.p], dtype=np.int32), **kw)

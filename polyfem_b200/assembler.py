@@ -238,8 +238,12 @@ class Mass(LinearAssembler):
 class NLAssembler(Assembler):
     """Assembler.hpp:236-300, NLAssembler::assemble_* (Assembler.cpp:495-771)."""
 
+    def _before_call(self, h, dt, displacement, displacement_prev):
+        """materials that read dt / displacement_prev hand them to the handle here (ViscousDamping)"""
+
     def assemble_energy(self, is_volume, bases, gbases, cache, t, dt, displacement, displacement_prev):
         h = self._get_handle(bases.n_bases, bases, gbases, cache)
+        self._before_call(h, dt, displacement, displacement_prev)
         try:
             return h.energy(displacement)
         except capi.PfaError as ex:
@@ -247,6 +251,7 @@ class NLAssembler(Assembler):
 
     def assemble_energy_per_element(self, is_volume, bases, gbases, cache, t, dt, displacement, displacement_prev):
         h = self._get_handle(bases.n_bases, bases, gbases, cache)
+        self._before_call(h, dt, displacement, displacement_prev)
         try:
             return h.energy_per_element(displacement)
         except capi.PfaError as ex:
@@ -254,6 +259,7 @@ class NLAssembler(Assembler):
 
     def assemble_gradient(self, is_volume, n_basis, bases, gbases, cache, t, dt, displacement, displacement_prev):
         h = self._get_handle(n_basis, bases, gbases, cache)
+        self._before_call(h, dt, displacement, displacement_prev)
         try:
             return h.gradient(displacement).reshape(-1, 1)
         except capi.PfaError as ex:
@@ -262,6 +268,7 @@ class NLAssembler(Assembler):
     def assemble_hessian(self, is_volume, n_basis, project_to_psd, bases, gbases, cache, t, dt,
                          displacement, displacement_prev, mat_cache: MatrixCache | None = None):
         h = self._get_handle(n_basis, bases, gbases, cache)
+        self._before_call(h, dt, displacement, displacement_prev)
         try:
             values = h.hessian(displacement, project_to_psd)
         except capi.PfaError as ex:
@@ -319,6 +326,33 @@ class MooneyRivlinElasticity(NLAssembler):
         return self._per_element(bases, 2)
 
 
+class ViscousDamping(NLAssembler):
+    """assembler/ViscousDamping.{hpp,cpp}; name() == "ViscousDamping". Material JSON: psi, phi (ViscousDamping.cpp:64-73).
+    Reads displacement_prev and dt of the NL virtuals; a displacement_prev of another size means "no previous step" and
+    gives zeros (ViscousDamping.cpp:125-126)."""
+    _material = "ViscousDamping"
+
+    def add_multimaterial(self, index: int, params: dict):
+        old = self._materials.get("default", (0.0, 0.0))
+        val = (float(params.get("psi", old[0])), float(params.get("phi", old[1])))
+        self._materials[int(params.get("id", index))] = val
+        self._materials["default"] = val
+        self._lam_mu_arrays = None
+
+    def set_params(self, psi: float, phi: float):
+        self.add_multimaterial(0, {"psi": psi, "phi": phi})
+        self.invalidate()
+
+    def _before_call(self, h, dt, displacement, displacement_prev):
+        prev = None if displacement_prev is None else np.asarray(displacement_prev)
+        if prev is not None and prev.size != np.asarray(displacement).size:
+            prev = None
+        try:
+            h.set_previous(prev, dt)
+        except capi.PfaError as ex:
+            log_and_throw_error(str(ex))
+
+
 class LinearElasticity(NLAssembler, LinearAssembler):
     """assembler/LinearElasticity.{hpp,cpp}: linear `assemble` plus the NL energy / gradient /
     Hessian used when a linear material sits inside a nonlinear solve."""
@@ -337,7 +371,7 @@ class Laplacian(LinearAssembler):
 def make_assembler(formulation: str, device: int = 0) -> Assembler:
     """AssemblerUtils::make_assembler (AssemblerUtils.cpp:55-122) for the hot-path names."""
     table = {"NeoHookean": NeoHookeanElasticity, "LinearElasticity": LinearElasticity, "Laplacian": Laplacian, "Mass": Mass,
-             "SaintVenant": SaintVenantElasticity, "MooneyRivlin": MooneyRivlinElasticity}
+             "SaintVenant": SaintVenantElasticity, "MooneyRivlin": MooneyRivlinElasticity, "ViscousDamping": ViscousDamping}
     if formulation not in table:
         log_and_throw_error(f"Unsupported assembler on the B200 path: {formulation}")
     return table[formulation](device)

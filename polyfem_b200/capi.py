@@ -16,9 +16,9 @@ LIB_PATH = os.environ.get("PFA_LIB", os.path.join(_HERE, "libpfa.so"))  # PFA_LI
 
 PFA_OK = 0
 PFA_ERR_INVALID, PFA_ERR_UNSUPPORTED, PFA_ERR_CUDA, PFA_ERR_NOMEM, PFA_ERR_NO_DEVICE = -1, -2, -3, -4, -5
-NEOHOOKEAN, LINEAR_ELASTICITY, LAPLACIAN, MASS, SAINT_VENANT, MOONEY_RIVLIN = 0, 1, 2, 3, 4, 5
+NEOHOOKEAN, LINEAR_ELASTICITY, LAPLACIAN, MASS, SAINT_VENANT, MOONEY_RIVLIN, VISCOUS_DAMPING = 0, 1, 2, 3, 4, 5, 6
 MATERIAL_IDS = {"NeoHookean": NEOHOOKEAN, "LinearElasticity": LINEAR_ELASTICITY, "Laplacian": LAPLACIAN, "Mass": MASS, "SaintVenant": SAINT_VENANT,
-                "MooneyRivlin": MOONEY_RIVLIN}
+                "MooneyRivlin": MOONEY_RIVLIN, "ViscousDamping": VISCOUS_DAMPING}
 
 _dp = ctypes.POINTER(ctypes.c_double)
 _ip = ctypes.POINTER(ctypes.c_int32)
@@ -27,7 +27,7 @@ _ip = ctypes.POINTER(ctypes.c_int32)
 EXPORTS = [
     "pfa_create", "pfa_destroy", "pfa_last_error", "pfa_sizes", "pfa_pattern", "pfa_block_pattern", "pfa_pattern_device",
     "pfa_pattern_wide", "pfa_pattern_wide_device",
-    "pfa_set_materials", "pfa_set_material_params", "pfa_energy", "pfa_energy_per_element", "pfa_gradient", "pfa_hessian",
+    "pfa_set_materials", "pfa_set_material_params", "pfa_set_previous", "pfa_energy", "pfa_energy_per_element", "pfa_gradient", "pfa_hessian",
     "pfa_linear_stiffness", "pfa_grad_hess", "pfa_grad_hess_weighted", "pfa_synchronize", "pfa_stream", "pfa_set_stream", "pfa_profile_enable",
     "pfa_profile_read", "pfa_launch_count", "pfa_setup_seconds",
     "pfa_is_step_valid", "pfa_set_constrained_dofs", "pfa_reduced_sizes", "pfa_reduced_pattern", "pfa_reduced_pattern_device",
@@ -95,6 +95,7 @@ def lib():
     L.pfa_pattern_wide_device.argtypes = [vp, ctypes.POINTER(vp), ctypes.POINTER(vp)]
     L.pfa_set_materials.argtypes = [vp, vp, vp, ctypes.c_int32]
     L.pfa_set_material_params.argtypes = [vp, vp, vp, vp, ctypes.c_int32]
+    L.pfa_set_previous.argtypes = [vp, vp, ctypes.c_double]
     L.pfa_energy.argtypes = [vp, vp, vp]
     L.pfa_energy_per_element.argtypes = [vp, vp, vp]
     L.pfa_gradient.argtypes = [vp, vp, vp]
@@ -289,6 +290,15 @@ class Handle:
             self._check(lib().pfa_set_material_params(self._h, _ptr(lam), _ptr(mu), _ptr(p3), int(stride)))
             return
         self._check(lib().pfa_set_materials(self._h, _ptr(lam), _ptr(mu), int(stride)))
+
+    def set_previous(self, x_prev, dt):
+        """displacement_prev / dt of the NL virtuals (PFA_VISCOUS_DAMPING); x_prev None: no previous displacement"""
+        if x_prev is None:
+            self._check(lib().pfa_set_previous(self._h, None, float(dt)))
+            return
+        xp = np.ascontiguousarray(x_prev, dtype=np.float64).reshape(-1)
+        assert xp.size == self.ndof
+        self._check(lib().pfa_set_previous(self._h, _ptr(xp), float(dt)))
 
     # ---- host-array convenience wrappers (numpy in, numpy out) ----
     def energy(self, x):

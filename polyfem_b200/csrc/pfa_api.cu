@@ -46,6 +46,9 @@ struct pfa_handle
 	int64_t *d_outer64 = nullptr, *d_inner64 = nullptr;
 	std::vector<int64_t> h_outer64, h_inner64;
 	double *d_lambda = nullptr, *d_mu = nullptr, *d_param3 = nullptr;
+	double *d_x_prev = nullptr; // pfa_set_previous (PFA_VISCOUS_DAMPING)
+	bool has_prev = false;
+	double dt = 1.0;
 	int32_t *d_elem_id = nullptr; // internal -> caller element index (nullptr: identity)
 	double *s_mat = nullptr;      // staging for pfa_set_materials when elements are re-ordered
 	// staging for host-pointer calls (allocated on first use)
@@ -271,13 +274,13 @@ namespace
 		// matrix unchanged (its six rigid-body eigenvalues are zero up to rounding), so the flag has no effect there.
 		if (project_to_psd && h->dm.material == PFA_LINEAR_ELASTICITY)
 			project_to_psd = 0;
-		if (project_to_psd && h->dm.material != PFA_NEOHOOKEAN && h->dm.material != PFA_SAINT_VENANT && h->dm.material != PFA_MOONEY_RIVLIN)
+		if (project_to_psd && h->dm.material != PFA_NEOHOOKEAN && h->dm.material != PFA_SAINT_VENANT && h->dm.material != PFA_MOONEY_RIVLIN && h->dm.material != PFA_VISCOUS_DAMPING)
 			return fail(h, PFA_ERR_UNSUPPORTED, "project_to_psd applies to the NLAssembler materials only");
 		if (scale != 1.0 && !rowlane_applies(h->dm.material, h->dm.n_loc, h->dm.n_qp))
 			return fail(h, PFA_ERR_UNSUPPORTED, "a Form weight other than 1 is fused for NeoHookean P1/P2 tets only");
 		if ((h->dm.material == PFA_LAPLACIAN || h->dm.material == PFA_MASS) && !linear)
 			return fail(h, PFA_ERR_UNSUPPORTED, "Laplacian and Mass are LinearAssemblers: only pfa_linear_stiffness applies");
-		if ((h->dm.material == PFA_NEOHOOKEAN || h->dm.material == PFA_SAINT_VENANT || h->dm.material == PFA_MOONEY_RIVLIN) && linear)
+		if ((h->dm.material == PFA_NEOHOOKEAN || h->dm.material == PFA_SAINT_VENANT || h->dm.material == PFA_MOONEY_RIVLIN || h->dm.material == PFA_VISCOUS_DAMPING) && linear)
 			return fail(h, PFA_ERR_UNSUPPORTED, "NeoHookean / SaintVenant are NLAssemblers: pfa_linear_stiffness does not apply");
 
 		AssembleArgs a;
@@ -354,11 +357,19 @@ namespace
 
 		if (a.e_end <= a.e_begin)
 			return PFA_OK; // empty part: outputs are cleared (or left), nothing to launch
+		// ViscousDamping without a previous displacement: every output is zero (ViscousDamping.cpp:125-126, 176-179, 299-300)
+		const bool no_prev = h->dm.material == PFA_VISCOUS_DAMPING && !h->has_prev;
+		if (no_prev && a.energy_per_el)
+			PFA_CUDA(h, cudaMemsetAsync(a.energy_per_el, 0, size_t(h->dm.n_el) * sizeof(double), h->stream));
+		a.x_prev = h->d_x_prev;
+		a.inv_dt = 1.0 / h->dt;
 		const char *kname = use_cl ? "assemble_nh_column_lane(records+columns)" : "assemble";
 		NvtxRange kernel_range(use_cl ? "pfa: owner-computes kernels (records + columns)" : "pfa: assembly kernel");
 		prof_begin(h, kname);
 		int cl_launches = 0;
-		cudaError_t ce = use_cl ? launch_column_lane2(dm, a, h->cl, h->sm_count, h->stream, &cl_launches) : launch_assemble(dm, a, linear, h->sm_count, h->stream, &kname);
+		cudaError_t ce = no_prev ? cudaSuccess
+						 : use_cl ? launch_column_lane2(dm, a, h->cl, h->sm_count, h->stream, &cl_launches)
+								  : launch_assemble(dm, a, linear, h->sm_count, h->stream, &kname);
 		h->launches += cl_launches; // records (+ energy sum) + one column kernel per strip class
 		if (h->profiling && !h->prof.empty() && !h->prof.back().stop_recorded)
 			h->prof.back().name = kname;
@@ -391,7 +402,7 @@ extern "C"
 		*out = nullptr;
 		if (d->struct_size != int32_t(sizeof(pfa_mesh_desc)))
 			return fail(nullptr, PFA_ERR_INVALID, "pfa_create: struct_size does not match this library's pfa_mesh_desc");
-		if (d->material < PFA_NEOHOOKEAN || d->material > PFA_MOONEY_RIVLIN)
+		if (d->material < PFA_NEOHOOKEAN || d->material > PFA_VISCOUS_DAMPING)
 			return fail(nullptr, PFA_ERR_INVALID, "pfa_create: unknown material");
 		if (d->n_elements <= 0 || d->n_loc <= 0 || d->n_bases <= 0 || d->n_qp <= 0 || d->n_ghost_elements < 0)
 			return fail(nullptr, PFA_ERR_INVALID, "pfa_create: n_elements, n_loc, n_bases and n_qp must be positive");
@@ -984,6 +995,29 @@ extern "C"
 	int pfa_set_materials(pfa_handle *h, const double *lambda, const double *mu, int32_t material_stride)
 	{
 		return pfa_set_material_params(h, lambda, mu, nullptr, material_stride);
+	}
+
+	int pfa_set_previous(pfa_handle *h, const double *x_prev, double dt)
+	{
+		if (!h)
+			return PFA_ERR_INVALID;
+		if (!(dt > 0.0))
+			return fail(h, PFA_ERR_INVALID, "pfa_set_previous: dt must be positive");
+		PFA_CUDA(h, cudaSetDevice(h->device));
+		h->dt = dt;
+		h->has_prev = x_prev != nullptr;
+		if (x_prev)
+		{
+			if (h->d_x_prev == nullptr)
+			{
+				int rc = dev_alloc<double>(h, &h->d_x_prev, size_t(h->ndof));
+				if (rc != PFA_OK)
+					return rc;
+			}
+			PFA_CUDA(h, cudaMemcpyAsync(h->d_x_prev, x_prev, size_t(h->ndof) * sizeof(double), cudaMemcpyDefault, h->stream));
+			PFA_CUDA(h, cudaStreamSynchronize(h->stream)); // the caller may reuse x_prev
+		}
+		return PFA_OK;
 	}
 
 	int pfa_energy(pfa_handle *h, const double *x, double *energy)

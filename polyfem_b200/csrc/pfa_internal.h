@@ -77,6 +77,8 @@ namespace pfa
 		const int32_t *old_to_new = nullptr;
 		int *work_counter = nullptr; // device int, zeroed before the launch (dynamic batch hand-out)
 		int32_t epoch = 0;           // > 0: values[] is zero-filled inside the kernel (see DeviceMesh::zoff)
+		const double *x_prev = nullptr; // [ndof] device, PFA_VISCOUS_DAMPING
+		double inv_dt = 0.0;
 	};
 
 	// Owner-computes (column-lane) tables of a handle (pfa_collane2.h / pfa_collane2.cu), built at create time for NeoHookean

@@ -172,6 +172,7 @@ namespace pfa
 		struct WarpLayout
 		{
 			int U, D, A, Q, J, DA, I; // offsets in doubles (I: start of the int region, in doubles)
+			int UP = 0;               // previous local displacement (ViscousDamping)
 			int H = 0, V = 0, CS = 0, PQ = 0; // project_to_psd variant only
 			int total;                // doubles per warp
 		};
@@ -184,7 +185,9 @@ namespace pfa
 		// dimension of the local matrix as project_to_psd sees it: 3 n_loc, plus one zero row and column when that is odd
 		__host__ __device__ inline int psd_dim(int n_loc) { return 3 * n_loc + ((3 * n_loc) & 1); }
 
-		__host__ __device__ inline WarpLayout warp_layout(int n_loc, int n_qp, bool psd = false, int qrec = kQRec)
+		__host__ __device__ constexpr bool needs_prev(int material) { return material == PFA_VISCOUS_DAMPING; }
+
+		__host__ __device__ inline WarpLayout warp_layout(int n_loc, int n_qp, bool psd = false, int qrec = kQRec, bool prev = false)
 		{
 			WarpLayout L;
 			int o = 0;
@@ -202,6 +205,11 @@ namespace pfa
 			o += n_qp;
 			L.I = o;
 			o += (3 * n_loc + 1) / 2;
+			if (prev)
+			{
+				L.UP = o;
+				o += n_loc * 3;
+			}
 			if (psd)
 			{
 				// local matrix H and eigenvector matrix V [Np][Np|1] (Np = N rounded up to even: the round-robin ordering pairs all
@@ -387,7 +395,7 @@ namespace pfa
 			const int n_loc = m.n_loc, n_qp = m.n_qp;
 			const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 			constexpr int QR = qrec_of(MAT);
-			const WarpLayout L = warp_layout(n_loc, n_qp, PSD, QR);
+			const WarpLayout L = warp_layout(n_loc, n_qp, PSD, QR, needs_prev(MAT));
 
 			// CTA-shared reference tables
 			// (TABLES_SHARED false: read through the cache from global memory instead - the P4 projection needs the space)
@@ -432,6 +440,13 @@ namespace pfa
 						sU[j * 3 + 0] = a.x[size_t(g) * 3 + 0];
 						sU[j * 3 + 1] = a.x[size_t(g) * 3 + 1];
 						sU[j * 3 + 2] = a.x[size_t(g) * 3 + 2];
+						if (needs_prev(MAT))
+						{
+							double *sUP = ws + L.UP;
+							sUP[j * 3 + 0] = a.x_prev[size_t(g) * 3 + 0];
+							sUP[j * 3 + 1] = a.x_prev[size_t(g) * 3 + 1];
+							sUP[j * 3 + 2] = a.x_prev[size_t(g) * 3 + 2];
+						}
 					}
 				}
 				const int gq = m.geom_per_qp ? n_qp : 1;
@@ -509,6 +524,67 @@ namespace pfa
 							}
 							rec[27] = (mu + lam * (1.0 - lJ)) * invJ * invJ * da; // c1 * da
 							e_loc += (0.5 * mu * (sq - 3.0 - 2.0 * lJ) + 0.5 * lam * lJ * lJ) * da;
+						}
+						else if (MAT == PFA_VISCOUS_DAMPING)
+						{
+							// ViscousDamping.cpp:297-342 (energy), :122-170 (gradient), :16-62 + :173-229 (Hessian) in closed form. With
+							// Fp = I + grad u_prev, dF/dt = (F - Fp) / dt, dE/dt = sym(dF/dt^T F), T = 2 psi dE/dt + phi tr(dE/dt) I and
+							// A = 2 F - Fp (the variation of dE/dt is sym(A^T dF) / dt, its second variation 2 sym(dF1^T dF2) / dt):
+							//   P = A T / dt,   tangent = SaintVenant's with F -> A, S -> 2 T / dt, mu -> psi / dt^2, lambda -> phi / dt^2
+							// (psi, phi) = (lambda, mu) arrays. The record uses the SaintVenant slots.
+							const double *sUP = ws + L.UP;
+							double Fp[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+							for (int i = 0; i < n_loc; ++i)
+							{
+								const double *Di = sD + (q * n_loc + i) * 3;
+								for (int r = 0; r < 3; ++r)
+									for (int c = 0; c < 3; ++c)
+										Fp[r * 3 + c] += sUP[i * 3 + r] * Di[c];
+							}
+							F[0] += 1.0;
+							F[4] += 1.0;
+							F[8] += 1.0;
+							Fp[0] += 1.0;
+							Fp[4] += 1.0;
+							Fp[8] += 1.0;
+							const double psi = lam, phi = mu, idt = a.inv_dt;
+							double Fd[9], A[9], Ed[9], T[9];
+							for (int k = 0; k < 9; ++k)
+							{
+								Fd[k] = (F[k] - Fp[k]) * idt;
+								A[k] = 2.0 * F[k] - Fp[k];
+							}
+							for (int r = 0; r < 3; ++r)
+								for (int c = 0; c < 3; ++c)
+								{
+									const double m1 = Fd[0 + r] * F[0 + c] + Fd[3 + r] * F[3 + c] + Fd[6 + r] * F[6 + c];
+									const double m2 = Fd[0 + c] * F[0 + r] + Fd[3 + c] * F[3 + r] + Fd[6 + c] * F[6 + r];
+									Ed[r * 3 + c] = 0.5 * (m1 + m2);
+								}
+							const double trE = Ed[0] + Ed[4] + Ed[8];
+							double EE = 0.0;
+							for (int k = 0; k < 9; ++k)
+							{
+								EE += Ed[k] * Ed[k];
+								T[k] = 2.0 * psi * Ed[k];
+							}
+							T[0] += phi * trE;
+							T[4] += phi * trE;
+							T[8] += phi * trE;
+							for (int r = 0; r < 3; ++r)
+								for (int c = 0; c < 3; ++c)
+								{
+									rec[r * 3 + c] = A[r * 3 + c];
+									rec[9 + r * 3 + c] = (A[r * 3 + 0] * T[0 + c] + A[r * 3 + 1] * T[3 + c] + A[r * 3 + 2] * T[6 + c]) * idt * da;
+									rec[18 + r * 3 + c] = 2.0 * T[r * 3 + c] * idt * da;
+								}
+							rec[28] = psi * idt * idt * da;
+							rec[29] = phi * idt * idt * da;
+							int k6 = 0;
+							for (int r = 0; r < 3; ++r)
+								for (int c = r; c < 3; ++c)
+									rec[30 + k6++] = rec[28] * (A[r * 3 + 0] * A[c * 3 + 0] + A[r * 3 + 1] * A[c * 3 + 1] + A[r * 3 + 2] * A[c * 3 + 2]);
+							e_loc += (psi * EE + 0.5 * phi * trE * trE) * da;
 						}
 						else if (MAT == PFA_MOONEY_RIVLIN)
 						{
@@ -647,7 +723,7 @@ namespace pfa
 						atomicAdd(a.grad + size_t(sG[i]) * 3 + c, g);
 					}
 				}
-				if (want_h && (MAT == PFA_NEOHOOKEAN || MAT == PFA_SAINT_VENANT) && !LINEAR)
+				if (want_h && (MAT == PFA_NEOHOOKEAN || MAT == PFA_SAINT_VENANT || MAT == PFA_VISCOUS_DAMPING) && !LINEAR)
 				{
 					// A_i = C D_i (NeoHookean: C = cof F) or F D_i (SaintVenant: the first record slot holds F)
 					for (int t = lane; t < n_qp * n_loc; t += 32)
@@ -795,8 +871,9 @@ namespace pfa
 								blk[7] -= W0;
 							}
 						}
-						else if (MAT == PFA_SAINT_VENANT && !LINEAR)
+						else if ((MAT == PFA_SAINT_VENANT || MAT == PFA_VISCOUS_DAMPING) && !LINEAR)
 						{
+							// (ViscousDamping: the same form with the substitutions of its record)
 							// H[(i,a),(j,b)] = sum_q [ (D_i . S D_j) delta_ab + mu (F D_j)_a (F D_i)_b + lambda (F D_i)_a (F D_j)_b
 							//                          + mu (F F^T)_ab (D_i . D_j) ] da     (tangent of P = F S(E))
 							for (int q = 0; q < n_qp; ++q)
@@ -2149,17 +2226,17 @@ namespace pfa
 
 		constexpr size_t kMaxSmem = 227 * 1024;
 
-		size_t generic_smem_bytes(int n_loc, int n_qp, int warps, bool psd = false, bool tables_shared = true, int qrec = kQRec)
+		size_t generic_smem_bytes(int n_loc, int n_qp, int warps, bool psd = false, bool tables_shared = true, int qrec = kQRec, bool prev = false)
 		{
-			const WarpLayout L = warp_layout(n_loc, n_qp, psd, qrec);
+			const WarpLayout L = warp_layout(n_loc, n_qp, psd, qrec, prev);
 			return sizeof(double) * ((tables_shared ? size_t(n_qp) * n_loc * 3 + n_qp : size_t(0)) + size_t(warps) * L.total);
 		}
 
 		// warps per CTA: the largest of 8/4/2/1 whose staging fits in shared memory
-		int pick_warps(int n_loc, int n_qp, int qrec = kQRec)
+		int pick_warps(int n_loc, int n_qp, int qrec = kQRec, bool prev = false)
 		{
 			for (int w = 8; w >= 1; w >>= 1)
-				if (generic_smem_bytes(n_loc, n_qp, w, false, true, qrec) <= kMaxSmem)
+				if (generic_smem_bytes(n_loc, n_qp, w, false, true, qrec, prev) <= kMaxSmem)
 					return w;
 			return 0;
 		}
@@ -2167,7 +2244,7 @@ namespace pfa
 		template <int MAT, bool LINEAR, int kWarps>
 		cudaError_t launch_generic_w(const DeviceMesh &m, const AssembleArgs &a, int sm_count, cudaStream_t st)
 		{
-			const size_t smem = generic_smem_bytes(m.n_loc, m.n_qp, kWarps, false, true, qrec_of(MAT));
+			const size_t smem = generic_smem_bytes(m.n_loc, m.n_qp, kWarps, false, true, qrec_of(MAT), needs_prev(MAT));
 			auto kern = assemble_generic_kernel<MAT, LINEAR, kWarps>;
 			cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
 			if (err != cudaSuccess)
@@ -2189,7 +2266,7 @@ namespace pfa
 		template <int MAT, int kW, bool TABLES_SHARED>
 		cudaError_t launch_generic_psd_w(const DeviceMesh &m, const AssembleArgs &a, int sm_count, cudaStream_t st)
 		{
-			const size_t smem = generic_smem_bytes(m.n_loc, m.n_qp, kW, true, TABLES_SHARED, qrec_of(MAT));
+			const size_t smem = generic_smem_bytes(m.n_loc, m.n_qp, kW, true, TABLES_SHARED, qrec_of(MAT), needs_prev(MAT));
 			if (smem > kMaxSmem)
 				return cudaErrorNotSupported;
 			auto kern = assemble_generic_kernel<MAT, false, kW, true, TABLES_SHARED>;
@@ -2212,9 +2289,9 @@ namespace pfa
 		{
 			if (psd_dim(m.n_loc) > 128) // the diagonal of the rebuilt matrix is held in four registers per lane
 				return cudaErrorNotSupported;
-			if (generic_smem_bytes(m.n_loc, m.n_qp, 2, true, true, qrec_of(MAT)) <= kMaxSmem)
+			if (generic_smem_bytes(m.n_loc, m.n_qp, 2, true, true, qrec_of(MAT), needs_prev(MAT)) <= kMaxSmem)
 				return launch_generic_psd_w<MAT, 2, true>(m, a, sm_count, st);
-			if (generic_smem_bytes(m.n_loc, m.n_qp, 1, true, true, qrec_of(MAT)) <= kMaxSmem)
+			if (generic_smem_bytes(m.n_loc, m.n_qp, 1, true, true, qrec_of(MAT), needs_prev(MAT)) <= kMaxSmem)
 				return launch_generic_psd_w<MAT, 1, true>(m, a, sm_count, st);
 			return launch_generic_psd_w<MAT, 1, false>(m, a, sm_count, st);
 		}
@@ -2222,7 +2299,7 @@ namespace pfa
 		template <int MAT, bool LINEAR>
 		cudaError_t launch_generic(const DeviceMesh &m, const AssembleArgs &a, int sm_count, cudaStream_t st)
 		{
-			switch (pick_warps(m.n_loc, m.n_qp, qrec_of(MAT)))
+			switch (pick_warps(m.n_loc, m.n_qp, qrec_of(MAT), needs_prev(MAT)))
 			{
 			case 8:
 				return launch_generic_w<MAT, LINEAR, 8>(m, a, sm_count, st);
@@ -2376,6 +2453,14 @@ namespace pfa
 			if (a.project_to_psd)
 				return launch_generic_psd<PFA_MOONEY_RIVLIN>(m, a, sm_count, st);
 			return launch_generic<PFA_MOONEY_RIVLIN, false>(m, a, sm_count, st);
+		case PFA_VISCOUS_DAMPING:
+			if (linear || a.x_prev == nullptr)
+				return cudaErrorNotSupported;
+			if (kernel_name)
+				*kernel_name = a.project_to_psd ? "assemble_generic_kernel<ViscousDamping,psd>" : "assemble_generic_kernel<ViscousDamping>";
+			if (a.project_to_psd)
+				return launch_generic_psd<PFA_VISCOUS_DAMPING>(m, a, sm_count, st);
+			return launch_generic<PFA_VISCOUS_DAMPING, false>(m, a, sm_count, st);
 		case PFA_LINEAR_ELASTICITY:
 			if (linear && affine_linear_applies(m) && a.values != nullptr)
 			{

@@ -20,6 +20,7 @@
 #include <polyfem/assembler/MooneyRivlinElasticity.hpp>
 #include <polyfem/assembler/NeoHookeanElasticity.hpp>
 #include <polyfem/assembler/SaintVenantElasticity.hpp>
+#include <polyfem/assembler/ViscousDamping.hpp>
 #include <polyfem/basis/ElementBases.hpp>
 #include <polyfem/utils/Logger.hpp>
 #include <polyfem/utils/MatrixCache.hpp>
@@ -264,6 +265,7 @@ namespace polyfem::assembler::b200
 			if (!on_device())
 				return Base::assemble_energy(is_volume, bases, gbases, cache, t, dt, displacement, displacement_prev);
 			pfa_handle *h = handle(is_volume, int(displacement.size() / this->size()), bases, gbases, cache, t);
+			before_call(h, dt, displacement, displacement_prev);
 			double e = 0;
 			DeviceAssembly::check(h, pfa_energy(h, displacement.data(), &e));
 			return e;
@@ -277,6 +279,7 @@ namespace polyfem::assembler::b200
 			if (!on_device())
 				return Base::assemble_energy_per_element(is_volume, bases, gbases, cache, t, dt, displacement, displacement_prev);
 			pfa_handle *h = handle(is_volume, int(displacement.size() / this->size()), bases, gbases, cache, t);
+			before_call(h, dt, displacement, displacement_prev);
 			Eigen::VectorXd out(bases.size());
 			DeviceAssembly::check(h, pfa_energy_per_element(h, displacement.data(), out.data()));
 			return out;
@@ -290,6 +293,7 @@ namespace polyfem::assembler::b200
 			if (!on_device())
 				return Base::assemble_gradient(is_volume, n_basis, bases, gbases, cache, t, dt, displacement, displacement_prev, rhs);
 			pfa_handle *h = handle(is_volume, n_basis, bases, gbases, cache, t);
+			before_call(h, dt, displacement, displacement_prev);
 			rhs.resize(n_basis * this->size(), 1);
 			DeviceAssembly::check(h, pfa_gradient(h, displacement.data(), rhs.data()));
 		}
@@ -303,6 +307,7 @@ namespace polyfem::assembler::b200
 			if (!on_device())
 				return Base::assemble_hessian(is_volume, n_basis, project_to_psd, bases, gbases, cache, t, dt, displacement, displacement_prev, mat_cache, hess);
 			pfa_handle *h = handle(is_volume, n_basis, bases, gbases, cache, t);
+			before_call(h, dt, displacement, displacement_prev);
 			int64_t nnz;
 			pfa_sizes(h, nullptr, nullptr, &nnz);
 			values_.resize(nnz);
@@ -325,6 +330,8 @@ namespace polyfem::assembler::b200
 
 	protected:
 		virtual bool on_device() const { return true; }
+		/// assemblers that read dt / displacement_prev hand them to the handle here (ViscousDamping)
+		virtual void before_call(pfa_handle *, const double, const Eigen::MatrixXd &, const Eigen::MatrixXd &) const {}
 		/// parameters of the element behind `vals` at quadrature point q, evaluated like the reference does inside its local
 		/// assembly (p3 only for three-parameter materials)
 		virtual void material_params(const ElementAssemblyValues &vals, const int q, const double t, double &p1, double &p2, double &p3) const = 0;
@@ -393,6 +400,24 @@ namespace polyfem::assembler::b200
 			p1 = c1()(vals.val.row(q), t, vals.element_id);
 			p2 = c2()(vals.val.row(q), t, vals.element_id);
 			p3 = k()(vals.val.row(q), t, vals.element_id);
+		}
+	};
+
+	/// Drop-in for ViscousDamping ("ViscousDamping"; the damping form of a transient elastic solve): psi, phi are global
+	/// (DampingParameters); displacement_prev and dt of the virtuals go through pfa_set_previous, and a displacement_prev of
+	/// another size - the first step - gives zeros exactly like ViscousDamping.cpp:125-126, 176-179, 299-300.
+	class ViscousDampingB200 : public NLAssemblerB200<ViscousDamping, PFA_VISCOUS_DAMPING>
+	{
+	protected:
+		bool on_device() const override { return size() == 3; }
+		void material_params(const ElementAssemblyValues &, const int, const double, double &psi, double &phi, double &) const override
+		{
+			psi = get_psi();
+			phi = get_phi();
+		}
+		void before_call(pfa_handle *h, const double dt, const Eigen::MatrixXd &displacement, const Eigen::MatrixXd &displacement_prev) const override
+		{
+			DeviceAssembly::check(h, pfa_set_previous(h, displacement_prev.size() == displacement.size() ? displacement_prev.data() : nullptr, dt));
 		}
 	};
 

@@ -210,6 +210,14 @@ namespace polyfem
 			const GenericMatParam &c2() const;
 			const GenericMatParam &k() const;
 		};
+		class ViscousDamping : public NLAssembler // ViscousDamping.hpp:10-66
+		{
+		public:
+			std::string name() const override;
+			void add_multimaterial(const int index, const json &params, const Units &units, const std::string &root_path) override; // :28
+			double get_psi() const;                                                                                                // :49
+			double get_phi() const;
+		};
 		class LinearElasticity : public LinearAssembler, public ElasticityNLAssembler // LinearElasticity.hpp
 		{
 		public:
