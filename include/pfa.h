@@ -64,12 +64,17 @@ extern "C"
 		                            * reference): psi = c1 (I1~ - 3) + c2 (I2~ - 3) + k/2 ln^2 J on the isochoric invariants. Parameters
 		                            * (c1, c2, k) = (lambda[], mu[], param3[]). Here: the chain rule over (I1, I2, J) of F in closed
 		                            * form (generic kernel, any order P1..P4). */
-		PFA_VISCOUS_DAMPING = 6    /* assembler/ViscousDamping.cpp, name() == "ViscousDamping": R = psi |dE/dt|^2 + phi/2 tr(dE/dt)^2,
+		PFA_VISCOUS_DAMPING = 6,   /* assembler/ViscousDamping.cpp, name() == "ViscousDamping": R = psi |dE/dt|^2 + phi/2 tr(dE/dt)^2,
 		                            * dE/dt = sym(dF/dt^T F), dF/dt = (F - F_prev) / dt; (psi, phi) = (lambda[], mu[]). The previous
 		                            * displacement and dt of the NLAssembler virtuals come through pfa_set_previous; until it is
 		                            * called every result is zero (the reference's x_prev.size() != x.size() branch). Closed form:
 		                            * with A = 2 F - F_prev the tangent is SaintVenant's with F -> A, mu -> psi / dt^2,
 		                            * lambda -> phi / dt^2, S -> 2 (2 psi dE/dt + phi tr(dE/dt) I) / dt. */
+		PFA_FIXED_COROTATIONAL = 7 /* assembler/FixedCorotational.cpp, name() == "FixedCorotational": psi = mu sum (sigma_i - 1)^2 +
+		                            * lambda/2 (prod sigma - 1)^2 on the signed singular values of F (utils/svd.hpp); stress
+		                            * lambda (J - 1) cof F + 2 mu (F - U V^T) and the 9 x 9 stiffness assembled from (U, sigma, V) per
+		                            * quadrature point, contracted with the basis gradients by the whole warp. Inverted elements are
+		                            * allowed (allow_inversion() is true in the reference). */
 	} pfa_material;
 
 	/* What the shim reads out of std::vector<basis::ElementBases> bases / gbases and the

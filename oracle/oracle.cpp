@@ -1419,6 +1419,227 @@ namespace
 		std::vector<double> da;
 	};
 
+	// =======================================================================================
+	// FixedCorotational (assembler/FixedCorotational.cpp) on the signed SVD of utils/svd.hpp
+	// =======================================================================================
+
+	// utils/svd.hpp:270-317 fastSVD3d as AutoFlipSVD<Matrix3d> presents it: eigen-decomposition of A^T A (here: cyclic Jacobi,
+	// eigenvalues in decreasing order), sigma = sqrt(max(lambda, 0)) with sigma_2 negated when det A < 0, U from A V:
+	// u_0 = A v_0 normalised, u_1 = the part of A v_1 orthogonal to u_0 normalised, u_2 = u_0 x u_1; V a rotation.
+	// Matrices row-major [r*3+c]; columns of U / V are the singular vectors.
+	void svd3_signed(const double *A, double *U, double *sig, double *V)
+	{
+		std::vector<double> C(9), Vv, w;
+		for (int r = 0; r < 3; ++r)
+			for (int c = 0; c < 3; ++c)
+				C[r * 3 + c] = A[0 + r] * A[0 + c] + A[3 + r] * A[3 + c] + A[6 + r] * A[6 + c];
+		jacobi_eigen(3, C, Vv, w);
+		int order[3] = {0, 1, 2};
+		std::sort(order, order + 3, [&](int a, int b) { return w[a] > w[b]; });
+		for (int k = 0; k < 3; ++k)
+		{
+			sig[k] = std::sqrt(std::max(w[order[k]], 0.0));
+			for (int r = 0; r < 3; ++r)
+				V[r * 3 + k] = Vv[size_t(r) * 3 + order[k]];
+		}
+		if (det3(V) < 0) // keep V a rotation
+			for (int r = 0; r < 3; ++r)
+				V[r * 3 + 2] = -V[r * 3 + 2];
+		if (det3(A) < 0)
+			sig[2] = -sig[2];
+		double u0[3], u1[3], av1[3];
+		for (int r = 0; r < 3; ++r)
+		{
+			u0[r] = A[r * 3 + 0] * V[0] + A[r * 3 + 1] * V[3] + A[r * 3 + 2] * V[6];
+			av1[r] = A[r * 3 + 0] * V[1] + A[r * 3 + 1] * V[4] + A[r * 3 + 2] * V[7];
+		}
+		double n0 = std::sqrt(u0[0] * u0[0] + u0[1] * u0[1] + u0[2] * u0[2]);
+		if (n0 != 0)
+			for (int r = 0; r < 3; ++r)
+				u0[r] /= n0;
+		else
+			u0[0] = 1, u0[1] = u0[2] = 0;
+		const double d01 = av1[0] * u0[0] + av1[1] * u0[1] + av1[2] * u0[2];
+		for (int r = 0; r < 3; ++r)
+			u1[r] = av1[r] - d01 * u0[r];
+		double n1 = std::sqrt(u1[0] * u1[0] + u1[1] * u1[1] + u1[2] * u1[2]);
+		if (n1 != 0)
+			for (int r = 0; r < 3; ++r)
+				u1[r] /= n1;
+		else
+		{
+			// any unit vector orthogonal to u0
+			const int k = std::fabs(u0[0]) < std::fabs(u0[1]) ? (std::fabs(u0[0]) < std::fabs(u0[2]) ? 0 : 2) : (std::fabs(u0[1]) < std::fabs(u0[2]) ? 1 : 2);
+			double e[3] = {0, 0, 0};
+			e[k] = 1;
+			const double d = u0[k];
+			for (int r = 0; r < 3; ++r)
+				u1[r] = e[r] - d * u0[r];
+			n1 = std::sqrt(u1[0] * u1[0] + u1[1] * u1[1] + u1[2] * u1[2]);
+			for (int r = 0; r < 3; ++r)
+				u1[r] /= n1;
+		}
+		const double u2[3] = {u0[1] * u1[2] - u0[2] * u1[1], u0[2] * u1[0] - u0[0] * u1[2], u0[0] * u1[1] - u0[1] * u1[0]};
+		for (int r = 0; r < 3; ++r)
+		{
+			U[r * 3 + 0] = u0[r];
+			U[r * 3 + 1] = u1[r];
+			U[r * 3 + 2] = u2[r];
+		}
+	}
+
+	void fc_def_grad(const NLData &data, const std::vector<double> &u, int p, double *F)
+	{
+		for (int k = 0; k < 9; ++k)
+			F[k] = 0.0;
+		for (int i = 0; i < data.vals.n_loc; ++i)
+		{
+			const double *gt = data.vals.gt(i, p);
+			for (int a = 0; a < 3; ++a)
+				for (int d = 0; d < 3; ++d)
+					F[a * 3 + d] += u[size_t(i) * 3 + a] * gt[d];
+		}
+		F[0] += 1.0;
+		F[4] += 1.0;
+		F[8] += 1.0;
+	}
+
+	// FixedCorotational.cpp:601-628 compute_stress_from_singular_values
+	void fc_dE_dsigma(const double *s, double lambda, double mu, double *dE)
+	{
+		const double pl = lambda * (s[0] * s[1] * s[2] - 1.0);
+		const double other[3] = {s[1] * s[2], s[2] * s[0], s[0] * s[1]};
+		for (int k = 0; k < 3; ++k)
+			dE[k] = 2 * mu * (s[k] - 1.0) + other[k] * pl;
+	}
+
+	// FixedCorotational.cpp:293-319, 592-599, 671-676 compute_energy
+	double fixed_corotational_energy(const NLData &data)
+	{
+		std::vector<double> u;
+		gather_local_disp(data, u);
+		double energy = 0.0;
+		for (int p = 0; p < data.vals.n_qp; ++p)
+		{
+			double F[9], U[9], s[3], V[9];
+			fc_def_grad(data, u, p, F);
+			svd3_signed(F, U, s, V);
+			const double sq = (s[0] - 1) * (s[0] - 1) + (s[1] - 1) * (s[1] - 1) + (s[2] - 1) * (s[2] - 1);
+			const double pm1 = s[0] * s[1] * s[2] - 1.0;
+			energy += (data.mu * sq + data.lambda / 2.0 * pm1 * pm1) * data.da[p];
+		}
+		return energy;
+	}
+
+	// FixedCorotational.cpp:321-377, 678-706: stress = lambda (prod sigma - 1) dJ/dF + 2 mu (F - U V^T), G += delF_delU stress^T da
+	void fixed_corotational_gradient(const NLData &data, std::vector<double> &g)
+	{
+		const int n_loc = data.vals.n_loc;
+		g.assign(size_t(n_loc) * 3, 0.0);
+		std::vector<double> u;
+		gather_local_disp(data, u);
+		for (int p = 0; p < data.vals.n_qp; ++p)
+		{
+			double F[9], U[9], s[3], V[9], P[9];
+			fc_def_grad(data, u, p, F);
+			svd3_signed(F, U, s, V);
+			// dJ/dF: columns are the cross products of the other two columns of F
+			double cof[9];
+			for (int c = 0; c < 3; ++c)
+			{
+				const int c1 = (c + 1) % 3, c2 = (c + 2) % 3;
+				cof[0 * 3 + c] = F[1 * 3 + c1] * F[2 * 3 + c2] - F[2 * 3 + c1] * F[1 * 3 + c2];
+				cof[1 * 3 + c] = F[2 * 3 + c1] * F[0 * 3 + c2] - F[0 * 3 + c1] * F[2 * 3 + c2];
+				cof[2 * 3 + c] = F[0 * 3 + c1] * F[1 * 3 + c2] - F[1 * 3 + c1] * F[0 * 3 + c2];
+			}
+			const double pm1 = s[0] * s[1] * s[2] - 1.0;
+			for (int r = 0; r < 3; ++r)
+				for (int c = 0; c < 3; ++c)
+				{
+					const double R = U[r * 3 + 0] * V[c * 3 + 0] + U[r * 3 + 1] * V[c * 3 + 1] + U[r * 3 + 2] * V[c * 3 + 2];
+					P[r * 3 + c] = data.lambda * pm1 * cof[r * 3 + c] + data.mu * 2 * (F[r * 3 + c] - R);
+				}
+			for (int i = 0; i < n_loc; ++i)
+			{
+				const double *gt = data.vals.gt(i, p);
+				for (int a = 0; a < 3; ++a)
+					g[size_t(i) * 3 + a] += (gt[0] * P[a * 3 + 0] + gt[1] * P[a * 3 + 1] + gt[2] * P[a * 3 + 2]) * data.da[p];
+			}
+		}
+	}
+
+	// FixedCorotational.cpp:630-669, 708-827 compute_stiffness_from_def_grad: d2psi / dF(i,j) dF(r,s) =
+	//   sum_kl A_kl U_ik V_jk U_rl V_sl  (A = d2E / dsigma2)
+	// + sum over the pairs {k,l} of (L + R) (U_ik V_jl U_rk V_sl + U_il V_jk U_rl V_sk) + (L - R) (U_ik V_jl U_rl V_sk + U_il V_jk U_rk V_sl)
+	// with L = mu - lambda/2 (prod sigma - 1) sigma_m (m the third index), R = (dE_k + dE_l) / (2 max(sigma_k + sigma_l, 1e-12)).
+	// T[(i*3+j)*9 + r*3+s].
+	void fc_stiffness(const double *F, double lambda, double mu, double *T)
+	{
+		double U[9], s[3], V[9], dE[3], A[9];
+		svd3_signed(F, U, s, V);
+		fc_dE_dsigma(s, lambda, mu, dE);
+		const double prod = s[0] * s[1] * s[2];
+		const double other[3] = {s[1] * s[2], s[2] * s[0], s[0] * s[1]};
+		for (int k = 0; k < 3; ++k)
+			for (int l = 0; l < 3; ++l)
+			{
+				if (k == l)
+					A[k * 3 + l] = 2 * mu + lambda * other[k] * other[k];
+				else
+					A[k * 3 + l] = lambda * (s[3 - k - l] * (prod - 1.0) + other[k] * other[l]);
+			}
+		for (int k = 0; k < 81; ++k)
+			T[k] = 0.0;
+		for (int i = 0; i < 3; ++i)
+			for (int j = 0; j < 3; ++j)
+				for (int r = 0; r < 3; ++r)
+					for (int q = 0; q < 3; ++q)
+					{
+						double sum = 0.0;
+						for (int k = 0; k < 3; ++k)
+							for (int l = 0; l < 3; ++l)
+								sum += A[k * 3 + l] * U[i * 3 + k] * V[j * 3 + k] * U[r * 3 + l] * V[q * 3 + l];
+						for (int k = 0; k < 3; ++k)
+						{
+							const int l = (k + 1) % 3, m = 3 - k - l;
+							const double left = mu - lambda / 2.0 * (prod - 1.0) * s[m];
+							const double right = (dE[k] + dE[l]) / (2.0 * std::max(s[k] + s[l], 1.0e-12));
+							sum += (left + right) * (U[i * 3 + k] * V[j * 3 + l] * U[r * 3 + k] * V[q * 3 + l] + U[i * 3 + l] * V[j * 3 + k] * U[r * 3 + l] * V[q * 3 + k]);
+							sum += (left - right) * (U[i * 3 + k] * V[j * 3 + l] * U[r * 3 + l] * V[q * 3 + k] + U[i * 3 + l] * V[j * 3 + k] * U[r * 3 + k] * V[q * 3 + l]);
+						}
+						T[(i * 3 + j) * 9 + r * 3 + q] = sum;
+					}
+	}
+
+	// FixedCorotational.cpp:379-436: H += B^T stiffness B da, B(F(j,k), 3 i + j) = delF_delU(i, k)
+	void fixed_corotational_hessian(const NLData &data, std::vector<double> &h)
+	{
+		const int n_loc = data.vals.n_loc, N = 3 * n_loc;
+		h.assign(size_t(N) * N, 0.0);
+		std::vector<double> u;
+		gather_local_disp(data, u);
+		for (int p = 0; p < data.vals.n_qp; ++p)
+		{
+			double F[9], T[81];
+			fc_def_grad(data, u, p, F);
+			fc_stiffness(F, data.lambda, data.mu, T);
+			for (int i = 0; i < n_loc; ++i)
+				for (int j = 0; j < n_loc; ++j)
+				{
+					const double *gi = data.vals.gt(i, p), *gj = data.vals.gt(j, p);
+					for (int a = 0; a < 3; ++a)
+						for (int b = 0; b < 3; ++b)
+						{
+							double sum = 0.0;
+							for (int d = 0; d < 3; ++d)
+								for (int d2 = 0; d2 < 3; ++d2)
+									sum += gi[d] * T[(a * 3 + d) * 9 + b * 3 + d2] * gj[d2];
+							h[size_t(i * 3 + a) * N + j * 3 + b] += sum * data.da[p];
+						}
+				}
+		}
+	}
+
 	void compute_da(const ElementAssemblyValues &vals, std::vector<double> &da)
 	{
 		da.resize(vals.n_qp);
@@ -1437,6 +1658,8 @@ namespace
 			return mooney_rivlin_energy<double>(data);
 		if (pb.d.material == ORACLE_VISCOUS_DAMPING)
 			return viscous_damping_energy(data);
+		if (pb.d.material == ORACLE_FIXED_COROTATIONAL)
+			return fixed_corotational_energy(data);
 		return linear_elasticity_energy<double>(data);
 	}
 	void local_gradient(const Problem &pb, const NLData &data, std::vector<double> &g)
@@ -1449,6 +1672,11 @@ namespace
 		if (pb.d.material == ORACLE_VISCOUS_DAMPING)
 		{
 			viscous_damping_gradient(data, g);
+			return;
+		}
+		if (pb.d.material == ORACLE_FIXED_COROTATIONAL)
+		{
+			fixed_corotational_gradient(data, g);
 			return;
 		}
 		// utils/ElasticityUtils.cpp:81-... gradient_from_energy: autodiff gradient
@@ -1467,6 +1695,11 @@ namespace
 		if (pb.d.material == ORACLE_VISCOUS_DAMPING)
 		{
 			viscous_damping_hessian(data, h);
+			return;
+		}
+		if (pb.d.material == ORACLE_FIXED_COROTATIONAL)
+		{
+			fixed_corotational_hessian(data, h);
 			return;
 		}
 		const D2 e = pb.d.material == ORACLE_SAINT_VENANT   ? saint_venant_energy<D2>(data)

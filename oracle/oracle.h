@@ -53,7 +53,10 @@ extern "C"
 		/* assembler/ViscousDamping.cpp (NLAssembler that depends on the previous displacement and dt): parameters
 		 * (psi, phi) = (lambda[], mu[]); oracle_set_previous supplies x_prev and dt, without it every result is zero
 		 * (the reference's `data.x_prev.size() != data.x.size()` branch) */
-		ORACLE_VISCOUS_DAMPING = 6
+		ORACLE_VISCOUS_DAMPING = 6,
+		/* assembler/FixedCorotational.cpp: psi = mu sum (sigma_i - 1)^2 + lambda/2 (prod sigma - 1)^2 on the signed singular
+		 * values of F (utils/svd.hpp AutoFlipSVD); stress and 9 x 9 stiffness from the SVD */
+		ORACLE_FIXED_COROTATIONAL = 7
 	};
 
 	typedef struct

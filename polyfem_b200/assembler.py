@@ -298,6 +298,11 @@ class SaintVenantElasticity(NLAssembler):
     _material = "SaintVenant"
 
 
+class FixedCorotational(NLAssembler):
+    """assembler/FixedCorotational.{hpp,cpp}; name() == "FixedCorotational"; Lame parameters like NeoHookean."""
+    _material = "FixedCorotational"
+
+
 class MooneyRivlinElasticity(NLAssembler):
     """assembler/MooneyRivlinElasticity.{hpp,cpp} (GenericElastic<MooneyRivlinElasticity>); name() == "MooneyRivlin".
     Material JSON: c1, c2, k (GenericMatParam, MooneyRivlinElasticity.cpp:5-15)."""
@@ -371,7 +376,8 @@ class Laplacian(LinearAssembler):
 def make_assembler(formulation: str, device: int = 0) -> Assembler:
     """AssemblerUtils::make_assembler (AssemblerUtils.cpp:55-122) for the hot-path names."""
     table = {"NeoHookean": NeoHookeanElasticity, "LinearElasticity": LinearElasticity, "Laplacian": Laplacian, "Mass": Mass,
-             "SaintVenant": SaintVenantElasticity, "MooneyRivlin": MooneyRivlinElasticity, "ViscousDamping": ViscousDamping}
+             "SaintVenant": SaintVenantElasticity, "MooneyRivlin": MooneyRivlinElasticity, "ViscousDamping": ViscousDamping,
+             "FixedCorotational": FixedCorotational}
     if formulation not in table:
         log_and_throw_error(f"Unsupported assembler on the B200 path: {formulation}")
     return table[formulation](device)

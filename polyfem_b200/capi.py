@@ -16,9 +16,10 @@ LIB_PATH = os.environ.get("PFA_LIB", os.path.join(_HERE, "libpfa.so"))  # PFA_LI
 
 PFA_OK = 0
 PFA_ERR_INVALID, PFA_ERR_UNSUPPORTED, PFA_ERR_CUDA, PFA_ERR_NOMEM, PFA_ERR_NO_DEVICE = -1, -2, -3, -4, -5
-NEOHOOKEAN, LINEAR_ELASTICITY, LAPLACIAN, MASS, SAINT_VENANT, MOONEY_RIVLIN, VISCOUS_DAMPING = 0, 1, 2, 3, 4, 5, 6
+NEOHOOKEAN, LINEAR_ELASTICITY, LAPLACIAN, MASS, SAINT_VENANT, MOONEY_RIVLIN, VISCOUS_DAMPING, FIXED_COROTATIONAL = 0, 1, 2, 3, 4, 5, 6, 7
 MATERIAL_IDS = {"NeoHookean": NEOHOOKEAN, "LinearElasticity": LINEAR_ELASTICITY, "Laplacian": LAPLACIAN, "Mass": MASS, "SaintVenant": SAINT_VENANT,
-                "MooneyRivlin": MOONEY_RIVLIN, "ViscousDamping": VISCOUS_DAMPING}
+                "MooneyRivlin": MOONEY_RIVLIN, "ViscousDamping": VISCOUS_DAMPING,
+                "FixedCorotational": FIXED_COROTATIONAL}
 
 _dp = ctypes.POINTER(ctypes.c_double)
 _ip = ctypes.POINTER(ctypes.c_int32)

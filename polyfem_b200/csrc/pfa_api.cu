@@ -274,13 +274,13 @@ namespace
 		// matrix unchanged (its six rigid-body eigenvalues are zero up to rounding), so the flag has no effect there.
 		if (project_to_psd && h->dm.material == PFA_LINEAR_ELASTICITY)
 			project_to_psd = 0;
-		if (project_to_psd && h->dm.material != PFA_NEOHOOKEAN && h->dm.material != PFA_SAINT_VENANT && h->dm.material != PFA_MOONEY_RIVLIN && h->dm.material != PFA_VISCOUS_DAMPING)
+		if (project_to_psd && h->dm.material != PFA_NEOHOOKEAN && h->dm.material != PFA_SAINT_VENANT && h->dm.material != PFA_MOONEY_RIVLIN && h->dm.material != PFA_VISCOUS_DAMPING && h->dm.material != PFA_FIXED_COROTATIONAL)
 			return fail(h, PFA_ERR_UNSUPPORTED, "project_to_psd applies to the NLAssembler materials only");
 		if (scale != 1.0 && !rowlane_applies(h->dm.material, h->dm.n_loc, h->dm.n_qp))
 			return fail(h, PFA_ERR_UNSUPPORTED, "a Form weight other than 1 is fused for NeoHookean P1/P2 tets only");
 		if ((h->dm.material == PFA_LAPLACIAN || h->dm.material == PFA_MASS) && !linear)
 			return fail(h, PFA_ERR_UNSUPPORTED, "Laplacian and Mass are LinearAssemblers: only pfa_linear_stiffness applies");
-		if ((h->dm.material == PFA_NEOHOOKEAN || h->dm.material == PFA_SAINT_VENANT || h->dm.material == PFA_MOONEY_RIVLIN || h->dm.material == PFA_VISCOUS_DAMPING) && linear)
+		if ((h->dm.material == PFA_NEOHOOKEAN || h->dm.material == PFA_SAINT_VENANT || h->dm.material == PFA_MOONEY_RIVLIN || h->dm.material == PFA_VISCOUS_DAMPING || h->dm.material == PFA_FIXED_COROTATIONAL) && linear)
 			return fail(h, PFA_ERR_UNSUPPORTED, "NeoHookean / SaintVenant are NLAssemblers: pfa_linear_stiffness does not apply");
 
 		AssembleArgs a;
@@ -402,7 +402,7 @@ extern "C"
 		*out = nullptr;
 		if (d->struct_size != int32_t(sizeof(pfa_mesh_desc)))
 			return fail(nullptr, PFA_ERR_INVALID, "pfa_create: struct_size does not match this library's pfa_mesh_desc");
-		if (d->material < PFA_NEOHOOKEAN || d->material > PFA_VISCOUS_DAMPING)
+		if (d->material < PFA_NEOHOOKEAN || d->material > PFA_FIXED_COROTATIONAL)
 			return fail(nullptr, PFA_ERR_INVALID, "pfa_create: unknown material");
 		if (d->n_elements <= 0 || d->n_loc <= 0 || d->n_bases <= 0 || d->n_qp <= 0 || d->n_ghost_elements < 0)
 			return fail(nullptr, PFA_ERR_INVALID, "pfa_create: n_elements, n_loc, n_bases and n_qp must be positive");

@@ -165,6 +165,133 @@ namespace pfa
 			}
 		}
 
+		// Signed SVD of a 3 x 3 matrix the way utils/svd.hpp (fastSVD3d behind AutoFlipSVD) defines it: eigenvectors of A^T A (cyclic
+		// Jacobi here), eigenvalues in decreasing order, sigma = sqrt(max(lambda, 0)) with sigma_2 negated when det A < 0, V a
+		// rotation, u_0 = A v_0 normalised, u_1 = the normalised part of A v_1 orthogonal to u_0, u_2 = u_0 x u_1. Row-major
+		// matrices, singular vectors in the columns.
+		__device__ inline void svd3_signed(const double *A, double *U, double *sig, double *V)
+		{
+			double C[9], W[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+			for (int r = 0; r < 3; ++r)
+				for (int c = 0; c < 3; ++c)
+					C[r * 3 + c] = A[0 + r] * A[0 + c] + A[3 + r] * A[3 + c] + A[6 + r] * A[6 + c];
+			for (int sweep = 0; sweep < 30; ++sweep)
+			{
+				const double off = C[1] * C[1] + C[2] * C[2] + C[5] * C[5], diag = C[0] * C[0] + C[4] * C[4] + C[8] * C[8];
+				if (off <= 1e-32 * diag || off == 0.0)
+					break;
+				for (int p = 0; p < 2; ++p)
+					for (int q = p + 1; q < 3; ++q)
+					{
+						const double apq = C[p * 3 + q];
+						if (apq == 0.0)
+							continue;
+						const double theta = (C[q * 3 + q] - C[p * 3 + p]) / (2.0 * apq);
+						const double t = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+						const double c = 1.0 / sqrt(t * t + 1.0), sn = t * c;
+						for (int k = 0; k < 3; ++k)
+						{
+							const double akp = C[k * 3 + p], akq = C[k * 3 + q];
+							C[k * 3 + p] = c * akp - sn * akq;
+							C[k * 3 + q] = sn * akp + c * akq;
+						}
+						for (int k = 0; k < 3; ++k)
+						{
+							const double apk = C[p * 3 + k], aqk = C[q * 3 + k];
+							C[p * 3 + k] = c * apk - sn * aqk;
+							C[q * 3 + k] = sn * apk + c * aqk;
+						}
+						for (int k = 0; k < 3; ++k)
+						{
+							const double vkp = W[k * 3 + p], vkq = W[k * 3 + q];
+							W[k * 3 + p] = c * vkp - sn * vkq;
+							W[k * 3 + q] = sn * vkp + c * vkq;
+						}
+					}
+			}
+			// decreasing order (3-element sort of column indices)
+			int o0 = 0, o1 = 1, o2 = 2;
+			double w0 = C[0], w1 = C[4], w2 = C[8];
+			if (w0 < w1)
+			{
+				const double tw = w0;
+				w0 = w1;
+				w1 = tw;
+				const int to = o0;
+				o0 = o1;
+				o1 = to;
+			}
+			if (w1 < w2)
+			{
+				const double tw = w1;
+				w1 = w2;
+				w2 = tw;
+				const int to = o1;
+				o1 = o2;
+				o2 = to;
+			}
+			if (w0 < w1)
+			{
+				const double tw = w0;
+				w0 = w1;
+				w1 = tw;
+				const int to = o0;
+				o0 = o1;
+				o1 = to;
+			}
+			sig[0] = sqrt(fmax(w0, 0.0));
+			sig[1] = sqrt(fmax(w1, 0.0));
+			sig[2] = sqrt(fmax(w2, 0.0));
+			for (int r = 0; r < 3; ++r)
+			{
+				V[r * 3 + 0] = W[r * 3 + o0];
+				V[r * 3 + 1] = W[r * 3 + o1];
+				V[r * 3 + 2] = W[r * 3 + o2];
+			}
+			if (det3(V) < 0)
+				for (int r = 0; r < 3; ++r)
+					V[r * 3 + 2] = -V[r * 3 + 2];
+			if (det3(A) < 0)
+				sig[2] = -sig[2];
+			double u0[3], u1[3], av1[3];
+			for (int r = 0; r < 3; ++r)
+			{
+				u0[r] = A[r * 3 + 0] * V[0] + A[r * 3 + 1] * V[3] + A[r * 3 + 2] * V[6];
+				av1[r] = A[r * 3 + 0] * V[1] + A[r * 3 + 1] * V[4] + A[r * 3 + 2] * V[7];
+			}
+			const double n0 = sqrt(u0[0] * u0[0] + u0[1] * u0[1] + u0[2] * u0[2]);
+			if (n0 != 0)
+				for (int r = 0; r < 3; ++r)
+					u0[r] /= n0;
+			else
+			{
+				u0[0] = 1;
+				u0[1] = u0[2] = 0;
+			}
+			const double d01 = av1[0] * u0[0] + av1[1] * u0[1] + av1[2] * u0[2];
+			for (int r = 0; r < 3; ++r)
+				u1[r] = av1[r] - d01 * u0[r];
+			double n1 = sqrt(u1[0] * u1[0] + u1[1] * u1[1] + u1[2] * u1[2]);
+			if (n1 == 0)
+			{
+				// any unit vector orthogonal to u0: start from the axis u0 is least aligned with
+				const int k = fabs(u0[0]) < fabs(u0[1]) ? (fabs(u0[0]) < fabs(u0[2]) ? 0 : 2) : (fabs(u0[1]) < fabs(u0[2]) ? 1 : 2);
+				const double d = u0[k];
+				for (int r = 0; r < 3; ++r)
+					u1[r] = (r == k ? 1.0 : 0.0) - d * u0[r];
+				n1 = sqrt(u1[0] * u1[0] + u1[1] * u1[1] + u1[2] * u1[2]);
+			}
+			for (int r = 0; r < 3; ++r)
+				u1[r] /= n1;
+			const double u2[3] = {u0[1] * u1[2] - u0[2] * u1[1], u0[2] * u1[0] - u0[0] * u1[2], u0[0] * u1[1] - u0[1] * u1[0]};
+			for (int r = 0; r < 3; ++r)
+			{
+				U[r * 3 + 0] = u0[r];
+				U[r * 3 + 1] = u1[r];
+				U[r * 3 + 2] = u2[r];
+			}
+		}
+
 		// ------------------------------------------------------------------------------------
 		// Generic fused assembly kernel: one warp per element, any n_loc / n_qp (runtime),
 		// per-warp staging in shared memory, scatter with RED.ADD.F64 into the CSC values.
@@ -180,7 +307,8 @@ namespace pfa
 		// SaintVenant uses the slots as: F[9] | P*da[9] | S*da[9] | - | mu*da | lambda*da | mu*da*F F^T (00 01 02 11 12 22)
 		constexpr int kQRec = 36;
 		// MooneyRivlin: F | P da | F M | cof F | F F^T (6) | M (6) | psi_1, psi_2, psi_J, psi_1J, psi_2J, psi_JJ (x da)
-		__host__ __device__ constexpr int qrec_of(int material) { return material == PFA_MOONEY_RIVLIN ? 54 : kQRec; }
+		// FixedCorotational: U | P da | stiffness da (81) | V | d2E/dsigma2 (9) | pair coefficients L + R (3), L - R (3)
+		__host__ __device__ constexpr int qrec_of(int material) { return material == PFA_MOONEY_RIVLIN ? 54 : (material == PFA_FIXED_COROTATIONAL ? 124 : kQRec); }
 
 		// dimension of the local matrix as project_to_psd sees it: 3 n_loc, plus one zero row and column when that is odd
 		__host__ __device__ inline int psd_dim(int n_loc) { return 3 * n_loc + ((3 * n_loc) & 1); }
@@ -525,6 +653,42 @@ namespace pfa
 							rec[27] = (mu + lam * (1.0 - lJ)) * invJ * invJ * da; // c1 * da
 							e_loc += (0.5 * mu * (sq - 3.0 - 2.0 * lJ) + 0.5 * lam * lJ * lJ) * da;
 						}
+						else if (MAT == PFA_FIXED_COROTATIONAL)
+						{
+							// FixedCorotational.cpp:293-319 (energy), :321-377 + :678-706 (stress), :379-436 + :708-827 (stiffness). This lane:
+							// SVD, energy, stress, and the coefficients of the stiffness in the singular basis; the 81 entries follow below,
+							// spread over the warp.
+							F[0] += 1.0;
+							F[4] += 1.0;
+							F[8] += 1.0;
+							double Us[9], Vs[9], sg[3], G[9];
+							svd3_signed(F, Us, sg, Vs);
+							cofactor3(F, G);
+							const double prod = sg[0] * sg[1] * sg[2], pm1 = prod - 1.0;
+							const double other[3] = {sg[1] * sg[2], sg[2] * sg[0], sg[0] * sg[1]};
+							double dE[3];
+							for (int k = 0; k < 3; ++k)
+								dE[k] = 2.0 * mu * (sg[k] - 1.0) + other[k] * lam * pm1;
+							for (int r = 0; r < 3; ++r)
+								for (int c = 0; c < 3; ++c)
+								{
+									const double R = Us[r * 3 + 0] * Vs[c * 3 + 0] + Us[r * 3 + 1] * Vs[c * 3 + 1] + Us[r * 3 + 2] * Vs[c * 3 + 2];
+									rec[r * 3 + c] = Us[r * 3 + c];
+									rec[99 + r * 3 + c] = Vs[r * 3 + c];
+									rec[9 + r * 3 + c] = (lam * pm1 * G[r * 3 + c] + 2.0 * mu * (F[r * 3 + c] - R)) * da;
+									// d2E / dsigma_r dsigma_c
+									rec[108 + r * 3 + c] = (r == c ? 2.0 * mu + lam * other[r] * other[r] : lam * (sg[3 - r - c] * pm1 + other[r] * other[c])) * da;
+								}
+							for (int k = 0; k < 3; ++k)
+							{
+								const int l = (k + 1) % 3, m3 = 3 - k - l;
+								const double left = mu - 0.5 * lam * pm1 * sg[m3];
+								const double right = (dE[k] + dE[l]) / (2.0 * fmax(sg[k] + sg[l], 1.0e-12));
+								rec[117 + k] = (left + right) * da;
+								rec[120 + k] = (left - right) * da;
+							}
+							e_loc += (mu * ((sg[0] - 1.0) * (sg[0] - 1.0) + (sg[1] - 1.0) * (sg[1] - 1.0) + (sg[2] - 1.0) * (sg[2] - 1.0)) + 0.5 * lam * pm1 * pm1) * da;
+						}
 						else if (MAT == PFA_VISCOUS_DAMPING)
 						{
 							// ViscousDamping.cpp:297-342 (energy), :122-170 (gradient), :16-62 + :173-229 (Hessian) in closed form. With
@@ -699,6 +863,32 @@ namespace pfa
 				}
 				__syncwarp();
 
+				if (MAT == PFA_FIXED_COROTATIONAL && want_h && !LINEAR)
+				{
+					// stiffness entry (i, j | r, s) of point q (x da): sum_kl A_kl U_ik V_jk U_rl V_sl + for the pairs {k, l}:
+					// (L + R) (U_ik V_jl U_rk V_sl + U_il V_jk U_rl V_sk) + (L - R) (U_ik V_jl U_rl V_sk + U_il V_jk U_rk V_sl)
+					for (int t = lane; t < n_qp * 81; t += 32)
+					{
+						const int q = t / 81, idx = t - q * 81;
+						const int ij = idx / 9, rs = idx - ij * 9;
+						const int i = ij / 3, j = ij - i * 3, r = rs / 3, sI = rs - r * 3;
+						double *rec = sQ + q * QR;
+						const double *Us = rec, *Vs = rec + 99, *Ak = rec + 108;
+						double sum = 0.0;
+						for (int k = 0; k < 3; ++k)
+						{
+							const double uv = Us[i * 3 + k] * Vs[j * 3 + k];
+							sum += uv * (Ak[k * 3 + 0] * Us[r * 3 + 0] * Vs[sI * 3 + 0] + Ak[k * 3 + 1] * Us[r * 3 + 1] * Vs[sI * 3 + 1] + Ak[k * 3 + 2] * Us[r * 3 + 2] * Vs[sI * 3 + 2]);
+							const int l = (k + 1) % 3;
+							const double a_kl = Us[i * 3 + k] * Vs[j * 3 + l], a_lk = Us[i * 3 + l] * Vs[j * 3 + k];
+							const double b_kl = Us[r * 3 + k] * Vs[sI * 3 + l], b_lk = Us[r * 3 + l] * Vs[sI * 3 + k];
+							sum += rec[117 + k] * (a_kl * b_kl + a_lk * b_lk) + rec[120 + k] * (a_kl * b_lk + a_lk * b_kl);
+						}
+						rec[18 + idx] = sum;
+					}
+					__syncwarp();
+				}
+
 				// ---- 4. energy, gradient, A = C D ----
 				if (want_e)
 				{
@@ -813,6 +1003,26 @@ namespace pfa
 							blk[5] += W0;
 							blk[6] += W1;
 							blk[7] -= W0;
+						}
+						else if (MAT == PFA_FIXED_COROTATIONAL && !LINEAR)
+						{
+							// H[(i,a),(j,b)] = sum_q sum_dd' D_i[d] T_q[(a,d),(b,d')] D_j[d']   (B^T T B of FixedCorotational.cpp:420-434)
+							for (int q = 0; q < n_qp; ++q)
+							{
+								const double *T = sQ + q * QR + 18;
+								const double *Di = sD + (q * n_loc + i) * 3, *Dj = sD + (q * n_loc + j) * 3;
+								for (int r = 0; r < 3; ++r)
+									for (int c = 0; c < 3; ++c)
+									{
+										double acc = 0.0;
+										for (int d = 0; d < 3; ++d)
+										{
+											const double *row = T + (r * 3 + d) * 9 + c * 3;
+											acc += Di[d] * (row[0] * Dj[0] + row[1] * Dj[1] + row[2] * Dj[2]);
+										}
+										blk[r * 3 + c] += acc;
+									}
+							}
 						}
 						else if (MAT == PFA_MOONEY_RIVLIN && !LINEAR)
 						{
@@ -2453,6 +2663,14 @@ namespace pfa
 			if (a.project_to_psd)
 				return launch_generic_psd<PFA_MOONEY_RIVLIN>(m, a, sm_count, st);
 			return launch_generic<PFA_MOONEY_RIVLIN, false>(m, a, sm_count, st);
+		case PFA_FIXED_COROTATIONAL:
+			if (linear)
+				return cudaErrorNotSupported;
+			if (kernel_name)
+				*kernel_name = a.project_to_psd ? "assemble_generic_kernel<FixedCorotational,psd>" : "assemble_generic_kernel<FixedCorotational>";
+			if (a.project_to_psd)
+				return launch_generic_psd<PFA_FIXED_COROTATIONAL>(m, a, sm_count, st);
+			return launch_generic<PFA_FIXED_COROTATIONAL, false>(m, a, sm_count, st);
 		case PFA_VISCOUS_DAMPING:
 			if (linear || a.x_prev == nullptr)
 				return cudaErrorNotSupported;

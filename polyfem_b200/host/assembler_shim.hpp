@@ -14,6 +14,7 @@
 #include <pfa.h>
 
 #include <polyfem/assembler/AssemblyValsCache.hpp>
+#include <polyfem/assembler/FixedCorotational.hpp>
 #include <polyfem/assembler/Laplacian.hpp>
 #include <polyfem/assembler/LinearElasticity.hpp>
 #include <polyfem/assembler/Mass.hpp>
@@ -353,6 +354,18 @@ namespace polyfem::assembler::b200
 		// Bezier evaluator of the Jacobian (NeoHookeanElasticity.cpp:357-359, 475-498, 567-587): energy, gradient and Hessian
 		// all use it, so the whole assembler stays on the CPU path when it is enabled
 		bool on_device() const override { return !use_robust_jacobian; }
+		void material_params(const ElementAssemblyValues &vals, const int q, const double t, double &lambda, double &mu, double &) const override
+		{
+			lame_params().lambda_mu(vals.quadrature.points.row(q), vals.val.row(q), t, vals.element_id, lambda, mu);
+		}
+	};
+
+	/// Drop-in for FixedCorotational ("FixedCorotational"): Lame parameters like NeoHookean; inverted elements stay on the
+	/// device path (allow_inversion() is true, the signed SVD handles det F < 0).
+	class FixedCorotationalB200 : public NLAssemblerB200<FixedCorotational, PFA_FIXED_COROTATIONAL>
+	{
+	protected:
+		bool on_device() const override { return size() == 3; }
 		void material_params(const ElementAssemblyValues &vals, const int q, const double t, double &lambda, double &mu, double &) const override
 		{
 			lame_params().lambda_mu(vals.quadrature.points.row(q), vals.val.row(q), t, vals.element_id, lambda, mu);

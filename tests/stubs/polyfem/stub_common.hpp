@@ -210,6 +210,13 @@ namespace polyfem
 			const GenericMatParam &c2() const;
 			const GenericMatParam &k() const;
 		};
+		class FixedCorotational : public ElasticityNLAssembler // FixedCorotational.hpp:11-100
+		{
+		public:
+			std::string name() const override;
+			void add_multimaterial(const int index, const json &params, const Units &units, const std::string &root_path) override; // :40
+			const LameParameters &lame_params() const;                                                                             // :43
+		};
 		class ViscousDamping : public NLAssembler // ViscousDamping.hpp:10-66
 		{
 		public:

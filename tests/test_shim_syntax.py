@@ -24,6 +24,7 @@ int main()
 	b200::SaintVenantElasticityB200 sv;
 	b200::MooneyRivlinElasticityB200 mr;
 	b200::ViscousDampingB200 vd;
+	b200::FixedCorotationalB200 fc;
 	std::vector<basis::ElementBases> bases, gbases;
 	AssemblyValsCache cache;
 	Eigen::MatrixXd x, rhs;
@@ -35,7 +36,7 @@ int main()
 	a.assemble_gradient(true, 1, bases, gbases, cache, 0.0, 1.0, x, x, rhs);
 	a.assemble_hessian(true, 1, false, bases, gbases, cache, 0.0, 1.0, x, x, mc, K);
 	static_cast<const Assembler &>(le).assemble(true, 1, bases, gbases, cache, 0.0, K);
-	for (const Assembler *nl : {static_cast<const Assembler *>(&sv), static_cast<const Assembler *>(&mr), static_cast<const Assembler *>(&vd)})
+	for (const Assembler *nl : {static_cast<const Assembler *>(&sv), static_cast<const Assembler *>(&mr), static_cast<const Assembler *>(&vd), static_cast<const Assembler *>(&fc)})
 	{
 		e += nl->assemble_energy(true, bases, gbases, cache, 0.0, 1.0, x, x);
 		nl->assemble_gradient(true, 1, bases, gbases, cache, 0.0, 1.0, x, x, rhs);
