@@ -191,7 +191,14 @@ namespace pfa
 			static constexpr int OFF_STAGE = (STAGES + 1) & ~1; // after the mbarriers (one per buffer)
 			static constexpr int OFF_TB = OFF_STAGE + STAGES * STAGE;
 			static constexpr int OFF_RG = OFF_TB + (TB_ALIAS ? 0 : ((TB + 1) & ~1));
-			static constexpr int OFF_INFO = OFF_RG + NL * NQ * 4; // 5 x 4 ints = 10 doubles
+			// rows of the own-node gradient table [ri][q][4]: with 4 points a row is 128 bytes = all 32 banks, so the triples of a
+			// half-warp (different ri) would collide on every load; two doubles of padding shift consecutive rows by 4 banks
+			// (ncu: 5.9 M excess wavefronts of 98.5 M in the edge launch at n = 40 without it)
+#ifndef PFA_CL2_RG_PAD
+#define PFA_CL2_RG_PAD 2
+#endif
+			static constexpr int RG_LD = NQ * 4 + (NQ > 1 ? PFA_CL2_RG_PAD : 0);
+			static constexpr int OFF_INFO = OFF_RG + NL * RG_LD; // 5 x 4 ints = 10 doubles
 			static constexpr int OFF_STRIP = OFF_INFO + 10;
 			static_assert(RECD % 2 == 0 && OFF_STAGE % 2 == 0 && OFF_RG % 2 == 0 && OFF_STRIP % 2 == 0, "16-byte alignment");
 			static size_t bytes(int strip_rows) { return sizeof(double) * (size_t(OFF_STRIP) + size_t(strip_rows) * kStripLd); }
@@ -232,7 +239,7 @@ namespace pfa
 			}
 			// own-node reference gradients, padded rows [ri][q][4]
 			for (int k = lane; k < NL * NQ * 4; k += 32)
-				s_rg[k] = t.rg_padded[k];
+				s_rg[(k / (NQ * 4)) * L::RG_LD + k % (NQ * 4)] = t.rg_padded[k];
 			asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 			__syncwarp();
 
@@ -349,7 +356,7 @@ namespace pfa
 					if (busy)
 					{
 						const int ri = (w0.w >> 16) & 0xff;
-						column_of_element<NL, NQ, MODE>(stage + buf * L::STAGE + tr * L::SSTR, s_rg + ri * (NQ * 4), mm, ConstTable<SLOT>(), acc, g_acc, t.z4b, t.zbeta);
+						column_of_element<NL, NQ, MODE>(stage + buf * L::STAGE + tr * L::SSTR, s_rg + ri * L::RG_LD, mm, ConstTable<SLOT>(), acc, g_acc, t.z4b, t.zbeta);
 					}
 					__syncwarp(); // every lane has read its record: the buffer can be refilled
 					const bool group_ends = s + 1 == g_last;

@@ -1,0 +1,14 @@
+#!/bin/bash
+mkdir -p gpurun_out
+OUT=gpurun_out/clvar_r02ab.jsonl; : > $OUT
+for r in 1 2; do
+PFA_LIB=polyfem_b200/libpfa_rg0.so timeout 300 python tools/clvar.py --tag rg_pad0_run$r >> $OUT
+timeout 300 python tools/clvar.py --tag rg_pad2_run$r >> $OUT
+done
+timeout 300 python tools/clvar.py --n 44 --p 1 --reps 20 --tag p1_cfg2 >> $OUT
+cat $OUT | python -c "
+import sys,json
+for l in sys.stdin:
+    d=json.loads(l); print(d['tag'], d['n'], 'p',d['p'], 'ms %.3f'%d['kernel_ms'], 'min %.3f'%d['kernel_ms_min'])
+"
+timeout 600 python -m pytest tests/test_zzzz_gpu_column_lane.py tests/test_gpu_parity.py -x -q -m gpu 2>&1 | tail -3
