@@ -21,7 +21,11 @@ def main(path, kernel, launch=0):
     hdr_i = next(i for i, r in enumerate(rows) if "Address" in r and "Source" in r)
     hdr = rows[hdr_i]
     ix = {h: i for i, h in enumerate(hdr)}
-    data = [r for r in rows[hdr_i + 1:] if len(r) == len(hdr)]
+    data, seen = [], set()
+    for r in rows[hdr_i + 1:]:  # the page repeats the listing (two views of the same SASS): keep the first row of every address
+        if len(r) == len(hdr) and r[ix["Address"]] not in seen:
+            seen.add(r[ix["Address"]])
+            data.append(r)
 
     def num(r, k):
         try:
