@@ -1004,8 +1004,7 @@ extern "C"
 		if (!(dt > 0.0))
 			return fail(h, PFA_ERR_INVALID, "pfa_set_previous: dt must be positive");
 		PFA_CUDA(h, cudaSetDevice(h->device));
-		h->dt = dt;
-		h->has_prev = x_prev != nullptr;
+		h->has_prev = false; // stays off if the copy below fails
 		if (x_prev)
 		{
 			if (h->d_x_prev == nullptr)
@@ -1017,6 +1016,8 @@ extern "C"
 			PFA_CUDA(h, cudaMemcpyAsync(h->d_x_prev, x_prev, size_t(h->ndof) * sizeof(double), cudaMemcpyDefault, h->stream));
 			PFA_CUDA(h, cudaStreamSynchronize(h->stream)); // the caller may reuse x_prev
 		}
+		h->dt = dt;
+		h->has_prev = x_prev != nullptr;
 		return PFA_OK;
 	}
 
