@@ -52,6 +52,19 @@ def test_per_element_parameters_and_update(oracle):
     assert ei.value.code == capi.PFA_ERR_UNSUPPORTED
 
 
+def test_parameters_per_quadrature_point(oracle):
+    """material_stride == n_qp (what the host shim sends: one value per element and quadrature point)"""
+    mesh, x, t = make_case(3, 2, jitter=0.1, scale=0.08)
+    x = x[: mesh.n_bases * 3]
+    rng = np.random.default_rng(4)
+    ne, nq = mesh.n_elements, t["weights"].size
+    c1, c2, k = C1 * rng.uniform(0.5, 1.5, ne), C2 * rng.uniform(0.5, 1.5, ne), K * rng.uniform(0.5, 1.5, ne)
+    h = handle(mesh, t, np.repeat(c1, nq), np.repeat(c2, nq), np.repeat(k, nq))
+    check_nl(h, oracle.problem_from_mesh(mesh, "MooneyRivlin", c1=c1, c2=c2, k=k), x)
+    h.set_materials(np.repeat(c2, nq), np.repeat(c1, nq), nq, param3=np.repeat(2.0 * k, nq))
+    check_nl(h, oracle.problem_from_mesh(mesh, "MooneyRivlin", c1=c2, c2=c1, k=2.0 * k), x)
+
+
 def test_curved_p2_elements(oracle):
     from polyfem_b200 import capi
     mesh = M.kuhn_cube(3, 2, jitter=0.1)
