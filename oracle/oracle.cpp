@@ -2023,7 +2023,7 @@ extern "C"
 		const NLData data = make_data(op->pb, e, x, vals, da);
 		if (op->pb.d.material == ORACLE_NEOHOOKEAN)
 			return autodiff ? neohookean_energy_autodiff<D1>(data).v : neohookean_energy(data);
-		return linear_elasticity_energy<double>(data);
+		return local_energy(op->pb, data); // the material's own compute_energy
 	}
 
 	void oracle_local_gradient(oracle_problem *op, int e, const double *x, int autodiff, double *g)

@@ -26,6 +26,15 @@
  *     (LinearElasticity.cpp:103-132, tests/golden/le_energy.npz); gradient / Hessian are autodiff of that function in the
  *     reference (not compilable here) and property-pinned: closed form == autodiff 1e-12, Hessian == pinned linear
  *     stiffness 1e-8, finite differences.
+ *   - ViscousDamping energy / gradient / Hessian: PINNED against the reference's own function bodies (ViscousDamping.cpp:5-62,
+ *     122-229, 297-342 compiled verbatim into oracle/_ref/libvdref.so; tests/golden/vd_local.npz,
+ *     tests/test_oracle_viscous_reference.py, 1e-13).
+ *   - FixedCorotational energy / gradient / Hessian: PINNED against the reference's own function bodies AND its own 3 x 3 SVD
+ *     (FixedCorotational.cpp:293-436, 592-827, utils/svd.hpp:134-317 compiled verbatim into oracle/_ref/libfcref.so;
+ *     tests/golden/fc_local.npz, tests/test_oracle_corotational_reference.py, 1e-12; the oracle's own SVD is a Jacobi one).
+ *   - SaintVenant, MooneyRivlin: property-pinned (the reference differentiates their energy expressions by its autodiff
+ *     scalars over Eigen matrices of them, not compilable here): known answers in tests/test_oracle_saint_venant_and_curved.py,
+ *     tests/test_oracle_mooney_rivlin.py.
  *   - project_to_psd (ipc-toolkit, source absent): UNPINNED, documented behaviour restated.
  *   - Mass (assembler/Mass.cpp:5-23): pinned by closed forms (P1 local mass rho*V/20*(1+delta_ij), total mass,
  *     stored zeros off the block diagonal; tests/test_oracle_mass.py) - the reference has no unit test for it.

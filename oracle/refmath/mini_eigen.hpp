@@ -133,10 +133,128 @@ namespace Eigen
 				s += d_[size_t(k)] * o(k);
 			return s;
 		}
-		Dense &noalias() { return *this; }
-		struct ArrayView // .array(): element-wise view, only the product of two views is used (Assembler.cpp:518)
+		double norm() const { return std::sqrt(squaredNorm()); }
+		double prod() const
+		{
+			double s = 1;
+			for (double v : d_)
+				s *= v;
+			return s;
+		}
+		Dense cross(const Dense &o) const // 3-vectors
+		{
+			assert(size() == 3 && o.size() == 3);
+			Dense r(r_, c_);
+			r(0) = (*this)(1) * o(2) - (*this)(2) * o(1);
+			r(1) = (*this)(2) * o(0) - (*this)(0) * o(2);
+			r(2) = (*this)(0) * o(1) - (*this)(1) * o(0);
+			return r;
+		}
+		// a unit vector orthogonal to this 3-vector, by the rule Eigen documents for unitOrthogonal(): rotate in the xy plane
+		// unless x and y are both negligible against z (relative 1e-12), then in the yz plane
+		Dense unitOrthogonal() const
+		{
+			assert(size() == 3);
+			const double x = (*this)(0), y = (*this)(1), z = (*this)(2), prec = 1e-12;
+			Dense r(r_, c_);
+			if (!(std::fabs(x) <= std::fabs(z) * prec) || !(std::fabs(y) <= std::fabs(z) * prec))
+			{
+				const double invnm = 1.0 / std::sqrt(x * x + y * y);
+				r(0) = -y * invnm;
+				r(1) = x * invnm;
+				r(2) = 0;
+			}
+			else
+			{
+				const double invnm = 1.0 / std::sqrt(y * y + z * z);
+				r(0) = 0;
+				r(1) = -z * invnm;
+				r(2) = y * invnm;
+			}
+			return r;
+		}
+		template <typename I>
+		double maxCoeff(I *where) const
+		{
+			long best = 0;
+			for (long k = 1; k < size(); ++k)
+				if (d_[size_t(k)] > d_[size_t(best)])
+					best = k;
+			*where = I(best);
+			return d_[size_t(best)];
+		}
+		struct CommaInit // m << a, b, c;  (column-major fill of a vector)
+		{
+			Dense &m;
+			long k;
+			CommaInit &operator,(double v)
+			{
+				m(k++) = v;
+				return *this;
+			}
+		};
+		CommaInit operator<<(double v)
+		{
+			(*this)(0) = v;
+			return CommaInit{*this, 1};
+		}
+		struct DiagArray // m.diagonal().array() += s
+		{
+			Dense &m;
+			DiagArray &array() { return *this; }
+			DiagArray &operator+=(double s)
+			{
+				for (long i = 0; i < m.rows() && i < m.cols(); ++i)
+					m(i, i) += s;
+				return *this;
+			}
+		};
+		DiagArray diagonal() { return DiagArray{*this}; }
+		struct Colwise // m.colwise().squaredNorm(): one entry per column
 		{
 			const Dense &m;
+			Dense squaredNorm() const
+			{
+				Dense r(1, m.cols());
+				for (long j = 0; j < m.cols(); ++j)
+					for (long i = 0; i < m.rows(); ++i)
+						r(0, j) += m(i, j) * m(i, j);
+				return r;
+			}
+		};
+		Colwise colwise() const { return Colwise{*this}; }
+		Dense &noalias() { return *this; }
+		Dense eval() const { return *this; }
+		void transposeInPlace() { *this = transpose(); }
+		struct Mask // (m.array() >= s): element-wise comparison result
+		{
+			std::vector<char> keep;
+			int r, c;
+			Dense select(const Dense &then, double otherwise) const
+			{
+				Dense out(r, c);
+				for (size_t k = 0; k < keep.size(); ++k)
+					out(long(k)) = keep[k] ? then(long(k)) : otherwise;
+				return out;
+			}
+		};
+		struct ArrayView // .array(): element-wise view (products of two views, Assembler.cpp:518; >=, sqrt: utils/svd.hpp)
+		{
+			const Dense &m;
+			Mask operator>=(double s) const
+			{
+				Mask k{std::vector<char>(size_t(m.size())), int(m.rows()), int(m.cols())};
+				for (long i = 0; i < m.size(); ++i)
+					k.keep[size_t(i)] = m(i) >= s;
+				return k;
+			}
+			Dense sqrt() const
+			{
+				Dense out(m.rows(), m.cols());
+				for (long i = 0; i < m.size(); ++i)
+					out(i) = std::sqrt(m(i));
+				return out;
+			}
 		};
 		ArrayView array() const { return ArrayView{*this}; }
 		SparseMatrix<double, 0, int> sparseView() const; // defined in mini_sparse.hpp
@@ -195,6 +313,25 @@ namespace Eigen
 					r(i, 0) = m(i, j);
 				return r;
 			}
+			ColProxy &operator=(const ColProxy &o) { return *this = Dense(o); }
+			double norm() const { return Dense(*this).norm(); }
+			Dense cross(const Dense &o) const { return Dense(*this).cross(o); }
+			Dense unitOrthogonal() const { return Dense(*this).unitOrthogonal(); }
+			struct CommaCol
+			{
+				ColProxy &p;
+				long k;
+				CommaCol &operator,(double v)
+				{
+					p.m(k++, p.j) = v;
+					return *this;
+				}
+			};
+			CommaCol operator<<(double v)
+			{
+				m(0, j) = v;
+				return CommaCol{*this, 1};
+			}
 		};
 		struct BlockProxy
 		{
@@ -222,6 +359,9 @@ namespace Eigen
 		Dense row(long i) const { return Dense(RowProxy{const_cast<Dense &>(*this), i}); }
 		ColProxy col(long j) { return ColProxy{*this, j}; }
 		Dense col(long j) const { return Dense(ColProxy{const_cast<Dense &>(*this), j}); }
+		// run-time sized block(i, j, rows, cols)
+		BlockProxy block(long i, long j, long br, long bc) { return BlockProxy{*this, i, j, br, bc}; }
+		Dense block(long i, long j, long br, long bc) const { return Dense(BlockProxy{const_cast<Dense &>(*this), i, j, br, bc}); }
 		template <int BR, int BC>
 		BlockProxy block(long i, long j) { return BlockProxy{*this, i, j, BR, BC}; }
 		template <int BR, int BC>
@@ -298,6 +438,7 @@ namespace Eigen
 	{
 	public:
 		typedef S Scalar;
+		typedef long Index;
 		Matrix() : Dense(R == Dynamic ? 0 : R, C == Dynamic ? 0 : C) {}
 		template <typename I, typename J, typename = std::enable_if_t<std::is_integral_v<I> && std::is_integral_v<J>>>
 		Matrix(I r, J c) : Dense(long(r), long(c)) {}
@@ -318,7 +459,16 @@ namespace Eigen
 				m(i, i) = 1.0;
 			return m;
 		}
+		static Dense Identity() { return Identity(R, C); } // fixed-size form
+		static Dense Ones()                                // fixed-size form
+		{
+			Dense m(R, C);
+			for (long k = 0; k < m.size(); ++k)
+				m(k) = 1.0;
+			return m;
+		}
 		static Dense Zero(long r, long c) { return Dense(r, c); }
+		static Dense Zero(long n) { return C == 1 ? Dense(n, 1) : Dense(1, n); } // vectors
 		static Dense Constant(double v) // fixed-size form only
 		{
 			Dense m(R, C);
@@ -330,6 +480,12 @@ namespace Eigen
 	using MatrixXd = Matrix<double, Dynamic, Dynamic>;
 	using VectorXd = Matrix<double, Dynamic, 1>;
 	using Matrix3d = Matrix<double, 3, 3>;
+	using Matrix2d = Matrix<double, 2, 2>;
+	using Vector3d = Matrix<double, 3, 1>;
+	using Vector2d = Matrix<double, 2, 1>;
+	template <typename S, int N>
+	using Vector = Matrix<S, N, 1>;
+	constexpr unsigned ComputeFullU = 0x04, ComputeFullV = 0x10; // Eigen/src/Core/util/Constants.h values (only tested for non-zero)
 
 	// Map<T>(ptr, n): the reference only reads through it (a column vector of n entries)
 	template <typename T>

@@ -260,7 +260,103 @@ def write_loop_golden():
     print("wrote tests/golden/linear_loops.npz")
 
 
+def write_vd_golden():
+    """tests/golden/vd_local.npz: single-element ViscousDamping cases (P1..P3, jittered tets, previous and current displacement,
+    two time steps) with the energy, gradient and Hessian returned by the reference's own function bodies
+    (oracle/_ref/libvdref.so = ViscousDamping.cpp:5-62, 122-229, 297-342 compiled verbatim against oracle/refmath/mini_eigen.hpp)."""
+    sys.path.insert(0, ROOT)
+    from polyfem_b200 import tables
+    lib = ctypes.CDLL(os.path.join(ROOT, "oracle", "_ref", "libvdref.so"))
+    dp = ctypes.POINTER(ctypes.c_double)
+    lib.ref_vd_local.argtypes = [ctypes.c_int, ctypes.c_int, dp, dp, dp, dp, dp, ctypes.c_double, ctypes.c_double, ctypes.c_double, dp, dp, dp]
+    rng = np.random.default_rng(535353)
+    gold = {"psi": 30.0, "phi": 20.0}
+    k = 0
+    for p in (1, 2, 3):
+        t = tables.reference_tables(p)
+        nl, nq = t["grad"].shape[1], t["weights"].size
+        grads = np.ascontiguousarray(t["grad"])
+        for rep in range(3):
+            verts = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0], [0, 0, 1]], dtype=np.float64)
+            verts = 0.3 * (verts + 0.25 * rng.uniform(-1, 1, (4, 3))) + rng.uniform(-1, 1, 3)
+            u_prev = 0.03 * rng.uniform(-1, 1, (nl, 3))
+            u = u_prev + 0.01 * rng.uniform(-1, 1, (nl, 3))
+            dt = (0.05, 0.2, 1e-3)[rep]
+            edges = verts[1:] - verts[0]
+            jac_it = np.ascontiguousarray(np.repeat(np.linalg.inv(edges).T[None], nq, 0).reshape(nq, 9))
+            da = np.ascontiguousarray(np.linalg.det(edges) * t["weights"])
+            e, g, H = np.zeros(1), np.zeros(nl * 3), np.zeros((nl * 3, nl * 3))
+            assert lib.ref_vd_local(nl, nq, ptr(np.ascontiguousarray(u.reshape(-1))), ptr(np.ascontiguousarray(u_prev.reshape(-1))), ptr(grads), ptr(jac_it),
+                                    ptr(da), dt, gold["psi"], gold["phi"], ptr(e), ptr(g), ptr(H)) == 0
+            gold[f"p_{k}"], gold[f"dt_{k}"] = p, dt
+            gold[f"vertices_{k}"], gold[f"u_{k}"], gold[f"u_prev_{k}"] = verts, u, u_prev
+            gold[f"energy_{k}"], gold[f"gradient_{k}"], gold[f"hessian_{k}"] = float(e[0]), g, H
+            k += 1
+    gold["n_cases"] = k
+    np.savez_compressed(os.path.join(ROOT, "tests", "golden", "vd_local.npz"), **gold)
+    print(f"wrote tests/golden/vd_local.npz ({k} cases)")
+
+
+def write_fc_golden():
+    """tests/golden/fc_local.npz: single-element FixedCorotational cases (P1..P3, jittered tets; small, moderate and large
+    displacements, one inverted element, one pure rotation) with the energy, gradient and Hessian returned by the reference's own
+    function bodies over its own SVD (oracle/_ref/libfcref.so), plus the reference's signed SVD of a few matrices."""
+    sys.path.insert(0, ROOT)
+    from polyfem_b200 import tables
+    lib = ctypes.CDLL(os.path.join(ROOT, "oracle", "_ref", "libfcref.so"))
+    dp = ctypes.POINTER(ctypes.c_double)
+    lib.ref_fc_local.argtypes = [ctypes.c_int, ctypes.c_int, dp, dp, dp, dp, ctypes.c_double, ctypes.c_double, dp, dp, dp]
+    lib.ref_svd3.argtypes = [dp, dp, dp, dp]
+    rng = np.random.default_rng(646464)
+    lam, mu = 57692.307692307695, 38461.53846153846  # E = 1e5, nu = 0.3
+    gold = {"lambda": lam, "mu": mu}
+    k = 0
+    for p in (1, 2, 3):
+        t = tables.reference_tables(p)
+        nodes = tables.p_nodes(p)
+        nl, nq = t["grad"].shape[1], t["weights"].size
+        grads = np.ascontiguousarray(t["grad"])
+        for rep in range(4):
+            verts = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0], [0, 0, 1]], dtype=np.float64)
+            verts = 0.3 * (verts + 0.25 * rng.uniform(-1, 1, (4, 3))) + rng.uniform(-1, 1, 3)
+            scale = (1e-4, 0.05, 0.3, 0.05)[rep] * 0.3 * (1.0 if p < 3 else 0.3)
+            u = scale * rng.uniform(-1, 1, (nl, 3))
+            if rep == 3 and p == 1:  # inverted element (det F < 0): allowed by this material, sigma_2 < 0
+                u[1] += 2.5 * (verts[0] - verts[1])
+            if rep == 3 and p == 2:  # a rigid rotation of the element: zero energy and stress
+                th = 0.8
+                R = np.array([[np.cos(th), -np.sin(th), 0], [np.sin(th), np.cos(th), 0], [0, 0, 1.0]])
+                edges0 = verts[1:] - verts[0]
+                X = verts[0] + nodes @ edges0
+                u = X @ R.T - X
+            edges = verts[1:] - verts[0]
+            jac_it = np.ascontiguousarray(np.repeat(np.linalg.inv(edges).T[None], nq, 0).reshape(nq, 9))
+            da = np.ascontiguousarray(np.linalg.det(edges) * t["weights"])
+            e, g, H = np.zeros(1), np.zeros(nl * 3), np.zeros((nl * 3, nl * 3))
+            assert lib.ref_fc_local(nl, nq, ptr(np.ascontiguousarray(u.reshape(-1))), ptr(grads), ptr(jac_it), ptr(da), lam, mu, ptr(e), ptr(g), ptr(H)) == 0
+            gold[f"p_{k}"] = p
+            gold[f"vertices_{k}"], gold[f"u_{k}"] = verts, u
+            gold[f"energy_{k}"], gold[f"gradient_{k}"], gold[f"hessian_{k}"] = float(e[0]), g, H
+            k += 1
+    gold["n_cases"] = k
+    mats, Us, Ss, Vs = [], [], [], []
+    for trial in range(6):
+        A = np.eye(3) + (0.3, 0.3, 1e-3, 1e-6, 0.8, 0.3)[trial] * rng.uniform(-1, 1, (3, 3))
+        if trial == 5:
+            A[:, 0] *= -1.0
+        U, S, V = np.zeros((3, 3)), np.zeros(3), np.zeros((3, 3))
+        lib.ref_svd3(ptr(np.ascontiguousarray(A)), ptr(U), ptr(S), ptr(V))
+        mats.append(A), Us.append(U), Ss.append(S), Vs.append(V)
+    gold["svd_A"], gold["svd_U"], gold["svd_S"], gold["svd_V"] = np.array(mats), np.array(Us), np.array(Ss), np.array(Vs)
+    np.savez_compressed(os.path.join(ROOT, "tests", "golden", "fc_local.npz"), **gold)
+    print(f"wrote tests/golden/fc_local.npz ({k} cases)")
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "corotational":
+        return write_fc_golden()
+    if len(sys.argv) > 1 and sys.argv[1] == "viscous":
+        return write_vd_golden()
     if len(sys.argv) > 1 and sys.argv[1] == "loops":
         return write_loop_golden()
     if len(sys.argv) > 1 and sys.argv[1] == "le_energy":
