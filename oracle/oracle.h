@@ -32,9 +32,15 @@
  *   - FixedCorotational energy / gradient / Hessian: PINNED against the reference's own function bodies AND its own 3 x 3 SVD
  *     (FixedCorotational.cpp:293-436, 592-827, utils/svd.hpp:134-317 compiled verbatim into oracle/_ref/libfcref.so;
  *     tests/golden/fc_local.npz, tests/test_oracle_corotational_reference.py, 1e-12; the oracle's own SVD is a Jacobi one).
- *   - SaintVenant, MooneyRivlin: property-pinned (the reference differentiates their energy expressions by its autodiff
- *     scalars over Eigen matrices of them, not compilable here): known answers in tests/test_oracle_saint_venant_and_curved.py,
- *     tests/test_oracle_mooney_rivlin.py.
+ *   - SaintVenant energy / gradient / Hessian: PINNED against the reference's own code path - compute_energy_aux<T>, stress<T, N>,
+ *     strain_from_disp_grad (SaintVenantElasticity.cpp:9-20, 61-70, 206-266) differentiated by the reference's OWN utils/autodiff.h
+ *     (included unmodified) through its own gradient_from_energy / hessian_from_energy (utils/ElasticityUtils.cpp:81-270), over its
+ *     own ElasticityTensor::set_from_lambda_mu (MatParams.cpp:211-253): oracle/_ref/libsvref.so, tests/golden/sv_local.npz,
+ *     tests/test_oracle_saint_venant_reference.py, 1e-13.
+ *   - MooneyRivlin energy / gradient / Hessian: PINNED the same way - MooneyRivlinElasticity::elastic_energy<T>
+ *     (MooneyRivlinElasticity.hpp:25-47) through the reference's own autodiff.h inside GenericElastic's compute_energy_aux,
+ *     compute_gradient_from_stress, compute_hessian_from_stress (GenericElastic.hpp:92-212, 268-351): oracle/_ref/libmrref.so,
+ *     tests/golden/mr_local.npz, tests/test_oracle_mooney_reference.py, 1e-13.
  *   - project_to_psd (ipc-toolkit, source absent): UNPINNED, documented behaviour restated.
  *   - Mass (assembler/Mass.cpp:5-23): pinned by closed forms (P1 local mass rho*V/20*(1+delta_ij), total mass,
  *     stored zeros off the block diagonal; tests/test_oracle_mass.py) - the reference has no unit test for it.

@@ -9,6 +9,7 @@
 #include <cassert>
 #include <cmath>
 #include <cstddef>
+#include <ostream>
 #include <type_traits>
 #include <vector>
 
@@ -18,9 +19,16 @@ namespace Eigen
 	template <typename S, int Opt, typename I>
 	class SparseMatrix; // mini_sparse.hpp
 
+	struct IOFormat // only named by the stream operators of utils/autodiff.h, which nothing here calls
+	{
+		template <typename... A>
+		IOFormat(A...) {}
+	};
+
 	class Dense
 	{
 	public:
+		typedef double Scalar;
 		Dense() = default;
 		Dense(long r, long c) : r_(int(r)), c_(int(c)), d_(size_t(r) * size_t(c), 0.0) {}
 
@@ -35,6 +43,14 @@ namespace Eigen
 			c_ = int(c);
 			d_.assign(size_t(r) * size_t(c), 0.0);
 		}
+		void resize(long n) // vectors
+		{
+			if (c_ == 1 || (r_ == 0 && c_ == 0))
+				resize(n, 1);
+			else
+				resize(1, n);
+		}
+		const char *format(const IOFormat &) const { return ""; }
 		void setZero() { d_.assign(d_.size(), 0.0); }
 		void setZero(long r, long c) { resize(r, c); }
 
@@ -183,13 +199,14 @@ namespace Eigen
 			*where = I(best);
 			return d_[size_t(best)];
 		}
-		struct CommaInit // m << a, b, c;  (column-major fill of a vector)
+		struct CommaInit // m << a, b, c, ...;  fills row by row, whatever the storage order (as Eigen's comma initialiser does)
 		{
 			Dense &m;
 			long k;
 			CommaInit &operator,(double v)
 			{
-				m(k++) = v;
+				m(k / m.cols(), k % m.cols()) = v;
+				++k;
 				return *this;
 			}
 		};
@@ -258,6 +275,26 @@ namespace Eigen
 		};
 		ArrayView array() const { return ArrayView{*this}; }
 		SparseMatrix<double, 0, int> sparseView() const; // defined in mini_sparse.hpp
+		Dense &operator*=(const Dense &o); // matrix product, defined after operator*
+		Dense &operator*=(double s)
+		{
+			for (double &v : d_)
+				v *= s;
+			return *this;
+		}
+		Dense &operator/=(double s)
+		{
+			for (double &v : d_)
+				v /= s;
+			return *this;
+		}
+		Dense &operator-=(const Dense &o)
+		{
+			assert(r_ == o.r_ && c_ == o.c_);
+			for (size_t k = 0; k < d_.size(); ++k)
+				d_[k] -= o.d_[k];
+			return *this;
+		}
 		Dense &operator+=(const Dense &o)
 		{
 			assert(r_ == o.r_ && c_ == o.c_);
@@ -345,6 +382,14 @@ namespace Eigen
 						m(i0 + i, j0 + j) = v(i, j);
 				return *this;
 			}
+			BlockProxy &operator+=(const Dense &v)
+			{
+				assert(v.rows() == br && v.cols() == bc);
+				for (long i = 0; i < br; ++i)
+					for (long j = 0; j < bc; ++j)
+						m(i0 + i, j0 + j) += v(i, j);
+				return *this;
+			}
 			operator Dense() const
 			{
 				Dense r(br, bc);
@@ -409,6 +454,7 @@ namespace Eigen
 			}
 		return r;
 	}
+	inline Dense &Dense::operator*=(const Dense &o) { return *this = *this * o; }
 	inline Dense operator*(double s, const Dense &a)
 	{
 		Dense r(a.rows(), a.cols());
@@ -433,9 +479,110 @@ namespace Eigen
 		return r;
 	}
 
+	// Primary template: a small dense column-major matrix of ANY scalar type (the autodiff scalars of utils/autodiff.h inside
+	// GenericElastic: 3 x 3 deformation gradients of DScalar1 / DScalar2). Only what those function bodies use.
 	template <typename S, int R, int C, int Opt = 0, int MR = R, int MC = C>
-	class Matrix : public Dense
+	class Matrix
 	{
+	public:
+		typedef S Scalar;
+		Matrix() : r_(R == Dynamic ? 0 : R), c_(C == Dynamic ? 0 : C), d_(size_t(r_) * size_t(c_)) {}
+		template <typename I, typename J, typename = std::enable_if_t<std::is_integral_v<I> && std::is_integral_v<J>>>
+		Matrix(I r, J c) : r_(int(r)), c_(int(c)), d_(size_t(r) * size_t(c)) {}
+		template <int R2, int C2, int O2, int MR2, int MC2>
+		Matrix(const Matrix<S, R2, C2, O2, MR2, MC2> &o) : r_(int(o.rows())), c_(int(o.cols())), d_(size_t(o.size()))
+		{
+			for (long k = 0; k < o.size(); ++k)
+				d_[size_t(k)] = o(k);
+		}
+		long rows() const { return r_; }
+		long cols() const { return c_; }
+		long size() const { return long(r_) * c_; }
+		void resize(long r, long c)
+		{
+			r_ = int(r);
+			c_ = int(c);
+			d_.assign(size_t(r) * size_t(c), S());
+		}
+		S &operator()(long i, long j) { return d_[size_t(j) * r_ + i]; }
+		const S &operator()(long i, long j) const { return d_[size_t(j) * r_ + i]; }
+		S &operator()(long k) { return d_[size_t(k)]; }
+		const S &operator()(long k) const { return d_[size_t(k)]; }
+		Matrix transpose() const
+		{
+			Matrix t(c_, r_);
+			for (int i = 0; i < r_; ++i)
+				for (int j = 0; j < c_; ++j)
+					t(j, i) = (*this)(i, j);
+			return t;
+		}
+		S trace() const
+		{
+			S s = (*this)(0, 0);
+			for (int i = 1; i < r_ && i < c_; ++i)
+				s = s + (*this)(i, i);
+			return s;
+		}
+		Matrix &operator*=(const Matrix &o) { return *this = *this * o; }
+		Matrix operator+(const Matrix &o) const
+		{
+			assert(r_ == o.r_ && c_ == o.c_);
+			Matrix r(r_, c_);
+			for (size_t k = 0; k < d_.size(); ++k)
+				r.d_[k] = d_[k] + o.d_[k];
+			return r;
+		}
+		struct CommaInit // row by row, as Eigen's comma initialiser
+		{
+			Matrix &m;
+			long k;
+			CommaInit &operator,(const S &v)
+			{
+				m(k / m.cols(), k % m.cols()) = v;
+				++k;
+				return *this;
+			}
+		};
+		CommaInit operator<<(const S &v)
+		{
+			(*this)(0, 0) = v;
+			return CommaInit{*this, 1};
+		}
+
+	private:
+		int r_, c_;
+		std::vector<S> d_;
+	};
+	template <typename S, int R, int C, int O, int MR, int MC, int R2, int C2, int O2, int MR2, int MC2>
+	std::enable_if_t<!std::is_same_v<S, double>, Matrix<S, R, C, O, MR, MC>> operator*(const Matrix<S, R, C, O, MR, MC> &a, const Matrix<S, R2, C2, O2, MR2, MC2> &b)
+	{
+		assert(a.cols() == b.rows());
+		Matrix<S, R, C, O, MR, MC> r(a.rows(), b.cols());
+		for (long i = 0; i < a.rows(); ++i)
+			for (long j = 0; j < b.cols(); ++j)
+			{
+				S s = a(i, 0) * b(0, j);
+				for (long k = 1; k < a.cols(); ++k)
+					s = s + a(i, k) * b(k, j);
+				r(i, j) = s;
+			}
+		return r;
+	}
+	template <typename S, int R, int C, int O, int MR, int MC>
+	std::enable_if_t<!std::is_same_v<S, double>, Matrix<S, R, C, O, MR, MC>> operator/(const Matrix<S, R, C, O, MR, MC> &a, const S &s)
+	{
+		Matrix<S, R, C, O, MR, MC> r(a.rows(), a.cols());
+		for (long k = 0; k < a.size(); ++k)
+			r(k) = a(k) / s;
+		return r;
+	}
+
+	// double: the eager `Dense` matrix above
+	template <int R, int C, int Opt, int MR, int MC>
+	class Matrix<double, R, C, Opt, MR, MC> : public Dense
+	{
+		typedef double S;
+
 	public:
 		typedef S Scalar;
 		typedef long Index;

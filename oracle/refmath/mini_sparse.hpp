@@ -217,9 +217,9 @@ namespace Eigen
 	template <typename S, int Opt, typename I>
 	SparseMatrix<S, Opt, I>::SparseMatrix(const Map<const SparseMatrix> &m) { *this = m; }
 
-	template <typename S, int R, int C, int Opt, int MR, int MC>
+	template <int R, int C, int Opt, int MR, int MC>
 	template <typename S2, int O2, typename I2>
-	Matrix<S, R, C, Opt, MR, MC>::Matrix(const SparseMatrix<S2, O2, I2> &sp) : Dense(sp.rows(), sp.cols())
+	Matrix<double, R, C, Opt, MR, MC>::Matrix(const SparseMatrix<S2, O2, I2> &sp) : Dense(sp.rows(), sp.cols())
 	{
 		for (long c = 0; c < sp.outerSize(); ++c)
 			for (typename SparseMatrix<S2, O2, I2>::InnerIterator it(sp, c); it; ++it)

@@ -1,7 +1,7 @@
-"""CUDA path vs the outputs of the reference's OWN ViscousDamping and FixedCorotational code (tests/golden/vd_local.npz,
-fc_local.npz: function bodies compiled verbatim from /root/reference, FixedCorotational over the reference's own SVD;
-tests/test_oracle_viscous_reference.py, tests/test_oracle_corotational_reference.py). Single-element meshes: the assembled
-matrix is the dense local Hessian."""
+"""CUDA path vs the outputs of the reference's OWN code for the materials added in round 2 (tests/golden/vd_local.npz, fc_local.npz,
+mr_local.npz, sv_local.npz: function bodies compiled verbatim from /root/reference - FixedCorotational over the reference's own
+SVD, MooneyRivlin and SaintVenant through the reference's own autodiff scalars; tests/test_oracle_*_reference.py). Single-element
+meshes: the assembled matrix is the dense local Hessian."""
 import os
 
 import numpy as np
@@ -13,6 +13,8 @@ pytestmark = pytest.mark.gpu
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 VD = np.load(os.path.join(GOLDEN, "vd_local.npz"))
 FC = np.load(os.path.join(GOLDEN, "fc_local.npz"))
+MR = np.load(os.path.join(GOLDEN, "mr_local.npz"))
+SV = np.load(os.path.join(GOLDEN, "sv_local.npz"))
 
 
 def dense(h, v, n):
@@ -58,3 +60,37 @@ def test_fixed_corotational_equals_the_reference_code(k):
     assert abs(e - e_ref) <= 1e-11 * max(abs(e_ref), hs * size * size * 1e-3)
     assert np.abs(g - g_ref).max() <= 1e-11 * max(np.abs(g_ref).max(), hs * size * 1e-3)
     assert np.abs(dense(h, v, 3 * nl) - H_ref).max() <= 1e-11 * hs
+
+
+@pytest.mark.parametrize("k", range(int(MR["n_cases"])))
+def test_mooney_rivlin_equals_the_reference_code(k):
+    from polyfem_b200 import capi
+    p = int(MR[f"p_{k}"])
+    t = tables.reference_tables(p)
+    u, verts = MR[f"u_{k}"], MR[f"vertices_{k}"]
+    nl = u.shape[0]
+    c1, c2, kk = float(MR["c1"]), float(MR["c2"]), float(MR["k"])
+    h = capi.Handle("MooneyRivlin", np.arange(nl, dtype=np.int32)[None, :], nl, t["weights"], t["grad"], vertices=verts[None], lam=c1, mu=c2, param3=kk)
+    e, g, v = h.grad_hess(u.reshape(-1))
+    e_ref, g_ref, H_ref = float(MR[f"energy_{k}"]), MR[f"gradient_{k}"], MR[f"hessian_{k}"]
+    vol = abs(np.linalg.det(verts[1:] - verts[0])) / 6.0
+    # (the energy of a tiny strain is a difference of numbers near 3 (c1 + c2) per unit volume on both sides)
+    assert abs(e - e_ref) <= 1e-12 * max(abs(e_ref), 3.0 * (c1 + c2) * vol)
+    assert np.abs(g - g_ref).max() <= 1e-12 * max(np.abs(g_ref).max(), 1e-6 * np.abs(H_ref).max() * float(np.linalg.norm(verts[1] - verts[0])))
+    assert np.abs(dense(h, v, 3 * nl) - H_ref).max() <= 1e-12 * np.abs(H_ref).max()
+
+
+@pytest.mark.parametrize("k", range(int(SV["n_cases"])))
+def test_saint_venant_equals_the_reference_code(k):
+    from polyfem_b200 import capi
+    p = int(SV[f"p_{k}"])
+    t = tables.reference_tables(p)
+    u = SV[f"u_{k}"]
+    nl = u.shape[0]
+    h = capi.Handle("SaintVenant", np.arange(nl, dtype=np.int32)[None, :], nl, t["weights"], t["grad"], vertices=SV[f"vertices_{k}"][None],
+                    lam=float(SV["lambda"]), mu=float(SV["mu"]))
+    e, g, v = h.grad_hess(u.reshape(-1))
+    e_ref, g_ref, H_ref = float(SV[f"energy_{k}"]), SV[f"gradient_{k}"], SV[f"hessian_{k}"]
+    assert abs(e - e_ref) <= 1e-12 * abs(e_ref)
+    assert np.abs(g - g_ref).max() <= 1e-12 * np.abs(g_ref).max()
+    assert np.abs(dense(h, v, 3 * nl) - H_ref).max() <= 1e-12 * np.abs(H_ref).max()

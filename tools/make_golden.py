@@ -352,7 +352,85 @@ def write_fc_golden():
     print(f"wrote tests/golden/fc_local.npz ({k} cases)")
 
 
+def write_mr_golden():
+    """tests/golden/mr_local.npz: single-element MooneyRivlin cases (P1..P4, jittered tets) with the energy, gradient and Hessian
+    of the reference's own code path: elastic_energy<T> through its own autodiff scalars inside GenericElastic (oracle/_ref/libmrref.so)."""
+    sys.path.insert(0, ROOT)
+    from polyfem_b200 import tables
+    lib = ctypes.CDLL(os.path.join(ROOT, "oracle", "_ref", "libmrref.so"))
+    dp = ctypes.POINTER(ctypes.c_double)
+    lib.ref_mr_local.argtypes = [ctypes.c_int, ctypes.c_int, dp, dp, dp, dp, ctypes.c_double, ctypes.c_double, ctypes.c_double, dp, dp, dp]
+    rng = np.random.default_rng(757575)
+    gold = {"c1": 11000.0, "c2": 7000.0, "k": 90000.0}
+    k = 0
+    for p in (1, 2, 3, 4):
+        t = tables.reference_tables(p)
+        nl, nq = t["grad"].shape[1], t["weights"].size
+        grads = np.ascontiguousarray(t["grad"])
+        for rep in range(3):
+            verts = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0], [0, 0, 1]], dtype=np.float64)
+            verts = 0.3 * (verts + 0.25 * rng.uniform(-1, 1, (4, 3))) + rng.uniform(-1, 1, 3)
+            scale = (1e-3, 0.05, 0.1)[rep] * 0.3 * (1.0, 1.0, 0.4, 0.1)[p - 1]
+            u = scale * rng.uniform(-1, 1, (nl, 3))
+            edges = verts[1:] - verts[0]
+            jac_it = np.ascontiguousarray(np.repeat(np.linalg.inv(edges).T[None], nq, 0).reshape(nq, 9))
+            da = np.ascontiguousarray(np.linalg.det(edges) * t["weights"])
+            e, g, H = np.zeros(1), np.zeros(nl * 3), np.zeros((nl * 3, nl * 3))
+            assert lib.ref_mr_local(nl, nq, ptr(np.ascontiguousarray(u.reshape(-1))), ptr(grads), ptr(jac_it), ptr(da), gold["c1"], gold["c2"], gold["k"],
+                                    ptr(e), ptr(g), ptr(H)) == 0
+            assert np.isfinite(e[0]) and np.isfinite(H).all()
+            gold[f"p_{k}"] = p
+            gold[f"vertices_{k}"], gold[f"u_{k}"] = verts, u
+            gold[f"energy_{k}"], gold[f"gradient_{k}"], gold[f"hessian_{k}"] = float(e[0]), g, H
+            k += 1
+    gold["n_cases"] = k
+    np.savez_compressed(os.path.join(ROOT, "tests", "golden", "mr_local.npz"), **gold)
+    print(f"wrote tests/golden/mr_local.npz ({k} cases)")
+
+
+def write_sv_golden():
+    """tests/golden/sv_local.npz: single-element SaintVenant cases (P1..P4, jittered tets; also compressed states, where the
+    tangent is indefinite) with the energy, gradient and Hessian of the reference's own code path (oracle/_ref/libsvref.so)."""
+    sys.path.insert(0, ROOT)
+    from polyfem_b200 import tables
+    lib = ctypes.CDLL(os.path.join(ROOT, "oracle", "_ref", "libsvref.so"))
+    dp = ctypes.POINTER(ctypes.c_double)
+    lib.ref_sv_local.argtypes = [ctypes.c_int, ctypes.c_int, dp, dp, dp, dp, ctypes.c_double, ctypes.c_double, dp, dp, dp]
+    rng = np.random.default_rng(868686)
+    lam, mu = 57692.307692307695, 38461.53846153846
+    gold = {"lambda": lam, "mu": mu}
+    k = 0
+    for p in (1, 2, 3, 4):
+        t = tables.reference_tables(p)
+        nodes = tables.p_nodes(p)
+        nl, nq = t["grad"].shape[1], t["weights"].size
+        grads = np.ascontiguousarray(t["grad"])
+        for rep in range(3):
+            verts = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0], [0, 0, 1]], dtype=np.float64)
+            verts = 0.3 * (verts + 0.25 * rng.uniform(-1, 1, (4, 3))) + rng.uniform(-1, 1, 3)
+            u = (1e-3, 0.1, 0.05)[rep] * 0.3 * rng.uniform(-1, 1, (nl, 3))
+            if rep == 2:  # compress the element to 40 % (SaintVenant allows it; the geometric stiffness turns negative)
+                X = verts[0] + nodes @ (verts[1:] - verts[0])
+                u = u - 0.6 * (X - X.mean(0))
+            edges = verts[1:] - verts[0]
+            jac_it = np.ascontiguousarray(np.repeat(np.linalg.inv(edges).T[None], nq, 0).reshape(nq, 9))
+            da = np.ascontiguousarray(np.linalg.det(edges) * t["weights"])
+            e, g, H = np.zeros(1), np.zeros(nl * 3), np.zeros((nl * 3, nl * 3))
+            assert lib.ref_sv_local(nl, nq, ptr(np.ascontiguousarray(u.reshape(-1))), ptr(grads), ptr(jac_it), ptr(da), lam, mu, ptr(e), ptr(g), ptr(H)) == 0
+            gold[f"p_{k}"] = p
+            gold[f"vertices_{k}"], gold[f"u_{k}"] = verts, u
+            gold[f"energy_{k}"], gold[f"gradient_{k}"], gold[f"hessian_{k}"] = float(e[0]), g, H
+            k += 1
+    gold["n_cases"] = k
+    np.savez_compressed(os.path.join(ROOT, "tests", "golden", "sv_local.npz"), **gold)
+    print(f"wrote tests/golden/sv_local.npz ({k} cases)")
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "saint_venant":
+        return write_sv_golden()
+    if len(sys.argv) > 1 and sys.argv[1] == "mooney":
+        return write_mr_golden()
     if len(sys.argv) > 1 and sys.argv[1] == "corotational":
         return write_fc_golden()
     if len(sys.argv) > 1 and sys.argv[1] == "viscous":
