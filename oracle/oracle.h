@@ -24,8 +24,9 @@
  *     own LinearElasticity / Laplacian / Mass local functions (tests/golden/linear_loops.npz).
  *   - the NL path of LinearElasticity: energy PINNED against the reference's own compute_energy_aux<double>
  *     (LinearElasticity.cpp:103-132, tests/golden/le_energy.npz); gradient / Hessian are autodiff of that function in the
- *     reference (not compilable here) and property-pinned: closed form == autodiff 1e-12, Hessian == pinned linear
- *     stiffness 1e-8, finite differences.
+ *     reference: PINNED since the end of round 2 against the reference's own assemble_gradient / assemble_hessian over its own
+ *     utils/autodiff.h (oracle/_ref/libsvref.so::ref_le_nl_local, tests/golden/le_nl_local.npz,
+ *     tests/test_oracle_saint_venant_reference.py, 1e-13), besides the earlier property checks.
  *   - ViscousDamping energy / gradient / Hessian: PINNED against the reference's own function bodies (ViscousDamping.cpp:5-62,
  *     122-229, 297-342 compiled verbatim into oracle/_ref/libvdref.so; tests/golden/vd_local.npz,
  *     tests/test_oracle_viscous_reference.py, 1e-13).

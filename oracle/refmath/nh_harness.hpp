@@ -180,6 +180,9 @@ namespace polyfem::assembler
 		Eigen::Matrix<double, Eigen::Dynamic, 1, 0, 9, 1> assemble(const LinearAssemblerData &data) const PFREF_OVERRIDE;
 		template <typename T>
 		T compute_energy_aux(const NonLinearAssemblerData &data) const; // LinearElasticity.cpp:103-132
+		// the autodiff gradient / Hessian of that energy (LinearElasticity.cpp:70-101), defined only by sv_glue.cpp
+		Eigen::VectorXd assemble_gradient(const NonLinearAssemblerData &data) const;
+		Eigen::MatrixXd assemble_hessian(const NonLinearAssemblerData &data) const;
 	};
 	class Laplacian PFREF_LIN_BASE
 	{

@@ -82,12 +82,70 @@ namespace polyfem::assembler
 #include "../_ref/sv_strain_extracted.inc"
 	}
 #include "../_ref/sv_extracted.inc"
+	// LinearElasticity inside a nonlinear solve: compute_energy_aux<T> (LinearElasticity.cpp:103-132) and its autodiff gradient /
+	// Hessian (:70-101), the class itself is declared in nh_harness.hpp
+#include "../_ref/le_energy_extracted.inc"
+#include "../_ref/le_ad_extracted.inc"
 } // namespace polyfem::assembler
 
 using namespace polyfem::assembler;
 
 extern "C"
 {
+	static void fill_values(ElementAssemblyValues &vals, Eigen::VectorXd &dav, int n_basis, int n_qp, const double *grads, const double *jac_it, const double *da)
+	{
+		dav.resize(n_qp, 1);
+		vals.quadrature.points.resize(n_qp, 3);
+		vals.val.resize(n_qp, 3);
+		vals.basis_values.resize(n_basis);
+		for (int i = 0; i < n_basis; ++i)
+		{
+			vals.basis_values[i].global = {Local2Global{i, 1.0}};
+			vals.basis_values[i].grad.resize(n_qp, 3);
+			for (int q = 0; q < n_qp; ++q)
+				for (int c = 0; c < 3; ++c)
+					vals.basis_values[i].grad(q, c) = grads[(size_t(q) * n_basis + i) * 3 + c];
+		}
+		vals.jac_it.resize(n_qp);
+		for (int q = 0; q < n_qp; ++q)
+		{
+			dav(q) = da[q];
+			vals.jac_it[q].resize(3, 3);
+			for (int r = 0; r < 3; ++r)
+				for (int c = 0; c < 3; ++c)
+					vals.jac_it[q](r, c) = jac_it[size_t(q) * 9 + r * 3 + c];
+		}
+	}
+
+	// LinearElasticity as an NLAssembler (LinearElasticity.cpp:65-132): energy and its autodiff gradient / Hessian
+	int ref_le_nl_local(int n_basis, int n_qp, const double *u, const double *grads, const double *jac_it, const double *da, double lambda, double mu,
+						double *energy, double *gradient, double *hessian)
+	{
+		ElementAssemblyValues vals;
+		Eigen::MatrixXd x(long(n_basis) * 3, 1), x_prev;
+		Eigen::VectorXd dav;
+		for (int i = 0; i < n_basis * 3; ++i)
+			x(i) = u[i];
+		fill_values(vals, dav, n_basis, n_qp, grads, jac_it, da);
+		LinearElasticity le;
+		le.params_.lambda = lambda;
+		le.params_.mu = mu;
+		const NonLinearAssemblerData data{vals, 0.0, 1.0, x, x_prev, dav};
+		*energy = le.compute_energy_aux<double>(data);
+		const Eigen::VectorXd g = le.assemble_gradient(data);
+		const Eigen::MatrixXd H = le.assemble_hessian(data);
+		const long N = long(n_basis) * 3;
+		if (g.size() != N || H.rows() != N || H.cols() != N)
+			return -1;
+		for (long r = 0; r < N; ++r)
+		{
+			gradient[r] = g(r);
+			for (long c = 0; c < N; ++c)
+				hessian[r * N + c] = H(r, c);
+		}
+		return 0;
+	}
+
 	// u [n_basis][3], grads [n_qp][n_basis][3], jac_it [n_qp][9] row-major, da [n_qp]; out: energy, gradient [N] node-major,
 	// hessian [N][N] row-major
 	int ref_sv_local(int n_basis, int n_qp, const double *u, const double *grads, const double *jac_it, const double *da, double lambda, double mu,

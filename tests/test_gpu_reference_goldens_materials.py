@@ -15,6 +15,7 @@ VD = np.load(os.path.join(GOLDEN, "vd_local.npz"))
 FC = np.load(os.path.join(GOLDEN, "fc_local.npz"))
 MR = np.load(os.path.join(GOLDEN, "mr_local.npz"))
 SV = np.load(os.path.join(GOLDEN, "sv_local.npz"))
+LE = np.load(os.path.join(GOLDEN, "le_nl_local.npz"))
 
 
 def dense(h, v, n):
@@ -91,6 +92,23 @@ def test_saint_venant_equals_the_reference_code(k):
                     lam=float(SV["lambda"]), mu=float(SV["mu"]))
     e, g, v = h.grad_hess(u.reshape(-1))
     e_ref, g_ref, H_ref = float(SV[f"energy_{k}"]), SV[f"gradient_{k}"], SV[f"hessian_{k}"]
+    assert abs(e - e_ref) <= 1e-12 * abs(e_ref)
+    assert np.abs(g - g_ref).max() <= 1e-12 * np.abs(g_ref).max()
+    assert np.abs(dense(h, v, 3 * nl) - H_ref).max() <= 1e-12 * np.abs(H_ref).max()
+
+
+@pytest.mark.parametrize("k", range(int(LE["n_cases"])))
+def test_linear_elasticity_nl_path_equals_the_reference_autodiff(k):
+    """LinearElasticity inside a nonlinear solve: energy, gradient and Hessian (LinearElasticity.cpp:65-132, autodiff in the reference)"""
+    from polyfem_b200 import capi
+    p = int(LE[f"p_{k}"])
+    t = tables.reference_tables(p)
+    u = LE[f"u_{k}"]
+    nl = u.shape[0]
+    h = capi.Handle("LinearElasticity", np.arange(nl, dtype=np.int32)[None, :], nl, t["weights"], t["grad"], vertices=LE[f"vertices_{k}"][None],
+                    lam=float(LE["lambda"]), mu=float(LE["mu"]))
+    e, g, v = h.grad_hess(u.reshape(-1))
+    e_ref, g_ref, H_ref = float(LE[f"energy_{k}"]), LE[f"gradient_{k}"], LE[f"hessian_{k}"]
     assert abs(e - e_ref) <= 1e-12 * abs(e_ref)
     assert np.abs(g - g_ref).max() <= 1e-12 * np.abs(g_ref).max()
     assert np.abs(dense(h, v, 3 * nl) - H_ref).max() <= 1e-12 * np.abs(H_ref).max()

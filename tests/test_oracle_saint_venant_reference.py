@@ -78,3 +78,26 @@ def test_live_against_libsvref_when_present(oracle):
             assert abs(prob.local_energy(e, x) - en[0]) <= TOL * abs(en[0])
             close(prob.local_gradient(e, x), g)
             close(prob.local_hessian(e, x).reshape(3 * nl, 3 * nl), H)
+
+
+LE = np.load(os.path.join(ROOT, "tests", "golden", "le_nl_local.npz"))
+
+
+@pytest.mark.parametrize("k", range(int(LE["n_cases"])))
+def test_linear_elasticity_nl_path_equals_reference_autodiff(oracle, k):
+    """LinearElasticity as an NLAssembler: the reference differentiates compute_energy_aux<T> with its own autodiff scalars
+    (LinearElasticity.cpp:65-132); tests/golden/le_nl_local.npz holds its outputs (ref_le_nl_local of oracle/_ref/libsvref.so,
+    `tools/make_golden.py le_nl`). The oracle's gradient / Hessian of that path were property-pinned until now."""
+    p = int(LE[f"p_{k}"])
+    t = tables.reference_tables(p)
+    u = LE[f"u_{k}"]
+    nl = u.shape[0]
+    prob = oracle.OracleProblem("LinearElasticity", np.arange(nl, dtype=np.int32)[None, :], LE[f"vertices_{k}"][None], nl, t["points"], t["weights"],
+                                t["grad"], lam=float(LE["lambda"]), mu=float(LE["mu"]))
+    x = u.reshape(-1)
+    e_ref = float(LE[f"energy_{k}"])
+    assert abs(prob.local_energy(0, x) - e_ref) <= TOL * abs(e_ref)
+    close(prob.local_gradient(0, x), LE[f"gradient_{k}"])
+    close(prob.local_hessian(0, x).reshape(3 * nl, 3 * nl), LE[f"hessian_{k}"])
+    close(prob.assemble_gradient(x), LE[f"gradient_{k}"])
+    close(np.asarray(prob.assemble_hessian(x).to_scipy().todense()), LE[f"hessian_{k}"])

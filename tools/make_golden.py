@@ -426,7 +426,44 @@ def write_sv_golden():
     print(f"wrote tests/golden/sv_local.npz ({k} cases)")
 
 
+def write_le_nl_golden():
+    """tests/golden/le_nl_local.npz: LinearElasticity as an NLAssembler (a linear material inside a nonlinear solve): energy and the
+    reference's own AUTODIFF gradient / Hessian of it (LinearElasticity.cpp:65-132 through utils/autodiff.h and
+    gradient_from_energy / hessian_from_energy; oracle/_ref/libsvref.so::ref_le_nl_local), P1..P4 single elements."""
+    sys.path.insert(0, ROOT)
+    from polyfem_b200 import tables
+    lib = ctypes.CDLL(os.path.join(ROOT, "oracle", "_ref", "libsvref.so"))
+    dp = ctypes.POINTER(ctypes.c_double)
+    lib.ref_le_nl_local.argtypes = [ctypes.c_int, ctypes.c_int, dp, dp, dp, dp, ctypes.c_double, ctypes.c_double, dp, dp, dp]
+    rng = np.random.default_rng(979797)
+    lam, mu = 57692.307692307695, 38461.53846153846
+    gold = {"lambda": lam, "mu": mu}
+    k = 0
+    for p in (1, 2, 3, 4):
+        t = tables.reference_tables(p)
+        nl, nq = t["grad"].shape[1], t["weights"].size
+        grads = np.ascontiguousarray(t["grad"])
+        for rep in range(2):
+            verts = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0], [0, 0, 1]], dtype=np.float64)
+            verts = 0.3 * (verts + 0.25 * rng.uniform(-1, 1, (4, 3))) + rng.uniform(-1, 1, 3)
+            u = (0.05, 1.0)[rep] * 0.3 * rng.uniform(-1, 1, (nl, 3))
+            edges = verts[1:] - verts[0]
+            jac_it = np.ascontiguousarray(np.repeat(np.linalg.inv(edges).T[None], nq, 0).reshape(nq, 9))
+            da = np.ascontiguousarray(np.linalg.det(edges) * t["weights"])
+            e, g, H = np.zeros(1), np.zeros(nl * 3), np.zeros((nl * 3, nl * 3))
+            assert lib.ref_le_nl_local(nl, nq, ptr(np.ascontiguousarray(u.reshape(-1))), ptr(grads), ptr(jac_it), ptr(da), lam, mu, ptr(e), ptr(g), ptr(H)) == 0
+            gold[f"p_{k}"] = p
+            gold[f"vertices_{k}"], gold[f"u_{k}"] = verts, u
+            gold[f"energy_{k}"], gold[f"gradient_{k}"], gold[f"hessian_{k}"] = float(e[0]), g, H
+            k += 1
+    gold["n_cases"] = k
+    np.savez_compressed(os.path.join(ROOT, "tests", "golden", "le_nl_local.npz"), **gold)
+    print(f"wrote tests/golden/le_nl_local.npz ({k} cases)")
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "le_nl":
+        return write_le_nl_golden()
     if len(sys.argv) > 1 and sys.argv[1] == "saint_venant":
         return write_sv_golden()
     if len(sys.argv) > 1 and sys.argv[1] == "mooney":
