@@ -42,6 +42,8 @@
  *     (MooneyRivlinElasticity.hpp:25-47) through the reference's own autodiff.h inside GenericElastic's compute_energy_aux,
  *     compute_gradient_from_stress, compute_hessian_from_stress (GenericElastic.hpp:92-212, 268-351): oracle/_ref/libmrref.so,
  *     tests/golden/mr_local.npz, tests/test_oracle_mooney_reference.py, 1e-13.
+ *   - isoparametric (curved P2) geometry: det, jac_it, grad_t_m PINNED against the reference's own finalize3d on curved elements
+ *     (oracle/_ref/libgeomref.so::ref_finalize3d_iso, tests/golden/geom_iso.npz, P2 and P3 bases over P2 geometry, 1e-13).
  *   - project_to_psd (ipc-toolkit, source absent): UNPINNED, documented behaviour restated.
  *   - Mass (assembler/Mass.cpp:5-23): pinned by closed forms (P1 local mass rho*V/20*(1+delta_ij), total mass,
  *     stored zeros off the block diagonal; tests/test_oracle_mass.py) - the reference has no unit test for it.

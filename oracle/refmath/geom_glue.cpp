@@ -97,4 +97,47 @@ extern "C"
 		}
 		return 0;
 	}
+
+	// isoparametric geometry: n_geom geometric bases with nodes geom_nodes[n_geom][3] and reference gradients
+	// geom_grads[n_qp][n_geom][3] (e.g. the P2 basis of a curved tet) -> the same outputs
+	int ref_finalize3d_iso(int n_loc, int n_qp, int n_geom, const double *geom_nodes, const double *geom_grads, const double *ref_grads, double *det,
+						   double *jac_it, double *grad_t_m)
+	{
+		basis::ElementBases gbasis;
+		std::vector<assembler::AssemblyValues> gvals(n_geom);
+		gbasis.bases.resize(n_geom);
+		for (int j = 0; j < n_geom; ++j)
+		{
+			basis::Local2Global l2g{j, 1.0, Eigen::Dense(1, 3)};
+			for (int c = 0; c < 3; ++c)
+				l2g.node(0, c) = geom_nodes[j * 3 + c];
+			gbasis.bases[j].g = {l2g};
+			gvals[j].grad.resize(n_qp, 3);
+			for (int q = 0; q < n_qp; ++q)
+				for (int c = 0; c < 3; ++c)
+					gvals[j].grad(q, c) = geom_grads[(size_t(q) * n_geom + j) * 3 + c];
+		}
+		assembler::ElementAssemblyValues vals;
+		vals.val.resize(n_qp, 3);
+		vals.basis_values.resize(n_loc);
+		for (int i = 0; i < n_loc; ++i)
+		{
+			vals.basis_values[i].grad.resize(n_qp, 3);
+			for (int q = 0; q < n_qp; ++q)
+				for (int c = 0; c < 3; ++c)
+					vals.basis_values[i].grad(q, c) = ref_grads[(size_t(q) * n_loc + i) * 3 + c];
+		}
+		vals.finalize3d(gbasis, gvals);
+		for (int q = 0; q < n_qp; ++q)
+		{
+			det[q] = vals.det(q);
+			for (int r = 0; r < 3; ++r)
+				for (int c = 0; c < 3; ++c)
+					jac_it[size_t(q) * 9 + r * 3 + c] = vals.jac_it[q](r, c);
+			for (int i = 0; i < n_loc; ++i)
+				for (int c = 0; c < 3; ++c)
+					grad_t_m[(size_t(q) * n_loc + i) * 3 + c] = vals.basis_values[i].grad_t_m(q, c);
+		}
+		return 0;
+	}
 }

@@ -93,3 +93,24 @@ def test_curved_elements_are_not_affine_and_stay_consistent(oracle):
     assert np.abs(H @ d - gd).max() <= 1e-6 * np.abs(gd).max()
     fd = (prob.assemble_energy(x + eps * d) - prob.assemble_energy(x - eps * d)) / (2 * eps)
     assert abs(g @ d - fd) <= 1e-6 * max(abs(fd), np.abs(g).max() * 1e-3)
+
+
+def test_curved_geometry_equals_the_reference_finalize3d(oracle):
+    """tests/golden/geom_iso.npz: det, jac_it and grad_t_m of CURVED elements (isoparametric P2 geometry under P2 and P3 bases) as
+    returned by the reference's own ElementAssemblyValues::finalize3d (ElementAssemblyValues.cpp:65-104, compiled verbatim into
+    oracle/_ref/libgeomref.so; `tools/make_golden.py geom_iso`). 1e-13 of the largest entry."""
+    import os
+    gold = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "geom_iso.npz"))
+    lat2 = np.array(tables.P_NODES_LATTICE[2], dtype=np.int32)
+    for k in range(int(gold["n_cases"])):
+        p = int(gold[f"p_{k}"])
+        t = tables.reference_tables(p)
+        nl = t["grad"].shape[1]
+        prob = oracle.OracleProblem("NeoHookean", np.arange(nl, dtype=np.int32)[None, :], gold[f"vertices_{k}"][None], nl, t["points"], t["weights"],
+                                    t["grad"], lam=1.0, mu=1.0, basis_order=p, node_lattice=np.array(tables.P_NODES_LATTICE[p], dtype=np.int32),
+                                    geom_order=2, geom_lattice=lat2, geom_nodes=gold[f"geom_nodes_{k}"][None])
+        det, jit, gt = prob.assembly_values(0)
+        assert np.abs(det - gold[f"det_{k}"]).max() <= 1e-13 * np.abs(gold[f"det_{k}"]).max()
+        assert np.abs(jit - gold[f"jac_it_{k}"]).max() <= 1e-13 * np.abs(gold[f"jac_it_{k}"]).max()
+        assert np.abs(gt - gold[f"grad_t_m_{k}"]).max() <= 1e-13 * np.abs(gold[f"grad_t_m_{k}"]).max()
+        assert np.abs(jit - jit[:1]).max() > 1e-3 * np.abs(jit).max()  # the Jacobian really varies over the element

@@ -461,7 +461,45 @@ def write_le_nl_golden():
     print(f"wrote tests/golden/le_nl_local.npz ({k} cases)")
 
 
+def write_geom_iso_golden():
+    """tests/golden/geom_iso.npz: the reference's own ElementAssemblyValues::finalize3d (oracle/_ref/libgeomref.so) on CURVED
+    elements - isoparametric P2 geometry (10 geometric nodes, edge midpoints pushed off their edges) under P2 and P3 bases: det,
+    jac_it, grad_t_m per quadrature point."""
+    sys.path.insert(0, ROOT)
+    from polyfem_b200 import tables
+    geo = ctypes.CDLL(os.path.join(ROOT, "oracle", "_ref", "libgeomref.so"))
+    dp = ctypes.POINTER(ctypes.c_double)
+    geo.ref_finalize3d_iso.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, dp, dp, dp, dp, dp, dp]
+    rng = np.random.default_rng(101010)
+    gold = {}
+    k = 0
+    for p in (2, 3):
+        t = tables.reference_tables(p)
+        nq, nl = t["weights"].size, t["grad"].shape[1]
+        # geometric basis: P2 at the quadrature points of the order-p rule
+        tg = tables.reference_tables(2, tables.quadrature_order(p))
+        assert np.allclose(tg["points"], t["points"])
+        nodes2 = tables.p_nodes(2)
+        for rep in range(3):
+            verts = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0], [0, 0, 1]], dtype=np.float64)
+            verts = 0.3 * (verts + 0.25 * rng.uniform(-1, 1, (4, 3))) + rng.uniform(-1, 1, 3)
+            gnodes = verts[0] + nodes2 @ (verts[1:] - verts[0])
+            gnodes[4:] += 0.02 * rng.uniform(-1, 1, (6, 3))  # curved edges
+            det, jit, gt = np.zeros(nq), np.zeros((nq, 3, 3)), np.zeros((nq, nl, 3))
+            assert geo.ref_finalize3d_iso(nl, nq, 10, ptr(np.ascontiguousarray(gnodes)), ptr(np.ascontiguousarray(tg["grad"])),
+                                          ptr(np.ascontiguousarray(t["grad"])), ptr(det), ptr(jit), ptr(gt)) == 0
+            gold[f"p_{k}"] = p
+            gold[f"vertices_{k}"], gold[f"geom_nodes_{k}"] = verts, gnodes
+            gold[f"det_{k}"], gold[f"jac_it_{k}"], gold[f"grad_t_m_{k}"] = det, jit, gt
+            k += 1
+    gold["n_cases"] = k
+    np.savez_compressed(os.path.join(ROOT, "tests", "golden", "geom_iso.npz"), **gold)
+    print(f"wrote tests/golden/geom_iso.npz ({k} cases)")
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "geom_iso":
+        return write_geom_iso_golden()
     if len(sys.argv) > 1 and sys.argv[1] == "le_nl":
         return write_le_nl_golden()
     if len(sys.argv) > 1 and sys.argv[1] == "saint_venant":
