@@ -428,6 +428,13 @@ extern "C"
 		if (three_params && !d->param3)
 			return fail(nullptr, PFA_ERR_INVALID, "pfa_create: PFA_MOONEY_RIVLIN needs param3 (k) besides lambda (c1) and mu (c2)");
 
+		// owned_nodes is honoured by the owner-computes kernels only: any other path would hand back partial sums of the
+		// interface columns without saying so
+		if (d->owned_nodes != nullptr
+			&& (!column_lane2_applies(d->material, d->n_loc, d->n_qp) || !affine || (d->flags & PFA_FLAG_ROW_LANE) != 0
+				|| (d->n_ghost_elements > 0 && (d->flags & PFA_FLAG_GHOST_GEOMETRY) == 0)))
+			return fail(nullptr, PFA_ERR_UNSUPPORTED, "pfa_create: owned_nodes needs the owner-computes path (NeoHookean P1/P2 on affine tets, no PFA_FLAG_ROW_LANE, ghost elements with PFA_FLAG_GHOST_GEOMETRY)");
+
 		int n_dev = 0;
 		if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev <= 0)
 		{
@@ -732,6 +739,11 @@ extern "C"
 		}
 		else
 			UP(m.slot, hp.slot.data(), size_t(ne) * nl * nl, int32_t);
+		if (d->owned_nodes != nullptr && !h->cl.enabled)
+		{
+			h->err = "pfa_create: owned_nodes was given but the owner-computes path is off for this mesh (PFA_ROW_LANE=1 in the environment, or a node with 128 or more neighbours)";
+			return bail(PFA_ERR_UNSUPPORTED);
+		}
 		if (m.material != PFA_LAPLACIAN)
 		{
 			const size_t cnt = ngeo * size_t(m.mat_stride);

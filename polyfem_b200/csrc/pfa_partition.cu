@@ -6,6 +6,7 @@
 
 #include <algorithm>
 #include <cstdint>
+#include <memory>
 #include <new>
 #include <vector>
 
@@ -66,7 +67,7 @@ extern "C"
 				cut[size_t(r)] = std::max(cut[size_t(r)], cut[size_t(r) - 1]);
 			}
 			auto rank_of = [&](int32_t e) { return int32_t(std::upper_bound(cut.begin() + 1, cut.end(), e) - (cut.begin() + 1)); };
-			pfa_partition *p = new pfa_partition();
+			std::unique_ptr<pfa_partition> p(new pfa_partition()); // released only when everything below succeeded
 			const int32_t e0 = cut[size_t(rank)], e1 = cut[size_t(rank) + 1];
 			for (int32_t e = e0; e < e1; ++e)
 				p->elements.push_back(e);
@@ -104,7 +105,7 @@ extern "C"
 					p->conn[t * nl + j] = g2l[size_t(g)];
 				}
 			p->n_local = int32_t(p->l2g.size());
-			*out = p;
+			*out = p.release();
 			return PFA_OK;
 		}
 		catch (const std::bad_alloc &)

@@ -60,3 +60,21 @@ def test_product_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".h", ".hpp", ".cpp", ".cuh")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert "pyoracle" not in src and "liboracle" not in src and "oracle/" not in src.replace("oracle/_ref", ""), f
+
+
+def test_owned_nodes_is_refused_off_the_owner_computes_path():
+    """pfa_mesh_desc.owned_nodes only has a meaning for the owner-computes kernels (NeoHookean P1/P2, affine, no
+    PFA_FLAG_ROW_LANE): every other combination is refused before a device is touched, so the check runs here too."""
+    from polyfem_b200 import capi, mesh, tables
+    m = mesh.kuhn_cube(2, 1)
+    t = tables.reference_tables(1)
+    own = np.ones(m.n_bases, np.uint8)
+    for material, flags in (("LinearElasticity", 0), ("NeoHookean", capi.FLAG_ROW_LANE)):
+        with pytest.raises(capi.PfaError) as ei:
+            capi.Handle(material, m.conn, m.n_bases, t["weights"], t["grad"], vertices=m.vertices, lam=1.0, mu=1.0, owned_nodes=own, flags=flags)
+        assert ei.value.code == capi.PFA_ERR_UNSUPPORTED and "owned_nodes" in str(ei.value)
+    # ghost elements without geometry cannot serve owned columns
+    with pytest.raises(capi.PfaError) as ei:
+        capi.Handle("NeoHookean", np.vstack([m.conn, m.conn[:1]]), m.n_bases, t["weights"], t["grad"], vertices=m.vertices, lam=1.0, mu=1.0,
+                    owned_nodes=own, n_ghost_elements=1)
+    assert ei.value.code == capi.PFA_ERR_UNSUPPORTED
