@@ -69,9 +69,10 @@ namespace polyfem::assembler::b200
 			const int first_count = bases.empty() ? 0 : int(bases[0].bases.size());
 			if (h_ && key_ == bases.data() && n_elements_ == int(bases.size()) && n_basis_ == n_basis && first_global_ == first_global && first_count_ == first_count)
 			{
-				if (t != t_ || material_version_ != uploaded_version_)
-					refresh_materials(material, is_volume, bases, gbases, cache, lame, t);
-				return h_;
+				// (a refresh that changes the layout - parameters that were constant per element now vary inside an
+				// element, or the other way round - rebuilds the handle below)
+				if ((t == t_ && material_version_ == uploaded_version_) || refresh_materials(material, is_volume, bases, gbases, cache, lame, t))
+					return h_;
 			}
 			const_cast<DeviceAssembly *>(this)->reset();
 			if (!is_volume)
@@ -139,6 +140,11 @@ namespace polyfem::assembler::b200
 				}
 			}
 
+			// One (lambda, mu) per element when the parameters do not vary inside any element (the common case: constant or
+			// per-body materials): the library then takes its per-element paths (LinearElasticity / Laplacian: the
+			// reference-moment kernel instead of the quadrature loop)
+			const int mat_stride = compress_if_uniform(n_el, n_qp, lambda, mu, third);
+
 			pfa_mesh_desc d{};
 			d.struct_size = sizeof(pfa_mesh_desc);
 			d.material = material;
@@ -165,7 +171,7 @@ namespace polyfem::assembler::b200
 			}
 			if (!third.empty())
 				d.param3 = third.data();
-			d.material_stride = n_qp;
+			d.material_stride = mat_stride;
 			d.device = 0;
 #ifdef POLYSOLVE_LARGE_INDEX
 			d.flags |= PFA_FLAG_LARGE_INDEX;
@@ -178,14 +184,37 @@ namespace polyfem::assembler::b200
 			first_global_ = first_global;
 			first_count_ = first_count;
 			n_qp_ = n_qp;
+			mat_stride_ = mat_stride;
 			t_ = t;
 			uploaded_version_ = material_version_;
 			return h_;
 		}
 
+		/// [n_el][n_qp] parameter arrays -> [n_el] when every element carries one value per array; returns the stride (1 or n_qp)
+		static int compress_if_uniform(const int n_el, const int n_qp, std::vector<double> &p1, std::vector<double> &p2, std::vector<double> &p3)
+		{
+			if (n_qp == 1)
+				return 1;
+			for (std::vector<double> *a : {&p1, &p2, &p3})
+				for (size_t e = 0; e < a->size() / size_t(n_qp); ++e)
+					for (int q = 1; q < n_qp; ++q)
+						if ((*a)[e * n_qp + q] != (*a)[e * n_qp])
+							return n_qp;
+			for (std::vector<double> *a : {&p1, &p2, &p3})
+				if (!a->empty())
+				{
+					for (int e = 1; e < n_el; ++e)
+						(*a)[size_t(e)] = (*a)[size_t(e) * n_qp];
+					a->resize(size_t(n_el));
+				}
+			return 1;
+		}
+
 		/// lambda / mu (or the density) of every (element, quadrature point) again, for a new t or after a material change
+		/// Returns false when the new parameters need another layout than the handle was created with (then nothing is uploaded
+		/// and the caller rebuilds the handle).
 		template <typename LameFn>
-		void refresh_materials(const pfa_material material, const bool is_volume, const std::vector<basis::ElementBases> &bases,
+		bool refresh_materials(const pfa_material material, const bool is_volume, const std::vector<basis::ElementBases> &bases,
 							   const std::vector<basis::ElementBases> &gbases, const AssemblyValsCache &cache, const LameFn &lame, const double t) const
 		{
 			if (material != PFA_LAPLACIAN)
@@ -204,13 +233,16 @@ namespace polyfem::assembler::b200
 							third[size_t(e) * n_qp_ + q] = p3;
 					}
 				}
+				if (compress_if_uniform(n_el, n_qp_, lambda, mu, third) != mat_stride_)
+					return false;
 				if (!third.empty())
-					check(h_, pfa_set_material_params(h_, lambda.data(), mu.data(), third.data(), n_qp_));
+					check(h_, pfa_set_material_params(h_, lambda.data(), mu.data(), third.data(), mat_stride_));
 				else
-					check(h_, pfa_set_materials(h_, lambda.data(), material == PFA_MASS ? nullptr : mu.data(), n_qp_));
+					check(h_, pfa_set_materials(h_, lambda.data(), material == PFA_MASS ? nullptr : mu.data(), mat_stride_));
 			}
 			t_ = t;
 			uploaded_version_ = material_version_;
+			return true;
 		}
 
 		/// Wraps values[] in the reference's matrix type (pattern identical to SparseMatrixCache's). With POLYSOLVE_LARGE_INDEX
@@ -245,7 +277,7 @@ namespace polyfem::assembler::b200
 	private:
 		mutable pfa_handle *h_ = nullptr;
 		mutable const void *key_ = nullptr;
-		mutable int n_elements_ = 0, n_basis_ = 0, first_global_ = -1, first_count_ = 0, n_qp_ = 0;
+		mutable int n_elements_ = 0, n_basis_ = 0, first_global_ = -1, first_count_ = 0, n_qp_ = 0, mat_stride_ = 1;
 		mutable double t_ = 0;
 		mutable unsigned material_version_ = 0, uploaded_version_ = 0;
 	};

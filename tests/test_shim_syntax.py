@@ -67,3 +67,42 @@ def test_shim_compiles_against_reference_signatures(tmp_path):
            "-I", os.path.join(ROOT, "tests", "stubs"), str(src)]
     r = subprocess.run(cmd, capture_output=True, text=True)
     assert r.returncode == 0, r.stderr[-4000:]
+
+
+RUNTIME_TU = r"""
+#include <assembler_shim.hpp>
+#include <cstdio>
+using polyfem::assembler::b200::DeviceAssembly;
+int main()
+{
+	// one value per element in every array: [n_el][n_qp] -> [n_el], stride 1
+	std::vector<double> a = {1, 1, 1, 1, 2, 2, 2, 2, 3, 3, 3, 3}, b = {5, 5, 5, 5, 6, 6, 6, 6, 7, 7, 7, 7}, c;
+	if (DeviceAssembly::compress_if_uniform(3, 4, a, b, c) != 1 || a != std::vector<double>{1, 2, 3} || b != std::vector<double>{5, 6, 7} || !c.empty())
+		return 1;
+	// one element varies inside: everything stays per quadrature point
+	std::vector<double> d = {1, 1, 1, 1, 2, 2, 2.5, 2}, e = {5, 5, 5, 5, 6, 6, 6, 6}, f = e;
+	if (DeviceAssembly::compress_if_uniform(2, 4, d, e, f) != 4 || d.size() != 8 || e.size() != 8 || f.size() != 8)
+		return 2;
+	std::vector<double> g = {1, 2}, h = {3, 4}, k;
+	if (DeviceAssembly::compress_if_uniform(2, 1, g, h, k) != 1 || g.size() != 2)
+		return 3;
+	std::puts("ok");
+	return 0;
+}
+"""
+
+
+def test_shim_material_layout_helper_runs(tmp_path):
+    """The one piece of host logic in the shim that does not need PolyFEM: per-element parameters are detected and sent with
+    material_stride 1 (the library's per-element kernels), per-quadrature-point ones with stride n_qp."""
+    gxx = shutil.which("g++")
+    libdir = os.path.join(ROOT, "polyfem_b200")
+    if gxx is None or not os.path.exists(os.path.join(libdir, "libpfa.so")):
+        pytest.skip("g++ or libpfa.so not available")
+    src = tmp_path / "shim_rt.cpp"
+    src.write_text(RUNTIME_TU)
+    exe = str(tmp_path / "shim_rt")
+    subprocess.run([gxx, "-std=c++17", "-O1", "-I", os.path.join(ROOT, "include"), "-I", os.path.join(ROOT, "polyfem_b200", "host"),
+                    "-I", os.path.join(ROOT, "tests", "stubs"), str(src), "-o", exe, "-L", libdir, "-lpfa", "-Wl,-rpath," + libdir], check=True)
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=60)
+    assert r.returncode == 0 and "ok" in r.stdout, (r.returncode, r.stdout, r.stderr)
