@@ -140,10 +140,25 @@ namespace pfa
 			return ok != 0;
 		}
 		// global -> shared bulk copy (TMA), bytes a multiple of 16, both addresses 16-byte aligned; completion = complete_tx on the mbarrier
-		__device__ __forceinline__ void tma_load(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar)
+		[[maybe_unused]] __device__ __forceinline__ void tma_load(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar)
 		{
 			asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
 						 : "memory");
+		}
+
+		// the same, predicated (no branch around the copy)
+		[[maybe_unused]] __device__ __forceinline__ void tma_load_if(bool pred, uint32_t dst, const void *src, uint32_t bytes, uint32_t bar)
+		{
+			asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %4, 0;\n\t@p cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n\t}" ::"r"(dst),
+						 "l"(src), "r"(bytes), "r"(bar), "r"(uint32_t(pred))
+						 : "memory");
+		}
+		// true in exactly one (the lowest active) lane of the warp
+		[[maybe_unused]] __device__ __forceinline__ bool elect_one()
+		{
+			uint32_t e;
+			asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(e));
+			return e != 0;
 		}
 
 		// Ampere-style asynchronous copy (LDGSTS): 16 bytes global -> shared without a register round trip; L2 only (.cg)
@@ -159,6 +174,9 @@ namespace pfa
 		// on an mbarrier) and cp.async (16 bytes per lane and instruction) are equally fast for the 432-byte P2 records
 		// (5.03 / 5.07 ms at cfg 3); for the 144-byte P1 records cp.async wins (0.224 / 0.263 ms at cfg 2). PFA_CL2_TMA
 		// overrides the per-element-type choice (experiments).
+#ifndef PFA_CL2_TMA_ELECT
+#define PFA_CL2_TMA_ELECT 1 // 1: one elected lane issues all TMA copies of a step (see issue()); 0: every triple leader issues its own
+#endif
 #ifdef PFA_CL2_TMA
 		template <int NQ>
 		constexpr bool kUseTma = PFA_CL2_TMA != 0;
@@ -250,9 +268,32 @@ namespace pfa
 			auto issue = [&](const uint4 &w, int buf, bool real) {
 				if constexpr (TMA)
 				{
-					// one TMA copy per busy triple; lane 0 arms the barrier with the byte count first
 					if (!real)
 						return;
+#if PFA_CL2_TMA_ELECT
+					// Every lane learns the ten elements of the step by shuffles from the triple leaders (constant source lanes: the
+					// results are warp-uniform, the compiler keeps them in uniform registers), then ONE elected lane arms the barrier
+					// and issues the up to ten copies back to back. (When each leader issues its own copy the compiler has to
+					// serialise the leaders in a loop - ELECT, three R2UR.BROADCAST, UBLKCP, BRA.U.ANY, about 58 cycles per copy in
+					// the ncu source view of the edge launch at cfg 3, profiles/cl2_r02al_phases_edge.txt - because UBLKCP takes its
+					// operands from uniform registers.) Measured at cfg 3: 4.881 -> 4.796 ms (profiles/clvar_r02am.jsonl). The P1 kernel
+					// keeps cp.async: TMA with the elected issue is 0.224 against 0.203 ms at cfg 2 (same file).
+					const unsigned mask = __ballot_sync(kFull, leader && w.x != kIdle);
+					uint32_t el[kTriples];
+#pragma unroll
+					for (int k = 0; k < kTriples; ++k)
+						el[k] = __shfl_sync(kFull, w.x, (k / kNodes) * 16 + (k % kNodes) * 3);
+					if (elect_one())
+					{
+						const uint32_t bar = bar0 + 8 * buf;
+						mbar_arrive_expect_tx(bar, uint32_t(__popc(mask)) * REC_BYTES);
+#pragma unroll
+						for (int k = 0; k < kTriples; ++k)
+							tma_load_if(el[k] != kIdle, stage_u32 + uint32_t(buf * L::STAGE + k * L::SSTR) * 8u, t.records + size_t(el[k]) * RECD, REC_BYTES, bar); // (address unused when idle)
+					}
+					return;
+#else
+					// one TMA copy per busy triple; lane 0 arms the barrier with the byte count first
 					const bool want = leader && w.x != kIdle;
 					const unsigned mask = __ballot_sync(kFull, want);
 					const uint32_t bar = bar0 + 8 * buf;
@@ -261,6 +302,7 @@ namespace pfa
 					__syncwarp();
 					if (want)
 						tma_load(stage_u32 + uint32_t(buf * L::STAGE + tr * L::SSTR) * 8u, t.records + size_t(w.x) * RECD, REC_BYTES, bar);
+#endif
 				}
 				else
 				{
@@ -427,7 +469,9 @@ namespace pfa
 						}
 						for (int r0 = 0; r0 < rows_g; r0 += kFlushRows)
 						{
-							// rows past the group's last row are never stored; rows past the allocation are not read
+							// rows past the group's last row are never stored; rows past the allocation are not read. (Loading the strip
+							// rows of the next block before the stores of this one, and the B-lane update in one batch of 30 instead of
+							// two of 15, were measured together: +0.7 %, profiles/clvar_r02am.jsonl.)
 							double v[16];
 #pragma unroll
 							for (int i = 0; i < 16; ++i)
