@@ -616,7 +616,9 @@ namespace pfa
 		// entry step: vertex-weighted sums when the table is the P2 basis on the symmetric 4-point rule (p2_rule_weights),
 		// else the structural zeros of the P2 reference gradients (DeviceMesh::p2_structured), else the plain table
 		static const bool no_z = [] { const char *v = std::getenv("PFA_CL_NO_P2Z"); return v && std::atoi(v) != 0; }(); // experiments
-		static const bool stream_z = [] { const char *v = std::getenv("PFA_CL_P2Y"); return v && std::atoi(v) != 0; }();     // experiments
+		// streamed form of the vertex-weighted step (MODE 3: 27 instead of 81 live doubles) is the default since the elected TMA issue:
+		// 4.737 against 4.802 ms at cfg 3 (profiles/clvar_r02ap.jsonl); PFA_CL_P2Y=0 selects the held form (MODE 2)
+		static const bool stream_z = [] { const char *v = std::getenv("PFA_CL_P2Y"); return v == nullptr || std::atoi(v) != 0; }();
 		if (t.p2z && !no_z)
 			return stream_z ? launch_cl2<10, 4, 1, 3>(m, a, t, sm_count, st, launches) : launch_cl2<10, 4, 1, 2>(m, a, t, sm_count, st, launches);
 		return m.p2_structured ? launch_cl2<10, 4, 1, 1>(m, a, t, sm_count, st, launches) : launch_cl2<10, 4, 1, 0>(m, a, t, sm_count, st, launches);
