@@ -183,6 +183,18 @@ extern "C"
 	const int32_t *pfa_partition_local_to_global(const pfa_partition *p);      /* [n_local_bases] caller's node id of each local node */
 	const uint8_t *pfa_partition_owned(const pfa_partition *p);    /* [n_local_bases] 1 = owned by this rank */
 	void pfa_partition_destroy(pfa_partition *p);
+	/* Host only, no device needed: the sparsity pattern pfa_create derives from a connectivity (it replaces the first-call path of
+	 * SparseMatrixCache, utils/MatrixCache.cpp:88-213), in node-block form - adj_off[n_bases + 1], adj[n_pairs] as pfa_block_pattern
+	 * describes them - and the slot map slot[e][i][j] = index into adj of (row node conn[e][i]) in the column list of node
+	 * conn[e][j]. For a symbolic factorisation that starts before a GPU is attached, and for checking the pattern builder on a
+	 * machine without one. The arrays are owned by the object. */
+	typedef struct pfa_host_pattern pfa_host_pattern;
+	int pfa_host_pattern_create(int32_t n_elements, int32_t n_loc, int32_t n_bases, const int32_t *conn, pfa_host_pattern **out);
+	int pfa_host_pattern_arrays(const pfa_host_pattern *p, int64_t *n_pairs, const int32_t **adj_off, const int32_t **adj, const int32_t **slot);
+	void pfa_host_pattern_destroy(pfa_host_pattern *p);
+	/* Host only: the internal element order pfa_create uses for affine meshes without PFA_FLAG_KEEP_ELEMENT_ORDER (space-filling
+	 * curve over the element centroids; vertices[e][4][3]): perm[k] = caller's index of the k-th internal element. */
+	int pfa_host_element_order(int32_t n_elements, const double *vertices, int32_t *perm);
 	void pfa_destroy(pfa_handle *h);
 	/* message of the last failing call on this handle (or of pfa_create when h == NULL) */
 	const char *pfa_last_error(const pfa_handle *h);

@@ -36,6 +36,7 @@ EXPORTS = [
     "pfa_symv", "pfa_inertia", "pfa_axpy",
     "pfa_partition_create", "pfa_partition_sizes", "pfa_partition_elements", "pfa_partition_conn", "pfa_partition_local_to_global",
     "pfa_partition_owned", "pfa_partition_destroy",
+    "pfa_host_pattern_create", "pfa_host_pattern_arrays", "pfa_host_pattern_destroy", "pfa_host_element_order",
 ]
 
 
@@ -484,3 +485,40 @@ def partition(conn, n_bases, world, rank):
     finally:
         L.pfa_partition_destroy(p)
     return out
+
+
+def host_pattern(conn, n_bases):
+    """pfa_host_pattern_create (include/pfa.h): the pattern builder of pfa_create without a device. Returns (adj_off[n_bases + 1],
+    adj[n_pairs], slot[n_el, n_loc, n_loc]) as int32 arrays."""
+    L = lib()
+    conn = np.ascontiguousarray(conn, dtype=np.int32)
+    ne, nl = conn.shape
+    p = ctypes.c_void_p()
+    L.pfa_host_pattern_create.argtypes = [ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, _ip, ctypes.POINTER(ctypes.c_void_p)]
+    rc = L.pfa_host_pattern_create(ne, nl, int(n_bases), conn.ctypes.data_as(_ip), ctypes.byref(p))
+    if rc != PFA_OK:
+        raise PfaError(rc, "pfa_host_pattern_create failed")
+    try:
+        n = ctypes.c_int64()
+        po, pa, ps = _ip(), _ip(), _ip()
+        L.pfa_host_pattern_arrays.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_int64), ctypes.POINTER(_ip), ctypes.POINTER(_ip), ctypes.POINTER(_ip)]
+        L.pfa_host_pattern_arrays(p, ctypes.byref(n), ctypes.byref(po), ctypes.byref(pa), ctypes.byref(ps))
+        out = (np.ctypeslib.as_array(po, shape=(int(n_bases) + 1,)).copy(), np.ctypeslib.as_array(pa, shape=(n.value,)).copy(),
+               np.ctypeslib.as_array(ps, shape=(ne, nl, nl)).copy())
+    finally:
+        L.pfa_host_pattern_destroy.argtypes = [ctypes.c_void_p]
+        L.pfa_host_pattern_destroy(p)
+    return out
+
+
+def host_element_order(vertices):
+    """pfa_host_element_order: perm[k] = caller's index of the k-th element of the internal (space-filling curve) order."""
+    L = lib()
+    v = np.ascontiguousarray(vertices, dtype=np.float64).reshape(-1, 4, 3)
+    perm = np.empty(v.shape[0], dtype=np.int32)
+    L.pfa_host_element_order.argtypes = [ctypes.c_int32, _dp, _ip]
+    rc = L.pfa_host_element_order(v.shape[0], v.ctypes.data_as(_dp), perm.ctypes.data_as(_ip))
+    if rc != PFA_OK:
+        raise PfaError(rc, "pfa_host_element_order failed")
+    return perm
+

@@ -11,6 +11,7 @@
 #include "pfa_internal.h"
 
 #include <algorithm>
+#include <new>
 #include <stdexcept>
 #include <thread>
 
@@ -240,3 +241,72 @@ namespace pfa
 		}
 	}
 } // namespace pfa
+
+// ---- host-only entry points of include/pfa.h: the pattern builder and the element order without a device ----
+struct pfa_host_pattern
+{
+	pfa::HostPattern hp;
+};
+
+extern "C"
+{
+	int pfa_host_pattern_create(int32_t n_elements, int32_t n_loc, int32_t n_bases, const int32_t *conn, pfa_host_pattern **out)
+	{
+		if (!conn || !out || n_elements <= 0 || n_loc <= 0 || n_bases <= 0)
+			return PFA_ERR_INVALID;
+		*out = nullptr;
+		pfa_host_pattern *p = new (std::nothrow) pfa_host_pattern();
+		if (!p)
+			return PFA_ERR_NOMEM;
+		try
+		{
+			pfa::build_pattern(conn, n_elements, n_loc, n_bases, p->hp);
+		}
+		catch (const std::bad_alloc &)
+		{
+			delete p;
+			return PFA_ERR_NOMEM;
+		}
+		catch (const std::exception &)
+		{
+			delete p;
+			return PFA_ERR_INVALID; // connectivity index out of range, or more than 2^31 node pairs
+		}
+		*out = p;
+		return PFA_OK;
+	}
+
+	int pfa_host_pattern_arrays(const pfa_host_pattern *p, int64_t *n_pairs, const int32_t **adj_off, const int32_t **adj, const int32_t **slot)
+	{
+		if (!p)
+			return PFA_ERR_INVALID;
+		if (n_pairs)
+			*n_pairs = int64_t(p->hp.adj.size());
+		if (adj_off)
+			*adj_off = p->hp.adj_off.data();
+		if (adj)
+			*adj = p->hp.adj.data();
+		if (slot)
+			*slot = p->hp.slot.data();
+		return PFA_OK;
+	}
+
+	void pfa_host_pattern_destroy(pfa_host_pattern *p) { delete p; }
+
+	int pfa_host_element_order(int32_t n_elements, const double *vertices, int32_t *perm)
+	{
+		if (!vertices || !perm || n_elements <= 0)
+			return PFA_ERR_INVALID;
+		try
+		{
+			std::vector<int32_t> order;
+			pfa::spatial_element_order(vertices, n_elements, order);
+			std::copy(order.begin(), order.end(), perm);
+		}
+		catch (const std::bad_alloc &)
+		{
+			return PFA_ERR_NOMEM;
+		}
+		return PFA_OK;
+	}
+}
