@@ -19,16 +19,24 @@ from polyfem_b200 import mesh as M, tables
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-@pytest.fixture(scope="module")
-def emul(tmp_path_factory):
-    out = str(tmp_path_factory.mktemp("collane") / "libcollane2_emul.so")
+def build_emul(out):
+    """compiles tests/collane2_emul.cpp (the kernels' own header on the CPU) into the shared library `out`"""
     subprocess.run(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-ffp-contract=off", os.path.join(ROOT, "tests", "collane2_emul.cpp"), "-o", out],
                    check=True)
-    lib = ctypes.CDLL(out)
+    return out
+
+
+def load_emul(path):
+    lib = ctypes.CDLL(path)
     dp, ip = ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_int32)
     lib.collane2_emulate.argtypes = [ctypes.c_int] * 4 + [ip, ip, ip, dp, dp, dp, dp, dp, dp, ctypes.c_int, dp, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                      ctypes.POINTER(ctypes.c_uint8), ctypes.c_double, dp, dp, dp, ctypes.POINTER(ctypes.c_int64)]
     return lib
+
+
+@pytest.fixture(scope="module")
+def emul(tmp_path_factory):
+    return load_emul(build_emul(str(tmp_path_factory.mktemp("collane") / "libcollane2_emul.so")))
 
 
 def node_adjacency(mesh):
