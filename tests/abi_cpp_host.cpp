@@ -56,6 +56,24 @@ int main(int argc, char **argv)
 	}
 	if (owned_total != 8)
 		return std::printf("every node must be owned exactly once\n"), 3;
+	// ---- sparsity pattern without a device: in one Kuhn cell the diagonal 0 - 7 touches every node, the other pairs as the tets list them
+	{
+		pfa_host_pattern *hp = nullptr;
+		if (pfa_host_pattern_create(6, 4, 8, conn.data(), &hp) != PFA_OK)
+			return std::printf("pfa_host_pattern_create failed\n"), 10;
+		int64_t n_pairs = 0;
+		const int32_t *adj_off, *adj, *slot;
+		pfa_host_pattern_arrays(hp, &n_pairs, &adj_off, &adj, &slot);
+		bool ok = adj_off[1] - adj_off[0] == 8 && adj_off[8] - adj_off[7] == 8 && adj_off[8] == n_pairs;
+		for (int e = 0; e < 6 && ok; ++e)
+			for (int i = 0; i < 4; ++i)
+				for (int j = 0; j < 4; ++j)
+					ok = ok && adj[slot[(e * 4 + i) * 4 + j]] == conn[e * 4 + i];
+		std::printf("host pattern: %lld node pairs\n", (long long)n_pairs);
+		pfa_host_pattern_destroy(hp);
+		if (!ok)
+			return std::printf("host pattern: wrong adjacency or slot map\n"), 11;
+	}
 	if (!assemble)
 	{
 		for (auto *p : parts)

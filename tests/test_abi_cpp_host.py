@@ -25,6 +25,8 @@ def test_cpp_host_partition(tmp_path):
     out = subprocess.run([exe, "partition"], capture_output=True, text=True, timeout=120)
     assert out.returncode == 0, out.stdout + out.stderr
     assert "rank 1" in out.stdout
+    # one Kuhn cell: nodes 0 and 7 see all 8 nodes, the six others 0, 7, themselves and their two tet neighbours... = 2*8 + 6*5 pairs
+    assert "host pattern: 46 node pairs" in out.stdout
 
 
 @pytest.mark.gpu
