@@ -29,6 +29,7 @@
 #ifndef PFA_H
 #define PFA_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -294,6 +295,13 @@ extern "C"
 	/* y[k] += a * x[k], k < n: e.g. Hessian of the time-stepping problem = dt^2-weighted elastic values
 	 * + mass values (same pattern when both handles come from the same connectivity) */
 	int pfa_axpy(pfa_handle *h, int64_t n, double a, const double *x, double *y);
+
+	/* Page-locked host memory for the host-pointer mode: the device-to-host copy of values[] (5.5 GB at BASELINE cfg 3) runs at
+	 * the PCIe rate only into pinned memory; ordinary (pageable) buffers work too, at a fraction of it. pfa_host_alloc returns
+	 * NULL when there is no device or not enough lockable memory - the caller then falls back to ordinary memory (the shim's
+	 * HostValues does). Free with pfa_host_free only. */
+	void *pfa_host_alloc(size_t bytes);
+	void pfa_host_free(void *p);
 
 	/* waits for all work enqueued on the handle's stream */
 	int pfa_synchronize(pfa_handle *h);

@@ -37,6 +37,7 @@ EXPORTS = [
     "pfa_partition_create", "pfa_partition_sizes", "pfa_partition_elements", "pfa_partition_conn", "pfa_partition_local_to_global",
     "pfa_partition_owned", "pfa_partition_destroy",
     "pfa_host_pattern_create", "pfa_host_pattern_arrays", "pfa_host_pattern_destroy", "pfa_host_element_order",
+    "pfa_host_alloc", "pfa_host_free",
 ]
 
 

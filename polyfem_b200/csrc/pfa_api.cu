@@ -1419,6 +1419,25 @@ extern "C"
 		return run_assemble(h, false, x, project_to_psd, energy, nullptr, grad_reduced, values_reduced, scale, true);
 	}
 
+	void *pfa_host_alloc(size_t bytes)
+	{
+		void *p = nullptr;
+		if (bytes == 0)
+			return nullptr;
+		if (cudaHostAlloc(&p, bytes, cudaHostAllocPortable) != cudaSuccess)
+		{
+			cudaGetLastError(); // no device / not enough lockable memory: the caller falls back to ordinary memory
+			return nullptr;
+		}
+		return p;
+	}
+
+	void pfa_host_free(void *p)
+	{
+		if (p)
+			cudaFreeHost(p);
+	}
+
 	int pfa_synchronize(pfa_handle *h)
 	{
 		if (!h)

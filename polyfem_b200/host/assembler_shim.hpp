@@ -32,12 +32,68 @@
 
 namespace polyfem::assembler::b200
 {
+	/// values[] buffer of the host-pointer calls, page-locked when the driver grants it (pfa_host_alloc): the device-to-host copy
+	/// of the matrix values reaches the PCIe rate only into pinned memory. Falls back to ordinary memory. Copies start empty.
+	class HostValues
+	{
+	public:
+		HostValues() = default;
+		HostValues(const HostValues &) {}
+		HostValues &operator=(const HostValues &)
+		{
+			release();
+			return *this;
+		}
+		~HostValues() { release(); }
+
+		double *resize(const size_t n)
+		{
+			if (n > cap_)
+			{
+				release();
+				p_ = static_cast<double *>(pfa_host_alloc(n * sizeof(double)));
+				pinned_ = p_ != nullptr;
+				if (!pinned_)
+				{
+					fallback_.resize(n);
+					p_ = fallback_.data();
+				}
+				cap_ = n;
+			}
+			return p_;
+		}
+		const double *data() const { return p_; }
+
+	private:
+		void release()
+		{
+			if (pinned_)
+				pfa_host_free(p_);
+			std::vector<double>().swap(fallback_);
+			p_ = nullptr;
+			cap_ = 0;
+			pinned_ = false;
+		}
+		double *p_ = nullptr;
+		size_t cap_ = 0;
+		bool pinned_ = false;
+		std::vector<double> fallback_;
+	};
+
 	/// Owns one pfa_handle; rebuilt when the FE space (bases pointer / size) changes.
 	/// The reference's methods are const and called from one host thread, so the
 	/// device state is `mutable` in the assemblers below.
 	class DeviceAssembly
 	{
 	public:
+		DeviceAssembly() = default;
+		// a copied assembler starts without device state (its handle is built on its first assemble_* call)
+		DeviceAssembly(const DeviceAssembly &) {}
+		DeviceAssembly &operator=(const DeviceAssembly &)
+		{
+			reset();
+			return *this;
+		}
 		~DeviceAssembly() { reset(); }
 
 		void reset()
@@ -248,7 +304,7 @@ namespace polyfem::assembler::b200
 		/// Wraps values[] in the reference's matrix type (pattern identical to SparseMatrixCache's). With POLYSOLVE_LARGE_INDEX
 		/// (utils/Types.hpp:21-25) StiffnessMatrix stores std::ptrdiff_t indices: the handle is then created with
 		/// PFA_FLAG_LARGE_INDEX and hands out the int64 pattern.
-		static void to_eigen(pfa_handle *h, const std::vector<double> &values, StiffnessMatrix &out)
+		static void to_eigen(pfa_handle *h, const double *values, StiffnessMatrix &out)
 		{
 			int32_t size;
 			int64_t ndof, nnz;
@@ -257,12 +313,12 @@ namespace polyfem::assembler::b200
 			const int64_t *outer, *inner;
 			if (pfa_pattern_wide(h, &nnz, &outer, &inner) != PFA_OK)
 				log_and_throw_error("B200 assembly path: {}", pfa_last_error(h));
-			out = Eigen::Map<const StiffnessMatrix>(ndof, ndof, nnz, reinterpret_cast<const std::ptrdiff_t *>(outer), reinterpret_cast<const std::ptrdiff_t *>(inner), values.data());
+			out = Eigen::Map<const StiffnessMatrix>(ndof, ndof, nnz, reinterpret_cast<const std::ptrdiff_t *>(outer), reinterpret_cast<const std::ptrdiff_t *>(inner), values);
 #else
 			const int32_t *outer, *inner;
 			if (pfa_pattern(h, &nnz, &outer, &inner) != PFA_OK)
 				log_and_throw_error("B200 assembly path: {}", pfa_last_error(h));
-			out = Eigen::Map<const StiffnessMatrix>(ndof, ndof, nnz, outer, inner, values.data());
+			out = Eigen::Map<const StiffnessMatrix>(ndof, ndof, nnz, outer, inner, values);
 #endif
 		}
 
@@ -343,9 +399,9 @@ namespace polyfem::assembler::b200
 			before_call(h, dt, displacement, displacement_prev);
 			int64_t nnz;
 			pfa_sizes(h, nullptr, nullptr, &nnz);
-			values_.resize(nnz);
-			DeviceAssembly::check(h, pfa_hessian(h, displacement.data(), project_to_psd ? 1 : 0, values_.data()));
-			DeviceAssembly::to_eigen(h, values_, hess);
+			double *values = values_.resize(size_t(nnz));
+			DeviceAssembly::check(h, pfa_hessian(h, displacement.data(), project_to_psd ? 1 : 0, values));
+			DeviceAssembly::to_eigen(h, values, hess);
 			// mat_cache is caller-owned scratch (ElasticForm.hpp:116); it is left untouched and valid.
 		}
 
@@ -376,7 +432,7 @@ namespace polyfem::assembler::b200
 							[&](const ElementAssemblyValues &vals, const int q, double &p1, double &p2, double &p3) { material_params(vals, q, t, p1, p2, p3); });
 		}
 		DeviceAssembly dev_;
-		mutable std::vector<double> values_;
+		mutable HostValues values_;
 	};
 
 	/// Drop-in for NeoHookeanElasticity ("NeoHookean" in AssemblerUtils::make_assembler).
@@ -480,14 +536,14 @@ namespace polyfem::assembler::b200
 									 [](const ElementAssemblyValues &, const int, double &lambda, double &mu, double &) { lambda = mu = 0; });
 			int64_t nnz;
 			pfa_sizes(h, nullptr, nullptr, &nnz);
-			values_.resize(nnz);
-			DeviceAssembly::check(h, pfa_linear_stiffness(h, values_.data()));
-			DeviceAssembly::to_eigen(h, values_, stiffness);
+			double *values = values_.resize(size_t(nnz));
+			DeviceAssembly::check(h, pfa_linear_stiffness(h, values));
+			DeviceAssembly::to_eigen(h, values, stiffness);
 		}
 
 	private:
 		DeviceAssembly dev_;
-		mutable std::vector<double> values_;
+		mutable HostValues values_;
 	};
 
 	/// Drop-in for Mass ("Mass"): the matrix InertiaForm is built with (State::build_mass_matrix /
@@ -508,14 +564,14 @@ namespace polyfem::assembler::b200
 									 });
 			int64_t nnz;
 			pfa_sizes(h, nullptr, nullptr, &nnz);
-			values_.resize(nnz);
-			DeviceAssembly::check(h, pfa_linear_stiffness(h, values_.data()));
-			DeviceAssembly::to_eigen(h, values_, stiffness);
+			double *values = values_.resize(size_t(nnz));
+			DeviceAssembly::check(h, pfa_linear_stiffness(h, values));
+			DeviceAssembly::to_eigen(h, values, stiffness);
 		}
 
 	private:
 		DeviceAssembly dev_;
-		mutable std::vector<double> values_;
+		mutable HostValues values_;
 	};
 
 	/// Optional: the Newton system of NLProblem straight from the device (fourth edit).
@@ -567,9 +623,9 @@ namespace polyfem::assembler::b200
 			pfa_handle *h = handle(is_volume, n_basis, bases, gbases, cache, t);
 			int64_t nnz;
 			pfa_sizes(h, nullptr, nullptr, &nnz);
-			values_.resize(nnz);
-			DeviceAssembly::check(h, pfa_linear_stiffness(h, values_.data()));
-			DeviceAssembly::to_eigen(h, values_, stiffness);
+			double *values = values_.resize(size_t(nnz));
+			DeviceAssembly::check(h, pfa_linear_stiffness(h, values));
+			DeviceAssembly::to_eigen(h, values, stiffness);
 		}
 
 		double assemble_energy(const bool is_volume, const std::vector<basis::ElementBases> &bases,
@@ -603,6 +659,6 @@ namespace polyfem::assembler::b200
 							});
 		}
 		DeviceAssembly dev_;
-		mutable std::vector<double> values_;
+		mutable HostValues values_;
 	};
 } // namespace polyfem::assembler::b200

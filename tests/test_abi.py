@@ -78,3 +78,24 @@ def test_owned_nodes_is_refused_off_the_owner_computes_path():
         capi.Handle("NeoHookean", np.vstack([m.conn, m.conn[:1]]), m.n_bases, t["weights"], t["grad"], vertices=m.vertices, lam=1.0, mu=1.0,
                     owned_nodes=own, n_ghost_elements=1)
     assert ei.value.code == capi.PFA_ERR_UNSUPPORTED
+
+
+def test_pinned_host_allocation_fails_softly_without_a_device():
+    """pfa_host_alloc returns NULL when no device can pin memory (the shim's HostValues then uses ordinary memory);
+    pfa_host_free(NULL) is a no-op."""
+    import torch
+    from polyfem_b200 import capi
+    L = capi.lib()
+    L.pfa_host_alloc.restype = ctypes.c_void_p
+    L.pfa_host_alloc.argtypes = [ctypes.c_size_t]
+    L.pfa_host_free.argtypes = [ctypes.c_void_p]
+    L.pfa_host_free(None)
+    assert L.pfa_host_alloc(0) is None
+    p = L.pfa_host_alloc(1 << 20)
+    if torch.cuda.is_available():
+        assert p is not None
+        ctypes.memset(p, 0, 1 << 20)
+        L.pfa_host_free(p)
+    else:
+        assert p is None
+

@@ -86,6 +86,26 @@ int main()
 	std::vector<double> g = {1, 2}, h = {3, 4}, k;
 	if (DeviceAssembly::compress_if_uniform(2, 1, g, h, k) != 1 || g.size() != 2)
 		return 3;
+	// values[] buffer: pinned when a device grants it, ordinary memory otherwise (here); grows, keeps its pointer while it fits,
+	// and a copy starts empty instead of sharing (or double-freeing) the allocation
+	polyfem::assembler::b200::HostValues hv;
+	double *q = hv.resize(10);
+	if (!q || hv.data() != q)
+		return 4;
+	for (int i = 0; i < 10; ++i)
+		q[i] = i;
+	if (hv.resize(5) != q)
+		return 5;
+	double *q2 = hv.resize(1000);
+	if (!q2)
+		return 6;
+	q2[999] = 1.0;
+	polyfem::assembler::b200::HostValues copy(hv);
+	if (copy.data() != nullptr)
+		return 7;
+	copy = hv;
+	if (copy.data() != nullptr || copy.resize(3) == nullptr)
+		return 8;
 	std::puts("ok");
 	return 0;
 }
